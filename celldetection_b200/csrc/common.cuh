@@ -1,0 +1,81 @@
+// Shared helpers for the cpn_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include "../../include/cpn_b200.h"
+
+namespace cpn {
+
+// Thread-local error string + global launch counter (cpn_last_error / cpn_launch_count).
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define CPN_CHECK_CUDA(expr)                                                                        \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      cpn::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));   \
+      return 1;                                                                                     \
+    }                                                                                               \
+  } while (0)
+
+#define CPN_REQUIRE(cond, ...)       \
+  do {                               \
+    if (!(cond)) {                   \
+      cpn::set_error(__VA_ARGS__);   \
+      return 1;                      \
+    }                                \
+  } while (0)
+
+#define CPN_CHECK_LAUNCH()                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess) {                                                                 \
+      cpn::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,                  \
+                     cudaGetErrorString(_e));                                                \
+      return 1;                                                                              \
+    }                                                                                        \
+    cpn::count_launch();                                                                     \
+  } while (0)
+
+inline int dtype_size(int dt) { return dt == CPN_DT_F32 ? 4 : (dt == CPN_DT_F16 ? 2 : 1); }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int sm_count();  // cached SM count of the current device
+
+// ---- engine entry points (one per translation unit) ----------------------------------------------------------------
+struct ConvTcPlan;  // opaque, conv_tc.cu
+int conv_simt_launch(const cpn_op_t& op, const void* src, void* dst, const void* res, const void* wgt,
+                     const float* bias, cudaStream_t st);
+int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const void* res, const void* wgt,
+                        const float* bias, ConvTcPlan** out);
+int conv_tc_launch(const ConvTcPlan* p, cudaStream_t st);
+void conv_tc_plan_destroy(ConvTcPlan* p);
+
+int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* dst, int32_t* flags, cudaStream_t st);
+int maxpool_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st);
+int upsample_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st);
+int bilinear_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st);
+int proj_launch(const cpn_op_t& op, const void* src, void* dst, const float* wgt, const float* bias, cudaStream_t st);
+
+// ---- device helpers -----------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+}  // namespace cpn

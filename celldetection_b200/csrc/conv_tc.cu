@@ -1,0 +1,474 @@
+// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (fp16 x fp16 -> fp32 in TMEM), operands staged by
+// TMA (im2col-free: one 4-D box load per filter tap with out-of-bounds zero fill), mbarrier pipeline, persistent CTAs,
+// warp-specialised (1 TMA warp, 1 MMA warp, 4 epilogue warps), double-buffered TMEM accumulators.
+//
+// Replaces nn.Conv2d (+ folded BatchNorm2d) (+ residual) (+ ReLU) on the dense stages of the path:
+//   /root/reference/celldetection/models/commons.py:494-500 (ReadOut 7x7), :120-149 (TwoConvNormRelu 3x3),
+//   models/resnet.py:88-116 (Bottleneck 1x1 / grouped 3x3 / 1x1, forward = torchvision), models/unet.py:121-128
+//   (1x1 "inner" convs), models/fpn.py:106-121 (lateral 1x1, output 3x3).
+//
+// GEMM view: D[m, n] = sum_{tap, c} A[pixel m shifted by tap, c] * Wt[tap][n][c]
+//   M tile  = 128 output pixels = a 16 (x) by 8 (y) patch of one image   (UMMA M = 128, cta_group::1)
+//   N tile  = BN output channels (64 / 128 / 256)                        (UMMA N = BN)
+//   K block = 64 input channels of one filter tap (= one 128-byte swizzle row; 4 x UMMA K = 16)
+// A operand: NHWC fp16 activations through a 4-D tensor map (C, W, H, N) with box {64, 16, 8, 1}, SWIZZLE_128B.
+//   The box lands in shared memory as 128 rows (x fastest, then y) of 128 bytes = the canonical K-major SW128 layout.
+//   Stride-2 convolutions read one of four parity views (base shifted by (py, px), strides doubled), so every tap is
+//   still a plain box load.  Zero padding is the TMA out-of-bounds fill.
+// B operand: weights pre-packed as fp16 [R*S][cout][kslab] (K-major) through a 3-D tensor map, box {64, BN, 1}.
+// Grouped convolutions use BN = 64 and contract only over their 64-channel block-diagonal slab (cpn_op_t::kslab).
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace cpn {
+
+constexpr int TC_BW = 16, TC_BH = 8, TC_BM = 128, TC_BK = 64;
+constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM_BUDGET = 196608;  // bytes of operand stages
+
+struct ConvTcParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  __half* out;
+  const __half* res;
+  const float* bias;
+  int out_pitch, res_pitch, res_h, res_w;
+  int N, Ho, Wo, cout;
+  int R, S, stride, pad;
+  int cblocks, kslab, slab_mode;
+  int relu;
+  int tiles_x, tiles_y, tiles_n;
+  long long total_tiles;
+};
+
+struct ConvTcPlan {
+  ConvTcParams p;
+  int bn;
+  int stages;
+  int smem_bytes;
+  int grid;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; fp16 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
+// LBO >> 4 in [16,30) (= 1, unused for swizzled K-major), SBO >> 4 in [32,46) (= 1024 B between 8-row groups),
+// version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6), a_format F16 = 0 @ [7,10),
+// b_format F16 = 0 @ [10,13), a_major = b_major = K (0), n_dim = N >> 3 @ [17,23), m_dim = M >> 4 @ [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p, int stages) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two >= 32)
+  constexpr int MAX_STAGES = 8;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // operand stages must be 1024-byte aligned for SWIZZLE_128B
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nk = p.R * p.S * p.cblocks;  // K blocks per tile
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA[0]);
+    prefetch_tmap(&p.tmB);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(smem_u32(&bar_full[i]), 1);
+      mbar_init(smem_u32(&bar_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_tfull[i]), 1);
+      mbar_init(smem_u32(&bar_tempty[i]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = (int)(tile % p.tiles_n);
+        const long long m_tile = tile / p.tiles_n;
+        const int img = (int)(m_tile / tiles_per_img);
+        const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
+        const int y0 = (t_in / p.tiles_x) * TC_BH, x0 = (t_in % p.tiles_x) * TC_BW;
+        const int n0 = n_tile * BN;
+        const int cbase = p.slab_mode ? (n0 / p.kslab) * p.kslab : 0;
+        for (int tap = 0; tap < p.R * p.S; ++tap) {
+          const int r = tap / p.S, s = tap - r * p.S;
+          int qy = r - p.pad, qx = s - p.pad, map = 0;
+          if (p.stride == 2) {
+            const int py = qy & 1, px = qx & 1;
+            map = py * 2 + px;
+            qy = (qy - py) >> 1;
+            qx = (qx - px) >> 1;
+          }
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+            const uint32_t full = smem_u32(&bar_full[stage]);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+            mbar_expect_tx(full, STAGE_BYTES);
+            tma_load_4d(sa, &p.tmA[map], full, cbase + cb * TC_BK, x0 + qx, y0 + qy, img);
+            tma_load_3d(sb, &p.tmB, full, cb * TC_BK, n0, tap);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = make_idesc_f16(TC_BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      if (lane == 0) {
+        mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          const uint64_t da = make_sw128_kmajor_desc(sa), db = make_sw128_kmajor_desc(sb);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+            umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(smem_u32(&bar_empty[stage]));  // frees the smem stage when these MMAs retire
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&bar_tfull[acc]));  // accumulator complete -> epilogue
+      }
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================================ epilogue (4 warps, 128 rows) ================================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const int py = row / TC_BW, px = row % TC_BW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = (int)(tile % p.tiles_n);
+      const long long m_tile = tile / p.tiles_n;
+      const int img = (int)(m_tile / tiles_per_img);
+      const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
+      const int y = (t_in / p.tiles_x) * TC_BH + py, x = (t_in % p.tiles_x) * TC_BW + px;
+      const int n0 = n_tile * BN;
+      const bool valid = (y < p.Ho) && (x < p.Wo);
+      __half* op = p.out + (((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0;
+      const __half* rp = nullptr;
+      if (p.res && valid) {
+        const int ry = (p.res_h == p.Ho) ? y : (int)(((long long)y * p.res_h) / p.Ho);
+        const int rx = (p.res_w == p.Wo) ? x : (int)(((long long)x * p.res_w) / p.Wo);
+        rp = p.res + (((long long)img * p.res_h + ry) * p.res_w + rx) * p.res_pitch + n0;
+      }
+      mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
+          uint4 packed[4];
+          uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 b = p.bias ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float f0 = __uint_as_float(v[q * 4 + 0]) + b.x, f1 = __uint_as_float(v[q * 4 + 1]) + b.y;
+            float f2 = __uint_as_float(v[q * 4 + 2]) + b.z, f3 = __uint_as_float(v[q * 4 + 3]) + b.w;
+            if (rp) {
+              const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp + ch * 32 + q * 4));
+              const __half2 r0 = *reinterpret_cast<const __half2*>(&rr.x), r1 = *reinterpret_cast<const __half2*>(&rr.y);
+              f0 += __low2float(r0); f1 += __high2float(r0); f2 += __low2float(r1); f3 += __high2float(r1);
+            }
+            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+            __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
+            pk[q * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[q * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+          uint4* o4 = reinterpret_cast<uint4*>(op + ch * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o4[q] = packed[q];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Host side: tensor maps + launch configuration
+// ---------------------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box) {
+  PFN_cuTensorMapEncodeTiled_v12000 fn = get_encode_fn();
+  CPN_REQUIRE(fn != nullptr, "conv_tc: cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CPN_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu)",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2]);
+  return 0;
+}
+
+static int pick_bn(int cout, int slab_mode) {
+  if (slab_mode) return 64;
+  if (cout % 256 == 0) return 256;
+  if (cout % 128 == 0) return 128;
+  return 64;
+}
+
+int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const void* res, const void* wgt,
+                        const float* bias, ConvTcPlan** out) {
+  CPN_REQUIRE(op.src.dtype == CPN_DT_F16 && op.dst.dtype == CPN_DT_F16, "conv_tc: fp16 activations required");
+  CPN_REQUIRE(op.res.n == 0 || op.res.dtype == CPN_DT_F16, "conv_tc: fp16 residual required");
+  CPN_REQUIRE(op.kslab % TC_BK == 0, "conv_tc: kslab %d must be a multiple of 64", op.kslab);
+  CPN_REQUIRE(op.dst.c % 64 == 0, "conv_tc: cout %d must be a multiple of 64", op.dst.c);
+  CPN_REQUIRE(op.stride == 1 || op.stride == 2, "conv_tc: stride %d unsupported", op.stride);
+  CPN_REQUIRE(op.src.pitch % 8 == 0 && op.dst.pitch % 8 == 0 && (op.res.n == 0 || op.res.pitch % 8 == 0),
+              "conv_tc: pitches must be multiples of 8 elements (16 bytes)");
+  CPN_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0) && ((uintptr_t)wgt % 16 == 0) &&
+                  (res == nullptr || (uintptr_t)res % 16 == 0) && (bias == nullptr || (uintptr_t)bias % 16 == 0),
+              "conv_tc: base pointers must be 16-byte aligned");
+  const int eh = (op.src.h + 2 * op.pad - op.r) / op.stride + 1, ew = (op.src.w + 2 * op.pad - op.s) / op.stride + 1;
+  CPN_REQUIRE(eh == op.dst.h && ew == op.dst.w && op.src.n == op.dst.n,
+              "conv_tc: output shape mismatch (%dx%d expected %dx%d)", op.dst.h, op.dst.w, eh, ew);
+  CPN_REQUIRE(op.slab_mode == 0 ? op.kslab <= op.src.c : true, "conv_tc: kslab exceeds input channels");
+
+  ConvTcPlan* pl = new ConvTcPlan();
+  ConvTcParams& p = pl->p;
+  memset(&p, 0, sizeof(p));
+  const int bn = pick_bn(op.dst.c, op.slab_mode);
+  pl->bn = bn;
+  // --- A maps: (C, W, H, N) with box {64, 16, 8, 1}; stride 2 -> four parity views
+  const int nmaps = op.stride == 2 ? 4 : 1;
+  for (int m = 0; m < nmaps; ++m) {
+    const int py = m >> 1, px = m & 1;
+    const int st = op.stride;
+    const long long wv = (op.src.w - px + st - 1) / st, hv = (op.src.h - py + st - 1) / st;
+    if (wv <= 0 || hv <= 0) {  // degenerate parity view (1-pixel maps): alias view 0, never selected with data
+      p.tmA[m] = p.tmA[0];
+      continue;
+    }
+    const char* base = reinterpret_cast<const char*>(src) + ((long long)py * op.src.w + px) * op.src.pitch * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)op.src.c, (cuuint64_t)wv, (cuuint64_t)hv, (cuuint64_t)op.src.n};
+    cuuint64_t strides[3] = {(cuuint64_t)st * op.src.pitch * 2, (cuuint64_t)st * op.src.w * op.src.pitch * 2,
+                             (cuuint64_t)op.src.h * op.src.w * op.src.pitch * 2};
+    cuuint32_t box[4] = {TC_BK, TC_BW, TC_BH, 1};
+    if (encode_map(&p.tmA[m], const_cast<char*>(base), 4, dims, strides, box)) { delete pl; return 1; }
+  }
+  for (int m = nmaps; m < 4; ++m) p.tmA[m] = p.tmA[0];
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)op.kslab, (cuuint64_t)op.dst.c, (cuuint64_t)(op.r * op.s)};
+    cuuint64_t strides[2] = {(cuuint64_t)op.kslab * 2, (cuuint64_t)op.kslab * op.dst.c * 2};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)bn, 1};
+    if (encode_map(&p.tmB, const_cast<void*>(wgt), 3, dims, strides, box)) { delete pl; return 1; }
+  }
+  p.out = reinterpret_cast<__half*>(dst);
+  p.res = op.res.n ? reinterpret_cast<const __half*>(res) : nullptr;
+  p.bias = bias;
+  p.out_pitch = op.dst.pitch; p.res_pitch = op.res.pitch;
+  p.res_h = op.res.n ? op.res.h : 0; p.res_w = op.res.n ? op.res.w : 0;
+  p.N = op.dst.n; p.Ho = op.dst.h; p.Wo = op.dst.w; p.cout = op.dst.c;
+  p.R = op.r; p.S = op.s; p.stride = op.stride; p.pad = op.pad;
+  p.cblocks = op.kslab / TC_BK; p.kslab = op.kslab; p.slab_mode = op.slab_mode;
+  p.relu = op.act == CPN_ACT_RELU;
+  p.tiles_x = (op.dst.w + TC_BW - 1) / TC_BW; p.tiles_y = (op.dst.h + TC_BH - 1) / TC_BH;
+  p.tiles_n = op.dst.c / bn;
+  p.total_tiles = (long long)op.dst.n * p.tiles_x * p.tiles_y * p.tiles_n;
+  const int stage_bytes = TC_BM * TC_BK * 2 + bn * TC_BK * 2;
+  pl->stages = TC_SMEM_BUDGET / stage_bytes;
+  if (pl->stages > 8) pl->stages = 8;
+  pl->smem_bytes = pl->stages * stage_bytes + 1024;
+  const long long sms = sm_count();
+  pl->grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  *out = pl;
+  return 0;
+}
+
+template <int BN>
+static int launch_bn(const ConvTcPlan* pl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TC_SMEM_BUDGET + 1024));
+    attr_set = true;
+  }
+  conv_tc_kernel<BN><<<pl->grid, TC_THREADS, pl->smem_bytes, st>>>(pl->p, pl->stages);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t st) {
+  switch (pl->bn) {
+    case 64: return launch_bn<64>(pl, st);
+    case 128: return launch_bn<128>(pl, st);
+    case 256: return launch_bn<256>(pl, st);
+  }
+  set_error("conv_tc: bad BN %d", pl->bn);
+  return 1;
+}
+
+void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
+
+}  // namespace cpn

@@ -1,0 +1,330 @@
+// Segmented greedy NMS with torchvision semantics (replaces torch.ops.torchvision.nms as called by
+// /root/reference/celldetection/ops/cpn.py:189-227 and celldetection_scripts/cpn_inference.py:405-408).
+//
+// Semantics mirrored (torchvision 0.26): candidates in stable descending score order (ties keep
+// the lower original index first); box j is suppressed by an earlier kept box i when
+//   inter / (area_i + area_j - inter) > thr   (fp32, strict, NaN never suppresses; areas (x2-x1)*(y2-y1), no +1);
+// the result lists kept indices in descending score order.  The 50 000-chunk rule of batched_box_nmsi is reproduced
+// with two passes (chunks of the ORIGINAL row order, then NMS over the concatenated survivors).
+//
+// Algorithm: one stable radix sort of (segment, ~score) keys (CUB, utility only), then one CTA per segment runs a
+// blocked greedy scan with O(P) memory: 256 candidates at a time are (a) tested against all previously kept boxes
+// (staged through shared memory), (b) cross-tested inside the tile into a 256x256 bit matrix, (c) resolved by one warp
+// that jumps from kept box to kept box (__ffs over the alive bitmap), so the sequential chain is K long, not P long.
+// Compiled with -fmad=false so the IoU arithmetic rounds exactly like the reference's.
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace cpn {
+
+constexpr int NMS_T = 256;  // candidates per tile == threads per CTA
+
+__device__ __forceinline__ uint32_t float_desc_key(float f) {
+  uint32_t u = __float_as_uint(f);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-order key
+  return ~u;                                       // descending
+}
+
+__device__ __forceinline__ int find_segment(const int32_t* __restrict__ seg_offsets, int n_segments, long long row) {
+  int lo = 0, hi = n_segments;  // largest s with seg_offsets[s] <= row
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)seg_offsets[mid] <= row) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// keys for pass A.  sub-segment id = sub_base[seg] + (row - seg_start) / chunk   (chunk <= 0: one sub per segment)
+__global__ void nms_keys_kernel(const float* __restrict__ scores, const int32_t* __restrict__ seg_offsets,
+                                int n_segments, long long n, int chunk, uint64_t* __restrict__ keys,
+                                int32_t* __restrict__ vals) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int seg = find_segment(seg_offsets, n_segments, i);
+  uint32_t sub = (uint32_t)seg;
+  if (chunk > 0) {
+    uint32_t base = 0;
+    for (int s = 0; s < seg; ++s) {
+      const int sz = seg_offsets[s + 1] - seg_offsets[s];
+      base += sz > 0 ? (uint32_t)((sz + chunk - 1) / chunk) : 1u;
+    }
+    sub = base + (uint32_t)((i - seg_offsets[seg]) / chunk);
+  }
+  keys[i] = ((uint64_t)sub << 32) | float_desc_key(scores[i]);
+  vals[i] = (int32_t)i;
+}
+
+// keys for pass B: rows are the survivors of pass A (in sub-segment order); group by the ORIGINAL segment
+__global__ void nms_keys_rows_kernel(const float* __restrict__ scores, const int32_t* __restrict__ seg_offsets,
+                                     int n_segments, const int32_t* __restrict__ rows,
+                                     const long long* __restrict__ n_ptr, uint64_t* __restrict__ keys,
+                                     int32_t* __restrict__ vals, long long capacity) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= capacity) return;
+  if (i >= *n_ptr) {  // padding sorts to the very end
+    keys[i] = ~0ull;
+    vals[i] = -1;
+    return;
+  }
+  const int r = rows[i];
+  const int seg = find_segment(seg_offsets, n_segments, r);
+  keys[i] = ((uint64_t)(uint32_t)seg << 32) | float_desc_key(scores[r]);
+  vals[i] = r;
+}
+
+// group_start[g] = lower_bound over the high 32 bits of the sorted keys, g in [0, n_groups]
+__global__ void nms_bounds_kernel(const uint64_t* __restrict__ keys, long long n, int n_groups,
+                                  int32_t* __restrict__ group_start) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > n_groups) return;
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((uint32_t)(keys[mid] >> 32) < (uint32_t)g) lo = mid + 1; else hi = mid;
+  }
+  group_start[g] = (int32_t)lo;
+}
+
+__device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const float4 b, const float area_b,
+                                       const float thr) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+  const float inter = w * h;
+  const float ovr = inter / (area_a + area_b - inter);
+  return ovr > thr;
+}
+
+// One CTA per group (sorted rows perm[group_start[g] .. group_start[g+1])).
+// kept rows are written to keep_out at out_offsets[g] (== group_start[g] when out_offsets is NULL); counts to counts[g].
+__global__ void __launch_bounds__(NMS_T) nms_group_kernel(const float* __restrict__ boxes,
+                                                          const int32_t* __restrict__ perm,
+                                                          const int32_t* __restrict__ group_start,
+                                                          const int32_t* __restrict__ out_offsets, float thr,
+                                                          float4* __restrict__ kept_boxes,
+                                                          int32_t* __restrict__ keep_out,
+                                                          int32_t* __restrict__ counts) {
+  __shared__ float4 kb[NMS_T];
+  __shared__ float4 cand[NMS_T];
+  __shared__ int32_t crow[NMS_T];
+  __shared__ uint32_t mask[NMS_T][NMS_T / 32];
+  __shared__ uint32_t alive_bm[NMS_T / 32];
+  __shared__ int nkept_s;
+
+  const int g = blockIdx.x;
+  const int start = group_start[g];
+  const int n = group_start[g + 1] - start;
+  const int out0 = out_offsets ? out_offsets[g] : start;
+  const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
+  if (j == 0) nkept_s = 0;
+  __syncthreads();
+
+  for (int t0 = 0; t0 < n; t0 += NMS_T) {
+    const int ntile = min(NMS_T, n - t0);
+    const bool valid = j < ntile;
+    int row = -1;
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      row = perm[start + t0 + j];
+      box = reinterpret_cast<const float4*>(boxes)[row];
+    }
+    const float area = (box.z - box.x) * (box.w - box.y);
+    bool alive = valid;
+    const int nkept = nkept_s;
+    // (a) against everything kept so far
+    for (int k0 = 0; k0 < nkept; k0 += NMS_T) {
+      const int m = min(NMS_T, nkept - k0);
+      if (j < m) kb[j] = kept_boxes[out0 + k0 + j];
+      __syncthreads();
+      if (alive) {
+        for (int k = 0; k < m; ++k) {
+          const float4 b = kb[k];
+          if (iou_gt(b, (b.z - b.x) * (b.w - b.y), box, area, thr)) { alive = false; break; }
+        }
+      }
+      __syncthreads();
+    }
+    // (b) tile-internal bit matrix (rows of dead candidates are never read)
+    cand[j] = box;
+    crow[j] = row;
+    const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) alive_bm[warp] = bal;
+    __syncthreads();
+    if (alive) {
+#pragma unroll 1
+      for (int wd = 0; wd < NMS_T / 32; ++wd) {
+        uint32_t bits = 0;
+        if (wd * 32 + 31 > j) {
+          for (int b = 0; b < 32; ++b) {
+            const int k = wd * 32 + b;
+            if (k > j && k < ntile) {
+              const float4 c = cand[k];
+              if (iou_gt(box, area, c, (c.z - c.x) * (c.w - c.y), thr)) bits |= 1u << b;
+            }
+          }
+        }
+        mask[j][wd] = bits;
+      }
+    }
+    __syncthreads();
+    // (c) resolve: warp 0, lanes 0..7 own one 32-bit word of the removed bitmap each
+    if (warp == 0) {
+      uint32_t rem = (lane < NMS_T / 32) ? ~alive_bm[lane] : 0xffffffffu;
+      int nk = nkept;
+      while (true) {
+        const uint32_t z = ~rem;
+        int first = z ? (lane * 32 + __ffs(z) - 1) : 1 << 20;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (first >= ntile) break;
+        if (lane == 0) {
+          keep_out[out0 + nk] = crow[first];
+          kept_boxes[out0 + nk] = cand[first];
+        }
+        ++nk;
+        if (lane < NMS_T / 32) {
+          rem |= mask[first][lane];
+          if ((first >> 5) == lane) rem |= 1u << (first & 31);
+        }
+      }
+      if (lane == 0) nkept_s = nk;
+    }
+    __syncthreads();
+  }
+  if (j == 0) counts[g] = nkept_s;
+}
+
+// pass-B glue: compact the per-sub-segment survivor lists (sub-segment order) into rows2, total -> n2
+__global__ void nms_compact_kernel(const int32_t* __restrict__ keepA, const int32_t* __restrict__ sub_start,
+                                   const int32_t* __restrict__ countsA, int n_sub, int32_t* __restrict__ rows2,
+                                   long long* __restrict__ n2) {
+  const int s = blockIdx.x;
+  long long off = 0;
+  for (int q = 0; q < s; ++q) off += countsA[q];
+  const int c = countsA[s];
+  for (int i = threadIdx.x; i < c; i += blockDim.x) rows2[off + i] = keepA[sub_start[s] + i];
+  if (s == n_sub - 1 && threadIdx.x == 0) *n2 = off + c;
+}
+
+// number of sub-segments on the device (pass B needs the true count for its grid guard)
+__global__ void nms_count_subs_kernel(const int32_t* __restrict__ seg_offsets, int n_segments, int chunk,
+                                      int32_t* __restrict__ n_sub_out) {
+  if (threadIdx.x || blockIdx.x) return;
+  int t = 0;
+  for (int s = 0; s < n_segments; ++s) {
+    const int sz = seg_offsets[s + 1] - seg_offsets[s];
+    t += sz > 0 ? (sz + chunk - 1) / chunk : 1;
+  }
+  *n_sub_out = t;
+}
+
+__global__ void nms_zero_counts_kernel(int32_t* __restrict__ counts, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) counts[i] = 0;
+}
+
+struct NmsWs {
+  uint64_t *keys_a, *keys_b;
+  int32_t *vals_a, *vals_b;
+  float4* kept_boxes;
+  int32_t *keepA, *rows2, *group_start, *countsA;
+  long long* n2;
+  void* cub_tmp;
+  size_t cub_bytes;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t carve(void* base, int64_t n, int n_segments, NmsWs* ws) {
+  const int64_t n_sub_max = (int64_t)n_segments + n / 1024 + 2;  // chunk >= 1024 enforced
+  size_t off = 0;
+  char* b = reinterpret_cast<char*>(base);
+  auto take = [&](size_t bytes) { char* p = b ? b + off : nullptr; off = align_up(off + bytes, 256); return p; };
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  uint64_t* ka = (uint64_t*)take(nn * 8);
+  uint64_t* kb2 = (uint64_t*)take(nn * 8);
+  int32_t* va = (int32_t*)take(nn * 4);
+  int32_t* vb = (int32_t*)take(nn * 4);
+  float4* kept = (float4*)take(nn * 16);
+  int32_t* keepA = (int32_t*)take(nn * 4);
+  int32_t* rows2 = (int32_t*)take(nn * 4);
+  int32_t* gs = (int32_t*)take((size_t)(n_sub_max + 2) * 4);
+  int32_t* ca = (int32_t*)take((size_t)(n_sub_max + 2) * 4);
+  long long* n2 = (long long*)take(64);
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)nn, 0, 64, (cudaStream_t)0);
+  void* tmp = take(cub_bytes + 256);
+  if (ws) {
+    ws->keys_a = ka; ws->keys_b = kb2; ws->vals_a = va; ws->vals_b = vb; ws->kept_boxes = kept; ws->keepA = keepA;
+    ws->rows2 = rows2; ws->group_start = gs; ws->countsA = ca; ws->n2 = n2; ws->cub_tmp = tmp;
+    ws->cub_bytes = cub_bytes + 256;
+  }
+  return off;
+}
+
+}  // namespace cpn
+
+using namespace cpn;
+
+extern "C" size_t cpn_nms_workspace_bytes(int64_t n_boxes, int n_segments) {
+  return carve(nullptr, n_boxes, n_segments, nullptr);
+}
+
+extern "C" int cpn_nms_segments(const float* boxes, const float* scores, const int32_t* seg_offsets, int n_segments,
+                                int64_t n_boxes, float iou_threshold, int chunk, void* workspace, int32_t* keep,
+                                int32_t* keep_counts, void* stream) {
+  CPN_REQUIRE(n_segments >= 1, "nms: need at least one segment");
+  CPN_REQUIRE(n_boxes < (1ll << 31), "nms: too many boxes");
+  CPN_REQUIRE(chunk <= 0 || chunk >= 1024, "nms: chunk must be <= 0 (off) or >= 1024");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_boxes <= 0) {
+    nms_zero_counts_kernel<<<(n_segments + 127) / 128, 128, 0, st>>>(keep_counts, n_segments);
+    CPN_CHECK_LAUNCH();
+    return 0;
+  }
+  NmsWs ws;
+  carve(workspace, n_boxes, n_segments, &ws);
+  const int n = (int)n_boxes;
+  const bool two_pass = chunk > 0 && n_boxes > chunk;
+  const int tb = 256, gb = (n + tb - 1) / tb;
+
+  // ---- pass A: sort by (sub-segment, score desc), NMS per sub-segment ----
+  nms_keys_kernel<<<gb, tb, 0, st>>>(scores, seg_offsets, n_segments, n, two_pass ? chunk : 0, ws.keys_a, ws.vals_a);
+  CPN_CHECK_LAUNCH();
+  const int n_groups_a = two_pass ? (int)(n_segments + n_boxes / chunk + 1) : n_segments;
+  int end_bit = 32;
+  while ((1ll << (end_bit - 32)) < n_groups_a + 1 && end_bit < 64) ++end_bit;
+  size_t cb = ws.cub_bytes;
+  CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, cb, ws.keys_a, ws.keys_b, ws.vals_a, ws.vals_b, n, 0,
+                                                 end_bit, st));
+  count_launch(4);
+  nms_bounds_kernel<<<(n_groups_a + 1 + 127) / 128, 128, 0, st>>>(ws.keys_b, n, n_groups_a, ws.group_start);
+  CPN_CHECK_LAUNCH();
+  if (!two_pass) {
+    nms_group_kernel<<<n_groups_a, NMS_T, 0, st>>>(boxes, ws.vals_b, ws.group_start, nullptr, iou_threshold,
+                                                   ws.kept_boxes, keep, keep_counts);
+    CPN_CHECK_LAUNCH();
+    return 0;
+  }
+  nms_group_kernel<<<n_groups_a, NMS_T, 0, st>>>(boxes, ws.vals_b, ws.group_start, nullptr, iou_threshold,
+                                                 ws.kept_boxes, ws.keepA, ws.countsA);
+  CPN_CHECK_LAUNCH();
+  // ---- pass B: survivors (sub-segment order) -> sort by (segment, score desc) -> NMS per segment ----
+  nms_compact_kernel<<<n_groups_a, 256, 0, st>>>(ws.keepA, ws.group_start, ws.countsA, n_groups_a, ws.rows2, ws.n2);
+  CPN_CHECK_LAUNCH();
+  nms_keys_rows_kernel<<<gb, tb, 0, st>>>(scores, seg_offsets, n_segments, ws.rows2, ws.n2, ws.keys_a, ws.vals_a, n);
+  CPN_CHECK_LAUNCH();
+  cb = ws.cub_bytes;
+  CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, cb, ws.keys_a, ws.keys_b, ws.vals_a, ws.vals_b, n, 0, 64,
+                                                 st));
+  count_launch(4);
+  nms_bounds_kernel<<<(n_segments + 1 + 127) / 128, 128, 0, st>>>(ws.keys_b, n, n_segments, ws.group_start);
+  CPN_CHECK_LAUNCH();
+  // results are packed at each segment's ORIGINAL offset (seg_offsets), as documented
+  nms_group_kernel<<<n_segments, NMS_T, 0, st>>>(boxes, ws.vals_b, ws.group_start, seg_offsets, iou_threshold,
+                                                 ws.kept_boxes, keep, keep_counts);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,308 @@
+// Memory-bound layer kernels of the plan (NHWC, fp32 or fp16 activations): input preparation, max-pooling, nearest and
+// bilinear resampling and the ReadOut projection.  All are HBM-bound element-wise / gather work: coalesced along the
+// channel axis, 8-byte or 16-byte vector accesses where the pitch allows, grid sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace cpn {
+
+static inline int grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PREP: network input -> NHWC activations.  Fuses Normalize's range assertion (commons.py:694-700; mean 0 / std 1 so the
+// affine part is the identity), the uint8 -> float / 255 of lightning_base.py:774-780 and the NCHW -> NHWC change.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void prep_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out, int N, int C, int H, int W,
+                            int pitch, int32_t* __restrict__ flags) {
+  const long long total = (long long)N * H * W;
+  bool bad = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ((long long)H * W));
+    const long long rem = i - (long long)n * H * W;
+    T* o = out + i * pitch;
+    for (int c = 0; c < C; ++c) {
+      float v;
+      if (fmt == CPN_IN_F32_NCHW) {
+        v = reinterpret_cast<const float*>(in)[((long long)n * C + c) * H * W + rem];
+        bad |= !(v >= 0.f && v <= 1.f);
+      } else if (fmt == CPN_IN_U8_NCHW) {
+        v = (float)reinterpret_cast<const uint8_t*>(in)[((long long)n * C + c) * H * W + rem] / 255.f;
+      } else {
+        v = (float)reinterpret_cast<const uint8_t*>(in)[i * C + c] / 255.f;
+      }
+      o[c] = from_f32<T>(v);
+    }
+  }
+  if (bad) atomicOr(flags, 1);
+}
+
+int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* dst, int32_t* flags, cudaStream_t st) {
+  CPN_REQUIRE(input_format >= 0 && input_format <= 2, "prep: bad input format %d", input_format);
+  const long long total = (long long)op.dst.n * op.dst.h * op.dst.w;
+  const int grid = grid_for(total, 256);
+  if (op.dst.dtype == CPN_DT_F32)
+    prep_kernel<float><<<grid, 256, 0, st>>>(input, input_format, (float*)dst, op.dst.n, op.dst.c, op.dst.h, op.dst.w,
+                                             op.dst.pitch, flags);
+  else
+    prep_kernel<__half><<<grid, 256, 0, st>>>(input, input_format, (__half*)dst, op.dst.n, op.dst.c, op.dst.h,
+                                              op.dst.w, op.dst.pitch, flags);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// vector helpers: a "pack" is 4 channels (float4 / 4 halves)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Pack4;
+template <>
+struct Pack4<float> {
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ void get(float (&f)[4]) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+  __device__ __forceinline__ void set(const float (&f)[4]) { v = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <>
+struct Pack4<__half> {
+  uint2 v;
+  __device__ __forceinline__ void load(const __half* p) { v = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void store(__half* p) const { *reinterpret_cast<uint2*>(p) = v; }
+  __device__ __forceinline__ void get(float (&f)[4]) const {
+    const __half2 a = *reinterpret_cast<const __half2*>(&v.x), b = *reinterpret_cast<const __half2*>(&v.y);
+    f[0] = __low2float(a); f[1] = __high2float(a); f[2] = __low2float(b); f[3] = __high2float(b);
+  }
+  __device__ __forceinline__ void set(const float (&f)[4]) {
+    __half2 a = __floats2half2_rn(f[0], f[1]), b = __floats2half2_rn(f[2], f[3]);
+    v.x = *reinterpret_cast<uint32_t*>(&a); v.y = *reinterpret_cast<uint32_t*>(&b);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MAXPOOL (nn.MaxPool2d(k, stride, pad); padding never wins) -- resnet.py:279 (3,2,1), unet.py:56 (2,2,0)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int C, int sp,
+                               int Ho, int Wo, int dp, int k, int stride, int pad) {
+  const int c4 = C / 4;
+  const long long total = (long long)N * Ho * Wo * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    long long pix = i / c4;
+    const int ox = (int)(pix % Wo);
+    pix /= Wo;
+    const int oy = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int dy = 0; dy < k; ++dy) {
+      const int iy = oy * stride - pad + dy;
+      if (iy < 0 || iy >= H) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        const int ix = ox * stride - pad + dx;
+        if (ix < 0 || ix >= W) continue;
+        Pack4<T> pk;
+        pk.load(src + (((long long)n * H + iy) * W + ix) * sp + c);
+        float f[4];
+        pk.get(f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = fmaxf(m[j], f[j]);
+      }
+    }
+    Pack4<T> o;
+    o.set(m);
+    o.store(dst + (((long long)n * Ho + oy) * Wo + ox) * dp + c);
+  }
+}
+
+int maxpool_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st) {
+  CPN_REQUIRE(op.src.c % 4 == 0 && op.src.pitch % 4 == 0 && op.dst.pitch % 4 == 0 && op.src.c == op.dst.c,
+              "maxpool: channels/pitch must be multiples of 4");
+  CPN_REQUIRE(op.src.dtype == op.dst.dtype, "maxpool: dtype mismatch");
+  const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * (op.dst.c / 4);
+  const int grid = grid_for(total, 256);
+  if (op.src.dtype == CPN_DT_F32)
+    maxpool_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, op.src.n, op.src.h, op.src.w, op.src.c,
+                                                op.src.pitch, op.dst.h, op.dst.w, op.dst.pitch, op.r, op.stride, op.pad);
+  else
+    maxpool_kernel<__half><<<grid, 256, 0, st>>>((const __half*)src, (__half*)dst, op.src.n, op.src.h, op.src.w,
+                                                 op.src.c, op.src.pitch, op.dst.h, op.dst.w, op.dst.pitch, op.r,
+                                                 op.stride, op.pad);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// UPSAMPLE: F.interpolate(mode='nearest') -- src index = floor(dst * in / out) (unet.py:215-217, torchvision FPN)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void upsample_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int C, int sp,
+                                int Ho, int Wo, int dp) {
+  const int c4 = C / 4;
+  const long long total = (long long)N * Ho * Wo * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    long long pix = i / c4;
+    const int ox = (int)(pix % Wo);
+    pix /= Wo;
+    const int oy = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    const int iy = (int)(((long long)oy * H) / Ho), ix = (int)(((long long)ox * W) / Wo);
+    Pack4<T> pk;
+    pk.load(src + (((long long)n * H + iy) * W + ix) * sp + c);
+    pk.store(dst + (((long long)n * Ho + oy) * Wo + ox) * dp + c);
+  }
+}
+
+int upsample_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st) {
+  CPN_REQUIRE(op.src.c % 4 == 0 && op.src.pitch % 4 == 0 && op.dst.pitch % 4 == 0 && op.src.c == op.dst.c,
+              "upsample: channels/pitch must be multiples of 4");
+  CPN_REQUIRE(op.src.dtype == op.dst.dtype, "upsample: dtype mismatch");
+  const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * (op.dst.c / 4);
+  const int grid = grid_for(total, 256);
+  if (op.src.dtype == CPN_DT_F32)
+    upsample_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, op.src.n, op.src.h, op.src.w,
+                                                 op.src.c, op.src.pitch, op.dst.h, op.dst.w, op.dst.pitch);
+  else
+    upsample_kernel<__half><<<grid, 256, 0, st>>>((const __half*)src, (__half*)dst, op.src.n, op.src.h, op.src.w,
+                                                  op.src.c, op.src.pitch, op.dst.h, op.dst.w, op.dst.pitch);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BILINEAR: F.interpolate(mode='bilinear', align_corners=False) (models/cpn.py:109-115): half-pixel centres,
+// src = (dst + 0.5) * in/out - 0.5 clamped at 0, upper neighbour clamped to in-1 (ATen area_pixel_compute_source_index).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void bilinear_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int N, int H, int W, int C, int sp,
+                                int Ho, int Wo, int dp) {
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long pix = i / C;
+    const int ox = (int)(pix % Wo);
+    pix /= Wo;
+    const int oy = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    float fy = sy * ((float)oy + 0.5f) - 0.5f, fx = sx * ((float)ox + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const TI* b = src + (long long)n * H * W * sp + c;
+    const float v00 = to_f32<TI>(b[((long long)y0 * W + x0) * sp]), v01 = to_f32<TI>(b[((long long)y0 * W + x1) * sp]);
+    const float v10 = to_f32<TI>(b[((long long)y1 * W + x0) * sp]), v11 = to_f32<TI>(b[((long long)y1 * W + x1) * sp]);
+    const float v = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+    dst[(((long long)n * Ho + oy) * Wo + ox) * dp + c] = from_f32<TO>(v);
+  }
+}
+
+int bilinear_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st) {
+  CPN_REQUIRE(op.src.c == op.dst.c, "bilinear: channel mismatch");
+  const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * op.dst.c;
+  const int grid = grid_for(total, 256);
+#define CPN_BIL(TI, TO)                                                                                             \
+  bilinear_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)src, (TO*)dst, op.src.n, op.src.h, op.src.w, op.src.c, \
+                                                op.src.pitch, op.dst.h, op.dst.w, op.dst.pitch)
+  if (op.src.dtype == CPN_DT_F32 && op.dst.dtype == CPN_DT_F32) CPN_BIL(float, float);
+  else if (op.src.dtype == CPN_DT_F16 && op.dst.dtype == CPN_DT_F16) CPN_BIL(__half, __half);
+  else if (op.src.dtype == CPN_DT_F16 && op.dst.dtype == CPN_DT_F32) CPN_BIL(__half, float);
+  else { set_error("bilinear: unsupported dtypes"); return 1; }
+#undef CPN_BIL
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PROJ: ReadOut's final 1x1 convolution (commons.py:499) + final activation (ScaledTanh for the refinement head,
+// cpn.py:230) to fp32 pixel records.  One warp per pixel: lanes split the input channels (coalesced 8/16-byte loads),
+// weights live in shared memory, warp-shuffle reduction per output channel.
+//   dst[pixel * dp + j] = act( bias[j] + sum_c src[pixel * sp + cin_off + c] * w[j][c] ),  j < cout <= 32
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) proj_kernel(const T* __restrict__ src, float* __restrict__ dst,
+                                                   const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                   long long pixels, int sp, int cin_off, int cin, int cout, int dp,
+                                                   int act, float act_scale) {
+  extern __shared__ float wsm[];  // [cout][cin]
+  for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) wsm[i] = wgt[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (long long pix = (long long)blockIdx.x * wpb + warp; pix < pixels; pix += (long long)gridDim.x * wpb) {
+    const T* sp_ = src + pix * sp + cin_off;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int c = lane * 4; c < cin; c += 128) {
+      Pack4<T> pk;
+      pk.load(sp_ + c);
+      float f[4];
+      pk.get(f);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < cout) {
+          const float* w = wsm + j * cin + c;
+          acc[j] = fmaf(f[0], w[0], acc[j]);
+          acc[j] = fmaf(f[1], w[1], acc[j]);
+          acc[j] = fmaf(f[2], w[2], acc[j]);
+          acc[j] = fmaf(f[3], w[3], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < cout) {
+        float v = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[j] = v;
+      }
+    }
+    // lane j writes output channel j (coalesced record write)
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == lane) mine = acc[j];
+    if (lane < cout) {
+      float v = mine + (bias ? bias[lane] : 0.f);
+      if (act == CPN_ACT_SCALED_TANH) v = tanhf(v) * act_scale;
+      else if (act == CPN_ACT_RELU) v = fmaxf(v, 0.f);
+      dst[pix * dp + lane] = v;
+    }
+  }
+}
+
+int proj_launch(const cpn_op_t& op, const void* src, void* dst, const float* wgt, const float* bias, cudaStream_t st) {
+  CPN_REQUIRE(op.dst.dtype == CPN_DT_F32, "proj: fp32 output required");
+  CPN_REQUIRE(op.dst.c >= 1 && op.dst.c <= 32, "proj: cout %d must be in [1, 32]", op.dst.c);
+  CPN_REQUIRE(op.proj_cin % 4 == 0 && op.proj_cin_off % 4 == 0 && op.src.pitch % 4 == 0,
+              "proj: cin/cin_off/pitch must be multiples of 4");
+  const long long pixels = (long long)op.src.n * op.src.h * op.src.w;
+  const size_t smem = (size_t)op.dst.c * op.proj_cin * sizeof(float);
+  CPN_REQUIRE(smem <= 48 * 1024, "proj: weights (%zu B) exceed 48 KB of shared memory", smem);
+  long long blocks = (pixels + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (op.src.dtype == CPN_DT_F32)
+    proj_kernel<float><<<(int)blocks, 256, smem, st>>>((const float*)src, (float*)dst, wgt, bias, pixels, op.src.pitch,
+                                                       op.proj_cin_off, op.proj_cin, op.dst.c, op.dst.pitch, op.act,
+                                                       op.act_scale);
+  else
+    proj_kernel<__half><<<(int)blocks, 256, smem, st>>>((const __half*)src, (float*)dst, wgt, bias, pixels,
+                                                        op.src.pitch, op.proj_cin_off, op.proj_cin, op.dst.c,
+                                                        op.dst.pitch, op.act, op.act_scale);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace cpn

@@ -1,0 +1,550 @@
+// Post-head chain of the Contour Proposal Network (compiled with -fmad=false: the fused decode must round exactly like
+// the reference's un-fused torch ops, because torch.round() in the refinement loop is discontinuous).
+//
+//   select   : sigmoid / score bounds / threshold / ordered compaction      models/cpn.py:575-587, 616-620
+//   decode   : rel->abs location, inverse DFT, rescale, 4x local refinement,
+//              clamp, boxes, offsets -- one kernel, one warp per proposal    ops/cpn.py:15-165, models/cpn.py:63-85,
+//                                                                            :661-670, :695-702
+//   f2c      : stand-alone ops.cpn.fouriers2contours (register-tiled)        ops/cpn.py:44-95
+//   border   : remove_border_contours                                        ops/cpn.py:258-290
+//   gather   : row gather (resolve_keep_indices)                             models/cpn.py:53-60
+// All of it is HBM-/latency-bound gather-scatter work; no tensor cores.
+#include "common.cuh"
+
+namespace cpn {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// select
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SEL_THREADS = 256, SEL_PER_THREAD = 4, SEL_CHUNK = SEL_THREADS * SEL_PER_THREAD;
+
+__device__ __forceinline__ float score_of(const float* __restrict__ logits, const float* __restrict__ lower,
+                                          const float* __restrict__ upper, long long i) {
+  float s = 1.f / (1.f + expf(-logits[i]));  // torch.sigmoid
+  if (upper) s = fminf(s, upper[i]);         // cpn.py:118-123 (upper first, then lower)
+  if (lower) s = fmaxf(s, lower[i]);
+  return s;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_count_kernel(const float* __restrict__ logits,
+                                                                   const float* __restrict__ lower,
+                                                                   const float* __restrict__ upper, long long pixels,
+                                                                   float thresh, int* __restrict__ block_counts) {
+  __shared__ int warp_sums[SEL_THREADS / 32];
+  const long long base = (long long)blockIdx.x * SEL_CHUNK + threadIdx.x * SEL_PER_THREAD;
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < SEL_PER_THREAD; ++j) {
+    const long long i = base + j;
+    if (i < pixels) cnt += score_of(logits, lower, upper, i) > thresh ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < SEL_THREADS / 32; ++w) t += warp_sums[w];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of block_counts -> block_offsets[0..nblocks) (int64), block_offsets[nblocks] = total
+__global__ void __launch_bounds__(1024) select_scan_kernel(const int* __restrict__ block_counts, int nblocks,
+                                                           long long* __restrict__ block_offsets,
+                                                           long long* __restrict__ total) {
+  __shared__ long long warp_tot[32];
+  __shared__ long long carry_s, chunk_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+    const int b = b0 + threadIdx.x;
+    const long long v = b < nblocks ? block_counts[b] : 0;
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const long long w = warp_tot[lane];
+      long long winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      warp_tot[lane] = winc - w;  // exclusive offset of each warp inside this chunk
+      if (lane == 31) chunk_s = winc;
+    }
+    __syncthreads();
+    if (b < nblocks) block_offsets[b] = carry_s + warp_tot[warp] + (inc - v);
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += chunk_s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    block_offsets[nblocks] = carry_s;
+    *total = carry_s;
+  }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_write_kernel(const float* __restrict__ logits,
+                                                                   const float* __restrict__ lower,
+                                                                   const float* __restrict__ upper, long long pixels,
+                                                                   float thresh,
+                                                                   const long long* __restrict__ block_offsets,
+                                                                   int32_t* __restrict__ idx, float* __restrict__ score,
+                                                                   long long capacity) {
+  __shared__ int warp_sums[SEL_THREADS / 32];
+  const long long base = (long long)blockIdx.x * SEL_CHUNK + threadIdx.x * SEL_PER_THREAD;
+  float sc[SEL_PER_THREAD];
+  bool fg[SEL_PER_THREAD];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < SEL_PER_THREAD; ++j) {
+    const long long i = base + j;
+    sc[j] = 0.f;
+    fg[j] = false;
+    if (i < pixels) {
+      sc[j] = score_of(logits, lower, upper, i);
+      fg[j] = sc[j] > thresh;
+    }
+    cnt += fg[j] ? 1 : 0;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += warp_sums[w];
+  long long pos = block_offsets[blockIdx.x] + woff + (inc - cnt);
+#pragma unroll
+  for (int j = 0; j < SEL_PER_THREAD; ++j) {
+    if (fg[j]) {
+      if (pos < capacity) {
+        idx[pos] = (int32_t)(base + j);
+        score[pos] = sc[j];
+      }
+      ++pos;
+    }
+  }
+}
+
+// seg_offsets[n] = lower_bound(idx, n * hw) for n in [0, N]
+__global__ void select_segments_kernel(const int32_t* __restrict__ idx, const long long* __restrict__ total_p,
+                                       long long capacity, int n_images, long long hw,
+                                       int32_t* __restrict__ seg_offsets) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n > n_images) return;
+  long long total = *total_p;
+  if (total > capacity) total = capacity;
+  const long long key = (long long)n * hw;
+  long long lo = 0, hi = total;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((long long)idx[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  seg_offsets[n] = (int32_t)lo;
+}
+
+}  // namespace cpn
+
+using namespace cpn;
+
+extern "C" size_t cpn_select_workspace_bytes(int64_t pixels) {
+  const int64_t nblocks = (pixels + SEL_CHUNK - 1) / SEL_CHUNK;
+  // block_counts int32[nblocks] (padded to 8) + block_offsets int64[nblocks + 1] + total int64
+  return (size_t)(((nblocks * 4 + 15) / 16) * 16 + (nblocks + 2) * 8 + 64);
+}
+
+static inline void select_ws(void* ws, int64_t pixels, int** counts, long long** offsets) {
+  const int64_t nblocks = (pixels + SEL_CHUNK - 1) / SEL_CHUNK;
+  *counts = reinterpret_cast<int*>(ws);
+  *offsets = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + ((nblocks * 4 + 15) / 16) * 16);
+}
+
+extern "C" int cpn_select_count(const float* logits, const float* lower, const float* upper, int64_t pixels,
+                                float thresh, void* workspace, int64_t* total_dev, void* stream) {
+  CPN_REQUIRE(pixels > 0 && pixels < (1ll << 31), "select: pixels %lld out of range", (long long)pixels);
+  cudaStream_t st = (cudaStream_t)stream;
+  int* counts; long long* offsets;
+  select_ws(workspace, pixels, &counts, &offsets);
+  const int nblocks = (int)((pixels + SEL_CHUNK - 1) / SEL_CHUNK);
+  select_count_kernel<<<nblocks, SEL_THREADS, 0, st>>>(logits, lower, upper, pixels, thresh, counts);
+  CPN_CHECK_LAUNCH();
+  select_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, offsets, reinterpret_cast<long long*>(total_dev));
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cpn_select_write(const float* logits, const float* lower, const float* upper, int n_images, int64_t hw,
+                                float thresh, void* workspace, int32_t* idx, float* score, int64_t capacity,
+                                int32_t* seg_offsets, void* stream) {
+  const int64_t pixels = (int64_t)n_images * hw;
+  CPN_REQUIRE(pixels > 0 && pixels < (1ll << 31), "select: pixels %lld out of range", (long long)pixels);
+  cudaStream_t st = (cudaStream_t)stream;
+  int* counts; long long* offsets;
+  select_ws(workspace, pixels, &counts, &offsets);
+  const int nblocks = (int)((pixels + SEL_CHUNK - 1) / SEL_CHUNK);
+  select_write_kernel<<<nblocks, SEL_THREADS, 0, st>>>(logits, lower, upper, pixels, thresh, offsets, idx, score,
+                                                       capacity);
+  CPN_CHECK_LAUNCH();
+  select_segments_kernel<<<(n_images + 1 + 127) / 128, 128, 0, st>>>(idx, offsets + nblocks, capacity, n_images, hw,
+                                                                     seg_offsets);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// decode + refine (one warp per proposal)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace cpn {
+
+constexpr int DEC_WARPS = 8, DEC_MAX_ORDER = 32, DEC_MAX_SPL = 8;  // samples <= 32 * DEC_MAX_SPL
+
+struct DecodeParams {
+  const int32_t* idx;
+  long long P;
+  const float* locfou;
+  int order_core, order, n_images, h, w, H, W;
+  const float* trig;
+  int samples;
+  const float* refinement;
+  int iters;
+  const float* offsets;
+  float *contours, *proposals, *boxes, *locations, *fourier_out;
+  int trig_in_smem;
+};
+
+__global__ void __launch_bounds__(DEC_WARPS * 32) decode_refine_kernel(const DecodeParams p) {
+  extern __shared__ float dsm[];
+  float* trig_s = dsm;  // [2][order][samples] when trig_in_smem
+  const int trig_n = 2 * p.order * p.samples;
+  float* rec_s = dsm + (p.trig_in_smem ? trig_n : 0);  // [DEC_WARPS][2 + 4 * order]
+  if (p.trig_in_smem)
+    for (int i = threadIdx.x; i < trig_n; i += blockDim.x) trig_s[i] = p.trig[i];
+  __syncthreads();
+  const float* trig = p.trig_in_smem ? trig_s : p.trig;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rec_len = 2 + 4 * p.order;
+  const int rec_core = 2 + 4 * p.order_core;
+  float* rec = rec_s + warp * (2 + 4 * DEC_MAX_ORDER);
+  const long long hw = (long long)p.h * p.w;
+  // scale = original / actual, xy order (ops/cpn.py:98-104); computed in fp32 like torch.as_tensor(...)/...
+  const float sx = (float)p.W / (float)p.w, sy = (float)p.H / (float)p.h;
+  const float xmax = (float)(p.W - 1), ymax = (float)(p.H - 1);
+
+  for (long long pr = (long long)blockIdx.x * DEC_WARPS + warp; pr < p.P; pr += (long long)gridDim.x * DEC_WARPS) {
+    const long long pix = p.idx[pr];
+    const int b = (int)(pix / hw);
+    const int rem = (int)(pix - (long long)b * hw);
+    const int py = rem / p.w, px = rem - py * p.w;
+    __syncwarp();
+    for (int i = lane; i < rec_len; i += 32) rec[i] = p.locfou[pix * rec_core + i];
+    __syncwarp();
+    // rel -> abs location (ops/cpn.py:15-41): x += column index, y += row index
+    const float lx = rec[0] + (float)px, ly = rec[1] + (float)py;
+    float ox = 0.f, oy = 0.f;
+    if (p.offsets) { ox = p.offsets[b * 2]; oy = p.offsets[b * 2 + 1]; }
+
+    float bx0 = INFINITY, by0 = INFINITY, bx1 = -INFINITY, by1 = -INFINITY;
+    for (int s = lane; s < p.samples; s += 32) {
+      // con = (0 + loc) + sum_k f[k,(1,3)] * sin + sum_k f[k,(0,2)] * cos   (ops/cpn.py:92-94, sequential in k)
+      float ssx = 0.f, ssy = 0.f, scx = 0.f, scy = 0.f;
+      const float* tc = trig + s;
+      const float* ts = trig + p.order * p.samples + s;
+      for (int k = 0; k < p.order; ++k) {
+        const float c = tc[k * p.samples], sn = ts[k * p.samples];
+        const float* f = rec + 2 + 4 * k;
+        ssx = ssx + f[1] * sn;
+        ssy = ssy + f[3] * sn;
+        scx = scx + f[0] * c;
+        scy = scy + f[2] * c;
+      }
+      float cx = (lx + ssx) + scx, cy = (ly + ssy) + scy;
+      cx = cx * sx;  // scale_contours
+      cy = cy * sy;
+      if (p.proposals) {
+        float qx = cx, qy = cy;
+        if (!(p.refinement && p.iters > 0)) {  // proposals alias contours when refinement is off (cpn.py:658-663)
+          qx = fminf(fmaxf(qx, 0.f), xmax);
+          qy = fminf(fmaxf(qy, 0.f), ymax);
+          if (p.offsets) { qx = qx + ox; qy = qy + oy; }  // added twice in the reference (same tensor, cpn.py:698-699)
+        }
+        if (p.offsets) { qx = qx + ox; qy = qy + oy; }
+        reinterpret_cast<float2*>(p.proposals)[pr * p.samples + s] = make_float2(qx, qy);
+      }
+      if (p.refinement && p.iters > 0) {  // models/cpn.py:63-85
+        const float2* ref = reinterpret_cast<const float2*>(p.refinement) + (long long)b * p.H * p.W;
+        for (int it = 0; it < p.iters; ++it) {
+          float rx = rintf(cx), ry = rintf(cy);  // torch.round: half to even
+          rx = fminf(fmaxf(rx, 0.f), xmax);
+          ry = fminf(fmaxf(ry, 0.f), ymax);
+          const float2 d = __ldg(ref + (long long)((int)ry) * p.W + (int)rx);
+          cx = rx + d.x;
+          cy = ry + d.y;
+        }
+      }
+      cx = fminf(fmaxf(cx, 0.f), xmax);  // cpn.py:661-663
+      cy = fminf(fmaxf(cy, 0.f), ymax);
+      bx0 = fminf(bx0, cx); by0 = fminf(by0, cy); bx1 = fmaxf(bx1, cx); by1 = fmaxf(by1, cy);
+      if (p.contours) {
+        float qx = cx, qy = cy;
+        if (p.offsets) {
+          qx = qx + ox; qy = qy + oy;
+          if (!(p.refinement && p.iters > 0)) { qx = qx + ox; qy = qy + oy; }
+        }
+        reinterpret_cast<float2*>(p.contours)[pr * p.samples + s] = make_float2(qx, qy);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+      by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+      bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+      by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    if (lane == 0) {
+      if (p.boxes) reinterpret_cast<float4*>(p.boxes)[pr] = make_float4(bx0 + ox, by0 + oy, bx1 + ox, by1 + oy);
+      if (p.locations) reinterpret_cast<float2*>(p.locations)[pr] = make_float2(lx * sx + ox, ly * sy + oy);
+    }
+    if (p.fourier_out) {  // scale_fourier: cols (0,1) * sx, (2,3) * sy (ops/cpn.py:133-137)
+      for (int i = lane; i < 4 * p.order; i += 32)
+        p.fourier_out[pr * 4 * p.order + i] = rec[2 + i] * (((i & 3) < 2) ? sx : sy);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stand-alone fouriers2contours, default sampling: register-tiled, uses t_{S-1-s} = 1 - t_s (cos even, sin odd) so
+// each (cos, sin) partial sum serves two output samples.  Thread tile: 4 proposals x up to 4 sample pairs.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int F2C_TX = 16, F2C_TY = 8, F2C_TP = 4, F2C_PB = F2C_TY * F2C_TP;  // 32 proposals per block iteration
+
+__global__ void __launch_bounds__(F2C_TX * F2C_TY) f2c_tiled_kernel(const float* __restrict__ fourier,
+                                                                    const float* __restrict__ locations, long long P,
+                                                                    int order, int samples,
+                                                                    const float* __restrict__ trig,
+                                                                    float* __restrict__ out) {
+  extern __shared__ float fsm[];
+  const int np = (samples + 1) / 2;  // sample pairs (s, S-1-s); the middle sample of an odd S pairs with itself
+  float* cos_s = fsm;                 // [order][np]
+  float* sin_s = fsm + order * np;    // [order][np]
+  float* coef = fsm + ((2 * order * np + 3) & ~3);  // [F2C_PB][order * 4 + 4] (+2 used: location), 16-byte aligned
+  const int cstride = order * 4 + 4;
+  for (int i = threadIdx.x; i < order * np; i += blockDim.x) {
+    const int k = i / np, j = i - k * np;
+    cos_s[i] = trig[k * samples + j];
+    sin_s[i] = trig[(order + k) * samples + j];
+  }
+  const int tx = threadIdx.x % F2C_TX, ty = threadIdx.x / F2C_TX;
+  const long long nblk = (P + F2C_PB - 1) / F2C_PB;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const long long p0 = blk * F2C_PB;
+    __syncthreads();
+    // stage coefficients (coalesced: the fourier rows of 32 consecutive proposals are contiguous)
+    const long long nf = min((long long)F2C_PB, P - p0) * order * 4;
+    for (long long i = threadIdx.x; i < nf; i += blockDim.x) {
+      const int pl = (int)(i / (order * 4)), r = (int)(i - (long long)pl * order * 4);
+      coef[pl * cstride + r] = __ldg(fourier + p0 * order * 4 + i);
+    }
+    for (int i = threadIdx.x; i < F2C_PB * 2; i += blockDim.x) {
+      const int pl = i >> 1;
+      if (p0 + pl < P) coef[pl * cstride + order * 4 + (i & 1)] = __ldg(locations + (p0 + pl) * 2 + (i & 1));
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < np; j0 += F2C_TX * 4) {
+      float cx[F2C_TP][4], sx_[F2C_TP][4], cy[F2C_TP][4], sy_[F2C_TP][4];
+#pragma unroll
+      for (int a = 0; a < F2C_TP; ++a)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cx[a][q] = sx_[a][q] = cy[a][q] = sy_[a][q] = 0.f;
+      for (int k = 0; k < order; ++k) {
+        float c[4], s[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = j0 + tx + q * F2C_TX;
+          c[q] = j < np ? cos_s[k * np + j] : 0.f;
+          s[q] = j < np ? sin_s[k * np + j] : 0.f;
+        }
+#pragma unroll
+        for (int a = 0; a < F2C_TP; ++a) {
+          const float4 f = *reinterpret_cast<const float4*>(coef + (ty * F2C_TP + a) * cstride + k * 4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            cx[a][q] = __fmaf_rn(f.x, c[q], cx[a][q]);
+            sx_[a][q] = __fmaf_rn(f.y, s[q], sx_[a][q]);
+            cy[a][q] = __fmaf_rn(f.z, c[q], cy[a][q]);
+            sy_[a][q] = __fmaf_rn(f.w, s[q], sy_[a][q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < F2C_TP; ++a) {
+        const int pl = ty * F2C_TP + a;
+        const long long pr = p0 + pl;
+        if (pr >= P) continue;
+        const float lx = coef[pl * cstride + order * 4], ly = coef[pl * cstride + order * 4 + 1];
+        float2* o = reinterpret_cast<float2*>(out) + pr * samples;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = j0 + tx + q * F2C_TX;
+          if (j >= np) continue;
+          o[j] = make_float2((lx + sx_[a][q]) + cx[a][q], (ly + sy_[a][q]) + cy[a][q]);
+          const int jm = samples - 1 - j;
+          if (jm != j) o[jm] = make_float2((lx - sx_[a][q]) + cx[a][q], (ly - sy_[a][q]) + cy[a][q]);
+        }
+      }
+    }
+  }
+}
+
+// explicit per-proposal sampling [P, S] (ops/cpn.py:67-71): one warp per proposal, trig evaluated on the fly
+__global__ void __launch_bounds__(256) f2c_sampling_kernel(const float* __restrict__ fourier,
+                                                           const float* __restrict__ locations, long long P, int order,
+                                                           int samples, const float* __restrict__ sampling,
+                                                           float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float two_pi = 6.2831854820251465f;  // float(np.pi) * 2 rounded to fp32
+  for (long long pr = (long long)blockIdx.x * 8 + warp; pr < P; pr += (long long)gridDim.x * 8) {
+    const float lx = locations[pr * 2], ly = locations[pr * 2 + 1];
+    const float* f = fourier + pr * order * 4;
+    for (int s = lane; s < samples; s += 32) {
+      const float t = sampling[pr * samples + s];
+      float ssx = 0.f, ssy = 0.f, scx = 0.f, scy = 0.f;
+      for (int k = 0; k < order; ++k) {
+        const float arg = (two_pi * (float)(k + 1)) * t;
+        const float c = cosf(arg), sn = sinf(arg);
+        ssx = ssx + f[k * 4 + 1] * sn;
+        ssy = ssy + f[k * 4 + 3] * sn;
+        scx = scx + f[k * 4 + 0] * c;
+        scy = scy + f[k * 4 + 2] * c;
+      }
+      reinterpret_cast<float2*>(out)[pr * samples + s] = make_float2((lx + ssx) + scx, (ly + ssy) + scy);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// border filter + gather
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) border_filter_kernel(const float* __restrict__ contours,
+                                                            const int32_t* __restrict__ tile_of_row,
+                                                            const float* __restrict__ tile_meta, long long K,
+                                                            int samples, float padding, uint8_t* __restrict__ keep) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < K; r += (long long)gridDim.x * 8) {
+    const float* m = tile_meta + (long long)tile_of_row[r] * 8;
+    const float offx = m[0], offy = m[1], h = m[2], w = m[3];
+    const bool top = m[4] != 0.f, right = m[5] != 0.f, bottom = m[6] != 0.f, left = m[7] != 0.f;
+    bool ok = true;
+    for (int s = lane; s < samples; s += 32) {
+      const float2 v = reinterpret_cast<const float2*>(contours)[r * samples + s];
+      const float x = v.x + (-offx), y = v.y + (-offy);  // contours + offsets with offsets = -tile offset
+      if (top) ok = ok && (y > padding);
+      if (right) ok = ok && (x < (w - padding));
+      if (bottom) ok = ok && (y < (h - padding));
+      if (left) ok = ok && (x > padding);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) keep[r] = ok ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint32_t* __restrict__ src, long long row_words,
+                                                          const int32_t* __restrict__ index, long long n_rows,
+                                                          uint32_t* __restrict__ dst) {
+  const long long total = n_rows * row_words;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / row_words, c = i - r * row_words;
+    dst[i] = src[(long long)index[r] * row_words + c];
+  }
+}
+
+static inline int capped_grid(long long blocks, int per_sm) {
+  const long long cap = (long long)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace cpn
+
+extern "C" int cpn_decode_refine(const int32_t* idx, int64_t P, const float* locfou, int order_core, int order,
+                                 int n_images, int h, int w, int H, int W, const float* trig, int samples,
+                                 const float* refinement, int iters, const float* offsets, float* contours,
+                                 float* proposals, float* boxes, float* locations, float* fourier_out, void* stream) {
+  CPN_REQUIRE(order >= 1 && order <= DEC_MAX_ORDER && order <= order_core, "decode: order %d out of range (core %d)",
+              order, order_core);
+  CPN_REQUIRE(samples >= 1, "decode: samples must be >= 1");
+  if (P <= 0) return 0;
+  DecodeParams p;
+  p.idx = idx; p.P = P; p.locfou = locfou; p.order_core = order_core; p.order = order; p.n_images = n_images;
+  p.h = h; p.w = w; p.H = H; p.W = W; p.trig = trig; p.samples = samples; p.refinement = refinement; p.iters = iters;
+  p.offsets = offsets; p.contours = contours; p.proposals = proposals; p.boxes = boxes; p.locations = locations;
+  p.fourier_out = fourier_out;
+  const size_t trig_bytes = (size_t)2 * order * samples * sizeof(float);
+  const size_t rec_bytes = (size_t)DEC_WARPS * (2 + 4 * DEC_MAX_ORDER) * sizeof(float);
+  p.trig_in_smem = trig_bytes + rec_bytes <= 48 * 1024;
+  const size_t smem = rec_bytes + (p.trig_in_smem ? trig_bytes : 0);
+  const int grid = capped_grid((P + DEC_WARPS - 1) / DEC_WARPS, 8);
+  decode_refine_kernel<<<grid, DEC_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cpn_fouriers2contours(const float* fourier, const float* locations, int64_t P, int order, int samples,
+                                     const float* trig, const float* sampling, float* out, void* stream) {
+  CPN_REQUIRE(order >= 1 && samples >= 1, "fouriers2contours: bad order/samples");
+  CPN_REQUIRE((trig != nullptr) != (sampling != nullptr), "fouriers2contours: pass exactly one of trig / sampling");
+  if (P <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sampling) {
+    f2c_sampling_kernel<<<capped_grid((P + 7) / 8, 8), 256, 0, st>>>(fourier, locations, P, order, samples, sampling,
+                                                                     out);
+    CPN_CHECK_LAUNCH();
+    return 0;
+  }
+  const int np = (samples + 1) / 2;
+  const size_t smem = ((size_t)((2 * order * np + 3) & ~3) + (size_t)F2C_PB * (order * 4 + 4)) * sizeof(float);
+  CPN_REQUIRE(smem <= 200 * 1024, "fouriers2contours: order*samples too large for shared memory (%zu B)", smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(f2c_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const long long nblk = (P + F2C_PB - 1) / F2C_PB;
+  f2c_tiled_kernel<<<capped_grid(nblk, 8), F2C_TX * F2C_TY, smem, st>>>(fourier, locations, P, order, samples, trig,
+                                                                        out);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cpn_border_filter(const float* contours, const int32_t* tile_of_row, const float* tile_meta, int64_t K,
+                                 int samples, float padding, uint8_t* keep, void* stream) {
+  if (K <= 0) return 0;
+  border_filter_kernel<<<capped_grid((K + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>(contours, tile_of_row, tile_meta,
+                                                                                      K, samples, padding, keep);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cpn_gather_rows(const void* src, int64_t row_bytes, const int32_t* index, int64_t n_rows, void* dst,
+                               void* stream) {
+  CPN_REQUIRE(row_bytes > 0 && row_bytes % 4 == 0, "gather_rows: row_bytes must be a positive multiple of 4");
+  if (n_rows <= 0) return 0;
+  const long long total = n_rows * (row_bytes / 4);
+  gather_rows_kernel<<<capped_grid((total + 255) / 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint32_t*>(src), row_bytes / 4, index, n_rows, reinterpret_cast<uint32_t*>(dst));
+  CPN_CHECK_LAUNCH();
+  return 0;
+}

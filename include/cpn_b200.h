@@ -1,0 +1,183 @@
+/*
+ * cpn_b200.h -- C ABI of the B200-native Contour Proposal Network inference path.
+ *
+ * The reference (FZJ-INM1-BDA/celldetection) is pure Python and has no FFI layer; its boundary for this path is the
+ * public Python API.  This header is the C boundary a host in any language binds instead: plain device
+ * pointers + sizes + a cudaStream_t (passed as void*), int status return (0 = ok) and cpn_last_error().  No torch
+ * types appear in any signature.  Each entry point cites the reference code it replaces (paths relative to
+ * /root/reference/celldetection unless noted).  The ctypes binding the reference side would add is shown in
+ * INTEGRATION.md; celldetection_b200/_lib.py is that binding for this repository.
+ *
+ * All pointers are DEVICE pointers unless a parameter name ends in _host.  All kernels are enqueued on `stream` and
+ * return without synchronising unless stated.
+ */
+#ifndef CPN_B200_H
+#define CPN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPN_B200_ABI_VERSION 1
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* status / diagnostics                                                                                             */
+/* ---------------------------------------------------------------------------------------------------------------- */
+int cpn_abi_version(void);
+/* Thread-local message of the last failing call (never NULL). */
+const char* cpn_last_error(void);
+/* Number of kernels this library has launched since load (all streams); feeds bench.py's "gpu_launches". */
+int64_t cpn_launch_count(void);
+/* Fills name[0..n) with the device name and returns the SM count of the current device (or <0 on error). */
+int cpn_device_info(char* name_host, int n, int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* layer plan: backbone + heads (replaces CPNCore.forward, models/cpn.py:238-283, and everything below it:           */
+/* models/unet.py:29-58,178-249, models/resnet.py:56-290, models/fpn.py:50-134, models/commons.py:120-149,461-511,  */
+/* 686-700, i.e. the nn.Conv2d/BatchNorm2d/MaxPool2d/F.interpolate calls into cuDNN/ATen)                           */
+/* ---------------------------------------------------------------------------------------------------------------- */
+
+enum { CPN_DT_F32 = 0, CPN_DT_F16 = 1, CPN_DT_U8 = 2 };
+
+/* NHWC view into the activation arena: element (n,y,x,c) lives at
+ *   arena + offset + ((n*h + y)*w + x) * pitch * sizeof(dtype) + c * sizeof(dtype).
+ * `pitch` (in elements) >= c lets a tensor be a channel slice of a wider buffer, which is how torch.cat
+ * (models/unet.py:219-224) is realised without a copy. */
+typedef struct {
+  int64_t offset; /* bytes from arena base (for INPUT/OUTPUT bindings: bytes from the bound pointer) */
+  int32_t n, h, w, c;
+  int32_t pitch;
+  int32_t dtype;  /* CPN_DT_* */
+} cpn_view_t;
+
+enum {
+  CPN_OP_PREP = 0,      /* network input -> NHWC activations; fuses Normalize's range check (commons.py:694-700),
+                           uint8 -> float / 255 (lightning_base.py:774-780) and the layout change */
+  CPN_OP_CONV = 1,      /* conv (+ folded BN) (+ residual) (+ ReLU)  */
+  CPN_OP_MAXPOOL = 2,   /* nn.MaxPool2d(k, stride, pad), -inf padding */
+  CPN_OP_UPSAMPLE = 3,  /* F.interpolate(mode='nearest'): src = floor(dst * in / out) */
+  CPN_OP_BILINEAR = 4,  /* F.interpolate(mode='bilinear', align_corners=False) (models/cpn.py:109-115) */
+  CPN_OP_PROJ = 5       /* ReadOut's final 1x1 conv (+ ScaledTanh) to fp32 head tensors (commons.py:494-511) */
+};
+
+enum { CPN_IN_F32_NCHW = 0, CPN_IN_U8_NCHW = 1, CPN_IN_U8_NHWC = 2 };
+enum { CPN_ACT_NONE = 0, CPN_ACT_RELU = 1, CPN_ACT_SCALED_TANH = 2 };
+/* conv engines */
+enum { CPN_ENGINE_SIMT = 0, CPN_ENGINE_TCGEN05 = 1 };
+
+typedef struct {
+  int32_t kind;          /* CPN_OP_* */
+  int32_t engine;        /* CONV only: CPN_ENGINE_* */
+  cpn_view_t src;        /* PREP: describes the *logical* input (n,h,w,c); the pointer is bound at forward time */
+  cpn_view_t dst;
+  cpn_view_t res;        /* CONV: optional residual (n == 0 -> none).  If res.h/res.w differ from dst.h/dst.w the
+                            residual is read through nearest up-sampling (torchvision FPN top-down path). */
+  int64_t w_offset;      /* CONV/PROJ: bytes into the weight blob.
+                            SIMT   : float  [R*S][kslab][cout]
+                            TCGEN05: __half [R*S][cout][kslab]   (K-major, TMA box {64, BN, 1})
+                            PROJ   : float  [cout][cin_slice]    */
+  int64_t b_offset;      /* CONV/PROJ: bytes into the weight blob of float bias[cout] (-1 -> no bias) */
+  int32_t r, s, stride, pad;
+  int32_t kslab;         /* input channels each 64-wide output-channel slab contracts over: cin for dense convs,
+                            max(64, cin/groups) for grouped convs (block-diagonal weights are expanded to the slab) */
+  int32_t slab_mode;     /* 0: dense (slab base 0); 1: grouped (slab base = (n0 / kslab) * kslab) */
+  int32_t act;           /* CPN_ACT_* */
+  float act_scale;       /* ScaledTanh factor (models/commons.py:167-168) */
+  int32_t proj_cin_off;  /* PROJ: first input channel of the slice this projection contracts over */
+  int32_t proj_cin;      /* PROJ: number of input channels */
+  int32_t out_binding;   /* PROJ/any: -1 -> dst is in the arena; >= 0 -> dst is the caller's output pointer #k */
+  int32_t reserved;
+} cpn_op_t;
+
+typedef struct cpn_plan cpn_plan_t;
+
+/* Validates the op list, builds every TMA tensor map / launch configuration once, and keeps device pointers to the
+ * caller-owned weight blob and activation arena (both must outlive the plan; the library never allocates device
+ * memory).  `flags_dev` must point to >= 4 int32 of device memory (bit 0 of flags_dev[0] is set by PREP when an
+ * input value is outside [0, 1] -- the reference raises AssertionError there, commons.py:695-697). */
+int cpn_plan_create(const cpn_op_t* ops_host, int n_ops, const void* weights, size_t weights_bytes, void* arena,
+                    size_t arena_bytes, int32_t* flags_dev, cpn_plan_t** plan_out);
+/* Runs the whole list on `stream`.  `input` is the network input in `input_format`; outputs_host[k] is the device
+ * pointer bound to ops with out_binding == k. */
+int cpn_plan_forward(cpn_plan_t* plan, const void* input, int input_format, void* const* outputs_host, int n_outputs,
+                     void* stream);
+/* Kernel launches one forward of this plan issues. */
+int cpn_plan_num_launches(const cpn_plan_t* plan);
+/* Debug/profiling: run only op `index` (same bindings as forward). */
+int cpn_plan_run_op(cpn_plan_t* plan, int index, const void* input, int input_format, void* const* outputs_host,
+                    int n_outputs, void* stream);
+void cpn_plan_destroy(cpn_plan_t* plan);
+
+/* Stand-alone convolution (same kernels as the plan; used by the per-layer parity tests).  Views are relative to
+ * the given base pointers instead of an arena. */
+int cpn_conv2d(const cpn_op_t* op_host, const void* src_base, void* dst_base, const void* res_base,
+               const void* weights, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* post-head chain (replaces models/cpn.py:575-734 and ops/cpn.py:15-165)                                           */
+/* ---------------------------------------------------------------------------------------------------------------- */
+
+/* Bytes of scratch cpn_select_* needs for a score map with `pixels` = N*h*w entries. */
+size_t cpn_select_workspace_bytes(int64_t pixels);
+
+/* Pass 1 of proposal selection (models/cpn.py:578-579, 616-620): sigmoid(logit) [min upper] [max lower] > thresh.
+ * logits [N,h,w] fp32; lower/upper: optional [N,h,w] fp32 bounds already at head resolution (NULL -> none).
+ * Writes the total number of proposals to total_dev[0] (int64). */
+int cpn_select_count(const float* logits, const float* lower, const float* upper, int64_t pixels, float thresh,
+                     void* workspace, int64_t* total_dev, void* stream);
+/* Pass 2: writes, in torch.where order (n, y, x ascending), the flat pixel index (int32, n*h*w + y*w + x) and the
+ * post-bound score of every proposal, plus seg_offsets[N+1] (int32 row offsets of each image's proposals).
+ * `capacity` rows are available in idx/score; must be >= the total from pass 1 (same workspace, same inputs). */
+int cpn_select_write(const float* logits, const float* lower, const float* upper, int n_images, int64_t hw,
+                     float thresh, void* workspace, int32_t* idx, float* score, int64_t capacity,
+                     int32_t* seg_offsets, void* stream);
+
+/* Decode + rescale + local refinement + clamp + boxes + offsets for P selected pixels in one kernel
+ * (ops/cpn.py:15-41 rel->abs, :44-95 inverse DFT, :98-165 rescale; models/cpn.py:63-85 refinement, :661-670 clamp
+ * and boxes, :695-702 offsets).
+ *   idx        [P] int32 flat pixel indices into the head maps
+ *   locfou     [N,h,w,2+4*order_core] fp32 records: (loc_x, loc_y, fourier[order_core][4]) per pixel
+ *   trig       [2][order][samples] fp32: cos then sin of 2*pi*k*t_s (host computes it exactly as ops/cpn.py:74-81)
+ *   refinement [N,H,W,2] fp32 (x then y displacement, already 3*tanh) or NULL
+ *   offsets    [N,2] fp32 (x, y) or NULL
+ * outputs (any may be NULL): contours [P,S,2], proposals [P,S,2], boxes [P,4], locations [P,2], fourier [P,order,4] */
+int cpn_decode_refine(const int32_t* idx, int64_t P, const float* locfou, int order_core, int order, int n_images,
+                      int h, int w, int H, int W, const float* trig, int samples, const float* refinement, int iters,
+                      const float* offsets, float* contours, float* proposals, float* boxes, float* locations,
+                      float* fourier_out, void* stream);
+
+/* ops.cpn.fouriers2contours (ops/cpn.py:44-95): fourier [P,order,4], locations [P,2] -> out [P,samples,2].
+ * trig as above; or sampling [P,samples] (per-proposal t, :67-71) with trig == NULL. */
+int cpn_fouriers2contours(const float* fourier, const float* locations, int64_t P, int order, int samples,
+                          const float* trig, const float* sampling, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* NMS (replaces torch.ops.torchvision.nms as called by ops/cpn.py:189-227 and cpn_inference.py:405-408)            */
+/* ---------------------------------------------------------------------------------------------------------------- */
+size_t cpn_nms_workspace_bytes(int64_t n_boxes, int n_segments);
+/* Greedy NMS per segment with torchvision semantics: stable descending score order, suppress when IoU > thr (strict,
+ * NaN never suppresses), areas without +1.  seg_offsets [n_segments+1] int32 (device).  Segments larger than
+ * `chunk` follow ops/cpn.py:213-224 (NMS per chunk, then NMS over the survivors); chunk <= 0 disables the rule.
+ * keep [n_boxes] int32 receives, per segment and packed at the segment's offset, the kept GLOBAL row indices in
+ * descending score order; keep_counts [n_segments] int32 the number kept. */
+int cpn_nms_segments(const float* boxes, const float* scores, const int32_t* seg_offsets, int n_segments,
+                     int64_t n_boxes, float iou_threshold, int chunk, void* workspace, int32_t* keep,
+                     int32_t* keep_counts, void* stream);
+
+/* remove_border_contours (ops/cpn.py:258-290) as called by cpn_inference.py:375-380: keep[i] = 1 iff every vertex of
+ * contour i satisfies the enabled side tests in tile-local coordinates (contours + (-offset)).
+ * contours [K,S,2]; tile_of_row [K] int32 -> row of tile_meta; tile_meta [T,8] float:
+ * (off_x, off_y, h, w, top, right, bottom, left). */
+int cpn_border_filter(const float* contours, const int32_t* tile_of_row, const float* tile_meta, int64_t K, int samples,
+                      float padding, uint8_t* keep, void* stream);
+
+/* dst[i, :] = src[index[i], :] for rows of row_bytes (multiple of 4) bytes (resolve_keep_indices, cpn.py:53-60). */
+int cpn_gather_rows(const void* src, int64_t row_bytes, const int32_t* index, int64_t n_rows, void* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPN_B200_H */
