@@ -1,0 +1,109 @@
+"""ctypes binding of ``libcpn_b200.so`` (the C ABI declared in ``include/cpn_b200.h``).
+
+This is the only place the package touches native code.  There is no CPU fallback: if the shared object is missing
+or a call fails, a ``RuntimeError`` is raised.  Tensors cross the boundary as raw ``data_ptr()`` device pointers plus
+explicit sizes and the current CUDA stream handle.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcpn_b200.so')
+
+ABI_VERSION = 1
+
+# ---- enums (mirror include/cpn_b200.h) -------------------------------------------------------------------------------
+DT_F32, DT_F16, DT_U8 = 0, 1, 2
+OP_PREP, OP_CONV, OP_MAXPOOL, OP_UPSAMPLE, OP_BILINEAR, OP_PROJ = range(6)
+IN_F32_NCHW, IN_U8_NCHW, IN_U8_NHWC = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SCALED_TANH = 0, 1, 2
+ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
+
+
+class View(ctypes.Structure):
+    _fields_ = [('offset', ctypes.c_int64), ('n', ctypes.c_int32), ('h', ctypes.c_int32), ('w', ctypes.c_int32),
+                ('c', ctypes.c_int32), ('pitch', ctypes.c_int32), ('dtype', ctypes.c_int32)]
+
+
+class Op(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int32), ('engine', ctypes.c_int32), ('src', View), ('dst', View), ('res', View),
+                ('w_offset', ctypes.c_int64), ('b_offset', ctypes.c_int64),
+                ('r', ctypes.c_int32), ('s', ctypes.c_int32), ('stride', ctypes.c_int32), ('pad', ctypes.c_int32),
+                ('kslab', ctypes.c_int32), ('slab_mode', ctypes.c_int32), ('act', ctypes.c_int32),
+                ('act_scale', ctypes.c_float), ('proj_cin_off', ctypes.c_int32), ('proj_cin', ctypes.c_int32),
+                ('out_binding', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/cpn_b200.h declares
+_P, _I, _I64, _F, _SZ = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+SYMBOLS = {
+    'cpn_abi_version': (_I, []),
+    'cpn_last_error': (ctypes.c_char_p, []),
+    'cpn_launch_count': (_I64, []),
+    'cpn_device_info': (_I, [ctypes.c_char_p, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I)]),
+    'cpn_plan_create': (_I, [ctypes.POINTER(Op), _I, _P, _SZ, _P, _SZ, _P, ctypes.POINTER(_P)]),
+    'cpn_plan_forward': (_I, [_P, _P, _I, ctypes.POINTER(_P), _I, _P]),
+    'cpn_plan_num_launches': (_I, [_P]),
+    'cpn_plan_run_op': (_I, [_P, _I, _P, _I, ctypes.POINTER(_P), _I, _P]),
+    'cpn_plan_destroy': (None, [_P]),
+    'cpn_conv2d': (_I, [ctypes.POINTER(Op), _P, _P, _P, _P, _P]),
+    'cpn_select_workspace_bytes': (_SZ, [_I64]),
+    'cpn_select_count': (_I, [_P, _P, _P, _I64, _F, _P, _P, _P]),
+    'cpn_select_write': (_I, [_P, _P, _P, _I, _I64, _F, _P, _P, _P, _I64, _P, _P]),
+    'cpn_decode_refine': (_I, [_P, _I64, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
+    'cpn_fouriers2contours': (_I, [_P, _P, _I64, _I, _I, _P, _P, _P, _P]),
+    'cpn_nms_workspace_bytes': (_SZ, [_I64, _I]),
+    'cpn_nms_segments': (_I, [_P, _P, _P, _I, _I64, _F, _I, _P, _P, _P, _P]),
+    'cpn_border_filter': (_I, [_P, _P, _P, _I64, _I, _F, _P, _P]),
+    'cpn_gather_rows': (_I, [_P, _I64, _P, _I64, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared object (once).  Raises if it is missing -- there is deliberately no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} not found: build it with `python -m celldetection_b200.build` (nvcc, sm_100a). '
+            'celldetection_b200 has no CPU or PyTorch fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.cpn_abi_version() != ABI_VERSION:
+        raise RuntimeError(f'libcpn_b200.so ABI {lib.cpn_abi_version()} != expected {ABI_VERSION}; rebuild')
+    _lib = lib
+    return lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = load().cpn_last_error().decode(errors='replace')
+        raise RuntimeError(f'cpn_b200 {what} failed: {msg}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(load().cpn_launch_count())
+
+
+def device_info():
+    lib = load()
+    name = ctypes.create_string_buffer(256)
+    sm, ma, mi = _I(), _I(), _I()
+    check(lib.cpn_device_info(name, 256, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi)), 'device_info')
+    return dict(name=name.value.decode(), sm_count=sm.value, cc=(ma.value, mi.value))

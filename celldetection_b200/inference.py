@@ -1,0 +1,241 @@
+"""Tiled CPN inference over large images: the B200-native counterpart of ``celldetection_scripts.cpn_inference``
+(/root/reference/celldetection_scripts/cpn_inference.py: ``apply_model`` :311-429, ``cpn_inference`` :432-869,
+``TileLoader`` :51-130, ``oom_safe_gather_dict`` :257-308) and ``cd.get_tiling_slices``
+(/root/reference/celldetection/util/util.py:1305-1354).
+
+Semantics kept: tiles from ``get_tiling_slices`` (last tile shifted inward, never padded); per-tile model call with
+``offsets=[w0, h0]``; removal of contours touching a tile border that is not an image border (tile-local test,
+``border_removal`` px); concatenation of all tiles; one global NMS with the model's ``nms_thresh``
+(``stitching_rule='nms'``).  Multi-GPU: tiles are sharded ``i -> rank i % world``; each rank keeps its detections on
+its GPU; ONE padded ``all_gather`` (NCCL over NVLink) exchanges the packed detection records, every rank then runs the
+same global NMS, so every rank returns the identical, complete result (the reference gathers to rank 0 with
+sequential send/recv).  No Lightning, no DataLoader workers: crops are staged through pinned host memory and copied
+asynchronously while the previous batch computes.
+"""
+from collections import OrderedDict
+from itertools import product
+from typing import Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .ops import cpn as O
+
+__all__ = ['get_tiling_slices', 'apply_model', 'cpn_inference']
+
+
+def get_tiling_slices(size: Sequence[int], crop_size: Union[int, Sequence[int]], strides: Union[int, Sequence[int]],
+                      return_overlaps=False):
+    """util/util.py:1305-1354 -> (iterator of slice tuples, [overlaps], tiles per dimension)."""
+    assert isinstance(size, (tuple, list))
+    nd = len(size)
+    crop_size = (crop_size,) * nd if isinstance(crop_size, int) else tuple(crop_size)
+    strides = (strides,) * nd if isinstance(strides, int) else tuple(strides)
+    slices, shape, overlaps = [], [], []
+    for axis in range(nd):
+        if crop_size[axis] >= size[axis]:
+            tl = [size[axis]]
+        else:
+            tl = range(crop_size[axis],
+                       1 + crop_size[axis] + (int(np.ceil((size[axis] - crop_size[axis]) / strides[axis]))) *
+                       strides[axis], strides[axis])
+        stops = np.minimum(tl, size[axis])
+        starts = np.maximum(0, stops - crop_size[axis])
+        overlaps_start = np.concatenate((starts[:1], stops[:-1])) - starts
+        axis_slices, axis_overlaps = [], []
+        for a, b, *ov in zip(starts, stops, overlaps_start, np.concatenate((overlaps_start[1:], [0]))):
+            axis_slices.append(slice(int(a), int(b)))
+            axis_overlaps.append(ov)
+        slices.append(axis_slices), shape.append(len(starts)), overlaps.append(axis_overlaps)
+    if return_overlaps:
+        return product(*slices), product(*overlaps), shape
+    return product(*slices), shape
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+REC_KEYS = ('contours', 'boxes', 'scores', 'classes', 'locations', 'fourier', 'contour_proposals')
+
+
+def pack_records(res: OrderedDict):
+    """Flat per-detection float32 records [K, L] (classes are stored as float; exact for small ints)."""
+    K = int(res['scores'].shape[0])
+    cols = [res[k].reshape(K, -1).float() for k in REC_KEYS]
+    return torch.cat(cols, 1).contiguous(), [c.shape[1] for c in cols]
+
+
+def unpack_records(rec, widths, like: OrderedDict):
+    out, o = OrderedDict(), 0
+    for k, wd in zip(REC_KEYS, widths):
+        v = rec[:, o:o + wd]
+        o += wd
+        shape = (rec.shape[0],) + tuple(like[k].shape[1:])
+        out[k] = v.reshape(shape).long() if k == 'classes' else v.reshape(shape).contiguous()
+    return out
+
+
+def allgather_detections(res: OrderedDict, group=None):
+    """One collective for all keys: all_gather of per-rank counts (world ints) + ONE all_gather of the packed,
+    max-count-padded record buffer; returns the concatenation in rank order on every rank."""
+    dist, rank, world = _dist()
+    if dist is None or world == 1:
+        return res
+    rec, widths = pack_records(res)
+    dev = rec.device
+    cnt = torch.tensor([rec.shape[0]], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    counts = [int(c.item()) for c in cnts]
+    mx = max(max(counts), 1)
+    padded = torch.zeros((mx, rec.shape[1]), dtype=torch.float32, device=dev)
+    padded[:rec.shape[0]] = rec
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)     # the one payload collective (NCCL over NVLink on the GPU box)
+    parts = [gathered[r][:counts[r]] for r in range(world)]
+    return unpack_records(torch.cat(parts, 0), widths, res)
+
+
+def _to_rgb(img):
+    if img.ndim == 2:
+        img = img[..., None]
+    if img.shape[-1] == 1:
+        img = np.repeat(img, 3, axis=-1)   # cv2.COLOR_GRAY2RGB (cpn_inference.py:330-331)
+    return img
+
+
+@torch.no_grad()
+def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size=(768, 768), strides=(384, 384),
+                reps=1, transforms=None, model_kwargs_list=None, batch_size=1, num_workers=0, pin_memory=False,
+                border_removal=4, min_vote=1, stitching_rule='nms', verbose=False, device=None, **kwargs):
+    """cpn_inference.py:311-429.  ``img``: uint8 or float ``Array[h, w, (c)]``; ``models``: a ``CPN`` instance or a
+    list of them.  Returns the flat dict of concatenated tensors (contours, boxes, scores, classes, locations,
+    fourier, contour_proposals) after border removal and global NMS -- identical on every rank when distributed."""
+    if not isinstance(models, (list, tuple)):
+        models = [models]
+    assert len(models) >= 1, 'Please specify at least one model.'
+    if min_vote != 1 or len(models) > 1:
+        raise NotImplementedError('model ensembles / box voting are outside the accelerated path (SURVEY 8f-4).')
+    if mask is not None or point_mask is not None or transforms is not None or reps != 1:
+        raise NotImplementedError('masks, point masks and test-time transforms are outside the accelerated path.')
+    if stitching_rule != 'nms':
+        raise NotImplementedError("only stitching_rule='nms' is implemented")
+    model = models[0]
+    dev = torch.device(device) if device is not None else model.device
+    if dev.type != 'cuda':
+        raise RuntimeError('apply_model needs the model on a CUDA device')
+    if not isinstance(crop_size, (tuple, list)):
+        crop_size = (crop_size,) * 2
+    if not isinstance(strides, (tuple, list)):
+        strides = (strides,) * 2
+    img = _to_rgb(np.asarray(img))
+    if img.dtype.kind == 'f':
+        img = img.astype(np.float32)
+    elif img.dtype != np.uint8:
+        raise ValueError('image must be uint8 or floating point')
+    H, W = img.shape[:2]
+    slices, _, (h_tiles, w_tiles) = get_tiling_slices((H, W), tuple(crop_size), tuple(strides), return_overlaps=True)
+    slices = list(slices)
+    dist, rank, world = _dist()
+    mine = list(range(rank, len(slices), world))
+    th, tw = (slices[0][0].stop - slices[0][0].start), (slices[0][1].stop - slices[0][1].start)
+    nms_thresh = kwargs.get('nms_thresh', model.nms_thresh)
+    is_u8 = img.dtype == np.uint8
+    C = img.shape[-1]
+    # double-buffered pinned staging
+    stage = [torch.empty((batch_size, th, tw, C), dtype=torch.uint8 if is_u8 else torch.float32).pin_memory()
+             for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    acc = []
+
+    def load(bi, slot):
+        ids = mine[bi * batch_size:(bi + 1) * batch_size]
+        buf = stage[slot]
+        for j, t in enumerate(ids):
+            buf[j].copy_(torch.from_numpy(np.ascontiguousarray(img[slices[t]])))
+        with torch.cuda.stream(copy_stream):
+            d = buf[:len(ids)].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ids, d, ev
+
+    nb = (len(mine) + batch_size - 1) // batch_size
+    nxt = load(0, 0) if nb else None
+    for bi in range(nb):
+        ids, d, ev = nxt
+        main.wait_event(ev)
+        if bi + 1 < nb:
+            # the other staging slot was consumed two batches ago (its copy finished before the previous forward)
+            nxt = load(bi + 1, (bi + 1) % 2)
+        offs = torch.tensor([[slices[t][1].start, slices[t][0].start] for t in ids], dtype=torch.float32, device=dev)
+        if is_u8:
+            flat, counts = model.forward_flat(d, L.IN_U8_NHWC, offsets=offs)
+        else:
+            flat, counts = model.forward_flat(d.permute(0, 3, 1, 2).contiguous(), L.IN_F32_NCHW, offsets=offs)
+        K = int(sum(counts))
+        if K == 0:
+            continue
+        meta = []
+        for t in ids:
+            h_i, w_i = np.unravel_index(t, (h_tiles, w_tiles))
+            meta.append([slices[t][1].start, slices[t][0].start, th, tw, float(h_i > 0), float(w_i < w_tiles - 1),
+                         float(h_i < h_tiles - 1), float(w_i > 0)])
+        meta = torch.tensor(meta, dtype=torch.float32, device=dev)
+        tile_of_row = torch.repeat_interleave(torch.arange(len(ids), dtype=torch.int32, device=dev),
+                                              torch.tensor(counts, device=dev))
+        keep = torch.empty((K,), dtype=torch.uint8, device=dev)
+        lib = L.load()
+        L.check(lib.cpn_border_filter(L.ptr(flat['contours']), L.ptr(tile_of_row), L.ptr(meta), K,
+                                      int(flat['contours'].shape[1]), float(border_removal), L.ptr(keep),
+                                      L.stream_ptr()), 'border_filter')
+        sel = torch.nonzero(keep, as_tuple=False).reshape(-1)
+        acc.append(OrderedDict((k, v[sel]) for k, v in flat.items()))
+    if acc:
+        res = OrderedDict((k, torch.cat([a[k] for a in acc], 0)) for k in acc[0].keys())
+    else:
+        S, order = int(model.samples), int(min(model.order, model.core_order))
+        z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
+        res = OrderedDict(contours=z(0, S, 2), boxes=z(0, 4), scores=z(0), classes=z(0, dt=torch.long),
+                          locations=z(0, 2), fourier=z(0, order, 4), contour_proposals=z(0, S, 2))
+    res = allgather_detections(res)
+    if 'nms' in stitching_rule.split(',') and res['boxes'].shape[0] > 0:
+        keep = O.nms(res['boxes'], res['scores'], nms_thresh)
+        res = OrderedDict((k, v[keep]) for k, v in res.items())
+    return res
+
+
+def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, border_removal=4, stitching_rule='nms',
+                  batch_size=1, devices='auto', precision=None, return_results=True, model_parameters=None,
+                  verbose=False, **kwargs):
+    """Programmatic entry point in the spirit of cpn_inference.py:432-869: run tiled inference for each input image
+    (numpy arrays; file I/O, masks, label rasterisation and h5/tif export are outside the hot path).
+    ``models``: CPN instance(s) or a filename loadable by ``load_model``.  Returns ``{index: result dict}``."""
+    from .utils import load_model
+    if not isinstance(inputs, (list, tuple)):
+        inputs = [inputs]
+    if isinstance(models, str):
+        models = load_model(models)
+    model = models[0] if isinstance(models, (list, tuple)) else models
+    if model.device.type != 'cuda':
+        model = model.cuda()
+    if precision in ('32-true', 'fp32'):
+        model.precision = 'fp32'
+    elif precision in ('16-mixed', 'fp16', '16-true'):
+        model.precision = 'fp16'
+    if model_parameters:
+        for k, v in (model_parameters.items() if isinstance(model_parameters, dict) else
+                     [kv.split('=') for kv in model_parameters.split(',')]):
+            setattr(model, k.strip(), type(getattr(model, k.strip()))(v))
+    results = OrderedDict()
+    for i, img in enumerate(inputs):
+        if isinstance(img, str):
+            raise NotImplementedError('file inputs need image I/O, which is outside the accelerated path')
+        results[i] = apply_model(img, [model], crop_size=tile_size, strides=stride, border_removal=border_removal,
+                                 stitching_rule=stitching_rule, batch_size=batch_size, verbose=verbose, **kwargs)
+    return results if return_results else None

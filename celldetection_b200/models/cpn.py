@@ -1,0 +1,333 @@
+"""``cd.models.CPN`` drop-in for the inference path, executing on the C ABI's sm_100a kernels.
+
+Mirrors the public surface of /root/reference/celldetection/models/cpn.py (``CPN`` :287, ``CpnU22`` :772,
+``CpnResNeXt101UNet`` :930, ``CpnResNet18FPN`` :1250): constructor arguments, mutable attributes read on every call
+(``order, nms_thresh, samples, score_thresh, refinement_iterations``, :368-380), ``nn.Module`` semantics with the
+reference's ``state_dict`` key layout, and ``model(inputs, targets=None, nms=True, **kwargs) -> OrderedDict`` of
+per-image lists (:710-734).  Training (``compute_loss``), the uncertainty head, ``classes > 2`` and
+``refinement_buckets > 1`` are outside the accelerated path and raise ``NotImplementedError``.
+
+Nothing here computes on the CPU or with PyTorch operators: modules only *hold* parameters; ``forward`` lowers to
+``cpn_plan_forward`` + the post-head C entry points.  PyTorch supplies device memory, the stream and list plumbing.
+"""
+from collections import OrderedDict
+import math
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .. import _lib as L
+from ..ops import cpn as O
+from .graph import trace, ARCHS
+from .plan import Plan, WeightPack
+
+__all__ = ['CPN', 'CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet']
+
+PRECISIONS = ('fp16', 'fp32')
+
+
+class _Node(nn.Module):
+    """Parameter container mirroring one node of the reference's module tree (never called)."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError('celldetection_b200 modules hold parameters only; call the CPN model itself.')
+
+
+def _get_node(root: nn.Module, path):
+    m = root
+    for p in path:
+        if p not in m._modules:
+            m.add_module(p, _Node())
+        m = m._modules[p]
+    return m
+
+
+class CPN(nn.Module):
+    def __init__(self, backbone: str, in_channels: int = 3, order: int = 5, nms_thresh: float = .2,
+                 score_thresh: float = .9, certainty_thresh: float = None, samples: int = 32, classes: int = 2,
+                 refinement: bool = True, refinement_iterations: int = 4, refinement_margin: float = 3.,
+                 refinement_buckets: int = 1, uncertainty_head=False, precision: str = 'fp16', **kwargs):
+        """Contour Proposal Network (inference).
+
+        Args:
+            backbone: architecture name, one of ``CpnU22 | CpnResNet18FPN | CpnResNeXt101UNet`` (the reference takes a
+                backbone *module*; here the backbone is part of the compiled plan).
+            order, nms_thresh, score_thresh, samples, classes, refinement, refinement_iterations, refinement_margin,
+                refinement_buckets: as in the reference (models/cpn.py:288-321).
+            precision: ``'fp16'`` -- tcgen05 tensor-core engine, fp16 activations/weights, fp32 accumulation (default);
+                ``'fp32'`` -- strict CUDA-core fp32 engine used for parity gating.
+        """
+        super().__init__()
+        if backbone not in ARCHS:
+            raise ValueError(f'Unknown backbone/architecture {backbone!r}; available: {ARCHS}')
+        if classes not in (1, 2):
+            raise NotImplementedError('classes > 2 (softmax/argmax scoring) is outside the accelerated path.')
+        if refinement_buckets != 1:
+            raise NotImplementedError('refinement_buckets > 1 is outside the accelerated path.')
+        if uncertainty_head:
+            raise NotImplementedError('uncertainty_head is outside the accelerated path.')
+        if precision not in PRECISIONS:
+            raise ValueError(f'precision must be one of {PRECISIONS}')
+        self.arch = backbone
+        self.in_channels = in_channels
+        self.order = order
+        self.core_order = order
+        self.nms_thresh = nms_thresh
+        self.samples = samples
+        self.score_thresh = score_thresh
+        self.score_channels = 1
+        self.refinement = refinement
+        self.refinement_iterations = refinement_iterations
+        self.refinement_margin = refinement_margin
+        self.certainty_thresh = certainty_thresh
+        self.uncertainty_nms = False
+        self.precision = precision
+        self.hparams = dict(in_channels=in_channels, order=order, nms_thresh=nms_thresh, score_thresh=score_thresh,
+                            samples=samples, classes=classes, refinement=refinement,
+                            refinement_iterations=refinement_iterations, refinement_margin=refinement_margin,
+                            refinement_buckets=refinement_buckets, **kwargs)
+        # ---- parameters / buffers with the reference's state_dict keys ----
+        g = trace(backbone, 1, 64, 64, in_channels=in_channels, order=order, refinement_margin=refinement_margin)
+        self._spec = g.spec
+        gen = torch.Generator().manual_seed(torch.initial_seed() & 0x7fffffff)
+        for key, (shape, role) in g.spec.items():
+            *path, leaf = key.split('.')
+            node = _get_node(self, path)
+            if role == 'order_weights':
+                x = torch.arange(order).float()
+                spread = max(order - 1, 1)
+                node.register_buffer(leaf, (1 + 4 * (1 - (x / spread).clamp(0., 1.)) ** 2)[:, None])  # ops/cpn.py:230-235
+            elif role == 'conv_w':
+                w = torch.empty(shape)
+                fan_in = shape[1] * shape[2] * shape[3]
+                a = 1. if ('.unet.' in key or '.fpn.' in key) else math.sqrt(5.)  # unet.py:171-176, fpn.py:125-129
+                bound = math.sqrt(6. / ((1 + a * a) * fan_in))
+                w.uniform_(-bound, bound, generator=gen)
+                node.register_parameter(leaf, nn.Parameter(w))
+            elif role == 'conv_b':
+                wshape = g.spec[key[:-len('bias')] + 'weight'][0]
+                fan_in = wshape[1] * wshape[2] * wshape[3]
+                b = torch.zeros(shape)
+                if not ('.unet.' in key or '.fpn.' in key):
+                    bound = 1. / math.sqrt(fan_in)
+                    b.uniform_(-bound, bound, generator=gen)
+                node.register_parameter(leaf, nn.Parameter(b))
+            elif role in ('bn_w', 'bn_w_res'):
+                node.register_parameter(leaf, nn.Parameter(torch.ones(shape)))
+            elif role == 'bn_b':
+                node.register_parameter(leaf, nn.Parameter(torch.zeros(shape)))
+            elif role == 'bn_rm':
+                node.register_buffer(leaf, torch.zeros(shape))
+            elif role == 'bn_rv':
+                node.register_buffer(leaf, torch.ones(shape))
+            elif role == 'bn_nbt':
+                node.register_buffer(leaf, torch.tensor(0, dtype=torch.long))
+            else:  # pragma: no cover
+                raise AssertionError(role)
+        self.eval()
+        self._packs = {}
+        self._plans = {}
+        self._ws = {}
+
+    # ---- plan management ------------------------------------------------------------------------------------------
+    def invalidate_plans(self):
+        """Drop packed weights / compiled plans (call after modifying parameters in place)."""
+        self._packs.clear()
+        self._plans.clear()
+        self._ws.clear()
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self.invalidate_plans()
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        if hasattr(self, '_packs'):
+            self.invalidate_plans()
+        return r
+
+    @property
+    def device(self):
+        return self.order_weights.device
+
+    def _plan(self, n, h, w) -> Plan:
+        dev = self.device
+        if dev.type != 'cuda':
+            raise RuntimeError('celldetection_b200.CPN runs on CUDA (sm_100a) only: move the model with .cuda(). '
+                               'There is no CPU fallback.')
+        fast = self.precision == 'fp16'
+        key = (n, h, w, fast)
+        plan = self._plans.get(key)
+        if plan is None:
+            g = trace(self.arch, n, h, w, in_channels=self.in_channels, order=self.core_order,
+                      refinement_margin=self.refinement_margin)
+            pack = self._packs.get(fast)
+            if pack is None:
+                with torch.no_grad():
+                    pack = WeightPack(g, self.state_dict(), fast, dev)
+                self._packs[fast] = pack
+            if len(self._plans) >= 4:
+                self._plans.pop(next(iter(self._plans)))
+            plan = Plan(g, pack, fast, dev)
+            self._plans[key] = plan
+        return plan
+
+    # ---- raw head tensors (debug / parity) ------------------------------------------------------------------------
+    def core_forward(self, inputs: Tensor):
+        """Raw head tensors in the reference's layout: scores [N,1,h,w], locations [N,2,h,w], refinement [N,2,H,W],
+        fourier [N,4*order,h,w] (CPNCore.forward, models/cpn.py:238-283)."""
+        plan, (sc, lf, rf), _ = self._run_plan(inputs)
+        if int(plan.flags[0].item()) & 1:
+            raise AssertionError('Inputs should be in interval (0.0, 1.0)')
+        return OrderedDict(scores=sc[:, None], locations=lf[..., :2].permute(0, 3, 1, 2),
+                           refinement=rf.permute(0, 3, 1, 2), fourier=lf[..., 2:].permute(0, 3, 1, 2))
+
+    # ---- post-head chain on head tensors --------------------------------------------------------------------------
+    def post_flat(self, scores: Tensor, locfou: Tensor, refinement: Tensor, original_size, nms=True, offsets=None,
+                  scores_lower_bound=None, scores_upper_bound=None, flags: Tensor = None):
+        """models/cpn.py:575-734 on device tensors: scores [N,h,w] logits, locfou [N,h,w,2+4*order_core] records,
+        refinement [N,H,W,2] (or None).  Returns (flat dict of concatenated tensors, rows per image)."""
+        lib = L.load()
+        dev = scores.device
+        n, h, w = scores.shape
+        H, W = original_size
+        order = min(int(self.order), int(self.core_order))
+        samples = int(self.samples)
+        pixels = n * h * w
+        st = L.stream_ptr()
+        lo = up = None
+        if scores_upper_bound is not None or scores_lower_bound is not None:
+            import torch.nn.functional as F  # bounds resize (cpn.py:118-123) -- input-side feature, not a hot kernel
+
+            def prep(bnd):
+                if bnd is None:
+                    return None
+                assert bnd.dtype.is_floating_point, 'score bounds must be floating point'
+                bnd = bnd.to(dev).float()
+                if tuple(bnd.shape[2:]) != (h, w):
+                    bnd = F.interpolate(bnd, (h, w), mode='bilinear', align_corners=False)
+                return bnd.reshape(n, h, w).contiguous()
+            lo, up = prep(scores_lower_bound), prep(scores_upper_bound)
+        ws_key = (pixels, str(dev))
+        ws = self._ws.get(ws_key)
+        if ws is None:
+            ws = torch.empty((int(lib.cpn_select_workspace_bytes(pixels)),), dtype=torch.uint8, device=dev)
+            self._ws = {ws_key: ws}
+        meta = torch.zeros((2,), dtype=torch.int64, device=dev)
+        thr = float(self.score_thresh)
+        L.check(lib.cpn_select_count(L.ptr(scores), L.ptr(lo), L.ptr(up), pixels, thr, L.ptr(ws), L.ptr(meta), st),
+                'select_count')
+        if flags is not None:
+            meta[1:2].copy_(flags[:1].to(torch.int64))
+        total, flag = meta.tolist()                       # host sync #1 (the reference syncs at torch.where)
+        if flag & 1:
+            raise AssertionError('Inputs should be in interval (0.0, 1.0)')
+        P = int(total)
+        idx = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
+        sel_scores = torch.empty((max(P, 1),), dtype=torch.float32, device=dev)
+        seg = torch.zeros((n + 1,), dtype=torch.int32, device=dev)
+        L.check(lib.cpn_select_write(L.ptr(scores), L.ptr(lo), L.ptr(up), n, h * w, thr, L.ptr(ws), L.ptr(idx),
+                                     L.ptr(sel_scores), max(P, 1), L.ptr(seg), st), 'select_write')
+        contours = torch.empty((P, samples, 2), dtype=torch.float32, device=dev)
+        proposals = torch.empty((P, samples, 2), dtype=torch.float32, device=dev)
+        boxes = torch.empty((P, 4), dtype=torch.float32, device=dev)
+        locations = torch.empty((P, 2), dtype=torch.float32, device=dev)
+        fourier = torch.empty((P, order, 4), dtype=torch.float32, device=dev)
+        use_ref = bool(self.refinement) and refinement is not None and int(self.refinement_iterations) > 0
+        off = None
+        if offsets is not None:
+            off = torch.as_tensor(offsets).to(device=dev, dtype=torch.float32).reshape(n, 2).contiguous()
+        if P > 0:
+            trig = O.trig_table(order, samples, dev)
+            L.check(lib.cpn_decode_refine(L.ptr(idx), P, L.ptr(locfou), int(self.core_order), order, n, h, w, H, W,
+                                          L.ptr(trig), samples, L.ptr(refinement) if use_ref else None,
+                                          int(self.refinement_iterations) if use_ref else 0, L.ptr(off),
+                                          L.ptr(contours), L.ptr(proposals), L.ptr(boxes), L.ptr(locations),
+                                          L.ptr(fourier), st), 'decode_refine')
+        sel_scores = sel_scores[:P]
+        classes = torch.ones((P,), dtype=torch.long, device=dev)   # (scores > thresh).long() at selected pixels
+        flat = OrderedDict(contours=contours, boxes=boxes, scores=sel_scores, classes=classes, locations=locations,
+                           fourier=fourier, contour_proposals=proposals)
+        if nms:
+            keep, counts = O.nms_segments(boxes, sel_scores, seg, n, float(self.nms_thresh), O.NMS_BATCH_SIZE)
+            seg_h = seg.tolist()                          # host sync #2: per-image sizes of the returned lists
+            counts_h = counts.tolist()
+            sel = torch.cat([keep[seg_h[i]:seg_h[i] + counts_h[i]] for i in range(n)]) if P > 0 else keep[:0]
+            K = int(sel.numel())
+            out = OrderedDict()
+            for k, v in flat.items():
+                row = v[0].numel() * v.element_size() if P > 0 else 0
+                dst = torch.empty((K,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+                if K > 0:
+                    L.check(lib.cpn_gather_rows(L.ptr(v), row, L.ptr(sel), K, L.ptr(dst), st), 'gather_rows')
+                out[k] = dst
+            return out, counts_h
+        seg_h = seg.tolist()
+        return flat, [seg_h[i + 1] - seg_h[i] for i in range(n)]
+
+    def post(self, scores, locfou, refinement, original_size, nms=True, **kw):
+        """``post_flat`` + the reference's per-image list structure (resolve_batch_index, models/cpn.py:42-60)."""
+        flat, sizes = self.post_flat(scores, locfou, refinement, original_size, nms=nms, **kw)
+        out = OrderedDict((k, list(torch.split(v, sizes, 0))) for k, v in flat.items())
+        out['box_uncertainties'] = None
+        return out
+
+    def _run_plan(self, inputs, fmt=None):
+        if not isinstance(inputs, Tensor) or inputs.dim() != 4:
+            raise ValueError('inputs must be a 4-d Tensor')
+        if not inputs.is_cuda:
+            raise RuntimeError('celldetection_b200.CPN expects CUDA inputs; there is no CPU fallback.')
+        if fmt is None:
+            fmt = L.IN_U8_NCHW if inputs.dtype == torch.uint8 else L.IN_F32_NCHW
+        if fmt == L.IN_U8_NHWC:
+            n, h, w, c = inputs.shape
+        else:
+            n, c, h, w = inputs.shape
+        if c != self.in_channels:
+            raise ValueError(f'expected {self.in_channels} input channels, got {c}')
+        plan = self._plan(n, h, w)
+        x = inputs.contiguous() if inputs.dtype == torch.uint8 else inputs.contiguous().float()
+        plan.flags.zero_()
+        return plan, plan.forward(x, fmt), (h, w)
+
+    def forward_flat(self, inputs, fmt=None, nms=True, **kwargs):
+        """Like ``forward`` but returns (flat dict of concatenated tensors, rows per image); accepts uint8 NHWC
+        batches (``fmt=_lib.IN_U8_NHWC``) so tile crops need no host-side transpose."""
+        plan, (sc, lf, rf), hw = self._run_plan(inputs, fmt)
+        return self.post_flat(sc, lf, rf, hw, nms=nms, offsets=kwargs.get('offsets'),
+                              scores_lower_bound=kwargs.get('scores_lower_bound'),
+                              scores_upper_bound=kwargs.get('scores_upper_bound'), flags=plan.flags)
+
+    # ---- model(x) ---------------------------------------------------------------------------------------------------
+    def forward(self, inputs: Tensor, targets=None, nms=True, **kwargs):
+        if self.training or targets is not None:
+            if self.training and targets is None:
+                raise ValueError('In training mode, targets should be passed')
+            raise NotImplementedError('celldetection_b200 accelerates CPN inference only (use .eval()).')
+        plan, (sc, lf, rf), hw = self._run_plan(inputs)
+        return self.post(sc, lf, rf, hw, nms=nms, offsets=kwargs.get('offsets'),
+                         scores_lower_bound=kwargs.get('scores_lower_bound'),
+                         scores_upper_bound=kwargs.get('scores_upper_bound'), flags=plan.flags)
+
+
+def _make(arch):
+    class _Cpn(CPN):
+        def __init__(self, in_channels: int = 3, order: int = 5, nms_thresh: float = .2, score_thresh: float = .9,
+                     samples: int = 32, classes: int = 2, refinement: bool = True, refinement_iterations: int = 4,
+                     refinement_margin: float = 3., refinement_buckets: int = 1, backbone_kwargs: dict = None,
+                     **kwargs):
+            if backbone_kwargs:
+                raise NotImplementedError('backbone_kwargs are outside the accelerated path.')
+            super().__init__(arch, in_channels=in_channels, order=order, nms_thresh=nms_thresh,
+                             score_thresh=score_thresh, samples=samples, classes=classes, refinement=refinement,
+                             refinement_iterations=refinement_iterations, refinement_margin=refinement_margin,
+                             refinement_buckets=refinement_buckets, **kwargs)
+    _Cpn.__name__ = _Cpn.__qualname__ = arch
+    return _Cpn
+
+
+CpnU22 = _make('CpnU22')                          # models/cpn.py:772
+CpnResNet18FPN = _make('CpnResNet18FPN')          # models/cpn.py:1250
+CpnResNeXt101UNet = _make('CpnResNeXt101UNet')    # models/cpn.py:930

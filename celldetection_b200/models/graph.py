@@ -1,0 +1,387 @@
+"""Model descriptions of the three configured Contour Proposal Networks as flat layer graphs.
+
+The reference expresses these networks as ``nn.Module`` trees (all paths relative to /root/reference/celldetection):
+``CpnU22`` (models/cpn.py:772, unet.py:405 ``U22``), ``CpnResNet18FPN`` (cpn.py:1250, fpn.py:240) and
+``CpnResNeXt101UNet`` (cpn.py:930, unet.py:670).  Here one *tracer* walks the same structure and emits
+
+* the ordered parameter/buffer specification with the reference's ``state_dict`` key names, and
+* a flat list of layer ops on NHWC tensors (conv + folded BN + residual + ReLU, max-pool, nearest/bilinear resize, head
+  projection) that ``plan.py`` lowers to the C ABI's ``cpn_op_t`` array.
+
+Exact algebraic rewrites applied while tracing (each keeps per-pixel arithmetic identical):
+
+* ``torch.cat((lateral, top_down), 1)`` (unet.py:219-224) is a shared NHWC buffer whose channel slices are written by
+  the producers directly;
+* the decoder's 1x1 "inner" convolution is applied *before* the nearest up-sampling it follows in the reference
+  (unet.py:213-218): a 1x1 convolution commutes with nearest-neighbour replication, at a quarter of the work;
+* torchvision's FPN ``lateral + interpolate(top_down)`` is the residual input of the lateral 1x1 convolution, read
+  through the nearest index map;
+* the three ReadOut heads that share the feature map (score / location / fourier, cpn.py:253-263) run as one
+  convolution with concatenated output channels; Dropout2d is the identity in eval mode;
+* FPN outputs CPN never reads (levels 2-4 and 'pool', fpn.py:67-76) are not computed, nor is the decoder's unused
+  same-size ``'out'`` resample (unet.py:237).
+"""
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+ARCHS = ('CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet')
+
+
+@dataclass
+class TT:
+    """Logical NHWC tensor of a trace."""
+    id: int
+    c: int
+    h: int
+    w: int
+    parent: Optional['TT'] = None   # channel slice of `parent` at `c_off`
+    c_off: int = 0
+    f32: bool = False               # fp32 head output (bound to a caller buffer)
+    binding: int = -1
+    first: int = 1 << 30            # op index of first write
+    last: int = -1                  # op index of last access
+
+    def root(self):
+        t, off = self, 0
+        while t.parent is not None:
+            off += t.c_off
+            t = t.parent
+        return t, off
+
+
+@dataclass
+class ConvParams:
+    """Where a convolution's parameters live in the reference state_dict (None entries are absent)."""
+    weight: List[str]                 # one or more keys; several = concatenated along the output-channel axis
+    bias: List[Optional[str]]
+    bn: List[Optional[str]]           # BatchNorm prefix per weight key
+    groups: int = 1
+
+
+@dataclass
+class LOp:
+    kind: str
+    src: Optional[TT] = None
+    dst: Optional[TT] = None
+    res: Optional[TT] = None
+    k: int = 1
+    stride: int = 1
+    pad: int = 0
+    act: str = 'none'
+    act_scale: float = 1.
+    params: Optional[ConvParams] = None
+    cin_off: int = 0     # proj: input channel slice
+    cin: int = 0
+    name: str = ''
+
+
+class Tracer:
+    def __init__(self, n, h, w):
+        self.n, self.h, self.w = n, h, w
+        self.tensors: List[TT] = []
+        self.ops: List[LOp] = []
+        self.spec = OrderedDict()   # state_dict key -> (shape, role)
+
+    # ---- parameter specification ----------------------------------------------------------------------------------
+    def conv_spec(self, key, cin, cout, k, bias, groups=1):
+        self.spec[key + '.weight'] = ((cout, cin // groups, k, k), 'conv_w')
+        if bias:
+            self.spec[key + '.bias'] = ((cout,), 'conv_b')
+
+    def bn_spec(self, key, c, residual_branch=False):
+        self.spec[key + '.weight'] = ((c,), 'bn_w_res' if residual_branch else 'bn_w')
+        self.spec[key + '.bias'] = ((c,), 'bn_b')
+        self.spec[key + '.running_mean'] = ((c,), 'bn_rm')
+        self.spec[key + '.running_var'] = ((c,), 'bn_rv')
+        self.spec[key + '.num_batches_tracked'] = ((), 'bn_nbt')
+
+    # ---- tensors / ops -------------------------------------------------------------------------------------------
+    def tensor(self, c, h, w, **kw):
+        t = TT(len(self.tensors), c, h, w, **kw)
+        self.tensors.append(t)
+        return t
+
+    def _emit(self, op):
+        i = len(self.ops)
+        self.ops.append(op)
+        for t in (op.src, op.res):
+            if t is not None:
+                t.last = max(t.last, i)
+        op.dst.first = min(op.dst.first, i)
+        op.dst.last = max(op.dst.last, i)
+        return op.dst
+
+    def prep(self, c):
+        return self._emit(LOp('prep', dst=self.tensor(c, self.h, self.w), name='input'))
+
+    def conv(self, x, cout, k, stride=1, pad=None, act='none', res=None, params=None, name=''):
+        pad = k // 2 if pad is None else pad
+        ho, wo = (x.h + 2 * pad - k) // stride + 1, (x.w + 2 * pad - k) // stride + 1
+        return self._emit(LOp('conv', src=x, dst=self.tensor(cout, ho, wo), res=res, k=k, stride=stride, pad=pad,
+                              act=act, params=params, name=name))
+
+    def maxpool(self, x, k, stride, pad):
+        ho, wo = (x.h + 2 * pad - k) // stride + 1, (x.w + 2 * pad - k) // stride + 1
+        return self._emit(LOp('maxpool', src=x, dst=self.tensor(x.c, ho, wo), k=k, stride=stride, pad=pad))
+
+    def upsample(self, x, h, w):
+        return self._emit(LOp('upsample', src=x, dst=self.tensor(x.c, h, w)))
+
+    def bilinear(self, x, h, w):
+        return self._emit(LOp('bilinear', src=x, dst=self.tensor(x.c, h, w)))
+
+    def cat(self, a, b):
+        """Concatenate along channels by making `a` and `b` slices of one buffer (both must be unplaced)."""
+        assert a.parent is None and b.parent is None and (a.h, a.w) == (b.h, b.w)
+        t = self.tensor(a.c + b.c, a.h, a.w)
+        a.parent, a.c_off = t, 0
+        b.parent, b.c_off = t, a.c
+        t.first = min(a.first, b.first)
+        t.last = max(a.last, b.last)
+        return t
+
+    def proj(self, x, dst, cin_off, cin, params, act='none', act_scale=1., name=''):
+        return self._emit(LOp('proj', src=x, dst=dst, cin_off=cin_off, cin=cin, params=params, act=act,
+                              act_scale=act_scale, name=name))
+
+    def finalize(self):
+        # propagate access ranges of slices to their roots
+        for t in self.tensors:
+            r, _ = t.root()
+            if r is not t:
+                r.first = min(r.first, t.first)
+                r.last = max(r.last, t.last)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# building blocks (state_dict layouts as dumped from the reference)
+# ----------------------------------------------------------------------------------------------------------------------
+
+def _conv_bn_act(g: Tracer, x, key, bn_key, cin, cout, k, stride=1, bias=True, groups=1, act='relu', res=None,
+                 res_branch=False):
+    g.conv_spec(key, cin, cout, k, bias, groups)
+    if bn_key is not None:
+        g.bn_spec(bn_key, cout, res_branch)
+    p = ConvParams([key + '.weight'], [key + '.bias' if bias else None], [bn_key], groups)
+    return g.conv(x, cout, k, stride=stride, act=act, res=res, params=p, name=key)
+
+
+def _two_conv_norm_relu(g, x, p, cin, cout, bias=True):
+    """models/commons.py:120-149 (Sequential indices 0,1,(2),3,4,(5))"""
+    x = _conv_bn_act(g, x, f'{p}.0', f'{p}.1', cin, cout, 3, bias=bias)
+    return _conv_bn_act(g, x, f'{p}.3', f'{p}.4', cout, cout, 3, bias=bias)
+
+
+def _unet_encoder(g, x, p, cin, depth=5, base=64):
+    """models/unet.py:29-58"""
+    feats, chans = [], []
+    for i in range(depth):
+        cout = base * 2 ** i
+        if i == 0:
+            x = _two_conv_norm_relu(g, x, f'{p}.0', cin, cout)
+        else:
+            x = g.maxpool(x, 2, 2, 0)
+            x = _two_conv_norm_relu(g, x, f'{p}.{i}.1', chans[-1], cout)
+        feats.append(x)
+        chans.append(cout)
+    return feats, chans
+
+
+def _resnet_encoder(g, x, p, cin, kind):
+    """models/resnet.py:265-290 with fused_initial=False; blocks :56-116; _make_layer :119-193."""
+    if kind == 'resnet18':
+        layers, bottleneck, groups, width_per_group = (2, 2, 2, 2), False, 1, 64
+    elif kind == 'resnext101_32x8d':
+        layers, bottleneck, groups, width_per_group = (3, 4, 23, 3), True, 32, 8
+    else:
+        raise ValueError(kind)
+    expansion = 4 if bottleneck else 1
+    x = _conv_bn_act(g, x, f'{p}.0.0', f'{p}.0.1', cin, 64, 7, stride=2, bias=False)
+    feats, chans = [x], [64]
+    inplanes = 64
+    for li, nblocks in enumerate(layers):
+        planes = 64 * 2 ** li
+        if li == 0:
+            x = g.maxpool(x, 3, 2, 1)
+        for bi in range(nblocks):
+            bp = f'{p}.1.1.{bi}' if li == 0 else f'{p}.{li + 1}.{bi}'
+            stride = 2 if (li > 0 and bi == 0) else 1
+            outp = planes * expansion
+            has_ds = stride != 1 or inplanes != outp
+            if bottleneck:
+                width = int(planes * (width_per_group / 64.)) * groups
+                # register in module order: conv1,bn1,conv2,bn2,conv3,bn3,(downsample)
+                y = _conv_bn_act(g, x, f'{bp}.conv1', f'{bp}.bn1', inplanes, width, 1, bias=False)
+                y = _conv_bn_act(g, y, f'{bp}.conv2', f'{bp}.bn2', width, width, 3, stride=stride, bias=False,
+                                 groups=groups)
+                g.conv_spec(f'{bp}.conv3', width, outp, 1, False)
+                g.bn_spec(f'{bp}.bn3', outp, True)
+                idt = x
+                if has_ds:
+                    idt = _conv_bn_act(g, x, f'{bp}.downsample.0', f'{bp}.downsample.1', inplanes, outp, 1,
+                                       stride=stride, bias=False, act='none')
+                pr = ConvParams([f'{bp}.conv3.weight'], [None], [f'{bp}.bn3'])
+                x = g.conv(y, outp, 1, act='relu', res=idt, params=pr, name=f'{bp}.conv3')
+            else:
+                y = _conv_bn_act(g, x, f'{bp}.conv1', f'{bp}.bn1', inplanes, planes, 3, stride=stride, bias=False)
+                g.conv_spec(f'{bp}.conv2', planes, planes, 3, False)
+                g.bn_spec(f'{bp}.bn2', planes, True)
+                idt = x
+                if has_ds:
+                    idt = _conv_bn_act(g, x, f'{bp}.downsample.0', f'{bp}.downsample.1', inplanes, outp, 1,
+                                       stride=stride, bias=False, act='none')
+                pr = ConvParams([f'{bp}.conv2.weight'], [None], [f'{bp}.bn2'])
+                x = g.conv(y, outp, 3, act='relu', res=idt, params=pr, name=f'{bp}.conv2')
+            inplanes = outp
+        feats.append(x)
+        chans.append(inplanes)
+    return feats, chans
+
+
+def _unet_decoder(g, feats, chans, p, bridges):
+    """models/unet.py:62-176 (bookkeeping) and :178-249 (forward), with the inner 1x1 conv commuted before the
+    nearest up-sampling.  Returns the decoder outputs per level (index 0 = finest)."""
+    in_list = [0] * bridges + list(chans)
+    out_list = list(chans)                      # out_channels_list (unet.py:78-79, 100-104)
+    nlev = len(in_list)
+    # parameter registration order: inner_blocks (i = 1..nlev-1) interleaved with layer_blocks in the ctor loop; the
+    # state_dict groups them by ModuleList, so register all inner blocks first, then all layer blocks.
+    inner = {}
+    for i in range(1, nlev):
+        ouc = out_list[i - 1]
+        inc = out_list[i] if i < nlev - 1 else in_list[i]
+        if inc > 0 and ouc < inc:
+            g.conv_spec(f'{p}.inner_blocks.{i - 1}', inc, ouc, 1, True)
+            inner[i - 1] = (inc, ouc)
+    blocks = {}
+    for i in range(nlev - 1):
+        lat = in_list[i]
+        inc = min(out_list[i:i + 2])
+        ouc = out_list[i]
+        bias = lat > 0                           # bridge block = TwoConvNormRelu(bias=False) (unet.py:95-98)
+        cin = inc + lat
+        bp = f'{p}.layer_blocks.{i}'
+        g.conv_spec(f'{bp}.0', cin, ouc, 3, bias)
+        g.bn_spec(f'{bp}.1', ouc)
+        g.conv_spec(f'{bp}.3', ouc, ouc, 3, bias)
+        g.bn_spec(f'{bp}.4', ouc)
+        blocks[i] = (cin, ouc, bias)
+    depth = nlev - 1
+    last = feats[-1]
+    last_c = chans[-1]
+    results = {}
+    for i in range(depth - 1, -1, -1):
+        lateral = feats[i - bridges] if i - bridges >= 0 else None
+        top = last
+        if i in inner:                           # forward applies inner_blocks[i] (unet.py:218)
+            inc, ouc = inner[i]
+            assert inc == last_c
+            pr = ConvParams([f'{p}.inner_blocks.{i}.weight'], [f'{p}.inner_blocks.{i}.bias'], [None])
+            top = g.conv(top, ouc, 1, act='none', params=pr, name=f'{p}.inner_blocks.{i}')
+            last_c = ouc
+        if lateral is not None:
+            up = g.upsample(top, lateral.h, lateral.w)
+            x = g.cat(lateral, up)               # cat_order 0: (lateral, top_down) (unet.py:219-224)
+        else:
+            x = g.upsample(top, top.h * 2, top.w * 2)
+        cin, ouc, bias = blocks[i]
+        assert x.c == cin, (x.c, cin)
+        bp = f'{p}.layer_blocks.{i}'
+        pa = ConvParams([f'{bp}.0.weight'], [f'{bp}.0.bias' if bias else None], [f'{bp}.1'])
+        pb = ConvParams([f'{bp}.3.weight'], [f'{bp}.3.bias' if bias else None], [f'{bp}.4'])
+        x = g.conv(x, ouc, 3, act='relu', params=pa, name=f'{bp}.0')
+        x = g.conv(x, ouc, 3, act='relu', params=pb, name=f'{bp}.3')
+        last, last_c = x, ouc
+        results[i] = x
+    return results, out_list
+
+
+def _fpn_decoder(g, feats, chans, p, fpn_channels=256, needed=(0, 1)):
+    """torchvision FeaturePyramidNetwork.forward with models/fpn.py:79-134 blocks (conv + bias, no norm/activation).
+    Only the levels CPN reads are finished with their 3x3 output convolution."""
+    n = len(feats)
+    for i in range(n):
+        g.conv_spec(f'{p}.inner_blocks.{i}.0', chans[i], fpn_channels, 1, True)
+    for i in range(n):
+        g.conv_spec(f'{p}.layer_blocks.{i}.0', fpn_channels, fpn_channels, 3, True)
+    results = {}
+    last = None
+    for i in range(n - 1, -1, -1):
+        pr = ConvParams([f'{p}.inner_blocks.{i}.0.weight'], [f'{p}.inner_blocks.{i}.0.bias'], [None])
+        last = g.conv(feats[i], fpn_channels, 1, act='none', res=last, params=pr, name=f'{p}.inner_blocks.{i}')
+        if i in needed:
+            po = ConvParams([f'{p}.layer_blocks.{i}.0.weight'], [f'{p}.layer_blocks.{i}.0.bias'], [None])
+            results[i] = g.conv(last, fpn_channels, 3, act='none', params=po, name=f'{p}.layer_blocks.{i}')
+    return results
+
+
+def _read_out_spec(g, p, cin, cmid, cout, k=7):
+    """models/commons.py:461-511: block.0 conv kxk (bias), block.1 BN, block.2 act, block.3 dropout, block.4 conv 1x1."""
+    g.conv_spec(f'{p}.block.0', cin, cmid, k, True)
+    g.bn_spec(f'{p}.block.1', cmid)
+    g.conv_spec(f'{p}.block.4', cmid, cout, 1, True)
+
+
+def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_margin=3., refinement_buckets=1):
+    """Trace architecture `arch` for an [n, in_channels, h, w] input.  Returns the Tracer; ``g.outputs`` maps
+    'scores' / 'locfou' / 'refinement' to fp32 output tensors (bindings 0 / 1 / 2)."""
+    assert arch in ARCHS, arch
+    assert score_channels == 1 and refinement_buckets == 1, 'only classes<=2 and refinement_buckets=1 are in scope'
+    g = Tracer(n, h, w)
+    g.spec['order_weights'] = ((order, 1), 'order_weights')   # buffer of CPN (cpn.py:406-412)
+    bb = 'core.backbone'
+    x = g.prep(in_channels)
+    if arch == 'CpnU22':
+        feats, chans = _unet_encoder(g, x, f'{bb}.body', in_channels)
+        res, out_ch = _unet_decoder(g, feats, chans, f'{bb}.unet', bridges=0)
+        head_feat, head_c, ref_feat, ref_c = res[1], out_ch[1], res[0], out_ch[0]
+    elif arch == 'CpnResNeXt101UNet':
+        feats, chans = _resnet_encoder(g, x, f'{bb}.body', in_channels, 'resnext101_32x8d')
+        res, out_ch = _unet_decoder(g, feats, chans, f'{bb}.unet', bridges=1)
+        head_feat, head_c, ref_feat, ref_c = res[1], out_ch[1], res[0], out_ch[0]
+    else:
+        feats, chans = _resnet_encoder(g, x, f'{bb}.body', in_channels, 'resnet18')
+        res = _fpn_decoder(g, feats, chans, f'{bb}.fpn')
+        head_feat, head_c, ref_feat, ref_c = res[1], 256, res[0], 256
+    # ---- heads (models/cpn.py:177-234, 238-283) ----
+    heads = [('core.score_head', score_channels), ('core.location_head', 2), ('core.fourier_head', order * 4)]
+    for hp, co in heads:
+        _read_out_spec(g, hp, head_c, head_c, co)
+    _read_out_spec(g, 'core.refinement_head', ref_c, ref_c, 2 * refinement_buckets)
+    pm = ConvParams([f'{hp}.block.0.weight' for hp, _ in heads], [f'{hp}.block.0.bias' for hp, _ in heads],
+                    [f'{hp}.block.1' for hp, _ in heads])
+    mid = g.conv(head_feat, 3 * head_c, 7, act='relu', params=pm, name='heads.block.0')
+    hh, hw_ = head_feat.h, head_feat.w
+    scores = g.tensor(1, hh, hw_, f32=True, binding=0)
+    locfou = g.tensor(2 + 4 * order, hh, hw_, f32=True, binding=1)
+    loc_t = g.tensor(2, hh, hw_, f32=True, parent=locfou, c_off=0, binding=1)
+    fou_t = g.tensor(4 * order, hh, hw_, f32=True, parent=locfou, c_off=2, binding=1)
+    for j, ((hp, co), dst) in enumerate(zip(heads, (scores, loc_t, fou_t))):
+        pp = ConvParams([f'{hp}.block.4.weight'], [f'{hp}.block.4.bias'], [None])
+        g.proj(mid, dst, j * head_c, head_c, pp, name=f'{hp}.block.4')
+    if (ref_feat.h, ref_feat.w) != (h, w):       # refinement_full_res (cpn.py:277-278)
+        ref_feat = g.bilinear(ref_feat, h, w)
+    pr = ConvParams(['core.refinement_head.block.0.weight'], ['core.refinement_head.block.0.bias'],
+                    ['core.refinement_head.block.1'])
+    rmid = g.conv(ref_feat, ref_c, 7, act='relu', params=pr, name='core.refinement_head.block.0')
+    refinement = g.tensor(2, h, w, f32=True, binding=2)
+    pp = ConvParams(['core.refinement_head.block.4.weight'], ['core.refinement_head.block.4.bias'], [None])
+    g.proj(rmid, refinement, 0, ref_c, pp, act='scaled_tanh', act_scale=float(refinement_margin),
+           name='core.refinement_head.block.4')
+    g.outputs = OrderedDict(scores=scores, locfou=locfou, refinement=refinement)
+    g.head_hw = (hh, hw_)
+    g.finalize()
+    return g
+
+
+def conv_flops(g: Tracer):
+    """Executed convolution FLOPs of a trace (2 * output elements * (C_in / groups) * k * k),
+    including the head projections."""
+    total = 0
+    for op in g.ops:
+        if op.kind == 'conv':
+            total += 2 * g.n * op.dst.h * op.dst.w * op.dst.c * (op.src.c // op.params.groups) * op.k * op.k
+        elif op.kind == 'proj':
+            total += 2 * g.n * op.dst.h * op.dst.w * op.dst.c * op.cin
+    return total

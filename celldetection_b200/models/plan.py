@@ -1,0 +1,239 @@
+"""Lowering of a traced layer graph to the C ABI: weight packing (BatchNorm folding, KRSC / K-major layouts, grouped
+convolutions expanded to block-diagonal 64-channel slabs), activation-arena assignment by live ranges, and the
+``cpn_op_t`` array handed to ``cpn_plan_create``.
+
+BatchNorm folding follows SURVEY.md appendix B (eval mode): ``w' = w * gamma / sqrt(var + eps)``,
+``b' = (b - mean) * gamma / sqrt(var + eps) + beta`` in fp32, then cast.
+"""
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from .. import _lib as L
+from .graph import TT, LOp, Tracer
+
+ALIGN = 256
+BN_EPS = 1e-5
+
+
+def _align(v, a=ALIGN):
+    return (v + a - 1) // a * a
+
+
+def fold_conv(sd, params):
+    """Returns folded (weight [cout, cin/groups, k, k], bias [cout]) in fp32 for possibly concatenated convs."""
+    ws, bs = [], []
+    for wk, bk, bnk in zip(params.weight, params.bias, params.bn):
+        w = sd[wk].detach().float()
+        b = sd[bk].detach().float() if bk is not None else torch.zeros(w.shape[0], device=w.device)
+        if bnk is not None:
+            gamma, beta = sd[bnk + '.weight'].float(), sd[bnk + '.bias'].float()
+            mean, var = sd[bnk + '.running_mean'].float(), sd[bnk + '.running_var'].float()
+            scale = gamma / torch.sqrt(var + BN_EPS)
+            w = w * scale[:, None, None, None]
+            b = (b - mean) * scale + beta
+        ws.append(w)
+        bs.append(b)
+    return torch.cat(ws, 0), torch.cat(bs, 0)
+
+
+def slab_of(cin, cout, groups):
+    """(kslab, slab_mode) of a convolution -- see cpn_op_t::kslab."""
+    if groups == 1:
+        return cin, 0
+    cg_in, cg_out = cin // groups, cout // groups
+    assert cin == cout and cg_in == cg_out, 'grouped convolutions must have equal in/out widths'
+    assert 64 % cg_in == 0 or cg_in % 64 == 0, 'group width must divide or be a multiple of 64'
+    return max(64, cg_in), 1
+
+
+def expand_grouped(w, groups):
+    """[cout, cg, k, k] -> block-diagonal dense-slab weight [cout, kslab, k, k] (zeros off the diagonal blocks)."""
+    cout, cg, kh, kw = w.shape
+    cin = cg * groups
+    kslab, _ = slab_of(cin, cout, groups)
+    out = torch.zeros(cout, kslab, kh, kw, dtype=w.dtype, device=w.device)
+    o = torch.arange(cout, device=w.device)
+    grp = o // cg                                   # group of each output channel
+    slab_base = (o // 64 * 64) // kslab * kslab     # first global input channel of the slab of o's 64-wide tile
+    first = grp * cg - slab_base                    # local index of the group's first input channel
+    for j in range(cg):
+        out[o, first + j] = w[:, j]
+    return out
+
+
+def engine_for(op: LOp, fast, cin):
+    if not fast:
+        return L.ENGINE_SIMT
+    kslab, _ = slab_of(cin, op.dst.c, op.params.groups)
+    if kslab % 64 == 0 and op.dst.c % 64 == 0 and op.stride in (1, 2):
+        return L.ENGINE_TCGEN05
+    return L.ENGINE_SIMT
+
+
+class WeightPack:
+    """Device blob with every conv / projection weight of a model in one precision mode."""
+
+    def __init__(self, g: Tracer, sd, fast, device):
+        chunks, off = [], 0
+        self.entries = {}
+        for i, op in enumerate(g.ops):
+            if op.kind not in ('conv', 'proj'):
+                continue
+            w, b = fold_conv(sd, op.params)
+            w, b = w.to(device), b.to(device)
+            if op.kind == 'proj':
+                wp = w.reshape(w.shape[0], w.shape[1]).contiguous().float()
+                eng = -1
+            else:
+                cin = op.src.c
+                eng = engine_for(op, fast, cin)
+                if op.params.groups > 1:
+                    w = expand_grouped(w, op.params.groups)
+                cout, kslab, kh, kw = w.shape
+                if eng == L.ENGINE_TCGEN05:   # [R*S][cout][kslab] fp16
+                    wp = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, kslab).contiguous().half()
+                else:                          # [R*S][kslab][cout] fp32
+                    wp = w.permute(2, 3, 1, 0).reshape(kh * kw, kslab, cout).contiguous().float()
+            wb = wp.view(torch.uint8).reshape(-1)
+            bb = b.contiguous().float().view(torch.uint8).reshape(-1)
+            w_off = off
+            off = _align(off + wb.numel())
+            b_off = off
+            off = _align(off + bb.numel())
+            chunks.append((w_off, wb))
+            chunks.append((b_off, bb))
+            self.entries[i] = (w_off, b_off, eng)
+        self.blob = torch.zeros(max(off, ALIGN), dtype=torch.uint8, device=device)
+        for o, c in chunks:
+            self.blob[o:o + c.numel()] = c
+        self.bytes = off
+
+
+def assign_arena(g: Tracer, elem_size):
+    """First-fit placement of root buffers by live range.  Returns ({tensor id: byte offset of its root}, bytes)."""
+    roots = []
+    for t in g.tensors:
+        if t.parent is None and not t.f32 and t.last >= 0:
+            pitch = t.c if t.c % 4 == 0 else _align(t.c, 4)
+            roots.append((t.first, t.last, _align(g.n * t.h * t.w * pitch * elem_size), t))
+    roots.sort(key=lambda r: (r[0], -r[2]))
+    placed = []   # (offset, size, last)
+    offsets = {}
+    total = 0
+    for first, last, size, t in roots:
+        live = sorted((o, s) for o, s, l in placed if l >= first)
+        pos = 0
+        for o, s in live:
+            if pos + size <= o:
+                break
+            pos = max(pos, o + s)
+        placed.append((pos, size, last))
+        offsets[t.id] = pos
+        total = max(total, pos + size)
+    return offsets, total
+
+
+def _view(t: TT, n, root_off, elem_size, dtype):
+    r, coff = t.root()
+    pitch = r.c if r.c % 4 == 0 else _align(r.c, 4)
+    v = L.View()
+    v.offset = root_off.get(r.id, 0) + coff * elem_size
+    v.n, v.h, v.w, v.c, v.pitch, v.dtype = n, t.h, t.w, t.c, pitch, dtype
+    return v
+
+
+class Plan:
+    """A compiled (architecture, N, H, W, precision) instance: C plan + arena + output buffers."""
+
+    def __init__(self, g: Tracer, pack: WeightPack, fast, device):
+        lib = L.load()
+        self.g, self.pack, self.fast, self.device = g, pack, fast, device
+        act_dt, es = (L.DT_F16, 2) if fast else (L.DT_F32, 4)
+        offsets, arena_bytes = assign_arena(g, es)
+        self.arena = torch.empty(max(arena_bytes, ALIGN), dtype=torch.uint8, device=device)
+        self.flags = torch.zeros(4, dtype=torch.int32, device=device)
+        ops = (L.Op * len(g.ops))()
+        kind_map = dict(prep=L.OP_PREP, conv=L.OP_CONV, maxpool=L.OP_MAXPOOL, upsample=L.OP_UPSAMPLE,
+                        bilinear=L.OP_BILINEAR, proj=L.OP_PROJ)
+        act_map = dict(none=L.ACT_NONE, relu=L.ACT_RELU, scaled_tanh=L.ACT_SCALED_TANH)
+        self.engines = []
+        for i, lop in enumerate(g.ops):
+            o = ops[i]
+            o.kind = kind_map[lop.kind]
+            o.out_binding = -1
+            o.w_offset, o.b_offset = 0, -1
+            if lop.dst.f32:
+                r, coff = lop.dst.root()
+                v = L.View()
+                v.offset, v.n, v.h, v.w, v.c, v.pitch, v.dtype = coff * 4, g.n, lop.dst.h, lop.dst.w, lop.dst.c, r.c, L.DT_F32
+                o.dst = v
+                o.out_binding = lop.dst.binding
+            else:
+                o.dst = _view(lop.dst, g.n, offsets, es, act_dt)
+            if lop.src is not None:
+                o.src = _view(lop.src, g.n, offsets, es, act_dt)
+            else:
+                o.src = o.dst
+            if lop.res is not None:
+                o.res = _view(lop.res, g.n, offsets, es, act_dt)
+            o.r = o.s = lop.k
+            o.stride, o.pad = lop.stride, lop.pad
+            o.act, o.act_scale = act_map[lop.act], lop.act_scale
+            if lop.kind in ('conv', 'proj'):
+                w_off, b_off, eng = pack.entries[i]
+                o.w_offset, o.b_offset = w_off, b_off
+                if lop.kind == 'conv':
+                    o.engine = eng
+                    o.kslab, o.slab_mode = slab_of(lop.src.c, lop.dst.c, lop.params.groups)
+                    self.engines.append(eng)
+                else:
+                    o.proj_cin_off, o.proj_cin = lop.cin_off, lop.cin
+        self.ops = ops
+        handle = ctypes.c_void_p()
+        L.check(lib.cpn_plan_create(ops, len(g.ops), L.ptr(pack.blob), pack.blob.numel(), L.ptr(self.arena),
+                                    self.arena.numel(), L.ptr(self.flags), ctypes.byref(handle)), 'plan_create')
+        self.handle = handle
+        self.n_launches = lib.cpn_plan_num_launches(handle)
+        hh, hw = g.head_hw
+        self.out_shapes = OrderedDict(scores=(g.n, hh, hw), locfou=(g.n, hh, hw, g.outputs['locfou'].c),
+                                      refinement=(g.n, g.h, g.w, 2))
+
+    def new_outputs(self):
+        return [torch.empty(s, dtype=torch.float32, device=self.device) for s in self.out_shapes.values()]
+
+    def forward(self, x, input_format, outputs=None):
+        """Enqueue the backbone + heads on the current stream.  Returns [scores, locfou, refinement] (fp32)."""
+        lib = L.load()
+        outputs = self.new_outputs() if outputs is None else outputs
+        arr = (ctypes.c_void_p * len(outputs))(*[o.data_ptr() for o in outputs])
+        L.check(lib.cpn_plan_forward(self.handle, L.ptr(x), input_format, arr, len(outputs), L.stream_ptr()),
+                'plan_forward')
+        return outputs
+
+    def run_op(self, index, x, input_format, outputs):
+        lib = L.load()
+        arr = (ctypes.c_void_p * len(outputs))(*[o.data_ptr() for o in outputs])
+        L.check(lib.cpn_plan_run_op(self.handle, index, L.ptr(x), input_format, arr, len(outputs), L.stream_ptr()),
+                'plan_run_op')
+
+    def read_tensor(self, t: TT):
+        """Debug: copy logical tensor `t` out of the arena as an NCHW fp32 tensor (valid right after forward only
+        for tensors whose buffer has not been reused)."""
+        es, dt = (2, torch.float16) if self.fast else (4, torch.float32)
+        offsets, _ = assign_arena(self.g, es)
+        r, coff = t.root()
+        pitch = r.c if r.c % 4 == 0 else _align(r.c, 4)
+        nbytes = self.g.n * t.h * t.w * pitch * es
+        base = offsets[r.id]
+        buf = self.arena[base:base + nbytes].view(dt).reshape(self.g.n, t.h, t.w, pitch)
+        return buf[..., coff:coff + t.c].permute(0, 3, 1, 2).float().contiguous()
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                L.load().cpn_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

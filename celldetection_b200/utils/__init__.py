@@ -1,0 +1,2 @@
+from .synth import synth_state_dict, calibrate_heads_
+from .io import load_model, fetch_model, save_fetchable_model, model2dict, dict2model

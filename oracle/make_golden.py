@@ -1,0 +1,215 @@
+"""TEST INFRASTRUCTURE ONLY -- mints the golden vectors under tests/golden from the *reference itself*.
+
+Run in the build container (needs /root/reference):  ``python oracle/make_golden.py``
+
+The reference has no golden vectors of its own for this path, so each fixture records what the
+unmodified reference (imported through oracle/ref_shim.py, torch CPU fp32) computes for a seeded input and a seeded
+synthetic state_dict.  State dicts are too large to commit (31-225 M parameters); fixtures store the seed of
+``celldetection_b200.utils.synth_state_dict`` plus the six calibrated head tensors, which reproduces the exact
+state_dict anywhere.  While minting, the oracle restatement (oracle/cpn_oracle.py) is checked against the reference
+and the script aborts on any mismatch.
+"""
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_shim  # noqa: E402
+import cpn_oracle as orc  # noqa: E402
+from celldetection_b200.utils.synth import synth_state_dict, calibrate_heads_  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+CALIB_KEYS = [f'core.{h}_head.block.4.{p}' for h in ('score', 'fourier', 'location') for p in ('weight', 'bias')]
+
+FOURIER_STD, LOCATION_STD = 1.0, 0.5   # small objects so that NMS keeps a useful number of detections
+
+MODEL_CASES = [
+    # name, arch, N, H, W, seed, fg_fraction, model kwargs
+    ('cpnu22_n1_128', 'CpnU22', 1, 128, 128, 1, 0.3, {}),
+    ('cpnresnet18fpn_n2_128', 'CpnResNet18FPN', 2, 128, 128, 2, 0.2, {}),
+    ('cpnresnext101unet_n1_128', 'CpnResNeXt101UNet', 1, 128, 128, 3, 0.2, {}),
+    ('cpnu22_n2_96x160_s64', 'CpnU22', 2, 96, 160, 4, 0.2, dict(samples=64)),
+]
+
+
+def spec_of(ref_model):
+    return OrderedDict((k, tuple(v.shape)) for k, v in ref_model.state_dict().items())
+
+
+def build_state_dict(cd, arch, seed, fg_fraction, calib_x):
+    model = getattr(cd.models, arch)(3).eval()
+    sd = synth_state_dict(spec_of(model), seed=seed)
+    # torchvision's FeaturePyramidNetwork._load_from_state_dict renames 'inner_blocks.N.weight' for version < 2
+    # state dicts; carry the module versions over so the reference loads our plain OrderedDict verbatim.
+    sd._metadata = model.state_dict()._metadata
+
+    def core_fn(x, sd_):
+        model.load_state_dict(sd_)
+        with torch.no_grad():
+            scores, locations, refinement, fourier, _ = model.core(x)
+        return dict(scores=scores, locations=locations, fourier=fourier)
+
+    calibrate_heads_(sd, core_fn, calib_x, fg_fraction=fg_fraction, fourier_std=FOURIER_STD, location_std=LOCATION_STD)
+    model.load_state_dict(sd)
+    return model, sd
+
+
+def to_np(v):
+    return v.detach().cpu().numpy()
+
+
+def check_close(name, a, b, tol=1e-5):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    if a.size:
+        err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+        assert err <= tol, f'oracle != reference for {name}: rel err {err}'
+
+
+def mint_model_case(cd, name, arch, n, h, w, seed, fg, mkw):
+    torch.manual_seed(seed)
+    x = torch.rand(n, 3, h, w)
+    model, sd = build_state_dict(cd, arch, seed, fg, x[:1])
+    for k, v in mkw.items():
+        setattr(model, k, v)
+    offsets = torch.tensor([[7., 3.]] * n) if n > 1 else None
+    with torch.no_grad():
+        scores, locations, refinement, fourier, _ = model.core(x)
+        out = model(x) if offsets is None else model(x, offsets=offsets)
+        out_nonms = model(x, nms=False)
+    # ---- pin the oracle against the reference ----
+    o_scores, o_loc, o_ref, o_fou = orc.cpn_core(x, sd, arch)
+    for nm, a, b in (('scores', o_scores, scores), ('locations', o_loc, locations), ('refinement', o_ref, refinement),
+                     ('fourier', o_fou, fourier)):
+        check_close(f'{name}/{nm}', to_np(a), to_np(b), 1e-5)
+    o_out = orc.cpn_forward(x, sd, arch, offsets=offsets, order=model.order, samples=model.samples)
+    for k in ('contours', 'boxes', 'scores', 'locations', 'fourier', 'contour_proposals'):
+        for i in range(n):
+            check_close(f'{name}/out/{k}/{i}', to_np(o_out[k][i]), to_np(out[k][i]), 1e-5)
+    arrays = dict(x=to_np(x), raw_scores=to_np(scores), raw_locations=to_np(locations), raw_refinement=to_np(refinement),
+                  raw_fourier=to_np(fourier))
+    if offsets is not None:
+        arrays['offsets'] = to_np(offsets)
+    for k in CALIB_KEYS:
+        arrays['calib/' + k] = to_np(sd[k])
+    for i in range(n):
+        for k in ('contours', 'boxes', 'scores', 'classes', 'locations', 'fourier', 'contour_proposals'):
+            arrays[f'out/{i}/{k}'] = to_np(out[k][i])
+        arrays[f'nonms_count/{i}'] = np.array(len(out_nonms['scores'][i]))
+    arrays['meta'] = np.array([n, h, w, seed, model.order, model.samples], dtype=np.int64)
+    arrays['fg_fraction'] = np.array(fg)
+    np.savez_compressed(os.path.join(GOLDEN, f'model_{name}.npz'), arch=np.array(arch), **arrays)
+    print(f'{name}: proposals {[int(arrays[f"nonms_count/{i}"]) for i in range(n)]} kept '
+          f'{[len(out["scores"][i]) for i in range(n)]}')
+
+
+def mint_f2c(cd):
+    arrays = {}
+    g = torch.Generator().manual_seed(11)
+    for order in (1, 5, 16):
+        for samples in (32, 64, 128):
+            P = 37
+            f = torch.randn(P, order, 4, generator=g)
+            loc = torch.rand(P, 2, generator=g) * 512
+            con, _ = cd.ops.cpn.fouriers2contours(f, loc, samples=samples)
+            o_con, _ = orc.fouriers2contours(f, loc, samples=samples)
+            check_close(f'f2c/{order}/{samples}', to_np(o_con), to_np(con), 1e-6)
+            tag = f'o{order}_s{samples}'
+            arrays[tag + '/fourier'], arrays[tag + '/locations'], arrays[tag + '/contours'] = to_np(f), to_np(loc), to_np(con)
+    # explicit per-proposal sampling (ops/cpn.py:67-71)
+    f = torch.randn(9, 5, 4, generator=g)
+    loc = torch.rand(9, 2, generator=g) * 64
+    samp = torch.sort(torch.rand(9, 48, generator=g), -1).values
+    con, _ = cd.ops.cpn.fouriers2contours(f, loc, sampling=samp)
+    arrays['explicit/fourier'], arrays['explicit/locations'] = to_np(f), to_np(loc)
+    arrays['explicit/sampling'], arrays['explicit/contours'] = to_np(samp), to_np(con)
+    np.savez_compressed(os.path.join(GOLDEN, 'fouriers2contours.npz'), **arrays)
+    print('fouriers2contours: ok')
+
+
+def mint_tiling(cd):
+    arrays = {}
+    cases = [((640, 896), (256, 256), (192, 192)), ((512, 512), (512, 512), (384, 384)), ((100, 300), (128, 128), (96, 96)),
+             ((2048, 2048), (512, 512), (384, 384)), ((1000, 777), (256, 192), (200, 100))]
+    for i, (size, crop, strides) in enumerate(cases):
+        sl, ov, shape = cd.get_tiling_slices(size, crop, strides, return_overlaps=True)
+        sl, ov = list(sl), list(ov)
+        arrays[f'{i}/args'] = np.array([size, crop, strides])
+        arrays[f'{i}/slices'] = np.array([[[s.start, s.stop] for s in t] for t in sl])
+        arrays[f'{i}/overlaps'] = np.array(ov).reshape(len(sl), len(size), 2)
+        arrays[f'{i}/shape'] = np.array(shape)
+        o_sl, o_ov, o_shape = orc.get_tiling_slices(size, crop, strides)
+        assert [[(s.start, s.stop) for s in t] for t in o_sl] == [[(int(s.start), int(s.stop)) for s in t] for t in sl]
+        assert np.array_equal(o_ov, arrays[f'{i}/overlaps']) and tuple(o_shape) == tuple(shape)
+    np.savez_compressed(os.path.join(GOLDEN, 'tiling.npz'), **arrays)
+    print('tiling: ok')
+
+
+def mint_apply_model(cd):
+    """Reference ``apply_model`` (FakeTrainer) on a small synthetic uint8 image, CpnU22, crop 64 / stride 48."""
+    import importlib
+    cs = importlib.import_module('celldetection_scripts.cpn_inference')
+    cs = sys.modules['celldetection_scripts.cpn_inference']
+    seed = 5
+    torch.manual_seed(seed)
+    calib = torch.rand(1, 3, 64, 64)
+    model, sd = build_state_dict(cd, 'CpnU22', seed, 0.05, calib)
+    rng = np.random.RandomState(seed)
+    img = rng.randint(0, 256, size=(150, 200, 3)).astype(np.uint8)
+    lit = cd.models.LitCpn(model)
+    lit.eval()
+    lit.max_imsize = None
+    res = cs.apply_model(img, [lit], ref_shim.FakeTrainer(), crop_size=(64, 64), strides=(48, 48),
+                         model_kwargs_list=[{}], batch_size=2, verbose=False)
+    o_res = orc.apply_model(img, sd, 'CpnU22', 64, 48, border_removal=4)
+    assert len(o_res['scores']) == len(res['scores']), (len(o_res['scores']), len(res['scores']))
+    for k in ('contours', 'boxes', 'scores', 'locations'):
+        check_close(f'apply_model/{k}', to_np(o_res[k]), to_np(res[k]), 1e-5)
+    arrays = dict(img=img, meta=np.array([seed, 64, 48, 4]))
+    for k in CALIB_KEYS:
+        arrays['calib/' + k] = to_np(sd[k])
+    for k in ('contours', 'boxes', 'scores', 'classes', 'locations', 'fourier', 'contour_proposals'):
+        arrays['out/' + k] = to_np(res[k])
+    np.savez_compressed(os.path.join(GOLDEN, 'apply_model_cpnu22.npz'), **arrays)
+    print(f'apply_model: {len(res["scores"])} stitched detections')
+
+
+def mint_keys(cd):
+    """state_dict key -> shape of the three reference models (drop-in contract)."""
+    import json
+    out = {}
+    for arch in ('CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet'):
+        m = getattr(cd.models, arch)(3)
+        out[arch] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    with open(os.path.join(GOLDEN, 'state_dict_keys.json'), 'w') as f:
+        json.dump(out, f)
+    print('keys: ok', {k: len(v) for k, v in out.items()})
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    cd = ref_shim.import_reference()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    which = sys.argv[1:] or ['keys', 'f2c', 'tiling', 'models', 'apply']
+    if 'keys' in which:
+        mint_keys(cd)
+    if 'f2c' in which:
+        mint_f2c(cd)
+    if 'tiling' in which:
+        mint_tiling(cd)
+    if 'models' in which:
+        for case in MODEL_CASES:
+            mint_model_case(cd, *case)
+    if 'apply' in which:
+        mint_apply_model(cd)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,171 @@
+"""CPU: host-side logic of the product package -- state_dict contract, C-ABI surface, graph lowering, weight packing,
+arena assignment, tiling, and the world_size-2 exchange step over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import celldetection_b200 as cd
+from celldetection_b200 import _lib
+from celldetection_b200.models import graph as G
+from celldetection_b200.models import plan as PL
+from conftest import ROOT
+from helpers import key_spec, load_npz
+
+
+@pytest.mark.parametrize('arch', G.ARCHS)
+def test_state_dict_keys_match_reference(arch):
+    """Drop-in contract: same keys, same order, same shapes as the reference's state_dict."""
+    model = getattr(cd.models, arch)(3)
+    want = key_spec(arch)
+    got = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    assert [k for k, _ in got] == list(want.keys())
+    assert got == list(want.items())
+
+
+def test_library_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, 'include', 'cpn_b200.h')) as f:
+        header = f.read()
+    declared = set(re.findall(r'\b(cpn_[a-z0-9_]+)\s*\(', header))
+    declared -= {'cpn_plan_t', 'cpn_op_t', 'cpn_view_t'}
+    assert declared == set(_lib.SYMBOLS.keys()), declared ^ set(_lib.SYMBOLS.keys())
+    lib = _lib.load()                      # raises if the .so is missing or a symbol is not exported
+    assert lib.cpn_abi_version() == _lib.ABI_VERSION
+    assert lib.cpn_last_error() is not None
+    assert lib.cpn_select_workspace_bytes(1 << 20) > 0
+
+
+def test_struct_layout_matches_header():
+    import ctypes
+    assert ctypes.sizeof(_lib.View) == 32
+    assert ctypes.sizeof(_lib.Op) == 8 + 3 * 32 + 16 + 4 * 4 + 8 * 4
+
+
+def test_no_cpu_fallback():
+    model = cd.models.CpnU22(3)
+    with pytest.raises(RuntimeError):
+        model(torch.rand(1, 3, 64, 64))
+    with pytest.raises(RuntimeError):
+        cd.ops.cpn.fouriers2contours(torch.zeros(3, 5, 4), torch.zeros(3, 2))
+    with pytest.raises(NotImplementedError):
+        cd.models.CpnU22(3, classes=3)
+
+
+def test_graph_flop_census():
+    """Executed conv FLOPs per 3x512x512 (256x256 for U22) tile vs SURVEY 8a/8d: reference totals 201.67 / 2124.85 /
+    2392.83 GFLOP minus the stated savings (1x1-upsample commute, dead FPN output convs)."""
+    for arch, hw, ref_total, saved in (('CpnU22', 256, 201.67, 3.2), ('CpnResNet18FPN', 512, 2124.85, 6.3),
+                                       ('CpnResNeXt101UNet', 512, 2392.83, 45.1)):
+        g = G.trace(arch, 1, hw, hw)
+        gf = G.conv_flops(g) / 1e9
+        assert abs(gf - (ref_total - saved)) / ref_total < 0.004, (arch, gf)
+
+
+def test_grouped_expansion_and_bn_folding_equal_conv():
+    torch.manual_seed(0)
+    for cg, c in ((8, 128), (16, 128), (64, 128)):
+        groups = c // cg
+        x = torch.randn(1, c, 9, 9)
+        sd = {'c.weight': torch.randn(c, cg, 3, 3) * 0.1, 'bn.weight': torch.rand(c) + 0.5, 'bn.bias': torch.randn(c),
+              'bn.running_mean': torch.randn(c) * 0.1, 'bn.running_var': torch.rand(c) + 0.5}
+        ref = F.batch_norm(F.conv2d(x, sd['c.weight'], None, padding=1, groups=groups), sd['bn.running_mean'],
+                           sd['bn.running_var'], sd['bn.weight'], sd['bn.bias'], False, 0., 1e-5)
+        w, b = PL.fold_conv(sd, G.ConvParams(['c.weight'], [None], ['bn'], groups))
+        wexp = PL.expand_grouped(w, groups)             # [cout, kslab, 3, 3]
+        kslab, mode = PL.slab_of(c, c, groups)
+        assert mode == 1 and wexp.shape[1] == kslab
+        out = torch.zeros_like(ref)
+        for n0 in range(0, c, 64):                      # what the kernels do per 64-wide output slab
+            base = (n0 // kslab) * kslab
+            out[:, n0:n0 + 64] = F.conv2d(x[:, base:base + kslab], wexp[n0:n0 + 64], b[n0:n0 + 64], padding=1)
+        assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize('arch', G.ARCHS)
+def test_arena_assignment_has_no_live_overlap(arch):
+    g = G.trace(arch, 2, 128, 128)
+    offsets, total = PL.assign_arena(g, 2)
+    roots = [(t, offsets[t.id]) for t in g.tensors if t.id in offsets]
+    sizes = {t.id: PL._align(2 * t.h * t.w * (t.c if t.c % 4 == 0 else PL._align(t.c, 4)) * 2) for t, _ in roots}
+    for i, (a, oa) in enumerate(roots):
+        assert oa % 256 == 0 and oa + sizes[a.id] <= total
+        for b, ob in roots[i + 1:]:
+            live = not (a.last < b.first or b.last < a.first)
+            overlap = not (oa + sizes[a.id] <= ob or ob + sizes[b.id] <= oa)
+            assert not (live and overlap), (a.id, b.id)
+    # every op reads tensors that were written before
+    written = set()
+    for op in g.ops:
+        for t in (op.src, op.res):
+            if t is not None:
+                assert t.root()[0].id in written or t.id in written, op.name
+        written.add(op.dst.id)
+        written.add(op.dst.root()[0].id)
+
+
+def test_get_tiling_slices_matches_reference_golden():
+    z = load_npz('tiling')
+    i = 0
+    while f'{i}/args' in z.files:
+        size, crop, strides = [tuple(int(v) for v in r) for r in z[f'{i}/args']]
+        sl, ov, shape = cd.get_tiling_slices(size, crop, strides, return_overlaps=True)
+        sl = list(sl)
+        assert np.array_equal(np.array([[[s.start, s.stop] for s in t] for t in sl]), z[f'{i}/slices'])
+        assert np.array_equal(np.array(list(ov)).reshape(len(sl), 2, 2), z[f'{i}/overlaps'])
+        assert tuple(shape) == tuple(z[f'{i}/shape'])
+        i += 1
+
+
+def test_model_file_round_trip(tmp_path):
+    m = cd.models.CpnU22(3, order=4, samples=48)
+    f = str(tmp_path / 'm.pt')
+    cd.save_fetchable_model(m, f)
+    m2 = cd.load_model(f, map_location='cpu')
+    assert type(m2).__name__ == 'CpnU22' and m2.order == 4 and m2.samples == 48
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from collections import OrderedDict
+from celldetection_b200.inference import allgather_detections
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:' + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+K = 3 if rank == 0 else 5
+g = torch.Generator().manual_seed(100 + rank)
+res = OrderedDict(contours=torch.rand(K, 8, 2, generator=g), boxes=torch.rand(K, 4, generator=g),
+                  scores=torch.rand(K, generator=g), classes=torch.ones(K, dtype=torch.long),
+                  locations=torch.rand(K, 2, generator=g), fourier=torch.rand(K, 5, 4, generator=g),
+                  contour_proposals=torch.rand(K, 8, 2, generator=g))
+out = allgather_detections(res)
+assert out['scores'].shape[0] == 8 and out['classes'].dtype == torch.long
+for r, (a, b) in enumerate(((0, 3), (3, 8))):
+    gg = torch.Generator().manual_seed(100 + r)
+    kk = b - a
+    want = torch.rand(kk, 8, 2, generator=gg)
+    assert torch.equal(out['contours'][a:b], want), r
+torch.save({k: v for k, v in out.items()}, sys.argv[4] + f'.{rank}')
+dist.destroy_process_group()
+'''
+
+
+def test_allgather_detections_world2_gloo(tmp_path):
+    """N > 1 exchange step on CPU: both ranks end up with the identical rank-ordered concatenation."""
+    script = tmp_path / 'worker.py'
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    out = str(tmp_path / 'res')
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), out]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=240) == 0
+    a, b = torch.load(out + '.0'), torch.load(out + '.1')
+    for k in a:
+        assert torch.equal(a[k], b[k]), k

@@ -1,0 +1,122 @@
+"""CPU: the oracle restatement against the golden vectors minted from the reference itself (oracle/make_golden.py).
+
+This is what pins the oracle (the reference ships no golden vectors for this path)."""
+import numpy as np
+import pytest
+import torch
+
+import cpn_oracle as orc
+from helpers import load_npz, fixture_state_dict, rel_err, MODEL_FIXTURES
+
+
+@pytest.mark.parametrize('name', MODEL_FIXTURES)
+def test_oracle_model_matches_reference_golden(name):
+    z = load_npz(name)
+    arch = str(z['arch'])
+    n, h, w, seed, order, samples = [int(v) for v in z['meta']]
+    sd = fixture_state_dict(z, arch, seed)
+    x = torch.from_numpy(z['x'])
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        scores, locations, refinement, fourier = orc.cpn_core(x, sd, arch)
+    # fp32 torch-CPU restatement of the same ops: agreement to rounding level
+    assert rel_err(scores, z['raw_scores']) < 1e-5
+    assert rel_err(locations, z['raw_locations']) < 1e-5
+    assert rel_err(refinement, z['raw_refinement']) < 1e-5
+    assert rel_err(fourier, z['raw_fourier']) < 1e-5
+    offsets = torch.from_numpy(z['offsets']) if 'offsets' in z.files else None
+    # post chain on the *reference's* head tensors: isolates it from conv rounding -> exact counts
+    out = orc.cpn_post(torch.from_numpy(z['raw_scores']), torch.from_numpy(z['raw_locations']),
+                       torch.from_numpy(z['raw_refinement']), torch.from_numpy(z['raw_fourier']), (h, w), order=order,
+                       samples=samples, offsets=offsets)
+    for i in range(n):
+        assert len(out['scores'][i]) == len(z[f'out/{i}/scores'])
+        for k in ('contours', 'boxes', 'scores', 'locations', 'fourier', 'contour_proposals'):
+            assert rel_err(out[k][i].numpy(), z[f'out/{i}/{k}']) < 1e-6, (k, i)
+        assert np.array_equal(out['classes'][i].numpy(), z[f'out/{i}/classes'])
+    nonms = orc.cpn_post(torch.from_numpy(z['raw_scores']), torch.from_numpy(z['raw_locations']),
+                         torch.from_numpy(z['raw_refinement']), torch.from_numpy(z['raw_fourier']), (h, w), order=order,
+                         samples=samples, nms_on=False)
+    for i in range(n):
+        assert len(nonms['scores'][i]) == int(z[f'nonms_count/{i}'])
+
+
+def test_oracle_fouriers2contours_golden():
+    z = load_npz('fouriers2contours')
+    for order in (1, 5, 16):
+        for samples in (32, 64, 128):
+            t = f'o{order}_s{samples}'
+            con, _ = orc.fouriers2contours(torch.from_numpy(z[t + '/fourier']), torch.from_numpy(z[t + '/locations']),
+                                           samples=samples)
+            assert np.abs(con.numpy() - z[t + '/contours']).max() < 1e-4  # px
+    con, _ = orc.fouriers2contours(torch.from_numpy(z['explicit/fourier']), torch.from_numpy(z['explicit/locations']),
+                                   sampling=torch.from_numpy(z['explicit/sampling']))
+    assert np.abs(con.numpy() - z['explicit/contours']).max() < 1e-4
+
+
+def test_oracle_tiling_golden():
+    z = load_npz('tiling')
+    i = 0
+    while f'{i}/args' in z.files:
+        size, crop, strides = [tuple(int(v) for v in r) for r in z[f'{i}/args']]
+        sl, ov, shape = orc.get_tiling_slices(size, crop, strides)
+        assert np.array_equal(np.array([[[s.start, s.stop] for s in t] for t in sl]), z[f'{i}/slices'])
+        assert np.array_equal(ov, z[f'{i}/overlaps'])
+        assert tuple(shape) == tuple(z[f'{i}/shape'])
+        i += 1
+    assert i == 5
+    # config C4: 16384^2, crop 512 -> 43 x 43 tiles at stride 384, 32 x 32 at stride 512
+    assert orc.get_tiling_slices((16384, 16384), (512, 512), (384, 384))[2] == (43, 43)
+    assert orc.get_tiling_slices((16384, 16384), (512, 512), (512, 512))[2] == (32, 32)
+
+
+def test_oracle_apply_model_golden():
+    z = load_npz('apply_model_cpnu22')
+    seed, crop, stride, border = [int(v) for v in z['meta']]
+    sd = fixture_state_dict(z, 'CpnU22', seed)
+    torch.set_num_threads(8)
+    res = orc.apply_model(z['img'], sd, 'CpnU22', crop, stride, border_removal=border)
+    assert len(res['scores']) == len(z['out/scores']) > 0
+    for k in ('contours', 'boxes', 'scores', 'locations', 'fourier', 'contour_proposals'):
+        assert rel_err(res[k].numpy(), z['out/' + k]) < 1e-5, k
+
+
+def test_oracle_nms_matches_torchvision():
+    """The NMS restatement against the third-party op the reference calls (torchvision)."""
+    import torchvision  # noqa: F401
+    g = torch.Generator().manual_seed(0)
+    for n in (0, 1, 2, 50, 700):
+        xy = torch.rand(n, 2, generator=g) * 100
+        wh = torch.rand(n, 2, generator=g) * 30
+        boxes = torch.cat((xy, xy + wh), 1)
+        scores = torch.rand(n, generator=g)
+        if n >= 50:  # ties and degenerate boxes
+            scores[10:20] = scores[10]
+            boxes[5] = torch.tensor([5., 5., 5., 5.])
+            boxes[6] = torch.tensor([5., 5., 5., 5.])
+        for thr in (0.2, 0.5):
+            ref = torch.ops.torchvision.nms(boxes, scores, thr).numpy()
+            got = orc.nms(boxes.numpy(), scores.numpy(), thr)
+            assert np.array_equal(ref, got), (n, thr)
+    # appendix A.3 cases
+    z = torch.tensor([[5., 5., 5., 5.], [5., 5., 5., 5.]])
+    assert list(orc.nms(z.numpy(), np.array([.5, .4], np.float32), .2)) == [0, 1]
+    b = torch.tensor([[0., 0., 10., 10.], [0., 0., 10., 10.]])
+    assert list(orc.nms(b.numpy(), np.array([.5, .5], np.float32), 1.0)) == [0, 1]   # IoU == thr keeps both
+    assert list(orc.nms(b.numpy(), np.array([.5, .5], np.float32), .99)) == [0]
+
+
+def test_oracle_chunked_nms_rule():
+    g = torch.Generator().manual_seed(1)
+    n = 300
+    xy = torch.rand(n, 2, generator=g) * 60
+    boxes = torch.cat((xy, xy + torch.rand(n, 2, generator=g) * 20 + 1), 1)
+    scores = torch.rand(n, generator=g)
+    # reference formulation (ops/cpn.py:213-224) spelled out with torchvision's op
+    idx = torch.zeros(0, dtype=torch.long)
+    for s in range(0, n, 128):
+        e = min(s + 128, n)
+        idx = torch.cat((idx, torch.ops.torchvision.nms(boxes[s:e], scores[s:e], .3) + s))
+    idx = idx[torch.ops.torchvision.nms(boxes[idx], scores[idx], .3)]
+    got = orc.batched_box_nmsi([boxes.numpy()], [scores.numpy()], .3, batch_size=128)[0]
+    assert np.array_equal(got, idx.numpy())
