@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: tiles/sec (3x512x512) of CpnResNeXt101UNet inference (BASELINE.json configs[2]: batch 16 per GPU,
+synthetic tiles, random-init weights with calibrated heads) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repository's CUDA path (one JSON line)
+  python bench.py --impl reference ...                          # the reference's CPU path (oracle port) on host cores
+  python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...   # N > 1 (weak scaling, no data-path collective)
+
+A "step" is one full pass of the hot path over one batch: backbone + heads + select/decode/refine/boxes + NMS.
+``value`` times it with the batch already resident in HBM; ``e2e`` times ``model(x)`` from pinned HOST memory with
+the results copied back to the host inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ARCH = 'CpnResNeXt101UNet'
+TILE = 512
+BATCH = 16
+SEED = 0
+FG_FRACTION = 0.02     # SURVEY 8(d) calibration: 2 % of head pixels above score_thresh
+METRIC = 'tiles/sec (3x512x512) CpnResNeXt101UNet inference'
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d['hbm_gbs'], tflops=d['bf16_tflops'], tflops_sustained=d['bf16_tflops_sustained'],
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650., tflops=1590., tflops_sustained=1400., source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.p = index, None
+
+    def __enter__(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                       '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+        return self
+
+    def __exit__(self, *a):
+        self.result = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            return
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [c.strip() for c in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            self.result = dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def build_state_dict(core_fn, calib_x):
+    from celldetection_b200.models.graph import trace
+    from celldetection_b200.utils.synth import synth_state_dict, calibrate_heads_
+    spec = trace(ARCH, 1, 64, 64).spec
+    sd = synth_state_dict(spec, seed=SEED)
+    calibrate_heads_(sd, core_fn, calib_x, fg_fraction=FG_FRACTION, fourier_std=3.0, location_std=1.0)
+    return sd
+
+
+def synthetic_batches(n_batches, device, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(BATCH, 3, TILE, TILE, generator=g).to(device) for _ in range(n_batches)]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU path (oracle port, torch CPU fp32 on all host threads)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_tiles_per_sec(sd, steps, warmup, tiles_per_step=1):
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import cpn_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(SEED + 17)
+    xs = [torch.rand(tiles_per_step, 3, TILE, TILE, generator=g) for _ in range(2)]
+    kept = 0
+    for i in range(warmup):
+        orc.cpn_forward(xs[i % 2], sd, ARCH)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        out = orc.cpn_forward(xs[i % 2], sd, ARCH)
+        kept = sum(len(s) for s in out['scores'])
+    dt = time.perf_counter() - t0
+    return tiles_per_step * steps / dt, dt / steps * 1e3, cores, kept
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import cpn_oracle as orc
+
+    def core_fn(x, sd_):
+        with torch.no_grad():
+            s, l, r, f = orc.cpn_core(x, sd_, ARCH)
+        return dict(scores=s, locations=l, fourier=f)
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(SEED)
+    calib = torch.rand(1, 3, TILE, TILE, generator=g)
+    sd = build_state_dict(core_fn, calib)
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    val, ms, cores, kept = cpu_reference_tiles_per_sec(sd, steps, warmup)
+    line = dict(impl='reference', metric=METRIC, value=val, unit='tiles/s', n_gpus=args.gpus, steps=steps,
+                warmup=warmup, ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic',
+                config=dict(workload=f'{ARCH} random-init (calibrated heads), 1x3x{TILE}x{TILE} per step on CPU',
+                            tile=TILE, kept_last_step=kept),
+                cpu_baseline=dict(value=val, unit='tiles/s', cores=cores, kind='port',
+                                  sample=f'{steps} steps x 1 tile of 3x{TILE}x{TILE}, oracle/cpn_oracle.py torch-CPU fp32'),
+                e2e=dict(value=val, unit='tiles/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# this repository's arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import celldetection_b200 as cd
+    from celldetection_b200 import _lib
+    from celldetection_b200.models.graph import conv_flops
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.load()
+
+    model = getattr(cd.models, ARCH)(3, precision=args.precision)
+    g = torch.Generator().manual_seed(SEED)
+    calib = torch.rand(1, 3, TILE, TILE, generator=g)
+
+    def core_fn(x, sd_):
+        model.load_state_dict(sd_)
+        model.to(dev)
+        out = model.core_forward(x.to(dev))
+        return {k: v.float().cpu() for k, v in out.items()}
+
+    sd = build_state_dict(core_fn, calib)
+    model.load_state_dict(sd)
+    model.to(dev)
+
+    n_rot = 4   # rotate 4 distinct batches (201 MB of inputs; per-step activations are several GB) -> no L2 reuse
+    xs = synthetic_batches(n_rot, dev, SEED + 1 + rank)
+    host = [x.cpu().pin_memory() for x in xs]
+
+    def step(i):
+        return model.forward_flat(xs[i % n_rot])
+
+    def step_e2e(i):
+        x = host[i % n_rot].to(dev, non_blocking=True)
+        flat, counts = model.forward_flat(x)
+        out = {k: v.cpu() for k, v in flat.items()}       # device -> host read of the step's result
+        return out, counts
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(steps):
+            last = fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, _lib.launch_count() - l0, last
+
+    with ClockSampler(local) as clk:
+        ms, launches, last = timed(step, args.steps, args.warmup)
+    flat, counts = last
+    ms_e2e, _, last_e = timed(step_e2e, args.steps, max(1, args.warmup))
+    tiles = BATCH * world
+    value = tiles * args.steps / (ms / 1e3)
+    e2e = tiles * args.steps / (ms_e2e / 1e3)
+    d2h = sum(v.numel() * v.element_size() for v in last_e[0].values())
+
+    # ---- roofline of the dominant kernel: the merged 7x7 head convolution (tcgen05), timed alone ----
+    plan = model._plan(BATCH, TILE, TILE)
+    peaks = measured_peaks()
+    roof = None
+    head_idx = [i for i, o in enumerate(plan.g.ops) if o.name == 'heads.block.0'][0]
+    hop = plan.g.ops[head_idx]
+    outs = plan.new_outputs()
+    for _ in range(3):
+        plan.run_op(head_idx, xs[0], _lib.IN_F32_NCHW, outs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        plan.run_op(head_idx, xs[0], _lib.IN_F32_NCHW, outs)
+    e1.record()
+    torch.cuda.synchronize()
+    hms = e0.elapsed_time(e1) / reps
+    hflops = 2. * BATCH * hop.dst.h * hop.dst.w * hop.dst.c * hop.src.c * hop.k * hop.k
+    achieved = hflops / (hms / 1e3) / 1e12
+    if args.precision == 'fp16':
+        roof = dict(bound='tensor', kernel='conv_tc_kernel<256> (merged 7x7 heads 256->768 @256x256, batch 16)',
+                    achieved=achieved, peak=peaks['tflops'], unit='TFLOP/s', frac=achieved / peaks['tflops'],
+                    traffic=None, peak_source=peaks['source'] + ', burst cuBLAS bf16', ms_per_launch=hms,
+                    flops_per_launch=hflops)
+    else:
+        roof = dict(bound='tensor', kernel='conv_simt_kernel<float> (strict fp32 CUDA-core engine)', achieved=achieved,
+                    peak=peaks['tflops'], unit='TFLOP/s', frac=achieved / peaks['tflops'], traffic=None,
+                    peak_source=peaks['source'], ms_per_launch=hms, flops_per_launch=hflops)
+    total_flops = conv_flops(plan.g)
+    net_tflops = total_flops * args.steps / (ms / 1e3) / 1e12 * 1.0
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sd_cpu = {k: v.cpu() for k, v in sd.items()}
+            v, cms, cores, kept = cpu_reference_tiles_per_sec(sd_cpu, 3, 1)
+            cpu = dict(value=v, unit='tiles/s', cores=cores, kind='port',
+                       sample=f'3 steps x 1 tile of 3x{TILE}x{TILE} (+1 warm-up), oracle/cpn_oracle.py torch-CPU fp32')
+        line = dict(metric=METRIC, value=value, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f16' if args.precision == 'fp16' else 'f32', data='synthetic',
+                    config=dict(workload=f'{ARCH} random-init (synthetic weights seed {SEED}, heads calibrated to '
+                                         f'{FG_FRACTION:.0%} foreground), batch {BATCH}x3x{TILE}x{TILE} per GPU',
+                                global_batch=tiles, tile=TILE, parallelism=f'tile-parallel x{world}',
+                                l2='4 rotating input batches; per-step activations >> 126 MB L2',
+                                proposals_last_step=int(sum(model.forward_flat(xs[0], nms=False)[1])),
+                                kept_last_step=int(sum(counts)), precision=args.precision,
+                                conv_gflop_per_tile=total_flops / BATCH / 1e9),
+                    clocks=clk.result,
+                    e2e=dict(value=e2e, unit='tiles/s', h2d_bytes_per_step=int(host[0].numel() * 4),
+                             d2h_bytes_per_step=int(d2h), ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=int(launches), roofline=roof,
+                    network=dict(conv_tflops=net_tflops, frac_of_sustained_peak=net_tflops / peaks['tflops_sustained'],
+                                 launches_per_step=launches / args.steps))
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,2 +1,3 @@
 from . import cpn
+from . import conv
 from .cpn import *  # noqa: F401,F403

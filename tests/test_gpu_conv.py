@@ -1,0 +1,41 @@
+"""GPU: per-layer-type convolution parity through the C ABI's cpn_conv2d, against
+torch.nn.functional.conv2d on the CPU in fp32.  Each engine runs in a child process with a timeout."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TC_CASES = list(range(0, 16))
+ALL_CASES = list(range(0, 18))
+
+
+def _run(engine, ids, timeout=600):
+    p = subprocess.run([sys.executable, os.path.join(HERE, 'gpu_conv_check.py'), engine] + [str(i) for i in ids],
+                       capture_output=True, text=True, timeout=timeout)
+    rows = [json.loads(l) for l in p.stdout.splitlines() if l.startswith('{')]
+    assert p.returncode == 0 and len(rows) == len(ids), (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
+    return rows
+
+
+@pytest.mark.gpu
+def test_conv_simt_fp32_matches_torch():
+    for r in _run('simt32', ALL_CASES):
+        assert 'error' not in r, r
+        assert r['rel_err'] < 2e-5 and not r['nan'], r          # fp32, different summation order only
+
+
+@pytest.mark.gpu
+def test_conv_simt_fp16_storage_matches_torch():
+    for r in _run('simt16', ALL_CASES):
+        assert 'error' not in r, r
+        assert r['rel_err'] < 2e-3 and not r['nan'], r          # fp16 output rounding (2^-11 relative)
+
+
+@pytest.mark.gpu
+def test_conv_tcgen05_matches_torch():
+    for r in _run('tcgen05', TC_CASES):
+        assert 'error' not in r, r
+        assert r['rel_err'] < 2e-3 and not r['nan'], r          # fp16 operands, fp32 accumulate, fp16 store

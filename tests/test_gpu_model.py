@@ -1,0 +1,188 @@
+"""GPU: whole-model parity against the golden vectors minted from the reference (strict fp32 engine gates parity; the
+fp16 tensor-core engine is measured against the tolerance BASELINE.json's north_star states and its deviation is
+written to gpurun_out/parity_report.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import celldetection_b200 as cd
+import cpn_oracle as orc
+from conftest import ROOT
+from helpers import load_npz, fixture_state_dict, rel_err, match_by_box, MODEL_FIXTURES
+
+pytestmark = pytest.mark.gpu
+REPORT = os.path.join(ROOT, 'gpurun_out', 'parity_report.json')
+
+
+def _report(key, val):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    data = {}
+    if os.path.exists(REPORT):
+        with open(REPORT) as f:
+            data = json.load(f)
+    data[key] = val
+    with open(REPORT, 'w') as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+
+
+def _model(z, precision):
+    arch = str(z['arch'])
+    n, h, w, seed, order, samples = [int(v) for v in z['meta']]
+    m = getattr(cd.models, arch)(3, order=order, samples=samples, precision=precision)
+    m.load_state_dict(fixture_state_dict(z, arch, seed))
+    return m.cuda(), (n, h, w)
+
+
+def _compare_outputs(out, z, n):
+    stats = dict(count=[], ref_count=[], matched=[], max_vertex_err=0., max_box_err=0.)
+    for i in range(n):
+        rb = z[f'out/{i}/boxes']
+        gb = out['boxes'][i].cpu().numpy()
+        pairs = match_by_box(gb, rb)
+        stats['count'].append(len(gb)), stats['ref_count'].append(len(rb)), stats['matched'].append(len(pairs))
+        for a, b in pairs:
+            stats['max_vertex_err'] = max(stats['max_vertex_err'], float(
+                np.abs(out['contours'][i][a].cpu().numpy() - z[f'out/{i}/contours'][b]).max()))
+            stats['max_box_err'] = max(stats['max_box_err'], float(np.abs(gb[a] - rb[b]).max()))
+    return stats
+
+
+@pytest.mark.parametrize('name', MODEL_FIXTURES)
+def test_strict_fp32_model_matches_reference(name):
+    """north_star gates: score/fourier tensors within 1e-3 rel (||a-b||inf / ||b||inf), contour vertices within 0.5 px,
+    identical instance count after NMS."""
+    z = load_npz(name)
+    m, (n, h, w) = _model(z, 'fp32')
+    x = torch.from_numpy(z['x']).cuda()
+    raw = m.core_forward(x)
+    errs = {k: rel_err(raw[k].cpu().numpy(), z['raw_' + k]) for k in ('scores', 'locations', 'refinement', 'fourier')}
+    _report(f'{name}/fp32/raw_rel_err', errs)
+    for k, e in errs.items():
+        assert e < 1e-3, (k, e)
+    kw = dict(offsets=torch.from_numpy(z['offsets']).cuda()) if 'offsets' in z.files else {}
+    out = m(x, **kw)
+    st = _compare_outputs(out, z, n)
+    _report(f'{name}/fp32/outputs', st)
+    assert st['count'] == st['ref_count'] == st['matched'], st
+    assert st['max_vertex_err'] < 0.5, st
+    for i in range(n):
+        assert len(m(x, nms=False)['scores'][i]) == int(z[f'nonms_count/{i}'])
+
+
+@pytest.mark.parametrize('name', MODEL_FIXTURES)
+def test_fp16_tensor_core_model_close_to_reference(name):
+    """fp16 storage / fp32 accumulate engine: head tensors within 2e-2 rel, matched contours within 0.5 px, instance
+    count within max(2, 10 %) of the reference (thresholding is discontinuous; the exact flip rate is reported)."""
+    z = load_npz(name)
+    m, (n, h, w) = _model(z, 'fp16')
+    x = torch.from_numpy(z['x']).cuda()
+    raw = m.core_forward(x)
+    errs = {k: rel_err(raw[k].cpu().numpy(), z['raw_' + k]) for k in ('scores', 'locations', 'refinement', 'fourier')}
+    _report(f'{name}/fp16/raw_rel_err', errs)
+    kw = dict(offsets=torch.from_numpy(z['offsets']).cuda()) if 'offsets' in z.files else {}
+    out = m(x, **kw)
+    st = _compare_outputs(out, z, n)
+    _report(f'{name}/fp16/outputs', st)
+    for k, e in errs.items():
+        assert e < 2e-2, (k, e)
+    for c, r, mt in zip(st['count'], st['ref_count'], st['matched']):
+        assert abs(c - r) <= max(2, 0.1 * r) and mt >= 0.8 * r, st
+    assert st['max_vertex_err'] < 0.5 or sum(st['matched']) == 0, st
+
+
+def test_input_contract_and_uint8_path():
+    z = load_npz(MODEL_FIXTURES[0])
+    m, (n, h, w) = _model(z, 'fp32')
+    x = torch.from_numpy(z['x']).cuda()
+    with pytest.raises(AssertionError):
+        m(x * 1.5)                                        # commons.py:695-697
+    with pytest.raises(AssertionError):
+        m(x - 0.5)
+    u8 = (x * 255).round().to(torch.uint8)
+    a = m(u8)                                             # lightning_base.py:774-780: uint8 -> float / 255
+    b = m(u8.float() / 255)
+    assert len(a['scores'][0]) == len(b['scores'][0])
+    assert torch.equal(a['contours'][0], b['contours'][0])
+    nhwc = u8.permute(0, 2, 3, 1).contiguous()
+    flat, counts = m.forward_flat(nhwc, cd._lib.IN_U8_NHWC)
+    assert counts[0] == len(a['scores'][0]) and torch.equal(flat['contours'], a['contours'][0])
+    with pytest.raises(ValueError):                       # cpn.py:602-603: training mode needs targets
+        m.train()(x)
+    m.eval()
+
+
+def test_default_init_gives_empty_result_like_reference():
+    m = cd.models.CpnU22(3).cuda()                        # sigmoid ~ 0.5 < 0.9 everywhere
+    out = m(torch.rand(2, 3, 64, 64, device='cuda'))
+    assert [len(s) for s in out['scores']] == [0, 0]
+    assert out['contours'][0].shape == (0, 32, 2) and out['fourier'][1].shape == (0, 5, 4)
+
+
+def test_batch_invariance_and_determinism():
+    z = load_npz('model_cpnu22_n2_96x160_s64')
+    for prec in ('fp32', 'fp16'):
+        m, (n, h, w) = _model(z, prec)
+        x = torch.from_numpy(z['x']).cuda()
+        both, again = m(x), m(x)
+        for i in range(n):
+            single = m(x[i:i + 1])
+            assert torch.equal(both['contours'][i], again['contours'][i])
+            assert torch.equal(both['contours'][i], single['contours'][0]), (prec, i)
+
+
+def test_apply_model_matches_reference_golden():
+    z = load_npz('apply_model_cpnu22')
+    seed, crop, stride, border = [int(v) for v in z['meta']]
+    m = cd.models.CpnU22(3, precision='fp32')
+    m.load_state_dict(fixture_state_dict(z, 'CpnU22', seed))
+    m = m.cuda()
+    for bs in (1, 3):
+        res = cd.apply_model(z['img'], [m], crop_size=crop, strides=stride, border_removal=border, batch_size=bs)
+        assert len(res['scores']) == len(z['out/scores']) > 0
+        pairs = match_by_box(res['boxes'].cpu().numpy(), z['out/boxes'])
+        assert len(pairs) == len(z['out/scores'])
+        for a, b in pairs:
+            assert np.abs(res['contours'][a].cpu().numpy() - z['out/contours'][b]).max() < 0.5
+            assert np.abs(res['contour_proposals'][a].cpu().numpy() - z['out/contour_proposals'][b]).max() < 0.5
+    rr = cd.cpn_inference(z['img'], m, tile_size=crop, stride=stride, border_removal=border, batch_size=2)
+    assert len(rr[0]['scores']) == len(z['out/scores'])
+
+
+def test_full_size_c3_properties():
+    """BASELINE config C3 (CpnResNeXt101UNet, 3x512x512 tiles): size-independent properties at full tile size --
+    batch invariance (tile i of a batch == the same tile alone, bit for bit) and fp16-vs-fp32 engine agreement."""
+    from helpers import key_spec
+    from celldetection_b200.utils.synth import synth_state_dict, calibrate_heads_
+    arch = 'CpnResNeXt101UNet'
+    sd = synth_state_dict(key_spec(arch), seed=0)
+    torch.manual_seed(0)
+    x = torch.rand(2, 3, 512, 512).cuda()
+    strict = getattr(cd.models, arch)(3, precision='fp32')
+    strict.load_state_dict(sd)
+    strict = strict.cuda()
+
+    def core_fn(xx, sd_):
+        strict.load_state_dict(sd_)
+        strict.cuda()
+        return {k: v.cpu() for k, v in strict.core_forward(xx).items()}
+
+    calibrate_heads_(sd, core_fn, x[:1], fg_fraction=0.05, fourier_std=1.0, location_std=0.5)
+    strict.load_state_dict(sd)
+    strict.cuda()
+    fast = getattr(cd.models, arch)(3, precision='fp16')
+    fast.load_state_dict(sd)
+    fast = fast.cuda()
+    rs, rf = strict.core_forward(x), fast.core_forward(x)
+    errs = {k: rel_err(rf[k].cpu().numpy(), rs[k].cpu().numpy()) for k in rs}
+    _report('c3_512/fp16_vs_fp32_raw_rel_err', errs)
+    a, b = fast(x), fast(x[1:2])
+    assert torch.equal(a['contours'][1], b['contours'][0]) and torch.equal(a['scores'][1], b['scores'][0])
+    s = strict(x)
+    _report('c3_512/counts', dict(fp32=[len(v) for v in s['scores']], fp16=[len(v) for v in a['scores']]))
+    for k, e in errs.items():
+        assert e < 2e-2, (k, e)
+    for cs, cf in zip(s['scores'], a['scores']):
+        assert abs(len(cs) - len(cf)) <= max(2, 0.1 * len(cs))
