@@ -130,7 +130,7 @@ def run_reference(args):
     def core_fn(x, sd_):
         with torch.no_grad():
             s, l, r, f = orc.cpn_core(x, sd_, ARCH)
-        return dict(scores=s, locations=l, fourier=f)
+        return dict(scores=s, locations=l, fourier=f, refinement=r)
 
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(SEED)

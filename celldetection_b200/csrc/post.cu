@@ -408,6 +408,125 @@ __global__ void __launch_bounds__(F2C_TX * F2C_TY) f2c_tiled_kernel(const float*
   }
 }
 
+// Fast path for samples % 8 == 0 (the common 32 / 64 / 128): same register tile, but
+//  * the coefficient tile of the NEXT 32 proposals is prefetched with cp.async (double buffer) while this one computes,
+//  * each thread owns 4 ADJACENT sample pairs, so trig factors are one LDS.128 and every store is a 16-byte
+//    st.global.cs (two (x, y) vertices), on both the forward and the mirrored half of the contour.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void st_cs_f4(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(F2C_TX * F2C_TY, 4) f2c_fast_kernel(const float* __restrict__ fourier,
+                                                                       const float* __restrict__ locations,
+                                                                       long long P, int order, int samples,
+                                                                       const float* __restrict__ trig,
+                                                                       float* __restrict__ out, int txe) {
+  extern __shared__ __align__(16) float fsm[];
+  const int np = samples / 2;             // multiple of 4
+  const int row = order * 4;              // floats per proposal
+  const int cstride = row + 4;            // padded row (16-byte multiple)
+  float* cos_s = fsm;                     // [order][np]
+  float* sin_s = fsm + order * np;        // [order][np]
+  float* coef0 = fsm + 2 * order * np;    // 2 x [PB][cstride]
+  const int PB = (F2C_TX * F2C_TY / txe) * F2C_TP;  // proposals per block iteration (txe threads share a proposal row)
+  float* loc0 = coef0 + 2 * PB * cstride;  // 2 x [PB][2]
+  for (int i = threadIdx.x; i < order * np; i += blockDim.x) {
+    const int k = i / np, j = i - k * np;
+    cos_s[i] = trig[k * samples + j];
+    sin_s[i] = trig[(order + k) * samples + j];
+  }
+  const int tx = threadIdx.x % txe, ty = threadIdx.x / txe;
+  const long long nblk = (P + PB - 1) / PB;
+  const int chunks_per_row = row / 4;     // 16-byte chunks per proposal
+
+  auto prefetch = [&](long long blk, int buf) {
+    const long long p0 = blk * PB;
+    const int npr = (int)min((long long)PB, P - p0);
+    float* cb = coef0 + buf * PB * cstride;
+    for (int i = threadIdx.x; i < npr * chunks_per_row; i += blockDim.x) {
+      const int pl = i / chunks_per_row, c = i - pl * chunks_per_row;
+      cp_async16(cb + pl * cstride + c * 4, fourier + (p0 + pl) * row + c * 4);
+    }
+    float* lb = loc0 + buf * PB * 2;
+    for (int i = threadIdx.x; i < npr / 2; i += blockDim.x) cp_async16(lb + i * 4, locations + p0 * 2 + i * 4);
+    if ((npr & 1) && threadIdx.x == 0) {   // odd tail proposal: plain loads (visible after the barrier)
+      lb[(npr - 1) * 2] = locations[(p0 + npr - 1) * 2];
+      lb[(npr - 1) * 2 + 1] = locations[(p0 + npr - 1) * 2 + 1];
+    }
+  };
+
+  int buf = 0;
+  if ((long long)blockIdx.x < nblk) prefetch(blockIdx.x, 0);
+  cp_async_commit();
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x, buf ^= 1) {
+    const long long nxt = blk + gridDim.x;
+    if (nxt < nblk) prefetch(nxt, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const long long p0 = blk * PB;
+    const float* cb = coef0 + buf * PB * cstride;
+    const float* lb = loc0 + buf * PB * 2;
+    for (int j0 = 0; j0 < np; j0 += txe * 4) {
+      const int j = j0 + tx * 4;          // this thread's 4 adjacent pairs j .. j+3
+      if (j < np) {
+        float cx[F2C_TP][4], sx_[F2C_TP][4], cy[F2C_TP][4], sy_[F2C_TP][4];
+#pragma unroll
+        for (int a = 0; a < F2C_TP; ++a)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cx[a][q] = sx_[a][q] = cy[a][q] = sy_[a][q] = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < order; ++k) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cos_s + k * np + j);
+          const float4 s4 = *reinterpret_cast<const float4*>(sin_s + k * np + j);
+          const float c[4] = {c4.x, c4.y, c4.z, c4.w}, s[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int a = 0; a < F2C_TP; ++a) {
+            const float4 f = *reinterpret_cast<const float4*>(cb + (ty * F2C_TP + a) * cstride + k * 4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              cx[a][q] = __fmaf_rn(f.x, c[q], cx[a][q]);
+              sx_[a][q] = __fmaf_rn(f.y, s[q], sx_[a][q]);
+              cy[a][q] = __fmaf_rn(f.z, c[q], cy[a][q]);
+              sy_[a][q] = __fmaf_rn(f.w, s[q], sy_[a][q]);
+            }
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < F2C_TP; ++a) {
+          const int pl = ty * F2C_TP + a;
+          const long long pr = p0 + pl;
+          if (pr >= P) continue;
+          const float lx = lb[pl * 2], ly = lb[pl * 2 + 1];
+          float* o = out + pr * samples * 2;
+          float fx[4], fy[4], mx[4], my[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            fx[q] = (lx + sx_[a][q]) + cx[a][q];
+            fy[q] = (ly + sy_[a][q]) + cy[a][q];
+            mx[q] = (lx - sx_[a][q]) + cx[a][q];
+            my[q] = (ly - sy_[a][q]) + cy[a][q];
+          }
+          st_cs_f4(o + (j + 0) * 2, fx[0], fy[0], fx[1], fy[1]);
+          st_cs_f4(o + (j + 2) * 2, fx[2], fy[2], fx[3], fy[3]);
+          const int jm = samples - 4 - j;   // mirrored samples S-1-j-3 .. S-1-j, ascending order
+          st_cs_f4(o + (jm + 0) * 2, mx[3], my[3], mx[2], my[2]);
+          st_cs_f4(o + (jm + 2) * 2, mx[1], my[1], mx[0], my[0]);
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with `buf` before the next iteration's prefetch overwrites it
+  }
+  cp_async_wait<0>();
+}
+
 // explicit per-proposal sampling [P, S] (ops/cpn.py:67-71): one warp per proposal, trig evaluated on the fly
 __global__ void __launch_bounds__(256) f2c_sampling_kernel(const float* __restrict__ fourier,
                                                            const float* __restrict__ locations, long long P, int order,
@@ -513,6 +632,26 @@ extern "C" int cpn_fouriers2contours(const float* fourier, const float* location
                                                                      out);
     CPN_CHECK_LAUNCH();
     return 0;
+  }
+  if (samples % 8 == 0 && ((uintptr_t)fourier % 16 == 0) && ((uintptr_t)locations % 16 == 0) &&
+      ((uintptr_t)out % 16 == 0)) {
+    const int nph = samples / 2;
+    int txe = 16;
+    while (txe > 1 && txe * 4 > nph) txe >>= 1;          // threads per proposal row: 4 adjacent pairs each
+    const int pb = (F2C_TX * F2C_TY / txe) * F2C_TP;
+    const size_t fsmem = ((size_t)2 * order * nph + 2 * (size_t)pb * (order * 4 + 4) + 2 * (size_t)pb * 2) * sizeof(float);
+    if (fsmem <= 200 * 1024) {
+      static size_t fconfigured = 0;
+      if (fsmem > 48 * 1024 && fsmem > fconfigured) {
+        CPN_CHECK_CUDA(cudaFuncSetAttribute(f2c_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        fconfigured = fsmem;
+      }
+      const long long nb = (P + pb - 1) / pb;
+      f2c_fast_kernel<<<capped_grid(nb, 4), F2C_TX * F2C_TY, fsmem, st>>>(fourier, locations, P, order, samples, trig,
+                                                                          out, txe);
+      CPN_CHECK_LAUNCH();
+      return 0;
+    }
   }
   const int np = (samples + 1) / 2;
   const size_t smem = ((size_t)((2 * order * np + 3) & ~3) + (size_t)F2C_PB * (order * 4 + 4)) * sizeof(float);

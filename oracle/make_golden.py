@@ -26,7 +26,8 @@ import cpn_oracle as orc  # noqa: E402
 from celldetection_b200.utils.synth import synth_state_dict, calibrate_heads_  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-CALIB_KEYS = [f'core.{h}_head.block.4.{p}' for h in ('score', 'fourier', 'location') for p in ('weight', 'bias')]
+CALIB_KEYS = [f'core.{h}_head.block.4.{p}' for h in ('score', 'fourier', 'location', 'refinement')
+              for p in ('weight', 'bias')]
 
 FOURIER_STD, LOCATION_STD = 1.0, 0.5   # small objects so that NMS keeps a useful number of detections
 
@@ -54,7 +55,7 @@ def build_state_dict(cd, arch, seed, fg_fraction, calib_x):
         model.load_state_dict(sd_)
         with torch.no_grad():
             scores, locations, refinement, fourier, _ = model.core(x)
-        return dict(scores=scores, locations=locations, fourier=fourier)
+        return dict(scores=scores, locations=locations, fourier=fourier, refinement=refinement)
 
     calibrate_heads_(sd, core_fn, calib_x, fg_fraction=fg_fraction, fourier_std=FOURIER_STD, location_std=LOCATION_STD)
     model.load_state_dict(sd)

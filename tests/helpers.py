@@ -9,7 +9,8 @@ import torch
 from conftest import GOLDEN
 from celldetection_b200.utils.synth import synth_state_dict
 
-CALIB_KEYS = [f'core.{h}_head.block.4.{p}' for h in ('score', 'fourier', 'location') for p in ('weight', 'bias')]
+CALIB_KEYS = [f'core.{h}_head.block.4.{p}' for h in ('score', 'fourier', 'location', 'refinement')
+              for p in ('weight', 'bias')]
 MODEL_FIXTURES = ['model_cpnu22_n1_128', 'model_cpnresnet18fpn_n2_128', 'model_cpnresnext101unet_n1_128',
                   'model_cpnu22_n2_96x160_s64']
 
@@ -39,24 +40,20 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
 
 
-def match_by_box(boxes_a, boxes_b):
-    """Greedy one-to-one matching of detections by box IoU (near-tie score ordering may differ between
-    implementations).  Returns index pairs (ia, ib)."""
-    boxes_a, boxes_b = np.asarray(boxes_a, np.float64), np.asarray(boxes_b, np.float64)
+def match_by_box(boxes_a, boxes_b, max_dist=2.0):
+    """Greedy one-to-one matching of detections by box distance (max |coordinate difference| <= max_dist px); robust
+    to near-tie score ordering differences and to degenerate (zero-area) boxes.  Returns index pairs (ia, ib)."""
+    boxes_a, boxes_b = np.asarray(boxes_a, np.float64).reshape(-1, 4), np.asarray(boxes_b, np.float64).reshape(-1, 4)
     pairs, used = [], set()
     for i, a in enumerate(boxes_a):
-        best, bj = 0., -1
+        best, bj = max_dist, -1
         for j, b in enumerate(boxes_b):
             if j in used:
                 continue
-            iw = max(0., min(a[2], b[2]) - max(a[0], b[0]))
-            ih = max(0., min(a[3], b[3]) - max(a[1], b[1]))
-            inter = iw * ih
-            ua = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
-            iou = inter / ua if ua > 0 else 0.
-            if iou > best:
-                best, bj = iou, j
-        if bj >= 0 and best > 0.5:
+            d = np.abs(a - b).max()
+            if d <= best:
+                best, bj = d, j
+        if bj >= 0:
             used.add(bj)
             pairs.append((i, bj))
     return pairs

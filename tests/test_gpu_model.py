@@ -103,7 +103,7 @@ def test_input_contract_and_uint8_path():
         m(x - 0.5)
     u8 = (x * 255).round().to(torch.uint8)
     a = m(u8)                                             # lightning_base.py:774-780: uint8 -> float / 255
-    b = m(u8.float() / 255)
+    b = m((u8.cpu().float() / 255).cuda())              # true division like the CPU reference (torch-CUDA multiplies by 1/255)
     assert len(a['scores'][0]) == len(b['scores'][0])
     assert torch.equal(a['contours'][0], b['contours'][0])
     nhwc = u8.permute(0, 2, 3, 1).contiguous()
