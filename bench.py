@@ -207,12 +207,17 @@ def run_b200(args):
         barrier()
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prof = os.environ.get('CPN_PROFILE_RANGE') == fn.__name__   # ncu --profile-from-start off
+        if prof:
+            torch.cuda.profiler.start()
         e0.record()
         last = None
         for i in range(steps):
             last = fn(i)
         e1.record()
         barrier()
+        if prof:
+            torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms], device=dev)

@@ -31,7 +31,7 @@ class Op(ctypes.Structure):
                 ('r', ctypes.c_int32), ('s', ctypes.c_int32), ('stride', ctypes.c_int32), ('pad', ctypes.c_int32),
                 ('kslab', ctypes.c_int32), ('slab_mode', ctypes.c_int32), ('act', ctypes.c_int32),
                 ('act_scale', ctypes.c_float), ('proj_cin_off', ctypes.c_int32), ('proj_cin', ctypes.c_int32),
-                ('out_binding', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('out_binding', ctypes.c_int32), ('fuse_next', ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/cpn_b200.h declares

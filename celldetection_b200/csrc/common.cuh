@@ -55,6 +55,8 @@ int conv_simt_launch(const cpn_op_t& op, const void* src, void* dst, const void*
 int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const void* res, const void* wgt,
                         const float* bias, ConvTcPlan** out);
 int conv_tc_launch(const ConvTcPlan* p, cudaStream_t st);
+int conv_tc_fuse_proj(ConvTcPlan* p, int n, const cpn_op_t* projs, const char* weights);
+void conv_tc_bind_proj_out(ConvTcPlan* p, int head, void* out);
 void conv_tc_plan_destroy(ConvTcPlan* p);
 
 int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* dst, int32_t* flags, cudaStream_t st);

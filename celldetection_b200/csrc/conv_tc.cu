@@ -26,10 +26,26 @@ namespace cpn {
 constexpr int TC_BW = 16, TC_BH = 8, TC_BM = 128, TC_BK = 64;
 constexpr int TC_THREADS = 192;
 constexpr int TC_SMEM_BUDGET = 196608;  // bytes of operand stages
+constexpr int TC_PROJ_SMEM_MAX = 24576; // fused projection weights (fp32)
+
+constexpr int TC_MAX_HEADS = 4;    // fused ReadOut projections: one per N tile
+constexpr int TC_PROJ_MAX = 24;    // max output channels of one fused projection
+
+// ReadOut's final 1x1 convolution (+ final activation) fused into the epilogue of the kxk convolution that feeds it
+// (models/commons.py:494-511): the BN mid channels of one N tile never leave registers.
+struct ProjHead {
+  const float* w;   // [cout][BN] fp32
+  const float* b;   // [cout] or nullptr
+  float* out;       // fp32 records: out[pixel * pitch + j]
+  int cout, pitch, act;
+  float act_scale;
+};
 
 struct ConvTcParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  ProjHead proj[TC_MAX_HEADS];
+  int nproj;
   __half* out;
   const __half* res;
   const float* bias;
@@ -44,6 +60,7 @@ struct ConvTcParams {
 
 struct ConvTcPlan {
   ConvTcParams p;
+  int proj_smem_bytes;
   int bn;
   int stages;
   int smem_bytes;
@@ -184,6 +201,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nk = p.R * p.S * p.cblocks;  // K blocks per tile
+  // fused projection weights live behind the operand stages: [head][cout][BN] fp32
+  float* proj_w = reinterpret_cast<float*>(smem_raw + ((smem_base - smem_u32(smem_raw)) + stages * STAGE_BYTES));
+  if (p.nproj > 0) {
+    int off = 0;
+    for (int h = 0; h < p.nproj; ++h) {
+      const int nw = p.proj[h].cout * BN;
+      for (int i = threadIdx.x; i < nw; i += blockDim.x) proj_w[off + i] = p.proj[h].w[i];
+      off += nw;
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA[0]);
@@ -298,6 +325,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * BN;
+      if (p.nproj > 0) {
+        // ---- fused ReadOut: bias + ReLU on the fp32 accumulators, then the 1x1 projection of this N tile's head ----
+        const ProjHead& H = p.proj[n_tile];
+        int woff = 0;
+        for (int h = 0; h < n_tile; ++h) woff += p.proj[h].cout * BN;
+        const float* wh = proj_w + woff;
+        float pacc[TC_PROJ_MAX];
+#pragma unroll
+        for (int j = 0; j < TC_PROJ_MAX; ++j) pacc[j] = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          float f[32];
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b = p.bias ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + b.x;
+            f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + b.y;
+            f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + b.z;
+            f[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + b.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < TC_PROJ_MAX; ++j) {
+            if (j < H.cout) {
+              const float4* w4 = reinterpret_cast<const float4*>(wh + j * BN + ch * 32);
+              float a = pacc[j];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 w = w4[q];
+                a = fmaf(f[q * 4 + 0], w.x, a);
+                a = fmaf(f[q * 4 + 1], w.y, a);
+                a = fmaf(f[q * 4 + 2], w.z, a);
+                a = fmaf(f[q * 4 + 3], w.w, a);
+              }
+              pacc[j] = a;
+            }
+          }
+        }
+        if (valid) {
+          float* o = H.out + (((long long)img * p.Ho + y) * p.Wo + x) * H.pitch;
+#pragma unroll
+          for (int j = 0; j < TC_PROJ_MAX; ++j) {
+            if (j < H.cout) {
+              float r = pacc[j] + (H.b ? __ldg(H.b + j) : 0.f);
+              if (H.act == CPN_ACT_SCALED_TANH) r = tanhf(r) * H.act_scale;
+              else if (H.act == CPN_ACT_RELU) r = fmaxf(r, 0.f);
+              o[j] = r;
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t v[32];
@@ -326,6 +411,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int q = 0; q < 4; ++q) o4[q] = packed[q];
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -439,6 +525,7 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   const int stage_bytes = TC_BM * TC_BK * 2 + bn * TC_BK * 2;
   pl->stages = TC_SMEM_BUDGET / stage_bytes;
   if (pl->stages > 8) pl->stages = 8;
+  pl->proj_smem_bytes = 0;
   pl->smem_bytes = pl->stages * stage_bytes + 1024;
   const long long sms = sm_count();
   pl->grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
@@ -451,7 +538,7 @@ static int launch_bn(const ConvTcPlan* pl, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     CPN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        TC_SMEM_BUDGET + 1024));
+                                        TC_SMEM_BUDGET + 1024 + TC_PROJ_SMEM_MAX));
     attr_set = true;
   }
   conv_tc_kernel<BN><<<pl->grid, TC_THREADS, pl->smem_bytes, st>>>(pl->p, pl->stages);
@@ -468,6 +555,34 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t st) {
   set_error("conv_tc: bad BN %d", pl->bn);
   return 1;
 }
+
+// Fuse `n` ReadOut projections (one per N tile, in tile order) into the epilogue; the convolution then writes the fp32
+// head records instead of its fp16 output.  Output pointers are (re)bound with conv_tc_bind_proj_out before launches.
+int conv_tc_fuse_proj(ConvTcPlan* pl, int n, const cpn_op_t* projs, const char* weights) {
+  CPN_REQUIRE(n >= 1 && n <= TC_MAX_HEADS && n == pl->p.tiles_n, "conv_tc: %d fused projections for %d N tiles", n,
+              pl->p.tiles_n);
+  CPN_REQUIRE(pl->p.res == nullptr, "conv_tc: fused projection with residual is not supported");
+  int total = 0;
+  for (int h = 0; h < n; ++h) {
+    const cpn_op_t& q = projs[h];
+    CPN_REQUIRE(q.kind == CPN_OP_PROJ && q.proj_cin == pl->bn && q.proj_cin_off == h * pl->bn && q.dst.c <= TC_PROJ_MAX &&
+                    q.dst.dtype == CPN_DT_F32,
+                "conv_tc: projection %d cannot be fused (cin %d off %d cout %d)", h, q.proj_cin, q.proj_cin_off, q.dst.c);
+    ProjHead& H = pl->p.proj[h];
+    H.w = reinterpret_cast<const float*>(weights + q.w_offset);
+    H.b = q.b_offset >= 0 ? reinterpret_cast<const float*>(weights + q.b_offset) : nullptr;
+    H.out = nullptr;
+    H.cout = q.dst.c; H.pitch = q.dst.pitch; H.act = q.act; H.act_scale = q.act_scale;
+    total += q.dst.c * pl->bn * 4;
+  }
+  CPN_REQUIRE(total <= TC_PROJ_SMEM_MAX, "conv_tc: fused projection weights (%d B) exceed %d B", total, TC_PROJ_SMEM_MAX);
+  pl->p.nproj = n;
+  pl->proj_smem_bytes = total;
+  pl->smem_bytes += total;
+  return 0;
+}
+
+void conv_tc_bind_proj_out(ConvTcPlan* pl, int head, void* out) { pl->p.proj[head].out = reinterpret_cast<float*>(out); }
 
 void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
 

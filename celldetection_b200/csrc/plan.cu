@@ -117,6 +117,10 @@ extern "C" int cpn_plan_create(const cpn_op_t* ops_host, int n_ops, const void* 
                                 op.res.n ? pl->arena + op.res.offset : nullptr, pl->weights + op.w_offset, bias,
                                 &pl->tc[i]))
           return fail();
+        if (op.fuse_next > 0) {   // the next `fuse_next` PROJ ops run inside this convolution's epilogue
+          if (i + op.fuse_next > n_ops - 1) { set_error("op %d: fuse_next out of range", i); return fail(); }
+          if (conv_tc_fuse_proj(pl->tc[i], op.fuse_next, &pl->ops[i + 1], pl->weights)) return fail();
+        }
       } else if (op.engine != CPN_ENGINE_SIMT) {
         set_error("op %d: unknown conv engine %d", i, op.engine);
         return fail();
@@ -124,6 +128,7 @@ extern "C" int cpn_plan_create(const cpn_op_t* ops_host, int n_ops, const void* 
     }
     if (op.kind < CPN_OP_PREP || op.kind > CPN_OP_PROJ) { set_error("op %d: unknown kind %d", i, op.kind); return fail(); }
     pl->n_launches += 1;
+    if (op.kind == CPN_OP_CONV && op.engine == CPN_ENGINE_TCGEN05 && op.fuse_next > 0) pl->n_launches -= op.fuse_next;
   }
   *plan_out = pl;
   return 0;
@@ -147,7 +152,16 @@ static int run_op(cpn_plan* pl, int i, const void* input, int input_format, void
       CPN_REQUIRE(input != nullptr, "forward: input pointer is NULL");
       return prep_launch(op, input, input_format, dst, pl->flags, st);
     case CPN_OP_CONV:
-      if (op.engine == CPN_ENGINE_TCGEN05) return conv_tc_launch(pl->tc[i], st);
+      if (op.engine == CPN_ENGINE_TCGEN05) {
+        for (int h = 0; h < op.fuse_next; ++h) {   // bind the fused projections' caller-provided output buffers
+          const cpn_op_t& q = pl->ops[i + 1 + h];
+          CPN_REQUIRE(q.out_binding < 0 || (q.out_binding < n_outputs && outputs && outputs[q.out_binding]),
+                      "op %d: output binding %d not provided", i + 1 + h, q.out_binding);
+          char* base = q.out_binding >= 0 ? reinterpret_cast<char*>(outputs[q.out_binding]) : pl->arena;
+          conv_tc_bind_proj_out(pl->tc[i], h, base + q.dst.offset);
+        }
+        return conv_tc_launch(pl->tc[i], st);
+      }
       return conv_simt_launch(op, src, dst, op.res.n ? pl->arena + op.res.offset : nullptr, pl->weights + op.w_offset,
                               bias, st);
     case CPN_OP_MAXPOOL: return maxpool_launch(op, src, dst, st);
@@ -164,8 +178,11 @@ extern "C" int cpn_plan_forward(cpn_plan_t* plan, const void* input, int input_f
                                 int n_outputs, void* stream) {
   CPN_REQUIRE(plan, "plan_forward: NULL plan");
   cudaStream_t st = (cudaStream_t)stream;
-  for (int i = 0; i < (int)plan->ops.size(); ++i)
+  for (int i = 0; i < (int)plan->ops.size(); ++i) {
     if (run_op(plan, i, input, input_format, outputs_host, n_outputs, st)) return 1;
+    const cpn_op_t& op = plan->ops[i];
+    if (op.kind == CPN_OP_CONV && op.engine == CPN_ENGINE_TCGEN05) i += op.fuse_next;  // ran inside the epilogue
+  }
   return 0;
 }
 

@@ -42,8 +42,72 @@ __global__ void prep_kernel(const void* __restrict__ in, int fmt, T* __restrict_
   if (bad) atomicOr(flags, 1);
 }
 
+// PREP, im2col mode (op.r > 0): the network input is expanded to the K-major operand of the stem convolution,
+//   dst[n, oy, ox, (r*k + s)*C + c] = in[n, c, oy*stride - pad + r, ox*stride - pad + s]   (zero outside, zero-padded
+// to a multiple of 64 channels), so that the C_in = 3 stem (7x7 s2, resnet.py:273; 3x3 s1, unet.py:52) runs on the
+// tensor cores as a 1x1 convolution with K = 64-padded k*k*C.  One thread writes 8 consecutive channels (16 bytes).
+template <typename T>
+__global__ void prep_im2col_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out, int N, int C, int H, int W,
+                                   int Ho, int Wo, int Kp, int pitch, int k, int stride, int pad,
+                                   int32_t* __restrict__ flags) {
+  const int chunks = Kp / 8;
+  const long long total = (long long)N * Ho * Wo * chunks;
+  const int kk = k * k * C;
+  bool bad = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    long long pix = i / chunks;
+    const int ox = (int)(pix % Wo);
+    pix /= Wo;
+    const int oy = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    T vals[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = ch * 8 + j;
+      float v = 0.f;
+      if (e < kk) {
+        const int tap = e / C, c = e - tap * C;
+        const int r = tap / k, s_ = tap - r * k;
+        const int iy = oy * stride - pad + r, ix = ox * stride - pad + s_;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          if (fmt == CPN_IN_F32_NCHW) {
+            v = reinterpret_cast<const float*>(in)[(((long long)n * C + c) * H + iy) * W + ix];
+            bad |= !(v >= 0.f && v <= 1.f);
+          } else if (fmt == CPN_IN_U8_NCHW) {
+            v = (float)reinterpret_cast<const uint8_t*>(in)[(((long long)n * C + c) * H + iy) * W + ix] / 255.f;
+          } else {
+            v = (float)reinterpret_cast<const uint8_t*>(in)[(((long long)n * H + iy) * W + ix) * C + c] / 255.f;
+          }
+        }
+      }
+      vals[j] = from_f32<T>(v);
+    }
+    T* o = out + (((long long)n * Ho + oy) * Wo + ox) * pitch + ch * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = vals[j];
+  }
+  if (bad) atomicOr(flags, 1);
+}
+
 int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* dst, int32_t* flags, cudaStream_t st) {
   CPN_REQUIRE(input_format >= 0 && input_format <= 2, "prep: bad input format %d", input_format);
+  if (op.r > 0) {  // im2col mode: src view describes the logical input (n, h, w, c)
+    CPN_REQUIRE(op.dst.c % 8 == 0 && op.dst.pitch % 8 == 0 && op.dst.c >= op.r * op.r * op.src.c,
+                "prep(im2col): dst channels %d must be a multiple of 8 and >= k*k*c", op.dst.c);
+    const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * (op.dst.c / 8);
+    const int grid = grid_for(total, 256);
+    if (op.dst.dtype == CPN_DT_F32)
+      prep_im2col_kernel<float><<<grid, 256, 0, st>>>(input, input_format, (float*)dst, op.src.n, op.src.c, op.src.h,
+                                                      op.src.w, op.dst.h, op.dst.w, op.dst.c, op.dst.pitch, op.r,
+                                                      op.stride, op.pad, flags);
+    else
+      prep_im2col_kernel<__half><<<grid, 256, 0, st>>>(input, input_format, (__half*)dst, op.src.n, op.src.c, op.src.h,
+                                                       op.src.w, op.dst.h, op.dst.w, op.dst.c, op.dst.pitch, op.r,
+                                                       op.stride, op.pad, flags);
+    CPN_CHECK_LAUNCH();
+    return 0;
+  }
   const long long total = (long long)op.dst.n * op.dst.h * op.dst.w;
   const int grid = grid_for(total, 256);
   if (op.dst.dtype == CPN_DT_F32)

@@ -10,6 +10,7 @@
 //   gather   : row gather (resolve_keep_indices)                             models/cpn.py:53-60
 // All of it is HBM-/latency-bound gather-scatter work; no tensor cores.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace cpn {
 
@@ -423,57 +424,64 @@ __device__ __forceinline__ void st_cs_f4(float* p, float a, float b, float c, fl
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(F2C_TX * F2C_TY, 4) f2c_fast_kernel(const float* __restrict__ fourier,
+template <int MINB>
+__global__ void __launch_bounds__(F2C_TX * F2C_TY, MINB) f2c_fast_kernel(const float* __restrict__ fourier,
                                                                        const float* __restrict__ locations,
                                                                        long long P, int order, int samples,
                                                                        const float* __restrict__ trig,
                                                                        float* __restrict__ out, int txe) {
+  // Warp-granular software pipeline: every warp owns a double-buffered coefficient tile of PBW proposals and runs its
+  // own cp.async prefetch / compute / store loop, synchronising with __syncwarp only (no block barriers in the loop).
   extern __shared__ __align__(16) float fsm[];
   const int np = samples / 2;             // multiple of 4
   const int row = order * 4;              // floats per proposal
   const int cstride = row + 4;            // padded row (16-byte multiple)
+  constexpr int NWARP = F2C_TX * F2C_TY / 32;
+  const int rows_w = 32 / txe;            // proposal rows (of F2C_TP proposals) per warp
+  const int PBW = rows_w * F2C_TP;        // proposals per warp iteration
   float* cos_s = fsm;                     // [order][np]
   float* sin_s = fsm + order * np;        // [order][np]
-  float* coef0 = fsm + 2 * order * np;    // 2 x [PB][cstride]
-  const int PB = (F2C_TX * F2C_TY / txe) * F2C_TP;  // proposals per block iteration (txe threads share a proposal row)
-  float* loc0 = coef0 + 2 * PB * cstride;  // 2 x [PB][2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* coef0 = fsm + 2 * order * np + warp * 2 * PBW * cstride;          // this warp: 2 x [PBW][cstride]
+  float* loc0 = fsm + 2 * order * np + NWARP * 2 * PBW * cstride + warp * 2 * PBW * 2;  // this warp: 2 x [PBW][2]
   for (int i = threadIdx.x; i < order * np; i += blockDim.x) {
     const int k = i / np, j = i - k * np;
     cos_s[i] = trig[k * samples + j];
     sin_s[i] = trig[(order + k) * samples + j];
   }
-  const int tx = threadIdx.x % txe, ty = threadIdx.x / txe;
-  const long long nblk = (P + PB - 1) / PB;
+  __syncthreads();
+  const int tx = lane % txe, ty = lane / txe;
+  const long long ntile = (P + PBW - 1) / PBW;
+  const long long wid = (long long)blockIdx.x * NWARP + warp, nw = (long long)gridDim.x * NWARP;
   const int chunks_per_row = row / 4;     // 16-byte chunks per proposal
 
-  auto prefetch = [&](long long blk, int buf) {
-    const long long p0 = blk * PB;
-    const int npr = (int)min((long long)PB, P - p0);
-    float* cb = coef0 + buf * PB * cstride;
-    for (int i = threadIdx.x; i < npr * chunks_per_row; i += blockDim.x) {
+  auto prefetch = [&](long long t, int buf) {
+    const long long p0 = t * PBW;
+    const int npr = (int)min((long long)PBW, P - p0);
+    float* cb = coef0 + buf * PBW * cstride;
+    for (int i = lane; i < npr * chunks_per_row; i += 32) {
       const int pl = i / chunks_per_row, c = i - pl * chunks_per_row;
       cp_async16(cb + pl * cstride + c * 4, fourier + (p0 + pl) * row + c * 4);
     }
-    float* lb = loc0 + buf * PB * 2;
-    for (int i = threadIdx.x; i < npr / 2; i += blockDim.x) cp_async16(lb + i * 4, locations + p0 * 2 + i * 4);
-    if ((npr & 1) && threadIdx.x == 0) {   // odd tail proposal: plain loads (visible after the barrier)
+    float* lb = loc0 + buf * PBW * 2;
+    for (int i = lane; i < npr / 2; i += 32) cp_async16(lb + i * 4, locations + p0 * 2 + i * 4);
+    if ((npr & 1) && lane == 0) {          // odd tail proposal: plain loads (visible after __syncwarp)
       lb[(npr - 1) * 2] = locations[(p0 + npr - 1) * 2];
       lb[(npr - 1) * 2 + 1] = locations[(p0 + npr - 1) * 2 + 1];
     }
   };
 
   int buf = 0;
-  if ((long long)blockIdx.x < nblk) prefetch(blockIdx.x, 0);
+  if (wid < ntile) prefetch(wid, 0);
   cp_async_commit();
-  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x, buf ^= 1) {
-    const long long nxt = blk + gridDim.x;
-    if (nxt < nblk) prefetch(nxt, buf ^ 1);
+  for (long long t = wid; t < ntile; t += nw, buf ^= 1) {
+    if (t + nw < ntile) prefetch(t + nw, buf ^ 1);
     cp_async_commit();
     cp_async_wait<1>();
-    __syncthreads();
-    const long long p0 = blk * PB;
-    const float* cb = coef0 + buf * PB * cstride;
-    const float* lb = loc0 + buf * PB * 2;
+    __syncwarp();
+    const long long p0 = t * PBW;
+    const float* cb = coef0 + buf * PBW * cstride;
+    const float* lb = loc0 + buf * PBW * 2;
     for (int j0 = 0; j0 < np; j0 += txe * 4) {
       const int j = j0 + tx * 4;          // this thread's 4 adjacent pairs j .. j+3
       if (j < np) {
@@ -522,7 +530,7 @@ __global__ void __launch_bounds__(F2C_TX * F2C_TY, 4) f2c_fast_kernel(const floa
         }
       }
     }
-    __syncthreads();   // everyone is done with `buf` before the next iteration's prefetch overwrites it
+    __syncwarp();   // all lanes are done with `buf` before the next iteration's prefetch overwrites it
   }
   cp_async_wait<0>();
 }
@@ -638,17 +646,24 @@ extern "C" int cpn_fouriers2contours(const float* fourier, const float* location
     const int nph = samples / 2;
     int txe = 16;
     while (txe > 1 && txe * 4 > nph) txe >>= 1;          // threads per proposal row: 4 adjacent pairs each
-    const int pb = (F2C_TX * F2C_TY / txe) * F2C_TP;
+    const int pb = (F2C_TX * F2C_TY / txe) * F2C_TP;     // proposals per block iteration (all warps together)
     const size_t fsmem = ((size_t)2 * order * nph + 2 * (size_t)pb * (order * 4 + 4) + 2 * (size_t)pb * 2) * sizeof(float);
     if (fsmem <= 200 * 1024) {
       static size_t fconfigured = 0;
       if (fsmem > 48 * 1024 && fsmem > fconfigured) {
-        CPN_CHECK_CUDA(cudaFuncSetAttribute(f2c_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        CPN_CHECK_CUDA(cudaFuncSetAttribute(f2c_fast_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        CPN_CHECK_CUDA(cudaFuncSetAttribute(f2c_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         fconfigured = fsmem;
       }
       const long long nb = (P + pb - 1) / pb;
-      f2c_fast_kernel<<<capped_grid(nb, 4), F2C_TX * F2C_TY, fsmem, st>>>(fourier, locations, P, order, samples, trig,
-                                                                          out, txe);
+      static int minb = 0;
+      if (minb == 0) { const char* e = getenv("CPN_F2C_MINB"); minb = (e && atoi(e) == 4) ? 4 : 3; }
+      if (minb == 4)
+        f2c_fast_kernel<4><<<capped_grid(nb, 4), F2C_TX * F2C_TY, fsmem, st>>>(fourier, locations, P, order, samples,
+                                                                               trig, out, txe);
+      else
+        f2c_fast_kernel<3><<<capped_grid(nb, 3), F2C_TX * F2C_TY, fsmem, st>>>(fourier, locations, P, order, samples,
+                                                                               trig, out, txe);
       CPN_CHECK_LAUNCH();
       return 0;
     }

@@ -162,7 +162,7 @@ class CPN(nn.Module):
         plan = self._plans.get(key)
         if plan is None:
             g = trace(self.arch, n, h, w, in_channels=self.in_channels, order=self.core_order,
-                      refinement_margin=self.refinement_margin)
+                      refinement_margin=self.refinement_margin, stem_im2col=fast)
             pack = self._packs.get(fast)
             if pack is None:
                 with torch.no_grad():

@@ -74,11 +74,14 @@ class LOp:
     cin_off: int = 0     # proj: input channel slice
     cin: int = 0
     name: str = ''
+    im2col: Optional[Tuple[int, int]] = None   # (k, cin) of the original convolution when it runs as a 1x1 on an
+                                               # im2col'd input (tensor-core stem), or of the prep op producing it
 
 
 class Tracer:
-    def __init__(self, n, h, w):
+    def __init__(self, n, h, w, stem_im2col=False):
         self.n, self.h, self.w = n, h, w
+        self.stem_im2col = stem_im2col   # run C_in<=4 stem convolutions on the tensor cores via an im2col'd input
         self.tensors: List[TT] = []
         self.ops: List[LOp] = []
         self.spec = OrderedDict()   # state_dict key -> (shape, role)
@@ -113,7 +116,26 @@ class Tracer:
         return op.dst
 
     def prep(self, c):
-        return self._emit(LOp('prep', dst=self.tensor(c, self.h, self.w), name='input'))
+        t = self._emit(LOp('prep', dst=self.tensor(c, self.h, self.w), name='input'))
+        t.is_input = True
+        return t
+
+    def stem_conv(self, x, cout, k, stride, act, params, name):
+        """Convolution on the raw network input.  With ``stem_im2col`` the preceding prep op is turned into an im2col
+        producer (K = k*k*c padded to 64) and the convolution becomes a 1x1 over it (same arithmetic, K reordered)."""
+        pad = k // 2
+        if not (self.stem_im2col and getattr(x, 'is_input', False) and self.ops[-1].kind == 'prep'):
+            return self.conv(x, cout, k, stride=stride, act=act, params=params, name=name)
+        prep = self.ops[-1]
+        cin = x.c
+        ho, wo = (x.h + 2 * pad - k) // stride + 1, (x.w + 2 * pad - k) // stride + 1
+        kp = (k * k * cin + 63) // 64 * 64
+        prep.src = TT(-1, cin, x.h, x.w)           # logical input (not an arena tensor)
+        prep.k, prep.stride, prep.pad, prep.im2col = k, stride, pad, (k, cin)
+        x.c, x.h, x.w = kp, ho, wo                 # the prep output is now the im2col matrix
+        op = LOp('conv', src=x, dst=self.tensor(cout, ho, wo), k=1, stride=1, pad=0, act=act, params=params,
+                 name=name, im2col=(k, cin))
+        return self._emit(op)
 
     def conv(self, x, cout, k, stride=1, pad=None, act='none', res=None, params=None, name=''):
         pad = k // 2 if pad is None else pad
@@ -164,6 +186,8 @@ def _conv_bn_act(g: Tracer, x, key, bn_key, cin, cout, k, stride=1, bias=True, g
     if bn_key is not None:
         g.bn_spec(bn_key, cout, res_branch)
     p = ConvParams([key + '.weight'], [key + '.bias' if bias else None], [bn_key], groups)
+    if getattr(x, 'is_input', False) and res is None and groups == 1:
+        return g.stem_conv(x, cout, k, stride, act, p, key)
     return g.conv(x, cout, k, stride=stride, act=act, res=res, params=p, name=key)
 
 
@@ -323,12 +347,13 @@ def _read_out_spec(g, p, cin, cmid, cout, k=7):
     g.conv_spec(f'{p}.block.4', cmid, cout, 1, True)
 
 
-def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_margin=3., refinement_buckets=1):
+def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_margin=3., refinement_buckets=1,
+          stem_im2col=False):
     """Trace architecture `arch` for an [n, in_channels, h, w] input.  Returns the Tracer; ``g.outputs`` maps
     'scores' / 'locfou' / 'refinement' to fp32 output tensors (bindings 0 / 1 / 2)."""
     assert arch in ARCHS, arch
     assert score_channels == 1 and refinement_buckets == 1, 'only classes<=2 and refinement_buckets=1 are in scope'
-    g = Tracer(n, h, w)
+    g = Tracer(n, h, w, stem_im2col=stem_im2col)
     g.spec['order_weights'] = ((order, 1), 'order_weights')   # buffer of CPN (cpn.py:406-412)
     bb = 'core.backbone'
     x = g.prep(in_channels)
@@ -381,7 +406,8 @@ def conv_flops(g: Tracer):
     total = 0
     for op in g.ops:
         if op.kind == 'conv':
-            total += 2 * g.n * op.dst.h * op.dst.w * op.dst.c * (op.src.c // op.params.groups) * op.k * op.k
+            kk = op.im2col[0] ** 2 * op.im2col[1] if op.im2col else (op.src.c // op.params.groups) * op.k * op.k
+            total += 2 * g.n * op.dst.h * op.dst.w * op.dst.c * kk
         elif op.kind == 'proj':
             total += 2 * g.n * op.dst.h * op.dst.w * op.dst.c * op.cin
     return total

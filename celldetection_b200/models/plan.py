@@ -83,6 +83,11 @@ class WeightPack:
                 continue
             w, b = fold_conv(sd, op.params)
             w, b = w.to(device), b.to(device)
+            if op.kind == 'conv' and op.im2col is not None:   # [cout, cin, k, k] -> [cout, (r*k+s)*cin + c] padded
+                cout_ = w.shape[0]
+                wk = w.permute(0, 2, 3, 1).reshape(cout_, -1)
+                w = torch.zeros(cout_, op.src.c, 1, 1, dtype=w.dtype, device=device)
+                w[:, :wk.shape[1], 0, 0] = wk
             if op.kind == 'proj':
                 wp = w.reshape(w.shape[0], w.shape[1]).contiguous().float()
                 eng = -1
@@ -172,13 +177,17 @@ class Plan:
                 o.out_binding = lop.dst.binding
             else:
                 o.dst = _view(lop.dst, g.n, offsets, es, act_dt)
-            if lop.src is not None:
+            if lop.kind == 'prep' and lop.src is not None:   # im2col prep: logical input dims
+                v = L.View()
+                v.offset, v.n, v.h, v.w, v.c, v.pitch, v.dtype = 0, g.n, lop.src.h, lop.src.w, lop.src.c, lop.src.c, L.DT_F32
+                o.src = v
+            elif lop.src is not None:
                 o.src = _view(lop.src, g.n, offsets, es, act_dt)
             else:
                 o.src = o.dst
             if lop.res is not None:
                 o.res = _view(lop.res, g.n, offsets, es, act_dt)
-            o.r = o.s = lop.k
+            o.r = o.s = (lop.k if (lop.kind != 'prep' or lop.im2col) else 0)
             o.stride, o.pad = lop.stride, lop.pad
             o.act, o.act_scale = act_map[lop.act], lop.act_scale
             if lop.kind in ('conv', 'proj'):
@@ -190,6 +199,24 @@ class Plan:
                     self.engines.append(eng)
                 else:
                     o.proj_cin_off, o.proj_cin = lop.cin_off, lop.cin
+        # ---- fuse ReadOut projections into the epilogue of the tcgen05 convolution that feeds them ----
+        self.fused = set()
+        if fast:
+            for i, lop in enumerate(g.ops):
+                if lop.kind != 'conv' or ops[i].engine != L.ENGINE_TCGEN05 or lop.res is not None:
+                    continue
+                c = lop.dst.c
+                bn = 256 if c % 256 == 0 else (128 if c % 128 == 0 else 64)
+                nt = c // bn
+                nxt = g.ops[i + 1:i + 1 + nt]
+                if nt > 4 or len(nxt) != nt or lop.params.groups != 1:
+                    continue
+                ok = all(q.kind == 'proj' and q.src is lop.dst and q.cin == bn and q.cin_off == h * bn and q.dst.c <= 24
+                         for h, q in enumerate(nxt))
+                users = sum(1 for q in g.ops if q.src is lop.dst or q.res is lop.dst)
+                if ok and users == nt and sum(q.dst.c for q in nxt) * bn * 4 <= 24576:
+                    ops[i].fuse_next = nt
+                    self.fused.update(range(i + 1, i + 1 + nt))
         self.ops = ops
         handle = ctypes.c_void_p()
         L.check(lib.cpn_plan_create(ops, len(g.ops), L.ptr(pack.blob), pack.blob.numel(), L.ptr(self.arena),

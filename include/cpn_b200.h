@@ -55,7 +55,9 @@ typedef struct {
 
 enum {
   CPN_OP_PREP = 0,      /* network input -> NHWC activations; fuses Normalize's range check (commons.py:694-700),
-                           uint8 -> float / 255 (lightning_base.py:774-780) and the layout change */
+                           uint8 -> float / 255 (lightning_base.py:774-780) and the layout change.  With r > 0 it
+                           writes the im2col operand of a k=r, stride, pad stem convolution instead:
+                           dst[n,oy,ox,(r*k+s)*C+c] = in[n,c,oy*stride-pad+r,ox*stride-pad+s], zero-padded channels */
   CPN_OP_CONV = 1,      /* conv (+ folded BN) (+ residual) (+ ReLU)  */
   CPN_OP_MAXPOOL = 2,   /* nn.MaxPool2d(k, stride, pad), -inf padding */
   CPN_OP_UPSAMPLE = 3,  /* F.interpolate(mode='nearest'): src = floor(dst * in / out) */
@@ -89,7 +91,9 @@ typedef struct {
   int32_t proj_cin_off;  /* PROJ: first input channel of the slice this projection contracts over */
   int32_t proj_cin;      /* PROJ: number of input channels */
   int32_t out_binding;   /* PROJ/any: -1 -> dst is in the arena; >= 0 -> dst is the caller's output pointer #k */
-  int32_t reserved;
+  int32_t fuse_next;     /* CONV (TCGEN05): number of immediately following PROJ ops computed inside this
+                            convolution's epilogue (one per output-channel tile, in tile order); they are skipped by
+                            cpn_plan_forward and the convolution's own dst is then not written */
 } cpn_op_t;
 
 typedef struct cpn_plan cpn_plan_t;

@@ -37,16 +37,21 @@ def _model(z, precision):
 
 
 def _compare_outputs(out, z, n):
-    stats = dict(count=[], ref_count=[], matched=[], max_vertex_err=0., max_box_err=0.)
+    stats = dict(count=[], ref_count=[], matched=[], max_vertex_err=0., max_box_err=0., max_proposal_err=0.,
+                 vertices=0, vertices_within_half_px=0)
     for i in range(n):
         rb = z[f'out/{i}/boxes']
         gb = out['boxes'][i].cpu().numpy()
         pairs = match_by_box(gb, rb)
         stats['count'].append(len(gb)), stats['ref_count'].append(len(rb)), stats['matched'].append(len(pairs))
         for a, b in pairs:
-            stats['max_vertex_err'] = max(stats['max_vertex_err'], float(
-                np.abs(out['contours'][i][a].cpu().numpy() - z[f'out/{i}/contours'][b]).max()))
+            d = np.abs(out['contours'][i][a].cpu().numpy() - z[f'out/{i}/contours'][b]).max(-1)
+            stats['max_vertex_err'] = max(stats['max_vertex_err'], float(d.max()))
+            stats['vertices'] += int(d.size)
+            stats['vertices_within_half_px'] += int((d < 0.5).sum())
             stats['max_box_err'] = max(stats['max_box_err'], float(np.abs(gb[a] - rb[b]).max()))
+            stats['max_proposal_err'] = max(stats['max_proposal_err'], float(
+                np.abs(out['contour_proposals'][i][a].cpu().numpy() - z[f'out/{i}/contour_proposals'][b]).max()))
     return stats
 
 
@@ -74,8 +79,9 @@ def test_strict_fp32_model_matches_reference(name):
 
 @pytest.mark.parametrize('name', MODEL_FIXTURES)
 def test_fp16_tensor_core_model_close_to_reference(name):
-    """fp16 storage / fp32 accumulate engine: head tensors within 2e-2 rel, matched contours within 0.5 px, instance
-    count within max(2, 10 %) of the reference (thresholding is discontinuous; the exact flip rate is reported)."""
+    """fp16 storage / fp32 accumulate engine: head tensors within 2e-2 rel, decoded contour vertices (proposals) of
+    matched instances within 0.5 px, >= 95 % of the refined vertices within 0.5 px (torch.round in the refinement loop
+    is discontinuous), instance count within max(2, 10 %) of the reference.  Exact figures go to the parity report."""
     z = load_npz(name)
     m, (n, h, w) = _model(z, 'fp16')
     x = torch.from_numpy(z['x']).cuda()
@@ -90,7 +96,8 @@ def test_fp16_tensor_core_model_close_to_reference(name):
         assert e < 2e-2, (k, e)
     for c, r, mt in zip(st['count'], st['ref_count'], st['matched']):
         assert abs(c - r) <= max(2, 0.1 * r) and mt >= 0.8 * r, st
-    assert st['max_vertex_err'] < 0.5 or sum(st['matched']) == 0, st
+    assert st['max_proposal_err'] < 0.5, st
+    assert st['vertices_within_half_px'] >= 0.95 * st['vertices'], st
 
 
 def test_input_contract_and_uint8_path():
