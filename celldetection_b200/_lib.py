@@ -54,6 +54,8 @@ SYMBOLS = {
     'cpn_fouriers2contours': (_I, [_P, _P, _I64, _I, _I, _P, _P, _P, _P]),
     'cpn_nms_workspace_bytes': (_SZ, [_I64, _I]),
     'cpn_nms_segments': (_I, [_P, _P, _P, _I, _I64, _F, _I, _P, _P, _P, _P]),
+    'cpn_nms_grid_workspace_bytes': (_SZ, [_I64]),
+    'cpn_nms_grid': (_I, [_P, _P, _I64, _F, _P, _P, _P, ctypes.POINTER(_I), _P]),
     'cpn_border_filter': (_I, [_P, _P, _P, _I64, _I, _F, _P, _P]),
     'cpn_gather_rows': (_I, [_P, _I64, _P, _I64, _P, _P]),
 }

@@ -1,6 +1,6 @@
 // Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (fp16 x fp16 -> fp32 in TMEM), operands staged by
 // TMA (im2col-free: one 4-D box load per filter tap with out-of-bounds zero fill), mbarrier pipeline, persistent CTAs,
-// warp-specialised (1 TMA warp, 1 MMA warp, 4 epilogue warps), double-buffered TMEM accumulators.
+// warp-specialised (1 TMA warp, 1 MMA warp, 8 epilogue warps), double-buffered TMEM accumulators.
 //
 // Replaces nn.Conv2d (+ folded BatchNorm2d) (+ residual) (+ ReLU) on the dense stages of the path:
 //   /root/reference/celldetection/models/commons.py:494-500 (ReadOut 7x7), :120-149 (TwoConvNormRelu 3x3),
@@ -18,13 +18,16 @@
 // B operand: weights pre-packed as fp16 [R*S][cout][kslab] (K-major) through a 3-D tensor map, box {64, BN, 1}.
 // Grouped convolutions use BN = 64 and contract only over their 64-channel block-diagonal slab (cpn_op_t::kslab).
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
 namespace cpn {
 
 constexpr int TC_BW = 16, TC_BH = 8, TC_BM = 128, TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                        // two warps per TMEM lane quadrant, each takes every other chunk
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_SMEM_BUDGET = 196608;  // bytes of operand stages
 constexpr int TC_PROJ_SMEM_MAX = 24576; // fused projection weights (fp32)
 
@@ -56,11 +59,16 @@ struct ConvTcParams {
   int relu;
   int tiles_x, tiles_y, tiles_n;
   long long total_tiles;
+  // halo variant (stride-1 kxk): activations of one 64-channel block are staged ONCE per tile as a (16+R-1) x
+  // (8*MSUB+S-1) pixel patch and every filter tap addresses a shifted window of it
+  CUtensorMap tmH;          // (C, W, H, N), box {8, PW, PH, 1}, no swizzle
+  int halo, pw, ph, plane_stride, nb_stages, swap_lbo_sbo;
 };
 
 struct ConvTcPlan {
   ConvTcParams p;
   int proj_smem_bytes;
+  int msub;
   int bn;
   int stages;
   int smem_bytes;
@@ -172,10 +180,128 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// K-major, no-swizzle ("interleaved") descriptor: core matrix = 8 rows x 16 bytes with rows 16 bytes apart;
+// LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_nosw_kmajor_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6), a_format F16 = 0 @ [7,10),
 // b_format F16 = 0 @ [10,13), a_major = b_major = K (0), n_dim = N >> 3 @ [17,23), m_dim = M >> 4 @ [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Epilogue of one accumulator (128 rows x BN columns in TMEM at `taddr`): this thread owns output pixel (img, y, x).
+// Either the fused ReadOut projection (p.nproj > 0) or bias / residual / ReLU / fp16 store of every other 32-column
+// chunk (`half` selects which of the two warps of a lane quadrant this is).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint32_t taddr, const int img, const int y,
+                                              const int x, const int n_tile, const int n0, const int half,
+                                              const float* proj_w) {
+  const bool valid = (y < p.Ho) && (x < p.Wo);
+  __half* op = p.out + (((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0;
+  const __half* rp = nullptr;
+  if (p.res && valid) {
+    const int ry = (p.res_h == p.Ho) ? y : (int)(((long long)y * p.res_h) / p.Ho);
+    const int rx = (p.res_w == p.Wo) ? x : (int)(((long long)x * p.res_w) / p.Wo);
+    rp = p.res + (((long long)img * p.res_h + ry) * p.res_w + rx) * p.res_pitch + n0;
+  }
+  if (p.nproj > 0) {
+    // ---- fused ReadOut: bias + ReLU on the fp32 accumulators, then the 1x1 projection of this N tile's head ----
+    const ProjHead& H = p.proj[n_tile];
+    int woff = 0;
+    for (int h = 0; h < n_tile; ++h) woff += p.proj[h].cout * BN;
+    const float* wh = proj_w + woff;
+    float pacc[TC_PROJ_MAX];
+#pragma unroll
+    for (int j = 0; j < TC_PROJ_MAX; ++j) pacc[j] = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(taddr + ch * 32, v);
+      tmem_ld_wait();
+      float f[32];
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 b = p.bias ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + b.x;
+        f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + b.y;
+        f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + b.z;
+        f[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + b.w;
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < TC_PROJ_MAX; ++j) {
+        if (j < H.cout) {
+          const float4* w4 = reinterpret_cast<const float4*>(wh + j * BN + ch * 32);
+          float a = pacc[j];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 w = w4[q];
+            a = fmaf(f[q * 4 + 0], w.x, a);
+            a = fmaf(f[q * 4 + 1], w.y, a);
+            a = fmaf(f[q * 4 + 2], w.z, a);
+            a = fmaf(f[q * 4 + 3], w.w, a);
+          }
+          pacc[j] = a;
+        }
+      }
+    }
+    if (valid) {
+      float* o = H.out + (((long long)img * p.Ho + y) * p.Wo + x) * H.pitch;
+#pragma unroll
+      for (int j = 0; j < TC_PROJ_MAX; ++j) {
+        if (j < H.cout) {
+          float r = pacc[j] + (H.b ? __ldg(H.b + j) : 0.f);
+          if (H.act == CPN_ACT_SCALED_TANH) r = tanhf(r) * H.act_scale;
+          else if (H.act == CPN_ACT_RELU) r = fmaxf(r, 0.f);
+          o[j] = r;
+        }
+      }
+    }
+  } else {
+#pragma unroll 1
+  for (int ch = half; ch < BN / 32; ch += 2) {
+    uint32_t v[32];
+    tmem_ld32(taddr + ch * 32, v);
+    tmem_ld_wait();
+    if (valid) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
+      uint4 packed[4];
+      uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 b = p.bias ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float f0 = __uint_as_float(v[q * 4 + 0]) + b.x, f1 = __uint_as_float(v[q * 4 + 1]) + b.y;
+        float f2 = __uint_as_float(v[q * 4 + 2]) + b.z, f3 = __uint_as_float(v[q * 4 + 3]) + b.w;
+        if (rp) {
+          const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp + ch * 32 + q * 4));
+          const __half2 r0 = *reinterpret_cast<const __half2*>(&rr.x), r1 = *reinterpret_cast<const __half2*>(&rr.y);
+          f0 += __low2float(r0); f1 += __high2float(r0); f2 += __low2float(r1); f3 += __high2float(r1);
+        }
+        if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+        __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
+        pk[q * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
+        pk[q * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+      }
+      uint4* o4 = reinterpret_cast<uint4*>(op + ch * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o4[q] = packed[q];
+    }
+  }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -221,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_tfull[i]), 1);
-      mbar_init(smem_u32(&bar_tempty[i]), 4);
+      mbar_init(smem_u32(&bar_tempty[i]), p.nproj > 0 ? 4 : TC_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -301,8 +427,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ================================ epilogue (4 warps, 128 rows) ================================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ================================ epilogue (8 warps, 128 rows x 2 column halves) ================================
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // which of the two warps of this quadrant (takes chunks ch % 2 == half)
+    if (p.nproj > 0 && half == 1) {     // the fused-projection epilogue keeps a whole row per thread: 4 warps only
+      // fall through to the teardown barrier
+    } else {
     const int row = quad * 32 + lane;
     const int py = row / TC_BW, px = row % TC_BW;
     int acc = 0;
@@ -314,112 +444,207 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
       const int y = (t_in / p.tiles_x) * TC_BH + py, x = (t_in % p.tiles_x) * TC_BW + px;
       const int n0 = n_tile * BN;
-      const bool valid = (y < p.Ho) && (x < p.Wo);
-      __half* op = p.out + (((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0;
-      const __half* rp = nullptr;
-      if (p.res && valid) {
-        const int ry = (p.res_h == p.Ho) ? y : (int)(((long long)y * p.res_h) / p.Ho);
-        const int rx = (p.res_w == p.Wo) ? x : (int)(((long long)x * p.res_w) / p.Wo);
-        rp = p.res + (((long long)img * p.res_h + ry) * p.res_w + rx) * p.res_pitch + n0;
-      }
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * BN;
-      if (p.nproj > 0) {
-        // ---- fused ReadOut: bias + ReLU on the fp32 accumulators, then the 1x1 projection of this N tile's head ----
-        const ProjHead& H = p.proj[n_tile];
-        int woff = 0;
-        for (int h = 0; h < n_tile; ++h) woff += p.proj[h].cout * BN;
-        const float* wh = proj_w + woff;
-        float pacc[TC_PROJ_MAX];
-#pragma unroll
-        for (int j = 0; j < TC_PROJ_MAX; ++j) pacc[j] = 0.f;
-#pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          uint32_t v[32];
-          tmem_ld32(taddr + ch * 32, v);
-          tmem_ld_wait();
-          float f[32];
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 b = p.bias ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + b.x;
-            f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + b.y;
-            f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + b.z;
-            f[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + b.w;
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < TC_PROJ_MAX; ++j) {
-            if (j < H.cout) {
-              const float4* w4 = reinterpret_cast<const float4*>(wh + j * BN + ch * 32);
-              float a = pacc[j];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 w = w4[q];
-                a = fmaf(f[q * 4 + 0], w.x, a);
-                a = fmaf(f[q * 4 + 1], w.y, a);
-                a = fmaf(f[q * 4 + 2], w.z, a);
-                a = fmaf(f[q * 4 + 3], w.w, a);
-              }
-              pacc[j] = a;
-            }
-          }
-        }
-        if (valid) {
-          float* o = H.out + (((long long)img * p.Ho + y) * p.Wo + x) * H.pitch;
-#pragma unroll
-          for (int j = 0; j < TC_PROJ_MAX; ++j) {
-            if (j < H.cout) {
-              float r = pacc[j] + (H.b ? __ldg(H.b + j) : 0.f);
-              if (H.act == CPN_ACT_SCALED_TANH) r = tanhf(r) * H.act_scale;
-              else if (H.act == CPN_ACT_RELU) r = fmaxf(r, 0.f);
-              o[j] = r;
-            }
-          }
-        }
-      } else {
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        tmem_ld_wait();
-        if (valid) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
-          uint4 packed[4];
-          uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 b = p.bias ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float f0 = __uint_as_float(v[q * 4 + 0]) + b.x, f1 = __uint_as_float(v[q * 4 + 1]) + b.y;
-            float f2 = __uint_as_float(v[q * 4 + 2]) + b.z, f3 = __uint_as_float(v[q * 4 + 3]) + b.w;
-            if (rp) {
-              const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp + ch * 32 + q * 4));
-              const __half2 r0 = *reinterpret_cast<const __half2*>(&rr.x), r1 = *reinterpret_cast<const __half2*>(&rr.y);
-              f0 += __low2float(r0); f1 += __high2float(r0); f2 += __low2float(r1); f3 += __high2float(r1);
-            }
-            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
-            __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
-            pk[q * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
-            pk[q * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-          }
-          uint4* o4 = reinterpret_cast<uint4*>(op + ch * 32);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) o4[q] = packed[q];
-        }
-      }
-      }
+      epilogue_rows<BN>(p, taddr, img, y, x, n_tile, n0, half, proj_w);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    }
   }
 
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Halo kernel: stride-1 kxk convolutions with operand reuse across filter taps.
+//   tile      = 16 rows x (8 * MSUB) columns of output pixels: MSUB accumulators of M = 128 (8 x 16 pixels each)
+//   A operand = per 64-channel block ONE patch of (16+R-1) x (8*MSUB+S-1) input pixels, stored as 8 planes
+//               [16-byte channel chunk][y][x] (8 TMA box loads {8, PW, PH, 1}, no swizzle).  Tap (r, s) of sub-tile j is
+//               the no-swizzle K-major descriptor starting at pixel (r, s + 8j): rows (8 consecutive x) 16 bytes apart,
+//               8-row groups (next y) PW*16 bytes apart, K chunks one plane apart -- no re-load per tap, so L2->SM
+//               traffic drops from R*S to ~(1 + halo) input reads.
+//   B operand = weights of one (tap, channel block): BN x 64 halves, SWIZZLE_128B, shared by the MSUB sub-tiles.
+// Warps: 0 = B producer, 1 = MMA issuer, 2 = A producer, 3.. = epilogue (8 warps).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TCH_THREADS = 96 + 32 * TC_EPI_WARPS;
+
+template <int BN, int MSUB>
+__global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t TMEM_COLS = 2 * MSUB * BN;
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
+  constexpr int MAX_NB = 8;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bar_bfull[MAX_NB];
+  __shared__ __align__(8) uint64_t bar_bempty[MAX_NB];
+  __shared__ __align__(8) uint64_t bar_afull[2];
+  __shared__ __align__(8) uint64_t bar_aempty[2];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = p.nb_stages;
+  const uint32_t patch_bytes = 8u * (uint32_t)p.plane_stride;
+  const uint32_t a_base = smem_base + nb * B_BYTES;                    // 2 patches behind the B ring
+  const uint32_t a_tx = 8u * (uint32_t)(p.ph * p.pw * 16);            // bytes the 8 box loads deliver
+  float* proj_w = reinterpret_cast<float*>(smem_raw + ((a_base - smem_u32(smem_raw)) + 2 * patch_bytes));
+  if (p.nproj > 0) {
+    int off = 0;
+    for (int h = 0; h < p.nproj; ++h) {
+      const int nw = p.proj[h].cout * BN;
+      for (int i = threadIdx.x; i < nw; i += blockDim.x) proj_w[off + i] = p.proj[h].w[i];
+      off += nw;
+    }
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmH);
+    prefetch_tmap(&p.tmB);
+    for (int i = 0; i < nb; ++i) { mbar_init(smem_u32(&bar_bfull[i]), 1); mbar_init(smem_u32(&bar_bempty[i]), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_afull[i]), 1);
+      mbar_init(smem_u32(&bar_aempty[i]), 1);
+      mbar_init(smem_u32(&bar_tfull[i]), 1);
+      mbar_init(smem_u32(&bar_tempty[i]), p.nproj > 0 ? 4 : TC_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int taps = p.R * p.S;
+  constexpr int TW = 8 * MSUB, TH = 16;
+
+  if (warp == 0) {
+    // ================================ B (weights) producer ================================
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t phb = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (int)(tile % p.tiles_n) * BN;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(smem_u32(&bar_bempty[sb]), phb ^ 1);
+            const uint32_t full = smem_u32(&bar_bfull[sb]);
+            mbar_expect_tx(full, B_BYTES);
+            tma_load_3d(smem_base + sb * B_BYTES, &p.tmB, full, cb * TC_BK, n0, tap);
+            if (++sb == nb) { sb = 0; phb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ A (activation patch) producer ================================
+    if (lane == 0) {
+      int ab = 0;
+      uint32_t pha = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const long long m_tile = tile / p.tiles_n;
+        const int img = (int)(m_tile / tiles_per_img);
+        const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
+        const int y0 = (t_in / p.tiles_x) * TH, x0 = (t_in % p.tiles_x) * TW;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          mbar_wait(smem_u32(&bar_aempty[ab]), pha ^ 1);
+          const uint32_t full = smem_u32(&bar_afull[ab]);
+          mbar_expect_tx(full, a_tx);
+          const uint32_t dst = a_base + ab * patch_bytes;
+#pragma unroll
+          for (int kc = 0; kc < 8; ++kc)
+            tma_load_4d(dst + kc * p.plane_stride, &p.tmH, full, cb * TC_BK + kc * 8, x0 - p.pad, y0 - p.pad, img);
+          ab ^= 1;
+          if (ab == 0) pha ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = make_idesc_f16(TC_BM, BN);
+    int sb = 0, ab = 0, acc = 0;
+    uint32_t phb = 0, pha = 0, acc_phase = 0;
+    const uint32_t lbo = p.swap_lbo_sbo ? (uint32_t)(p.pw * 16) : (uint32_t)p.plane_stride;
+    const uint32_t sbo = p.swap_lbo_sbo ? (uint32_t)p.plane_stride : (uint32_t)(p.pw * 16);
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      if (lane == 0) {
+        mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          mbar_wait(smem_u32(&bar_afull[ab]), pha);
+          tc_fence_after();
+          const uint32_t patch = a_base + ab * patch_bytes;
+          for (int tap = 0; tap < taps; ++tap) {
+            const int r = tap / p.S, s_ = tap - r * p.S;
+            mbar_wait(smem_u32(&bar_bfull[sb]), phb);
+            tc_fence_after();
+            const uint64_t db = make_sw128_kmajor_desc(smem_base + sb * B_BYTES);
+#pragma unroll
+            for (int j = 0; j < MSUB; ++j) {
+              const uint32_t win = patch + (uint32_t)((r * p.pw + s_ + 8 * j) * 16);
+              const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MSUB + j) * BN);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                const uint64_t da = make_nosw_kmajor_desc(win + (uint32_t)(2 * k) * p.plane_stride, lbo, sbo);
+                umma_f16(d_tmem, da, db + (uint64_t)(k * 2), idesc, (uint32_t)((cb | tap | k) != 0));
+              }
+            }
+            umma_commit(smem_u32(&bar_bempty[sb]));
+            if (++sb == nb) { sb = 0; phb ^= 1; }
+          }
+          umma_commit(smem_u32(&bar_aempty[ab]));   // patch free once every tap's MMAs have retired
+          ab ^= 1;
+          if (ab == 0) pha ^= 1;
+        }
+        umma_commit(smem_u32(&bar_tfull[acc]));
+      }
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;
+    const int half = (warp - 3) >> 2;
+    if (!(p.nproj > 0 && half == 1)) {
+      const int row = quad * 32 + lane;
+      const int py = row >> 3, px = row & 7;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = (int)(tile % p.tiles_n);
+        const long long m_tile = tile / p.tiles_n;
+        const int img = (int)(m_tile / tiles_per_img);
+        const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
+        const int y = (t_in / p.tiles_x) * TH + py, xb = (t_in % p.tiles_x) * TW + px;
+        mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < MSUB; ++j) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * MSUB + j) * BN);
+          epilogue_rows<BN>(p, taddr, img, y, xb + 8 * j, n_tile, n_tile * BN, half, proj_w);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -445,12 +670,13 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box) {
+                      const cuuint32_t* box, bool swizzle128 = true) {
   PFN_cuTensorMapEncodeTiled_v12000 fn = get_encode_fn();
   CPN_REQUIRE(fn != nullptr, "conv_tc: cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CPN_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu)",
               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2]);
@@ -522,11 +748,40 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   p.tiles_x = (op.dst.w + TC_BW - 1) / TC_BW; p.tiles_y = (op.dst.h + TC_BH - 1) / TC_BH;
   p.tiles_n = op.dst.c / bn;
   p.total_tiles = (long long)op.dst.n * p.tiles_x * p.tiles_y * p.tiles_n;
+  // ---- halo variant for stride-1 kxk dense convolutions (CPN_HALO=0 disables) ----
+  pl->msub = 1;
+  {
+    static int halo_env = -1, swap_env = -1;
+    if (halo_env < 0) { const char* e = getenv("CPN_HALO"); halo_env = (e && atoi(e) == 0) ? 0 : 1; }
+    if (swap_env < 0) { const char* e = getenv("CPN_HALO_SWAP"); swap_env = (e && atoi(e) == 1) ? 1 : 0; }
+    if (halo_env && op.stride == 1 && op.r * op.s > 1 && op.slab_mode == 0 && op.r <= 16 && op.s <= 16) {
+      const int msub = bn == 256 ? 1 : 2;
+      const int pw = 8 * msub + op.s - 1, ph = 16 + op.r - 1;
+      const int plane_stride = (ph * pw * 16 + 127) / 128 * 128;
+      const int patch = 8 * plane_stride;
+      const int b_bytes = bn * TC_BK * 2;
+      int nbs = (TC_SMEM_BUDGET - 2 * patch) / b_bytes;
+      if (nbs > 8) nbs = 8;
+      if (nbs >= 2 && pw <= 256 && ph <= 256) {
+        cuuint64_t dims[4] = {(cuuint64_t)op.src.c, (cuuint64_t)op.src.w, (cuuint64_t)op.src.h, (cuuint64_t)op.src.n};
+        cuuint64_t strides[3] = {(cuuint64_t)op.src.pitch * 2, (cuuint64_t)op.src.w * op.src.pitch * 2,
+                                 (cuuint64_t)op.src.h * op.src.w * op.src.pitch * 2};
+        cuuint32_t box[4] = {8, (cuuint32_t)pw, (cuuint32_t)ph, 1};
+        if (encode_map(&p.tmH, const_cast<void*>(src), 4, dims, strides, box, false)) { delete pl; return 1; }
+        p.halo = 1; p.pw = pw; p.ph = ph; p.plane_stride = plane_stride; p.nb_stages = nbs; p.swap_lbo_sbo = swap_env;
+        pl->msub = msub;
+        p.tiles_x = (op.dst.w + 8 * msub - 1) / (8 * msub);
+        p.tiles_y = (op.dst.h + 15) / 16;
+        p.total_tiles = (long long)op.dst.n * p.tiles_x * p.tiles_y * p.tiles_n;
+      }
+    }
+  }
   const int stage_bytes = TC_BM * TC_BK * 2 + bn * TC_BK * 2;
   pl->stages = TC_SMEM_BUDGET / stage_bytes;
   if (pl->stages > 8) pl->stages = 8;
   pl->proj_smem_bytes = 0;
   pl->smem_bytes = pl->stages * stage_bytes + 1024;
+  if (p.halo) pl->smem_bytes = p.nb_stages * bn * TC_BK * 2 + 2 * 8 * p.plane_stride + 1024;
   const long long sms = sm_count();
   pl->grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
   *out = pl;
@@ -546,7 +801,27 @@ static int launch_bn(const ConvTcPlan* pl, cudaStream_t st) {
   return 0;
 }
 
+template <int BN, int MSUB>
+static int launch_halo(const ConvTcPlan* pl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TC_SMEM_BUDGET + 1024 + TC_PROJ_SMEM_MAX));
+    attr_set = true;
+  }
+  conv_halo_kernel<BN, MSUB><<<pl->grid, TCH_THREADS, pl->smem_bytes, st>>>(pl->p);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
 int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t st) {
+  if (pl->p.halo) {
+    if (pl->bn == 64 && pl->msub == 2) return launch_halo<64, 2>(pl, st);
+    if (pl->bn == 128 && pl->msub == 2) return launch_halo<128, 2>(pl, st);
+    if (pl->bn == 256 && pl->msub == 1) return launch_halo<256, 1>(pl, st);
+    set_error("conv_tc: bad halo configuration BN %d MSUB %d", pl->bn, pl->msub);
+    return 1;
+  }
   switch (pl->bn) {
     case 64: return launch_bn<64>(pl, st);
     case 128: return launch_bn<128>(pl, st);

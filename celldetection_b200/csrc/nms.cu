@@ -235,6 +235,7 @@ struct NmsWs {
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int capped_blocks(int blocks) { const int cap = sm_count() * 8; return blocks > cap ? cap : (blocks < 1 ? 1 : blocks); }
 
 static size_t carve(void* base, int64_t n, int n_segments, NmsWs* ws) {
   const int64_t n_sub_max = (int64_t)n_segments + n / 1024 + 2;  // chunk >= 1024 enforced
@@ -326,5 +327,248 @@ extern "C" int cpn_nms_segments(const float* boxes, const float* scores, const i
   nms_group_kernel<<<n_segments, NMS_T, 0, st>>>(boxes, ws.vals_b, ws.group_start, seg_offsets, iou_threshold,
                                                  ws.kept_boxes, keep, keep_counts);
   CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+// =====================================================================================================================
+// Grid NMS: exact greedy NMS for ONE large segment (the global stitch of a tiled whole-slide image,
+// celldetection_scripts/cpn_inference.py:405-408, 1e5-1e6 boxes) in parallel.
+//
+// Greedy NMS keeps box i iff no KEPT box of higher priority overlaps it (IoU > thr).  That fixed point is computed by
+// parallel rounds over a uniform spatial grid: a box becomes SUPPRESSED as soon as a higher-priority overlapping box is
+// KEPT, and KEPT once every higher-priority overlapping box is SUPPRESSED; the highest-priority undecided box always
+// resolves, so the rounds terminate, and the fixed point is unique = the sequential greedy result (same IoU arithmetic,
+// same stable score order).  Cell size = the largest box extent, so overlapping boxes lie in 3x3 neighbouring cells.
+// =====================================================================================================================
+namespace cpn {
+
+struct GridInfo {
+  float x0, y0, inv_cell;
+  int ncx, ncy;
+};
+
+// pass 1: extents (min corner, max corner, max box size) via atomics on ordered-int floats
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void grid_extent_kernel(const float4* __restrict__ boxes, int n, int* __restrict__ ext) {
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY, ms = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 b = boxes[i];
+    const float cx = 0.5f * (b.x + b.z), cy = 0.5f * (b.y + b.w);
+    mnx = fminf(mnx, cx); mny = fminf(mny, cy); mxx = fmaxf(mxx, cx); mxy = fmaxf(mxy, cy);
+    ms = fmaxf(ms, fmaxf(b.z - b.x, b.w - b.y));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(ext + 0, f2ord(mnx)); atomicMin(ext + 1, f2ord(mny));
+    atomicMax(ext + 2, f2ord(mxx)); atomicMax(ext + 3, f2ord(mxy)); atomicMax(ext + 4, f2ord(ms));
+  }
+}
+
+__global__ void grid_setup_kernel(const int* __restrict__ ext, GridInfo* __restrict__ gi) {
+  if (threadIdx.x || blockIdx.x) return;
+  const float mnx = ord2f(ext[0]), mny = ord2f(ext[1]), mxx = ord2f(ext[2]), mxy = ord2f(ext[3]);
+  float cell = fmaxf(ord2f(ext[4]), 1e-3f) * 1.0001f;
+  const float spanx = fmaxf(mxx - mnx, 0.f), spany = fmaxf(mxy - mny, 0.f);
+  cell = fmaxf(cell, fmaxf(spanx, spany) / 4000.f);   // at most ~4000 x 4000 cells
+  gi->x0 = mnx; gi->y0 = mny; gi->inv_cell = 1.f / cell;
+  gi->ncx = (int)(spanx / cell) + 1; gi->ncy = (int)(spany / cell) + 1;
+}
+
+__device__ __forceinline__ int cell_of(const GridInfo& g, const float4 b, int* cx_out, int* cy_out) {
+  int cx = (int)((0.5f * (b.x + b.z) - g.x0) * g.inv_cell), cy = (int)((0.5f * (b.y + b.w) - g.y0) * g.inv_cell);
+  cx = min(max(cx, 0), g.ncx - 1); cy = min(max(cy, 0), g.ncy - 1);
+  if (cx_out) { *cx_out = cx; *cy_out = cy; }
+  return cy * g.ncx + cx;
+}
+
+// keys: (cell << 32) | rank, where rank = position in the stable descending score order; value = rank
+__global__ void grid_cellkeys_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ perm, int n,
+                                     const GridInfo* __restrict__ gi, uint64_t* __restrict__ keys,
+                                     int32_t* __restrict__ vals) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const GridInfo g = *gi;
+  const int c = cell_of(g, boxes[perm[r]], nullptr, nullptr);
+  keys[r] = ((uint64_t)(uint32_t)c << 32) | (uint32_t)r;
+  vals[r] = r;
+}
+
+// state per rank: 0 undecided, 1 kept, 2 suppressed.  cell_rows: ranks sorted by (cell, rank).
+__global__ void grid_round_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ perm,
+                                  const uint64_t* __restrict__ cell_keys, const int32_t* __restrict__ cell_rows, int n,
+                                  const GridInfo* __restrict__ gi, float thr, const uint8_t* __restrict__ state_in,
+                                  uint8_t* __restrict__ state_out, int* __restrict__ undecided) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint8_t st = state_in[r];
+  if (st != 0) { state_out[r] = st; return; }
+  const GridInfo g = *gi;
+  const float4 b = boxes[perm[r]];
+  const float area = (b.z - b.x) * (b.w - b.y);
+  int cx, cy;
+  cell_of(g, b, &cx, &cy);
+  bool any_kept = false, any_open = false;
+  for (int dy = -1; dy <= 1 && !any_kept; ++dy) {
+    const int yy = cy + dy;
+    if (yy < 0 || yy >= g.ncy) continue;
+    const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, g.ncx - 1);
+    // the three cells of this row are contiguous in the (cell, rank) order
+    const uint64_t k_lo = (uint64_t)(uint32_t)(yy * g.ncx + x_lo) << 32;
+    const uint64_t k_hi = (uint64_t)(uint32_t)(yy * g.ncx + x_hi + 1) << 32;
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cell_keys[mid] < k_lo) lo = mid + 1; else hi = mid; }
+    for (int q = lo; q < n && cell_keys[q] < k_hi; ++q) {
+      const int rj = cell_rows[q];
+      if (rj >= r) continue;                       // only higher-priority boxes can suppress
+      const uint8_t sj = state_in[rj];
+      if (sj == 2) continue;
+      const float4 c = boxes[perm[rj]];
+      if (!iou_gt(c, (c.z - c.x) * (c.w - c.y), b, area, thr)) continue;
+      if (sj == 1) { any_kept = true; break; }
+      any_open = true;
+    }
+  }
+  uint8_t ns = 0;
+  if (any_kept) ns = 2;
+  else if (!any_open) ns = 1;
+  state_out[r] = ns;
+  if (ns == 0) atomicAdd(undecided, 1);
+}
+
+__global__ void grid_flags_kernel(const uint8_t* __restrict__ state, int n, int32_t* __restrict__ flags) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) flags[r] = state[r] == 1 ? 1 : 0;
+}
+
+// single block: exclusive scan of flags -> write kept rows (perm[r]) in rank order
+__global__ void __launch_bounds__(1024) grid_compact_kernel(const int32_t* __restrict__ flags,
+                                                            const int32_t* __restrict__ perm, int n,
+                                                            int32_t* __restrict__ keep, int32_t* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s, chunk_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = 0; b0 < n; b0 += 1024) {
+    const int r = b0 + threadIdx.x;
+    const int v = r < n ? flags[r] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = warp_tot[lane];
+      int winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+      warp_tot[lane] = winc - w;
+      if (lane == 31) chunk_s = winc;
+    }
+    __syncthreads();
+    if (v) keep[carry_s + warp_tot[warp] + inc - v] = perm[r];
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += chunk_s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = carry_s;
+}
+
+}  // namespace cpn
+
+extern "C" size_t cpn_nms_grid_workspace_bytes(int64_t n_boxes) {
+  const size_t nn = (size_t)(n_boxes > 0 ? n_boxes : 1);
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)nn, 0, 64, (cudaStream_t)0);
+  // keys a/b (8), vals a/b (4), perm (4), cell_keys (8), cell_rows (4), state a/b (1), flags (4) + small
+  return align_up(nn * 8, 256) * 3 + align_up(nn * 4, 256) * 5 + align_up(nn, 256) * 2 + align_up(cub_bytes + 256, 256) +
+         4096;
+}
+
+extern "C" int cpn_nms_grid(const float* boxes, const float* scores, int64_t n_boxes, float iou_threshold,
+                            void* workspace, int32_t* keep, int32_t* keep_count, int* rounds_host, void* stream) {
+  CPN_REQUIRE(n_boxes < (1ll << 31), "nms_grid: too many boxes");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rounds_host) *rounds_host = 0;
+  if (n_boxes <= 0) {
+    nms_zero_counts_kernel<<<1, 32, 0, st>>>(keep_count, 1);
+    CPN_CHECK_LAUNCH();
+    return 0;
+  }
+  const int n = (int)n_boxes;
+  const size_t nn = (size_t)n;
+  char* b = reinterpret_cast<char*>(workspace);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = b + off; off += align_up(bytes, 256); return p; };
+  uint64_t* keys_a = (uint64_t*)take(nn * 8);
+  uint64_t* keys_b = (uint64_t*)take(nn * 8);
+  uint64_t* cell_keys = (uint64_t*)take(nn * 8);
+  int32_t* vals_a = (int32_t*)take(nn * 4);
+  int32_t* vals_b = (int32_t*)take(nn * 4);
+  int32_t* perm = (int32_t*)take(nn * 4);
+  int32_t* cell_rows = (int32_t*)take(nn * 4);
+  int32_t* flags = (int32_t*)take(nn * 4);
+  uint8_t* state_a = (uint8_t*)take(nn);
+  uint8_t* state_b = (uint8_t*)take(nn);
+  int* small = (int*)take(2048);   // [0..4] extents, [8] undecided, GridInfo at +64 bytes
+  GridInfo* gi = reinterpret_cast<GridInfo*>(reinterpret_cast<char*>(small) + 64);
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, n, 0, 64, st);
+  void* cub_tmp = take(cub_bytes + 256);
+  const int tb = 256, gb = (n + tb - 1) / tb;
+  // 1. stable descending score order -> perm[rank] = row
+  const int32_t seg_host[2] = {0, n};
+  int32_t* seg_dev = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(small) + 256);
+  CPN_CHECK_CUDA(cudaMemcpyAsync(seg_dev, seg_host, sizeof(seg_host), cudaMemcpyHostToDevice, st));
+  nms_keys_kernel<<<gb, tb, 0, st>>>(scores, seg_dev, 1, n, 0, keys_a, vals_a);
+  CPN_CHECK_LAUNCH();
+  size_t cb = cub_bytes + 256;
+  CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_a, keys_b, vals_a, perm, n, 0, 33, st));
+  count_launch(4);
+  // 2. grid: extents -> cell size -> (cell, rank) order
+  const int ext_init[5] = {0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+  CPN_CHECK_CUDA(cudaMemcpyAsync(small, ext_init, sizeof(ext_init), cudaMemcpyHostToDevice, st));
+  grid_extent_kernel<<<capped_blocks(gb), tb, 0, st>>>(reinterpret_cast<const float4*>(boxes), n, small);
+  CPN_CHECK_LAUNCH();
+  grid_setup_kernel<<<1, 32, 0, st>>>(small, gi);
+  CPN_CHECK_LAUNCH();
+  grid_cellkeys_kernel<<<gb, tb, 0, st>>>(reinterpret_cast<const float4*>(boxes), perm, n, gi, keys_a, vals_a);
+  CPN_CHECK_LAUNCH();
+  cb = cub_bytes + 256;
+  CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_a, cell_keys, vals_a, cell_rows, n, 0, 64, st));
+  count_launch(4);
+  // 3. rounds until every box is decided (the undecided count is read back every 4 rounds)
+  CPN_CHECK_CUDA(cudaMemsetAsync(state_a, 0, nn, st));
+  uint8_t *s_in = state_a, *s_out = state_b;
+  int rounds = 0;
+  int undecided = n;
+  while (undecided > 0) {
+    for (int k = 0; k < 4; ++k) {
+      CPN_CHECK_CUDA(cudaMemsetAsync(small + 8, 0, sizeof(int), st));
+      grid_round_kernel<<<gb, tb, 0, st>>>(reinterpret_cast<const float4*>(boxes), perm, cell_keys, cell_rows, n, gi,
+                                           iou_threshold, s_in, s_out, small + 8);
+      CPN_CHECK_LAUNCH();
+      uint8_t* t = s_in; s_in = s_out; s_out = t;
+      ++rounds;
+    }
+    CPN_CHECK_CUDA(cudaMemcpyAsync(&undecided, small + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CPN_CHECK_CUDA(cudaStreamSynchronize(st));
+    CPN_REQUIRE(rounds < 100000, "nms_grid: did not converge");
+  }
+  // 4. kept rows in descending score order
+  grid_flags_kernel<<<gb, tb, 0, st>>>(s_in, n, flags);
+  CPN_CHECK_LAUNCH();
+  grid_compact_kernel<<<1, 1024, 0, st>>>(flags, perm, n, keep, keep_count);
+  CPN_CHECK_LAUNCH();
+  if (rounds_host) *rounds_host = rounds;
   return 0;
 }

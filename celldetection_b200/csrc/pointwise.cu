@@ -47,12 +47,23 @@ __global__ void prep_kernel(const void* __restrict__ in, int fmt, T* __restrict_
 // to a multiple of 64 channels), so that the C_in = 3 stem (7x7 s2, resnet.py:273; 3x3 s1, unet.py:52) runs on the
 // tensor cores as a 1x1 convolution with K = 64-padded k*k*C.  One thread writes 8 consecutive channels (16 bytes).
 template <typename T>
-__global__ void prep_im2col_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out, int N, int C, int H, int W,
-                                   int Ho, int Wo, int Kp, int pitch, int k, int stride, int pad,
-                                   int32_t* __restrict__ flags) {
+__global__ void __launch_bounds__(256) prep_im2col_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out, int N,
+                                                          int C, int H, int W, int Ho, int Wo, int Kp, int pitch, int k,
+                                                          int stride, int pad, int32_t* __restrict__ flags) {
+  // per-entry tables: e -> (dy, dx, c) and the NCHW / NHWC offsets relative to the window origin
+  __shared__ int off_nchw[512], off_nhwc[512];
+  __shared__ signed char dys[512], dxs[512];
+  const int kk = k * k * C;
+  for (int e = threadIdx.x; e < Kp && e < 512; e += blockDim.x) {
+    const int tap = e / C, c = e - tap * C;
+    const int r = tap / k, s_ = tap - r * k;
+    dys[e] = (signed char)r; dxs[e] = (signed char)s_;
+    off_nchw[e] = (c * H + r) * W + s_;
+    off_nhwc[e] = (r * W + s_) * C + c;
+  }
+  __syncthreads();
   const int chunks = Kp / 8;
   const long long total = (long long)N * Ho * Wo * chunks;
-  const int kk = k * k * C;
   bool bad = false;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(i % chunks);
@@ -61,31 +72,37 @@ __global__ void prep_im2col_kernel(const void* __restrict__ in, int fmt, T* __re
     pix /= Wo;
     const int oy = (int)(pix % Ho);
     const int n = (int)(pix / Ho);
-    T vals[8];
+    const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+    const bool interior = iy0 >= 0 && ix0 >= 0 && iy0 + k <= H && ix0 + k <= W;
+    const long long base_nchw = ((long long)n * C * H + iy0) * W + ix0;
+    const long long base_nhwc = (((long long)n * H + iy0) * W + ix0) * C;
+    __align__(16) T vals[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int e = ch * 8 + j;
       float v = 0.f;
       if (e < kk) {
-        const int tap = e / C, c = e - tap * C;
-        const int r = tap / k, s_ = tap - r * k;
-        const int iy = oy * stride - pad + r, ix = ox * stride - pad + s_;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const bool ok = interior || (iy0 + dys[e] >= 0 && iy0 + dys[e] < H && ix0 + dxs[e] >= 0 && ix0 + dxs[e] < W);
+        if (ok) {
           if (fmt == CPN_IN_F32_NCHW) {
-            v = reinterpret_cast<const float*>(in)[(((long long)n * C + c) * H + iy) * W + ix];
+            v = __ldg(reinterpret_cast<const float*>(in) + base_nchw + off_nchw[e]);
             bad |= !(v >= 0.f && v <= 1.f);
           } else if (fmt == CPN_IN_U8_NCHW) {
-            v = (float)reinterpret_cast<const uint8_t*>(in)[(((long long)n * C + c) * H + iy) * W + ix] / 255.f;
+            v = (float)__ldg(reinterpret_cast<const uint8_t*>(in) + base_nchw + off_nchw[e]) / 255.f;
           } else {
-            v = (float)reinterpret_cast<const uint8_t*>(in)[(((long long)n * H + iy) * W + ix) * C + c] / 255.f;
+            v = (float)__ldg(reinterpret_cast<const uint8_t*>(in) + base_nhwc + off_nhwc[e]) / 255.f;
           }
         }
       }
       vals[j] = from_f32<T>(v);
     }
     T* o = out + (((long long)n * Ho + oy) * Wo + ox) * pitch + ch * 8;
+    if (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(vals);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = vals[j];
+      for (int j = 0; j < 8; ++j) o[j] = vals[j];
+    }
   }
   if (bad) atomicOr(flags, 1);
 }
@@ -93,8 +110,8 @@ __global__ void prep_im2col_kernel(const void* __restrict__ in, int fmt, T* __re
 int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* dst, int32_t* flags, cudaStream_t st) {
   CPN_REQUIRE(input_format >= 0 && input_format <= 2, "prep: bad input format %d", input_format);
   if (op.r > 0) {  // im2col mode: src view describes the logical input (n, h, w, c)
-    CPN_REQUIRE(op.dst.c % 8 == 0 && op.dst.pitch % 8 == 0 && op.dst.c >= op.r * op.r * op.src.c,
-                "prep(im2col): dst channels %d must be a multiple of 8 and >= k*k*c", op.dst.c);
+    CPN_REQUIRE(op.dst.c % 8 == 0 && op.dst.pitch % 8 == 0 && op.dst.c >= op.r * op.r * op.src.c && op.dst.c <= 512,
+                "prep(im2col): dst channels %d must be a multiple of 8, >= k*k*c and <= 512", op.dst.c);
     const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * (op.dst.c / 8);
     const int grid = grid_for(total, 256);
     if (op.dst.dtype == CPN_DT_F32)

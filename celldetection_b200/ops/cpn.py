@@ -15,7 +15,8 @@ from torch import Tensor
 from .. import _lib as L
 
 __all__ = ['fouriers2contours', 'rel_location2abs_location', 'get_scale', 'scale_contours', 'scale_fourier',
-           'batched_box_nmsi', 'batched_box_nms', 'remove_border_contours', 'nms', 'trig_table', 'NMS_BATCH_SIZE']
+           'batched_box_nmsi', 'batched_box_nms', 'remove_border_contours', 'nms', 'nms_grid', 'trig_table',
+           'NMS_BATCH_SIZE']
 
 NMS_BATCH_SIZE = 50000  # ops/cpn.py:12
 
@@ -129,12 +130,33 @@ def nms_segments(boxes: Tensor, scores: Tensor, seg_offsets: Tensor, n_segments:
     return keep, counts
 
 
+GRID_NMS_MIN = 20000   # above this many boxes a single segment goes to the parallel grid NMS
+
+
+def nms_grid(boxes: Tensor, scores: Tensor, iou_threshold: float, return_rounds=False):
+    """Exact greedy NMS of one large box set by parallel rounds over a spatial grid (global stitch NMS)."""
+    _require_cuda(boxes, scores)
+    lib = L.load()
+    P = int(boxes.shape[0])
+    keep = torch.empty((max(P, 1),), dtype=torch.int32, device=boxes.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    ws = torch.empty((int(lib.cpn_nms_grid_workspace_bytes(P)),), dtype=torch.uint8, device=boxes.device)
+    rounds = ctypes.c_int(0)
+    L.check(lib.cpn_nms_grid(L.ptr(boxes.contiguous().float()), L.ptr(scores.contiguous().float()), P,
+                             float(iou_threshold), L.ptr(ws), L.ptr(keep), L.ptr(count), ctypes.byref(rounds),
+                             L.stream_ptr()), 'nms_grid')
+    out = keep[:int(count.item())].long()
+    return (out, rounds.value) if return_rounds else out
+
+
 def nms(boxes: Tensor, scores: Tensor, iou_threshold: float) -> Tensor:
     """Drop-in for ``torch.ops.torchvision.nms``: kept indices (int64) in descending score order."""
     _require_cuda(boxes, scores)
     P = int(boxes.shape[0])
     if P == 0:
         return torch.zeros((0,), dtype=torch.long, device=boxes.device)
+    if P >= GRID_NMS_MIN:
+        return nms_grid(boxes, scores, iou_threshold)
     seg = torch.tensor([0, P], dtype=torch.int32, device=boxes.device)
     keep, counts = nms_segments(boxes.contiguous().float(), scores.contiguous().float(), seg, 1, iou_threshold, 0)
     return keep[:int(counts.item())].long()

@@ -171,6 +171,14 @@ int cpn_nms_segments(const float* boxes, const float* scores, const int32_t* seg
                      int64_t n_boxes, float iou_threshold, int chunk, void* workspace, int32_t* keep,
                      int32_t* keep_counts, void* stream);
 
+/* Exact greedy NMS of ONE large segment (the global stitch over all tiles, cpn_inference.py:405-408: 1e5-1e6 boxes)
+ * by parallel fixed-point rounds over a uniform spatial grid; same semantics and result as cpn_nms_segments with one
+ * segment and chunk <= 0.  Synchronises the stream internally (the round loop polls a device counter).
+ * rounds_host (optional) receives the number of rounds executed. */
+size_t cpn_nms_grid_workspace_bytes(int64_t n_boxes);
+int cpn_nms_grid(const float* boxes, const float* scores, int64_t n_boxes, float iou_threshold, void* workspace,
+                 int32_t* keep, int32_t* keep_count, int* rounds_host, void* stream);
+
 /* remove_border_contours (ops/cpn.py:258-290) as called by cpn_inference.py:375-380: keep[i] = 1 iff every vertex of
  * contour i satisfies the enabled side tests in tile-local coordinates (contours + (-offset)).
  * contours [K,S,2]; tile_of_row [K] int32 -> row of tile_meta; tile_meta [T,8] float:

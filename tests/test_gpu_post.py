@@ -176,3 +176,25 @@ def test_remove_border_contours():
         got = cd.ops.cpn.remove_border_contours(con.cuda(), (64, 64), 4, top=t, right=r, bottom=b, left=l_,
                                                 offsets=off)
         assert torch.equal(want, got.cpu())
+
+
+def test_grid_nms_matches_torchvision_exactly():
+    """Global stitch NMS (cpn_inference.py:405-408) at scale: the parallel grid algorithm returns exactly the greedy
+    result (index for index) of torchvision's op."""
+    import torchvision  # noqa: F401
+    g = torch.Generator().manual_seed(3)
+    for n, extent in ((1, 10.), (257, 100.), (5000, 400.), (60000, 3000.)):
+        boxes, scores = _rand_boxes(n, g, extent=extent, size=40.), torch.rand(n, generator=g)
+        if n > 100:
+            scores[7:40] = scores[7]
+            boxes[5] = boxes[6] = torch.tensor([5., 5., 5., 5.])
+            boxes[11] = torch.tensor([0., 0., extent * 0.5, 30.])      # one long box
+        for thr in (0.2, 0.5):
+            want = torch.ops.torchvision.nms(boxes, scores, thr)
+            got, rounds = cd.ops.cpn.nms_grid(boxes.cuda(), scores.cuda(), thr, return_rounds=True)
+            assert torch.equal(want, got.cpu()), (n, thr)
+            assert rounds >= 4
+    # the public nms switches to the grid path for large inputs
+    n = cd.ops.cpn.GRID_NMS_MIN + 10
+    boxes, scores = _rand_boxes(n, g, extent=2000.), torch.rand(n, generator=g)
+    assert torch.equal(torch.ops.torchvision.nms(boxes, scores, .2), cd.ops.cpn.nms(boxes.cuda(), scores.cuda(), .2).cpu())
