@@ -63,6 +63,7 @@ struct ConvTcParams {
   // (8*MSUB+S-1) pixel patch and every filter tap addresses a shifted window of it
   CUtensorMap tmH;          // (C, W, H, N), box {8, PW, PH, 1}, no swizzle
   int halo, pw, ph, plane_stride, nb_stages, swap_lbo_sbo;
+  int halo_sw128, halo_baseoff;   // 1: the patch is ONE box {64, PW, PH, 1} with SWIZZLE_128B (128-byte pixel rows)
 };
 
 struct ConvTcPlan {
@@ -176,6 +177,19 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// SW128 K-major descriptor whose 8-row groups are `sbo` bytes apart and whose start may sit on any 128-byte row of
+// a 1024-byte-aligned swizzled region (base_offset = row phase, optional).
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc_ex(uint32_t smem_addr, uint32_t sbo, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_off & 7) << 49;
   d |= (uint64_t)2 << 61;
   return d;
 }
@@ -497,9 +511,9 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = p.nb_stages;
-  const uint32_t patch_bytes = 8u * (uint32_t)p.plane_stride;
+  const uint32_t patch_bytes = 8u * (uint32_t)p.plane_stride;         // (sw128 mode: plane_stride = patch / 8)
   const uint32_t a_base = smem_base + nb * B_BYTES;                    // 2 patches behind the B ring
-  const uint32_t a_tx = 8u * (uint32_t)(p.ph * p.pw * 16);            // bytes the 8 box loads deliver
+  const uint32_t a_tx = 8u * (uint32_t)(p.ph * p.pw * 16);            // bytes the box load(s) deliver
   float* proj_w = reinterpret_cast<float*>(smem_raw + ((a_base - smem_u32(smem_raw)) + 2 * patch_bytes));
   if (p.nproj > 0) {
     int off = 0;
@@ -566,9 +580,13 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
           const uint32_t full = smem_u32(&bar_afull[ab]);
           mbar_expect_tx(full, a_tx);
           const uint32_t dst = a_base + ab * patch_bytes;
+          if (p.halo_sw128) {
+            tma_load_4d(dst, &p.tmH, full, cb * TC_BK, x0 - p.pad, y0 - p.pad, img);
+          } else {
 #pragma unroll
-          for (int kc = 0; kc < 8; ++kc)
-            tma_load_4d(dst + kc * p.plane_stride, &p.tmH, full, cb * TC_BK + kc * 8, x0 - p.pad, y0 - p.pad, img);
+            for (int kc = 0; kc < 8; ++kc)
+              tma_load_4d(dst + kc * p.plane_stride, &p.tmH, full, cb * TC_BK + kc * 8, x0 - p.pad, y0 - p.pad, img);
+          }
           ab ^= 1;
           if (ab == 0) pha ^= 1;
         }
@@ -596,12 +614,22 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
             const uint64_t db = make_sw128_kmajor_desc(smem_base + sb * B_BYTES);
 #pragma unroll
             for (int j = 0; j < MSUB; ++j) {
-              const uint32_t win = patch + (uint32_t)((r * p.pw + s_ + 8 * j) * 16);
               const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MSUB + j) * BN);
+              if (p.halo_sw128) {
+                // window start = 128-byte pixel row (r, s + 8j) of the swizzled patch; 8-row groups one patch row apart
+                const uint32_t win = patch + (uint32_t)((r * p.pw + s_ + 8 * j) * 128);
+                const uint64_t da0 = make_sw128_kmajor_desc_ex(win, (uint32_t)(p.pw * 128),
+                                                               p.halo_baseoff ? ((win >> 7) & 7) : 0);
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k) {
-                const uint64_t da = make_nosw_kmajor_desc(win + (uint32_t)(2 * k) * p.plane_stride, lbo, sbo);
-                umma_f16(d_tmem, da, db + (uint64_t)(k * 2), idesc, (uint32_t)((cb | tap | k) != 0));
+                for (int k = 0; k < TC_BK / 16; ++k)
+                  umma_f16(d_tmem, da0 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((cb | tap | k) != 0));
+              } else {
+                const uint32_t win = patch + (uint32_t)((r * p.pw + s_ + 8 * j) * 16);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                  const uint64_t da = make_nosw_kmajor_desc(win + (uint32_t)(2 * k) * p.plane_stride, lbo, sbo);
+                  umma_f16(d_tmem, da, db + (uint64_t)(k * 2), idesc, (uint32_t)((cb | tap | k) != 0));
+                }
               }
             }
             umma_commit(smem_u32(&bar_bempty[sb]));
@@ -751,13 +779,19 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   // ---- halo variant for stride-1 kxk dense convolutions (CPN_HALO=0 disables) ----
   pl->msub = 1;
   {
-    static int halo_env = -1, swap_env = -1;
+    static int halo_env = -1, swap_env = -1, sw128_env = -1, baseoff_env = -1, halo33_env = -1;
     if (halo_env < 0) { const char* e = getenv("CPN_HALO"); halo_env = (e && atoi(e) == 0) ? 0 : 1; }
+    if (sw128_env < 0) { const char* e = getenv("CPN_HALO_SW128"); sw128_env = (e && atoi(e) == 1) ? 1 : 0; }
+    if (baseoff_env < 0) { const char* e = getenv("CPN_HALO_BASEOFF"); baseoff_env = (e && atoi(e) == 1) ? 1 : 0; }
+    if (halo33_env < 0) { const char* e = getenv("CPN_HALO_ALL"); halo33_env = (e && atoi(e) == 1) ? 1 : 0; }
     if (swap_env < 0) { const char* e = getenv("CPN_HALO_SWAP"); swap_env = (e && atoi(e) == 1) ? 1 : 0; }
-    if (halo_env && op.stride == 1 && op.r * op.s > 1 && op.slab_mode == 0 && op.r <= 16 && op.s <= 16) {
+    // measured (profiles/r01): the halo variant wins whenever the operand traffic per MMA is high -- every 7x7, and
+    // kxk layers with <= 128 output channels; 3x3 layers with 256-wide tiles are faster with per-tap box loads.
+    const bool worth = halo33_env || op.r * op.s >= 25 || bn <= 128;
+    if (halo_env && worth && op.stride == 1 && op.r * op.s > 1 && op.slab_mode == 0 && op.r <= 16 && op.s <= 16) {
       const int msub = bn == 256 ? 1 : 2;
       const int pw = 8 * msub + op.s - 1, ph = 16 + op.r - 1;
-      const int plane_stride = (ph * pw * 16 + 127) / 128 * 128;
+      const int plane_stride = sw128_env ? ((ph * pw * 128 + 1023) / 1024 * 1024) / 8 : (ph * pw * 16 + 127) / 128 * 128;
       const int patch = 8 * plane_stride;
       const int b_bytes = bn * TC_BK * 2;
       int nbs = (TC_SMEM_BUDGET - 2 * patch) / b_bytes;
@@ -766,8 +800,9 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
         cuuint64_t dims[4] = {(cuuint64_t)op.src.c, (cuuint64_t)op.src.w, (cuuint64_t)op.src.h, (cuuint64_t)op.src.n};
         cuuint64_t strides[3] = {(cuuint64_t)op.src.pitch * 2, (cuuint64_t)op.src.w * op.src.pitch * 2,
                                  (cuuint64_t)op.src.h * op.src.w * op.src.pitch * 2};
-        cuuint32_t box[4] = {8, (cuuint32_t)pw, (cuuint32_t)ph, 1};
-        if (encode_map(&p.tmH, const_cast<void*>(src), 4, dims, strides, box, false)) { delete pl; return 1; }
+        cuuint32_t box[4] = {(cuuint32_t)(sw128_env ? 64 : 8), (cuuint32_t)pw, (cuuint32_t)ph, 1};
+        if (encode_map(&p.tmH, const_cast<void*>(src), 4, dims, strides, box, sw128_env != 0)) { delete pl; return 1; }
+        p.halo_sw128 = sw128_env; p.halo_baseoff = baseoff_env;
         p.halo = 1; p.pw = pw; p.ph = ph; p.plane_stride = plane_stride; p.nb_stages = nbs; p.swap_lbo_sbo = swap_env;
         pl->msub = msub;
         p.tiles_x = (op.dst.w + 8 * msub - 1) / (8 * msub);
