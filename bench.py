@@ -221,10 +221,10 @@ def run_b200(args):
         return model.forward_flat(xs[i % n_rot])
 
     def step_e2e(i):
-        x = host[i % n_rot].to(dev, non_blocking=True)
-        flat, counts = model.forward_flat(x)
-        out = {k: v.cpu() for k, v in flat.items()}       # device -> host read of the step's result
-        return out, counts
+        x = host[i % n_rot].to(dev, non_blocking=True)    # host -> device copy of this step's inputs (pinned)
+        y = model(x)                                      # the call a user makes (reference API: per-image lists)
+        out = {k: [t.cpu() for t in v] for k, v in y.items() if v is not None}   # device -> host read of the result
+        return out, [len(s) for s in out['scores']]
 
     def barrier():
         if dist is not None:
@@ -262,7 +262,7 @@ def run_b200(args):
     tiles = BATCH * world
     value = tiles * args.steps / (ms / 1e3)
     e2e = tiles * args.steps / (ms_e2e / 1e3)
-    d2h = sum(v.numel() * v.element_size() for v in last_e[0].values())
+    d2h = sum(t.numel() * t.element_size() for v in last_e[0].values() for t in v)
 
     # ---- roofline of the dominant kernel: the merged 7x7 head convolution (tcgen05), timed alone ----
     plan = model._plan(BATCH, TILE, TILE)
@@ -285,9 +285,23 @@ def run_b200(args):
     hflops = 2. * BATCH * hop.dst.h * hop.dst.w * hop.dst.c * hop.src.c * hop.k * hop.k
     achieved = hflops / (hms / 1e3) / 1e12
     if args.precision == 'fp16':
-        roof = dict(bound='tensor', kernel='conv_tc_kernel<256> (merged 7x7 heads 256->768 @256x256, batch 16)',
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
+        ncu_json = os.path.join(ROOT, 'profiles', 'r01_ncu_heads_conv.json')
+        if os.path.exists(ncu_json):
+            try:
+                with open(ncu_json) as f:
+                    r0 = json.load(f)[0]
+                unit = {'byte': 1., 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+                traffic = sum(float(r0[k][0]) * unit[r0[k][1]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+            except Exception:
+                traffic = None
+        roof = dict(bound='tensor',
+                    kernel='conv_halo_kernel<256,1>: merged 7x7 heads 256->768 @256x256 + fused ReadOut projections, '
+                           'batch 16 (tcgen05 kind::f16, fp32 accumulate)',
                     achieved=achieved, peak=peaks['tflops'], unit='TFLOP/s', frac=achieved / peaks['tflops'],
-                    traffic=None, peak_source=peaks['source'] + ', burst cuBLAS bf16', ms_per_launch=hms,
+                    traffic=traffic, algorithmic_bytes=BATCH * hop.src.h * hop.src.w * hop.src.c * 2
+                    + hop.dst.c * hop.src.c * hop.k * hop.k * 2 + BATCH * hop.dst.h * hop.dst.w * 23 * 4,
+                    peak_source=peaks['source'] + ', burst cuBLAS bf16', ms_per_launch=hms,
                     flops_per_launch=hflops)
     else:
         roof = dict(bound='tensor', kernel='conv_simt_kernel<float> (strict fp32 CUDA-core engine)', achieved=achieved,

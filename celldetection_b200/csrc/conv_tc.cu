@@ -63,7 +63,8 @@ struct ConvTcParams {
   // (8*MSUB+S-1) pixel patch and every filter tap addresses a shifted window of it
   CUtensorMap tmH;          // (C, W, H, N), box {8, PW, PH, 1}, no swizzle
   int halo, pw, ph, plane_stride, nb_stages, swap_lbo_sbo;
-  int halo_sw128, halo_baseoff;   // 1: the patch is ONE box {64, PW, PH, 1} with SWIZZLE_128B (128-byte pixel rows)
+  int halo_sw128, halo_baseoff;
+  int rotate;               // start each CTA's K loop at a different (tap, block): de-correlates the L2 reads of the shared weights   // 1: the patch is ONE box {64, PW, PH, 1} with SWIZZLE_128B (128-byte pixel rows)
 };
 
 struct ConvTcPlan {
@@ -389,7 +390,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int y0 = (t_in / p.tiles_x) * TC_BH, x0 = (t_in % p.tiles_x) * TC_BW;
         const int n0 = n_tile * BN;
         const int cbase = p.slab_mode ? (n0 / p.kslab) * p.kslab : 0;
-        for (int tap = 0; tap < p.R * p.S; ++tap) {
+        int kk = p.rotate ? (int)(blockIdx.x % (unsigned)nk) : 0;   // rotated start of the K loop (sum order is free)
+        for (int it = 0; it < nk; ++it) {
+          const int tap = kk / p.cblocks, cb = kk - tap * p.cblocks;
+          if (++kk == nk) kk = 0;
           const int r = tap / p.S, s = tap - r * p.S;
           int qy = r - p.pad, qx = s - p.pad, map = 0;
           if (p.stride == 2) {
@@ -398,15 +402,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             qy = (qy - py) >> 1;
             qx = (qx - px) >> 1;
           }
-          for (int cb = 0; cb < p.cblocks; ++cb) {
-            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
-            const uint32_t full = smem_u32(&bar_full[stage]);
-            const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-            mbar_expect_tx(full, STAGE_BYTES);
-            tma_load_4d(sa, &p.tmA[map], full, cbase + cb * TC_BK, x0 + qx, y0 + qy, img);
-            tma_load_3d(sb, &p.tmB, full, cb * TC_BK, n0, tap);
-            if (++stage == stages) { stage = 0; phase ^= 1; }
-          }
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          mbar_expect_tx(full, STAGE_BYTES);
+          tma_load_4d(sa, &p.tmA[map], full, cbase + cb * TC_BK, x0 + qx, y0 + qy, img);
+          tma_load_3d(sb, &p.tmB, full, cb * TC_BK, n0, tap);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -555,7 +557,8 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n0 = (int)(tile % p.tiles_n) * BN;
         for (int cb = 0; cb < p.cblocks; ++cb) {
-          for (int tap = 0; tap < taps; ++tap) {
+          int tap = p.rotate ? (int)(blockIdx.x % (unsigned)taps) : 0;
+          for (int it = 0; it < taps; ++it, tap = (tap + 1 == taps ? 0 : tap + 1)) {
             mbar_wait(smem_u32(&bar_bempty[sb]), phb ^ 1);
             const uint32_t full = smem_u32(&bar_bfull[sb]);
             mbar_expect_tx(full, B_BYTES);
@@ -575,17 +578,20 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
         const int img = (int)(m_tile / tiles_per_img);
         const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
         const int y0 = (t_in / p.tiles_x) * TH, x0 = (t_in % p.tiles_x) * TW;
+        const int n0 = (int)(tile % p.tiles_n) * BN;
+        const int cbase = p.slab_mode ? (n0 / p.kslab) * p.kslab : 0;   // grouped: this N tile's 64-channel slab
         for (int cb = 0; cb < p.cblocks; ++cb) {
           mbar_wait(smem_u32(&bar_aempty[ab]), pha ^ 1);
           const uint32_t full = smem_u32(&bar_afull[ab]);
           mbar_expect_tx(full, a_tx);
           const uint32_t dst = a_base + ab * patch_bytes;
           if (p.halo_sw128) {
-            tma_load_4d(dst, &p.tmH, full, cb * TC_BK, x0 - p.pad, y0 - p.pad, img);
+            tma_load_4d(dst, &p.tmH, full, cbase + cb * TC_BK, x0 - p.pad, y0 - p.pad, img);
           } else {
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc)
-              tma_load_4d(dst + kc * p.plane_stride, &p.tmH, full, cb * TC_BK + kc * 8, x0 - p.pad, y0 - p.pad, img);
+              tma_load_4d(dst + kc * p.plane_stride, &p.tmH, full, cbase + cb * TC_BK + kc * 8, x0 - p.pad, y0 - p.pad,
+                          img);
           }
           ab ^= 1;
           if (ab == 0) pha ^= 1;
@@ -607,7 +613,8 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
           mbar_wait(smem_u32(&bar_afull[ab]), pha);
           tc_fence_after();
           const uint32_t patch = a_base + ab * patch_bytes;
-          for (int tap = 0; tap < taps; ++tap) {
+          int tap = p.rotate ? (int)(blockIdx.x % (unsigned)taps) : 0;
+          for (int it = 0; it < taps; ++it, tap = (tap + 1 == taps ? 0 : tap + 1)) {
             const int r = tap / p.S, s_ = tap - r * p.S;
             mbar_wait(smem_u32(&bar_bfull[sb]), phb);
             tc_fence_after();
@@ -622,13 +629,13 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
                                                                p.halo_baseoff ? ((win >> 7) & 7) : 0);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k)
-                  umma_f16(d_tmem, da0 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((cb | tap | k) != 0));
+                  umma_f16(d_tmem, da0 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((cb | it | k) != 0));
               } else {
                 const uint32_t win = patch + (uint32_t)((r * p.pw + s_ + 8 * j) * 16);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
                   const uint64_t da = make_nosw_kmajor_desc(win + (uint32_t)(2 * k) * p.plane_stride, lbo, sbo);
-                  umma_f16(d_tmem, da, db + (uint64_t)(k * 2), idesc, (uint32_t)((cb | tap | k) != 0));
+                  umma_f16(d_tmem, da, db + (uint64_t)(k * 2), idesc, (uint32_t)((cb | it | k) != 0));
                 }
               }
             }
@@ -773,6 +780,11 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   p.R = op.r; p.S = op.s; p.stride = op.stride; p.pad = op.pad;
   p.cblocks = op.kslab / TC_BK; p.kslab = op.kslab; p.slab_mode = op.slab_mode;
   p.relu = op.act == CPN_ACT_RELU;
+  {
+    static int rot_env = -1;
+    if (rot_env < 0) { const char* e = getenv("CPN_ROTATE"); rot_env = (e && atoi(e) == 0) ? 0 : 1; }
+    p.rotate = rot_env;
+  }
   p.tiles_x = (op.dst.w + TC_BW - 1) / TC_BW; p.tiles_y = (op.dst.h + TC_BH - 1) / TC_BH;
   p.tiles_n = op.dst.c / bn;
   p.total_tiles = (long long)op.dst.n * p.tiles_x * p.tiles_y * p.tiles_n;
@@ -781,14 +793,14 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   {
     static int halo_env = -1, swap_env = -1, sw128_env = -1, baseoff_env = -1, halo33_env = -1;
     if (halo_env < 0) { const char* e = getenv("CPN_HALO"); halo_env = (e && atoi(e) == 0) ? 0 : 1; }
-    if (sw128_env < 0) { const char* e = getenv("CPN_HALO_SW128"); sw128_env = (e && atoi(e) == 1) ? 1 : 0; }
+    if (sw128_env < 0) { const char* e = getenv("CPN_HALO_SW128"); sw128_env = (e && atoi(e) == 0) ? 0 : 1; }
     if (baseoff_env < 0) { const char* e = getenv("CPN_HALO_BASEOFF"); baseoff_env = (e && atoi(e) == 1) ? 1 : 0; }
     if (halo33_env < 0) { const char* e = getenv("CPN_HALO_ALL"); halo33_env = (e && atoi(e) == 1) ? 1 : 0; }
     if (swap_env < 0) { const char* e = getenv("CPN_HALO_SWAP"); swap_env = (e && atoi(e) == 1) ? 1 : 0; }
     // measured (profiles/r01): the halo variant wins whenever the operand traffic per MMA is high -- every 7x7, and
     // kxk layers with <= 128 output channels; 3x3 layers with 256-wide tiles are faster with per-tap box loads.
     const bool worth = halo33_env || op.r * op.s >= 25 || bn <= 128;
-    if (halo_env && worth && op.stride == 1 && op.r * op.s > 1 && op.slab_mode == 0 && op.r <= 16 && op.s <= 16) {
+    if (halo_env && worth && op.stride == 1 && op.r * op.s > 1 && op.r <= 16 && op.s <= 16) {
       const int msub = bn == 256 ? 1 : 2;
       const int pw = 8 * msub + op.s - 1, ph = 16 + op.r - 1;
       const int plane_stride = sw128_env ? ((ph * pw * 128 + 1023) / 1024 * 1024) / 8 : (ph * pw * 16 + 127) / 128 * 128;

@@ -240,12 +240,44 @@ __global__ void upsample_kernel(const T* __restrict__ src, T* __restrict__ dst, 
   }
 }
 
+// 16-byte variant (fp16, C % 8 == 0): one thread = one source chunk of 8 channels of one SOURCE pixel, replicated to
+// the (up to fy x fx) destination pixels that map onto it (exact integer factors only) -- 1 load, fy*fx stores.
+__global__ void __launch_bounds__(256) upsample_int_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N,
+                                                           int H, int W, int c8, int sp8, int dp8, int fy, int fx) {
+  const int total = N * H * W * c8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % c8;
+    int pix = i / c8;
+    const int x = pix % W;
+    pix /= W;
+    const int y = pix % H;
+    const int n = pix / H;
+    const uint4 v = __ldg(src + (size_t)((n * H + y) * W + x) * sp8 + c);
+    const int Wo = W * fx, Ho = H * fy;
+    for (int dy = 0; dy < fy; ++dy)
+      for (int dx = 0; dx < fx; ++dx)
+        dst[(size_t)((n * Ho + y * fy + dy) * Wo + x * fx + dx) * dp8 + c] = v;
+  }
+}
+
 int upsample_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st) {
   CPN_REQUIRE(op.src.c % 4 == 0 && op.src.pitch % 4 == 0 && op.dst.pitch % 4 == 0 && op.src.c == op.dst.c,
               "upsample: channels/pitch must be multiples of 4");
   CPN_REQUIRE(op.src.dtype == op.dst.dtype, "upsample: dtype mismatch");
   const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * (op.dst.c / 4);
   const int grid = grid_for(total, 256);
+  const bool integer = op.dst.h % op.src.h == 0 && op.dst.w % op.src.w == 0;
+  if (op.src.dtype == CPN_DT_F16 && integer && op.src.c % 8 == 0 && op.src.pitch % 8 == 0 && op.dst.pitch % 8 == 0 &&
+      (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0 &&
+      (long long)op.src.n * op.src.h * op.src.w * (op.src.c / 8) < (1ll << 31) &&
+      (long long)op.dst.n * op.dst.h * op.dst.w * (op.dst.pitch / 8) < (1ll << 31)) {
+    const long long items = (long long)op.src.n * op.src.h * op.src.w * (op.src.c / 8);
+    upsample_int_kernel<<<grid_for(items, 256), 256, 0, st>>>((const uint4*)src, (uint4*)dst, op.src.n, op.src.h, op.src.w,
+                                                            op.src.c / 8, op.src.pitch / 8, op.dst.pitch / 8,
+                                                            op.dst.h / op.src.h, op.dst.w / op.src.w);
+    CPN_CHECK_LAUNCH();
+    return 0;
+  }
   if (op.src.dtype == CPN_DT_F32)
     upsample_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, op.src.n, op.src.h, op.src.w,
                                                  op.src.c, op.src.pitch, op.dst.h, op.dst.w, op.dst.pitch);
