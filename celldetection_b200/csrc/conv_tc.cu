@@ -782,7 +782,9 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   p.relu = op.act == CPN_ACT_RELU;
   {
     static int rot_env = -1;
-    if (rot_env < 0) { const char* e = getenv("CPN_ROTATE"); rot_env = (e && atoi(e) == 0) ? 0 : 1; }
+    // Off by default: measured no gain on B200 (profiles/r01_summary.md), and a CTA-dependent summation order would
+    // make a tile's result depend on the batch it is computed in (the tests assert batch invariance bit for bit).
+    if (rot_env < 0) { const char* e = getenv("CPN_ROTATE"); rot_env = (e && atoi(e) == 1) ? 1 : 0; }
     p.rotate = rot_env;
   }
   p.tiles_x = (op.dst.w + TC_BW - 1) / TC_BW; p.tiles_y = (op.dst.h + TC_BH - 1) / TC_BH;
