@@ -570,10 +570,12 @@ __global__ void __launch_bounds__(256) border_filter_kernel(const float* __restr
                                                             int samples, float padding, uint8_t* __restrict__ keep) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long r = (long long)blockIdx.x * 8 + warp; r < K; r += (long long)gridDim.x * 8) {
-    const float* m = tile_meta + (long long)tile_of_row[r] * 8;
+    const float* m = tile_meta + (long long)tile_of_row[r] * CPN_TILE_META;
     const float offx = m[0], offy = m[1], h = m[2], w = m[3];
     const bool top = m[4] != 0.f, right = m[5] != 0.f, bottom = m[6] != 0.f, left = m[7] != 0.f;
-    bool ok = true;
+    const bool ex_br = m[8] != 0.f;           // filter_contours_by_stitching_rule 'ex_br' (ops/cpn.py:316-319)
+    const float stop_x = m[9], stop_y = m[10];
+    bool ok = true, all_rb = true;
     for (int s = lane; s < samples; s += 32) {
       const float2 v = reinterpret_cast<const float2*>(contours)[r * samples + s];
       const float x = v.x + (-offx), y = v.y + (-offy);  // contours + offsets with offsets = -tile offset
@@ -581,9 +583,11 @@ __global__ void __launch_bounds__(256) border_filter_kernel(const float* __restr
       if (right) ok = ok && (x < (w - padding));
       if (bottom) ok = ok && (y < (h - padding));
       if (left) ok = ok && (x > padding);
+      all_rb = all_rb && ((x >= stop_x) || (y >= stop_y));   // (contours >= stop).any(-1)
     }
     ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) keep[r] = ok ? 1 : 0;
+    all_rb = __all_sync(0xffffffffu, all_rb);                // ....all(-1): every vertex lies in the right/bottom overlap
+    if (lane == 0) keep[r] = (ok && !(ex_br && all_rb)) ? 1 : 0;
   }
 }
 

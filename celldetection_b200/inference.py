@@ -60,7 +60,7 @@ def _dist():
     return None, 0, 1
 
 
-REC_KEYS = ('contours', 'boxes', 'scores', 'classes', 'locations', 'fourier', 'contour_proposals')
+REC_KEYS = ('contours', 'boxes', 'scores', 'classes', 'locations', 'fourier', 'contour_proposals', 'order_key')
 
 
 def pack_records(res: OrderedDict):
@@ -76,8 +76,17 @@ def unpack_records(rec, widths, like: OrderedDict):
         v = rec[:, o:o + wd]
         o += wd
         shape = (rec.shape[0],) + tuple(like[k].shape[1:])
-        out[k] = v.reshape(shape).long() if k == 'classes' else v.reshape(shape).contiguous()
+        out[k] = v.reshape(shape).long() if k in ('classes',) else v.reshape(shape).contiguous()
     return out
+
+
+def canonical_order(res: OrderedDict):
+    """Sort detections by their (tile index, row within tile) key so that the input order of the global NMS -- which
+    breaks score ties -- is the single-process tile order no matter how tiles were sharded over ranks."""
+    key = res['order_key']
+    k64 = key[:, 0].to(torch.int64) * (1 << 24) + key[:, 1].to(torch.int64)
+    order = torch.argsort(k64, stable=True)
+    return OrderedDict((k, v[order]) for k, v in res.items())
 
 
 def allgather_detections(res: OrderedDict, group=None):
@@ -123,8 +132,9 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
         raise NotImplementedError('model ensembles / box voting are outside the accelerated path (SURVEY 8f-4).')
     if mask is not None or point_mask is not None or transforms is not None or reps != 1:
         raise NotImplementedError('masks, point masks and test-time transforms are outside the accelerated path.')
-    if stitching_rule != 'nms':
-        raise NotImplementedError("only stitching_rule='nms' is implemented")
+    rules = stitching_rule.split(',')
+    if any(r not in ('nms', 'ex_br') for r in rules):
+        raise ValueError(f'Unknown stitching rule: {stitching_rule}')
     model = models[0]
     dev = torch.device(device) if device is not None else model.device
     if dev.type != 'cuda':
@@ -139,8 +149,10 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
     elif img.dtype != np.uint8:
         raise ValueError('image must be uint8 or floating point')
     H, W = img.shape[:2]
-    slices, _, (h_tiles, w_tiles) = get_tiling_slices((H, W), tuple(crop_size), tuple(strides), return_overlaps=True)
-    slices = list(slices)
+    slices, overlaps, (h_tiles, w_tiles) = get_tiling_slices((H, W), tuple(crop_size), tuple(strides),
+                                                             return_overlaps=True)
+    slices, overlaps = list(slices), list(overlaps)
+    ex_br = float(stitching_rule != 'nms' and 'ex_br' in rules)
     dist, rank, world = _dist()
     mine = list(range(rank, len(slices), world))
     th, tw = (slices[0][0].stop - slices[0][0].start), (slices[0][1].stop - slices[0][1].start)
@@ -184,8 +196,9 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
         meta = []
         for t in ids:
             h_i, w_i = np.unravel_index(t, (h_tiles, w_tiles))
+            (_, ov_y1), (_, ov_x1) = overlaps[t]      # right/bottom overlaps (cpn_inference.py:382-385)
             meta.append([slices[t][1].start, slices[t][0].start, th, tw, float(h_i > 0), float(w_i < w_tiles - 1),
-                         float(h_i < h_tiles - 1), float(w_i > 0)])
+                         float(h_i < h_tiles - 1), float(w_i > 0), ex_br, float(tw - ov_x1), float(th - ov_y1), 0.])
         meta = torch.tensor(meta, dtype=torch.float32, device=dev)
         tile_of_row = torch.repeat_interleave(torch.arange(len(ids), dtype=torch.int32, device=dev),
                                               torch.tensor(counts, device=dev))
@@ -195,16 +208,22 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
                                       int(flat['contours'].shape[1]), float(border_removal), L.ptr(keep),
                                       L.stream_ptr()), 'border_filter')
         sel = torch.nonzero(keep, as_tuple=False).reshape(-1)
-        acc.append(OrderedDict((k, v[sel]) for k, v in flat.items()))
+        part = OrderedDict((k, v[sel]) for k, v in flat.items())
+        tile_ids = torch.tensor(ids, dtype=torch.float32, device=dev)[tile_of_row.long()][sel]
+        part['order_key'] = torch.stack((tile_ids, sel.to(torch.float32)), 1)   # (global tile index, row in batch)
+        acc.append(part)
     if acc:
         res = OrderedDict((k, torch.cat([a[k] for a in acc], 0)) for k in acc[0].keys())
     else:
         S, order = int(model.samples), int(min(model.order, model.core_order))
         z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
         res = OrderedDict(contours=z(0, S, 2), boxes=z(0, 4), scores=z(0), classes=z(0, dt=torch.long),
-                          locations=z(0, 2), fourier=z(0, order, 4), contour_proposals=z(0, S, 2))
+                          locations=z(0, 2), fourier=z(0, order, 4), contour_proposals=z(0, S, 2), order_key=z(0, 2))
     res = allgather_detections(res)
-    if 'nms' in stitching_rule.split(',') and res['boxes'].shape[0] > 0:
+    if world > 1:
+        res = canonical_order(res)      # 1-GPU and N-GPU runs feed the global NMS the same sequence
+    res.pop('order_key')
+    if 'nms' in rules and res['boxes'].shape[0] > 0:
         keep = O.nms(res['boxes'], res['scores'], nms_thresh)
         res = OrderedDict((k, v[keep]) for k, v in res.items())
     return res

@@ -15,7 +15,8 @@ from torch import Tensor
 from .. import _lib as L
 
 __all__ = ['fouriers2contours', 'rel_location2abs_location', 'get_scale', 'scale_contours', 'scale_fourier',
-           'batched_box_nmsi', 'batched_box_nms', 'remove_border_contours', 'nms', 'nms_grid', 'trig_table',
+           'batched_box_nmsi', 'batched_box_nms', 'remove_border_contours', 'filter_contours_by_stitching_rule', 'nms',
+           'nms_grid', 'trig_table',
            'NMS_BATCH_SIZE']
 
 NMS_BATCH_SIZE = 50000  # ops/cpn.py:12
@@ -198,9 +199,32 @@ def remove_border_contours(contours, size, padding=1, top=True, right=True, bott
         return keep.bool()
     h, w = size[:2]
     off = [0., 0.] if offsets is None else [float(-v) for v in torch.as_tensor(offsets).reshape(-1)[:2].tolist()]
-    meta = torch.tensor([[off[0], off[1], float(h), float(w), float(top), float(right), float(bottom), float(left)]],
-                        dtype=torch.float32, device=contours.device)
+    meta = torch.tensor([[off[0], off[1], float(h), float(w), float(top), float(right), float(bottom), float(left),
+                          0., 0., 0., 0.]], dtype=torch.float32, device=contours.device)
     tile = torch.zeros((K,), dtype=torch.int32, device=contours.device)
     L.check(lib.cpn_border_filter(L.ptr(contours.contiguous().float()), L.ptr(tile), L.ptr(meta), K, S,
                                   float(padding), L.ptr(keep), L.stream_ptr()), 'border_filter')
     return keep.bool()
+
+
+def filter_contours_by_stitching_rule(contours, tile_size, overlaps, rule='ex_br', offsets=None, indices=False):
+    """ops/cpn.py:293-325: 'ex_br' keeps a contour unless every vertex lies in the right/bottom overlap region of the
+    tile (``(contours >= (tile_size - overlaps[:, 1])[[1, 0]]).any(-1).all(-1)``)."""
+    _require_cuda(contours)
+    if 'ex_br' not in rule.split(','):
+        raise ValueError(f'Unknown stitching rule: {rule}')
+    lib = L.load()
+    K, S = int(contours.shape[0]), int(contours.shape[1])
+    keep = torch.ones((K,), dtype=torch.uint8, device=contours.device)
+    if K > 0:
+        ts = torch.as_tensor(tile_size).reshape(-1).tolist()
+        ov = torch.as_tensor(overlaps).reshape(2, 2).tolist()
+        stop_y, stop_x = ts[0] - ov[0][1], ts[1] - ov[1][1]
+        off = [0., 0.] if offsets is None else [float(-v) for v in torch.as_tensor(offsets).reshape(-1)[:2].tolist()]
+        meta = torch.tensor([[off[0], off[1], float(ts[0]), float(ts[1]), 0., 0., 0., 0., 1., float(stop_x),
+                              float(stop_y), 0.]], dtype=torch.float32, device=contours.device)
+        tile = torch.zeros((K,), dtype=torch.int32, device=contours.device)
+        L.check(lib.cpn_border_filter(L.ptr(contours.contiguous().float()), L.ptr(tile), L.ptr(meta), K, S, 0.,
+                                      L.ptr(keep), L.stream_ptr()), 'border_filter')
+    keep = keep.bool()
+    return torch.where(keep)[0] if indices else keep

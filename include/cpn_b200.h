@@ -181,8 +181,11 @@ int cpn_nms_grid(const float* boxes, const float* scores, int64_t n_boxes, float
 
 /* remove_border_contours (ops/cpn.py:258-290) as called by cpn_inference.py:375-380: keep[i] = 1 iff every vertex of
  * contour i satisfies the enabled side tests in tile-local coordinates (contours + (-offset)).
- * contours [K,S,2]; tile_of_row [K] int32 -> row of tile_meta; tile_meta [T,8] float:
- * (off_x, off_y, h, w, top, right, bottom, left). */
+ * contours [K,S,2]; tile_of_row [K] int32 -> row of tile_meta; tile_meta [T,CPN_TILE_META] float:
+ * (off_x, off_y, h, w, top, right, bottom, left, ex_br, stop_x, stop_y, 0).  With ex_br != 0 the 'ex_br' stitching rule
+ * (filter_contours_by_stitching_rule, ops/cpn.py:293-325) additionally drops contours whose every vertex has
+ * x >= stop_x or y >= stop_y (stop = tile size - right/bottom overlap), in the same tile-local coordinates. */
+#define CPN_TILE_META 12
 int cpn_border_filter(const float* contours, const int32_t* tile_of_row, const float* tile_meta, int64_t K, int samples,
                       float padding, uint8_t* keep, void* stream);
 

@@ -23,6 +23,7 @@ oracle function        reference code it follows (relative to /root/reference/ce
 ``fouriers2contours``  ops/cpn.py:44-95
 ``get_tiling_slices``  util/util.py:1305-1354
 ``remove_border_contours`` ops/cpn.py:258-290
+``filter_contours_by_stitching_rule`` ops/cpn.py:293-325
 ``apply_model``        celldetection_scripts/cpn_inference.py:311-429 (single model, stitching_rule='nms')
 =====================  ==========================================================================================
 
@@ -419,6 +420,18 @@ def remove_border_contours(contours, size, padding=1, top=True, right=True, bott
     if left:
         keep = keep & (x > padding).all(1)
     return keep
+
+
+def filter_contours_by_stitching_rule(contours, tile_size, overlaps, rule='ex_br', offsets=None):
+    """ops/cpn.py:293-325 ('ex_br'): drop contours whose every vertex lies in the right/bottom overlap of the tile."""
+    contours = torch.as_tensor(contours)
+    tile_size = torch.as_tensor(tile_size)
+    overlaps = torch.as_tensor(overlaps)
+    if offsets is not None:
+        contours = contours + offsets
+    assert 'ex_br' in rule.split(',')
+    stop = (tile_size - overlaps[:, 1])[[1, 0]]
+    return ~((contours >= stop).any(-1).all(-1))
 
 
 def apply_model(img, sd, arch, crop_size, strides, border_removal=4, batch_size=1, **kw):

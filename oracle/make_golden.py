@@ -135,7 +135,18 @@ def mint_f2c(cd):
     print('fouriers2contours: ok')
 
 
+def check_stitching_rule(cd):
+    g = torch.Generator().manual_seed(21)
+    con = torch.rand(300, 16, 2, generator=g) * 70
+    for ov in ([[8, 16], [8, 24]], [[0, 0], [0, 30]]):
+        want = cd.ops.filter_contours_by_stitching_rule(con, (64, 64), torch.tensor(ov), offsets=torch.tensor([-2., -3.]))
+        got = orc.filter_contours_by_stitching_rule(con, (64, 64), ov, offsets=torch.tensor([-2., -3.]))
+        assert torch.equal(want, got)
+    print('stitching rule: ok')
+
+
 def mint_tiling(cd):
+    check_stitching_rule(cd)
     arrays = {}
     cases = [((640, 896), (256, 256), (192, 192)), ((512, 512), (512, 512), (384, 384)), ((100, 300), (128, 128), (96, 96)),
              ((2048, 2048), (512, 512), (384, 384)), ((1000, 777), (256, 192), (200, 100))]

@@ -198,3 +198,15 @@ def test_grid_nms_matches_torchvision_exactly():
     n = cd.ops.cpn.GRID_NMS_MIN + 10
     boxes, scores = _rand_boxes(n, g, extent=2000.), torch.rand(n, generator=g)
     assert torch.equal(torch.ops.torchvision.nms(boxes, scores, .2), cd.ops.cpn.nms(boxes.cuda(), scores.cuda(), .2).cpu())
+
+
+def test_filter_contours_by_stitching_rule():
+    g = torch.Generator().manual_seed(21)
+    con = torch.rand(300, 16, 2, generator=g) * 70
+    for ov in ([[8, 16], [8, 24]], [[0, 0], [0, 30]]):
+        off = torch.tensor([-2., -3.])
+        want = orc.filter_contours_by_stitching_rule(con, (64, 64), ov, offsets=off)
+        got = cd.ops.cpn.filter_contours_by_stitching_rule(con.cuda(), (64, 64), torch.tensor(ov), offsets=off)
+        assert torch.equal(want, got.cpu()) and 0 < int(want.sum()) < 300
+        idx = cd.ops.cpn.filter_contours_by_stitching_rule(con.cuda(), (64, 64), torch.tensor(ov), offsets=off, indices=True)
+        assert torch.equal(idx.cpu(), torch.where(want)[0])

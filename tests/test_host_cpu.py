@@ -136,7 +136,7 @@ import os, sys
 sys.path.insert(0, sys.argv[1])
 import torch, torch.distributed as dist
 from collections import OrderedDict
-from celldetection_b200.inference import allgather_detections
+from celldetection_b200.inference import allgather_detections, canonical_order
 dist.init_process_group('gloo', init_method='tcp://127.0.0.1:' + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank = dist.get_rank()
 K = 3 if rank == 0 else 5
@@ -144,7 +144,8 @@ g = torch.Generator().manual_seed(100 + rank)
 res = OrderedDict(contours=torch.rand(K, 8, 2, generator=g), boxes=torch.rand(K, 4, generator=g),
                   scores=torch.rand(K, generator=g), classes=torch.ones(K, dtype=torch.long),
                   locations=torch.rand(K, 2, generator=g), fourier=torch.rand(K, 5, 4, generator=g),
-                  contour_proposals=torch.rand(K, 8, 2, generator=g))
+                  contour_proposals=torch.rand(K, 8, 2, generator=g),
+                  order_key=torch.stack((torch.arange(K).float() * 2 + rank, torch.arange(K).float()), 1))
 out = allgather_detections(res)
 assert out['scores'].shape[0] == 8 and out['classes'].dtype == torch.long
 for r, (a, b) in enumerate(((0, 3), (3, 8))):
@@ -152,6 +153,9 @@ for r, (a, b) in enumerate(((0, 3), (3, 8))):
     kk = b - a
     want = torch.rand(kk, 8, 2, generator=gg)
     assert torch.equal(out['contours'][a:b], want), r
+can = canonical_order(out)                       # tiles were dealt round-robin: rank 0 -> 0,2,4  rank 1 -> 1,3,5,7,9
+assert can['order_key'][:, 0].tolist() == [0., 1., 2., 3., 4., 5., 7., 9.]
+assert torch.equal(can['contours'][1], out['contours'][3])
 torch.save({k: v for k, v in out.items()}, sys.argv[4] + f'.{rank}')
 dist.destroy_process_group()
 '''
