@@ -151,6 +151,29 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-convergent variants: the WHOLE warp executes the surrounding code (so descriptors stay in uniform registers and
+// ptxas does not serialise R2UR moves on a single divergent thread); elect.sync picks the one lane that issues.
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar)
+      : "memory");
+}
 // Arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -420,25 +443,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      if (lane == 0) {
-        mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);  // epilogue has drained this accumulator
+      mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-        for (int kb = 0; kb < nk; ++kb) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-          const uint64_t da = make_sw128_kmajor_desc(sa), db = make_sw128_kmajor_desc(sb);
+        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+        const uint64_t da = make_sw128_kmajor_desc(sa), db = make_sw128_kmajor_desc(sb);
+        // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+        umma_f16_elect(d_tmem, da, db, idesc, (uint32_t)(kb != 0));
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
-            umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
-          }
-          umma_commit(smem_u32(&bar_empty[stage]));  // frees the smem stage when these MMAs retire
-          if (++stage == stages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(smem_u32(&bar_tfull[acc]));  // accumulator complete -> epilogue
+        for (int k = 1; k < TC_BK / 16; ++k) umma_f16_elect(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+        umma_commit_elect(smem_u32(&bar_empty[stage]));  // frees the smem stage when these MMAs retire
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
+      umma_commit_elect(smem_u32(&bar_tfull[acc]));  // accumulator complete -> epilogue
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -606,48 +626,52 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
     const uint32_t lbo = p.swap_lbo_sbo ? (uint32_t)(p.pw * 16) : (uint32_t)p.plane_stride;
     const uint32_t sbo = p.swap_lbo_sbo ? (uint32_t)p.plane_stride : (uint32_t)(p.pw * 16);
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      if (lane == 0) {
-        mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);
+      mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);
+      tc_fence_after();
+      for (int cb = 0; cb < p.cblocks; ++cb) {
+        mbar_wait(smem_u32(&bar_afull[ab]), pha);
         tc_fence_after();
-        for (int cb = 0; cb < p.cblocks; ++cb) {
-          mbar_wait(smem_u32(&bar_afull[ab]), pha);
+        const uint32_t patch = a_base + ab * patch_bytes;
+        int tap = p.rotate ? (int)(blockIdx.x % (unsigned)taps) : 0;
+        for (int it = 0; it < taps; ++it, tap = (tap + 1 == taps ? 0 : tap + 1)) {
+          const int r = tap / p.S, s_ = tap - r * p.S;
+          mbar_wait(smem_u32(&bar_bfull[sb]), phb);
           tc_fence_after();
-          const uint32_t patch = a_base + ab * patch_bytes;
-          int tap = p.rotate ? (int)(blockIdx.x % (unsigned)taps) : 0;
-          for (int it = 0; it < taps; ++it, tap = (tap + 1 == taps ? 0 : tap + 1)) {
-            const int r = tap / p.S, s_ = tap - r * p.S;
-            mbar_wait(smem_u32(&bar_bfull[sb]), phb);
-            tc_fence_after();
-            const uint64_t db = make_sw128_kmajor_desc(smem_base + sb * B_BYTES);
+          const uint64_t db = make_sw128_kmajor_desc(smem_base + sb * B_BYTES);
+          const uint32_t first = (uint32_t)((cb | it) != 0);
+          if (p.halo_sw128) {
+            // window start = 128-byte pixel row (r, s) of the swizzled patch; 8-row groups one patch row apart;
+            // sub-tile j starts 8 pixel rows (1024 B -> +64 in the >>4 field) further, K steps +32 B (+2)
+            const uint64_t da0 = make_sw128_kmajor_desc_ex(patch + (uint32_t)((r * p.pw + s_) * 128),
+                                                           (uint32_t)(p.pw * 128), 0);
 #pragma unroll
             for (int j = 0; j < MSUB; ++j) {
               const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MSUB + j) * BN);
-              if (p.halo_sw128) {
-                // window start = 128-byte pixel row (r, s + 8j) of the swizzled patch; 8-row groups one patch row apart
-                const uint32_t win = patch + (uint32_t)((r * p.pw + s_ + 8 * j) * 128);
-                const uint64_t da0 = make_sw128_kmajor_desc_ex(win, (uint32_t)(p.pw * 128),
-                                                               p.halo_baseoff ? ((win >> 7) & 7) : 0);
+              umma_f16_elect(d_tmem, da0 + (uint64_t)(j * 64), db, idesc, first);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)
-                  umma_f16(d_tmem, da0 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((cb | it | k) != 0));
-              } else {
-                const uint32_t win = patch + (uint32_t)((r * p.pw + s_ + 8 * j) * 16);
+              for (int k = 1; k < TC_BK / 16; ++k)
+                umma_f16_elect(d_tmem, da0 + (uint64_t)(j * 64 + k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+            }
+          } else {
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                  const uint64_t da = make_nosw_kmajor_desc(win + (uint32_t)(2 * k) * p.plane_stride, lbo, sbo);
-                  umma_f16(d_tmem, da, db + (uint64_t)(k * 2), idesc, (uint32_t)((cb | it | k) != 0));
-                }
+            for (int j = 0; j < MSUB; ++j) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MSUB + j) * BN);
+              const uint32_t win = patch + (uint32_t)((r * p.pw + s_ + 8 * j) * 16);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                const uint64_t da = make_nosw_kmajor_desc(win + (uint32_t)(2 * k) * p.plane_stride, lbo, sbo);
+                umma_f16_elect(d_tmem, da, db + (uint64_t)(k * 2), idesc, k == 0 ? first : 1u);
               }
             }
-            umma_commit(smem_u32(&bar_bempty[sb]));
-            if (++sb == nb) { sb = 0; phb ^= 1; }
           }
-          umma_commit(smem_u32(&bar_aempty[ab]));   // patch free once every tap's MMAs have retired
-          ab ^= 1;
-          if (ab == 0) pha ^= 1;
+          umma_commit_elect(smem_u32(&bar_bempty[sb]));
+          if (++sb == nb) { sb = 0; phb ^= 1; }
         }
-        umma_commit(smem_u32(&bar_tfull[acc]));
+        umma_commit_elect(smem_u32(&bar_aempty[ab]));   // patch free once every tap's MMAs have retired
+        ab ^= 1;
+        if (ab == 0) pha ^= 1;
       }
+      umma_commit_elect(smem_u32(&bar_tfull[acc]));
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

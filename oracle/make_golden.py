@@ -137,7 +137,7 @@ def mint_f2c(cd):
 
 def check_stitching_rule(cd):
     g = torch.Generator().manual_seed(21)
-    con = torch.rand(300, 16, 2, generator=g) * 70
+    con = torch.rand(300, 1, 2, generator=g) * 70 + torch.rand(300, 16, 2, generator=g) * 6   # small blobs
     for ov in ([[8, 16], [8, 24]], [[0, 0], [0, 30]]):
         want = cd.ops.filter_contours_by_stitching_rule(con, (64, 64), torch.tensor(ov), offsets=torch.tensor([-2., -3.]))
         got = orc.filter_contours_by_stitching_rule(con, (64, 64), ov, offsets=torch.tensor([-2., -3.]))

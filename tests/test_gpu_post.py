@@ -202,7 +202,7 @@ def test_grid_nms_matches_torchvision_exactly():
 
 def test_filter_contours_by_stitching_rule():
     g = torch.Generator().manual_seed(21)
-    con = torch.rand(300, 16, 2, generator=g) * 70
+    con = torch.rand(300, 1, 2, generator=g) * 70 + torch.rand(300, 16, 2, generator=g) * 6   # small blobs
     for ov in ([[8, 16], [8, 24]], [[0, 0], [0, 30]]):
         off = torch.tensor([-2., -3.])
         want = orc.filter_contours_by_stitching_rule(con, (64, 64), ov, offsets=off)

@@ -173,3 +173,27 @@ def test_allgather_detections_world2_gloo(tmp_path):
     a, b = torch.load(out + '.0'), torch.load(out + '.1')
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_im2col_stem_trace_keeps_flops_and_shapes():
+    """The tensor-core engine rewrites the C_in = 3 stem as prep(im2col) + 1x1 conv: same arithmetic, same FLOP census."""
+    for arch, hw in (('CpnU22', 64), ('CpnResNeXt101UNet', 128)):
+        a, b = G.trace(arch, 2, hw, hw), G.trace(arch, 2, hw, hw, stem_im2col=True)
+        assert G.conv_flops(a) == G.conv_flops(b)
+        assert len(a.ops) == len(b.ops)
+        prep, stem = b.ops[0], b.ops[1]
+        k, cin = prep.im2col
+        assert prep.kind == 'prep' and stem.k == 1 and stem.im2col == (k, cin)
+        assert stem.src.c % 64 == 0 and stem.src.c >= k * k * cin
+        assert (stem.dst.h, stem.dst.w) == (a.ops[1].dst.h, a.ops[1].dst.w)
+        assert list(a.spec.keys()) == list(b.spec.keys())
+
+
+def test_synth_state_dict_is_deterministic_and_complete():
+    from celldetection_b200.utils.synth import synth_state_dict
+    spec = key_spec('CpnResNet18FPN')
+    a, b = synth_state_dict(spec, seed=3), synth_state_dict(spec, seed=3)
+    assert list(a.keys()) == list(spec.keys())
+    assert all(torch.equal(a[k], b[k]) and tuple(a[k].shape) == tuple(spec[k]) for k in spec)
+    c = synth_state_dict(spec, seed=4)
+    assert not torch.equal(a['core.score_head.block.0.weight'], c['core.score_head.block.0.weight'])
