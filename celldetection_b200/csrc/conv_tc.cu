@@ -510,9 +510,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 //               8-row groups (next y) PW*16 bytes apart, K chunks one plane apart -- no re-load per tap, so L2->SM
 //               traffic drops from R*S to ~(1 + halo) input reads.
 //   B operand = weights of one (tap, channel block): BN x 64 halves, SWIZZLE_128B, shared by the MSUB sub-tiles.
-// Warps: 0 = B producer, 1 = MMA issuer, 2 = A producer, 3.. = epilogue (8 warps).
+// Warps: 0 = B producer, 1 = MMA issuer (sub-tiles [0, MSUB/2) or all), 2 = A producer, 3 = second MMA issuer (MSUB = 2:
+// a 64-wide MMA occupies the tensor pipe for only 32 cycles, less than one thread needs to issue it), 4.. = epilogue.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int TCH_THREADS = 96 + 32 * TC_EPI_WARPS;
+constexpr int TCH_THREADS = 128 + 32 * TC_EPI_WARPS;   // B producer, MMA issuer 0, A producer, MMA issuer 1, epilogue
 
 template <int BN, int MSUB>
 __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
@@ -548,11 +549,12 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmH);
     prefetch_tmap(&p.tmB);
-    for (int i = 0; i < nb; ++i) { mbar_init(smem_u32(&bar_bfull[i]), 1); mbar_init(smem_u32(&bar_bempty[i]), 1); }
+    constexpr uint32_t NISSUE = MSUB >= 2 ? 2 : 1;   // MMA issuer warps; each commits once per barrier phase
+    for (int i = 0; i < nb; ++i) { mbar_init(smem_u32(&bar_bfull[i]), 1); mbar_init(smem_u32(&bar_bempty[i]), NISSUE); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_afull[i]), 1);
-      mbar_init(smem_u32(&bar_aempty[i]), 1);
-      mbar_init(smem_u32(&bar_tfull[i]), 1);
+      mbar_init(smem_u32(&bar_aempty[i]), NISSUE);
+      mbar_init(smem_u32(&bar_tfull[i]), NISSUE);
       mbar_init(smem_u32(&bar_tempty[i]), p.nproj > 0 ? 4 : TC_EPI_WARPS);
     }
     fence_barrier_init();
@@ -618,9 +620,11 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1 || (warp == 3 && MSUB >= 2)) {
+    // ================================ MMA issuer(s) ================================
     constexpr uint32_t idesc = make_idesc_f16(TC_BM, BN);
+    constexpr int JN = MSUB >= 2 ? MSUB / 2 : 1;           // sub-tiles per issuer warp
+    const int jb = (warp == 3) ? JN : 0;                   // first sub-tile of this issuer
     int sb = 0, ab = 0, acc = 0;
     uint32_t phb = 0, pha = 0, acc_phase = 0;
     const uint32_t lbo = p.swap_lbo_sbo ? (uint32_t)(p.pw * 16) : (uint32_t)p.plane_stride;
@@ -645,7 +649,8 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
             const uint64_t da0 = make_sw128_kmajor_desc_ex(patch + (uint32_t)((r * p.pw + s_) * 128),
                                                            (uint32_t)(p.pw * 128), 0);
 #pragma unroll
-            for (int j = 0; j < MSUB; ++j) {
+            for (int jj = 0; jj < JN; ++jj) {
+              const int j = jb + jj;
               const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MSUB + j) * BN);
               umma_f16_elect(d_tmem, da0 + (uint64_t)(j * 64), db, idesc, first);
 #pragma unroll
@@ -654,7 +659,8 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < MSUB; ++j) {
+            for (int jj = 0; jj < JN; ++jj) {
+              const int j = jb + jj;
               const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MSUB + j) * BN);
               const uint32_t win = patch + (uint32_t)((r * p.pw + s_ + 8 * j) * 16);
 #pragma unroll
@@ -677,8 +683,11 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
     }
   } else {
     // ================================ epilogue ================================
+    if (warp == 3) {
+      // MSUB == 1: the second issuer slot is idle
+    } else {
     const int quad = warp & 3;
-    const int half = (warp - 3) >> 2;
+    const int half = (warp - 4) >> 2;
     if (!(p.nproj > 0 && half == 1)) {
       const int row = quad * 32 + lane;
       const int py = row >> 3, px = row & 7;
@@ -702,6 +711,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
         if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+    }
     }
   }
   tc_fence_before();
