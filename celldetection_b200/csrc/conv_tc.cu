@@ -831,10 +831,10 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
     if (halo_env < 0) { const char* e = getenv("CPN_HALO"); halo_env = (e && atoi(e) == 0) ? 0 : 1; }
     if (sw128_env < 0) { const char* e = getenv("CPN_HALO_SW128"); sw128_env = (e && atoi(e) == 0) ? 0 : 1; }
     if (baseoff_env < 0) { const char* e = getenv("CPN_HALO_BASEOFF"); baseoff_env = (e && atoi(e) == 1) ? 1 : 0; }
-    if (halo33_env < 0) { const char* e = getenv("CPN_HALO_ALL"); halo33_env = (e && atoi(e) == 1) ? 1 : 0; }
+    if (halo33_env < 0) { const char* e = getenv("CPN_HALO_ALL"); halo33_env = (e && atoi(e) == 0) ? 0 : 1; }
     if (swap_env < 0) { const char* e = getenv("CPN_HALO_SWAP"); swap_env = (e && atoi(e) == 1) ? 1 : 0; }
-    // measured (profiles/r01): the halo variant wins whenever the operand traffic per MMA is high -- every 7x7, and
-    // kxk layers with <= 128 output channels; 3x3 layers with 256-wide tiles are faster with per-tap box loads.
+    // measured (profiles/r01_summary.md): with the warp-convergent MMA issue the halo variant wins for every stride-1
+    // kxk layer (3x3 @256-wide: 1500-1650 vs 1360-1590 TF/s); CPN_HALO_ALL=0 restricts it to 7x7 and <= 128-wide tiles.
     const bool worth = halo33_env || op.r * op.s >= 25 || bn <= 128;
     if (halo_env && worth && op.stride == 1 && op.r * op.s > 1 && op.r <= 16 && op.s <= 16) {
       const int msub = bn == 256 ? 1 : 2;
