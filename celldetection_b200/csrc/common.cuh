@@ -43,7 +43,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     cpn::count_launch();                                                                     \
   } while (0)
 
-inline int dtype_size(int dt) { return dt == CPN_DT_F32 ? 4 : (dt == CPN_DT_F16 ? 2 : 1); }
+inline int dtype_size(int dt) { return dt == CPN_DT_F32 ? 4 : ((dt == CPN_DT_F16 || dt == CPN_DT_F16X2) ? 2 : 1); }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();  // cached SM count of the current device

@@ -64,6 +64,8 @@ struct ConvTcParams {
   CUtensorMap tmH;          // (C, W, H, N), box {8, PW, PH, 1}, no swizzle
   int halo, pw, ph, plane_stride, nb_stages, swap_lbo_sbo;
   int halo_sw128, halo_baseoff;
+  int split, a_lo, out_lo, res_lo;   // CPN_DT_F16X2: 3 passes per 64-channel block (A_hi W_hi, A_lo W_hi, A_hi W_lo);
+                                     // element distance hi -> lo half in the A / output / residual buffers
   int rotate;               // start each CTA's K loop at a different (tap, block): de-correlates the L2 reads of the shared weights   // 1: the patch is ONE box {64, PW, PH, 1} with SWIZZLE_128B (128-byte pixel rows)
 };
 
@@ -317,8 +319,9 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
     tmem_ld_wait();
     if (valid) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
-      uint4 packed[4];
+      uint4 packed[4], packed_lo[4];
       uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
+      uint32_t* pl = reinterpret_cast<uint32_t*>(packed_lo);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float4 b = p.bias ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -328,15 +331,31 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
           const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp + ch * 32 + q * 4));
           const __half2 r0 = *reinterpret_cast<const __half2*>(&rr.x), r1 = *reinterpret_cast<const __half2*>(&rr.y);
           f0 += __low2float(r0); f1 += __high2float(r0); f2 += __low2float(r1); f3 += __high2float(r1);
+          if (p.split) {   // residual = hi + lo
+            const uint2 rl = __ldg(reinterpret_cast<const uint2*>(rp + p.res_lo + ch * 32 + q * 4));
+            const __half2 l0 = *reinterpret_cast<const __half2*>(&rl.x), l1 = *reinterpret_cast<const __half2*>(&rl.y);
+            f0 += __low2float(l0); f1 += __high2float(l0); f2 += __low2float(l1); f3 += __high2float(l1);
+          }
         }
         if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
         __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
         pk[q * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
         pk[q * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        if (p.split) {     // lo = fp16(v - hi)
+          __half2 g0 = __floats2half2_rn(f0 - __low2float(h0), f1 - __high2float(h0));
+          __half2 g1 = __floats2half2_rn(f2 - __low2float(h1), f3 - __high2float(h1));
+          pl[q * 2 + 0] = *reinterpret_cast<uint32_t*>(&g0);
+          pl[q * 2 + 1] = *reinterpret_cast<uint32_t*>(&g1);
+        }
       }
       uint4* o4 = reinterpret_cast<uint4*>(op + ch * 32);
 #pragma unroll
       for (int q = 0; q < 4; ++q) o4[q] = packed[q];
+      if (p.split) {
+        uint4* l4 = reinterpret_cast<uint4*>(op + p.out_lo + ch * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) l4[q] = packed_lo[q];
+      }
     }
   }
   }
@@ -415,8 +434,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int cbase = p.slab_mode ? (n0 / p.kslab) * p.kslab : 0;
         int kk = p.rotate ? (int)(blockIdx.x % (unsigned)nk) : 0;   // rotated start of the K loop (sum order is free)
         for (int it = 0; it < nk; ++it) {
-          const int tap = kk / p.cblocks, cb = kk - tap * p.cblocks;
+          const int tap = kk / p.cblocks, cb = kk - tap * p.cblocks;   // cb runs over 3 * logical blocks when split
           if (++kk == nk) kk = 0;
+          int a_ch = cb * TC_BK;
+          if (p.split) {
+            const int cbl = p.cblocks / 3, pass = cb / cbl;
+            a_ch = (cb - pass * cbl) * TC_BK + (pass == 1 ? p.a_lo : 0);
+          }
           const int r = tap / p.S, s = tap - r * p.S;
           int qy = r - p.pad, qx = s - p.pad, map = 0;
           if (p.stride == 2) {
@@ -429,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const uint32_t full = smem_u32(&bar_full[stage]);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
           mbar_expect_tx(full, STAGE_BYTES);
-          tma_load_4d(sa, &p.tmA[map], full, cbase + cb * TC_BK, x0 + qx, y0 + qy, img);
+          tma_load_4d(sa, &p.tmA[map], full, cbase + a_ch, x0 + qx, y0 + qy, img);
           tma_load_3d(sb, &p.tmB, full, cb * TC_BK, n0, tap);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -603,17 +627,21 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
         const int n0 = (int)(tile % p.tiles_n) * BN;
         const int cbase = p.slab_mode ? (n0 / p.kslab) * p.kslab : 0;   // grouped: this N tile's 64-channel slab
         for (int cb = 0; cb < p.cblocks; ++cb) {
+          int a_ch = cb * TC_BK;
+          if (p.split) {
+            const int cbl = p.cblocks / 3, pass = cb / cbl;
+            a_ch = (cb - pass * cbl) * TC_BK + (pass == 1 ? p.a_lo : 0);
+          }
           mbar_wait(smem_u32(&bar_aempty[ab]), pha ^ 1);
           const uint32_t full = smem_u32(&bar_afull[ab]);
           mbar_expect_tx(full, a_tx);
           const uint32_t dst = a_base + ab * patch_bytes;
           if (p.halo_sw128) {
-            tma_load_4d(dst, &p.tmH, full, cbase + cb * TC_BK, x0 - p.pad, y0 - p.pad, img);
+            tma_load_4d(dst, &p.tmH, full, cbase + a_ch, x0 - p.pad, y0 - p.pad, img);
           } else {
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc)
-              tma_load_4d(dst + kc * p.plane_stride, &p.tmH, full, cbase + cb * TC_BK + kc * 8, x0 - p.pad, y0 - p.pad,
-                          img);
+              tma_load_4d(dst + kc * p.plane_stride, &p.tmH, full, cbase + a_ch + kc * 8, x0 - p.pad, y0 - p.pad, img);
           }
           ab ^= 1;
           if (ab == 0) pha ^= 1;
@@ -761,8 +789,12 @@ static int pick_bn(int cout, int slab_mode) {
 
 int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const void* res, const void* wgt,
                         const float* bias, ConvTcPlan** out) {
-  CPN_REQUIRE(op.src.dtype == CPN_DT_F16 && op.dst.dtype == CPN_DT_F16, "conv_tc: fp16 activations required");
-  CPN_REQUIRE(op.res.n == 0 || op.res.dtype == CPN_DT_F16, "conv_tc: fp16 residual required");
+  const bool split = op.src.dtype == CPN_DT_F16X2;
+  CPN_REQUIRE((op.src.dtype == CPN_DT_F16 || split) && op.dst.dtype == op.src.dtype,
+              "conv_tc: fp16 (or split fp16) activations required");
+  CPN_REQUIRE(op.res.n == 0 || op.res.dtype == op.src.dtype, "conv_tc: residual dtype must match");
+  CPN_REQUIRE(!split || (op.src.lo_delta % 8 == 0 && op.dst.lo_delta % 8 == 0 && (op.res.n == 0 || op.res.lo_delta % 8 == 0)),
+              "conv_tc: lo_delta must be a multiple of 8 elements");
   CPN_REQUIRE(op.kslab % TC_BK == 0, "conv_tc: kslab %d must be a multiple of 64", op.kslab);
   CPN_REQUIRE(op.dst.c % 64 == 0, "conv_tc: cout %d must be a multiple of 64", op.dst.c);
   CPN_REQUIRE(op.stride == 1 || op.stride == 2, "conv_tc: stride %d unsupported", op.stride);
@@ -792,7 +824,8 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
       continue;
     }
     const char* base = reinterpret_cast<const char*>(src) + ((long long)py * op.src.w + px) * op.src.pitch * 2;
-    cuuint64_t dims[4] = {(cuuint64_t)op.src.c, (cuuint64_t)wv, (cuuint64_t)hv, (cuuint64_t)op.src.n};
+    cuuint64_t dims[4] = {(cuuint64_t)(op.src.c + (split ? op.src.lo_delta : 0)), (cuuint64_t)wv, (cuuint64_t)hv,
+                          (cuuint64_t)op.src.n};
     cuuint64_t strides[3] = {(cuuint64_t)st * op.src.pitch * 2, (cuuint64_t)st * op.src.w * op.src.pitch * 2,
                              (cuuint64_t)op.src.h * op.src.w * op.src.pitch * 2};
     cuuint32_t box[4] = {TC_BK, TC_BW, TC_BH, 1};
@@ -800,8 +833,9 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   }
   for (int m = nmaps; m < 4; ++m) p.tmA[m] = p.tmA[0];
   {
-    cuuint64_t dims[3] = {(cuuint64_t)op.kslab, (cuuint64_t)op.dst.c, (cuuint64_t)(op.r * op.s)};
-    cuuint64_t strides[2] = {(cuuint64_t)op.kslab * 2, (cuuint64_t)op.kslab * op.dst.c * 2};
+    const cuuint64_t kw = (cuuint64_t)op.kslab * (split ? 3 : 1);   // split: weights are (W_hi | W_hi | W_lo) along K
+    cuuint64_t dims[3] = {kw, (cuuint64_t)op.dst.c, (cuuint64_t)(op.r * op.s)};
+    cuuint64_t strides[2] = {kw * 2, kw * op.dst.c * 2};
     cuuint32_t box[3] = {TC_BK, (cuuint32_t)bn, 1};
     if (encode_map(&p.tmB, const_cast<void*>(wgt), 3, dims, strides, box)) { delete pl; return 1; }
   }
@@ -812,7 +846,8 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   p.res_h = op.res.n ? op.res.h : 0; p.res_w = op.res.n ? op.res.w : 0;
   p.N = op.dst.n; p.Ho = op.dst.h; p.Wo = op.dst.w; p.cout = op.dst.c;
   p.R = op.r; p.S = op.s; p.stride = op.stride; p.pad = op.pad;
-  p.cblocks = op.kslab / TC_BK; p.kslab = op.kslab; p.slab_mode = op.slab_mode;
+  p.cblocks = op.kslab / TC_BK * (split ? 3 : 1); p.kslab = op.kslab; p.slab_mode = op.slab_mode;
+  p.split = split ? 1 : 0; p.a_lo = op.src.lo_delta; p.out_lo = op.dst.lo_delta; p.res_lo = op.res.n ? op.res.lo_delta : 0;
   p.relu = op.act == CPN_ACT_RELU;
   {
     static int rot_env = -1;
@@ -845,7 +880,8 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
       int nbs = (TC_SMEM_BUDGET - 2 * patch) / b_bytes;
       if (nbs > 8) nbs = 8;
       if (nbs >= 2 && pw <= 256 && ph <= 256) {
-        cuuint64_t dims[4] = {(cuuint64_t)op.src.c, (cuuint64_t)op.src.w, (cuuint64_t)op.src.h, (cuuint64_t)op.src.n};
+        cuuint64_t dims[4] = {(cuuint64_t)(op.src.c + (split ? op.src.lo_delta : 0)), (cuuint64_t)op.src.w,
+                              (cuuint64_t)op.src.h, (cuuint64_t)op.src.n};
         cuuint64_t strides[3] = {(cuuint64_t)op.src.pitch * 2, (cuuint64_t)op.src.w * op.src.pitch * 2,
                                  (cuuint64_t)op.src.h * op.src.w * op.src.pitch * 2};
         cuuint32_t box[4] = {(cuuint32_t)(sw128_env ? 64 : 8), (cuuint32_t)pw, (cuuint32_t)ph, 1};

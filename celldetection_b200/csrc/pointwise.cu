@@ -17,9 +17,15 @@ static inline int grid_for(long long work_items, int threads) {
 // PREP: network input -> NHWC activations.  Fuses Normalize's range assertion (commons.py:694-700; mean 0 / std 1 so the
 // affine part is the identity), the uint8 -> float / 255 of lightning_base.py:774-780 and the NCHW -> NHWC change.
 // ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_store(__half* o, int lo_delta, float v) {
+  const __half h = __float2half_rn(v);
+  o[0] = h;
+  o[lo_delta] = __float2half_rn(v - __half2float(h));
+}
+
 template <typename T>
 __global__ void prep_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out, int N, int C, int H, int W,
-                            int pitch, int32_t* __restrict__ flags) {
+                            int pitch, int32_t* __restrict__ flags, int lo_delta) {
   const long long total = (long long)N * H * W;
   bool bad = false;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -37,6 +43,7 @@ __global__ void prep_kernel(const void* __restrict__ in, int fmt, T* __restrict_
         v = (float)reinterpret_cast<const uint8_t*>(in)[i * C + c] / 255.f;
       }
       o[c] = from_f32<T>(v);
+      if (sizeof(T) == 2 && lo_delta > 0) o[c + lo_delta] = from_f32<T>(v - to_f32<T>(o[c]));
     }
   }
   if (bad) atomicOr(flags, 1);
@@ -49,7 +56,8 @@ __global__ void prep_kernel(const void* __restrict__ in, int fmt, T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) prep_im2col_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out, int N,
                                                           int C, int H, int W, int Ho, int Wo, int Kp, int pitch, int k,
-                                                          int stride, int pad, int32_t* __restrict__ flags) {
+                                                          int stride, int pad, int32_t* __restrict__ flags,
+                                                          int lo_delta) {
   // per-entry tables: e -> (dy, dx, c) and the NCHW / NHWC offsets relative to the window origin
   __shared__ int off_nchw[512], off_nhwc[512];
   __shared__ signed char dys[512], dxs[512];
@@ -77,6 +85,7 @@ __global__ void __launch_bounds__(256) prep_im2col_kernel(const void* __restrict
     const long long base_nchw = ((long long)n * C * H + iy0) * W + ix0;
     const long long base_nhwc = (((long long)n * H + iy0) * W + ix0) * C;
     __align__(16) T vals[8];
+    __align__(16) T vlo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int e = ch * 8 + j;
@@ -95,10 +104,12 @@ __global__ void __launch_bounds__(256) prep_im2col_kernel(const void* __restrict
         }
       }
       vals[j] = from_f32<T>(v);
+      vlo[j] = from_f32<T>(v - to_f32<T>(vals[j]));
     }
     T* o = out + (((long long)n * Ho + oy) * Wo + ox) * pitch + ch * 8;
     if (sizeof(T) == 2) {
       *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(vals);
+      if (lo_delta > 0) *reinterpret_cast<uint4*>(o + lo_delta) = *reinterpret_cast<const uint4*>(vlo);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = vals[j];
@@ -117,11 +128,12 @@ int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* d
     if (op.dst.dtype == CPN_DT_F32)
       prep_im2col_kernel<float><<<grid, 256, 0, st>>>(input, input_format, (float*)dst, op.src.n, op.src.c, op.src.h,
                                                       op.src.w, op.dst.h, op.dst.w, op.dst.c, op.dst.pitch, op.r,
-                                                      op.stride, op.pad, flags);
+                                                      op.stride, op.pad, flags, 0);
     else
       prep_im2col_kernel<__half><<<grid, 256, 0, st>>>(input, input_format, (__half*)dst, op.src.n, op.src.c, op.src.h,
                                                        op.src.w, op.dst.h, op.dst.w, op.dst.c, op.dst.pitch, op.r,
-                                                       op.stride, op.pad, flags);
+                                                       op.stride, op.pad, flags,
+                                                       op.dst.dtype == CPN_DT_F16X2 ? op.dst.lo_delta : 0);
     CPN_CHECK_LAUNCH();
     return 0;
   }
@@ -129,10 +141,11 @@ int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* d
   const int grid = grid_for(total, 256);
   if (op.dst.dtype == CPN_DT_F32)
     prep_kernel<float><<<grid, 256, 0, st>>>(input, input_format, (float*)dst, op.dst.n, op.dst.c, op.dst.h, op.dst.w,
-                                             op.dst.pitch, flags);
+                                             op.dst.pitch, flags, 0);
   else
     prep_kernel<__half><<<grid, 256, 0, st>>>(input, input_format, (__half*)dst, op.dst.n, op.dst.c, op.dst.h,
-                                              op.dst.w, op.dst.pitch, flags);
+                                              op.dst.w, op.dst.pitch, flags,
+                                              op.dst.dtype == CPN_DT_F16X2 ? op.dst.lo_delta : 0);
   CPN_CHECK_LAUNCH();
   return 0;
 }
@@ -201,7 +214,48 @@ __global__ void maxpool_kernel(const T* __restrict__ src, T* __restrict__ dst, i
   }
 }
 
+// split fp16 pairs: the maximum is taken on the reconstructed value hi + lo and the winning PAIR is copied
+__global__ void maxpool_split_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int H, int W, int C,
+                                     int sp, int slo, int Ho, int Wo, int dp, int dlo, int k, int stride, int pad) {
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long pix = i / C;
+    const int ox = (int)(pix % Wo);
+    pix /= Wo;
+    const int oy = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    float best = -INFINITY;
+    __half bh = __float2half(0.f), bl = __float2half(0.f);
+    for (int dy = 0; dy < k; ++dy) {
+      const int iy = oy * stride - pad + dy;
+      if (iy < 0 || iy >= H) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        const int ix = ox * stride - pad + dx;
+        if (ix < 0 || ix >= W) continue;
+        const __half* q = src + (((long long)n * H + iy) * W + ix) * sp + c;
+        const __half h = q[0], l = q[slo];
+        const float v = __half2float(h) + __half2float(l);
+        if (v > best) { best = v; bh = h; bl = l; }
+      }
+    }
+    __half* o = dst + (((long long)n * Ho + oy) * Wo + ox) * dp + c;
+    o[0] = bh;
+    o[dlo] = bl;
+  }
+}
+
 int maxpool_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st) {
+  if (op.src.dtype == CPN_DT_F16X2) {
+    CPN_REQUIRE(op.dst.dtype == CPN_DT_F16X2 && op.src.c == op.dst.c, "maxpool: split dtype/channel mismatch");
+    const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * op.dst.c;
+    maxpool_split_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __half*)src, (__half*)dst, op.src.n, op.src.h,
+                                                              op.src.w, op.src.c, op.src.pitch, op.src.lo_delta, op.dst.h,
+                                                              op.dst.w, op.dst.pitch, op.dst.lo_delta, op.r, op.stride,
+                                                              op.pad);
+    CPN_CHECK_LAUNCH();
+    return 0;
+  }
   CPN_REQUIRE(op.src.c % 4 == 0 && op.src.pitch % 4 == 0 && op.dst.pitch % 4 == 0 && op.src.c == op.dst.c,
               "maxpool: channels/pitch must be multiples of 4");
   CPN_REQUIRE(op.src.dtype == op.dst.dtype, "maxpool: dtype mismatch");
@@ -260,7 +314,16 @@ __global__ void __launch_bounds__(256) upsample_int_kernel(const uint4* __restri
   }
 }
 
-int upsample_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st) {
+int upsample_launch(const cpn_op_t& op_in, const void* src, void* dst, cudaStream_t st) {
+  if (op_in.src.dtype == CPN_DT_F16X2) {   // nearest copy is exact per half: run the fp16 kernel on the hi and lo planes
+    CPN_REQUIRE(op_in.dst.dtype == CPN_DT_F16X2, "upsample: split dtype mismatch");
+    cpn_op_t o = op_in;
+    o.src.dtype = o.dst.dtype = CPN_DT_F16;
+    if (upsample_launch(o, src, dst, st)) return 1;
+    return upsample_launch(o, reinterpret_cast<const __half*>(src) + op_in.src.lo_delta,
+                           reinterpret_cast<__half*>(dst) + op_in.dst.lo_delta, st);
+  }
+  const cpn_op_t& op = op_in;
   CPN_REQUIRE(op.src.c % 4 == 0 && op.src.pitch % 4 == 0 && op.dst.pitch % 4 == 0 && op.src.c == op.dst.c,
               "upsample: channels/pitch must be multiples of 4");
   CPN_REQUIRE(op.src.dtype == op.dst.dtype, "upsample: dtype mismatch");
@@ -359,8 +422,46 @@ __global__ void __launch_bounds__(256) bilinear_h8_kernel(const uint4* __restric
   }
 }
 
+// split fp16 pairs: blend the reconstructed values in fp32, split the result again
+__global__ void bilinear_split_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int H, int W, int C,
+                                      int sp, int slo, int Ho, int Wo, int dp, int dlo) {
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long pix = i / C;
+    const int ox = (int)(pix % Wo);
+    pix /= Wo;
+    const int oy = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    float fy = sy * ((float)oy + 0.5f) - 0.5f, fx = sx * ((float)ox + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const __half* b = src + (long long)n * H * W * sp + c;
+    auto val = [&](int y, int x) {
+      const __half* q = b + ((long long)y * W + x) * sp;
+      return __half2float(q[0]) + __half2float(q[slo]);
+    };
+    const float v = hy * (hx * val(y0, x0) + lx * val(y0, x1)) + ly * (hx * val(y1, x0) + lx * val(y1, x1));
+    split_store(dst + (((long long)n * Ho + oy) * Wo + ox) * dp + c, dlo, v);
+  }
+}
+
 int bilinear_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st) {
   CPN_REQUIRE(op.src.c == op.dst.c, "bilinear: channel mismatch");
+  if (op.src.dtype == CPN_DT_F16X2) {
+    CPN_REQUIRE(op.dst.dtype == CPN_DT_F16X2, "bilinear: split dtype mismatch");
+    const long long tot = (long long)op.dst.n * op.dst.h * op.dst.w * op.dst.c;
+    bilinear_split_kernel<<<grid_for(tot, 256), 256, 0, st>>>((const __half*)src, (__half*)dst, op.src.n, op.src.h,
+                                                             op.src.w, op.src.c, op.src.pitch, op.src.lo_delta, op.dst.h,
+                                                             op.dst.w, op.dst.pitch, op.dst.lo_delta);
+    CPN_CHECK_LAUNCH();
+    return 0;
+  }
   const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * op.dst.c;
   const int grid = grid_for(total, 256);
   if (op.src.dtype == CPN_DT_F16 && op.dst.dtype == CPN_DT_F16 && op.src.c % 8 == 0 && op.src.pitch % 8 == 0 &&
@@ -393,7 +494,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) proj_kernel(const T* __restrict__ src, float* __restrict__ dst,
                                                    const float* __restrict__ wgt, const float* __restrict__ bias,
                                                    long long pixels, int sp, int cin_off, int cin, int cout, int dp,
-                                                   int act, float act_scale) {
+                                                   int act, float act_scale, int lo_delta) {
   extern __shared__ float wsm[];  // [cout][cin]
   for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) wsm[i] = wgt[i];
   __syncthreads();
@@ -403,9 +504,10 @@ __global__ void __launch_bounds__(256) proj_kernel(const T* __restrict__ src, fl
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-    for (int c = lane * 4; c < cin; c += 128) {
+    for (int cc = lane * 4; cc < (lo_delta > 0 ? 2 * cin : cin); cc += 128) {
+      const int c = cc < cin ? cc : cc - cin;            // split sources: second sweep adds the lo halves
       Pack4<T> pk;
-      pk.load(sp_ + c);
+      pk.load(sp_ + c + (cc < cin ? 0 : lo_delta));
       float f[4];
       pk.get(f);
 #pragma unroll
@@ -457,11 +559,12 @@ int proj_launch(const cpn_op_t& op, const void* src, void* dst, const float* wgt
   if (op.src.dtype == CPN_DT_F32)
     proj_kernel<float><<<(int)blocks, 256, smem, st>>>((const float*)src, (float*)dst, wgt, bias, pixels, op.src.pitch,
                                                        op.proj_cin_off, op.proj_cin, op.dst.c, op.dst.pitch, op.act,
-                                                       op.act_scale);
+                                                       op.act_scale, 0);
   else
     proj_kernel<__half><<<(int)blocks, 256, smem, st>>>((const __half*)src, (float*)dst, wgt, bias, pixels,
                                                         op.src.pitch, op.proj_cin_off, op.proj_cin, op.dst.c,
-                                                        op.dst.pitch, op.act, op.act_scale);
+                                                        op.dst.pitch, op.act, op.act_scale,
+                                                        op.src.dtype == CPN_DT_F16X2 ? op.src.lo_delta : 0);
   CPN_CHECK_LAUNCH();
   return 0;
 }

@@ -24,7 +24,7 @@ from .plan import Plan, WeightPack
 
 __all__ = ['CPN', 'CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet']
 
-PRECISIONS = ('fp16', 'fp32')
+PRECISIONS = ('fp16', 'fp16x3', 'fp32')
 
 
 class _Node(nn.Module):
@@ -56,7 +56,9 @@ class CPN(nn.Module):
             order, nms_thresh, score_thresh, samples, classes, refinement, refinement_iterations, refinement_margin,
                 refinement_buckets: as in the reference (models/cpn.py:288-321).
             precision: ``'fp16'`` -- tcgen05 tensor-core engine, fp16 activations/weights, fp32 accumulation (default);
-                ``'fp32'`` -- strict CUDA-core fp32 engine used for parity gating.
+                ``'fp16x3'`` -- the same engine with activations and weights split into fp16 (hi, lo) pairs and three
+                tensor-core passes per K block (hi*hi + lo*hi + hi*lo), i.e. fp32-level accuracy at a third of the
+                tensor throughput; ``'fp32'`` -- strict CUDA-core fp32 engine (reference for parity gating).
         """
         super().__init__()
         if backbone not in ARCHS:
@@ -157,20 +159,21 @@ class CPN(nn.Module):
         if dev.type != 'cuda':
             raise RuntimeError('celldetection_b200.CPN runs on CUDA (sm_100a) only: move the model with .cuda(). '
                                'There is no CPU fallback.')
-        fast = self.precision == 'fp16'
-        key = (n, h, w, fast)
+        fast = self.precision in ('fp16', 'fp16x3')
+        split = self.precision == 'fp16x3'
+        key = (n, h, w, self.precision)
         plan = self._plans.get(key)
         if plan is None:
             g = trace(self.arch, n, h, w, in_channels=self.in_channels, order=self.core_order,
                       refinement_margin=self.refinement_margin, stem_im2col=fast)
-            pack = self._packs.get(fast)
+            pack = self._packs.get(self.precision)
             if pack is None:
                 with torch.no_grad():
-                    pack = WeightPack(g, self.state_dict(), fast, dev)
-                self._packs[fast] = pack
+                    pack = WeightPack(g, self.state_dict(), fast, dev, split=split)
+                self._packs[self.precision] = pack
             if len(self._plans) >= 4:
                 self._plans.pop(next(iter(self._plans)))
-            plan = Plan(g, pack, fast, dev)
+            plan = Plan(g, pack, fast, dev, split=split)
             self._plans[key] = plan
         return plan
 

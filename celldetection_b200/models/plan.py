@@ -73,9 +73,10 @@ def engine_for(op: LOp, fast, cin):
 
 
 class WeightPack:
-    """Device blob with every conv / projection weight of a model in one precision mode."""
+    """Device blob with every conv / projection weight of a model in one precision mode.  ``split``: weights of the
+    3-pass engine, ``(W_hi | W_hi | W_lo)`` along K with ``W_hi = fp16(W)``, ``W_lo = fp16(W - W_hi)``."""
 
-    def __init__(self, g: Tracer, sd, fast, device):
+    def __init__(self, g: Tracer, sd, fast, device, split=False):
         chunks, off = [], 0
         self.entries = {}
         for i, op in enumerate(g.ops):
@@ -94,11 +95,20 @@ class WeightPack:
             else:
                 cin = op.src.c
                 eng = engine_for(op, fast, cin)
+                if split and eng != L.ENGINE_TCGEN05:
+                    raise NotImplementedError(f'{op.name}: the fp16x3 engine needs tensor-core-eligible layers')
                 if op.params.groups > 1:
                     w = expand_grouped(w, op.params.groups)
                 cout, kslab, kh, kw = w.shape
                 if eng == L.ENGINE_TCGEN05:   # [R*S][cout][kslab] fp16
-                    wp = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, kslab).contiguous().half()
+                    wp = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, kslab).contiguous()
+                    if split:
+                        assert eng == L.ENGINE_TCGEN05
+                        hi = wp.half()
+                        lo = (wp - hi.float()).half()
+                        wp = torch.cat((hi, hi, lo), 2).contiguous()
+                    else:
+                        wp = wp.half()
                 else:                          # [R*S][kslab][cout] fp32
                     wp = w.permute(2, 3, 1, 0).reshape(kh * kw, kslab, cout).contiguous().float()
             wb = wp.view(torch.uint8).reshape(-1)
@@ -116,12 +126,20 @@ class WeightPack:
         self.bytes = off
 
 
-def assign_arena(g: Tracer, elem_size):
+def _pitch(c, split=False):
+    """Physical pixel pitch (elements) of a root buffer with c logical channels; split buffers hold (hi | lo) halves."""
+    p = c if c % 4 == 0 else _align(c, 4)
+    if split:
+        p = 2 * (p if p % 8 == 0 else _align(p, 8))
+    return p
+
+
+def assign_arena(g: Tracer, elem_size, split=False):
     """First-fit placement of root buffers by live range.  Returns ({tensor id: byte offset of its root}, bytes)."""
     roots = []
     for t in g.tensors:
         if t.parent is None and not t.f32 and t.last >= 0:
-            pitch = t.c if t.c % 4 == 0 else _align(t.c, 4)
+            pitch = _pitch(t.c, split)
             roots.append((t.first, t.last, _align(g.n * t.h * t.w * pitch * elem_size), t))
     roots.sort(key=lambda r: (r[0], -r[2]))
     placed = []   # (offset, size, last)
@@ -142,21 +160,23 @@ def assign_arena(g: Tracer, elem_size):
 
 def _view(t: TT, n, root_off, elem_size, dtype):
     r, coff = t.root()
-    pitch = r.c if r.c % 4 == 0 else _align(r.c, 4)
+    split = dtype == L.DT_F16X2
+    pitch = _pitch(r.c, split)
     v = L.View()
     v.offset = root_off.get(r.id, 0) + coff * elem_size
     v.n, v.h, v.w, v.c, v.pitch, v.dtype = n, t.h, t.w, t.c, pitch, dtype
+    v.lo_delta = pitch // 2 if split else 0        # (hi block | lo block) inside every pixel of the root buffer
     return v
 
 
 class Plan:
     """A compiled (architecture, N, H, W, precision) instance: C plan + arena + output buffers."""
 
-    def __init__(self, g: Tracer, pack: WeightPack, fast, device):
+    def __init__(self, g: Tracer, pack: WeightPack, fast, device, split=False):
         lib = L.load()
-        self.g, self.pack, self.fast, self.device = g, pack, fast, device
-        act_dt, es = (L.DT_F16, 2) if fast else (L.DT_F32, 4)
-        offsets, arena_bytes = assign_arena(g, es)
+        self.g, self.pack, self.fast, self.device, self.split = g, pack, fast, device, split
+        act_dt, es = ((L.DT_F16X2 if split else L.DT_F16), 2) if fast else (L.DT_F32, 4)
+        offsets, arena_bytes = assign_arena(g, es, split)
         self.arena = torch.empty(max(arena_bytes, ALIGN), dtype=torch.uint8, device=device)
         self.flags = torch.zeros(4, dtype=torch.int32, device=device)
         ops = (L.Op * len(g.ops))()
@@ -249,13 +269,16 @@ class Plan:
         """Debug: copy logical tensor `t` out of the arena as an NCHW fp32 tensor (valid right after forward only
         for tensors whose buffer has not been reused)."""
         es, dt = (2, torch.float16) if self.fast else (4, torch.float32)
-        offsets, _ = assign_arena(self.g, es)
+        offsets, _ = assign_arena(self.g, es, self.split)
         r, coff = t.root()
-        pitch = r.c if r.c % 4 == 0 else _align(r.c, 4)
+        pitch = _pitch(r.c, self.split)
         nbytes = self.g.n * t.h * t.w * pitch * es
         base = offsets[r.id]
         buf = self.arena[base:base + nbytes].view(dt).reshape(self.g.n, t.h, t.w, pitch)
-        return buf[..., coff:coff + t.c].permute(0, 3, 1, 2).float().contiguous()
+        out = buf[..., coff:coff + t.c].float()
+        if self.split:
+            out = out + buf[..., pitch // 2 + coff:pitch // 2 + coff + t.c].float()
+        return out.permute(0, 3, 1, 2).contiguous()
 
     def __del__(self):
         try:

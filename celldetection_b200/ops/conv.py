@@ -12,9 +12,24 @@ from ..models.plan import expand_grouped, slab_of
 __all__ = ['conv2d']
 
 
+def _split_nhwc(t_nchw, c_pad):
+    """NCHW fp32 -> NHWC (hi | lo) fp16 pairs with c_pad channels per half."""
+    n, c, h, w = t_nchw.shape
+    v = t_nchw.permute(0, 2, 3, 1).float()
+    hi = v.half()
+    lo = (v - hi.float()).half()
+    out = torch.zeros((n, h, w, 2 * c_pad), dtype=torch.float16, device=t_nchw.device)
+    out[..., :c] = hi
+    out[..., c_pad:c_pad + c] = lo
+    return out
+
+
 def conv2d(x, weight, bias=None, stride=1, padding=0, groups=1, residual=None, relu=False, engine='simt',
            half=None):
-    """x [N,Cin,H,W], weight [Cout,Cin/groups,k,k] (CUDA) -> [N,Cout,Ho,Wo] fp32."""
+    """x [N,Cin,H,W], weight [Cout,Cin/groups,k,k] (CUDA) -> [N,Cout,Ho,Wo] fp32.
+    ``engine``: 'simt' | 'tcgen05' | 'tcgen05x3' (split fp16 pairs, three tensor-core passes)."""
+    if engine == 'tcgen05x3':
+        return _conv2d_split(x, weight, bias, stride, padding, groups, residual, relu)
     if not x.is_cuda:
         raise RuntimeError('conv2d runs on CUDA tensors only')
     lib = L.load()
@@ -59,3 +74,45 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, groups=1, residual=None, r
     import ctypes
     L.check(lib.cpn_conv2d(ctypes.byref(op), L.ptr(xs), L.ptr(out), L.ptr(rs), L.ptr(blob), L.stream_ptr()), 'conv2d')
     return out.permute(0, 3, 1, 2).float()
+
+
+def _conv2d_split(x, weight, bias, stride, padding, groups, residual, relu):
+    import ctypes
+    lib = L.load()
+    n, cin, h, w = x.shape
+    cout, _, k, _ = weight.shape
+    ho, wo = (h + 2 * padding - k) // stride + 1, (w + 2 * padding - k) // stride + 1
+    cin_p, cout_p = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
+    xs = _split_nhwc(x, cin_p)
+    out = torch.zeros((n, ho, wo, 2 * cout_p), dtype=torch.float16, device=x.device)
+    wf = weight.float()
+    if groups > 1:
+        wf = expand_grouped(wf, groups)
+    kslab, mode = slab_of(cin, cout, groups)
+    wp = wf.permute(2, 3, 0, 1).reshape(k * k, cout, kslab).contiguous()
+    hi = wp.half()
+    lo = (wp - hi.float()).half()
+    wb = torch.cat((hi, hi, lo), 2).contiguous().view(torch.uint8).reshape(-1)
+    b_off = (wb.numel() + 255) // 256 * 256
+    bb = (bias if bias is not None else torch.zeros(cout, device=x.device)).float().contiguous().view(torch.uint8)
+    blob = torch.zeros(b_off + bb.numel() + 256, dtype=torch.uint8, device=x.device)
+    blob[:wb.numel()] = wb
+    blob[b_off:b_off + bb.numel()] = bb.reshape(-1)
+    op = L.Op()
+    op.kind, op.engine = L.OP_CONV, L.ENGINE_TCGEN05
+    for v, (c, hh, ww, cp) in ((op.src, (cin, h, w, cin_p)), (op.dst, (cout, ho, wo, cout_p))):
+        v.offset, v.n, v.h, v.w, v.c, v.pitch, v.dtype, v.lo_delta = 0, n, hh, ww, c, 2 * cp, L.DT_F16X2, cp
+    rs = None
+    if residual is not None:
+        rs = _split_nhwc(residual, cout_p)
+        v = op.res
+        v.offset, v.n, v.h, v.w, v.c, v.pitch, v.dtype, v.lo_delta = (0, n, residual.shape[2], residual.shape[3], cout,
+                                                                      2 * cout_p, L.DT_F16X2, cout_p)
+    op.w_offset, op.b_offset = 0, b_off
+    op.r = op.s = k
+    op.stride, op.pad, op.kslab, op.slab_mode = stride, padding, kslab, mode
+    op.act = L.ACT_RELU if relu else L.ACT_NONE
+    op.out_binding = -1
+    L.check(lib.cpn_conv2d(ctypes.byref(op), L.ptr(xs), L.ptr(out), L.ptr(rs), L.ptr(blob), L.stream_ptr()), 'conv2d')
+    o = out[..., :cout].float() + out[..., cout_p:cout_p + cout].float()
+    return o.permute(0, 3, 1, 2).contiguous()

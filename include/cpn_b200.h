@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CPN_B200_ABI_VERSION 1
+#define CPN_B200_ABI_VERSION 2
 
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* status / diagnostics                                                                                             */
@@ -40,7 +40,14 @@ int cpn_device_info(char* name_host, int n, int* sm_count_host, int* cc_major_ho
 /* 686-700, i.e. the nn.Conv2d/BatchNorm2d/MaxPool2d/F.interpolate calls into cuDNN/ATen)                           */
 /* ---------------------------------------------------------------------------------------------------------------- */
 
-enum { CPN_DT_F32 = 0, CPN_DT_F16 = 1, CPN_DT_U8 = 2 };
+enum {
+  CPN_DT_F32 = 0,
+  CPN_DT_F16 = 1,
+  CPN_DT_U8 = 2,
+  CPN_DT_F16X2 = 3 /* split fp16 pair: value = hi + lo, hi = fp16(v), lo = fp16(v - hi); channel c of a view lives at
+                      element c (hi) and c + lo_delta (lo) of the pixel.  Used by the 3-pass tensor-core engine
+                      (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate) that reaches fp32-level accuracy. */
+};
 
 /* NHWC view into the activation arena: element (n,y,x,c) lives at
  *   arena + offset + ((n*h + y)*w + x) * pitch * sizeof(dtype) + c * sizeof(dtype).
@@ -51,6 +58,8 @@ typedef struct {
   int32_t n, h, w, c;
   int32_t pitch;
   int32_t dtype;  /* CPN_DT_* */
+  int32_t lo_delta; /* CPN_DT_F16X2: elements from a channel's hi half to its lo half (0 otherwise) */
+  int32_t reserved;
 } cpn_view_t;
 
 enum {
@@ -79,7 +88,8 @@ typedef struct {
                             residual is read through nearest up-sampling (torchvision FPN top-down path). */
   int64_t w_offset;      /* CONV/PROJ: bytes into the weight blob.
                             SIMT   : float  [R*S][kslab][cout]
-                            TCGEN05: __half [R*S][cout][kslab]   (K-major, TMA box {64, BN, 1})
+                            TCGEN05: __half [R*S][cout][kslab]   (K-major, TMA box {64, BN, 1}); for CPN_DT_F16X2
+                                     activations [R*S][cout][3*kslab] = (W_hi | W_hi | W_lo) along K
                             PROJ   : float  [cout][cin_slice]    */
   int64_t b_offset;      /* CONV/PROJ: bytes into the weight blob of float bias[cout] (-1 -> no bias) */
   int32_t r, s, stride, pad;

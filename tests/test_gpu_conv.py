@@ -39,3 +39,11 @@ def test_conv_tcgen05_matches_torch():
     for r in _run('tcgen05', TC_CASES):
         assert 'error' not in r, r
         assert r['rel_err'] < 2e-3 and not r['nan'], r          # fp16 operands, fp32 accumulate, fp16 store
+
+
+@pytest.mark.gpu
+def test_conv_tcgen05_split_fp16x3_matches_fp32():
+    """Three-pass split-fp16 engine: fp32-level accuracy on unrounded fp32 operands."""
+    for r in _run('tcgen05x3', TC_CASES):
+        assert 'error' not in r, r
+        assert r['rel_err'] < 2e-5 and not r['nan'], r

@@ -193,3 +193,23 @@ def test_full_size_c3_properties():
         assert e < 2e-2, (k, e)
     for cs, cf in zip(s['scores'], a['scores']):
         assert abs(len(cs) - len(cf)) <= max(2, 0.1 * len(cs))
+
+
+@pytest.mark.parametrize('name', MODEL_FIXTURES)
+def test_fp16x3_tensor_core_model_meets_parity_gate(name):
+    """Split-precision tensor-core engine (3 passes): the same gates as the strict fp32 engine -- head tensors within
+    1e-3 rel, identical instance counts, matched contour vertices within 0.5 px."""
+    z = load_npz(name)
+    m, (n, h, w) = _model(z, 'fp16x3')
+    x = torch.from_numpy(z['x']).cuda()
+    raw = m.core_forward(x)
+    errs = {k: rel_err(raw[k].cpu().numpy(), z['raw_' + k]) for k in ('scores', 'locations', 'refinement', 'fourier')}
+    _report(f'{name}/fp16x3/raw_rel_err', errs)
+    for k, e in errs.items():
+        assert e < 1e-3, (k, e)
+    kw = dict(offsets=torch.from_numpy(z['offsets']).cuda()) if 'offsets' in z.files else {}
+    out = m(x, **kw)
+    st = _compare_outputs(out, z, n)
+    _report(f'{name}/fp16x3/outputs', st)
+    assert st['count'] == st['ref_count'] == st['matched'], st
+    assert st['max_vertex_err'] < 0.5, st

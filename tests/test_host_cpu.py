@@ -42,8 +42,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     import ctypes
-    assert ctypes.sizeof(_lib.View) == 32
-    assert ctypes.sizeof(_lib.Op) == 8 + 3 * 32 + 16 + 4 * 4 + 8 * 4
+    assert ctypes.sizeof(_lib.View) == 40
+    assert ctypes.sizeof(_lib.Op) == 8 + 3 * 40 + 16 + 4 * 4 + 8 * 4
 
 
 def test_no_cpu_fallback():
