@@ -284,7 +284,7 @@ def run_b200(args):
     hms = e0.elapsed_time(e1) / reps
     hflops = 2. * BATCH * hop.dst.h * hop.dst.w * hop.dst.c * hop.src.c * hop.k * hop.k
     achieved = hflops / (hms / 1e3) / 1e12
-    if args.precision == 'fp16':
+    if args.precision in ('fp16', 'fp16x3'):
         traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
         ncu_json = os.path.join(ROOT, 'profiles', 'r01_ncu_heads_conv.json')
         if os.path.exists(ncu_json):
@@ -310,6 +310,28 @@ def run_b200(args):
     total_flops = conv_flops(plan.g)
     net_tflops = total_flops * args.steps / (ms / 1e3) / 1e12 * 1.0
 
+    # ---- the engine that meets north_star's 1e-3 tensor gate (3-pass split fp16), same workload, a few steps ----
+    parity_engine = None
+    if args.precision == 'fp16' and world == 1:
+        m3 = getattr(cd.models, ARCH)(3, precision='fp16x3')
+        m3.load_state_dict(sd)
+        m3.to(dev)
+        for i in range(2):
+            m3.forward_flat(xs[i % n_rot])
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(3):
+            f3, c3 = m3.forward_flat(xs[i % n_rot])
+        a1.record()
+        torch.cuda.synchronize()
+        ms3 = a0.elapsed_time(a1) / 3
+        parity_engine = dict(precision='fp16x3', value=BATCH / (ms3 / 1e3), unit='tiles/s', ms_per_step=ms3,
+                             kept_last_step=int(sum(c3)),
+                             note='activations and weights as fp16 (hi, lo) pairs, 3 tcgen05 passes per K block; head '
+                                  'tensors within 1e-3 of the reference (tests/test_gpu_model.py)')
+        del m3
+
     line = None
     if rank == 0:
         cpu = None
@@ -320,7 +342,7 @@ def run_b200(args):
                        sample=f'3 steps x 1 tile of 3x{TILE}x{TILE} (+1 warm-up), oracle/cpn_oracle.py torch-CPU fp32')
         line = dict(metric=METRIC, value=value, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                    dtype='f16' if args.precision == 'fp16' else 'f32', data='synthetic',
+                    dtype={'fp16': 'f16', 'fp16x3': 'f16x3', 'fp32': 'f32'}[args.precision], data='synthetic',
                     config=dict(workload=f'{ARCH} random-init (synthetic weights seed {SEED}, heads calibrated to '
                                          f'{FG_FRACTION:.0%} foreground), batch {BATCH}x3x{TILE}x{TILE} per GPU',
                                 global_batch=tiles, tile=TILE, parallelism=f'tile-parallel x{world}',
@@ -336,6 +358,8 @@ def run_b200(args):
                                  launches_per_step=launches / args.steps))
         if cpu is not None:
             line['cpu_baseline'] = cpu
+        if parity_engine is not None:
+            line['parity_engine'] = parity_engine
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -347,7 +371,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp16x3', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
