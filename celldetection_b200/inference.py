@@ -177,14 +177,24 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
             ev.record(copy_stream)
         return ids, d, ev
 
+    # Crops are staged by a helper thread (numpy slicing + the pinned copy release the GIL) while the main thread drives
+    # the GPU: model calls block on the proposal count, so same-thread staging would serialise with the GPU.
+    from concurrent.futures import ThreadPoolExecutor
     nb = (len(mine) + batch_size - 1) // batch_size
-    nxt = load(0, 0) if nb else None
+    pool = ThreadPoolExecutor(max_workers=1)
+    cur_dev = torch.cuda.current_device()
+
+    def load_in_thread(bi, slot):
+        torch.cuda.set_device(cur_dev)
+        return load(bi, slot)
+
+    nxt = pool.submit(load_in_thread, 0, 0) if nb else None
     for bi in range(nb):
-        ids, d, ev = nxt
+        ids, d, ev = nxt.result()
         main.wait_event(ev)
         if bi + 1 < nb:
             # the other staging slot was consumed two batches ago (its copy finished before the previous forward)
-            nxt = load(bi + 1, (bi + 1) % 2)
+            nxt = pool.submit(load_in_thread, bi + 1, (bi + 1) % 2)
         offs = torch.tensor([[slices[t][1].start, slices[t][0].start] for t in ids], dtype=torch.float32, device=dev)
         if is_u8:
             flat, counts = model.forward_flat(d, L.IN_U8_NHWC, offsets=offs)
@@ -212,6 +222,7 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
         tile_ids = torch.tensor(ids, dtype=torch.float32, device=dev)[tile_of_row.long()][sel]
         part['order_key'] = torch.stack((tile_ids, sel.to(torch.float32)), 1)   # (global tile index, row in batch)
         acc.append(part)
+    pool.shutdown(wait=True)
     if acc:
         res = OrderedDict((k, torch.cat([a[k] for a in acc], 0)) for k in acc[0].keys())
     else:
