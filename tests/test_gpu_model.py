@@ -216,3 +216,35 @@ def test_fp16x3_tensor_core_model_meets_parity_gate(name):
     assert sum(st['matched']) >= sum(st['ref_count']) - 1, st
     assert st['max_proposal_err'] < 0.5, st
     assert st['vertices_within_half_px'] >= 0.99 * st['vertices'], st
+
+
+@pytest.mark.parametrize('arch,hw', [('CpnResNeXt101UNet', (90, 120)), ('CpnU22', (90, 120)), ('CpnResNet18FPN', (72, 200))])
+def test_ragged_input_sizes_against_oracle(arch, hw):
+    """Sizes that are not multiples of the encoder stride: partial conv tiles, non-integer nearest up-sampling factors
+    (floor(dst * in / out)), odd max-pool extents, bilinear resize for the FPN refinement features.  Checked directly
+    against the oracle (CPU) for the strict and the split-precision engines."""
+    from helpers import key_spec
+    from celldetection_b200.utils.synth import synth_state_dict, calibrate_heads_
+    torch.manual_seed(7)
+    h, w = hw
+    x = torch.rand(2, 3, h, w)
+    sd = synth_state_dict(key_spec(arch), seed=11)
+
+    def core_fn(xx, sd_):
+        s, l, r, f = orc.cpn_core(xx, sd_, arch)
+        return dict(scores=s, locations=l, fourier=f, refinement=r)
+
+    with torch.no_grad():
+        calibrate_heads_(sd, core_fn, x[:1], fg_fraction=0.2, fourier_std=1.0, location_std=0.5)
+        s, l, r, f = orc.cpn_core(x, sd, arch)
+        want = orc.cpn_post(s, l, r, f, (h, w))
+    for prec, tol in (('fp32', 1e-3), ('fp16x3', 1e-3)):
+        m = getattr(cd.models, arch)(3, precision=prec)
+        m.load_state_dict(sd)
+        m = m.cuda()
+        raw = m.core_forward(x.cuda())
+        for k, ref in (('scores', s), ('locations', l), ('refinement', r), ('fourier', f)):
+            assert tuple(raw[k].shape) == tuple(ref.shape), (k, raw[k].shape, ref.shape)
+            assert rel_err(raw[k].cpu().numpy(), ref.numpy()) < tol, (prec, k)
+        out = m(x.cuda())
+        assert [len(v) for v in out['scores']] == [len(v) for v in want['scores']], prec
