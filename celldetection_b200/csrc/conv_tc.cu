@@ -1,22 +1,30 @@
-// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (fp16 x fp16 -> fp32 in TMEM), operands staged by
-// TMA (im2col-free: one 4-D box load per filter tap with out-of-bounds zero fill), mbarrier pipeline, persistent CTAs,
-// warp-specialised (1 TMA warp, 1 MMA warp, 8 epilogue warps), double-buffered TMEM accumulators.
+// Tensor-core implicit-GEMM convolutions for sm_100a: tcgen05.mma (fp16 x fp16 -> fp32 in TMEM), operands staged by
+// TMA, mbarrier pipelines, persistent warp-specialised CTAs, double-buffered TMEM accumulators.
 //
-// Replaces nn.Conv2d (+ folded BatchNorm2d) (+ residual) (+ ReLU) on the dense stages of the path:
-//   /root/reference/celldetection/models/commons.py:494-500 (ReadOut 7x7), :120-149 (TwoConvNormRelu 3x3),
+// Replaces nn.Conv2d (+ folded BatchNorm2d) (+ residual) (+ ReLU) (+ ReadOut's final 1x1 projection) on the path:
+//   /root/reference/celldetection/models/commons.py:494-511 (ReadOut 7x7 + 1x1), :120-149 (TwoConvNormRelu 3x3),
 //   models/resnet.py:88-116 (Bottleneck 1x1 / grouped 3x3 / 1x1, forward = torchvision), models/unet.py:121-128
-//   (1x1 "inner" convs), models/fpn.py:106-121 (lateral 1x1, output 3x3).
+//   (1x1 "inner" convs), models/fpn.py:106-121 (lateral 1x1, output 3x3), models/resnet.py:273 (7x7 s2 stem, as a 1x1
+//   over the im2col operand written by prep_im2col_kernel).
 //
 // GEMM view: D[m, n] = sum_{tap, c} A[pixel m shifted by tap, c] * Wt[tap][n][c]
-//   M tile  = 128 output pixels = a 16 (x) by 8 (y) patch of one image   (UMMA M = 128, cta_group::1)
-//   N tile  = BN output channels (64 / 128 / 256)                        (UMMA N = BN)
-//   K block = 64 input channels of one filter tap (= one 128-byte swizzle row; 4 x UMMA K = 16)
-// A operand: NHWC fp16 activations through a 4-D tensor map (C, W, H, N) with box {64, 16, 8, 1}, SWIZZLE_128B.
-//   The box lands in shared memory as 128 rows (x fastest, then y) of 128 bytes = the canonical K-major SW128 layout.
-//   Stride-2 convolutions read one of four parity views (base shifted by (py, px), strides doubled), so every tap is
-//   still a plain box load.  Zero padding is the TMA out-of-bounds fill.
-// B operand: weights pre-packed as fp16 [R*S][cout][kslab] (K-major) through a 3-D tensor map, box {64, BN, 1}.
+//   M = 128 output pixels per accumulator (UMMA M = 128, cta_group::1), N tile = BN in {64, 128, 256} output channels,
+//   K block = 64 input channels of one filter tap (one 128-byte swizzle row = 4 x UMMA K = 16).
+// Two kernels share the descriptors, the epilogue (epilogue_rows) and the host-side plan:
+//   conv_tc_kernel<BN>         any stride-1/2 convolution: per (tap, channel block) one TMA box {64ch, 16, 8, 1} of the
+//                              NHWC activations (out-of-bounds zero fill = padding; stride 2 via four parity views) and
+//                              one box {64, BN, 1} of the K-major weights, both SWIZZLE_128B, 4-8 stage ring.
+//   conv_halo_kernel<BN,MSUB>  stride-1 kxk: the input patch of a tile is loaded ONCE per channel block and every filter
+//                              tap is a UMMA descriptor on a shifted window of it (see the kernel's header).
+// Warp roles: TMA producer(s), MMA issuer(s), 8 epilogue warps (two per TMEM lane quadrant).  The MMA warp runs fully
+// converged and elects the issuing lane inside the asm (umma_f16_elect): with a single divergent thread ptxas moved every
+// descriptor through R2UR one MMA at a time and the tensor pipe idled 20 % (BN = 256) to 75 % (BN = 64) of the time.
+// fp32 accumulators never leave TMEM until the epilogue: bias (+ residual, optionally through nearest up-sampling)
+// (+ ReLU) -> fp16 NHWC store, or -> fused ReadOut projection (+ 3*tanh) -> fp32 head records.
+// Split-precision mode (CPN_DT_F16X2): three passes per K block, A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, outputs re-split.
 // Grouped convolutions use BN = 64 and contract only over their 64-channel block-diagonal slab (cpn_op_t::kslab).
+// Environment switches (experiments, see profiles/r01_summary.md): CPN_HALO=0, CPN_HALO_ALL=0, CPN_HALO_SW128=0,
+// CPN_HALO_BASEOFF=1, CPN_HALO_SWAP=1, CPN_ROTATE=1.
 #include "common.cuh"
 #include <cstdlib>
 #include <cstring>
@@ -528,14 +536,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------------------------------------
 // Halo kernel: stride-1 kxk convolutions with operand reuse across filter taps.
 //   tile      = 16 rows x (8 * MSUB) columns of output pixels: MSUB accumulators of M = 128 (8 x 16 pixels each)
-//   A operand = per 64-channel block ONE patch of (16+R-1) x (8*MSUB+S-1) input pixels, stored as 8 planes
-//               [16-byte channel chunk][y][x] (8 TMA box loads {8, PW, PH, 1}, no swizzle).  Tap (r, s) of sub-tile j is
-//               the no-swizzle K-major descriptor starting at pixel (r, s + 8j): rows (8 consecutive x) 16 bytes apart,
-//               8-row groups (next y) PW*16 bytes apart, K chunks one plane apart -- no re-load per tap, so L2->SM
-//               traffic drops from R*S to ~(1 + halo) input reads.
+//   A operand = per 64-channel block ONE patch of (16+R-1) x (8*MSUB+S-1) input pixels: one TMA box
+//               {64ch, PW, PH, 1} with SWIZZLE_128B, i.e. 128-byte pixel rows in (y, x) order.  Tap (r, s) of sub-tile j
+//               is a K-major SW128 descriptor that STARTS at pixel row (r, s + 8j) with the 8-row groups one patch row
+//               (PW * 128 B) apart.  The tensor core applies the 128-byte swizzle on absolute shared-memory address
+//               bits, so a start that is not 1024-byte aligned needs no base_offset (verified on hardware; a phase-
+//               corrected base_offset gives wrong results).  No re-load per tap: L2->SM activation traffic drops from
+//               R*S to ~(1 + halo) reads.  (CPN_HALO_SW128=0 selects the first working variant: 8 no-swizzle planes
+//               [16-byte channel chunk][y][x] with rows 16 B apart, LBO = one plane, SBO = PW*16.)
 //   B operand = weights of one (tap, channel block): BN x 64 halves, SWIZZLE_128B, shared by the MSUB sub-tiles.
 // Warps: 0 = B producer, 1 = MMA issuer (sub-tiles [0, MSUB/2) or all), 2 = A producer, 3 = second MMA issuer (MSUB = 2:
-// a 64-wide MMA occupies the tensor pipe for only 32 cycles, less than one thread needs to issue it), 4.. = epilogue.
+// a 64-wide MMA occupies the tensor pipe for only 32 cycles, less than one warp needs to issue it), 4..11 = epilogue.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TCH_THREADS = 128 + 32 * TC_EPI_WARPS;   // B producer, MMA issuer 0, A producer, MMA issuer 1, epilogue
 

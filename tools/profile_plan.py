@@ -74,3 +74,28 @@ for k, (ms, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 with open(os.path.join(ROOT, 'gpurun_out', f'plan_profile_{arch}_{N}x{H}_{prec}.json'), 'w') as f:
     json.dump(rows, f)
+
+# ---- whole-step breakdown: plan forward (one C call) vs post-head chain vs full forward_flat ----
+def timeit(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+import time
+t_plan = timeit(lambda: plan.forward(x, L.IN_F32_NCHW, outs))
+sc, lf, rf = outs
+t_post = timeit(lambda: m.post_flat(sc, lf, rf, (H, H)))
+t_full = timeit(lambda: m.forward_flat(x))
+t0 = time.perf_counter()
+for _ in range(5):
+    plan.forward(x, L.IN_F32_NCHW, outs)
+host_ms = (time.perf_counter() - t0) / 5 * 1e3
+torch.cuda.synchronize()
+print(f'# plan.forward {t_plan:.3f} ms (host-side enqueue {host_ms:.3f} ms), post_flat {t_post:.3f} ms, forward_flat {t_full:.3f} ms')
