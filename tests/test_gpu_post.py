@@ -210,3 +210,24 @@ def test_filter_contours_by_stitching_rule():
         assert torch.equal(want, got.cpu()) and 0 < int(want.sum()) < 300
         idx = cd.ops.cpn.filter_contours_by_stitching_rule(con.cuda(), (64, 64), torch.tensor(ov), offsets=off, indices=True)
         assert torch.equal(idx.cpu(), torch.where(want)[0])
+
+
+def test_all_foreground_image_triggers_the_50000_chunk_rule():
+    """Edge case of SURVEY appendix C.2: every pixel of a 256x256 head map is a proposal (P = 65 536 > NMS_BATCH_SIZE),
+    so batched_box_nmsi runs NMS per 50 000-chunk and then over the survivors (ops/cpn.py:213-224)."""
+    g = torch.Generator().manual_seed(5)
+    n, h, w, order, samples = 1, 256, 256, 2, 8
+    scores = torch.rand(n, 1, h, w, generator=g) * 4 + 3.0            # sigmoid > 0.95 everywhere
+    locations = torch.randn(n, 2, h, w, generator=g)
+    fourier = torch.randn(n, 4 * order, h, w, generator=g) * 2.0
+    refinement = torch.tanh(torch.randn(n, 2, 2 * h, 2 * w, generator=g)) * 3
+    want = orc.cpn_post(scores, locations, refinement, fourier, (2 * h, 2 * w), order=order, samples=samples)
+    m = cd.models.CPN('CpnU22', order=order, samples=samples).cuda()
+    locfou = torch.cat((locations, fourier), 1).permute(0, 2, 3, 1).contiguous().cuda()
+    got = m.post(scores[:, 0].contiguous().cuda(), locfou, refinement.permute(0, 2, 3, 1).contiguous().cuda(),
+                 (2 * h, 2 * w))
+    assert len(m.post(scores[:, 0].contiguous().cuda(), locfou, refinement.permute(0, 2, 3, 1).contiguous().cuda(),
+                      (2 * h, 2 * w), nms=False)['scores'][0]) == h * w
+    assert len(got['scores'][0]) == len(want['scores'][0]) > 100
+    assert np.abs(got['boxes'][0].cpu().numpy() - want['boxes'][0].numpy()).max() < 1e-3
+    assert np.abs(got['scores'][0].cpu().numpy() - want['scores'][0].numpy()).max() < 1e-6
