@@ -248,3 +248,36 @@ def test_ragged_input_sizes_against_oracle(arch, hw):
             assert rel_err(raw[k].cpu().numpy(), ref.numpy()) < tol, (prec, k)
         out = m(x.cuda())
         assert [len(v) for v in out['scores']] == [len(v) for v in want['scores']], prec
+
+
+def test_full_size_c3_tile_fp16x3_against_oracle():
+    """One full-size BASELINE tile (CpnResNeXt101UNet, 3x512x512) through the split-precision tensor-core engine against
+    the oracle on the CPU: north_star's tensor gate (1e-3 rel) and identical instance count after NMS."""
+    from helpers import key_spec
+    from celldetection_b200.utils.synth import synth_state_dict, calibrate_heads_
+    arch = 'CpnResNeXt101UNet'
+    torch.manual_seed(3)
+    torch.set_num_threads(max(1, min(32, (os.cpu_count() or 8) // 2)))
+    x = torch.rand(1, 3, 512, 512)
+    sd = synth_state_dict(key_spec(arch), seed=0)
+
+    def core_fn(xx, sd_):
+        s, l, r, f = orc.cpn_core(xx, sd_, arch)
+        return dict(scores=s, locations=l, fourier=f, refinement=r)
+
+    with torch.no_grad():
+        calibrate_heads_(sd, core_fn, x, fg_fraction=0.02, fourier_std=3.0, location_std=1.0)
+        s, l, r, f = orc.cpn_core(x, sd, arch)
+        want = orc.cpn_post(s, l, r, f, (512, 512))
+    m = getattr(cd.models, arch)(3, precision='fp16x3')
+    m.load_state_dict(sd)
+    m = m.cuda()
+    raw = m.core_forward(x.cuda())
+    errs = {k: rel_err(raw[k].cpu().numpy(), ref.numpy()) for k, ref in
+            (('scores', s), ('locations', l), ('refinement', r), ('fourier', f))}
+    _report('c3_512/fp16x3_vs_oracle_raw_rel_err', errs)
+    out = m(x.cuda())
+    _report('c3_512/fp16x3_counts', dict(oracle=len(want['scores'][0]), fp16x3=len(out['scores'][0])))
+    for k, e in errs.items():
+        assert e < 1e-3, (k, e)
+    assert len(out['scores'][0]) == len(want['scores'][0]) > 0
