@@ -10,13 +10,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcpn_b200.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # ---- enums (mirror include/cpn_b200.h) -------------------------------------------------------------------------------
 DT_F32, DT_F16, DT_U8, DT_F16X2 = 0, 1, 2, 3
 OP_PREP, OP_CONV, OP_MAXPOOL, OP_UPSAMPLE, OP_BILINEAR, OP_PROJ = range(6)
 IN_F32_NCHW, IN_U8_NCHW, IN_U8_NHWC = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_SCALED_TANH = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SCALED_TANH, ACT_SIGMOID = 0, 1, 2, 3
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
 
 
@@ -35,6 +35,13 @@ class Op(ctypes.Structure):
                 ('out_binding', ctypes.c_int32), ('fuse_next', ctypes.c_int32)]
 
 
+class SelectParams(ctypes.Structure):
+    """cpn_select_params_t"""
+    _fields_ = [('logits', ctypes.c_void_p), ('lower', ctypes.c_void_p), ('upper', ctypes.c_void_p),
+                ('uncertainty', ctypes.c_void_p), ('channels', ctypes.c_int32), ('use_certainty', ctypes.c_int32),
+                ('thresh', ctypes.c_float), ('certainty_limit', ctypes.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/cpn_b200.h declares
 _P, _I, _I64, _F, _SZ = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
 SYMBOLS = {
@@ -51,6 +58,11 @@ SYMBOLS = {
     'cpn_select_workspace_bytes': (_SZ, [_I64]),
     'cpn_select_count': (_I, [_P, _P, _P, _I64, _F, _P, _P, _P]),
     'cpn_select_write': (_I, [_P, _P, _P, _I, _I64, _F, _P, _P, _P, _I64, _P, _P]),
+    'cpn_select_count_ex': (_I, [ctypes.POINTER(SelectParams), _I64, _P, _P, _P]),
+    'cpn_select_write_ex': (_I, [ctypes.POINTER(SelectParams), _I, _I64, _P, _P, _P, _P, _I64, _P, _P]),
+    'cpn_nms_weights': (_I, [_P, _P, _P, _I64, _P, _P]),
+    'cpn_decode_refine_buckets': (_I, [_P, _I64, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P,
+                                       _P, _P, _P, _P]),
     'cpn_decode_refine': (_I, [_P, _I64, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
     'cpn_fouriers2contours': (_I, [_P, _P, _I64, _I, _I, _P, _P, _P, _P]),
     'cpn_nms_workspace_bytes': (_SZ, [_I64, _I]),
@@ -93,6 +105,11 @@ def check(rc, what=''):
 def ptr(t):
     """Device pointer of a tensor (or None)."""
     return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def addr(t):
+    """Device address of a tensor as a plain int (None -> NULL), for pointer fields of ctypes structures."""
+    return None if t is None else int(t.data_ptr())
 
 
 def stream_ptr():

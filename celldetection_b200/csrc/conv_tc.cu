@@ -37,7 +37,7 @@ constexpr int TC_BW = 16, TC_BH = 8, TC_BM = 128, TC_BK = 64;
 constexpr int TC_EPI_WARPS = 8;                        // two warps per TMEM lane quadrant, each takes every other chunk
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_SMEM_BUDGET = 196608;  // bytes of operand stages
-constexpr int TC_PROJ_SMEM_MAX = 24576; // fused projection weights (fp32)
+constexpr int TC_PROJ_SMEM_MAX = 32768; // fused projection weights (fp32): up to 4 heads x 8 outputs x 256 mid channels
 
 constexpr int TC_MAX_HEADS = 4;    // fused ReadOut projections: one per N tile
 constexpr int TC_PROJ_MAX = 24;    // max output channels of one fused projection
@@ -72,6 +72,7 @@ struct ConvTcParams {
   CUtensorMap tmH;          // (C, W, H, N), box {8, PW, PH, 1}, no swizzle
   int halo, pw, ph, plane_stride, nb_stages, swap_lbo_sbo;
   int halo_sw128, halo_baseoff;
+  int split_lofirst;                 // split mode: run the two correction passes before the main pass
   int split, a_lo, out_lo, res_lo;   // CPN_DT_F16X2: 3 passes per 64-channel block (A_hi W_hi, A_lo W_hi, A_hi W_lo);
                                      // element distance hi -> lo half in the A / output / residual buffers
   int rotate;               // start each CTA's K loop at a different (tap, block): de-correlates the L2 reads of the shared weights   // 1: the patch is ONE box {64, PW, PH, 1} with SWIZZLE_128B (128-byte pixel rows)
@@ -245,6 +246,13 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Split-precision (CPN_DT_F16X2) K order.  Pass ids: 0 = A_hi*W_hi, 1 = A_lo*W_hi, 2 = A_hi*W_lo.  The tensor core's fp32
+// accumulator truncates the aligned sum of every MMA step, an error of a fraction of ulp(|D|) per step that does not
+// average out.  Running the two correction passes FIRST, while |D| is still ~2^-11 of its final magnitude, leaves only
+// the K/16 steps of the main pass exposed (a third of the steps of an interleaved order).
+// (CPN_SPLIT_LOFIRST=0 restores the interleaved-era order hi, lo, lo for A/B measurements.)
+__device__ __forceinline__ int split_pass_order(int i, int lofirst) { return lofirst ? (i == 2 ? 0 : i + 1) : i; }
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Epilogue of one accumulator (128 rows x BN columns in TMEM at `taddr`): this thread owns output pixel (img, y, x).
 // Either the fused ReadOut projection (p.nproj > 0) or bias / residual / ReLU / fp16 store of every other 32-column
@@ -315,6 +323,7 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
           float r = pacc[j] + (H.b ? __ldg(H.b + j) : 0.f);
           if (H.act == CPN_ACT_SCALED_TANH) r = tanhf(r) * H.act_scale;
           else if (H.act == CPN_ACT_RELU) r = fmaxf(r, 0.f);
+          else if (H.act == CPN_ACT_SIGMOID) r = 1.f / (1.f + expf(-r));
           o[j] = r;
         }
       }
@@ -442,12 +451,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int cbase = p.slab_mode ? (n0 / p.kslab) * p.kslab : 0;
         int kk = p.rotate ? (int)(blockIdx.x % (unsigned)nk) : 0;   // rotated start of the K loop (sum order is free)
         for (int it = 0; it < nk; ++it) {
-          const int tap = kk / p.cblocks, cb = kk - tap * p.cblocks;   // cb runs over 3 * logical blocks when split
+          int tap = kk / p.cblocks, cb = kk - tap * p.cblocks;   // cb runs over 3 * logical blocks when split
           if (++kk == nk) kk = 0;
           int a_ch = cb * TC_BK;
           if (p.split) {
-            const int cbl = p.cblocks / 3, pass = cb / cbl;
-            a_ch = (cb - pass * cbl) * TC_BK + (pass == 1 ? p.a_lo : 0);
+            // pass-major K order, the two correction passes first (see split_pass_order)
+            const int cbl = p.cblocks / 3, per_pass = p.R * p.S * cbl;
+            const int kq = tap * p.cblocks + cb, pi = kq / per_pass, rem = kq - pi * per_pass;
+            const int pass = split_pass_order(pi, p.split_lofirst);
+            tap = rem / cbl;
+            const int c = rem - tap * cbl;
+            cb = pass * cbl + c;
+            a_ch = c * TC_BK + (pass == 1 ? p.a_lo : 0);
           }
           const int r = tap / p.S, s = tap - r * p.S;
           int qy = r - p.pad, qx = s - p.pad, map = 0;
@@ -614,12 +629,17 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n0 = (int)(tile % p.tiles_n) * BN;
         for (int cb = 0; cb < p.cblocks; ++cb) {
+          int cbw = cb;                                   // K block of the (W_hi | W_hi | W_lo) weight tensor
+          if (p.split) {
+            const int cbl = p.cblocks / 3, pi = cb / cbl;
+            cbw = split_pass_order(pi, p.split_lofirst) * cbl + (cb - pi * cbl);
+          }
           int tap = p.rotate ? (int)(blockIdx.x % (unsigned)taps) : 0;
           for (int it = 0; it < taps; ++it, tap = (tap + 1 == taps ? 0 : tap + 1)) {
             mbar_wait(smem_u32(&bar_bempty[sb]), phb ^ 1);
             const uint32_t full = smem_u32(&bar_bfull[sb]);
             mbar_expect_tx(full, B_BYTES);
-            tma_load_3d(smem_base + sb * B_BYTES, &p.tmB, full, cb * TC_BK, n0, tap);
+            tma_load_3d(smem_base + sb * B_BYTES, &p.tmB, full, cbw * TC_BK, n0, tap);
             if (++sb == nb) { sb = 0; phb ^= 1; }
           }
         }
@@ -640,8 +660,8 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
         for (int cb = 0; cb < p.cblocks; ++cb) {
           int a_ch = cb * TC_BK;
           if (p.split) {
-            const int cbl = p.cblocks / 3, pass = cb / cbl;
-            a_ch = (cb - pass * cbl) * TC_BK + (pass == 1 ? p.a_lo : 0);
+            const int cbl = p.cblocks / 3, pi = cb / cbl, pass = split_pass_order(pi, p.split_lofirst);
+            a_ch = (cb - pi * cbl) * TC_BK + (pass == 1 ? p.a_lo : 0);
           }
           mbar_wait(smem_u32(&bar_aempty[ab]), pha ^ 1);
           const uint32_t full = smem_u32(&bar_afull[ab]);
@@ -866,6 +886,9 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
     // make a tile's result depend on the batch it is computed in (the tests assert batch invariance bit for bit).
     if (rot_env < 0) { const char* e = getenv("CPN_ROTATE"); rot_env = (e && atoi(e) == 1) ? 1 : 0; }
     p.rotate = rot_env;
+    static int lofirst_env = -1;
+    if (lofirst_env < 0) { const char* e = getenv("CPN_SPLIT_LOFIRST"); lofirst_env = (e && atoi(e) == 0) ? 0 : 1; }
+    p.split_lofirst = lofirst_env;
   }
   p.tiles_x = (op.dst.w + TC_BW - 1) / TC_BW; p.tiles_y = (op.dst.h + TC_BH - 1) / TC_BH;
   p.tiles_n = op.dst.c / bn;

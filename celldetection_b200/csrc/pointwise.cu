@@ -539,6 +539,7 @@ __global__ void __launch_bounds__(256) proj_kernel(const T* __restrict__ src, fl
       float v = mine + (bias ? bias[lane] : 0.f);
       if (act == CPN_ACT_SCALED_TANH) v = tanhf(v) * act_scale;
       else if (act == CPN_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (act == CPN_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
       dst[pix * dp + lane] = v;
     }
   }

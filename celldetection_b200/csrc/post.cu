@@ -19,25 +19,66 @@ namespace cpn {
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int SEL_THREADS = 256, SEL_PER_THREAD = 4, SEL_CHUNK = SEL_THREADS * SEL_PER_THREAD;
 
-__device__ __forceinline__ float score_of(const float* __restrict__ logits, const float* __restrict__ lower,
-                                          const float* __restrict__ upper, long long i) {
-  float s = 1.f / (1.f + expf(-logits[i]));  // torch.sigmoid
-  if (upper) s = fminf(s, upper[i]);         // cpn.py:118-123 (upper first, then lower)
-  if (lower) s = fmaxf(s, lower[i]);
-  return s;
+// Device copy of cpn_select_params_t (pointers are device pointers already).
+struct SelParams {
+  const float* logits;
+  const float* lower;
+  const float* upper;
+  const float* unc;
+  int channels, use_certainty;
+  float thresh, certainty_limit;
+};
+
+constexpr int SEL_MAX_CLASSES = 32;
+
+// Score, class and foreground decision of pixel i for every scoring variant (models/cpn.py:575-587, 616-618).
+__device__ __forceinline__ bool eval_pixel(const SelParams& p, long long i, float& score, int& cls) {
+  bool fg;
+  if (p.channels == 1) {
+    float s = 1.f / (1.f + expf(-p.logits[i]));  // torch.sigmoid
+    if (p.upper) s = fminf(s, p.upper[i]);       // cpn.py:118-123 (upper first, then lower)
+    if (p.lower) s = fmaxf(s, p.lower[i]);
+    score = s;
+    fg = s > p.thresh;
+    cls = fg ? 1 : 0;
+  } else {
+    // F.softmax(scores, dim=1): exp(x - max) / sum; bounds broadcast over the channels; argmax = first maximum
+    const float* l = p.logits + i * p.channels;
+    float m = l[0];
+    for (int c = 1; c < p.channels; ++c) m = fmaxf(m, l[c]);
+    float sum = 0.f;
+    for (int c = 0; c < p.channels; ++c) sum = sum + expf(l[c] - m);
+    float best = -INFINITY;
+    int arg = 0;
+    for (int c = 0; c < p.channels; ++c) {
+      float s = expf(l[c] - m) / sum;
+      if (p.upper) s = fminf(s, p.upper[i]);
+      if (p.lower) s = fmaxf(s, p.lower[i]);
+      if (s > best) { best = s; arg = c; }
+    }
+    score = best;
+    cls = arg;
+    fg = arg > 0;
+  }
+  if (fg && p.use_certainty) {  // fg_mask &= uncertainty.mean(1) < (1 - certainty_thresh)   (cpn.py:617-618)
+    const float4 u = *reinterpret_cast<const float4*>(p.unc + i * 4);
+    const float mean = (((u.x + u.y) + u.z) + u.w) / 4.f;
+    fg = mean < p.certainty_limit;
+  }
+  return fg;
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) select_count_kernel(const float* __restrict__ logits,
-                                                                   const float* __restrict__ lower,
-                                                                   const float* __restrict__ upper, long long pixels,
-                                                                   float thresh, int* __restrict__ block_counts) {
+__global__ void __launch_bounds__(SEL_THREADS) select_count_kernel(const SelParams p, long long pixels,
+                                                                   int* __restrict__ block_counts) {
   __shared__ int warp_sums[SEL_THREADS / 32];
   const long long base = (long long)blockIdx.x * SEL_CHUNK + threadIdx.x * SEL_PER_THREAD;
   int cnt = 0;
 #pragma unroll
   for (int j = 0; j < SEL_PER_THREAD; ++j) {
     const long long i = base + j;
-    if (i < pixels) cnt += score_of(logits, lower, upper, i) > thresh ? 1 : 0;
+    float sc;
+    int cl;
+    if (i < pixels) cnt += eval_pixel(p, i, sc, cl) ? 1 : 0;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -93,27 +134,24 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(const int* __restrict
   }
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) select_write_kernel(const float* __restrict__ logits,
-                                                                   const float* __restrict__ lower,
-                                                                   const float* __restrict__ upper, long long pixels,
-                                                                   float thresh,
+__global__ void __launch_bounds__(SEL_THREADS) select_write_kernel(const SelParams p, long long pixels,
                                                                    const long long* __restrict__ block_offsets,
                                                                    int32_t* __restrict__ idx, float* __restrict__ score,
+                                                                   long long* __restrict__ classes,
                                                                    long long capacity) {
   __shared__ int warp_sums[SEL_THREADS / 32];
   const long long base = (long long)blockIdx.x * SEL_CHUNK + threadIdx.x * SEL_PER_THREAD;
   float sc[SEL_PER_THREAD];
+  int cl[SEL_PER_THREAD];
   bool fg[SEL_PER_THREAD];
   int cnt = 0;
 #pragma unroll
   for (int j = 0; j < SEL_PER_THREAD; ++j) {
     const long long i = base + j;
     sc[j] = 0.f;
+    cl[j] = 0;
     fg[j] = false;
-    if (i < pixels) {
-      sc[j] = score_of(logits, lower, upper, i);
-      fg[j] = sc[j] > thresh;
-    }
+    if (i < pixels) fg[j] = eval_pixel(p, i, sc[j], cl[j]);
     cnt += fg[j] ? 1 : 0;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -134,6 +172,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_write_kernel(const float* 
       if (pos < capacity) {
         idx[pos] = (int32_t)(base + j);
         score[pos] = sc[j];
+        if (classes) classes[pos] = cl[j];
       }
       ++pos;
     }
@@ -173,34 +212,83 @@ static inline void select_ws(void* ws, int64_t pixels, int** counts, long long**
   *offsets = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + ((nblocks * 4 + 15) / 16) * 16);
 }
 
-extern "C" int cpn_select_count(const float* logits, const float* lower, const float* upper, int64_t pixels,
-                                float thresh, void* workspace, int64_t* total_dev, void* stream) {
+static int make_sel(const cpn_select_params_t* q, SelParams* p) {
+  CPN_REQUIRE(q != nullptr && q->logits != nullptr, "select: logits required");
+  CPN_REQUIRE(q->channels == 1 || (q->channels > 2 && q->channels <= SEL_MAX_CLASSES),
+              "select: score channels %d unsupported (1 or 3..%d)", q->channels, SEL_MAX_CLASSES);
+  CPN_REQUIRE(!q->use_certainty || q->uncertainty != nullptr, "select: certainty filter without uncertainty map");
+  CPN_REQUIRE(q->uncertainty == nullptr || ((uintptr_t)q->uncertainty % 16) == 0, "select: uncertainty must be 16-byte aligned");
+  p->logits = q->logits; p->lower = q->lower; p->upper = q->upper; p->unc = q->uncertainty;
+  p->channels = q->channels; p->use_certainty = q->use_certainty; p->thresh = q->thresh;
+  p->certainty_limit = q->certainty_limit;
+  return 0;
+}
+
+extern "C" int cpn_select_count_ex(const cpn_select_params_t* params, int64_t pixels, void* workspace,
+                                   int64_t* total_dev, void* stream) {
   CPN_REQUIRE(pixels > 0 && pixels < (1ll << 31), "select: pixels %lld out of range", (long long)pixels);
+  SelParams p;
+  if (make_sel(params, &p)) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   int* counts; long long* offsets;
   select_ws(workspace, pixels, &counts, &offsets);
   const int nblocks = (int)((pixels + SEL_CHUNK - 1) / SEL_CHUNK);
-  select_count_kernel<<<nblocks, SEL_THREADS, 0, st>>>(logits, lower, upper, pixels, thresh, counts);
+  select_count_kernel<<<nblocks, SEL_THREADS, 0, st>>>(p, pixels, counts);
   CPN_CHECK_LAUNCH();
   select_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, offsets, reinterpret_cast<long long*>(total_dev));
   CPN_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int cpn_select_write(const float* logits, const float* lower, const float* upper, int n_images, int64_t hw,
-                                float thresh, void* workspace, int32_t* idx, float* score, int64_t capacity,
-                                int32_t* seg_offsets, void* stream) {
+extern "C" int cpn_select_write_ex(const cpn_select_params_t* params, int n_images, int64_t hw, void* workspace,
+                                   int32_t* idx, float* score, int64_t* classes, int64_t capacity,
+                                   int32_t* seg_offsets, void* stream) {
   const int64_t pixels = (int64_t)n_images * hw;
   CPN_REQUIRE(pixels > 0 && pixels < (1ll << 31), "select: pixels %lld out of range", (long long)pixels);
+  SelParams p;
+  if (make_sel(params, &p)) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   int* counts; long long* offsets;
   select_ws(workspace, pixels, &counts, &offsets);
   const int nblocks = (int)((pixels + SEL_CHUNK - 1) / SEL_CHUNK);
-  select_write_kernel<<<nblocks, SEL_THREADS, 0, st>>>(logits, lower, upper, pixels, thresh, offsets, idx, score,
-                                                       capacity);
+  select_write_kernel<<<nblocks, SEL_THREADS, 0, st>>>(p, pixels, offsets, idx, score,
+                                                       reinterpret_cast<long long*>(classes), capacity);
   CPN_CHECK_LAUNCH();
   select_segments_kernel<<<(n_images + 1 + 127) / 128, 128, 0, st>>>(idx, offsets + nblocks, capacity, n_images, hw,
                                                                      seg_offsets);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cpn_select_count(const float* logits, const float* lower, const float* upper, int64_t pixels,
+                                float thresh, void* workspace, int64_t* total_dev, void* stream) {
+  cpn_select_params_t q = {logits, lower, upper, nullptr, 1, 0, thresh, 0.f};
+  return cpn_select_count_ex(&q, pixels, workspace, total_dev, stream);
+}
+
+extern "C" int cpn_select_write(const float* logits, const float* lower, const float* upper, int n_images, int64_t hw,
+                                float thresh, void* workspace, int32_t* idx, float* score, int64_t capacity,
+                                int32_t* seg_offsets, void* stream) {
+  cpn_select_params_t q = {logits, lower, upper, nullptr, 1, 0, thresh, 0.f};
+  return cpn_select_write_ex(&q, n_images, hw, workspace, idx, score, nullptr, capacity, seg_offsets, stream);
+}
+
+namespace cpn {
+__global__ void nms_weights_kernel(const float* __restrict__ scores, const float* __restrict__ unc,
+                                   const int32_t* __restrict__ idx, long long P, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float4 u = *reinterpret_cast<const float4*>(unc + (long long)idx[i] * 4);
+  const float mean = (((u.x + u.y) + u.z) + u.w) / 4.f;
+  out[i] = scores[i] * (1.f - mean);   // s * (1. - u.mean(1))   (models/cpn.py:724)
+}
+}  // namespace cpn
+
+extern "C" int cpn_nms_weights(const float* scores, const float* uncertainty, const int32_t* idx, int64_t P, float* out,
+                               void* stream) {
+  if (P <= 0) return 0;
+  CPN_REQUIRE(scores && uncertainty && idx && out, "nms_weights: null pointer");
+  cpn::nms_weights_kernel<<<(int)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(scores, uncertainty, idx, P, out);
   CPN_CHECK_LAUNCH();
   return 0;
 }
@@ -224,6 +312,9 @@ struct DecodeParams {
   const float* offsets;
   float *contours, *proposals, *boxes, *locations, *fourier_out;
   int trig_in_smem;
+  int buckets;                  // refinement_buckets (1: plain [N,H,W,2] map)
+  const int32_t* bucket_idx;    // [samples][3]
+  const float* bucket_w;        // [samples][3]
 };
 
 __global__ void __launch_bounds__(DEC_WARPS * 32) decode_refine_kernel(const DecodeParams p) {
@@ -284,7 +375,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_refine_kernel(const Dec
         if (p.offsets) { qx = qx + ox; qy = qy + oy; }
         reinterpret_cast<float2*>(p.proposals)[pr * p.samples + s] = make_float2(qx, qy);
       }
-      if (p.refinement && p.iters > 0) {  // models/cpn.py:63-85
+      if (p.refinement && p.iters > 0 && p.buckets == 1) {  // models/cpn.py:63-85
         const float2* ref = reinterpret_cast<const float2*>(p.refinement) + (long long)b * p.H * p.W;
         for (int it = 0; it < p.iters; ++it) {
           float rx = rintf(cx), ry = rintf(cy);  // torch.round: half to even
@@ -293,6 +384,23 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_refine_kernel(const Dec
           const float2 d = __ldg(ref + (long long)((int)ry) * p.W + (int)rx);
           cx = rx + d.x;
           cy = ry + d.y;
+        }
+      } else if (p.refinement && p.iters > 0) {
+        // bucketed refinement (models/cpn.py:73-82): three neighbouring buckets of this sample, weights from the host
+        // table (resolve_refinement_buckets); summed in the reference's order a, b, c with un-fused multiply/add
+        const float2* ref = reinterpret_cast<const float2*>(p.refinement) + (long long)b * p.H * p.W * p.buckets;
+        const int b0 = p.bucket_idx[s * 3], b1 = p.bucket_idx[s * 3 + 1], b2 = p.bucket_idx[s * 3 + 2];
+        const float w0 = p.bucket_w[s * 3], w1 = p.bucket_w[s * 3 + 1], w2 = p.bucket_w[s * 3 + 2];
+        for (int it = 0; it < p.iters; ++it) {
+          float rx = rintf(cx), ry = rintf(cy);
+          rx = fminf(fmaxf(rx, 0.f), xmax);
+          ry = fminf(fmaxf(ry, 0.f), ymax);
+          const float2* px_ref = ref + ((long long)((int)ry) * p.W + (int)rx) * p.buckets;
+          const float2 d0 = __ldg(px_ref + b0), d1 = __ldg(px_ref + b1), d2 = __ldg(px_ref + b2);
+          const float dx = (d0.x * w0 + d1.x * w1) + d2.x * w2;
+          const float dy = (d0.y * w0 + d1.y * w1) + d2.y * w2;
+          cx = rx + dx;
+          cy = ry + dy;
         }
       }
       cx = fminf(fmaxf(cx, 0.f), xmax);  // cpn.py:661-663
@@ -614,6 +722,20 @@ extern "C" int cpn_decode_refine(const int32_t* idx, int64_t P, const float* loc
                                  int n_images, int h, int w, int H, int W, const float* trig, int samples,
                                  const float* refinement, int iters, const float* offsets, float* contours,
                                  float* proposals, float* boxes, float* locations, float* fourier_out, void* stream) {
+  return cpn_decode_refine_buckets(idx, P, locfou, order_core, order, n_images, h, w, H, W, trig, samples, refinement,
+                                   iters, 1, nullptr, nullptr, offsets, contours, proposals, boxes, locations,
+                                   fourier_out, stream);
+}
+
+extern "C" int cpn_decode_refine_buckets(const int32_t* idx, int64_t P, const float* locfou, int order_core, int order,
+                                         int n_images, int h, int w, int H, int W, const float* trig, int samples,
+                                         const float* refinement, int iters, int buckets, const int32_t* bucket_idx,
+                                         const float* bucket_w, const float* offsets, float* contours,
+                                         float* proposals, float* boxes, float* locations, float* fourier_out,
+                                         void* stream) {
+  CPN_REQUIRE(buckets >= 1, "decode: refinement buckets must be >= 1");
+  CPN_REQUIRE(buckets == 1 || refinement == nullptr || iters <= 0 || (bucket_idx != nullptr && bucket_w != nullptr),
+              "decode: bucketed refinement needs the bucket tables");
   CPN_REQUIRE(order >= 1 && order <= DEC_MAX_ORDER && order <= order_core, "decode: order %d out of range (core %d)",
               order, order_core);
   CPN_REQUIRE(samples >= 1, "decode: samples must be >= 1");
@@ -623,6 +745,7 @@ extern "C" int cpn_decode_refine(const int32_t* idx, int64_t P, const float* loc
   p.h = h; p.w = w; p.H = H; p.W = W; p.trig = trig; p.samples = samples; p.refinement = refinement; p.iters = iters;
   p.offsets = offsets; p.contours = contours; p.proposals = proposals; p.boxes = boxes; p.locations = locations;
   p.fourier_out = fourier_out;
+  p.buckets = buckets; p.bucket_idx = bucket_idx; p.bucket_w = bucket_w;
   const size_t trig_bytes = (size_t)2 * order * samples * sizeof(float);
   const size_t rec_bytes = (size_t)DEC_WARPS * (2 + 4 * DEC_MAX_ORDER) * sizeof(float);
   p.trig_in_smem = trig_bytes + rec_bytes <= 48 * 1024;

@@ -2,10 +2,11 @@
 
 Mirrors the public surface of /root/reference/celldetection/models/cpn.py (``CPN`` :287, ``CpnU22`` :772,
 ``CpnResNeXt101UNet`` :930, ``CpnResNet18FPN`` :1250): constructor arguments, mutable attributes read on every call
-(``order, nms_thresh, samples, score_thresh, refinement_iterations``, :368-380), ``nn.Module`` semantics with the
-reference's ``state_dict`` key layout, and ``model(inputs, targets=None, nms=True, **kwargs) -> OrderedDict`` of
-per-image lists (:710-734).  Training (``compute_loss``), the uncertainty head, ``classes > 2`` and
-``refinement_buckets > 1`` are outside the accelerated path and raise ``NotImplementedError``.
+(``order, nms_thresh, samples, score_thresh, refinement_iterations, certainty_thresh, uncertainty_nms``, :368-380),
+``nn.Module`` semantics with the reference's ``state_dict`` key layout, and ``model(inputs, targets=None, nms=True,
+**kwargs) -> OrderedDict`` of per-image lists (:710-734).  The inference variants are covered: ``classes > 2``
+(softmax / argmax scoring, :583-585), ``uncertainty_head`` with ``certainty_thresh`` / ``uncertainty_nms`` (:617-618,
+:723-726) and ``refinement_buckets > 1`` (:73-82).  Training (``compute_loss``) raises ``NotImplementedError``.
 
 Nothing here computes on the CPU or with PyTorch operators: modules only *hold* parameters; ``forward`` lowers to
 ``cpn_plan_forward`` + the post-head C entry points.  PyTorch supplies device memory, the stream and list plumbing.
@@ -47,7 +48,8 @@ class CPN(nn.Module):
     def __init__(self, backbone: str, in_channels: int = 3, order: int = 5, nms_thresh: float = .2,
                  score_thresh: float = .9, certainty_thresh: float = None, samples: int = 32, classes: int = 2,
                  refinement: bool = True, refinement_iterations: int = 4, refinement_margin: float = 3.,
-                 refinement_buckets: int = 1, uncertainty_head=False, precision: str = 'fp16', **kwargs):
+                 refinement_buckets: int = 1, uncertainty_head=False, uncertainty_nms=False,
+                 precision: str = 'fp16', **kwargs):
         """Contour Proposal Network (inference).
 
         Args:
@@ -63,12 +65,10 @@ class CPN(nn.Module):
         super().__init__()
         if backbone not in ARCHS:
             raise ValueError(f'Unknown backbone/architecture {backbone!r}; available: {ARCHS}')
-        if classes not in (1, 2):
-            raise NotImplementedError('classes > 2 (softmax/argmax scoring) is outside the accelerated path.')
-        if refinement_buckets != 1:
-            raise NotImplementedError('refinement_buckets > 1 is outside the accelerated path.')
-        if uncertainty_head:
-            raise NotImplementedError('uncertainty_head is outside the accelerated path.')
+        if classes < 1 or classes > 32:
+            raise ValueError('classes must be in [1, 32]')
+        if refinement_buckets < 1 or refinement_buckets > 12:
+            raise ValueError('refinement_buckets must be in [1, 12]')
         if precision not in PRECISIONS:
             raise ValueError(f'precision must be one of {PRECISIONS}')
         self.arch = backbone
@@ -78,19 +78,23 @@ class CPN(nn.Module):
         self.nms_thresh = nms_thresh
         self.samples = samples
         self.score_thresh = score_thresh
-        self.score_channels = 1
+        self.score_channels = 1 if classes in (1, 2) else classes          # models/cpn.py:372
         self.refinement = refinement
         self.refinement_iterations = refinement_iterations
         self.refinement_margin = refinement_margin
+        self.refinement_buckets = int(refinement_buckets)
+        self.uncertainty_head = bool(uncertainty_head)
         self.certainty_thresh = certainty_thresh
-        self.uncertainty_nms = False
+        self.uncertainty_nms = uncertainty_nms
         self.precision = precision
         self.hparams = dict(in_channels=in_channels, order=order, nms_thresh=nms_thresh, score_thresh=score_thresh,
                             samples=samples, classes=classes, refinement=refinement,
                             refinement_iterations=refinement_iterations, refinement_margin=refinement_margin,
-                            refinement_buckets=refinement_buckets, **kwargs)
+                            refinement_buckets=refinement_buckets, uncertainty_head=uncertainty_head,
+                            uncertainty_nms=uncertainty_nms, certainty_thresh=certainty_thresh, **kwargs)
         # ---- parameters / buffers with the reference's state_dict keys ----
-        g = trace(backbone, 1, 64, 64, in_channels=in_channels, order=order, refinement_margin=refinement_margin)
+        g = trace(backbone, 1, 64, 64, in_channels=in_channels, order=order, refinement_margin=refinement_margin,
+                  **self._variant())
         self._spec = g.spec
         gen = torch.Generator().manual_seed(torch.initial_seed() & 0x7fffffff)
         for key, (shape, role) in g.spec.items():
@@ -132,6 +136,10 @@ class CPN(nn.Module):
         self._plans = {}
         self._ws = {}
 
+    def _variant(self):
+        return dict(score_channels=self.score_channels, refinement_buckets=self.refinement_buckets,
+                    uncertainty_head=self.uncertainty_head)
+
     # ---- plan management ------------------------------------------------------------------------------------------
     def invalidate_plans(self):
         """Drop packed weights / compiled plans (call after modifying parameters in place)."""
@@ -165,7 +173,7 @@ class CPN(nn.Module):
         plan = self._plans.get(key)
         if plan is None:
             g = trace(self.arch, n, h, w, in_channels=self.in_channels, order=self.core_order,
-                      refinement_margin=self.refinement_margin, stem_im2col=fast)
+                      refinement_margin=self.refinement_margin, stem_im2col=fast, **self._variant())
             pack = self._packs.get(self.precision)
             if pack is None:
                 with torch.no_grad():
@@ -179,22 +187,29 @@ class CPN(nn.Module):
 
     # ---- raw head tensors (debug / parity) ------------------------------------------------------------------------
     def core_forward(self, inputs: Tensor):
-        """Raw head tensors in the reference's layout: scores [N,1,h,w], locations [N,2,h,w], refinement [N,2,H,W],
-        fourier [N,4*order,h,w] (CPNCore.forward, models/cpn.py:238-283)."""
-        plan, (sc, lf, rf), _ = self._run_plan(inputs)
+        """Raw head tensors in the reference's layout: scores [N,C,h,w], locations [N,2,h,w], refinement [N,2B,H,W],
+        fourier [N,4*order,h,w] (+ uncertainty [N,4,h,w] with an uncertainty head) (CPNCore.forward, cpn.py:238-283)."""
+        plan, outs, _ = self._run_plan(inputs)
+        sc, lf, rf = outs[:3]
         if int(plan.flags[0].item()) & 1:
             raise AssertionError('Inputs should be in interval (0.0, 1.0)')
-        return OrderedDict(scores=sc[:, None], locations=lf[..., :2].permute(0, 3, 1, 2),
-                           refinement=rf.permute(0, 3, 1, 2), fourier=lf[..., 2:].permute(0, 3, 1, 2))
+        out = OrderedDict(scores=sc[:, None] if sc.dim() == 3 else sc.permute(0, 3, 1, 2),
+                          locations=lf[..., :2].permute(0, 3, 1, 2), refinement=rf.permute(0, 3, 1, 2),
+                          fourier=lf[..., 2:].permute(0, 3, 1, 2))
+        if len(outs) > 3:                      # key present only for models with an uncertainty head
+            out['uncertainty'] = outs[3].permute(0, 3, 1, 2)
+        return out
 
     # ---- post-head chain on head tensors --------------------------------------------------------------------------
     def post_flat(self, scores: Tensor, locfou: Tensor, refinement: Tensor, original_size, nms=True, offsets=None,
-                  scores_lower_bound=None, scores_upper_bound=None, flags: Tensor = None):
-        """models/cpn.py:575-734 on device tensors: scores [N,h,w] logits, locfou [N,h,w,2+4*order_core] records,
-        refinement [N,H,W,2] (or None).  Returns (flat dict of concatenated tensors, rows per image)."""
+                  scores_lower_bound=None, scores_upper_bound=None, flags: Tensor = None, uncertainty: Tensor = None):
+        """models/cpn.py:575-734 on device tensors: scores [N,h,w] logits ([N,h,w,C] for classes > 2), locfou
+        [N,h,w,2+4*order_core] records, refinement [N,H,W,2*buckets] (or None), uncertainty [N,h,w,4] (or None).
+        Returns (flat dict of concatenated tensors, rows per image)."""
         lib = L.load()
         dev = scores.device
-        n, h, w = scores.shape
+        n, h, w = scores.shape[:3]
+        channels = 1 if scores.dim() == 3 else int(scores.shape[3])
         H, W = original_size
         order = min(int(self.order), int(self.core_order))
         samples = int(self.samples)
@@ -219,9 +234,11 @@ class CPN(nn.Module):
             ws = torch.empty((int(lib.cpn_select_workspace_bytes(pixels)),), dtype=torch.uint8, device=dev)
             self._ws = {ws_key: ws}
         meta = torch.zeros((2,), dtype=torch.int64, device=dev)
-        thr = float(self.score_thresh)
-        L.check(lib.cpn_select_count(L.ptr(scores), L.ptr(lo), L.ptr(up), pixels, thr, L.ptr(ws), L.ptr(meta), st),
-                'select_count')
+        use_cert = self.certainty_thresh is not None and uncertainty is not None          # cpn.py:617-618
+        sel = L.SelectParams(L.addr(scores), L.addr(lo), L.addr(up), L.addr(uncertainty), channels, int(use_cert),
+                             float(self.score_thresh),
+                             float(torch.tensor(1 - self.certainty_thresh, dtype=torch.float32)) if use_cert else 0.)
+        L.check(lib.cpn_select_count_ex(sel, pixels, L.ptr(ws), L.ptr(meta), st), 'select_count')
         if flags is not None:
             meta[1:2].copy_(flags[:1].to(torch.int64))
         total, flag = meta.tolist()                       # host sync #1 (the reference syncs at torch.where)
@@ -230,41 +247,53 @@ class CPN(nn.Module):
         P = int(total)
         idx = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
         sel_scores = torch.empty((max(P, 1),), dtype=torch.float32, device=dev)
+        classes = torch.empty((max(P, 1),), dtype=torch.long, device=dev)
         seg = torch.zeros((n + 1,), dtype=torch.int32, device=dev)
-        L.check(lib.cpn_select_write(L.ptr(scores), L.ptr(lo), L.ptr(up), n, h * w, thr, L.ptr(ws), L.ptr(idx),
-                                     L.ptr(sel_scores), max(P, 1), L.ptr(seg), st), 'select_write')
+        L.check(lib.cpn_select_write_ex(sel, n, h * w, L.ptr(ws), L.ptr(idx), L.ptr(sel_scores), L.ptr(classes),
+                                        max(P, 1), L.ptr(seg), st), 'select_write')
         contours = torch.empty((P, samples, 2), dtype=torch.float32, device=dev)
         proposals = torch.empty((P, samples, 2), dtype=torch.float32, device=dev)
         boxes = torch.empty((P, 4), dtype=torch.float32, device=dev)
         locations = torch.empty((P, 2), dtype=torch.float32, device=dev)
         fourier = torch.empty((P, order, 4), dtype=torch.float32, device=dev)
         use_ref = bool(self.refinement) and refinement is not None and int(self.refinement_iterations) > 0
+        buckets = int(refinement.shape[-1]) // 2 if refinement is not None else 1
         off = None
         if offsets is not None:
             off = torch.as_tensor(offsets).to(device=dev, dtype=torch.float32).reshape(n, 2).contiguous()
         if P > 0:
             trig = O.trig_table(order, samples, dev)
-            L.check(lib.cpn_decode_refine(L.ptr(idx), P, L.ptr(locfou), int(self.core_order), order, n, h, w, H, W,
-                                          L.ptr(trig), samples, L.ptr(refinement) if use_ref else None,
-                                          int(self.refinement_iterations) if use_ref else 0, L.ptr(off),
-                                          L.ptr(contours), L.ptr(proposals), L.ptr(boxes), L.ptr(locations),
-                                          L.ptr(fourier), st), 'decode_refine')
-        sel_scores = sel_scores[:P]
-        classes = torch.ones((P,), dtype=torch.long, device=dev)   # (scores > thresh).long() at selected pixels
+            bidx, bw = O.bucket_table(samples, buckets, dev) if (use_ref and buckets > 1) else (None, None)
+            L.check(lib.cpn_decode_refine_buckets(
+                L.ptr(idx), P, L.ptr(locfou), int(self.core_order), order, n, h, w, H, W, L.ptr(trig), samples,
+                L.ptr(refinement) if use_ref else None, int(self.refinement_iterations) if use_ref else 0, buckets,
+                L.ptr(bidx), L.ptr(bw), L.ptr(off), L.ptr(contours), L.ptr(proposals), L.ptr(boxes), L.ptr(locations),
+                L.ptr(fourier), st), 'decode_refine')
+        idx, sel_scores, classes = idx[:P], sel_scores[:P], classes[:P]
         flat = OrderedDict(contours=contours, boxes=boxes, scores=sel_scores, classes=classes, locations=locations,
                            fourier=fourier, contour_proposals=proposals)
+        if uncertainty is not None:                       # selected_uncertainties = uncertainty[b, :, y, x]
+            unc_rows = torch.empty((P, 4), dtype=torch.float32, device=dev)
+            if P > 0:
+                L.check(lib.cpn_gather_rows(L.ptr(uncertainty), 16, L.ptr(idx), P, L.ptr(unc_rows), st), 'gather_rows')
+            flat['box_uncertainties'] = unc_rows
         if nms:
-            keep, counts = O.nms_segments(boxes, sel_scores, seg, n, float(self.nms_thresh), O.NMS_BATCH_SIZE)
+            weights = sel_scores
+            if self.uncertainty_nms and uncertainty is not None and P > 0:               # cpn.py:723-726
+                weights = torch.empty_like(sel_scores)
+                L.check(lib.cpn_nms_weights(L.ptr(sel_scores), L.ptr(uncertainty), L.ptr(idx), P, L.ptr(weights), st),
+                        'nms_weights')
+            keep, counts = O.nms_segments(boxes, weights, seg, n, float(self.nms_thresh), O.NMS_BATCH_SIZE)
             seg_h = seg.tolist()                          # host sync #2: per-image sizes of the returned lists
             counts_h = counts.tolist()
-            sel = torch.cat([keep[seg_h[i]:seg_h[i] + counts_h[i]] for i in range(n)]) if P > 0 else keep[:0]
-            K = int(sel.numel())
+            sel_rows = torch.cat([keep[seg_h[i]:seg_h[i] + counts_h[i]] for i in range(n)]) if P > 0 else keep[:0]
+            K = int(sel_rows.numel())
             out = OrderedDict()
             for k, v in flat.items():
                 row = v[0].numel() * v.element_size() if P > 0 else 0
                 dst = torch.empty((K,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
                 if K > 0:
-                    L.check(lib.cpn_gather_rows(L.ptr(v), row, L.ptr(sel), K, L.ptr(dst), st), 'gather_rows')
+                    L.check(lib.cpn_gather_rows(L.ptr(v), row, L.ptr(sel_rows), K, L.ptr(dst), st), 'gather_rows')
                 out[k] = dst
             return out, counts_h
         seg_h = seg.tolist()
@@ -274,7 +303,7 @@ class CPN(nn.Module):
         """``post_flat`` + the reference's per-image list structure (resolve_batch_index, models/cpn.py:42-60)."""
         flat, sizes = self.post_flat(scores, locfou, refinement, original_size, nms=nms, **kw)
         out = OrderedDict((k, list(torch.split(v, sizes, 0))) for k, v in flat.items())
-        out['box_uncertainties'] = None
+        out.setdefault('box_uncertainties', None)
         return out
 
     def _run_plan(self, inputs, fmt=None):
@@ -295,13 +324,16 @@ class CPN(nn.Module):
         plan.flags.zero_()
         return plan, plan.forward(x, fmt), (h, w)
 
+    def _post_kwargs(self, plan, outs, kwargs):
+        return dict(offsets=kwargs.get('offsets'), scores_lower_bound=kwargs.get('scores_lower_bound'),
+                    scores_upper_bound=kwargs.get('scores_upper_bound'), flags=plan.flags,
+                    uncertainty=outs[3] if len(outs) > 3 else None)
+
     def forward_flat(self, inputs, fmt=None, nms=True, **kwargs):
         """Like ``forward`` but returns (flat dict of concatenated tensors, rows per image); accepts uint8 NHWC
         batches (``fmt=_lib.IN_U8_NHWC``) so tile crops need no host-side transpose."""
-        plan, (sc, lf, rf), hw = self._run_plan(inputs, fmt)
-        return self.post_flat(sc, lf, rf, hw, nms=nms, offsets=kwargs.get('offsets'),
-                              scores_lower_bound=kwargs.get('scores_lower_bound'),
-                              scores_upper_bound=kwargs.get('scores_upper_bound'), flags=plan.flags)
+        plan, outs, hw = self._run_plan(inputs, fmt)
+        return self.post_flat(outs[0], outs[1], outs[2], hw, nms=nms, **self._post_kwargs(plan, outs, kwargs))
 
     # ---- model(x) ---------------------------------------------------------------------------------------------------
     def forward(self, inputs: Tensor, targets=None, nms=True, **kwargs):
@@ -309,10 +341,8 @@ class CPN(nn.Module):
             if self.training and targets is None:
                 raise ValueError('In training mode, targets should be passed')
             raise NotImplementedError('celldetection_b200 accelerates CPN inference only (use .eval()).')
-        plan, (sc, lf, rf), hw = self._run_plan(inputs)
-        return self.post(sc, lf, rf, hw, nms=nms, offsets=kwargs.get('offsets'),
-                         scores_lower_bound=kwargs.get('scores_lower_bound'),
-                         scores_upper_bound=kwargs.get('scores_upper_bound'), flags=plan.flags)
+        plan, outs, hw = self._run_plan(inputs)
+        return self.post(outs[0], outs[1], outs[2], hw, nms=nms, **self._post_kwargs(plan, outs, kwargs))
 
 
 def _make(arch):
@@ -320,7 +350,7 @@ def _make(arch):
         def __init__(self, in_channels: int = 3, order: int = 5, nms_thresh: float = .2, score_thresh: float = .9,
                      samples: int = 32, classes: int = 2, refinement: bool = True, refinement_iterations: int = 4,
                      refinement_margin: float = 3., refinement_buckets: int = 1, backbone_kwargs: dict = None,
-                     **kwargs):
+                     **kwargs):   # kwargs: uncertainty_head, uncertainty_nms, certainty_thresh, precision (cpn.py:288-321)
             if backbone_kwargs:
                 raise NotImplementedError('backbone_kwargs are outside the accelerated path.')
             super().__init__(arch, in_channels=in_channels, order=order, nms_thresh=nms_thresh,

@@ -348,11 +348,15 @@ def _read_out_spec(g, p, cin, cmid, cout, k=7):
 
 
 def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_margin=3., refinement_buckets=1,
-          stem_im2col=False):
+          uncertainty_head=False, stem_im2col=False):
     """Trace architecture `arch` for an [n, in_channels, h, w] input.  Returns the Tracer; ``g.outputs`` maps
-    'scores' / 'locfou' / 'refinement' to fp32 output tensors (bindings 0 / 1 / 2)."""
+    'scores' / 'locfou' / 'refinement' (/ 'uncertainty') to fp32 output tensors (bindings 0 / 1 / 2 (/ 3)).
+
+    Variants of models/cpn.py:177-234: ``score_channels`` > 1 widens the score head (classes > 2, :372),
+    ``refinement_buckets`` > 1 widens the refinement head to 2 * buckets channels (:222-234), ``uncertainty_head``
+    adds a fourth ReadOut with 4 sigmoid outputs on the head features (:208-219)."""
     assert arch in ARCHS, arch
-    assert score_channels == 1 and refinement_buckets == 1, 'only classes<=2 and refinement_buckets=1 are in scope'
+    assert score_channels >= 1 and refinement_buckets >= 1
     g = Tracer(n, h, w, stem_im2col=stem_im2col)
     g.spec['order_weights'] = ((order, 1), 'order_weights')   # buffer of CPN (cpn.py:406-412)
     bb = 'core.backbone'
@@ -369,32 +373,42 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
         feats, chans = _resnet_encoder(g, x, f'{bb}.body', in_channels, 'resnet18')
         res = _fpn_decoder(g, feats, chans, f'{bb}.fpn')
         head_feat, head_c, ref_feat, ref_c = res[1], 256, res[0], 256
-    # ---- heads (models/cpn.py:177-234, 238-283) ----
-    heads = [('core.score_head', score_channels), ('core.location_head', 2), ('core.fourier_head', order * 4)]
-    for hp, co in heads:
+    # ---- heads (models/cpn.py:177-234, 238-283); module order: score, location, fourier, (uncertainty), refinement ----
+    heads = [('core.score_head', score_channels, 'none'), ('core.location_head', 2, 'none'),
+             ('core.fourier_head', order * 4, 'none')]
+    if uncertainty_head:
+        heads.append(('core.uncertainty_head', 4, 'sigmoid'))
+    for hp, co, _ in heads:
         _read_out_spec(g, hp, head_c, head_c, co)
     _read_out_spec(g, 'core.refinement_head', ref_c, ref_c, 2 * refinement_buckets)
-    pm = ConvParams([f'{hp}.block.0.weight' for hp, _ in heads], [f'{hp}.block.0.bias' for hp, _ in heads],
-                    [f'{hp}.block.1' for hp, _ in heads])
-    mid = g.conv(head_feat, 3 * head_c, 7, act='relu', params=pm, name='heads.block.0')
+    pm = ConvParams([f'{hp}.block.0.weight' for hp, _, _ in heads], [f'{hp}.block.0.bias' for hp, _, _ in heads],
+                    [f'{hp}.block.1' for hp, _, _ in heads])
+    mid = g.conv(head_feat, len(heads) * head_c, 7, act='relu', params=pm, name='heads.block.0')
     hh, hw_ = head_feat.h, head_feat.w
-    scores = g.tensor(1, hh, hw_, f32=True, binding=0)
+    scores = g.tensor(score_channels, hh, hw_, f32=True, binding=0)
     locfou = g.tensor(2 + 4 * order, hh, hw_, f32=True, binding=1)
     loc_t = g.tensor(2, hh, hw_, f32=True, parent=locfou, c_off=0, binding=1)
     fou_t = g.tensor(4 * order, hh, hw_, f32=True, parent=locfou, c_off=2, binding=1)
-    for j, ((hp, co), dst) in enumerate(zip(heads, (scores, loc_t, fou_t))):
+    dsts = [scores, loc_t, fou_t]
+    uncertainty = None
+    if uncertainty_head:
+        uncertainty = g.tensor(4, hh, hw_, f32=True, binding=3)
+        dsts.append(uncertainty)
+    for j, ((hp, co, act), dst) in enumerate(zip(heads, dsts)):
         pp = ConvParams([f'{hp}.block.4.weight'], [f'{hp}.block.4.bias'], [None])
-        g.proj(mid, dst, j * head_c, head_c, pp, name=f'{hp}.block.4')
+        g.proj(mid, dst, j * head_c, head_c, pp, act=act, name=f'{hp}.block.4')
     if (ref_feat.h, ref_feat.w) != (h, w):       # refinement_full_res (cpn.py:277-278)
         ref_feat = g.bilinear(ref_feat, h, w)
     pr = ConvParams(['core.refinement_head.block.0.weight'], ['core.refinement_head.block.0.bias'],
                     ['core.refinement_head.block.1'])
     rmid = g.conv(ref_feat, ref_c, 7, act='relu', params=pr, name='core.refinement_head.block.0')
-    refinement = g.tensor(2, h, w, f32=True, binding=2)
+    refinement = g.tensor(2 * refinement_buckets, h, w, f32=True, binding=2)
     pp = ConvParams(['core.refinement_head.block.4.weight'], ['core.refinement_head.block.4.bias'], [None])
     g.proj(rmid, refinement, 0, ref_c, pp, act='scaled_tanh', act_scale=float(refinement_margin),
            name='core.refinement_head.block.4')
     g.outputs = OrderedDict(scores=scores, locfou=locfou, refinement=refinement)
+    if uncertainty is not None:
+        g.outputs['uncertainty'] = uncertainty
     g.head_hw = (hh, hw_)
     g.finalize()
     return g

@@ -182,7 +182,7 @@ class Plan:
         ops = (L.Op * len(g.ops))()
         kind_map = dict(prep=L.OP_PREP, conv=L.OP_CONV, maxpool=L.OP_MAXPOOL, upsample=L.OP_UPSAMPLE,
                         bilinear=L.OP_BILINEAR, proj=L.OP_PROJ)
-        act_map = dict(none=L.ACT_NONE, relu=L.ACT_RELU, scaled_tanh=L.ACT_SCALED_TANH)
+        act_map = dict(none=L.ACT_NONE, relu=L.ACT_RELU, scaled_tanh=L.ACT_SCALED_TANH, sigmoid=L.ACT_SIGMOID)
         self.engines = []
         for i, lop in enumerate(g.ops):
             o = ops[i]
@@ -234,7 +234,7 @@ class Plan:
                 ok = all(q.kind == 'proj' and q.src is lop.dst and q.cin == bn and q.cin_off == h * bn and q.dst.c <= 24
                          for h, q in enumerate(nxt))
                 users = sum(1 for q in g.ops if q.src is lop.dst or q.res is lop.dst)
-                if ok and users == nt and sum(q.dst.c for q in nxt) * bn * 4 <= 24576:
+                if ok and users == nt and sum(q.dst.c for q in nxt) * bn * 4 <= 32768:
                     ops[i].fuse_next = nt
                     self.fused.update(range(i + 1, i + 1 + nt))
         self.ops = ops
@@ -244,14 +244,19 @@ class Plan:
         self.handle = handle
         self.n_launches = lib.cpn_plan_num_launches(handle)
         hh, hw = g.head_hw
-        self.out_shapes = OrderedDict(scores=(g.n, hh, hw), locfou=(g.n, hh, hw, g.outputs['locfou'].c),
-                                      refinement=(g.n, g.h, g.w, 2))
+        sc = g.outputs['scores'].c      # score maps keep the historical [N,h,w] shape for a single channel
+        self.out_shapes = OrderedDict(scores=(g.n, hh, hw) if sc == 1 else (g.n, hh, hw, sc),
+                                      locfou=(g.n, hh, hw, g.outputs['locfou'].c),
+                                      refinement=(g.n, g.h, g.w, g.outputs['refinement'].c))
+        if 'uncertainty' in g.outputs:
+            self.out_shapes['uncertainty'] = (g.n, hh, hw, 4)
 
     def new_outputs(self):
         return [torch.empty(s, dtype=torch.float32, device=self.device) for s in self.out_shapes.values()]
 
     def forward(self, x, input_format, outputs=None):
-        """Enqueue the backbone + heads on the current stream.  Returns [scores, locfou, refinement] (fp32)."""
+        """Enqueue the backbone + heads on the current stream.  Returns [scores, locfou, refinement(, uncertainty)]
+        (fp32, in the order of ``out_shapes``)."""
         lib = L.load()
         outputs = self.new_outputs() if outputs is None else outputs
         arr = (ctypes.c_void_p * len(outputs))(*[o.data_ptr() for o in outputs])

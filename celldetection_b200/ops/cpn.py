@@ -16,7 +16,7 @@ from .. import _lib as L
 
 __all__ = ['fouriers2contours', 'rel_location2abs_location', 'get_scale', 'scale_contours', 'scale_fourier',
            'batched_box_nmsi', 'batched_box_nms', 'remove_border_contours', 'filter_contours_by_stitching_rule', 'nms',
-           'nms_grid', 'trig_table',
+           'nms_grid', 'trig_table', 'bucket_table', 'refinement_bucket_weight', 'resolve_refinement_buckets',
            'NMS_BATCH_SIZE']
 
 NMS_BATCH_SIZE = 50000  # ops/cpn.py:12
@@ -42,6 +42,44 @@ def trig_table(order: int, samples: int, device) -> Tensor:
         if len(_trig_cache) > 64:
             _trig_cache.pop(next(iter(_trig_cache)))
         _trig_cache[key] = t
+    return t
+
+
+def refinement_bucket_weight(index, base_index):
+    """ops/cpn.py:238-244"""
+    dist = torch.abs(index + 0.5 - base_index)
+    sel = dist > 1
+    dist = 1. - dist
+    dist[sel] = 0
+    return dist
+
+
+def resolve_refinement_buckets(samplings, num_buckets):
+    """ops/cpn.py:247-255: the three neighbouring buckets (index, weight) of every sampling position."""
+    base_index = samplings * num_buckets
+    base_index_int = base_index.long()
+    a, b, c = base_index_int - 1, base_index_int, base_index_int + 1
+    return ((a % num_buckets, refinement_bucket_weight(a, base_index)),
+            (b % num_buckets, refinement_bucket_weight(b, base_index)),
+            (c % num_buckets, refinement_bucket_weight(c, base_index)))
+
+
+_bucket_cache: Dict[tuple, tuple] = {}
+
+
+def bucket_table(samples: int, buckets: int, device):
+    """([samples, 3] int32 bucket indices, [samples, 3] fp32 weights) of the default sampling ``linspace(0, 1, samples)``
+    -- ``resolve_refinement_buckets`` evaluated with the reference's torch CPU ops so the bucketed refinement kernel
+    (``cpn_decode_refine_buckets``) multiplies by bit-identical weights (models/cpn.py:73-82)."""
+    key = (int(samples), int(buckets), str(device))
+    t = _bucket_cache.get(key)
+    if t is None:
+        res = resolve_refinement_buckets(torch.linspace(0, 1.0, samples), buckets)
+        idx = torch.stack([i for i, _ in res], -1).to(torch.int32).contiguous().to(device)
+        wts = torch.stack([w for _, w in res], -1).to(torch.float32).contiguous().to(device)
+        if len(_bucket_cache) > 64:
+            _bucket_cache.pop(next(iter(_bucket_cache)))
+        t = _bucket_cache[key] = (idx, wts)
     return t
 
 

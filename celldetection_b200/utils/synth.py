@@ -55,7 +55,7 @@ def _is_basic(spec, key):
 
 @torch.no_grad()
 def calibrate_heads_(sd, core_fn, x, fg_fraction=0.02, score_std=2., fourier_std=3., location_std=1.,
-                     score_thresh=0.9, refinement_std=0.5, refinement_margin=3.):
+                     score_thresh=0.9, refinement_std=0.5, refinement_margin=3., uncertainty_std=1.5):
     """In place: rescale ``core.{score,fourier,location}_head.block.4`` so that on calibration input ``x`` the raw score
     logits have std ``score_std`` and mean such that ``fg_fraction`` of the pixels exceed ``score_thresh`` (normal
     approximation), fourier std -> ``fourier_std`` px, location std -> ``location_std`` px.
@@ -64,8 +64,9 @@ def calibrate_heads_(sd, core_fn, x, fg_fraction=0.02, score_std=2., fourier_std
     rescaled (two passes, through atanh) so that its pre-activation has std ``refinement_std``: an uncalibrated head
     saturates tanh almost everywhere, which is unlike trained weights and makes the output needlessly steep.
 
-    ``core_fn(x, sd) -> dict(scores [N,1,h,w], locations [N,2,h,w], fourier [N,4*order,h,w][, refinement])`` is one
-    forward of whichever implementation is at hand.  Returns the measured pre-calibration statistics.
+    ``core_fn(x, sd) -> dict(scores [N,C,h,w], locations [N,2,h,w], fourier [N,4*order,h,w][, refinement]
+    [, uncertainty])`` is one forward of whichever implementation is at hand (an ``uncertainty`` entry, the sigmoid output
+    of the uncertainty head, gets its logits calibrated to std ``uncertainty_std``).  Returns the measured pre-calibration statistics.
     """
     out = core_fn(x, sd)
     stats = {}
@@ -82,6 +83,16 @@ def calibrate_heads_(sd, core_fn, x, fg_fraction=0.02, score_std=2., fourier_std
         dev, dt = sd[key + '.weight'].device, sd[key + '.weight'].dtype
         sd[key + '.weight'] = (sd[key + '.weight'].float() * s).to(dev, dt)
         sd[key + '.bias'] = ((sd[key + '.bias'].float() - mu) * s + tmu).to(dev, dt)
+    key = 'core.uncertainty_head.block.4'
+    if out.get('uncertainty') is not None and uncertainty_std:      # sigmoid outputs: calibrate the logits to N(0, std)
+        u = out['uncertainty'].float().clamp(1e-6, 1 - 1e-6)
+        zed = torch.log(u / (1 - u))
+        mu, std = float(zed.mean()), float(zed.std())
+        stats['uncertainty_pre'] = (mu, std)
+        s = uncertainty_std / max(std, 1e-12)
+        dev, dt = sd[key + '.weight'].device, sd[key + '.weight'].dtype
+        sd[key + '.weight'] = (sd[key + '.weight'].float() * s).to(dev, dt)
+        sd[key + '.bias'] = ((sd[key + '.bias'].float() - mu) * s).to(dev, dt)
     key = 'core.refinement_head.block.4'
     if out.get('refinement') is not None and refinement_std:
         for it in range(2):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CPN_B200_ABI_VERSION 2
+#define CPN_B200_ABI_VERSION 3
 
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* status / diagnostics                                                                                             */
@@ -75,7 +75,8 @@ enum {
 };
 
 enum { CPN_IN_F32_NCHW = 0, CPN_IN_U8_NCHW = 1, CPN_IN_U8_NHWC = 2 };
-enum { CPN_ACT_NONE = 0, CPN_ACT_RELU = 1, CPN_ACT_SCALED_TANH = 2 };
+enum { CPN_ACT_NONE = 0, CPN_ACT_RELU = 1, CPN_ACT_SCALED_TANH = 2,
+       CPN_ACT_SIGMOID = 3 /* ReadOut(final_activation='sigmoid') of the uncertainty head, models/cpn.py:208-219 */ };
 /* conv engines */
 enum { CPN_ENGINE_SIMT = 0, CPN_ENGINE_TCGEN05 = 1 };
 
@@ -149,6 +150,35 @@ int cpn_select_write(const float* logits, const float* lower, const float* upper
                      float thresh, void* workspace, int32_t* idx, float* score, int64_t capacity,
                      int32_t* seg_offsets, void* stream);
 
+/* General form of the two selection passes for every scoring variant of models/cpn.py:575-587 and the certainty filter
+ * of :616-618.  `channels` = score_channels of the model:
+ *   1   scores = sigmoid(logit) [min upper] [max lower]; class = scores > thresh; foreground = class > 0
+ *   > 2 scores = softmax over the channels, every channel [min upper] [max lower]; class = argmax (first maximum);
+ *       foreground = class > 0 (thresh unused); the selected score is scores[class]
+ * logits [N,h,w,channels] fp32 (channel-last records, as the plan's score head writes them); lower/upper [N,h,w] or
+ * NULL.  uncertainty: optional [N,h,w,4] fp32 (sigmoid outputs of the uncertainty head); when use_certainty != 0 a
+ * pixel is foreground only if mean(uncertainty[pixel, :]) < certainty_limit (= 1 - certainty_thresh, rounded to fp32
+ * by the host exactly like the reference's tensor-scalar comparison). */
+typedef struct {
+  const float* logits;
+  const float* lower;
+  const float* upper;
+  const float* uncertainty;
+  int32_t channels;
+  int32_t use_certainty;
+  float thresh;
+  float certainty_limit;
+} cpn_select_params_t;
+int cpn_select_count_ex(const cpn_select_params_t* params_host, int64_t pixels, void* workspace, int64_t* total_dev,
+                        void* stream);
+/* classes (optional, may be NULL) receives the class of every proposal as int64 (1 for channels == 1). */
+int cpn_select_write_ex(const cpn_select_params_t* params_host, int n_images, int64_t hw, void* workspace, int32_t* idx,
+                        float* score, int64_t* classes, int64_t capacity, int32_t* seg_offsets, void* stream);
+
+/* NMS weights of models/cpn.py:723-726 (uncertainty_nms): out[i] = scores[i] * (1 - mean(uncertainty[idx[i], 0:4])). */
+int cpn_nms_weights(const float* scores, const float* uncertainty, const int32_t* idx, int64_t P, float* out,
+                    void* stream);
+
 /* Decode + rescale + local refinement + clamp + boxes + offsets for P selected pixels in one kernel
  * (ops/cpn.py:15-41 rel->abs, :44-95 inverse DFT, :98-165 rescale; models/cpn.py:63-85 refinement, :661-670 clamp
  * and boxes, :695-702 offsets).
@@ -162,6 +192,17 @@ int cpn_decode_refine(const int32_t* idx, int64_t P, const float* locfou, int or
                       int h, int w, int H, int W, const float* trig, int samples, const float* refinement, int iters,
                       const float* offsets, float* contours, float* proposals, float* boxes, float* locations,
                       float* fourier_out, void* stream);
+
+/* cpn_decode_refine with bucketed local refinement (refinement_buckets > 1; models/cpn.py:73-82, ops/cpn.py:238-255):
+ * refinement is [N,H,W,2*buckets] (bucket j: x at channel 2j, y at 2j+1); per contour sample s the three neighbouring
+ * buckets and their weights are read from bucket_idx [samples][3] int32 / bucket_w [samples][3] fp32, which the host
+ * computes from the sampling exactly like resolve_refinement_buckets; the displacement is
+ * ((r[b0]*w0) + (r[b1]*w1)) + (r[b2]*w2), the reference's summation order.  buckets == 1 ignores the tables. */
+int cpn_decode_refine_buckets(const int32_t* idx, int64_t P, const float* locfou, int order_core, int order,
+                              int n_images, int h, int w, int H, int W, const float* trig, int samples,
+                              const float* refinement, int iters, int buckets, const int32_t* bucket_idx,
+                              const float* bucket_w, const float* offsets, float* contours, float* proposals,
+                              float* boxes, float* locations, float* fourier_out, void* stream);
 
 /* ops.cpn.fouriers2contours (ops/cpn.py:44-95): fourier [P,order,4], locations [P,2] -> out [P,samples,2].
  * trig as above; or sampling [P,samples] (per-proposal t, :67-71) with trig == NULL. */

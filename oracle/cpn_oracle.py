@@ -17,8 +17,8 @@ oracle function        reference code it follows (relative to /root/reference/ce
 ``unet_decoder``       models/unet.py:178-249 (forward) with the ctor bookkeeping of :62-176
 ``fpn_decoder``        torchvision.ops.FeaturePyramidNetwork.forward, models/fpn.py:50-76 (LastLevelMaxPool), :79-134
 ``read_out``           models/commons.py:461-511
-``cpn_core``           models/cpn.py:238-283
-``cpn_post``           models/cpn.py:575-734, ops/cpn.py:15-165, :189-227
+``cpn_core5``          models/cpn.py:238-283 (``cpn_core`` = without the uncertainty map)
+``cpn_post``           models/cpn.py:575-734 (all inference variants), ops/cpn.py:15-165, :189-227, :238-255
 ``nms``                torch.ops.torchvision.nms semantics (third party, torchvision 0.26)
 ``fouriers2contours``  ops/cpn.py:44-95
 ``get_tiling_slices``  util/util.py:1305-1354
@@ -201,18 +201,28 @@ def _equal_size(x, ref_hw):
     return x
 
 
-def cpn_core(x, sd, arch, refinement_margin=3.):
-    """models/cpn.py:238-283 -> scores, locations, refinement, fourier (raw head tensors, NCHW fp32)."""
+def cpn_core5(x, sd, arch, refinement_margin=3.):
+    """models/cpn.py:238-283 -> scores, locations, refinement, fourier, uncertainty (raw head tensors, NCHW fp32).
+    The variants are read off the state_dict: score head width (classes > 2), refinement head width (2 * buckets),
+    presence of ``core.uncertainty_head`` (4 sigmoid outputs, cpn.py:208-219)."""
     cfg = ARCHS[arch]
     feats = backbone(x, sd, arch)
     hf, rf = feats[cfg['head_key']], feats[cfg['ref_key']]
     scores = read_out(hf, sd, 'core.score_head')
     locations = read_out(hf, sd, 'core.location_head')
     fourier = read_out(hf, sd, 'core.fourier_head')
+    uncertainty = None
+    if 'core.uncertainty_head.block.0.weight' in sd:
+        uncertainty = read_out(hf, sd, 'core.uncertainty_head', final=torch.sigmoid)
     rf = _equal_size(rf, x.shape[2:])
     refinement = read_out(rf, sd, 'core.refinement_head', final=lambda t: torch.tanh(t) * refinement_margin + 0.)
     refinement = _equal_size(refinement, x.shape[2:])
-    return scores, locations, refinement, fourier
+    return scores, locations, refinement, fourier, uncertainty
+
+
+def cpn_core(x, sd, arch, refinement_margin=3.):
+    """``cpn_core5`` without the uncertainty map."""
+    return cpn_core5(x, sd, arch, refinement_margin)[:4]
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -297,22 +307,54 @@ def batched_box_nmsi(boxes, scores, iou_threshold, batch_size=None):
     return keeps
 
 
+def refinement_bucket_weight(index, base_index):
+    """ops/cpn.py:238-244"""
+    dist = torch.abs(index + 0.5 - base_index)
+    sel = dist > 1
+    dist = 1. - dist
+    dist[sel] = 0
+    return dist
+
+
+def resolve_refinement_buckets(samplings, num_buckets):
+    """ops/cpn.py:247-255"""
+    base_index = samplings * num_buckets
+    base_index_int = base_index.long()
+    a, b, c = base_index_int - 1, base_index_int, base_index_int + 1
+    return ((a % num_buckets, refinement_bucket_weight(a, base_index)),
+            (b % num_buckets, refinement_bucket_weight(b, base_index)),
+            (c % num_buckets, refinement_bucket_weight(c, base_index)))
+
+
 def cpn_post(scores, locations, refinement, fourier, original_size, order=5, samples=32, score_thresh=.9,
              nms_thresh=.2, refinement_iterations=4, offsets=None, nms_on=True, scores_lower_bound=None,
-             scores_upper_bound=None):
-    """models/cpn.py:575-734 for classes=2, refinement_buckets=1, no uncertainty head.
+             scores_upper_bound=None, uncertainty=None, certainty_thresh=None, uncertainty_nms=False):
+    """models/cpn.py:575-734 (eval mode) including the variants: score_channels > 2 (softmax / argmax, :583-585),
+    uncertainty head (certainty filter :617-618, box_uncertainties :723-726, uncertainty_nms) and bucketed local
+    refinement (refinement.shape[1] = 2 * buckets, :73-82).
 
-    Inputs are the raw NCHW head tensors of ``cpn_core``.  Returns an OrderedDict of per-image lists of tensors,
+    Inputs are the raw NCHW head tensors of ``cpn_core5``.  Returns an OrderedDict of per-image lists of tensors,
     keys as the reference: contours, boxes, scores, classes, locations, fourier, contour_proposals, box_uncertainties.
     """
     n = scores.shape[0]
     H, W = original_size
-    sc = torch.sigmoid(scores)
-    if scores_upper_bound is not None:  # cpn.py:118-123
-        sc = torch.minimum(sc, _equal_size(scores_upper_bound, sc.shape[2:]))
-    if scores_lower_bound is not None:
-        sc = torch.maximum(sc, _equal_size(scores_lower_bound, sc.shape[2:]))
-    classes = torch.squeeze((sc > score_thresh).long(), 1)
+    score_channels = scores.shape[1]
+
+    def bounds(sc):  # cpn.py:118-123
+        if scores_upper_bound is not None:
+            sc = torch.minimum(sc, _equal_size(scores_upper_bound, sc.shape[2:]))
+        if scores_lower_bound is not None:
+            sc = torch.maximum(sc, _equal_size(scores_lower_bound, sc.shape[2:]))
+        return sc
+    if score_channels == 1:
+        sc = bounds(torch.sigmoid(scores))
+        classes = torch.squeeze((sc > score_thresh).long(), 1)
+    elif score_channels == 2:
+        sc = bounds(F.softmax(scores, dim=1)[:, 1:2])
+        classes = torch.squeeze((sc > score_thresh).long(), 1)
+    else:
+        sc = bounds(F.softmax(scores, dim=1))
+        classes = torch.argmax(sc, dim=1).long()
     h, w = fourier.shape[-2:]
     fo = fourier.view(n, fourier.shape[1] // 4, 4, h, w)
     if order < fo.shape[1]:
@@ -321,12 +363,16 @@ def cpn_post(scores, locations, refinement, fourier, original_size, order=5, sam
     grid = torch.stack((torch.arange(w)[None] + torch.zeros(h)[:, None],
                         torch.zeros(w)[None] + torch.arange(h)[:, None]), 0)
     loc = locations + grid
-    b, y, x = torch.where(classes > 0)
+    fg = classes > 0
+    if certainty_thresh is not None and uncertainty is not None:
+        fg = fg & (uncertainty.mean(1) < (1 - certainty_thresh))
+    b, y, x = torch.where(fg)
     sel_fourier = fo[b, :, :, y, x]
     sel_loc = loc[b, :, y, x]
     sel_classes = classes[b, y, x]
-    sel_scores = sc[b, 0, y, x]
-    proposals, _ = fouriers2contours(sel_fourier, sel_loc, samples=samples)
+    sel_scores = sc[b, 0, y, x] if score_channels in (1, 2) else sc[b, sel_classes, y, x]
+    sel_unc = uncertainty[b, :, y, x] if uncertainty is not None else None
+    proposals, sampling = fouriers2contours(sel_fourier, sel_loc, samples=samples)
     scale = (torch.as_tensor((H, W), dtype=torch.float) / torch.as_tensor((h, w), dtype=torch.float)).flip(-1)
     proposals = proposals * scale  # ops/cpn.py:98-127
     sel_fourier = sel_fourier.clone()
@@ -334,13 +380,23 @@ def cpn_post(scores, locations, refinement, fourier, original_size, order=5, sam
     sel_fourier[..., [2, 3]] = sel_fourier[..., [2, 3]] * scale[1]
     sel_loc = sel_loc * scale
     if refinement is not None and refinement_iterations > 0:  # cpn.py:63-85
+        num_buckets = refinement.shape[1] // 2
         det = proposals
         for _ in range(refinement_iterations):
             det = torch.round(det)
             det[..., 0].clamp_(0, W - 1)
             det[..., 1].clamp_(0, H - 1)
             idx = det.long()
-            det = det + refinement[b[:, None], :, idx[:, :, 1], idx[:, :, 0]]
+            if num_buckets == 1:
+                responses = refinement[b[:, None], :, idx[:, :, 1], idx[:, :, 0]]
+            else:
+                responses = None
+                for bucket_indices, bucket_weights in resolve_refinement_buckets(sampling, num_buckets):
+                    bckt_idx = torch.stack((bucket_indices * 2, bucket_indices * 2 + 1), -1)
+                    cur = refinement[b[:, None, None], bckt_idx, idx[:, :, 1, None], idx[:, :, 0, None]]
+                    cur = cur * bucket_weights[..., None]
+                    responses = cur if responses is None else responses + cur
+            det = det + responses
         contours = det
     else:
         contours = proposals
@@ -358,13 +414,18 @@ def cpn_post(scores, locations, refinement, fourier, original_size, order=5, sam
         sel_loc += off
     outputs = OrderedDict(contours=contours, boxes=boxes, scores=sel_scores, classes=sel_classes, locations=sel_loc,
                           fourier=sel_fourier, contour_proposals=proposals)
+    if sel_unc is not None:
+        outputs['box_uncertainties'] = sel_unc
     per_image = OrderedDict((k, [v[b == i] for i in range(n)]) for k, v in outputs.items())  # cpn.py:42-50
     if nms_on:
-        keeps = batched_box_nmsi([t.numpy() for t in per_image['boxes']], [t.numpy() for t in per_image['scores']],
-                                 nms_thresh)
+        if uncertainty_nms and sel_unc is not None:  # cpn.py:723-726
+            nms_w = [s * (1. - u.mean(1)) for s, u in zip(per_image['scores'], per_image['box_uncertainties'])]
+        else:
+            nms_w = per_image['scores']
+        keeps = batched_box_nmsi([t.numpy() for t in per_image['boxes']], [t.numpy() for t in nms_w], nms_thresh)
         per_image = OrderedDict((k, [v[i][torch.as_tensor(keeps[i])] for i in range(n)])
                                 for k, v in per_image.items())
-    per_image['box_uncertainties'] = None
+    per_image.setdefault('box_uncertainties', None)
     return per_image
 
 
@@ -372,8 +433,8 @@ def cpn_forward(x, sd, arch, **kw):
     """``model(x)`` of the reference in eval mode: core + post chain.  ``kw`` are the mutable CPN attributes."""
     x = torch.as_tensor(x, dtype=torch.float32)
     with torch.no_grad():
-        scores, locations, refinement, fourier = cpn_core(x, sd, arch)
-        return cpn_post(scores, locations, refinement, fourier, x.shape[-2:], **kw)
+        scores, locations, refinement, fourier, uncertainty = cpn_core5(x, sd, arch)
+        return cpn_post(scores, locations, refinement, fourier, x.shape[-2:], uncertainty=uncertainty, **kw)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@ synthetic state_dict.  State dicts are too large to commit (31-225 M parameters)
 state_dict anywhere.  While minting, the oracle restatement (oracle/cpn_oracle.py) is checked against the reference
 and the script aborts on any mismatch.
 """
+import json
 import os
 import sys
 from collections import OrderedDict
@@ -31,6 +32,21 @@ CALIB_KEYS = [f'core.{h}_head.block.4.{p}' for h in ('score', 'fourier', 'locati
 
 FOURIER_STD, LOCATION_STD = 1.0, 0.5   # small objects so that NMS keeps a useful number of detections
 
+# name, arch, N, H, W, seed, fg_fraction, ctor kwargs (variant), attributes set after construction
+VARIANT_CASES = [
+    ('cpnu22_c4_unc_b6', 'CpnU22', 2, 96, 128, 6, 0.2,
+     dict(classes=4, uncertainty_head=True, refinement_buckets=6), dict(certainty_thresh=0.5, uncertainty_nms=True)),
+    ('cpnresnext101unet_unc_b4', 'CpnResNeXt101UNet', 1, 128, 128, 7, 0.2,
+     dict(uncertainty_head=True, refinement_buckets=4), dict(certainty_thresh=0.47)),
+    ('cpnresnet18fpn_c3_b2', 'CpnResNet18FPN', 1, 128, 128, 8, 0.2,
+     dict(classes=3, refinement_buckets=2), dict()),
+]
+
+
+def variant_key(arch, ctor):
+    return arch + ''.join(f'|{k}={v}' for k, v in sorted(ctor.items()))
+
+
 MODEL_CASES = [
     # name, arch, N, H, W, seed, fg_fraction, model kwargs
     ('cpnu22_n1_128', 'CpnU22', 1, 128, 128, 1, 0.3, {}),
@@ -44,8 +60,8 @@ def spec_of(ref_model):
     return OrderedDict((k, tuple(v.shape)) for k, v in ref_model.state_dict().items())
 
 
-def build_state_dict(cd, arch, seed, fg_fraction, calib_x):
-    model = getattr(cd.models, arch)(3).eval()
+def build_state_dict(cd, arch, seed, fg_fraction, calib_x, ctor=None):
+    model = getattr(cd.models, arch)(3, **(ctor or {})).eval()
     sd = synth_state_dict(spec_of(model), seed=seed)
     # torchvision's FeaturePyramidNetwork._load_from_state_dict renames 'inner_blocks.N.weight' for version < 2
     # state dicts; carry the module versions over so the reference loads our plain OrderedDict verbatim.
@@ -54,10 +70,15 @@ def build_state_dict(cd, arch, seed, fg_fraction, calib_x):
     def core_fn(x, sd_):
         model.load_state_dict(sd_)
         with torch.no_grad():
-            scores, locations, refinement, fourier, _ = model.core(x)
-        return dict(scores=scores, locations=locations, fourier=fourier, refinement=refinement)
+            scores, locations, refinement, fourier, unc = model.core(x)
+        return dict(scores=scores, locations=locations, fourier=fourier, refinement=refinement, uncertainty=unc)
 
     calibrate_heads_(sd, core_fn, calib_x, fg_fraction=fg_fraction, fourier_std=FOURIER_STD, location_std=LOCATION_STD)
+    if model.score_channels > 2:      # softmax scoring: centre every class logit, then favour the background class
+        mu = core_fn(calib_x, sd)['scores'].mean((0, 2, 3))
+        b = sd['core.score_head.block.4.bias'].clone() - mu
+        b[0] += 2.0
+        sd['core.score_head.block.4.bias'] = b
     model.load_state_dict(sd)
     return model, sd
 
@@ -109,6 +130,55 @@ def mint_model_case(cd, name, arch, n, h, w, seed, fg, mkw):
     np.savez_compressed(os.path.join(GOLDEN, f'model_{name}.npz'), arch=np.array(arch), **arrays)
     print(f'{name}: proposals {[int(arrays[f"nonms_count/{i}"]) for i in range(n)]} kept '
           f'{[len(out["scores"][i]) for i in range(n)]}')
+
+
+def mint_variant_case(cd, name, arch, n, h, w, seed, fg, ctor, attrs):
+    """Variant models (classes > 2, uncertainty head, bucketed refinement): same recipe as ``mint_model_case``."""
+    torch.manual_seed(seed)
+    x = torch.rand(n, 3, h, w)
+    model, sd = build_state_dict(cd, arch, seed, fg, x[:1], ctor)
+    for k, v in attrs.items():
+        setattr(model, k, v)
+    offsets = torch.tensor([[7., 3.]] * n) if n > 1 else None
+    with torch.no_grad():
+        scores, locations, refinement, fourier, unc = model.core(x)
+        out = model(x) if offsets is None else model(x, offsets=offsets)
+        out_nonms = model(x, nms=False)
+    o = orc.cpn_core5(x, sd, arch)
+    for nm, a, b in zip(('scores', 'locations', 'refinement', 'fourier', 'uncertainty'), o,
+                        (scores, locations, refinement, fourier, unc)):
+        if b is not None:
+            check_close(f'{name}/{nm}', to_np(a), to_np(b), 1e-5)
+    okw = dict(offsets=offsets, order=model.order, samples=model.samples, certainty_thresh=model.certainty_thresh,
+               uncertainty_nms=model.uncertainty_nms)
+    o_out = orc.cpn_forward(x, sd, arch, **okw)
+    keys = ['contours', 'boxes', 'scores', 'classes', 'locations', 'fourier', 'contour_proposals']
+    if unc is not None:
+        keys.append('box_uncertainties')
+    for k in keys:
+        for i in range(n):
+            assert len(o_out[k][i]) == len(out[k][i]), (name, k, i, len(o_out[k][i]), len(out[k][i]))
+            check_close(f'{name}/out/{k}/{i}', to_np(o_out[k][i]), to_np(out[k][i]), 1e-5)
+    arrays = dict(x=to_np(x), raw_scores=to_np(scores), raw_locations=to_np(locations), raw_refinement=to_np(refinement),
+                  raw_fourier=to_np(fourier))
+    if unc is not None:
+        arrays['raw_uncertainty'] = to_np(unc)
+    if offsets is not None:
+        arrays['offsets'] = to_np(offsets)
+    calib = list(CALIB_KEYS) + ([f'core.uncertainty_head.block.4.{p}' for p in ('weight', 'bias')] if unc is not None else [])
+    for k in calib:
+        arrays['calib/' + k] = to_np(sd[k])
+    for i in range(n):
+        for k in keys:
+            arrays[f'out/{i}/{k}'] = to_np(out[k][i])
+        arrays[f'nonms_count/{i}'] = np.array(len(out_nonms['scores'][i]))
+    arrays['meta'] = np.array([n, h, w, seed, model.order, model.samples], dtype=np.int64)
+    arrays['ctor'] = np.array(json.dumps(ctor))
+    arrays['attrs'] = np.array(json.dumps(attrs))
+    arrays['spec_key'] = np.array(variant_key(arch, ctor))
+    np.savez_compressed(os.path.join(GOLDEN, f'model_{name}.npz'), arch=np.array(arch), **arrays)
+    print(f'{name}: proposals {[int(arrays[f"nonms_count/{i}"]) for i in range(n)]} kept '
+          f'{[len(out["scores"][i]) for i in range(n)]} classes {sorted(set(np.concatenate([to_np(c) for c in out["classes"]]).tolist()))}')
 
 
 def mint_f2c(cd):
@@ -195,11 +265,13 @@ def mint_apply_model(cd):
 
 def mint_keys(cd):
     """state_dict key -> shape of the three reference models (drop-in contract)."""
-    import json
     out = {}
     for arch in ('CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet'):
         m = getattr(cd.models, arch)(3)
         out[arch] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    for _, arch, _, _, _, _, _, ctor, _ in VARIANT_CASES:
+        m = getattr(cd.models, arch)(3, **ctor)
+        out[variant_key(arch, ctor)] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
     with open(os.path.join(GOLDEN, 'state_dict_keys.json'), 'w') as f:
         json.dump(out, f)
     print('keys: ok', {k: len(v) for k, v in out.items()})
@@ -209,7 +281,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     cd = ref_shim.import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    which = sys.argv[1:] or ['keys', 'f2c', 'tiling', 'models', 'apply']
+    which = sys.argv[1:] or ['keys', 'f2c', 'tiling', 'models', 'variants', 'apply']
     if 'keys' in which:
         mint_keys(cd)
     if 'f2c' in which:
@@ -219,6 +291,9 @@ def main():
     if 'models' in which:
         for case in MODEL_CASES:
             mint_model_case(cd, *case)
+    if 'variants' in which:
+        for case in VARIANT_CASES:
+            mint_variant_case(cd, *case)
     if 'apply' in which:
         mint_apply_model(cd)
 

@@ -25,11 +25,22 @@ def key_spec(arch):
     return OrderedDict((k, tuple(s)) for k, s in keys)
 
 
+VARIANT_FIXTURES = ['model_cpnu22_c4_unc_b6', 'model_cpnresnext101unet_unc_b4', 'model_cpnresnet18fpn_c3_b2']
+
+
+def fixture_ctor(z):
+    """(constructor kwargs, attributes set after construction) of a variant fixture ({} / {} for the default models)."""
+    if 'ctor' not in z.files:
+        return {}, {}
+    return json.loads(str(z['ctor'])), json.loads(str(z['attrs']))
+
+
 def fixture_state_dict(z, arch, seed):
     """Rebuild the exact state_dict a fixture was minted with: seeded synthetic weights + stored calibrated heads."""
-    sd = synth_state_dict(key_spec(arch), seed=seed)
-    for k in CALIB_KEYS:
-        sd[k] = torch.from_numpy(np.array(z['calib/' + k]))
+    sd = synth_state_dict(key_spec(str(z['spec_key']) if 'spec_key' in z.files else arch), seed=seed)
+    for f in z.files:
+        if f.startswith('calib/'):
+            sd[f[len('calib/'):]] = torch.from_numpy(np.array(z[f]))
     return sd
 
 

@@ -11,7 +11,8 @@ import torch
 import celldetection_b200 as cd
 import cpn_oracle as orc
 from conftest import ROOT
-from helpers import load_npz, fixture_state_dict, rel_err, match_by_box, MODEL_FIXTURES
+from helpers import (load_npz, fixture_state_dict, fixture_ctor, rel_err, match_by_box, MODEL_FIXTURES,
+                     VARIANT_FIXTURES)
 
 pytestmark = pytest.mark.gpu
 REPORT = os.path.join(ROOT, 'gpurun_out', 'parity_report.json')
@@ -31,8 +32,11 @@ def _report(key, val):
 def _model(z, precision):
     arch = str(z['arch'])
     n, h, w, seed, order, samples = [int(v) for v in z['meta']]
-    m = getattr(cd.models, arch)(3, order=order, samples=samples, precision=precision)
+    ctor, attrs = fixture_ctor(z)
+    m = getattr(cd.models, arch)(3, order=order, samples=samples, precision=precision, **ctor)
     m.load_state_dict(fixture_state_dict(z, arch, seed))
+    for k, v in attrs.items():
+        setattr(m, k, v)
     return m.cuda(), (n, h, w)
 
 
@@ -281,3 +285,43 @@ def test_full_size_c3_tile_fp16x3_against_oracle():
     for k, e in errs.items():
         assert e < 1e-3, (k, e)
     assert len(out['scores'][0]) == len(want['scores'][0]) > 0
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'fp16x3'])
+@pytest.mark.parametrize('name', VARIANT_FIXTURES)
+def test_variant_models_match_reference(name, precision):
+    """classes > 2 (softmax / argmax scoring), uncertainty head (certainty filter, uncertainty_nms, box_uncertainties)
+    and bucketed refinement through the whole model: head tensors within 1e-3 rel of the reference (incl. the sigmoid
+    uncertainty map), identical instance counts and classes, contour vertices of matched instances within 0.5 px
+    (fp32) / decoded vertices within 0.5 px and >= 95 % of refined vertices within 0.5 px (fp16x3)."""
+    z = load_npz(name)
+    m, (n, h, w) = _model(z, precision)
+    x = torch.from_numpy(z['x']).cuda()
+    raw = m.core_forward(x)
+    keys = ['scores', 'locations', 'refinement', 'fourier'] + (['uncertainty'] if 'raw_uncertainty' in z.files else [])
+    errs = {k: rel_err(raw[k].cpu().numpy(), z['raw_' + k]) for k in keys}
+    _report(f'{name}/{precision}/raw_rel_err', errs)
+    for k, e in errs.items():
+        assert e < 1e-3, (k, e)
+    kw = dict(offsets=torch.from_numpy(z['offsets']).cuda()) if 'offsets' in z.files else {}
+    out = m(x, **kw)
+    st = _compare_outputs(out, z, n)
+    _report(f'{name}/{precision}/outputs', st)
+    if precision == 'fp32':
+        assert st['count'] == st['ref_count'] == st['matched'], st
+        assert st['max_vertex_err'] < 0.5, st
+    else:
+        for c, r, mt in zip(st['count'], st['ref_count'], st['matched']):
+            assert abs(c - r) <= max(1, 0.05 * r) and mt >= 0.9 * r, st
+        assert st['max_proposal_err'] < 0.5, st
+        assert st['vertices_within_half_px'] >= 0.95 * st['vertices'], st
+    for i in range(n):
+        pairs = match_by_box(out['boxes'][i].cpu().numpy(), z[f'out/{i}/boxes'])
+        ia, ib = [a for a, _ in pairs], [b for _, b in pairs]
+        assert np.array_equal(out['classes'][i].cpu().numpy()[ia], z[f'out/{i}/classes'][ib])
+        assert np.abs(out['scores'][i].cpu().numpy()[ia] - z[f'out/{i}/scores'][ib]).max() < 2e-3
+        if 'raw_uncertainty' in z.files:
+            assert out['box_uncertainties'][i].shape == (len(out['scores'][i]), 4)
+            assert np.abs(out['box_uncertainties'][i].cpu().numpy()[ia] - z[f'out/{i}/box_uncertainties'][ib]).max() < 2e-3
+        else:
+            assert out['box_uncertainties'] is None

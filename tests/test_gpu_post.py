@@ -6,7 +6,7 @@ import torch
 
 import celldetection_b200 as cd
 import cpn_oracle as orc
-from helpers import load_npz, rel_err, MODEL_FIXTURES
+from helpers import load_npz, rel_err, fixture_ctor, MODEL_FIXTURES, VARIANT_FIXTURES
 
 pytestmark = pytest.mark.gpu
 
@@ -38,6 +38,46 @@ def test_post_chain_on_reference_head_tensors(name):
         assert np.abs(out['scores'][i].cpu().numpy() - z[f'out/{i}/scores']).max() < 1e-6
         assert np.array_equal(out['classes'][i].cpu().numpy(), z[f'out/{i}/classes'])
     assert out['box_uncertainties'] is None
+
+
+@pytest.mark.parametrize('name', VARIANT_FIXTURES)
+def test_post_chain_variants_on_reference_head_tensors(name):
+    """Softmax / argmax selection, certainty filter, uncertainty-weighted NMS and bucketed refinement on the
+    *reference's* head tensors: identical selection / keep sets / classes, values within 1e-4 px."""
+    z = load_npz(name)
+    ctor, attrs = fixture_ctor(z)
+    m, (n, h, w, order, samples) = _post_model(z, **ctor)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    rs = torch.from_numpy(z['raw_scores'])
+    scores = (rs[:, 0] if rs.shape[1] == 1 else rs.permute(0, 2, 3, 1)).contiguous().cuda()
+    locfou = torch.cat((torch.from_numpy(z['raw_locations']), torch.from_numpy(z['raw_fourier'])), 1)
+    locfou = locfou.permute(0, 2, 3, 1).contiguous().cuda()
+    ref = torch.from_numpy(z['raw_refinement']).permute(0, 2, 3, 1).contiguous().cuda()
+    unc = None
+    if 'raw_uncertainty' in z.files:
+        unc = torch.from_numpy(z['raw_uncertainty']).permute(0, 2, 3, 1).contiguous().cuda()
+    offsets = torch.from_numpy(z['offsets']).cuda() if 'offsets' in z.files else None
+    out = m.post(scores, locfou, ref, (h, w), offsets=offsets, uncertainty=unc)
+    nonms = m.post(scores, locfou, ref, (h, w), nms=False, uncertainty=unc)
+    keys = ['contours', 'boxes', 'locations', 'fourier', 'contour_proposals']
+    for i in range(n):
+        assert len(nonms['scores'][i]) == int(z[f'nonms_count/{i}'])
+        assert len(out['scores'][i]) == len(z[f'out/{i}/scores']) > 0
+        for k in keys:
+            assert np.abs(out[k][i].cpu().numpy() - z[f'out/{i}/{k}']).max() < 1e-4, (k, i)
+        assert np.abs(out['scores'][i].cpu().numpy() - z[f'out/{i}/scores']).max() < 1e-6
+        assert np.array_equal(out['classes'][i].cpu().numpy(), z[f'out/{i}/classes'])
+        if unc is not None:
+            assert np.abs(out['box_uncertainties'][i].cpu().numpy() - z[f'out/{i}/box_uncertainties']).max() < 1e-7
+    if unc is None:
+        assert out['box_uncertainties'] is None
+    # the certainty filter is a runtime attribute (cpn.py:617-618): turning it off can only add proposals
+    if unc is not None and m.certainty_thresh is not None:
+        m.certainty_thresh = None
+        more = m.post(scores, locfou, ref, (h, w), nms=False, uncertainty=unc)
+        assert all(len(a) >= len(b) for a, b in zip(more['scores'], nonms['scores']))
+        assert sum(len(a) for a in more['scores']) > sum(len(b) for b in nonms['scores'])
 
 
 def test_post_chain_runtime_attributes_and_edge_cases():

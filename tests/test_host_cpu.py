@@ -15,7 +15,7 @@ from celldetection_b200 import _lib
 from celldetection_b200.models import graph as G
 from celldetection_b200.models import plan as PL
 from conftest import ROOT
-from helpers import key_spec, load_npz
+from helpers import key_spec, load_npz, fixture_ctor, VARIANT_FIXTURES
 
 
 @pytest.mark.parametrize('arch', G.ARCHS)
@@ -26,6 +26,32 @@ def test_state_dict_keys_match_reference(arch):
     got = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
     assert [k for k, _ in got] == list(want.keys())
     assert got == list(want.items())
+
+
+@pytest.mark.parametrize('name', VARIANT_FIXTURES)
+def test_variant_state_dict_keys_match_reference(name):
+    """classes > 2 / uncertainty_head / refinement_buckets change the head widths and add ``core.uncertainty_head``
+    between the fourier and refinement heads (models/cpn.py:177-234): keys, order and shapes as the reference."""
+    z = load_npz(name)
+    ctor, attrs = fixture_ctor(z)
+    model = getattr(cd.models, str(z['arch']))(3, **ctor)
+    want = key_spec(str(z['spec_key']))
+    got = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    assert got == list(want.items())
+    for k, v in attrs.items():
+        assert hasattr(model, k)
+
+
+def test_bucket_table_matches_reference_formula():
+    """ops/cpn.py:238-255 on the default sampling: indices in [0, B), weights >= 0 and summing to 1 per sample."""
+    from celldetection_b200.ops.cpn import bucket_table
+    for samples, buckets in ((32, 2), (32, 6), (64, 4), (128, 12)):
+        idx, w = bucket_table(samples, buckets, 'cpu')
+        assert idx.shape == w.shape == (samples, 3) and idx.dtype == torch.int32
+        assert int(idx.min()) >= 0 and int(idx.max()) < buckets
+        assert float(w.min()) >= 0 and torch.allclose(w.sum(1), torch.ones(samples), atol=1e-6)
+        t = torch.linspace(0, 1.0, samples) * buckets
+        assert torch.equal(idx[:, 1].long(), t.long() % buckets)
 
 
 def test_library_exports_every_declared_symbol():
@@ -53,7 +79,9 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError):
         cd.ops.cpn.fouriers2contours(torch.zeros(3, 5, 4), torch.zeros(3, 2))
     with pytest.raises(NotImplementedError):
-        cd.models.CpnU22(3, classes=3)
+        cd.models.CpnU22(3, backbone_kwargs=dict(depth=4))
+    with pytest.raises(NotImplementedError):
+        cd.models.CpnU22(3).train()(torch.rand(1, 3, 64, 64), targets={})
 
 
 def test_graph_flop_census():

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import cpn_oracle as orc
-from helpers import load_npz, fixture_state_dict, rel_err, MODEL_FIXTURES
+from helpers import load_npz, fixture_state_dict, fixture_ctor, rel_err, MODEL_FIXTURES, VARIANT_FIXTURES
 
 
 @pytest.mark.parametrize('name', MODEL_FIXTURES)
@@ -39,6 +39,39 @@ def test_oracle_model_matches_reference_golden(name):
                          samples=samples, nms_on=False)
     for i in range(n):
         assert len(nonms['scores'][i]) == int(z[f'nonms_count/{i}'])
+
+
+@pytest.mark.parametrize('name', VARIANT_FIXTURES)
+def test_oracle_variant_models_match_reference_golden(name):
+    """classes > 2 (softmax / argmax), uncertainty head (certainty filter, uncertainty_nms, box_uncertainties) and
+    bucketed refinement: oracle vs vectors minted from the reference (models/cpn.py:73-82, 583-585, 617-618, 723-726)."""
+    z = load_npz(name)
+    arch = str(z['arch'])
+    n, h, w, seed, order, samples = [int(v) for v in z['meta']]
+    ctor, attrs = fixture_ctor(z)
+    sd = fixture_state_dict(z, arch, seed)
+    x = torch.from_numpy(z['x'])
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        raw = orc.cpn_core5(x, sd, arch)
+    for nm, t in zip(('scores', 'locations', 'refinement', 'fourier', 'uncertainty'), raw):
+        if t is not None:
+            assert rel_err(t, z['raw_' + nm]) < 1e-5, nm
+    assert (raw[4] is not None) == bool(ctor.get('uncertainty_head'))
+    assert raw[2].shape[1] == 2 * ctor.get('refinement_buckets', 1)
+    unc = torch.from_numpy(z['raw_uncertainty']) if 'raw_uncertainty' in z.files else None
+    offsets = torch.from_numpy(z['offsets']) if 'offsets' in z.files else None
+    out = orc.cpn_post(torch.from_numpy(z['raw_scores']), torch.from_numpy(z['raw_locations']),
+                       torch.from_numpy(z['raw_refinement']), torch.from_numpy(z['raw_fourier']), (h, w), order=order,
+                       samples=samples, offsets=offsets, uncertainty=unc, **attrs)
+    keys = ['contours', 'boxes', 'scores', 'locations', 'fourier', 'contour_proposals']
+    if unc is not None:
+        keys.append('box_uncertainties')
+    for i in range(n):
+        assert len(out['scores'][i]) == len(z[f'out/{i}/scores']) > 0
+        for k in keys:
+            assert rel_err(out[k][i].numpy(), z[f'out/{i}/{k}']) < 1e-6, (k, i)
+        assert np.array_equal(out['classes'][i].numpy(), z[f'out/{i}/classes'])
 
 
 def test_oracle_fouriers2contours_golden():
