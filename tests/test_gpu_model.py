@@ -15,7 +15,7 @@ from helpers import (load_npz, fixture_state_dict, fixture_ctor, rel_err, match_
                      VARIANT_FIXTURES)
 
 pytestmark = pytest.mark.gpu
-REPORT = os.path.join(ROOT, 'gpurun_out', 'parity_report.json')
+REPORT = os.environ.get('CPN_PARITY_REPORT') or os.path.join(ROOT, 'gpurun_out', 'parity_report.json')
 
 
 def _report(key, val):
