@@ -60,6 +60,7 @@ SYMBOLS = {
     'cpn_select_write': (_I, [_P, _P, _P, _I, _I64, _F, _P, _P, _P, _I64, _P, _P]),
     'cpn_select_count_ex': (_I, [ctypes.POINTER(SelectParams), _I64, _P, _P, _P]),
     'cpn_select_write_ex': (_I, [ctypes.POINTER(SelectParams), _I, _I64, _P, _P, _P, _P, _I64, _P, _P]),
+    'cpn_resize_bilinear': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),
     'cpn_nms_weights': (_I, [_P, _P, _P, _I64, _P, _P]),
     'cpn_decode_refine_buckets': (_I, [_P, _I64, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P,
                                        _P, _P, _P, _P]),
@@ -69,6 +70,8 @@ SYMBOLS = {
     'cpn_nms_segments': (_I, [_P, _P, _P, _I, _I64, _F, _I, _P, _P, _P, _P]),
     'cpn_nms_grid_workspace_bytes': (_SZ, [_I64]),
     'cpn_nms_grid': (_I, [_P, _P, _I64, _F, _P, _P, _P, ctypes.POINTER(_I), _P]),
+    'cpn_box_votes_workspace_bytes': (_SZ, [_I64]),
+    'cpn_box_votes': (_I, [_P, _I64, _F, _P, _P, _P]),
     'cpn_border_filter': (_I, [_P, _P, _P, _I64, _I, _F, _P, _P]),
     'cpn_gather_rows': (_I, [_P, _I64, _P, _I64, _P, _P]),
 }

@@ -258,18 +258,35 @@ __device__ __forceinline__ int split_pass_order(int i, int lofirst) { return lof
 // Either the fused ReadOut projection (p.nproj > 0) or bias / residual / ReLU / fp16 store of every other 32-column
 // chunk (`half` selects which of the two warps of a lane quadrant this is).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int BN>
+// Residual row of output pixel (img, y, x) at channel n0 (nullptr: no residual / pixel outside the image).  A residual
+// of a different spatial size is read through the nearest-neighbour index map (torchvision FPN top-down path).
+__device__ __forceinline__ const __half* residual_row(const ConvTcParams& p, const int img, const int y, const int x,
+                                                      const int n0) {
+  if (!p.res || y >= p.Ho || x >= p.Wo) return nullptr;
+  const int ry = (p.res_h == p.Ho) ? y : (int)(((long long)y * p.res_h) / p.Ho);
+  const int rx = (p.res_w == p.Wo) ? x : (int)(((long long)x * p.res_w) / p.Wo);
+  return p.res + (((long long)img * p.res_h + ry) * p.res_w + rx) * p.res_pitch + n0;
+}
+
+// The 32 residual halves (hi part) of one 32-column chunk: four 16-byte loads.
+struct ResChunk { uint4 v[4]; };
+__device__ __forceinline__ void load_res_chunk(const __half* rp, const int ch, ResChunk& r) {
+  const uint4* q = reinterpret_cast<const uint4*>(rp + ch * 32);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.v[i] = __ldg(q + i);
+}
+
+// PF: software-pipelined residual loads -- `rfirst` holds the residual of this warp's first chunk (loaded by the caller
+// BEFORE it waited for the accumulator: the residual does not depend on the MMAs), and the next chunk's residual is
+// requested before the current chunk's TMEM load is awaited.  Without it the epilogue of a 1x1 + residual layer, whose
+// mainloop is only 4-16 K blocks long, exposed one global-memory latency per chunk and ran longer than the mainloop.
+template <int BN, bool PF>
 __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint32_t taddr, const int img, const int y,
                                               const int x, const int n_tile, const int n0, const int half,
-                                              const float* proj_w) {
+                                              const float* proj_w, const ResChunk* rfirst = nullptr) {
   const bool valid = (y < p.Ho) && (x < p.Wo);
   __half* op = p.out + (((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0;
-  const __half* rp = nullptr;
-  if (p.res && valid) {
-    const int ry = (p.res_h == p.Ho) ? y : (int)(((long long)y * p.res_h) / p.Ho);
-    const int rx = (p.res_w == p.Wo) ? x : (int)(((long long)x * p.res_w) / p.Wo);
-    rp = p.res + (((long long)img * p.res_h + ry) * p.res_w + rx) * p.res_pitch + n0;
-  }
+  const __half* rp = residual_row(p, img, y, x, n0);
   if (p.nproj > 0) {
     // ---- fused ReadOut: bias + ReLU on the fp32 accumulators, then the 1x1 projection of this N tile's head ----
     const ProjHead& H = p.proj[n_tile];
@@ -329,24 +346,32 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
       }
     }
   } else {
+  ResChunk rc;
+  if (PF && rp) rc = *rfirst;
 #pragma unroll 1
   for (int ch = half; ch < BN / 32; ch += 2) {
     uint32_t v[32];
     tmem_ld32(taddr + ch * 32, v);
+    ResChunk rn;
+    if (rp) {
+      if (!PF) load_res_chunk(rp, ch, rc);
+      else if (ch + 2 < BN / 32) load_res_chunk(rp, ch + 2, rn);   // next chunk's residual while TMEM is being read
+    }
     tmem_ld_wait();
     if (valid) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
       uint4 packed[4], packed_lo[4];
       uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
       uint32_t* pl = reinterpret_cast<uint32_t*>(packed_lo);
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(rc.v);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float4 b = p.bias ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         float f0 = __uint_as_float(v[q * 4 + 0]) + b.x, f1 = __uint_as_float(v[q * 4 + 1]) + b.y;
         float f2 = __uint_as_float(v[q * 4 + 2]) + b.z, f3 = __uint_as_float(v[q * 4 + 3]) + b.w;
         if (rp) {
-          const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp + ch * 32 + q * 4));
-          const __half2 r0 = *reinterpret_cast<const __half2*>(&rr.x), r1 = *reinterpret_cast<const __half2*>(&rr.y);
+          const __half2 r0 = *reinterpret_cast<const __half2*>(&rw[q * 2]);
+          const __half2 r1 = *reinterpret_cast<const __half2*>(&rw[q * 2 + 1]);
           f0 += __low2float(r0); f1 += __high2float(r0); f2 += __low2float(r1); f3 += __high2float(r1);
           if (p.split) {   // residual = hi + lo
             const uint2 rl = __ldg(reinterpret_cast<const uint2*>(rp + p.res_lo + ch * 32 + q * 4));
@@ -374,6 +399,7 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
         for (int q = 0; q < 4; ++q) l4[q] = packed_lo[q];
       }
     }
+    if (PF) rc = rn;
   }
   }
 }
@@ -382,7 +408,9 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
 // Kernel
 // ---------------------------------------------------------------------------------------------------------------------
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p, int stages) {
+// __maxnreg__ instead of __launch_bounds__(TC_THREADS, 1): ptxas caps the latter at 168 registers (it budgets for 384
+// threads), which spills the pipelined residual registers; 320 threads x 192 allocated registers fit the 64 K file.
+__global__ void __maxnreg__(200) conv_tc_kernel(const __grid_constant__ ConvTcParams p, int stages) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -527,10 +555,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
       const int y = (t_in / p.tiles_x) * TC_BH + py, x = (t_in % p.tiles_x) * TC_BW + px;
       const int n0 = n_tile * BN;
+      ResChunk rfirst;
+      {   // residual of the first chunk: requested while the MMAs of this tile are still running
+        const __half* rp0 = residual_row(p, img, y, x, n0);
+        if (rp0) load_res_chunk(rp0, half, rfirst);
+      }
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * BN;
-      epilogue_rows<BN>(p, taddr, img, y, x, n_tile, n0, half, proj_w);
+      epilogue_rows<BN, true>(p, taddr, img, y, x, n_tile, n0, half, proj_w, &rfirst);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
@@ -763,7 +796,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
 #pragma unroll 1
         for (int j = 0; j < MSUB; ++j) {
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * MSUB + j) * BN);
-          epilogue_rows<BN>(p, taddr, img, y, xb + 8 * j, n_tile, n_tile * BN, half, proj_w);
+          epilogue_rows<BN, false>(p, taddr, img, y, xb + 8 * j, n_tile, n_tile * BN, half, proj_w);
         }
         tc_fence_before();
         __syncwarp();

@@ -572,3 +572,95 @@ extern "C" int cpn_nms_grid(const float* boxes, const float* scores, int64_t n_b
   if (rounds_host) *rounds_host = rounds;
   return 0;
 }
+
+// =====================================================================================================================
+// Box voting (ensembles): cd.ops.filter_by_box_voting / get_iou_voting, ops/boxes.py:53-83, as called by
+// cpn_inference.py:419-424.   votes[i] = sum_j iou(i, j) * (iou(i, j) > thr)   over ALL boxes j including i itself
+// (torchvision box_iou arithmetic: inter / (area_i + area_j - inter)).  The reference builds the dense K x K matrix; here
+// only the 3x3 neighbouring cells of the same uniform grid the stitch NMS uses are visited -- every other pair has
+// inter = 0 and contributes an exact zero.  A zero-area box has iou(i, i) = 0/0 = NaN and therefore a NaN vote, like the
+// reference (NaN * False = NaN).
+// =====================================================================================================================
+namespace cpn {
+
+__global__ void votes_cellkeys_kernel(const float4* __restrict__ boxes, int n, const GridInfo* __restrict__ gi,
+                                      uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const GridInfo g = *gi;
+  const int c = cell_of(g, boxes[r], nullptr, nullptr);
+  keys[r] = ((uint64_t)(uint32_t)c << 32) | (uint32_t)r;
+  vals[r] = r;
+}
+
+__global__ void votes_kernel(const float4* __restrict__ boxes, const uint64_t* __restrict__ cell_keys,
+                             const int32_t* __restrict__ cell_rows, int n, const GridInfo* __restrict__ gi, float thr,
+                             float* __restrict__ votes) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const GridInfo g = *gi;
+  const float4 b = boxes[r];
+  const float area = (b.z - b.x) * (b.w - b.y);
+  int cx, cy;
+  cell_of(g, b, &cx, &cy);
+  float sum = 0.f;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = cy + dy;
+    if (yy < 0 || yy >= g.ncy) continue;
+    const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, g.ncx - 1);
+    const uint64_t k_lo = (uint64_t)(uint32_t)(yy * g.ncx + x_lo) << 32;
+    const uint64_t k_hi = (uint64_t)(uint32_t)(yy * g.ncx + x_hi + 1) << 32;
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cell_keys[mid] < k_lo) lo = mid + 1; else hi = mid; }
+    for (int q = lo; q < n && cell_keys[q] < k_hi; ++q) {
+      const float4 c = boxes[cell_rows[q]];
+      const float xx1 = fmaxf(b.x, c.x), yy1 = fmaxf(b.y, c.y), xx2 = fminf(b.z, c.z), yy2 = fminf(b.w, c.w);
+      const float inter = fmaxf(0.f, xx2 - xx1) * fmaxf(0.f, yy2 - yy1);
+      const float iou = inter / (area + (c.z - c.x) * (c.w - c.y) - inter);
+      sum = sum + iou * (iou > thr ? 1.f : 0.f);       // iou *= iou > thresh; NaN stays NaN
+    }
+  }
+  votes[r] = sum;
+}
+
+}  // namespace cpn
+
+extern "C" size_t cpn_box_votes_workspace_bytes(int64_t n_boxes) { return cpn_nms_grid_workspace_bytes(n_boxes); }
+
+extern "C" int cpn_box_votes(const float* boxes, int64_t n_boxes, float iou_threshold, void* workspace, float* votes,
+                             void* stream) {
+  CPN_REQUIRE(n_boxes < (1ll << 31), "box_votes: too many boxes");
+  if (n_boxes <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = (int)n_boxes;
+  const size_t nn = (size_t)n;
+  char* b = reinterpret_cast<char*>(workspace);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = b + off; off += align_up(bytes, 256); return p; };
+  uint64_t* keys_a = (uint64_t*)take(nn * 8);
+  uint64_t* cell_keys = (uint64_t*)take(nn * 8);
+  int32_t* vals_a = (int32_t*)take(nn * 4);
+  int32_t* cell_rows = (int32_t*)take(nn * 4);
+  int* small = (int*)take(2048);
+  GridInfo* gi = reinterpret_cast<GridInfo*>(reinterpret_cast<char*>(small) + 64);
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, n, 0, 64, st);
+  void* cub_tmp = take(cub_bytes + 256);
+  const int tb = 256, gb = (n + tb - 1) / tb;
+  const int ext_init[5] = {0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+  CPN_CHECK_CUDA(cudaMemcpyAsync(small, ext_init, sizeof(ext_init), cudaMemcpyHostToDevice, st));
+  grid_extent_kernel<<<capped_blocks(gb), tb, 0, st>>>(reinterpret_cast<const float4*>(boxes), n, small);
+  CPN_CHECK_LAUNCH();
+  grid_setup_kernel<<<1, 32, 0, st>>>(small, gi);
+  CPN_CHECK_LAUNCH();
+  votes_cellkeys_kernel<<<gb, tb, 0, st>>>(reinterpret_cast<const float4*>(boxes), n, gi, keys_a, vals_a);
+  CPN_CHECK_LAUNCH();
+  size_t cb = cub_bytes + 256;
+  CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_a, cell_keys, vals_a, cell_rows, n, 0, 64, st));
+  count_launch(4);
+  votes_kernel<<<gb, tb, 0, st>>>(reinterpret_cast<const float4*>(boxes), cell_keys, cell_rows, n, gi, iou_threshold,
+                                  votes);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}

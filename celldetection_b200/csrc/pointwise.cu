@@ -2,6 +2,7 @@
 // bilinear resampling and the ReadOut projection.  All are HBM-bound element-wise / gather work: coalesced along the
 // channel axis, 8-byte or 16-byte vector accesses where the pitch allows, grid sized in multiples of the SM count.
 #include "common.cuh"
+#include <cstring>
 
 namespace cpn {
 
@@ -571,3 +572,18 @@ int proj_launch(const cpn_op_t& op, const void* src, void* dst, const float* wgt
 }
 
 }  // namespace cpn
+
+// F.interpolate(x, size, mode='bilinear', align_corners=False) on a stand-alone fp32 NHWC tensor: the resize of the
+// score bounds in _apply_score_bounds / _equal_size (models/cpn.py:109-123; c == 1 makes NHWC and NCHW coincide).
+extern "C" int cpn_resize_bilinear(const float* src, int n, int h, int w, int c, float* dst, int ho, int wo,
+                                   void* stream) {
+  CPN_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c > 0 && ho > 0 && wo > 0, "resize_bilinear: bad arguments");
+  cpn_op_t op;
+  memset(&op, 0, sizeof(op));
+  op.kind = CPN_OP_BILINEAR;
+  op.src.n = op.dst.n = n; op.src.c = op.dst.c = c; op.src.pitch = op.dst.pitch = c;
+  op.src.h = h; op.src.w = w; op.dst.h = ho; op.dst.w = wo;
+  op.src.dtype = op.dst.dtype = CPN_DT_F32;
+  return cpn::bilinear_launch(op, src, dst, (cudaStream_t)stream);
+}
+

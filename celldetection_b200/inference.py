@@ -21,6 +21,7 @@ import torch
 
 from . import _lib as L
 from .ops import cpn as O
+from .ops.boxes import filter_by_box_voting
 
 __all__ = ['get_tiling_slices', 'apply_model', 'cpn_inference']
 
@@ -60,19 +61,17 @@ def _dist():
     return None, 0, 1
 
 
-REC_KEYS = ('contours', 'boxes', 'scores', 'classes', 'locations', 'fourier', 'contour_proposals', 'order_key')
-
-
 def pack_records(res: OrderedDict):
-    """Flat per-detection float32 records [K, L] (classes are stored as float; exact for small ints)."""
+    """Flat per-detection float32 records [K, L] of every key of ``res`` (classes are stored as float; exact for
+    small ints).  Returns (records, [(key, width), ...])."""
     K = int(res['scores'].shape[0])
-    cols = [res[k].reshape(K, -1).float() for k in REC_KEYS]
-    return torch.cat(cols, 1).contiguous(), [c.shape[1] for c in cols]
+    cols = [(k, v.reshape(K, -1).float()) for k, v in res.items()]
+    return torch.cat([c for _, c in cols], 1).contiguous(), [(k, c.shape[1]) for k, c in cols]
 
 
 def unpack_records(rec, widths, like: OrderedDict):
     out, o = OrderedDict(), 0
-    for k, wd in zip(REC_KEYS, widths):
+    for k, wd in widths:
         v = rec[:, o:o + wd]
         o += wd
         shape = (rec.shape[0],) + tuple(like[k].shape[1:])
@@ -118,45 +117,46 @@ def _to_rgb(img):
     return img
 
 
-@torch.no_grad()
-def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size=(768, 768), strides=(384, 384),
-                reps=1, transforms=None, model_kwargs_list=None, batch_size=1, num_workers=0, pin_memory=False,
-                border_removal=4, min_vote=1, stitching_rule='nms', verbose=False, device=None, **kwargs):
-    """cpn_inference.py:311-429.  ``img``: uint8 or float ``Array[h, w, (c)]``; ``models``: a ``CPN`` instance or a
-    list of them.  Returns the flat dict of concatenated tensors (contours, boxes, scores, classes, locations,
-    fourier, contour_proposals) after border removal and global NMS -- identical on every rank when distributed."""
-    if not isinstance(models, (list, tuple)):
-        models = [models]
-    assert len(models) >= 1, 'Please specify at least one model.'
-    if min_vote != 1 or len(models) > 1:
-        raise NotImplementedError('model ensembles / box voting are outside the accelerated path (SURVEY 8f-4).')
-    if mask is not None or point_mask is not None or transforms is not None or reps != 1:
-        raise NotImplementedError('masks, point masks and test-time transforms are outside the accelerated path.')
-    rules = stitching_rule.split(',')
-    if any(r not in ('nms', 'ex_br') for r in rules):
-        raise ValueError(f'Unknown stitching rule: {stitching_rule}')
-    model = models[0]
-    dev = torch.device(device) if device is not None else model.device
-    if dev.type != 'cuda':
-        raise RuntimeError('apply_model needs the model on a CUDA device')
-    if not isinstance(crop_size, (tuple, list)):
-        crop_size = (crop_size,) * 2
-    if not isinstance(strides, (tuple, list)):
-        strides = (strides,) * 2
-    img = _to_rgb(np.asarray(img))
-    if img.dtype.kind == 'f':
-        img = img.astype(np.float32)
-    elif img.dtype != np.uint8:
-        raise ValueError('image must be uint8 or floating point')
+def _tile_bounds(mask, point_mask, point_mask_exclusive, sl):
+    """TileLoader.__getitem__ (cpn_inference.py:93-111): score bounds of one tile, or ``False`` if the tile is skipped
+    (empty mask / point-mask crop).  Returns (upper [th,tw,1] | None, lower | None)."""
+    upper = lower = None
+    if mask is not None:
+        crop = mask[sl]
+        if not np.any(crop):
+            return False
+        upper = (crop[..., None] if crop.ndim == 2 else crop).astype('float32')
+    if point_mask is not None:
+        crop = point_mask[sl]
+        if not np.any(crop):
+            return False
+        lower = np.clip(crop[..., None] if crop.ndim == 2 else crop, 0., 1.).astype('float32')
+        if point_mask_exclusive:
+            upper = lower
+    return upper, lower
+
+
+def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size, strides, batch_size, border_removal,
+                  rules, stitching_rule, nms_thresh, dev):
+    """One model over all tiles of ``img`` (this rank's share), border removal, exchange, stitch NMS
+    (cpn_inference.py:354-411)."""
     H, W = img.shape[:2]
     slices, overlaps, (h_tiles, w_tiles) = get_tiling_slices((H, W), tuple(crop_size), tuple(strides),
                                                              return_overlaps=True)
     slices, overlaps = list(slices), list(overlaps)
     ex_br = float(stitching_rule != 'nms' and 'ex_br' in rules)
     dist, rank, world = _dist()
-    mine = list(range(rank, len(slices), world))
+    bounds = {}
+    todo = list(range(len(slices)))
+    if mask is not None or point_mask is not None:      # tiles with an empty (point-)mask crop are never inferred
+        todo = []
+        for t in range(len(slices)):
+            bnd = _tile_bounds(mask, point_mask, point_mask_exclusive, slices[t])
+            if bnd is not False:
+                bounds[t] = bnd
+                todo.append(t)
+    mine = todo[rank::world]
     th, tw = (slices[0][0].stop - slices[0][0].start), (slices[0][1].stop - slices[0][1].start)
-    nms_thresh = kwargs.get('nms_thresh', model.nms_thresh)
     is_u8 = img.dtype == np.uint8
     C = img.shape[-1]
     # double-buffered pinned staging
@@ -196,10 +196,16 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
             # the other staging slot was consumed two batches ago (its copy finished before the previous forward)
             nxt = pool.submit(load_in_thread, bi + 1, (bi + 1) % 2)
         offs = torch.tensor([[slices[t][1].start, slices[t][0].start] for t in ids], dtype=torch.float32, device=dev)
+        kw = dict(offsets=offs)
+        if bounds:       # [B,1,th,tw] score bounds at input resolution (resized by the model, cpn.py:118-123)
+            for j, name in ((0, 'scores_upper_bound'), (1, 'scores_lower_bound')):
+                if bounds[ids[0]][j] is not None:
+                    b_np = np.stack([bounds[t][j][..., 0] for t in ids], 0)[:, None]
+                    kw[name] = torch.from_numpy(np.ascontiguousarray(b_np)).to(dev)
         if is_u8:
-            flat, counts = model.forward_flat(d, L.IN_U8_NHWC, offsets=offs)
+            flat, counts = model.forward_flat(d, L.IN_U8_NHWC, **kw)
         else:
-            flat, counts = model.forward_flat(d.permute(0, 3, 1, 2).contiguous(), L.IN_F32_NCHW, offsets=offs)
+            flat, counts = model.forward_flat(d.permute(0, 3, 1, 2).contiguous(), L.IN_F32_NCHW, **kw)
         K = int(sum(counts))
         if K == 0:
             continue
@@ -229,7 +235,10 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
         S, order = int(model.samples), int(min(model.order, model.core_order))
         z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
         res = OrderedDict(contours=z(0, S, 2), boxes=z(0, 4), scores=z(0), classes=z(0, dt=torch.long),
-                          locations=z(0, 2), fourier=z(0, order, 4), contour_proposals=z(0, S, 2), order_key=z(0, 2))
+                          locations=z(0, 2), fourier=z(0, order, 4), contour_proposals=z(0, S, 2))
+        if getattr(model, 'uncertainty_head', False):
+            res['box_uncertainties'] = z(0, 4)
+        res['order_key'] = z(0, 2)
     res = allgather_detections(res)
     if world > 1:
         res = canonical_order(res)      # 1-GPU and N-GPU runs feed the global NMS the same sequence
@@ -238,6 +247,62 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
         keep = O.nms(res['boxes'], res['scores'], nms_thresh)
         res = OrderedDict((k, v[keep]) for k, v in res.items())
     return res
+
+
+@torch.no_grad()
+def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size=(768, 768), strides=(384, 384),
+                reps=1, transforms=None, model_kwargs_list=None, batch_size=1, num_workers=0, pin_memory=False,
+                border_removal=4, min_vote=1, stitching_rule='nms', point_mask_exclusive=False, verbose=False,
+                device=None, **kwargs):
+    """cpn_inference.py:311-429.  ``img``: uint8 or float ``Array[h, w, (c)]``; ``models``: a ``CPN`` instance or a
+    list of them (an ensemble: every model is run over all tiles, the concatenated detections are filtered by
+    ``filter_by_box_voting(boxes, nms_thresh, min_vote)`` when ``min_vote > 1`` and de-duplicated by one more NMS,
+    :417-427).  ``mask`` / ``point_mask``: ``Array[h, w]`` upper / lower score bounds; tiles whose crop is empty are
+    skipped (TileLoader, :93-111).  Returns the flat dict of concatenated tensors (contours, boxes, scores, classes,
+    locations, fourier, contour_proposals[, box_uncertainties][, votes]) after border removal and global NMS --
+    identical on every rank when distributed."""
+    if not isinstance(models, (list, tuple)):
+        models = [models]
+    assert len(models) >= 1, 'Please specify at least one model.'
+    assert min_vote >= 1, f'Min vote smaller than minimum: {min_vote}'
+    assert len(models) >= min_vote, f'Min vote greater than number of models: {min_vote}'
+    if transforms is not None or reps != 1:
+        raise NotImplementedError('test-time transforms are outside the accelerated path.')
+    rules = stitching_rule.split(',')
+    if any(r not in ('nms', 'ex_br') for r in rules):
+        raise ValueError(f'Unknown stitching rule: {stitching_rule}')
+    dev = torch.device(device) if device is not None else models[0].device
+    if dev.type != 'cuda':
+        raise RuntimeError('apply_model needs the model on a CUDA device')
+    if not isinstance(crop_size, (tuple, list)):
+        crop_size = (crop_size,) * 2
+    if not isinstance(strides, (tuple, list)):
+        strides = (strides,) * 2
+    img = _to_rgb(np.asarray(img))
+    if img.dtype.kind == 'f':
+        img = img.astype(np.float32)
+    elif img.dtype != np.uint8:
+        raise ValueError('image must be uint8 or floating point')
+    mask = None if mask is None else np.asarray(mask)
+    point_mask = None if point_mask is None else np.asarray(point_mask)
+    results, nms_thresh = None, None
+    for model in models:
+        nms_thresh = kwargs.get('nms_thresh', model.nms_thresh)
+        res = _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size, strides, batch_size,
+                            border_removal, rules, stitching_rule, nms_thresh, dev)
+        if results is None:
+            results = res
+        else:                      # keys shared by all models (an uncertainty head may be missing in some)
+            results = OrderedDict((k, torch.cat((results[k], res[k]), 0)) for k in results if k in res)
+    # Remove duplicates from multi model (cpn_inference.py:417-427)
+    if len(models) > 1 and results['boxes'].shape[0] > 0:
+        if min_vote > 1:
+            keep, votes = filter_by_box_voting(results['boxes'], nms_thresh, min_vote, return_votes=True)
+            results = OrderedDict((k, v[keep.long()]) for k, v in results.items())
+            results['votes'] = votes
+        keep = O.nms(results['boxes'], results['scores'], nms_thresh)   # nms_thresh inherited from the last model
+        results = OrderedDict((k, v[keep]) for k, v in results.items())
+    return results
 
 
 def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, border_removal=4, stitching_rule='nms',
@@ -251,21 +316,22 @@ def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, bord
         inputs = [inputs]
     if isinstance(models, str):
         models = load_model(models)
-    model = models[0] if isinstance(models, (list, tuple)) else models
-    if model.device.type != 'cuda':
-        model = model.cuda()
-    if precision in ('32-true', 'fp32'):
-        model.precision = 'fp32'
-    elif precision in ('16-mixed', 'fp16', '16-true'):
-        model.precision = 'fp16'
-    if model_parameters:
-        for k, v in (model_parameters.items() if isinstance(model_parameters, dict) else
-                     [kv.split('=') for kv in model_parameters.split(',')]):
-            setattr(model, k.strip(), type(getattr(model, k.strip()))(v))
+    models = list(models) if isinstance(models, (list, tuple)) else [models]
+    for i, model in enumerate(models):
+        if model.device.type != 'cuda':
+            models[i] = model = model.cuda()
+        if precision in ('32-true', 'fp32'):
+            model.precision = 'fp32'
+        elif precision in ('16-mixed', 'fp16', '16-true'):
+            model.precision = 'fp16'
+        if model_parameters:
+            for k, v in (model_parameters.items() if isinstance(model_parameters, dict) else
+                         [kv.split('=') for kv in model_parameters.split(',')]):
+                setattr(model, k.strip(), type(getattr(model, k.strip()))(v))
     results = OrderedDict()
     for i, img in enumerate(inputs):
         if isinstance(img, str):
             raise NotImplementedError('file inputs need image I/O, which is outside the accelerated path')
-        results[i] = apply_model(img, [model], crop_size=tile_size, strides=stride, border_removal=border_removal,
+        results[i] = apply_model(img, models, crop_size=tile_size, strides=stride, border_removal=border_removal,
                                  stitching_rule=stitching_rule, batch_size=batch_size, verbose=verbose, **kwargs)
     return results if return_results else None

@@ -217,16 +217,18 @@ class CPN(nn.Module):
         st = L.stream_ptr()
         lo = up = None
         if scores_upper_bound is not None or scores_lower_bound is not None:
-            import torch.nn.functional as F  # bounds resize (cpn.py:118-123) -- input-side feature, not a hot kernel
-
-            def prep(bnd):
+            def prep(bnd):   # _apply_score_bounds / _equal_size (cpn.py:109-123): bilinear resize to the head resolution
                 if bnd is None:
                     return None
                 assert bnd.dtype.is_floating_point, 'score bounds must be floating point'
-                bnd = bnd.to(dev).float()
+                bnd = bnd.to(dev).float().contiguous()
+                assert bnd.dim() == 4 and bnd.shape[0] == n and bnd.shape[1] == 1, 'score bounds must be [N,1,h,w]'
                 if tuple(bnd.shape[2:]) != (h, w):
-                    bnd = F.interpolate(bnd, (h, w), mode='bilinear', align_corners=False)
-                return bnd.reshape(n, h, w).contiguous()
+                    out = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+                    L.check(lib.cpn_resize_bilinear(L.ptr(bnd), n, int(bnd.shape[2]), int(bnd.shape[3]), 1, L.ptr(out),
+                                                    h, w, st), 'resize_bilinear')
+                    return out
+                return bnd.reshape(n, h, w)
             lo, up = prep(scores_lower_bound), prep(scores_upper_bound)
         ws_key = (pixels, str(dev))
         ws = self._ws.get(ws_key)

@@ -175,6 +175,11 @@ int cpn_select_count_ex(const cpn_select_params_t* params_host, int64_t pixels, 
 int cpn_select_write_ex(const cpn_select_params_t* params_host, int n_images, int64_t hw, void* workspace, int32_t* idx,
                         float* score, int64_t* classes, int64_t capacity, int32_t* seg_offsets, void* stream);
 
+/* F.interpolate(mode='bilinear', align_corners=False) of a stand-alone fp32 NHWC tensor [n,h,w,c] -> [n,ho,wo,c]: the
+ * resize of scores_lower_bound / scores_upper_bound to the head resolution (_apply_score_bounds / _equal_size,
+ * models/cpn.py:109-123; with c == 1 the reference's [N,1,h,w] layout is the same memory). */
+int cpn_resize_bilinear(const float* src, int n, int h, int w, int c, float* dst, int ho, int wo, void* stream);
+
 /* NMS weights of models/cpn.py:723-726 (uncertainty_nms): out[i] = scores[i] * (1 - mean(uncertainty[idx[i], 0:4])). */
 int cpn_nms_weights(const float* scores, const float* uncertainty, const int32_t* idx, int64_t P, float* out,
                     void* stream);
@@ -229,6 +234,13 @@ int cpn_nms_segments(const float* boxes, const float* scores, const int32_t* seg
 size_t cpn_nms_grid_workspace_bytes(int64_t n_boxes);
 int cpn_nms_grid(const float* boxes, const float* scores, int64_t n_boxes, float iou_threshold, void* workspace,
                  int32_t* keep, int32_t* keep_count, int* rounds_host, void* stream);
+
+/* Box voting of model ensembles (cd.ops.filter_by_box_voting / get_iou_voting, ops/boxes.py:53-83, called by
+ * cpn_inference.py:419-424): votes[i] = sum over all boxes j (including i) of iou(i,j) * (iou(i,j) > iou_threshold),
+ * torchvision box_iou arithmetic.  Sparse: only boxes in neighbouring cells of a uniform grid are visited (all other
+ * pairs contribute exact zeros), O(n) memory.  The host keeps rows with votes >= min_vote. */
+size_t cpn_box_votes_workspace_bytes(int64_t n_boxes);
+int cpn_box_votes(const float* boxes, int64_t n_boxes, float iou_threshold, void* workspace, float* votes, void* stream);
 
 /* remove_border_contours (ops/cpn.py:258-290) as called by cpn_inference.py:375-380: keep[i] = 1 iff every vertex of
  * contour i satisfies the enabled side tests in tile-local coordinates (contours + (-offset)).

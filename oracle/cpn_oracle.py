@@ -24,7 +24,9 @@ oracle function        reference code it follows (relative to /root/reference/ce
 ``get_tiling_slices``  util/util.py:1305-1354
 ``remove_border_contours`` ops/cpn.py:258-290
 ``filter_contours_by_stitching_rule`` ops/cpn.py:293-325
-``apply_model``        celldetection_scripts/cpn_inference.py:311-429 (single model, stitching_rule='nms')
+``apply_model``        celldetection_scripts/cpn_inference.py:311-411 (one model, masks / point masks, 'nms' stitching)
+``apply_models``       cpn_inference.py:354-429 (ensemble: per-model results, box voting, final NMS)
+``filter_by_box_voting`` ops/boxes.py:53-83 (+ torchvision box_iou)
 =====================  ==========================================================================================
 
 Pinning: the reference ships no golden vectors for this path, so the oracle is pinned against
@@ -495,12 +497,14 @@ def filter_contours_by_stitching_rule(contours, tile_size, overlaps, rule='ex_br
     return ~((contours >= stop).any(-1).all(-1))
 
 
-def apply_model(img, sd, arch, crop_size, strides, border_removal=4, batch_size=1, **kw):
-    """cpn_inference.py:311-429 for one model, ``stitching_rule='nms'``, no masks / point masks.
+def apply_model(img, sd, arch, crop_size, strides, border_removal=4, batch_size=1, mask=None, point_mask=None,
+                point_mask_exclusive=False, **kw):
+    """cpn_inference.py:311-411 for one model, ``stitching_rule='nms'``.
 
     ``img`` is uint8 or float HxWx3.  uint8 tiles become float/255 (lightning_base.py:774-780).  Per tile: model with
-    ``offsets=[w0, h0]``; border removal in tile-local coordinates with sides disabled at the image border
-    (cpn_inference.py:370-387); then concat and one global NMS with the model's ``nms_thresh`` (:405-408).
+    ``offsets=[w0, h0]`` (and, with ``mask`` / ``point_mask``, the crop as upper / lower score bound; tiles whose crop
+    is empty are skipped, TileLoader :93-111); border removal in tile-local coordinates with sides disabled at the
+    image border (cpn_inference.py:370-387); then concat and one global NMS with the model's ``nms_thresh`` (:405-408).
     """
     img = np.asarray(img)
     H, W = img.shape[:2]
@@ -511,11 +515,24 @@ def apply_model(img, sd, arch, crop_size, strides, border_removal=4, batch_size=
     acc = OrderedDict()
     for t_idx, (sl_h, sl_w) in enumerate(tiles):
         gy, gx = np.unravel_index(t_idx, grid)
+        bkw = {}
+        if mask is not None:
+            mc = np.asarray(mask)[sl_h, sl_w]
+            if not np.any(mc):
+                continue
+            bkw['scores_upper_bound'] = torch.as_tensor(mc.astype('float32'))[None, None]
+        if point_mask is not None:
+            pc = np.asarray(point_mask)[sl_h, sl_w]
+            if not np.any(pc):
+                continue
+            bkw['scores_lower_bound'] = torch.as_tensor(np.clip(pc, 0., 1.).astype('float32'))[None, None]
+            if point_mask_exclusive:
+                bkw['scores_upper_bound'] = bkw['scores_lower_bound']
         crop_img = img[sl_h, sl_w]
         x = torch.as_tensor(np.ascontiguousarray(crop_img)).permute(2, 0, 1)[None]
         x = x.float() / 255 if crop_img.dtype == np.uint8 else x.float()
         off = torch.as_tensor([[sl_w.start, sl_h.start]], dtype=torch.float)
-        out = cpn_forward(x, sd, arch, offsets=off, **kw)
+        out = cpn_forward(x, sd, arch, offsets=off, **bkw, **kw)
         con = out['contours'][0]
         keep = remove_border_contours(con, crop_img.shape[:2], border_removal, top=gy > 0, right=gx < grid[1] - 1,
                                       bottom=gy < grid[0] - 1, left=gx > 0, offsets=-off[0])
@@ -526,3 +543,43 @@ def apply_model(img, sd, arch, crop_size, strides, border_removal=4, batch_size=
     res = OrderedDict((k, torch.cat(v, 0)) for k, v in acc.items())
     keep = torch.as_tensor(nms(res['boxes'].numpy(), res['scores'].numpy(), nms_thresh))
     return OrderedDict((k, v[keep]) for k, v in res.items())
+
+
+def box_iou(a, b):
+    """torchvision.ops.boxes.box_iou (third party): inter / (area_a + area_b - inter), fp32."""
+    a, b = torch.as_tensor(a, dtype=torch.float32), torch.as_tensor(b, dtype=torch.float32)
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    lt = torch.max(a[:, None, :2], b[None, :, :2])
+    rb = torch.min(a[:, None, 2:], b[None, :, 2:])
+    wh = (rb - lt).clamp(min=0)
+    inter = wh[..., 0] * wh[..., 1]
+    return inter / (area_a[:, None] + area_b[None] - inter)
+
+
+def filter_by_box_voting(boxes, thresh, min_vote):
+    """ops/boxes.py:53-83: votes = (iou * (iou > thresh)).sum(-1); keep votes >= min_vote.  Returns (keep, votes[keep])."""
+    iou = box_iou(boxes, boxes)
+    iou = iou * (iou > thresh)
+    votes = iou.sum(-1)
+    m = votes >= min_vote
+    return torch.arange(len(votes))[m], votes[m]
+
+
+def apply_models(img, sds, archs, crop_size, strides, min_vote=1, **kw):
+    """cpn_inference.py:354-429 for a list of models: per-model tiled inference + stitch NMS, concatenation, box voting
+    (``min_vote > 1``) and the final NMS with the (last) model's ``nms_thresh`` (:417-427)."""
+    assert len(sds) >= min_vote >= 1
+    results = None
+    for sd, arch in zip(sds, archs):
+        r = apply_model(img, sd, arch, crop_size, strides, **kw)
+        results = r if results is None else OrderedDict((k, torch.cat((results[k], r[k]), 0)) for k in results)
+    nms_thresh = kw.get('nms_thresh', .2)
+    if len(sds) > 1 and len(results['scores']):
+        if min_vote > 1:
+            keep, votes = filter_by_box_voting(results['boxes'], nms_thresh, min_vote)
+            results = OrderedDict((k, v[keep]) for k, v in results.items())
+            results['votes'] = votes
+        keep = torch.as_tensor(nms(results['boxes'].numpy(), results['scores'].numpy(), nms_thresh))
+        results = OrderedDict((k, v[keep]) for k, v in results.items())
+    return results

@@ -44,6 +44,18 @@ def fixture_state_dict(z, arch, seed):
     return sd
 
 
+def ensemble_state_dicts(z):
+    """The two CpnU22 members of the ensemble fixture (same seed, different calibrated / perturbed heads)."""
+    sds = []
+    for j, seed in enumerate(int(v) for v in z['seeds']):
+        sd = synth_state_dict(key_spec('CpnU22'), seed=seed)
+        for f in z.files:
+            if f.startswith(f'calib{j}/'):
+                sd[f[len(f'calib{j}/'):]] = torch.from_numpy(np.array(z[f]))
+        sds.append(sd)
+    return sds
+
+
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     if a.size == 0:

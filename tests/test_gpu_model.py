@@ -11,8 +11,8 @@ import torch
 import celldetection_b200 as cd
 import cpn_oracle as orc
 from conftest import ROOT
-from helpers import (load_npz, fixture_state_dict, fixture_ctor, rel_err, match_by_box, MODEL_FIXTURES,
-                     VARIANT_FIXTURES)
+from helpers import (load_npz, fixture_state_dict, fixture_ctor, ensemble_state_dicts, rel_err, match_by_box,
+                     MODEL_FIXTURES, VARIANT_FIXTURES)
 
 pytestmark = pytest.mark.gpu
 REPORT = os.environ.get('CPN_PARITY_REPORT') or os.path.join(ROOT, 'gpurun_out', 'parity_report.json')
@@ -325,3 +325,54 @@ def test_variant_models_match_reference(name, precision):
             assert np.abs(out['box_uncertainties'][i].cpu().numpy()[ia] - z[f'out/{i}/box_uncertainties'][ib]).max() < 2e-3
         else:
             assert out['box_uncertainties'] is None
+
+
+def test_apply_model_ensemble_mask_and_voting():
+    """cd.apply_model with two models + mask against the vector minted from the reference's apply_model, the oracle's
+    voting path for min_vote > 1 (where the reference itself raises IndexError), and cd.ops.filter_by_box_voting
+    against the reference op's golden (ops/boxes.py:53-83)."""
+    z = load_npz('apply_model_ensemble')
+    crop, stride, border = [int(v) for v in z['meta']]
+    sds = ensemble_state_dicts(z)
+    models = []
+    for sd in sds:
+        m = cd.models.CpnU22(3, precision='fp32')
+        m.load_state_dict(sd)
+        models.append(m.cuda())
+    for bs in (1, 4):
+        res = cd.apply_model(z['img'], models, mask=z['mask'], crop_size=crop, strides=stride, border_removal=border,
+                             batch_size=bs, min_vote=1)
+        assert len(res['scores']) == len(z['vote1/scores']) > 0
+        pairs = match_by_box(res['boxes'].cpu().numpy(), z['vote1/boxes'])
+        assert len(pairs) == len(z['vote1/scores'])
+        for a, b in pairs:
+            assert np.abs(res['contours'][a].cpu().numpy() - z['vote1/contours'][b]).max() < 0.5
+            assert abs(float(res['scores'][a]) - float(z['vote1/scores'][b])) < 1e-4
+    want = orc.apply_models(z['img'], sds, ['CpnU22'] * 2, crop, stride, border_removal=border, mask=z['mask'],
+                            min_vote=1.5)
+    got = cd.apply_model(z['img'], models, mask=z['mask'], crop_size=crop, strides=stride, border_removal=border,
+                         batch_size=2, min_vote=1.5)
+    assert len(got['scores']) == len(want['scores']) > 0 and 'votes' in got
+    pairs = match_by_box(got['boxes'].cpu().numpy(), want['boxes'].numpy())
+    assert len(pairs) == len(want['scores'])
+    for a, b in pairs:
+        assert abs(float(got['votes'][a]) - float(want['votes'][b])) < 1e-3
+    # point mask (lower bound): detections appear at the marked pixels even where the network's score is low
+    pm = np.zeros(z['mask'].shape, dtype=np.float32)
+    pm[70:74, 150:154] = 1.
+    pt = cd.apply_model(z['img'], models[:1], point_mask=pm, crop_size=crop, strides=stride, border_removal=border,
+                        batch_size=2)
+    want_pt = orc.apply_model(z['img'], sds[0], 'CpnU22', crop, stride, border_removal=border, point_mask=pm)
+    assert len(pt['scores']) == len(want_pt['scores']) > 0
+    assert float(pt['scores'].max()) == 1.0
+    # op level
+    bx = torch.from_numpy(z['voting/boxes']).cuda()
+    keep, votes = cd.ops.filter_by_box_voting(bx, 0.2, 2, return_votes=True)
+    assert np.array_equal(keep.cpu().numpy(), z['voting/keep'])
+    assert np.abs(votes.cpu().numpy() - z['voting/votes']).max() < 1e-5
+    all_votes = cd.ops.box_votes(bx, 0.2)
+    dense = orc.box_iou(z['voting/boxes'], z['voting/boxes'])
+    dense = (dense * (dense > 0.2)).sum(-1)
+    ok = ~torch.isnan(dense)
+    assert torch.isnan(all_votes.cpu()[~ok]).all() and (~ok).sum() == 1
+    assert (all_votes.cpu()[ok] - dense[ok]).abs().max() < 1e-5

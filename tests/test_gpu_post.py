@@ -127,6 +127,25 @@ def test_score_bounds():
                  scores_upper_bound=upper.cuda())
     assert len(got['scores'][0]) == len(want['scores'][0]) > 0
     assert np.abs(got['contours'][0].cpu().numpy() - want['contours'][0].numpy()).max() < 1e-4
+    # bounds given at the INPUT resolution (the tiled driver's mask crops): resized by cpn_resize_bilinear like
+    # _equal_size does with F.interpolate (cpn.py:109-123)
+    blocks = (torch.rand(n, 1, h // 8, w // 8, generator=g) > 0.4).float()
+    upper_full = blocks.repeat_interleave(8, 2).repeat_interleave(8, 3)
+    smooth = torch.rand(n, 1, h, w, generator=g) * 0.5
+    want = orc.cpn_post(*raw, (h, w), order=order, samples=samples, scores_upper_bound=upper_full,
+                        scores_lower_bound=smooth)
+    got = m.post(raw[0][:, 0].contiguous().cuda(), torch.cat((raw[1], raw[3]), 1).permute(0, 2, 3, 1).contiguous().cuda(),
+                 raw[2].permute(0, 2, 3, 1).contiguous().cuda(), (h, w), scores_upper_bound=upper_full.cuda(),
+                 scores_lower_bound=smooth.cuda())
+    assert len(got['scores'][0]) == len(want['scores'][0]) > 0
+    assert np.abs(got['scores'][0].cpu().numpy() - want['scores'][0].numpy()).max() < 1e-6
+    lib = cd._lib.load()
+    src = torch.rand(2, 37, 53, 1, generator=g)
+    dst = torch.empty(2, 20, 91, 1, device='cuda')
+    cd._lib.check(lib.cpn_resize_bilinear(cd._lib.ptr(src.cuda()), 2, 37, 53, 1, cd._lib.ptr(dst), 20, 91,
+                                          cd._lib.stream_ptr()))
+    ref = torch.nn.functional.interpolate(src.permute(0, 3, 1, 2), (20, 91), mode='bilinear', align_corners=False)
+    assert (dst.cpu().permute(0, 3, 1, 2) - ref).abs().max() < 1e-6
 
 
 def test_fouriers2contours_golden_and_edges():

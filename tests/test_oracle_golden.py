@@ -6,7 +6,8 @@ import pytest
 import torch
 
 import cpn_oracle as orc
-from helpers import load_npz, fixture_state_dict, fixture_ctor, rel_err, MODEL_FIXTURES, VARIANT_FIXTURES
+from helpers import (load_npz, fixture_state_dict, fixture_ctor, ensemble_state_dicts, rel_err, MODEL_FIXTURES,
+                     VARIANT_FIXTURES)
 
 
 @pytest.mark.parametrize('name', MODEL_FIXTURES)
@@ -153,3 +154,29 @@ def test_oracle_chunked_nms_rule():
     idx = idx[torch.ops.torchvision.nms(boxes[idx], scores[idx], .3)]
     got = orc.batched_box_nmsi([boxes.numpy()], [scores.numpy()], .3, batch_size=128)[0]
     assert np.array_equal(got, idx.numpy())
+
+
+def test_oracle_ensemble_mask_and_voting_golden():
+    """Two-model ensemble with a mask (upper score bound, empty tiles skipped) through the reference's apply_model, and
+    cd.ops.filter_by_box_voting at op level (cpn_inference.py:93-111, 417-427; ops/boxes.py:53-83).  With min_vote > 1
+    the reference's driver raises IndexError whenever the vote removes a box (votes are stored before the keep
+    indices are applied, cpn_inference.py:421-423), so the driver-level vector uses min_vote = 1."""
+    z = load_npz('apply_model_ensemble')
+    crop, stride, border = [int(v) for v in z['meta']]
+    sds = ensemble_state_dicts(z)
+    torch.set_num_threads(8)
+    res = orc.apply_models(z['img'], sds, ['CpnU22'] * 2, crop, stride, border_removal=border, mask=z['mask'], min_vote=1)
+    assert len(res['scores']) == len(z['vote1/scores']) > 0
+    for k in ('contours', 'boxes', 'scores', 'locations', 'fourier', 'contour_proposals'):
+        assert rel_err(res[k].numpy(), z['vote1/' + k]) < 1e-5, k
+    # every detection lies inside the mask's bounding region (the mask is the upper score bound)
+    cx = res['locations'][:, 0].numpy()
+    assert cx.max() < 125
+    keep, votes = orc.filter_by_box_voting(z['voting/boxes'], 0.2, 2)
+    assert np.array_equal(keep.numpy(), z['voting/keep'])
+    assert np.abs(votes.numpy() - z['voting/votes']).max() < 1e-5
+    # the sane order (filter, then attach votes) works where the reference crashes
+    res2 = orc.apply_models(z['img'], sds, ['CpnU22'] * 2, crop, stride, border_removal=border, mask=z['mask'],
+                            min_vote=1.5)
+    assert 0 < len(res2['scores']) <= len(res['scores']) and len(res2['votes']) == len(res2['scores'])
+    assert float(res2['votes'].min()) >= 1.5
