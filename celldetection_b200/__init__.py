@@ -7,6 +7,7 @@ CpnResNeXt101UNet``, ``cd.ops.cpn.*``, ``cd.fetch_model`` / ``cd.load_model`` an
 from . import _lib
 from . import ops
 from . import models
+from . import data
 from .utils import load_model, fetch_model, save_fetchable_model, synth_state_dict, calibrate_heads_
 from .inference import get_tiling_slices, apply_model, cpn_inference
 

@@ -21,6 +21,7 @@ SOURCES = [
     ('pointwise.cu', []),
     ('post.cu', ['-fmad=false']),
     ('nms.cu', ['-fmad=false']),
+    ('labels.cu', ['-fmad=false']),   # shares the grid-cell arithmetic with nms.cu: must round identically
 ]
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',

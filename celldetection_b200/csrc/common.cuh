@@ -65,6 +65,28 @@ int upsample_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t
 int bilinear_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st);
 int proj_launch(const cpn_op_t& op, const void* src, void* dst, const float* wgt, const float* bias, cudaStream_t st);
 
+// ---- uniform spatial grid over box centres (nms.cu): shared by the stitch NMS, box voting and label rasterisation ----
+struct GridInfo {
+  float x0, y0, inv_cell;
+  int ncx, ncy;
+};
+struct GridBins {
+  const uint64_t* cell_keys;  // [n] (cell << 32 | row), ascending
+  const int32_t* cell_rows;   // [n] row of each entry
+  const GridInfo* gi;         // device
+};
+size_t grid_bin_workspace_bytes(int64_t n_boxes);
+int grid_bin_boxes(const float4* boxes, int n, void* workspace, GridBins* out, cudaStream_t st);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int cell_of(const GridInfo& g, const float4 b, int* cx_out, int* cy_out) {
+  int cx = (int)((0.5f * (b.x + b.z) - g.x0) * g.inv_cell), cy = (int)((0.5f * (b.y + b.w) - g.y0) * g.inv_cell);
+  cx = min(max(cx, 0), g.ncx - 1); cy = min(max(cy, 0), g.ncy - 1);
+  if (cx_out) { *cx_out = cx; *cy_out = cy; }
+  return cy * g.ncx + cx;
+}
+#endif
+
 // ---- device helpers -----------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);

@@ -1,0 +1,277 @@
+// contours2labels: rasterisation of (stitched) contours into an overlap-aware multi-channel label image -- the step
+// that follows the CPN hot path.  Replaces /root/reference/celldetection/data/cpn.py:292-358
+// (contours2labels) and :246-256 (render_contour -> cv2.drawContours(thickness=-1), OpenCV imgproc/drawing.cpp:
+// CollectPolyEdges + Line + FillEdgeCollection), as called by celldetection_scripts/cpn_inference.py:809-813.
+//
+// Reference semantics (sequential over contours k = 0, 1, ...):  round (half to even) and clip the vertices, render the
+// polygon (boundary lines by 8-connected left-to-right Bresenham + integer scan-line interior on 16.16 fixed-point edge
+// x coordinates) with label k + 1, and add it to the FIRST channel whose gap-dilated bounding-box region holds no label
+// yet (a new channel is appended when all are occupied).
+//
+// B200 design: the greedy channel choice only depends on earlier contours whose bounding box meets this contour's
+// dilated box, so the sequence is a sparse dependency DAG.  One persistent warp per contour, contours taken in index
+// order (warp w handles k = w, w + G, ...): the warp (1) waits until every earlier neighbour (found through the same
+// uniform grid the stitch NMS uses) has published its `done` flag, (2) ORs the occupied-channel bits over its dilated
+// box (L2 loads, lanes across pixels, all channels of a pixel in one vector), (3) paints boundary + interior with plain
+// stores, (4) fences and publishes its own flag.  The smallest unfinished index never waits, so the schedule cannot
+// deadlock as long as all warps of the grid are resident (the grid is sized by the occupancy API).  Integer / byte work,
+// L2-resident; no tensor cores.  Results are bit-identical to the reference (tests/golden/contours2labels.npz).
+#include "common.cuh"
+#include <cstring>
+
+namespace cpn {
+
+constexpr int C2L_WARPS = 8;
+constexpr int C2L_MAX_CH = 64;          // occupied-channel bitmask width
+constexpr long long XY_ONE = 1ll << 16;
+
+struct C2LParams {
+  const float* contours;     // [K, S, 2] (x, y)
+  int K, S, H, W;
+  int rounded, clip, gap, C;
+  int2* pts;                 // [K, S] integer vertices
+  int4* bbox;                // [K] (xmin, ymin, xmax, ymax), from the float contour like render_contour
+  float4* ebox;              // [K] dilated boxes as floats (grid binning)
+  int32_t* labels;           // [H, W, C]
+  uint32_t* done;            // [K]
+  int32_t* info;             // [0] channels used, [1] channels needed, [2] error flags
+};
+
+// ---- pass 1: vertices -> integers, boxes -------------------------------------------------------------------------------
+__global__ void c2l_prep_kernel(const C2LParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.K) return;
+  const float2* c = reinterpret_cast<const float2*>(p.contours) + (long long)warp * p.S;
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int s = lane; s < p.S; s += 32) {
+    float2 v = c[s];
+    if (p.rounded) { v.x = rintf(v.x); v.y = rintf(v.y); }                   // np.round: half to even
+    if (p.clip) {                                                            // clip_contour_(contour, size - 1)
+      v.x = fminf(fmaxf(v.x, 0.f), (float)(p.W - 1));
+      v.y = fminf(fmaxf(v.y, 0.f), (float)(p.H - 1));
+    }
+    mnx = fminf(mnx, v.x); mny = fminf(mny, v.y); mxx = fmaxf(mxx, v.x); mxy = fmaxf(mxy, v.y);
+    p.pts[(long long)warp * p.S + s] = make_int2((int)v.x, (int)v.y);        // np.array(contour, dtype=np.int32)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if (lane == 0) {
+    const int x0 = (int)floorf(mnx), y0 = (int)floorf(mny), x1 = (int)ceilf(mxx), y1 = (int)ceilf(mxy);
+    p.bbox[warp] = make_int4(x0, y0, x1, y1);
+    p.ebox[warp] = make_float4((float)(x0 - p.gap), (float)(y0 - p.gap), (float)(x1 + p.gap + 1), (float)(y1 + p.gap + 1));
+    p.done[warp] = 0u;
+  }
+}
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- pass 2: ordered painting ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(C2L_WARPS * 32) c2l_paint_kernel(const C2LParams p, const GridBins bins) {
+  extern __shared__ int2 c2l_sm[];                      // [C2L_WARPS][S] vertices
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int2* v = c2l_sm + (size_t)wib * p.S;
+  const int gw = blockIdx.x * C2L_WARPS + wib, nw = gridDim.x * C2L_WARPS;
+  const GridInfo g = *bins.gi;
+  const int C = p.C;
+  for (int k = gw; k < p.K; k += nw) {
+    __syncwarp();
+    for (int s = lane; s < p.S; s += 32) v[s] = p.pts[(long long)k * p.S + s];
+    const int4 bb = p.bbox[k];
+    const int ex0 = bb.x - p.gap, ey0 = bb.y - p.gap, ex1 = bb.z + p.gap, ey1 = bb.w + p.gap;   // inclusive
+    __syncwarp();
+    // (1) wait for every earlier contour whose bounding box meets the dilated box of this one
+    {
+      int cx, cy;
+      cell_of(g, p.ebox[k], &cx, &cy);
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = cy + dy;
+        if (yy < 0 || yy >= g.ncy) continue;
+        const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, g.ncx - 1);
+        const uint64_t k_lo = (uint64_t)(uint32_t)(yy * g.ncx + x_lo) << 32;
+        const uint64_t k_hi = (uint64_t)(uint32_t)(yy * g.ncx + x_hi + 1) << 32;
+        int lo = 0, hi = p.K;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (bins.cell_keys[mid] < k_lo) lo = mid + 1; else hi = mid; }
+        int end = lo, hi2 = p.K;
+        while (end < hi2) { const int mid = (end + hi2) >> 1; if (bins.cell_keys[mid] < k_hi) end = mid + 1; else hi2 = mid; }
+        for (int q = lo + lane; q < end; q += 32) {
+          const int j = bins.cell_rows[q];
+          if (j >= k) continue;
+          const int4 bj = p.bbox[j];
+          if (bj.x > ex1 || bj.z < ex0 || bj.y > ey1 || bj.w < ey0) continue;
+          long long spins = 0;
+          while (ld_acquire(p.done + j) == 0u) {
+            __nanosleep(64);
+            if (++spins > (1ll << 22)) { atomicOr(p.info + 2, 1); break; }     // never expected: report, do not hang
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // (2) first channel whose dilated-box region is empty (labels[region] > 0).sum((0, 1)) == 0
+    const int rx0 = max(ex0, 0), ry0 = max(ey0, 0), rx1 = min(ex1, p.W - 1), ry1 = min(ey1, p.H - 1);
+    unsigned long long occ = 0;
+    if (rx1 >= rx0 && ry1 >= ry0) {
+      const int rw = rx1 - rx0 + 1;
+      const long long npx = (long long)rw * (ry1 - ry0 + 1);
+      for (long long i = lane; i < npx; i += 32) {
+        const int y = ry0 + (int)(i / rw), x = rx0 + (int)(i % rw);
+        const int32_t* px = p.labels + ((long long)y * p.W + x) * C;
+        if ((C & 3) == 0) {
+          for (int c = 0; c < C; c += 4) {
+            const int4 l = __ldcg(reinterpret_cast<const int4*>(px + c));
+            occ |= (unsigned long long)((l.x > 0 ? 1u : 0u) | (l.y > 0 ? 2u : 0u) | (l.z > 0 ? 4u : 0u) | (l.w > 0 ? 8u : 0u)) << c;
+          }
+        } else {
+          for (int c = 0; c < C; ++c) occ |= (unsigned long long)(__ldcg(px + c) > 0 ? 1u : 0u) << c;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) occ |= __shfl_xor_sync(0xffffffffu, occ, o);
+    const int ch = __ffsll((long long)~occ) - 1;         // first free channel (-1: all 64 mask bits taken)
+    if (ch < 0 || ch >= C) {
+      if (lane == 0) { atomicMax(p.info + 1, (ch < 0 ? C2L_MAX_CH : ch) + 1); }
+    } else {
+      if (lane == 0) { atomicMax(p.info + 0, ch + 1); atomicMax(p.info + 1, ch + 1); }
+      const int32_t lbl = k + 1;
+      int32_t* L = p.labels + ch;
+      // (3a) boundary: cv::Line, 8-connected Bresenham from the left end point (LineIterator leftToRight)
+      for (int e = lane; e < p.S; e += 32) {
+        int2 a = v[e == 0 ? p.S - 1 : e - 1], b = v[e];
+        int dx = b.x - a.x, dy = b.y - a.y;
+        if (dx < 0) { const int2 t = a; a = b; b = t; dx = -dx; dy = -dy; }
+        const int sy = dy >= 0 ? 1 : -1;
+        dy = dy >= 0 ? dy : -dy;
+        const bool steep = dy > dx;
+        if (steep) { const int t = dx; dx = dy; dy = t; }
+        int err = dx - (dy + dy);
+        const int plus = dx + dx, minus = -(dy + dy);
+        int x = a.x, y = a.y;
+        for (int i = 0; i <= dx; ++i) {
+          if ((unsigned)x < (unsigned)p.W && (unsigned)y < (unsigned)p.H) L[((long long)y * p.W + x) * C] = lbl;
+          const bool neg = err < 0;
+          err += minus + (neg ? plus : 0);
+          if (steep) { y += sy; if (neg) x += 1; } else { x += 1; if (neg) y += sy; }
+        }
+      }
+      // (3b) interior: FillEdgeCollection.  Row y takes the crossings x_e(y) = x_e(y0) + dx_e * (y - y0) of the edges
+      // with y0 <= y < y1 in ascending order and fills [ceil(x_1), floor(x_2)], [ceil(x_3), floor(x_4)], ...
+      int ymin = 0x7fffffff, ymax = -0x7fffffff;
+      for (int s = lane; s < p.S; s += 32) { ymin = min(ymin, v[s].y); ymax = max(ymax, v[s].y); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+      }
+      for (int y = ymin + lane; y < ymax; y += 32) {
+        if ((unsigned)y >= (unsigned)p.H) continue;
+        long long last_x = -(1ll << 62);
+        int last_e = -1;
+        bool open = false;
+        long long xa = 0;
+        for (;;) {
+          // next crossing in (x, edge index) order after (last_x, last_e)
+          long long best_x = 1ll << 62;
+          int best_e = -1;
+          for (int e = 0; e < p.S; ++e) {
+            const int2 a = v[e == 0 ? p.S - 1 : e - 1], b = v[e];
+            if (a.y == b.y) continue;
+            const int2 lo = a.y < b.y ? a : b, hi = a.y < b.y ? b : a;
+            if (y < lo.y || y >= hi.y) continue;
+            const long long num = ((long long)b.x - a.x) * XY_ONE, den = (long long)b.y - a.y;
+            const long long dxl = num / den;                                  // C++ truncating division, like OpenCV
+            const long long xe = (long long)lo.x * XY_ONE + dxl * (y - lo.y);
+            if ((xe > last_x || (xe == last_x && e > last_e)) && (xe < best_x || (xe == best_x && e < best_e))) {
+              best_x = xe; best_e = e;
+            }
+          }
+          if (best_e < 0) break;
+          last_x = best_x; last_e = best_e;
+          if (!open) { xa = best_x; open = true; }
+          else {
+            open = false;
+            int x1 = (int)((xa + XY_ONE - 1) >> 16), x2 = (int)(best_x >> 16);
+            if (x1 < p.W && x2 >= 0) {
+              x1 = max(x1, 0); x2 = min(x2, p.W - 1);
+              for (int x = x1; x <= x2; ++x) L[((long long)y * p.W + x) * C] = lbl;
+            }
+          }
+        }
+      }
+    }
+    // (4) publish
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(p.done + k, 1u);
+  }
+}
+
+static inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
+
+}  // namespace cpn
+
+using namespace cpn;
+
+extern "C" size_t cpn_contours2labels_workspace_bytes(int64_t K, int samples) {
+  const size_t k = (size_t)(K > 0 ? K : 1), s = (size_t)(samples > 0 ? samples : 1);
+  return al(k * s * sizeof(int2)) + al(k * sizeof(int4)) + al(k * sizeof(float4)) + al(k * sizeof(uint32_t)) +
+         al(grid_bin_workspace_bytes(K)) + 1024;
+}
+
+extern "C" int cpn_contours2labels(const float* contours, int64_t K, int samples, int H, int W, int rounded, int clip,
+                                   int gap, int32_t* labels, int channels, void* workspace, int32_t* info_dev,
+                                   void* stream) {
+  CPN_REQUIRE(H > 0 && W > 0 && samples >= 1 && samples <= 4096, "contours2labels: bad size / samples");
+  CPN_REQUIRE(channels >= 1 && channels <= C2L_MAX_CH, "contours2labels: channels %d must be in [1, %d]", channels,
+              C2L_MAX_CH);
+  CPN_REQUIRE(K >= 0 && K < (1ll << 31) - 1 && gap >= 0, "contours2labels: bad K / gap");
+  CPN_REQUIRE(labels && info_dev && ((uintptr_t)labels % 16) == 0, "contours2labels: labels must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  CPN_CHECK_CUDA(cudaMemsetAsync(labels, 0, (size_t)H * W * channels * sizeof(int32_t), st));
+  CPN_CHECK_CUDA(cudaMemsetAsync(info_dev, 0, 4 * sizeof(int32_t), st));
+  if (K == 0) return 0;
+  char* b = reinterpret_cast<char*>(workspace);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* q = b + off; off += al(bytes); return q; };
+  C2LParams p;
+  memset(&p, 0, sizeof(p));
+  p.contours = contours; p.K = (int)K; p.S = samples; p.H = H; p.W = W; p.rounded = rounded; p.clip = clip; p.gap = gap;
+  p.C = channels;
+  p.pts = (int2*)take((size_t)K * samples * sizeof(int2));
+  p.bbox = (int4*)take((size_t)K * sizeof(int4));
+  p.ebox = (float4*)take((size_t)K * sizeof(float4));
+  p.done = (uint32_t*)take((size_t)K * sizeof(uint32_t));
+  void* grid_ws = take(grid_bin_workspace_bytes(K));
+  p.labels = labels; p.info = info_dev;
+  c2l_prep_kernel<<<(int)((K * 32 + 255) / 256), 256, 0, st>>>(p);
+  CPN_CHECK_LAUNCH();
+  GridBins bins;
+  if (grid_bin_boxes(p.ebox, (int)K, grid_ws, &bins, st)) return 1;
+  // persistent grid: every warp must be resident (ordered spin-wait), so size it by occupancy
+  const size_t smem = (size_t)C2L_WARPS * samples * sizeof(int2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(c2l_paint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  CPN_REQUIRE(smem <= 200 * 1024, "contours2labels: %d samples per contour exceed the shared-memory budget", samples);
+  int per_sm = 0;
+  CPN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c2l_paint_kernel, C2L_WARPS * 32, smem));
+  CPN_REQUIRE(per_sm >= 1, "contours2labels: kernel does not fit");
+  long long grid = (long long)per_sm * sm_count();
+  const long long need = (K + C2L_WARPS - 1) / C2L_WARPS;
+  if (grid > need) grid = need;
+  c2l_paint_kernel<<<(int)grid, C2L_WARPS * 32, smem, st>>>(p, bins);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}

@@ -342,11 +342,6 @@ extern "C" int cpn_nms_segments(const float* boxes, const float* scores, const i
 // =====================================================================================================================
 namespace cpn {
 
-struct GridInfo {
-  float x0, y0, inv_cell;
-  int ncx, ncy;
-};
-
 // pass 1: extents (min corner, max corner, max box size) via atomics on ordered-int floats
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
@@ -379,13 +374,6 @@ __global__ void grid_setup_kernel(const int* __restrict__ ext, GridInfo* __restr
   cell = fmaxf(cell, fmaxf(spanx, spany) / 4000.f);   // at most ~4000 x 4000 cells
   gi->x0 = mnx; gi->y0 = mny; gi->inv_cell = 1.f / cell;
   gi->ncx = (int)(spanx / cell) + 1; gi->ncy = (int)(spany / cell) + 1;
-}
-
-__device__ __forceinline__ int cell_of(const GridInfo& g, const float4 b, int* cx_out, int* cy_out) {
-  int cx = (int)((0.5f * (b.x + b.z) - g.x0) * g.inv_cell), cy = (int)((0.5f * (b.y + b.w) - g.y0) * g.inv_cell);
-  cx = min(max(cx, 0), g.ncx - 1); cy = min(max(cy, 0), g.ncy - 1);
-  if (cx_out) { *cx_out = cx; *cy_out = cy; }
-  return cy * g.ncx + cx;
 }
 
 // keys: (cell << 32) | rank, where rank = position in the stable descending score order; value = rank
@@ -625,14 +613,20 @@ __global__ void votes_kernel(const float4* __restrict__ boxes, const uint64_t* _
 
 }  // namespace cpn
 
-extern "C" size_t cpn_box_votes_workspace_bytes(int64_t n_boxes) { return cpn_nms_grid_workspace_bytes(n_boxes); }
+namespace cpn {
 
-extern "C" int cpn_box_votes(const float* boxes, int64_t n_boxes, float iou_threshold, void* workspace, float* votes,
-                             void* stream) {
-  CPN_REQUIRE(n_boxes < (1ll << 31), "box_votes: too many boxes");
-  if (n_boxes <= 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int n = (int)n_boxes;
+size_t grid_bin_workspace_bytes(int64_t n_boxes) {
+  const size_t nn = (size_t)(n_boxes > 0 ? n_boxes : 1);
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)nn, 0, 64, (cudaStream_t)0);
+  return align_up(nn * 8, 256) * 2 + align_up(nn * 4, 256) * 2 + 2048 + align_up(cub_bytes + 256, 256) + 1024;
+}
+
+// Bins `n` boxes (by centre) into the uniform grid whose cell is the largest box extent: boxes that overlap lie in
+// 3x3 neighbouring cells.  Returns device arrays inside `workspace`: cell_keys[n] = (cell << 32 | row) ascending,
+// cell_rows[n] = the row of each entry, and the GridInfo.
+int grid_bin_boxes(const float4* boxes, int n, void* workspace, GridBins* out, cudaStream_t st) {
   const size_t nn = (size_t)n;
   char* b = reinterpret_cast<char*>(workspace);
   size_t off = 0;
@@ -650,17 +644,33 @@ extern "C" int cpn_box_votes(const float* boxes, int64_t n_boxes, float iou_thre
   const int tb = 256, gb = (n + tb - 1) / tb;
   const int ext_init[5] = {0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
   CPN_CHECK_CUDA(cudaMemcpyAsync(small, ext_init, sizeof(ext_init), cudaMemcpyHostToDevice, st));
-  grid_extent_kernel<<<capped_blocks(gb), tb, 0, st>>>(reinterpret_cast<const float4*>(boxes), n, small);
+  grid_extent_kernel<<<capped_blocks(gb), tb, 0, st>>>(boxes, n, small);
   CPN_CHECK_LAUNCH();
   grid_setup_kernel<<<1, 32, 0, st>>>(small, gi);
   CPN_CHECK_LAUNCH();
-  votes_cellkeys_kernel<<<gb, tb, 0, st>>>(reinterpret_cast<const float4*>(boxes), n, gi, keys_a, vals_a);
+  votes_cellkeys_kernel<<<gb, tb, 0, st>>>(boxes, n, gi, keys_a, vals_a);
   CPN_CHECK_LAUNCH();
   size_t cb = cub_bytes + 256;
   CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_a, cell_keys, vals_a, cell_rows, n, 0, 64, st));
   count_launch(4);
-  votes_kernel<<<gb, tb, 0, st>>>(reinterpret_cast<const float4*>(boxes), cell_keys, cell_rows, n, gi, iou_threshold,
-                                  votes);
+  out->cell_keys = cell_keys; out->cell_rows = cell_rows; out->gi = gi;
+  return 0;
+}
+
+}  // namespace cpn
+
+extern "C" size_t cpn_box_votes_workspace_bytes(int64_t n_boxes) { return cpn::grid_bin_workspace_bytes(n_boxes); }
+
+extern "C" int cpn_box_votes(const float* boxes, int64_t n_boxes, float iou_threshold, void* workspace, float* votes,
+                             void* stream) {
+  CPN_REQUIRE(n_boxes < (1ll << 31), "box_votes: too many boxes");
+  if (n_boxes <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = (int)n_boxes;
+  GridBins bins;
+  if (grid_bin_boxes(reinterpret_cast<const float4*>(boxes), n, workspace, &bins, st)) return 1;
+  votes_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(boxes), bins.cell_keys, bins.cell_rows, n,
+                                                bins.gi, iou_threshold, votes);
   CPN_CHECK_LAUNCH();
   return 0;
 }

@@ -1,0 +1,71 @@
+"""``cd.data`` functions that follow the CPN inference path, executed by the C ABI's CUDA kernels.
+
+``contours2labels`` mirrors /root/reference/celldetection/data/cpn.py:292-358 (and ``render_contour`` :246-256, i.e.
+OpenCV's ``drawContours(thickness=-1)`` polygon fill): contours of one image -> overlap-aware multi-channel label image.
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+
+__all__ = ['contours2labels']
+
+
+def contours2labels(contours, size, rounded=True, clip=True, initial_depth=1, gap=3, dtype='int32', ioa_thresh=None,
+                    sort_by=None, sort_descending=True, return_indices=False, device=None):
+    """Contours to labels (data/cpn.py:292-358).
+
+    Args:
+        contours: ``Array/Tensor[num_contours, num_points, 2]`` (x, y) of a single image (numpy or CUDA tensor).
+        size: label image size ``(height, width)``.
+        rounded, clip, initial_depth, gap, dtype: as in the reference.  ``sort_by`` / ``sort_descending`` reorder the
+            contours first (labels then follow the sorted order, like the reference).
+    Returns:
+        ``[height, width, channels]`` label image: a CUDA ``int32`` tensor for tensor input, a numpy array of ``dtype``
+        for numpy input.  Contour ``k`` carries label ``k + 1``; overlapping objects go to further channels.
+    """
+    if ioa_thresh is not None or return_indices:
+        raise NotImplementedError('ioa_thresh / return_indices are outside the accelerated path.')
+    as_numpy = not isinstance(contours, torch.Tensor)
+    if as_numpy:
+        if isinstance(contours, (list, tuple)):
+            if len({np.asarray(c).shape for c in contours}) > 1:
+                raise NotImplementedError('ragged contour lists are outside the accelerated path (pad or resample).')
+            contours = np.stack([np.asarray(c) for c in contours]) if len(contours) else np.zeros((0, 1, 2), 'float32')
+        dev = torch.device(device if device is not None else 'cuda')
+        con = torch.as_tensor(np.asarray(contours, dtype=np.float32)).to(dev)
+    else:
+        if not contours.is_cuda:
+            raise RuntimeError('celldetection_b200.data.contours2labels runs on CUDA tensors only (no CPU fallback).')
+        con = contours.float()
+    if sort_by is not None:
+        order = torch.argsort(torch.as_tensor(sort_by).to(con.device), stable=True)
+        if sort_descending:
+            order = order.flip(0)
+        con = con[order]
+    con = con.contiguous()
+    K = int(con.shape[0])
+    S = int(con.shape[1]) if con.dim() == 3 else 1
+    H, W = int(size[0]), int(size[1])
+    lib = L.load()
+    dev = con.device
+    ws = torch.empty((int(lib.cpn_contours2labels_workspace_bytes(K, S)),), dtype=torch.uint8, device=dev)
+    info = torch.zeros((4,), dtype=torch.int32, device=dev)
+    channels = max(int(initial_depth), 4)
+    while True:
+        labels = torch.empty((H, W, channels), dtype=torch.int32, device=dev)
+        L.check(lib.cpn_contours2labels(L.ptr(con), K, S, H, W, int(bool(rounded)), int(bool(clip)), int(gap),
+                                        L.ptr(labels), channels, L.ptr(ws), L.ptr(info), L.stream_ptr()),
+                'contours2labels')
+        used, needed, err, _ = info.tolist()
+        if err:
+            raise RuntimeError('contours2labels: dependency wait timed out (is the GPU shared with another process?)')
+        if needed <= channels:
+            break
+        if channels >= 64:
+            raise RuntimeError('contours2labels: more than 64 label channels needed')
+        channels = min(64, max(needed, 2 * channels))
+    labels = labels[:, :, :max(used, int(initial_depth))]
+    if as_numpy:
+        return labels.cpu().numpy().astype(dtype)
+    return labels.contiguous()

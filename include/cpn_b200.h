@@ -252,6 +252,20 @@ int cpn_box_votes(const float* boxes, int64_t n_boxes, float iou_threshold, void
 int cpn_border_filter(const float* contours, const int32_t* tile_of_row, const float* tile_meta, int64_t K, int samples,
                       float padding, uint8_t* keep, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* label rasterisation (replaces cd.data.contours2labels, data/cpn.py:292-358, incl. render_contour :246-256 and the  */
+/* third-party cv2.drawContours(thickness=-1) polygon fill it calls; used by cpn_inference.py:809-813)               */
+/* ---------------------------------------------------------------------------------------------------------------- */
+size_t cpn_contours2labels_workspace_bytes(int64_t n_contours, int samples);
+/* contours [K,S,2] fp32 (x, y) -> labels [H,W,channels] int32 (zeroed by the call): contour k is rounded (half to even,
+ * `rounded`), clipped to the image (`clip`), filled exactly like OpenCV's integer scan-line polygon fill and written as
+ * label k+1 into the first channel whose bounding-box region dilated by `gap` is still empty -- the reference's
+ * sequential rule, evaluated as an ordered dependency schedule (one warp per contour).  info_dev [4] int32 receives
+ * [0] channels used, [1] channels needed (> channels: the result is incomplete, call again with more channels; the
+ * reference appends channels on demand), [2] non-zero on an internal scheduling time-out.  channels <= 64. */
+int cpn_contours2labels(const float* contours, int64_t n_contours, int samples, int H, int W, int rounded, int clip,
+                        int gap, int32_t* labels, int channels, void* workspace, int32_t* info_dev, void* stream);
+
 /* dst[i, :] = src[index[i], :] for rows of row_bytes (multiple of 4) bytes (resolve_keep_indices, cpn.py:53-60). */
 int cpn_gather_rows(const void* src, int64_t row_bytes, const int32_t* index, int64_t n_rows, void* dst, void* stream);
 

@@ -323,6 +323,51 @@ def mint_apply_ensemble(cd):
     np.savez_compressed(os.path.join(GOLDEN, 'apply_model_ensemble.npz'), **arrays)
 
 
+def synth_contours(rng, K, S, H, W, radius=(2., 14.)):
+    """CPN-like closed contours (random low-order Fourier shapes, inclusive linspace sampling like ops/cpn.py:67-81)."""
+    t = np.linspace(0, 1, S)
+    out = np.zeros((K, S, 2), np.float32)
+    for k in range(K):
+        order, r = rng.randint(1, 6), rng.uniform(*radius)
+        xy = np.array([rng.rand() * W, rng.rand() * H])[None] + sum(
+            rng.randn(2)[None] * r / (j + 1) * np.cos(2 * np.pi * (j + 1) * t)[:, None] +
+            rng.randn(2)[None] * r / (j + 1) * np.sin(2 * np.pi * (j + 1) * t)[:, None] for j in range(order))
+        out[k] = xy
+    return out
+
+
+def mint_contours2labels(cd):
+    """cd.data.contours2labels of the reference (cv2.drawContours fill + greedy channel assignment) on seeded contour
+    sets: sparse, dense (many channels), image-border clipping, degenerate (collapsed) contours, odd sample counts."""
+    import c2l_oracle as c2l
+    rng = np.random.RandomState(31)
+    arrays = {}
+    cases = [('sparse', 60, 32, 160, 200, (2., 9.)), ('dense', 150, 16, 64, 96, (3., 12.)),
+             ('border', 80, 64, 90, 120, (6., 25.)), ('odd', 40, 21, 70, 70, (1., 6.))]
+    for name, K, S, H, W, rad in cases:
+        con = synth_contours(rng, K, S, H, W, rad)
+        if name == 'odd':
+            con[3] = con[3, :1]                         # collapsed to a point
+            con[7, :, 1] = con[7, 0, 1]                 # horizontal segment
+            con[11] = np.round(con[11]) + 0.5           # exact .5 coordinates: np.round is half-to-even
+        want = cd.data.contours2labels(con.copy(), (H, W))
+        got = c2l.contours2labels(con.copy(), (H, W))
+        assert want.shape == got.shape and np.array_equal(want, got), name
+        arrays[f'{name}/contours'] = con
+        arrays[f'{name}/size'] = np.array([H, W])
+        arrays[f'{name}/labels'] = want.astype(np.int16)
+        print(f'contours2labels {name}: {K} contours -> {want.shape[2]} channels')
+    # unrounded / gap variants
+    con = synth_contours(rng, 50, 32, 80, 80, (2., 10.))
+    for tag, kw in (('noround', dict(rounded=False)), ('gap0', dict(gap=0)), ('depth3', dict(initial_depth=3))):
+        want = cd.data.contours2labels(con.copy(), (80, 80), **kw)
+        got = c2l.contours2labels(con.copy(), (80, 80), **kw)
+        assert want.shape == got.shape and np.array_equal(want, got), tag
+        arrays[f'{tag}/labels'] = want.astype(np.int16)
+    arrays['variants/contours'] = con
+    np.savez_compressed(os.path.join(GOLDEN, 'contours2labels.npz'), **arrays)
+
+
 def mint_keys(cd):
     """state_dict key -> shape of the three reference models (drop-in contract)."""
     out = {}
@@ -341,7 +386,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     cd = ref_shim.import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    which = sys.argv[1:] or ['keys', 'f2c', 'tiling', 'models', 'variants', 'apply', 'ensemble']
+    which = sys.argv[1:] or ['keys', 'f2c', 'tiling', 'models', 'variants', 'apply', 'ensemble', 'labels']
     if 'keys' in which:
         mint_keys(cd)
     if 'f2c' in which:
@@ -358,6 +403,8 @@ def main():
         mint_apply_model(cd)
     if 'ensemble' in which:
         mint_apply_ensemble(cd)
+    if 'labels' in which:
+        mint_contours2labels(cd)
 
 
 if __name__ == '__main__':

@@ -180,3 +180,38 @@ def test_oracle_ensemble_mask_and_voting_golden():
                             min_vote=1.5)
     assert 0 < len(res2['scores']) <= len(res['scores']) and len(res2['votes']) == len(res2['scores'])
     assert float(res2['votes'].min()) >= 1.5
+
+
+C2L_CASES = ['sparse', 'dense', 'border', 'odd']
+
+
+def test_oracle_contours2labels_golden():
+    """Label rasterisation (data/cpn.py:292-358): the oracle's restated OpenCV polygon fill + greedy channel rule against
+    label images minted from the reference's own contours2labels."""
+    import c2l_oracle as c2l
+    z = load_npz('contours2labels')
+    for name in C2L_CASES:
+        H, W = [int(v) for v in z[f'{name}/size']]
+        got = c2l.contours2labels(z[f'{name}/contours'].copy(), (H, W))
+        assert got.shape == z[f'{name}/labels'].shape and np.array_equal(got, z[f'{name}/labels']), name
+    con = z['variants/contours']
+    for tag, kw in (('noround', dict(rounded=False)), ('gap0', dict(gap=0)), ('depth3', dict(initial_depth=3))):
+        got = c2l.contours2labels(con.copy(), (80, 80), **kw)
+        assert got.shape == z[f'{tag}/labels'].shape and np.array_equal(got, z[f'{tag}/labels']), tag
+
+
+def test_oracle_polygon_fill_matches_opencv():
+    """The third-party piece of the path: cv2.drawContours(thickness=-1) (OpenCV, unpinned by the reference; the
+    installed version is the oracle) against the restated Bresenham + scan-line fill, on random integer polygons."""
+    cv2 = pytest.importorskip('cv2')
+    import c2l_oracle as c2l
+    rng = np.random.RandomState(0)
+    for trial in range(400):
+        n = rng.randint(1, 40)
+        pts = rng.randint(0, [12, 40, 25][trial % 3], size=(n, 2)).astype(np.int32)
+        xmin, ymin = pts.min(0)
+        xmax, ymax = pts.max(0)
+        a = np.zeros((ymax - ymin + 1, xmax - xmin + 1), np.int32)
+        a = cv2.drawContours(a, [pts.reshape(-1, 1, 2)], 0, 1, -1, offset=(int(-xmin), int(-ymin)))
+        m = c2l.fill_polygon(pts - [xmin, ymin], a.shape[1], a.shape[0])
+        assert np.array_equal(a > 0, m), pts.tolist()
