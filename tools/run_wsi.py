@@ -31,6 +31,7 @@ def main():
     ap.add_argument('--batch', type=int, default=16)
     ap.add_argument('--arch', default='CpnResNeXt101UNet')
     ap.add_argument('--precision', default='fp16')
+    ap.add_argument('--labels', action='store_true', help='also rasterise the stitched contours (contours2labels)')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -74,11 +75,21 @@ def main():
     h = hashlib.sha256()
     for k in ('boxes', 'scores', 'contours'):
         h.update(res[k].cpu().numpy().tobytes())
+    extra = {}
+    if args.labels and rank == 0:           # the step after the path (cpn_inference.py:809-813)
+        cd.data.contours2labels(res['contours'][:64], (args.size, args.size))
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        lab = cd.data.contours2labels(res['contours'], (args.size, args.size))
+        torch.cuda.synchronize()
+        extra = dict(labels_seconds=time.perf_counter() - t1, label_channels=int(lab.shape[2]),
+                     labelled_pixels=int((lab > 0).sum()))
+        del lab
     if rank == 0:
         print(json.dumps(dict(config='C4', arch=args.arch, size=args.size, crop=args.crop, stride=args.stride,
                               tiles=ntiles, n_gpus=world, seconds=dt, tiles_per_s=ntiles / dt,
                               detections=int(res['scores'].shape[0]), digest=h.hexdigest()[:16],
-                              precision=args.precision)), flush=True)
+                              precision=args.precision, **extra)), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
