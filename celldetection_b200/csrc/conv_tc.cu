@@ -278,8 +278,10 @@ __device__ __forceinline__ void load_res_chunk(const __half* rp, const int ch, R
 
 // PF: software-pipelined residual loads -- `rfirst` holds the residual of this warp's first chunk (loaded by the caller
 // BEFORE it waited for the accumulator: the residual does not depend on the MMAs), and the next chunk's residual is
-// requested before the current chunk's TMEM load is awaited.  Without it the epilogue of a 1x1 + residual layer, whose
-// mainloop is only 4-16 K blocks long, exposed one global-memory latency per chunk and ran longer than the mainloop.
+// requested into the same registers as soon as the current chunk's values have been consumed, i.e. ahead of the stores,
+// the next TMEM load and its wait.  Without it the epilogue of a 1x1 + residual layer, whose mainloop is only 4-16 K
+// blocks long, exposed one global-memory latency per chunk and ran longer than the mainloop (ncu: 72.8 us with the
+// residual vs 49.6 us without, same 1024 -> 1024 shape).
 template <int BN, bool PF>
 __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint32_t taddr, const int img, const int y,
                                               const int x, const int n_tile, const int n0, const int half,
@@ -352,11 +354,7 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
   for (int ch = half; ch < BN / 32; ch += 2) {
     uint32_t v[32];
     tmem_ld32(taddr + ch * 32, v);
-    ResChunk rn;
-    if (rp) {
-      if (!PF) load_res_chunk(rp, ch, rc);
-      else if (ch + 2 < BN / 32) load_res_chunk(rp, ch + 2, rn);   // next chunk's residual while TMEM is being read
-    }
+    if (!PF && rp) load_res_chunk(rp, ch, rc);
     tmem_ld_wait();
     if (valid) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
@@ -390,6 +388,7 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
           pl[q * 2 + 1] = *reinterpret_cast<uint32_t*>(&g1);
         }
       }
+      if (PF && rp && ch + 2 < BN / 32) load_res_chunk(rp, ch + 2, rc);   // rc is dead: request the next chunk now
       uint4* o4 = reinterpret_cast<uint4*>(op + ch * 32);
 #pragma unroll
       for (int q = 0; q < 4; ++q) o4[q] = packed[q];
@@ -399,7 +398,6 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
         for (int q = 0; q < 4; ++q) l4[q] = packed_lo[q];
       }
     }
-    if (PF) rc = rn;
   }
   }
 }
@@ -408,9 +406,10 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
 // Kernel
 // ---------------------------------------------------------------------------------------------------------------------
 template <int BN>
-// __maxnreg__ instead of __launch_bounds__(TC_THREADS, 1): ptxas caps the latter at 168 registers (it budgets for 384
-// threads), which spills the pipelined residual registers; 320 threads x 192 allocated registers fit the 64 K file.
-__global__ void __maxnreg__(200) conv_tc_kernel(const __grid_constant__ ConvTcParams p, int stages) {
+// Register budget: 10 warps spread 3/3/2/2 over the four SM sub-partitions of 16 K registers each, so a thread may use at
+// most 168 registers (3 x 32 x 168 <= 16384) -- ptxas derives exactly that cap from __launch_bounds__(320, 1); forcing
+// more with __maxnreg__ compiles but fails at launch ("too many resources requested").
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p, int stages) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;

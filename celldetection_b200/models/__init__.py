@@ -1,3 +1,4 @@
-from .cpn import CPN, CpnU22, CpnResNet18FPN, CpnResNeXt101UNet
+from . import cpn as _cpn
+from .cpn import *  # noqa: F401,F403  (CPN and every Cpn<Encoder><Decoder> class of models.graph.ARCHS)
 
-__all__ = ['CPN', 'CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet']
+__all__ = list(_cpn.__all__)

@@ -23,7 +23,6 @@ from ..ops import cpn as O
 from .graph import trace, ARCHS
 from .plan import Plan, WeightPack
 
-__all__ = ['CPN', 'CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet']
 
 PRECISIONS = ('fp16', 'fp16x3', 'fp32')
 
@@ -53,8 +52,8 @@ class CPN(nn.Module):
         """Contour Proposal Network (inference).
 
         Args:
-            backbone: architecture name, one of ``CpnU22 | CpnResNet18FPN | CpnResNeXt101UNet`` (the reference takes a
-                backbone *module*; here the backbone is part of the compiled plan).
+            backbone: architecture name, one of ``models.graph.ARCHS`` -- ``CpnU22`` and ``Cpn<ResNet-family><UNet|FPN>``
+                (the reference takes a backbone *module*; here the backbone is part of the compiled plan).
             order, nms_thresh, score_thresh, samples, classes, refinement, refinement_iterations, refinement_margin,
                 refinement_buckets: as in the reference (models/cpn.py:288-321).
             precision: ``'fp16'`` -- tcgen05 tensor-core engine, fp16 activations/weights, fp32 accumulation (default);
@@ -363,6 +362,6 @@ def _make(arch):
     return _Cpn
 
 
-CpnU22 = _make('CpnU22')                          # models/cpn.py:772
-CpnResNet18FPN = _make('CpnResNet18FPN')          # models/cpn.py:1250
-CpnResNeXt101UNet = _make('CpnResNeXt101UNet')    # models/cpn.py:930
+for _arch in ARCHS:      # CpnU22 (cpn.py:772), CpnResNeXt101UNet (:930), CpnResNet18FPN (:1250) and the rest of the family
+    globals()[_arch] = _make(_arch)
+__all__ = ['CPN'] + list(ARCHS)

@@ -1,4 +1,4 @@
-"""Model descriptions of the three configured Contour Proposal Networks as flat layer graphs.
+"""Model descriptions of the Contour Proposal Networks (U22 and the ResNet-family U-Net / FPN variants) as flat layer graphs.
 
 The reference expresses these networks as ``nn.Module`` trees (all paths relative to /root/reference/celldetection):
 ``CpnU22`` (models/cpn.py:772, unet.py:405 ``U22``), ``CpnResNet18FPN`` (cpn.py:1250, fpn.py:240) and
@@ -25,7 +25,30 @@ from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import List, Optional, Tuple
 
-ARCHS = ('CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet')
+# ResNet-family encoders of models/resnet.py:330-487: name -> (layers, bottleneck, groups, width_per_group)
+RESNETS = {
+    'ResNet18': ((2, 2, 2, 2), False, 1, 64), 'ResNet34': ((3, 4, 6, 3), False, 1, 64),
+    'ResNet50': ((3, 4, 6, 3), True, 1, 64), 'ResNet101': ((3, 4, 23, 3), True, 1, 64),
+    'ResNet152': ((3, 8, 36, 3), True, 1, 64),
+    'ResNeXt50': ((3, 4, 6, 3), True, 32, 4), 'ResNeXt101': ((3, 4, 23, 3), True, 32, 8),
+    'ResNeXt152': ((3, 8, 36, 3), True, 32, 8),
+    'WideResNet50': ((3, 4, 6, 3), True, 1, 128), 'WideResNet101': ((3, 4, 23, 3), True, 1, 128),
+}
+# Cpn<Encoder><Decoder> classes of models/cpn.py:930-1637 (U-Net: unet.py:591-716, FPN: fpn.py:240-322); the reference has
+# no CpnWideResNet*UNet.  The three BASELINE configurations come first.
+ARCHS = ('CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet') + tuple(
+    f'Cpn{e}{d}' for d in ('UNet', 'FPN') for e in RESNETS
+    if not (d == 'UNet' and e.startswith('Wide')) and f'Cpn{e}{d}' not in ('CpnResNet18FPN', 'CpnResNeXt101UNet'))
+
+
+def split_arch(arch):
+    """'CpnResNet50FPN' -> ('ResNet50', 'FPN'); 'CpnU22' -> ('U22', 'UNet')."""
+    if arch == 'CpnU22':
+        return 'U22', 'UNet'
+    for d in ('UNet', 'FPN'):
+        if arch.endswith(d) and arch[3:-len(d)] in RESNETS:
+            return arch[3:-len(d)], d
+    raise ValueError(arch)
 
 
 @dataclass
@@ -214,12 +237,7 @@ def _unet_encoder(g, x, p, cin, depth=5, base=64):
 
 def _resnet_encoder(g, x, p, cin, kind):
     """models/resnet.py:265-290 with fused_initial=False; blocks :56-116; _make_layer :119-193."""
-    if kind == 'resnet18':
-        layers, bottleneck, groups, width_per_group = (2, 2, 2, 2), False, 1, 64
-    elif kind == 'resnext101_32x8d':
-        layers, bottleneck, groups, width_per_group = (3, 4, 23, 3), True, 32, 8
-    else:
-        raise ValueError(kind)
+    layers, bottleneck, groups, width_per_group = RESNETS[kind]
     expansion = 4 if bottleneck else 1
     x = _conv_bn_act(g, x, f'{p}.0.0', f'{p}.0.1', cin, 64, 7, stride=2, bias=False)
     feats, chans = [x], [64]
@@ -361,16 +379,17 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
     g.spec['order_weights'] = ((order, 1), 'order_weights')   # buffer of CPN (cpn.py:406-412)
     bb = 'core.backbone'
     x = g.prep(in_channels)
-    if arch == 'CpnU22':
+    enc, dec = split_arch(arch)
+    if enc == 'U22':
         feats, chans = _unet_encoder(g, x, f'{bb}.body', in_channels)
         res, out_ch = _unet_decoder(g, feats, chans, f'{bb}.unet', bridges=0)
         head_feat, head_c, ref_feat, ref_c = res[1], out_ch[1], res[0], out_ch[0]
-    elif arch == 'CpnResNeXt101UNet':
-        feats, chans = _resnet_encoder(g, x, f'{bb}.body', in_channels, 'resnext101_32x8d')
+    elif dec == 'UNet':
+        feats, chans = _resnet_encoder(g, x, f'{bb}.body', in_channels, enc)
         res, out_ch = _unet_decoder(g, feats, chans, f'{bb}.unet', bridges=1)
         head_feat, head_c, ref_feat, ref_c = res[1], out_ch[1], res[0], out_ch[0]
     else:
-        feats, chans = _resnet_encoder(g, x, f'{bb}.body', in_channels, 'resnet18')
+        feats, chans = _resnet_encoder(g, x, f'{bb}.body', in_channels, enc)
         res = _fpn_decoder(g, feats, chans, f'{bb}.fpn')
         head_feat, head_c, ref_feat, ref_c = res[1], 256, res[0], 256
     # ---- heads (models/cpn.py:177-234, 238-283); module order: score, location, fourier, (uncertainty), refinement ----

@@ -42,12 +42,20 @@ import torch.nn.functional as F
 
 NMS_BATCH_SIZE = 50000  # ops/cpn.py:12
 
-ARCHS = {
-    # name: (backbone kind, encoder kind)
-    'CpnU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0'),
-    'CpnResNet18FPN': dict(decoder='fpn', encoder='resnet18', head_key='1', ref_key='0'),
-    'CpnResNeXt101UNet': dict(decoder='unet', encoder='resnext101_32x8d', head_key='1', ref_key='0'),
+# ResNet-family encoders (models/resnet.py:330-487): name -> (layers, bottleneck, groups, width_per_group)
+RESNETS = {
+    'ResNet18': ((2, 2, 2, 2), False, 1, 64), 'ResNet34': ((3, 4, 6, 3), False, 1, 64),
+    'ResNet50': ((3, 4, 6, 3), True, 1, 64), 'ResNet101': ((3, 4, 23, 3), True, 1, 64),
+    'ResNet152': ((3, 8, 36, 3), True, 1, 64),
+    'ResNeXt50': ((3, 4, 6, 3), True, 32, 4), 'ResNeXt101': ((3, 4, 23, 3), True, 32, 8),
+    'ResNeXt152': ((3, 8, 36, 3), True, 32, 8),
+    'WideResNet50': ((3, 4, 6, 3), True, 1, 128), 'WideResNet101': ((3, 4, 23, 3), True, 1, 128),
 }
+ARCHS = {'CpnU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0')}
+for _e in RESNETS:                       # models/cpn.py:930-1637 (the reference has no CpnWideResNet*UNet)
+    ARCHS[f'Cpn{_e}FPN'] = dict(decoder='fpn', encoder=_e, head_key='1', ref_key='0')
+    if not _e.startswith('Wide'):
+        ARCHS[f'Cpn{_e}UNet'] = dict(decoder='unet', encoder=_e, head_key='1', ref_key='0')
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -111,12 +119,9 @@ def _bottleneck(x, sd, p, stride, groups):
 def resnet_encoder(x, sd, p, kind):
     """models/resnet.py:265-290 with fused_initial=False (unet.py:584-587, fpn.py:233-236):
     body.0 = conv7x7 s2 + BN + ReLU, body.1 = Sequential(MaxPool(3, 2, 1), layer1), body.2..4 = layer2..4."""
-    if kind == 'resnet18':
-        layers, block, groups = (2, 2, 2, 2), _basic_block, None
-    elif kind == 'resnext101_32x8d':
-        layers, block, groups = (3, 4, 23, 3), _bottleneck, 32
-    else:
-        raise ValueError(kind)
+    layers, bottle, groups, _ = RESNETS[kind]     # widths are read off the state_dict's weight shapes
+    block = _bottleneck if bottle else _basic_block
+    groups = groups if bottle else None
     feats = OrderedDict()
     x = F.relu(_bn(_conv(x, sd, f'{p}.0.0', stride=2, padding=3), sd, f'{p}.0.1'))
     feats['0'] = x

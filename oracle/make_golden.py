@@ -374,6 +374,21 @@ def mint_keys(cd):
     for arch in ('CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet'):
         m = getattr(cd.models, arch)(3)
         out[arch] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    from celldetection_b200.models.graph import ARCHS as ALL_ARCHS
+    for arch in ALL_ARCHS[3:]:           # the rest of the ResNet family: keys + a numerical pin of the oracle, no vectors
+        m = getattr(cd.models, arch)(3).eval()
+        out[arch] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        sd = synth_state_dict(spec_of(m), seed=3)
+        sd._metadata = m.state_dict()._metadata
+        m.load_state_dict(sd)
+        torch.manual_seed(1)
+        x = torch.rand(1, 3, 64, 64)
+        with torch.no_grad():
+            ref = m.core(x)
+            got = orc.cpn_core(x, sd, arch)
+        for nm, a, b in zip(('scores', 'locations', 'refinement', 'fourier'), got, ref):
+            check_close(f'{arch}/{nm}', to_np(a), to_np(b), 1e-5)
+        print(f'{arch}: oracle == reference on a 64x64 tile')
     for _, arch, _, _, _, _, _, ctor, _ in VARIANT_CASES:
         m = getattr(cd.models, arch)(3, **ctor)
         out[variant_key(arch, ctor)] = [[k, list(v.shape)] for k, v in m.state_dict().items()]

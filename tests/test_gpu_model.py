@@ -222,7 +222,17 @@ def test_fp16x3_tensor_core_model_meets_parity_gate(name):
     assert st['vertices_within_half_px'] >= 0.99 * st['vertices'], st
 
 
-@pytest.mark.parametrize('arch,hw', [('CpnResNeXt101UNet', (90, 120)), ('CpnU22', (90, 120)), ('CpnResNet18FPN', (72, 200))])
+# the three BASELINE architectures at ragged sizes + the rest of the ResNet family (models/cpn.py:970-1637): basic and
+# bottleneck blocks, 32x4d / 32x8d grouped and wide (base_width 128) 3x3 convolutions, U-Net and FPN decoders
+@pytest.mark.parametrize('arch,hw', [('CpnResNeXt101UNet', (90, 120)), ('CpnU22', (90, 120)), ('CpnResNet18FPN', (72, 200)),
+                                     ('CpnResNet18UNet', (96, 128)), ('CpnResNet34UNet', (64, 96)),
+                                     ('CpnResNet50UNet', (96, 128)), ('CpnResNet101UNet', (64, 64)),
+                                     ('CpnResNet152UNet', (64, 64)), ('CpnResNeXt50UNet', (72, 104)),
+                                     ('CpnResNeXt152UNet', (64, 64)), ('CpnResNet34FPN', (96, 128)),
+                                     ('CpnResNet50FPN', (96, 128)), ('CpnResNet101FPN', (64, 64)),
+                                     ('CpnResNet152FPN', (64, 64)), ('CpnResNeXt50FPN', (96, 128)),
+                                     ('CpnResNeXt101FPN', (64, 96)), ('CpnResNeXt152FPN', (64, 64)),
+                                     ('CpnWideResNet50FPN', (96, 128)), ('CpnWideResNet101FPN', (64, 64))])
 def test_ragged_input_sizes_against_oracle(arch, hw):
     """Sizes that are not multiples of the encoder stride: partial conv tiles, non-integer nearest up-sampling factors
     (floor(dst * in / out)), odd max-pool extents, bilinear resize for the FPN refinement features.  Checked directly

@@ -36,15 +36,27 @@ for _ in range(3):
     times.append(e0.elapsed_time(e1))
 ms = float(np.median(times))
 # CPU port on a bounded sample: the first 2000 contours of the same set, cropped canvas not needed (same image size)
-n_cpu = 2000
+n_cpu = 2000                                   # same shapes at the same density: 2000 contours on a 2318 x 2318 image
+side = int(round(H * (n_cpu / K) ** 0.5))
+con_cpu = (base[rng.randint(0, 500, n_cpu)] + (rng.rand(n_cpu, 1, 2) * side).astype(np.float32)).astype(np.float32)
 t0 = time.time()
-c2l.contours2labels(con[:n_cpu].copy(), (2048, 2048), clip=True)
+c2l.contours2labels(con_cpu.copy(), (side, side), clip=True)
 cpu_s = time.time() - t0
+try:                                           # the third-party fill the reference calls (OpenCV), same sample, for scale
+    import cv2
+    t0 = time.time()
+    for c in np.round(con_cpu).astype(np.int32):
+        a = np.zeros((c[:, 1].max() - c[:, 1].min() + 1, c[:, 0].max() - c[:, 0].min() + 1), np.int32)
+        cv2.drawContours(a, [c.reshape(-1, 1, 2)], 0, 1, -1, offset=(int(-c[:, 0].min()), int(-c[:, 1].min())))
+    cv2_s = time.time() - t0
+except Exception:
+    cv2_s = None
 painted = int((lab > 0).sum())
 print(json.dumps(dict(metric='contours2labels contours/s (16384x16384, 1e5 contours x 128 samples)', value=K / (ms / 1e3),
                       unit='contours/s', ms=ms, channels=int(lab.shape[2]), painted_pixels=painted,
                       label_image_gb=lab.numel() * 4 / 1e9,
-                      cpu_port=dict(value=n_cpu / cpu_s, unit='contours/s', sample=f'{n_cpu} contours (clipped into 2048^2)',
+                      cpu_port=dict(value=n_cpu / cpu_s, unit='contours/s', sample=f'{n_cpu} contours on {side}x{side} (same density)',
                                     cores=1, kind='port'),
+                      opencv_fill_only_contours_per_s=(n_cpu / cv2_s if cv2_s else None),
                       reference_note='reference docstring: ~137 ms for 1284 contours x 128 points on 1000x1000 = 9.4e3 contours/s '
                                      '(data/cpn.py:298)')))
