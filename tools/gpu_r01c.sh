@@ -3,7 +3,7 @@
 # contours2labels micro-bench, C4 slide incl. label rasterisation, per-op profile.
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out; OUT=gpurun_out
-timeout -s KILL 900 python -m pytest tests/test_gpu_labels.py tests/test_gpu_post.py -m gpu -q --timeout 600 -x -p no:cacheprovider > $OUT/pytest_new.log 2>&1
+timeout -s KILL 900 python -m pytest tests/test_gpu_conv.py -m gpu -q --timeout 600 -x -p no:cacheprovider > $OUT/pytest_new.log 2>&1
 echo "pytest(new) rc=$?" >> $OUT/pytest_new.log; tail -25 $OUT/pytest_new.log
 timeout -s KILL 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > $OUT/pytest.log 2>&1
 echo "pytest rc=$?" >> $OUT/pytest.log; tail -15 $OUT/pytest.log
