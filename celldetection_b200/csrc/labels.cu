@@ -77,15 +77,21 @@ __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
 
 // ---- pass 2: ordered painting ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(C2L_WARPS * 32) c2l_paint_kernel(const C2LParams p, const GridBins bins) {
-  extern __shared__ int2 c2l_sm[];                      // [C2L_WARPS][S] vertices
+  extern __shared__ long long c2l_sm[];                 // per warp: [S] edge slopes (16.16), then [S] vertices
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  int2* v = c2l_sm + (size_t)wib * p.S;
+  long long* slope = c2l_sm + (size_t)wib * 2 * p.S;    // slope[e]: dx per scan line of edge (v[e-1] -> v[e])
+  int2* v = reinterpret_cast<int2*>(slope + p.S);
   const int gw = blockIdx.x * C2L_WARPS + wib, nw = gridDim.x * C2L_WARPS;
   const GridInfo g = *bins.gi;
   const int C = p.C;
   for (int k = gw; k < p.K; k += nw) {
     __syncwarp();
     for (int s = lane; s < p.S; s += 32) v[s] = p.pts[(long long)k * p.S + s];
+    __syncwarp();
+    for (int e = lane; e < p.S; e += 32) {              // OpenCV: edge.dx = (x1 - x0) / (y1 - y0), truncating, 16.16
+      const int2 a = v[e == 0 ? p.S - 1 : e - 1], b = v[e];
+      slope[e] = a.y == b.y ? 0 : (((long long)b.x - a.x) * XY_ONE) / ((long long)b.y - a.y);
+    }
     const int4 bb = p.bbox[k];
     const int ex0 = bb.x - p.gap, ey0 = bb.y - p.gap, ex1 = bb.z + p.gap, ey1 = bb.w + p.gap;   // inclusive
     __syncwarp();
@@ -188,9 +194,7 @@ __global__ void __launch_bounds__(C2L_WARPS * 32) c2l_paint_kernel(const C2LPara
             if (a.y == b.y) continue;
             const int2 lo = a.y < b.y ? a : b, hi = a.y < b.y ? b : a;
             if (y < lo.y || y >= hi.y) continue;
-            const long long num = ((long long)b.x - a.x) * XY_ONE, den = (long long)b.y - a.y;
-            const long long dxl = num / den;                                  // C++ truncating division, like OpenCV
-            const long long xe = (long long)lo.x * XY_ONE + dxl * (y - lo.y);
+            const long long xe = (long long)lo.x * XY_ONE + slope[e] * (y - lo.y);
             if ((xe > last_x || (xe == last_x && e > last_e)) && (xe < best_x || (xe == best_x && e < best_e))) {
               best_x = xe; best_e = e;
             }
@@ -258,7 +262,7 @@ extern "C" int cpn_contours2labels(const float* contours, int64_t K, int samples
   GridBins bins;
   if (grid_bin_boxes(p.ebox, (int)K, grid_ws, &bins, st)) return 1;
   // persistent grid: every warp must be resident (ordered spin-wait), so size it by occupancy
-  const size_t smem = (size_t)C2L_WARPS * samples * sizeof(int2);
+  const size_t smem = (size_t)C2L_WARPS * samples * (sizeof(int2) + sizeof(long long));
   static bool attr_set = false;
   if (!attr_set) {
     CPN_CHECK_CUDA(cudaFuncSetAttribute(c2l_paint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
