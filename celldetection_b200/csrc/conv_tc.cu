@@ -37,6 +37,7 @@ constexpr int TC_BW = 16, TC_BH = 8, TC_BM = 128, TC_BK = 64;
 constexpr int TC_EPI_WARPS = 8;                        // two warps per TMEM lane quadrant, each takes every other chunk
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_SMEM_BUDGET = 196608;  // bytes of operand stages
+constexpr int TC_STAGING_BYTES = TC_EPI_WARPS * 2048;   // epilogue_coalesced: 32 rows x 64 B per epilogue warp
 constexpr int TC_PROJ_SMEM_MAX = 32768; // fused projection weights (fp32): up to 4 heads x 8 outputs x 256 mid channels
 
 constexpr int TC_MAX_HEADS = 4;    // fused ReadOut projections: one per N tile
@@ -75,6 +76,7 @@ struct ConvTcParams {
   int split_lofirst;                 // split mode: run the two correction passes before the main pass
   int split, a_lo, out_lo, res_lo;   // CPN_DT_F16X2: 3 passes per 64-channel block (A_hi W_hi, A_lo W_hi, A_hi W_lo);
                                      // element distance hi -> lo half in the A / output / residual buffers
+  int coalesce;             // conv_tc_kernel: smem-staged, line-coalesced residual loads / output stores (epilogue_coalesced)
   int rotate;               // start each CTA's K loop at a different (tap, block): de-correlates the L2 reads of the shared weights   // 1: the patch is ONE box {64, PW, PH, 1} with SWIZZLE_128B (128-byte pixel rows)
 };
 
@@ -403,9 +405,101 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Line-coalesced epilogue of conv_tc_kernel (fp16, no fused projection).  TMEM hands every thread one output pixel (row)
+// and 32 consecutive channels (64 bytes), so direct global accesses touch 32 different lines per warp instruction; ncu
+// showed the 1x1 layers of the encoder bound by exactly that (time proportional to the bytes moved through the LSU at
+// ~2 TB/s, tensor pipe 8-45 % active, DRAM 12-35 %).  Here each warp owns a 2 KB staging tile (32 rows x 64 B, 16-byte
+// slots XOR-swizzled with (row >> 1) & 3: conflict-free for both access patterns): residual and output cross it so that
+// the GLOBAL accesses are made in the transposed role -- lane l moves 16-byte segment l & 3 of rows i * 8 + (l >> 2) --
+// i.e. 8 rows x 64 contiguous bytes per instruction, a quarter of the wavefronts.  The residual of the next chunk is in
+// flight (registers) while the current one is computed; the first chunk's is requested before the accumulator barrier.
+// ---------------------------------------------------------------------------------------------------------------------
+struct CoalRows {
+  uint32_t ooff[4], roff[4];   // element offsets (out / residual) of this lane's four rows at its 16-byte segment
+  uint32_t okmask;             // bit i: row i is inside the image
+};
+
+__device__ __forceinline__ void coal_rows(const ConvTcParams& p, const int img, const int ty0, const int tx0,
+                                          const int n0, const int quad, const int lane, CoalRows& c) {
+  c.okmask = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = quad * 32 + i * 8 + (lane >> 2);
+    const int y = ty0 + r / TC_BW, x = tx0 + r % TC_BW;
+    const bool ok = y < p.Ho && x < p.Wo;
+    c.okmask |= ok ? (1u << i) : 0u;
+    c.ooff[i] = ok ? (uint32_t)((((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0 + (lane & 3) * 8) : 0u;
+    c.roff[i] = 0u;
+    if (p.res && ok) {
+      const int ry = (p.res_h == p.Ho) ? y : (int)(((long long)y * p.res_h) / p.Ho);
+      const int rx = (p.res_w == p.Wo) ? x : (int)(((long long)x * p.res_w) / p.Wo);
+      c.roff[i] = (uint32_t)((((long long)img * p.res_h + ry) * p.res_w + rx) * p.res_pitch + n0 + (lane & 3) * 8);
+    }
+  }
+}
+
+__device__ __forceinline__ void coal_load_res(const ConvTcParams& p, const CoalRows& c, const int ch, uint4 (&rg)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (c.okmask & (1u << i)) rg[i] = __ldg(reinterpret_cast<const uint4*>(p.res + c.roff[i] + ch * 32));
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_coalesced(const ConvTcParams& p, const uint32_t taddr, const CoalRows& c,
+                                                   const int n0, const int half, const int lane, uint4* stg,
+                                                   uint4 (&rg)[4]) {
+  const int q = lane & 3, rsub = lane >> 2;
+  const bool has_res = p.res != nullptr;
+#pragma unroll 1
+  for (int ch = half; ch < BN / 32; ch += 2) {
+    uint32_t v[32];
+    tmem_ld32(taddr + ch * 32, v);
+    uint4 rr[4];
+    if (has_res) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const int r = i * 8 + rsub; stg[r * 4 + (q ^ ((r >> 1) & 3))] = rg[i]; }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rr[k] = stg[lane * 4 + (k ^ ((lane >> 1) & 3))];
+      if (ch + 2 < BN / 32) coal_load_res(p, c, ch + 2, rg);          // next chunk's residual while this one computes
+    }
+    tmem_ld_wait();
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
+    uint32_t* pk = reinterpret_cast<uint32_t*>(rr);                  // results overwrite the residual registers in place
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 b = p.bias ? __ldg(b4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float f0 = __uint_as_float(v[k * 4 + 0]) + b.x, f1 = __uint_as_float(v[k * 4 + 1]) + b.y;
+      float f2 = __uint_as_float(v[k * 4 + 2]) + b.z, f3 = __uint_as_float(v[k * 4 + 3]) + b.w;
+      if (has_res) {
+        const __half2 r0 = *reinterpret_cast<const __half2*>(&rw[k * 2]);
+        const __half2 r1 = *reinterpret_cast<const __half2*>(&rw[k * 2 + 1]);
+        f0 += __low2float(r0); f1 += __high2float(r0); f2 += __low2float(r1); f3 += __high2float(r1);
+      }
+      if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+      const __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
+      pk[k * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h0);
+      pk[k * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+    }
+    __syncwarp();                                                    // every lane has read its residual row
+#pragma unroll
+    for (int k = 0; k < 4; ++k) stg[lane * 4 + (k ^ ((lane >> 1) & 3))] = rr[k];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 8 + rsub;
+      if (c.okmask & (1u << i))
+        *reinterpret_cast<uint4*>(p.out + c.ooff[i] + ch * 32) = stg[r * 4 + (q ^ ((r >> 1) & 3))];
+    }
+    __syncwarp();                                                    // staging tile free for the next chunk
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool COAL>
 // Register budget: 10 warps spread 3/3/2/2 over the four SM sub-partitions of 16 K registers each, so a thread may use at
 // most 168 registers (3 x 32 x 168 <= 16384) -- ptxas derives exactly that cap from __launch_bounds__(320, 1); forcing
 // more with __maxnreg__ compiles but fails at launch ("too many resources requested").
@@ -429,8 +523,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const int nk = p.R * p.S * p.cblocks;  // K blocks per tile
   // fused projection weights live behind the operand stages: [head][cout][BN] fp32
-  float* proj_w = reinterpret_cast<float*>(smem_raw + ((smem_base - smem_u32(smem_raw)) + stages * STAGE_BYTES));
-  if (p.nproj > 0) {
+  // behind the operand stages: the epilogue staging tiles (p.coalesce) or the fused projection weights (p.nproj > 0)
+  uint8_t* tail = smem_raw + ((smem_base - smem_u32(smem_raw)) + stages * STAGE_BYTES);
+  float* proj_w = reinterpret_cast<float*>(tail);
+  if (!COAL && p.nproj > 0) {
     int off = 0;
     for (int h = 0; h < p.nproj; ++h) {
       const int nw = p.proj[h].cout * BN;
@@ -540,7 +636,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // ================================ epilogue (8 warps, 128 rows x 2 column halves) ================================
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;   // which of the two warps of this quadrant (takes chunks ch % 2 == half)
-    if (p.nproj > 0 && half == 1) {     // the fused-projection epilogue keeps a whole row per thread: 4 warps only
+    if (!COAL && p.nproj > 0 && half == 1) {     // the fused-projection epilogue keeps a whole row per thread: 4 warps only
       // fall through to the teardown barrier
     } else {
     const int row = quad * 32 + lane;
@@ -552,8 +648,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const long long m_tile = tile / p.tiles_n;
       const int img = (int)(m_tile / tiles_per_img);
       const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
-      const int y = (t_in / p.tiles_x) * TC_BH + py, x = (t_in % p.tiles_x) * TC_BW + px;
+      const int ty0 = (t_in / p.tiles_x) * TC_BH, tx0 = (t_in % p.tiles_x) * TC_BW;
+      const int y = ty0 + py, x = tx0 + px;
       const int n0 = n_tile * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * BN;
+      if (COAL) {
+        CoalRows cr;
+        coal_rows(p, img, ty0, tx0, n0, quad, lane, cr);
+        uint4 rg[4];
+        if (p.res) coal_load_res(p, cr, half, rg);   // first chunk's residual: in flight while the MMAs still run
+        mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
+        tc_fence_after();
+        epilogue_coalesced<BN>(p, taddr, cr, n0, half, lane, reinterpret_cast<uint4*>(tail) + (warp - 2) * 128, rg);
+      } else {
       ResChunk rfirst;
       {   // residual of the first chunk: requested while the MMAs of this tile are still running
         const __half* rp0 = residual_row(p, img, y, x, n0);
@@ -561,8 +668,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * BN;
       epilogue_rows<BN, true>(p, taddr, img, y, x, n_tile, n0, half, proj_w, &rfirst);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
@@ -965,7 +1072,16 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   pl->stages = TC_SMEM_BUDGET / stage_bytes;
   if (pl->stages > 8) pl->stages = 8;
   pl->proj_smem_bytes = 0;
-  pl->smem_bytes = pl->stages * stage_bytes + 1024;
+  {
+    // line-coalesced epilogue (CPN_COALESCE=0 disables): single-precision-storage layers whose tensors can be
+    // addressed with 32-bit element offsets; conv_tc_fuse_proj switches it off again for fused ReadOut heads
+    static int coal_env = -1;
+    if (coal_env < 0) { const char* e = getenv("CPN_COALESCE"); coal_env = (e && atoi(e) == 0) ? 0 : 1; }
+    const long long out_elems = (long long)op.dst.n * op.dst.h * op.dst.w * op.dst.pitch;
+    const long long res_elems = op.res.n ? (long long)op.res.n * op.res.h * op.res.w * op.res.pitch : 0;
+    p.coalesce = (coal_env && !split && !p.halo && out_elems < (1ll << 31) && res_elems < (1ll << 31)) ? 1 : 0;
+  }
+  pl->smem_bytes = pl->stages * stage_bytes + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
   if (p.halo) pl->smem_bytes = p.nb_stages * bn * TC_BK * 2 + 2 * 8 * p.plane_stride + 1024;
   const long long sms = sm_count();
   pl->grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
@@ -973,17 +1089,22 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   return 0;
 }
 
-template <int BN>
-static int launch_bn(const ConvTcPlan* pl, cudaStream_t st) {
+template <int BN, bool COAL>
+static int launch_bn2(const ConvTcPlan* pl, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, COAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         TC_SMEM_BUDGET + 1024 + TC_PROJ_SMEM_MAX));
     attr_set = true;
   }
-  conv_tc_kernel<BN><<<pl->grid, TC_THREADS, pl->smem_bytes, st>>>(pl->p, pl->stages);
+  conv_tc_kernel<BN, COAL><<<pl->grid, TC_THREADS, pl->smem_bytes, st>>>(pl->p, pl->stages);
   CPN_CHECK_LAUNCH();
   return 0;
+}
+
+template <int BN>
+static int launch_bn(const ConvTcPlan* pl, cudaStream_t st) {
+  return pl->p.coalesce ? launch_bn2<BN, true>(pl, st) : launch_bn2<BN, false>(pl, st);
 }
 
 template <int BN, int MSUB>
@@ -1038,6 +1159,7 @@ int conv_tc_fuse_proj(ConvTcPlan* pl, int n, const cpn_op_t* projs, const char* 
   CPN_REQUIRE(total <= TC_PROJ_SMEM_MAX, "conv_tc: fused projection weights (%d B) exceed %d B", total, TC_PROJ_SMEM_MAX);
   pl->p.nproj = n;
   pl->proj_smem_bytes = total;
+  if (pl->p.coalesce) { pl->p.coalesce = 0; pl->smem_bytes -= TC_STAGING_BYTES; }   // the tail holds the projection weights
   pl->smem_bytes += total;
   return 0;
 }
