@@ -419,13 +419,15 @@ struct CoalRows {
   uint32_t okmask;             // bit i: row i is inside the image
 };
 
+// WLOG2: log2 of the accumulator's pixel-tile width (row r of the accumulator is pixel (r >> WLOG2, r & (2^WLOG2 - 1)))
+template <int WLOG2>
 __device__ __forceinline__ void coal_rows(const ConvTcParams& p, const int img, const int ty0, const int tx0,
                                           const int n0, const int quad, const int lane, CoalRows& c) {
   c.okmask = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = quad * 32 + i * 8 + (lane >> 2);
-    const int y = ty0 + r / TC_BW, x = tx0 + r % TC_BW;
+    const int y = ty0 + (r >> WLOG2), x = tx0 + (r & ((1 << WLOG2) - 1));
     const bool ok = y < p.Ho && x < p.Wo;
     c.okmask |= ok ? (1u << i) : 0u;
     c.ooff[i] = ok ? (uint32_t)((((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0 + (lane & 3) * 8) : 0u;
@@ -654,7 +656,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * BN;
       if (COAL) {
         CoalRows cr;
-        coal_rows(p, img, ty0, tx0, n0, quad, lane, cr);
+        coal_rows<4>(p, img, ty0, tx0, n0, quad, lane, cr);   // TC_BW = 16
         uint4 rg[4];
         if (p.res) coal_load_res(p, cr, half, rg);   // first chunk's residual: in flight while the MMAs still run
         mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
@@ -704,7 +706,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TCH_THREADS = 128 + 32 * TC_EPI_WARPS;   // B producer, MMA issuer 0, A producer, MMA issuer 1, epilogue
 
-template <int BN, int MSUB>
+template <int BN, int MSUB, bool COAL>
 __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t TMEM_COLS = 2 * MSUB * BN;
@@ -726,8 +728,10 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
   const uint32_t patch_bytes = 8u * (uint32_t)p.plane_stride;         // (sw128 mode: plane_stride = patch / 8)
   const uint32_t a_base = smem_base + nb * B_BYTES;                    // 2 patches behind the B ring
   const uint32_t a_tx = 8u * (uint32_t)(p.ph * p.pw * 16);            // bytes the box load(s) deliver
-  float* proj_w = reinterpret_cast<float*>(smem_raw + ((a_base - smem_u32(smem_raw)) + 2 * patch_bytes));
-  if (p.nproj > 0) {
+  // behind the patches: the epilogue staging tiles (COAL) or the fused projection weights (p.nproj > 0)
+  uint8_t* tail = smem_raw + ((a_base - smem_u32(smem_raw)) + 2 * patch_bytes);
+  float* proj_w = reinterpret_cast<float*>(tail);
+  if (!COAL && p.nproj > 0) {
     int off = 0;
     for (int h = 0; h < p.nproj; ++h) {
       const int nw = p.proj[h].cout * BN;
@@ -886,7 +890,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
     } else {
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
-    if (!(p.nproj > 0 && half == 1)) {
+    if (COAL || !(p.nproj > 0 && half == 1)) {
       const int row = quad * 32 + lane;
       const int py = row >> 3, px = row & 7;
       int acc = 0;
@@ -896,13 +900,23 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
         const long long m_tile = tile / p.tiles_n;
         const int img = (int)(m_tile / tiles_per_img);
         const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
-        const int y = (t_in / p.tiles_x) * TH + py, xb = (t_in % p.tiles_x) * TW + px;
+        const int ty0 = (t_in / p.tiles_x) * TH, tx0 = (t_in % p.tiles_x) * TW;
+        const int y = ty0 + py, xb = tx0 + px;
         mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int j = 0; j < MSUB; ++j) {
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * MSUB + j) * BN);
-          epilogue_rows<BN, false>(p, taddr, img, y, xb + 8 * j, n_tile, n_tile * BN, half, proj_w);
+          if (COAL) {     // line-coalesced stores / residual loads through the warp's staging tile (8-pixel-wide sub-tile)
+            CoalRows cr;
+            coal_rows<3>(p, img, ty0, tx0 + 8 * j, n_tile * BN, quad, lane, cr);
+            uint4 rg[4];
+            if (p.res) coal_load_res(p, cr, half, rg);
+            epilogue_coalesced<BN>(p, taddr, cr, n_tile * BN, half, lane, reinterpret_cast<uint4*>(tail) + (warp - 4) * 128,
+                                   rg);
+          } else {
+            epilogue_rows<BN, false>(p, taddr, img, y, xb + 8 * j, n_tile, n_tile * BN, half, proj_w);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -1079,10 +1093,12 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
     if (coal_env < 0) { const char* e = getenv("CPN_COALESCE"); coal_env = (e && atoi(e) == 0) ? 0 : 1; }
     const long long out_elems = (long long)op.dst.n * op.dst.h * op.dst.w * op.dst.pitch;
     const long long res_elems = op.res.n ? (long long)op.res.n * op.res.h * op.res.w * op.res.pitch : 0;
-    p.coalesce = (coal_env && !split && !p.halo && out_elems < (1ll << 31) && res_elems < (1ll << 31)) ? 1 : 0;
+    static int coal_halo_env = -1;   // CPN_COALESCE_HALO=0: keep the direct epilogue in conv_halo_kernel only (A/B switch)
+    if (coal_halo_env < 0) { const char* e = getenv("CPN_COALESCE_HALO"); coal_halo_env = (e && atoi(e) == 0) ? 0 : 1; }
+    p.coalesce = (coal_env && !split && (coal_halo_env || !p.halo) && out_elems < (1ll << 31) && res_elems < (1ll << 31)) ? 1 : 0;
   }
   pl->smem_bytes = pl->stages * stage_bytes + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
-  if (p.halo) pl->smem_bytes = p.nb_stages * bn * TC_BK * 2 + 2 * 8 * p.plane_stride + 1024;
+  if (p.halo) pl->smem_bytes = p.nb_stages * bn * TC_BK * 2 + 2 * 8 * p.plane_stride + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
   const long long sms = sm_count();
   pl->grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
   *out = pl;
@@ -1107,17 +1123,22 @@ static int launch_bn(const ConvTcPlan* pl, cudaStream_t st) {
   return pl->p.coalesce ? launch_bn2<BN, true>(pl, st) : launch_bn2<BN, false>(pl, st);
 }
 
-template <int BN, int MSUB>
-static int launch_halo(const ConvTcPlan* pl, cudaStream_t st) {
+template <int BN, int MSUB, bool COAL>
+static int launch_halo2(const ConvTcPlan* pl, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, MSUB, COAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         TC_SMEM_BUDGET + 1024 + TC_PROJ_SMEM_MAX));
     attr_set = true;
   }
-  conv_halo_kernel<BN, MSUB><<<pl->grid, TCH_THREADS, pl->smem_bytes, st>>>(pl->p);
+  conv_halo_kernel<BN, MSUB, COAL><<<pl->grid, TCH_THREADS, pl->smem_bytes, st>>>(pl->p);
   CPN_CHECK_LAUNCH();
   return 0;
+}
+
+template <int BN, int MSUB>
+static int launch_halo(const ConvTcPlan* pl, cudaStream_t st) {
+  return pl->p.coalesce ? launch_halo2<BN, MSUB, true>(pl, st) : launch_halo2<BN, MSUB, false>(pl, st);
 }
 
 int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t st) {
