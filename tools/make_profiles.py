@@ -93,14 +93,14 @@ def main():
                 v = float(v.replace(',', ''))
                 if k == 'gpu__time_duration.sum':
                     v = v / 1e3 if u == 'ns' else (v * 1e3 if u == 'ms' else v)        # -> us
-                if k.endswith('bytes.sum') or k.startswith('dram__bytes'):
-                    v = v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
+                if k.endswith('bytes.sum') or k.startswith('dram__bytes') or k.startswith('launch__shared'):
+                    v = v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u.split('/')[0], 1)
                 return v * scale
             except Exception:
                 return float('nan')
         lines = ['# ncu --set full --clock-control none, one launch per kernel class (times are cold-cache, serialised)',
                  f'# {"kernel":58s} {"grid":>6s} {"us":>9s} {"tensor%":>8s} {"dram%":>6s} {"dramGB/s":>9s} {"readMB":>8s} '
-                 f'{"writeMB":>8s} {"L2->SM MB":>10s} {"L2hit%":>7s} {"regs":>5s} {"smemKB":>7s}']
+                 f'{"writeMB":>8s} {"L2hit%":>7s} {"regs":>5s} {"smemKB":>7s}']
         for d in res:
             kn = re.sub(r'\(.*', '', d['Kernel Name'][0]).replace('void ', '').replace('cpn::', '')[:58]
             us = val(d, 'gpu__time_duration.sum')
@@ -108,11 +108,14 @@ def main():
             lines.append(f'{kn:60s} {d["Grid Size"][0].split(",")[0].strip("( "):>6s} {us:9.1f} '
                          f'{val(d, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"):8.1f} '
                          f'{val(d, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"):6.1f} '
-                         f'{(rd + wr) / us / 1e3:9.0f} {rd / 1e6:8.1f} {wr / 1e6:8.1f} {val(d, "lts__t_bytes.sum") / 1e6:10.1f} '
+                         f'{(rd + wr) / us / 1e3:9.0f} {rd / 1e6:8.1f} {wr / 1e6:8.1f} '
                          f'{val(d, "lts__t_sector_hit_rate.pct"):7.1f} {val(d, "launch__registers_per_thread"):5.0f} '
-                         f'{val(d, "launch__shared_mem_per_block_dynamic") / 1024:7.1f}')
+                         f'{val(d, "launch__shared_mem_per_block_dynamic") / 1e3:7.1f}')
         open(os.path.join(PROF, f'{TAG}_{name}.txt'), 'w').write('\n'.join(lines) + '\n')
-    for src, dst in (('plan_profile_fp16x3.txt', f'{TAG}_plan_profile_fp16x3.txt'),
+    for src, dst in (('plan_profile_fp16x3.txt', f'{TAG}_plan_profile_fp16x3.txt'), ('plan_profile_c2.txt', f'{TAG}_plan_profile_c2.txt'),
+                     ('bench_c2l.log', f'{TAG}_bench_c2l.log'), ('profile_post.txt', f'{TAG}_profile_post.txt'),
+                     ('bench_reference.log', f'{TAG}_bench_reference.log'), ('wsi_16384_n1.log', f'{TAG}_wsi_16384_n1.log'),
+                     ('bench_nocoal.log', f'{TAG}_bench_direct_epilogue.log'), ('smoke.log', f'{TAG}_smoke.log'),
                      ('parity_report_hifirst.json', f'{TAG}_parity_report_fp16x3_hi_first.json'),
                      ('plan_profile.txt', f'{TAG}_plan_profile.txt'), ('parity_report.json', f'{TAG}_parity_report.json'),
                      ('bench_fp16.log', f'{TAG}_bench_fp16.log'), ('bench_decode_minb3.log', f'{TAG}_bench_decode.log'),
