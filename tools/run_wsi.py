@@ -73,8 +73,14 @@ def main():
     slices, shape = cd.get_tiling_slices((args.size, args.size), args.crop, args.stride)
     ntiles = shape[0] * shape[1]
     h = hashlib.sha256()
+    parts = {}
     for k in ('boxes', 'scores', 'contours'):
-        h.update(res[k].cpu().numpy().tobytes())
+        b = res[k].cpu().numpy().tobytes()
+        h.update(b)
+        parts[k] = hashlib.sha256(b).hexdigest()[:8]
+    # order-independent digest: rows sorted by (score, box) -- separates "same set, different order" from "different values"
+    rows = np.concatenate((res['scores'].cpu().numpy()[:, None], res['boxes'].cpu().numpy()), 1)
+    parts['set'] = hashlib.sha256(rows[np.lexsort(rows.T[::-1])].tobytes()).hexdigest()[:8]
     extra = {}
     if args.labels and rank == 0:           # the step after the path (cpn_inference.py:809-813)
         cd.data.contours2labels(res['contours'][:64], (args.size, args.size))
@@ -89,7 +95,7 @@ def main():
         print(json.dumps(dict(config='C4', arch=args.arch, size=args.size, crop=args.crop, stride=args.stride,
                               tiles=ntiles, n_gpus=world, seconds=dt, tiles_per_s=ntiles / dt,
                               detections=int(res['scores'].shape[0]), digest=h.hexdigest()[:16],
-                              precision=args.precision, **extra)), flush=True)
+                              precision=args.precision, digests=parts, **extra)), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
