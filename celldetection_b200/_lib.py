@@ -75,6 +75,8 @@ SYMBOLS = {
     'cpn_border_filter': (_I, [_P, _P, _P, _I64, _I, _F, _P, _P]),
     'cpn_contours2labels_workspace_bytes': (_SZ, [_I64, _I]),
     'cpn_contours2labels': (_I, [_P, _I64, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
+    'cpn_resolve_label_channels_workspace_bytes': (_SZ, [_I, _I]),
+    'cpn_resolve_label_channels': (_I, [_P, _I, _I, _I, _I, _P, _P, ctypes.POINTER(_I), _P]),
     'cpn_gather_rows': (_I, [_P, _I64, _P, _I64, _P, _P]),
 }
 

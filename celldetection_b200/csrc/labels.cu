@@ -279,3 +279,99 @@ extern "C" int cpn_contours2labels(const float* contours, int64_t K, int samples
   CPN_CHECK_LAUNCH();
   return 0;
 }
+
+// =====================================================================================================================
+// resolve_label_channels (data/cpn.py:361-398, method='dilation', 3x3 cross kernel): channel image [H,W,C] -> flat label
+// image [H,W].  Pixels covered by exactly one object keep its label; pixels covered by several start at 0 and are filled
+// by repeated grey dilation (max over the pixel and its 4 neighbours of the previous iterate -- Jacobi sweeps, exactly
+// like `lbl[m] = cv2.dilate(lbl)[m]`) until nothing changes or max_iter sweeps ran.  HBM-bound integer work.
+// =====================================================================================================================
+namespace cpn {
+
+__global__ void rlc_init_kernel(const int32_t* __restrict__ labels, long long pixels, int C, int32_t* __restrict__ flat,
+                                uint8_t* __restrict__ overlap, int* __restrict__ flags) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+  const int32_t* px = labels + i * C;
+  int cnt = 0;
+  int32_t mx = px[0];
+  for (int c = 0; c < C; ++c) { const int32_t v = px[c]; cnt += v > 0 ? 1 : 0; mx = max(mx, v); }
+  // no overlap anywhere: the result is labels.max(-1); otherwise cores keep max, everything else starts at 0
+  overlap[i] = cnt > 1 ? 1 : 0;
+  flat[i] = cnt > 1 ? 0 : mx;             // provisional: plain max for non-overlap pixels (fixed up below if needed)
+  if (cnt > 1) atomicOr(flags, 1);
+  if (cnt == 0 && mx != 0) atomicOr(flags, 2);   // negative labels present (max over a pixel without foreground)
+}
+
+// with overlaps the reference zero-fills every pixel that is not a core (mask_sm == 1), including negative labels
+__global__ void rlc_fix_kernel(const int32_t* __restrict__ labels, long long pixels, int C, int32_t* __restrict__ flat) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+  const int32_t* px = labels + i * C;
+  int cnt = 0;
+  for (int c = 0; c < C; ++c) cnt += px[c] > 0 ? 1 : 0;
+  if (cnt == 0) flat[i] = 0;
+}
+
+__global__ void rlc_sweep_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                 const uint8_t* __restrict__ overlap, int H, int W, int* __restrict__ changed) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)H * W) return;
+  int32_t v = in[i];
+  if (overlap[i] && v <= 0) {
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    int32_t m = v;
+    if (y > 0) m = max(m, in[i - W]);
+    if (y + 1 < H) m = max(m, in[i + W]);
+    if (x > 0) m = max(m, in[i - 1]);
+    if (x + 1 < W) m = max(m, in[i + 1]);
+    if (m != v) { v = m; *changed = 1; }
+  }
+  out[i] = v;
+}
+
+}  // namespace cpn
+
+extern "C" size_t cpn_resolve_label_channels_workspace_bytes(int H, int W) {
+  return al((size_t)H * W * sizeof(int32_t)) + al((size_t)H * W) + 1024;
+}
+
+extern "C" int cpn_resolve_label_channels(const int32_t* labels, int H, int W, int channels, int max_iter, int32_t* flat,
+                                          void* workspace, int* sweeps_host, void* stream) {
+  CPN_REQUIRE(labels && flat && workspace && H > 0 && W > 0 && channels >= 1, "resolve_label_channels: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long pixels = (long long)H * W;
+  char* b = reinterpret_cast<char*>(workspace);
+  int32_t* tmp = reinterpret_cast<int32_t*>(b);
+  uint8_t* overlap = reinterpret_cast<uint8_t*>(b + al((size_t)pixels * sizeof(int32_t)));
+  int* flags = reinterpret_cast<int*>(b + al((size_t)pixels * sizeof(int32_t)) + al((size_t)pixels));
+  CPN_CHECK_CUDA(cudaMemsetAsync(flags, 0, 64, st));
+  const int tb = 256;
+  const int gb = (int)((pixels + tb - 1) / tb);
+  rlc_init_kernel<<<gb, tb, 0, st>>>(labels, pixels, channels, flat, overlap, flags);
+  CPN_CHECK_LAUNCH();
+  int h_flags = 0;
+  CPN_CHECK_CUDA(cudaMemcpyAsync(&h_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CPN_CHECK_CUDA(cudaStreamSynchronize(st));
+  int sweeps = 0;
+  if (h_flags & 1) {
+    if (h_flags & 2) { rlc_fix_kernel<<<gb, tb, 0, st>>>(labels, pixels, channels, flat); CPN_CHECK_LAUNCH(); }
+    int32_t *cur = flat, *nxt = tmp;
+    int* changed = flags + 4;
+    while (sweeps < max_iter) {
+      CPN_CHECK_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), st));
+      rlc_sweep_kernel<<<gb, tb, 0, st>>>(cur, nxt, overlap, H, W, changed);
+      CPN_CHECK_LAUNCH();
+      ++sweeps;
+      int32_t* t = cur; cur = nxt; nxt = t;
+      int h_changed = 0;
+      CPN_CHECK_CUDA(cudaMemcpyAsync(&h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CPN_CHECK_CUDA(cudaStreamSynchronize(st));
+      if (!h_changed) break;
+    }
+    if (cur != flat) CPN_CHECK_CUDA(cudaMemcpyAsync(flat, cur, (size_t)pixels * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  }
+  if (sweeps_host) *sweeps_host = sweeps;
+  return 0;
+}
+

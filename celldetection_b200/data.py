@@ -8,7 +8,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ['contours2labels']
+__all__ = ['contours2labels', 'resolve_label_channels']
 
 
 def contours2labels(contours, size, rounded=True, clip=True, initial_depth=1, gap=3, dtype='int32', ioa_thresh=None,
@@ -69,3 +69,28 @@ def contours2labels(contours, size, rounded=True, clip=True, initial_depth=1, ga
     if as_numpy:
         return labels.cpu().numpy().astype(dtype)
     return labels.contiguous()
+
+
+def resolve_label_channels(labels, method='dilation', max_iter=999, kernel=(3, 3)):
+    """Resolve label channels (data/cpn.py:361-398): ``[h, w, c]`` channel label image -> ``[h, w]`` flat label image.
+    Pixels assigned to exactly one object keep its label; conflicts are filled from the neighbouring cores by repeated
+    3x3-cross grey dilation.  numpy in -> numpy out, CUDA tensor in -> CUDA tensor out."""
+    if method != 'dilation':
+        raise ValueError(f'Invalid method: {method}')
+    if tuple(kernel) != (3, 3):
+        raise NotImplementedError('only the default (3, 3) cross kernel is on the accelerated path.')
+    as_numpy = not isinstance(labels, torch.Tensor)
+    if as_numpy:
+        dtype = np.asarray(labels).dtype
+        lab = torch.as_tensor(np.ascontiguousarray(labels).astype(np.int32)).cuda()
+    else:
+        if not labels.is_cuda:
+            raise RuntimeError('celldetection_b200.data.resolve_label_channels runs on CUDA tensors only.')
+        lab = labels.to(torch.int32).contiguous()
+    H, W, C = [int(v) for v in lab.shape]
+    lib = L.load()
+    flat = torch.empty((H, W), dtype=torch.int32, device=lab.device)
+    ws = torch.empty((int(lib.cpn_resolve_label_channels_workspace_bytes(H, W)),), dtype=torch.uint8, device=lab.device)
+    L.check(lib.cpn_resolve_label_channels(L.ptr(lab), H, W, C, int(max_iter), L.ptr(flat), L.ptr(ws), None,
+                                           L.stream_ptr()), 'resolve_label_channels')
+    return flat.cpu().numpy().astype(dtype) if as_numpy else flat

@@ -307,10 +307,13 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
 
 def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, border_removal=4, stitching_rule='nms',
                   batch_size=1, devices='auto', precision=None, return_results=True, model_parameters=None,
-                  verbose=False, **kwargs):
+                  labels=False, flat_labels=False, verbose=False, **kwargs):
     """Programmatic entry point in the spirit of cpn_inference.py:432-869: run tiled inference for each input image
-    (numpy arrays; file I/O, masks, label rasterisation and h5/tif export are outside the hot path).
-    ``models``: CPN instance(s) or a filename loadable by ``load_model``.  Returns ``{index: result dict}``."""
+    (numpy arrays; file I/O and h5/tif export are outside the hot path).  ``models``: CPN instance(s) or a
+    filename loadable by ``load_model``; ``masks`` / ``point_masks`` / ``min_vote`` etc. are forwarded to
+    ``apply_model``.  ``labels`` / ``flat_labels`` add the rasterised label image (``[h, w, c]``, contours2labels) and
+    its channel-free form (``[h, w]``, resolve_label_channels) to each result, like cpn_inference.py:805-818.
+    Returns ``{index: result dict}``."""
     from .utils import load_model
     if not isinstance(inputs, (list, tuple)):
         inputs = [inputs]
@@ -332,6 +335,13 @@ def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, bord
     for i, img in enumerate(inputs):
         if isinstance(img, str):
             raise NotImplementedError('file inputs need image I/O, which is outside the accelerated path')
-        results[i] = apply_model(img, models, crop_size=tile_size, strides=stride, border_removal=border_removal,
-                                 stitching_rule=stitching_rule, batch_size=batch_size, verbose=verbose, **kwargs)
+        results[i] = y = apply_model(img, models, crop_size=tile_size, strides=stride, border_removal=border_removal,
+                                     stitching_rule=stitching_rule, batch_size=batch_size, verbose=verbose, **kwargs)
+        if labels or flat_labels:                  # cpn_inference.py:805-818
+            from .data import contours2labels, resolve_label_channels
+            lab = contours2labels(y['contours'], np.asarray(img).shape[:2])
+            if labels:
+                y['labels'] = lab
+            if flat_labels:
+                y['flat_labels'] = resolve_label_channels(lab)
     return results if return_results else None

@@ -53,6 +53,14 @@ def _is_basic(spec, key):
     return (prefix + 'conv3.weight') not in spec
 
 
+def _mean_std(t):
+    """Mean / unbiased std in float64 with numpy's single-threaded pairwise summation: torch's CPU reductions split the
+    work by the number of OpenMP threads, so their last bits -- and with them the calibrated weights and every digest
+    derived from them -- would depend on the host's core count (seen as a 1-GPU-box vs 2-GPU-box digest mismatch)."""
+    a = t.detach().double().cpu().numpy().ravel()
+    return float(a.mean()), float(a.std(ddof=1)) if a.size > 1 else 0.
+
+
 @torch.no_grad()
 def calibrate_heads_(sd, core_fn, x, fg_fraction=0.02, score_std=2., fourier_std=3., location_std=1.,
                      score_thresh=0.9, refinement_std=0.5, refinement_margin=3., uncertainty_std=1.5):
@@ -76,8 +84,7 @@ def calibrate_heads_(sd, core_fn, x, fg_fraction=0.02, score_std=2., fourier_std
     for name, key, tstd, tmu in (('scores', 'core.score_head.block.4', score_std, target_mu),
                                  ('fourier', 'core.fourier_head.block.4', fourier_std, 0.),
                                  ('locations', 'core.location_head.block.4', location_std, 0.)):
-        t = out[name].float()
-        mu, std = float(t.mean()), float(t.std())
+        mu, std = _mean_std(out[name])
         stats[name] = (mu, std)
         s = tstd / max(std, 1e-12)
         dev, dt = sd[key + '.weight'].device, sd[key + '.weight'].dtype
@@ -87,7 +94,7 @@ def calibrate_heads_(sd, core_fn, x, fg_fraction=0.02, score_std=2., fourier_std
     if out.get('uncertainty') is not None and uncertainty_std:      # sigmoid outputs: calibrate the logits to N(0, std)
         u = out['uncertainty'].float().clamp(1e-6, 1 - 1e-6)
         zed = torch.log(u / (1 - u))
-        mu, std = float(zed.mean()), float(zed.std())
+        mu, std = _mean_std(zed)
         stats['uncertainty_pre'] = (mu, std)
         s = uncertainty_std / max(std, 1e-12)
         dev, dt = sd[key + '.weight'].device, sd[key + '.weight'].dtype
@@ -98,7 +105,7 @@ def calibrate_heads_(sd, core_fn, x, fg_fraction=0.02, score_std=2., fourier_std
         for it in range(2):
             r = (out if it == 0 else core_fn(x, sd))['refinement'].float()
             zed = torch.atanh((r / refinement_margin).clamp(-0.999, 0.999))
-            mu, std = float(zed.mean()), float(zed.std())
+            mu, std = _mean_std(zed)
             stats[f'refinement_pre{it}'] = (mu, std)
             s = refinement_std / max(std, 1e-12)
             dev, dt = sd[key + '.weight'].device, sd[key + '.weight'].dtype

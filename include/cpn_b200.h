@@ -266,6 +266,14 @@ size_t cpn_contours2labels_workspace_bytes(int64_t n_contours, int samples);
 int cpn_contours2labels(const float* contours, int64_t n_contours, int samples, int H, int W, int rounded, int clip,
                         int gap, int32_t* labels, int channels, void* workspace, int32_t* info_dev, void* stream);
 
+/* cd.data.resolve_label_channels (data/cpn.py:361-398, method='dilation', kernel (3,3) = cv2 MORPH_CROSS): labels
+ * [H,W,channels] int32 -> flat [H,W] int32.  Pixels of exactly one object keep its label, pixels of several are filled
+ * by Jacobi sweeps of a 5-point grey dilation until nothing changes or max_iter sweeps ran (reference default 999).
+ * Synchronises the stream (one flag read per sweep).  sweeps_host (optional) receives the number of sweeps. */
+size_t cpn_resolve_label_channels_workspace_bytes(int H, int W);
+int cpn_resolve_label_channels(const int32_t* labels, int H, int W, int channels, int max_iter, int32_t* flat,
+                               void* workspace, int* sweeps_host, void* stream);
+
 /* dst[i, :] = src[index[i], :] for rows of row_bytes (multiple of 4) bytes (resolve_keep_indices, cpn.py:53-60). */
 int cpn_gather_rows(const void* src, int64_t row_bytes, const int32_t* index, int64_t n_rows, void* dst, void* stream);
 

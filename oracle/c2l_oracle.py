@@ -114,3 +114,29 @@ def contours2labels(contours, size, rounded=True, clip=True, initial_depth=1, ga
             labels = np.concatenate((labels, np.zeros(size, dtype=dtype)[..., None]), axis=-1)
         labels[ymin:ymin + a.shape[0], xmin:xmin + a.shape[1], i] += a
     return labels
+
+
+def resolve_label_channels(labels, max_iter=999):
+    """data/cpn.py:361-398 (method='dilation', kernel = cv2.getStructuringElement(MORPH_CROSS, (3, 3))): cv2.dilate is
+    restated as the maximum over the pixel and its 4 neighbours (constant border = lowest value)."""
+    labels = np.asarray(labels)
+    mask_sm = np.sum(labels > 0, axis=-1)
+    mask = mask_sm > 1
+    if not mask.any():
+        return labels.max(-1).astype(labels.dtype)
+    lbl = np.zeros(labels.shape[:2], dtype='float64')
+    core = mask_sm == 1
+    lbl[core] = labels.max(-1)[core]
+    for _ in range(max_iter):
+        m = mask & (lbl <= 0)
+        if not np.any(m):
+            break
+        p = np.pad(lbl, 1, constant_values=-np.inf)
+        dil = np.maximum.reduce([p[1:-1, 1:-1], p[:-2, 1:-1], p[2:, 1:-1], p[1:-1, :-2], p[1:-1, 2:]])
+        new = lbl.copy()
+        new[m] = dil[m]
+        if np.allclose(new, lbl):
+            lbl = new
+            break
+        lbl = new
+    return lbl.astype(labels.dtype)

@@ -365,6 +365,15 @@ def mint_contours2labels(cd):
         assert want.shape == got.shape and np.array_equal(want, got), tag
         arrays[f'{tag}/labels'] = want.astype(np.int16)
     arrays['variants/contours'] = con
+    # resolve_label_channels (data/cpn.py:361-398) on the label images above: overlap pixels filled by dilation sweeps
+    for name in ('sparse', 'dense', 'border', 'odd'):
+        lab = arrays[f'{name}/labels'].astype(np.int32)
+        want = cd.data.resolve_label_channels(lab)
+        got = c2l.resolve_label_channels(lab)
+        assert want.shape == got.shape and np.array_equal(want, got), name
+        arrays[f'{name}/flat'] = want.astype(np.int16)
+    one = arrays['sparse/labels'].astype(np.int32)[..., :1]                   # no overlaps at all: plain max
+    assert np.array_equal(cd.data.resolve_label_channels(one), c2l.resolve_label_channels(one))
     np.savez_compressed(os.path.join(GOLDEN, 'contours2labels.npz'), **arrays)
 
 

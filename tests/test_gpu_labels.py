@@ -100,3 +100,35 @@ def test_contours2labels_full_size_properties():
         earlier = [int(v) for v in vals if 0 < int(v) < k + 1]
         assert not earlier, (k, earlier)                          # no earlier label inside the dilated box of k's channel
         assert int(counts[k + 1]) == int((crop[..., ch[0]] == k + 1).sum())   # painted only inside its own box
+
+
+@pytest.mark.parametrize('name', ['sparse', 'dense', 'border', 'odd'])
+def test_resolve_label_channels_matches_reference_golden(name):
+    """cd.data.resolve_label_channels (data/cpn.py:361-398) on the reference's own label images: bit-exact."""
+    z = load_npz('contours2labels')
+    lab = z[f'{name}/labels'].astype(np.int32)
+    got = cd.data.resolve_label_channels(lab)
+    assert got.shape == z[f'{name}/flat'].shape and got.dtype == np.int32
+    assert np.array_equal(got, z[f'{name}/flat'])
+    t = cd.data.resolve_label_channels(torch.from_numpy(lab).cuda())
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), z[f'{name}/flat'])
+    one = lab[..., :1]                                                          # no overlap anywhere -> labels.max(-1)
+    assert np.array_equal(cd.data.resolve_label_channels(one), one[..., 0])
+    neg = lab.copy()
+    neg[0, 0, :] = -1                                                           # an ignore label on a background pixel
+    assert np.array_equal(cd.data.resolve_label_channels(neg), c2l.resolve_label_channels(neg))
+    with pytest.raises(NotImplementedError):
+        cd.data.resolve_label_channels(lab, kernel=(5, 5))
+
+
+def test_resolve_label_channels_medium_against_oracle():
+    rng = np.random.RandomState(3)
+    H, W = 1024, 1536
+    con = synth_contours(rng, 2500, 32, H, W, (5., 30.))
+    lab = cd.data.contours2labels(torch.from_numpy(con).cuda(), (H, W))
+    flat = cd.data.resolve_label_channels(lab)
+    want = c2l.resolve_label_channels(lab.cpu().numpy())
+    assert np.array_equal(flat.cpu().numpy(), want)
+    # every overlap pixel got a label of one of the objects covering its neighbourhood; cores are untouched
+    cnt = (lab > 0).sum(-1)
+    assert torch.equal(flat[cnt == 1], lab.max(-1).values[cnt == 1]) and int((flat[cnt == 0] != 0).sum()) == 0

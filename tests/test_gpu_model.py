@@ -158,8 +158,13 @@ def test_apply_model_matches_reference_golden():
         for a, b in pairs:
             assert np.abs(res['contours'][a].cpu().numpy() - z['out/contours'][b]).max() < 0.5
             assert np.abs(res['contour_proposals'][a].cpu().numpy() - z['out/contour_proposals'][b]).max() < 0.5
-    rr = cd.cpn_inference(z['img'], m, tile_size=crop, stride=stride, border_removal=border, batch_size=2)
+    rr = cd.cpn_inference(z['img'], m, tile_size=crop, stride=stride, border_removal=border, batch_size=2, labels=True,
+                          flat_labels=True)
     assert len(rr[0]['scores']) == len(z['out/scores'])
+    import c2l_oracle as c2l
+    want = c2l.contours2labels(rr[0]['contours'].cpu().numpy(), z['img'].shape[:2])
+    assert np.array_equal(rr[0]['labels'].cpu().numpy(), want)
+    assert np.array_equal(rr[0]['flat_labels'].cpu().numpy(), c2l.resolve_label_channels(want))
 
 
 def test_full_size_c3_properties():

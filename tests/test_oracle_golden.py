@@ -194,6 +194,8 @@ def test_oracle_contours2labels_golden():
         H, W = [int(v) for v in z[f'{name}/size']]
         got = c2l.contours2labels(z[f'{name}/contours'].copy(), (H, W))
         assert got.shape == z[f'{name}/labels'].shape and np.array_equal(got, z[f'{name}/labels']), name
+        flat = c2l.resolve_label_channels(got)                                   # data/cpn.py:361-398
+        assert np.array_equal(flat, z[f'{name}/flat']), name
     con = z['variants/contours']
     for tag, kw in (('noround', dict(rounded=False)), ('gap0', dict(gap=0)), ('depth3', dict(initial_depth=3))):
         got = c2l.contours2labels(con.copy(), (80, 80), **kw)
