@@ -440,59 +440,103 @@ __device__ __forceinline__ void coal_rows(const ConvTcParams& p, const int img, 
   }
 }
 
-__device__ __forceinline__ void coal_load_res(const ConvTcParams& p, const CoalRows& c, const int ch, uint4 (&rg)[4]) {
+// lo_delta: 0 for the hi (or only) half of the residual, p.res_lo for the lo half of a split (CPN_DT_F16X2) tensor
+__device__ __forceinline__ void coal_load_res(const ConvTcParams& p, const CoalRows& c, const int ch, const int lo_delta,
+                                              uint4 (&rg)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    if (c.okmask & (1u << i)) rg[i] = __ldg(reinterpret_cast<const uint4*>(p.res + c.roff[i] + ch * 32));
+    if (c.okmask & (1u << i)) rg[i] = __ldg(reinterpret_cast<const uint4*>(p.res + c.roff[i] + lo_delta + ch * 32));
 }
 
+// staging-tile transposition helpers (see the header comment above): "t" = transposed / coalesced role, "o" = row owner
+__device__ __forceinline__ void stg_put_t(uint4* stg, const int lane, const uint4 (&x)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const int r = i * 8 + (lane >> 2); stg[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))] = x[i]; }
+}
+__device__ __forceinline__ void stg_get_o(const uint4* stg, const int lane, uint4 (&x)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) x[k] = stg[lane * 4 + (k ^ ((lane >> 1) & 3))];
+}
+__device__ __forceinline__ void stg_put_o(uint4* stg, const int lane, const uint4 (&x)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) stg[lane * 4 + (k ^ ((lane >> 1) & 3))] = x[k];
+}
+__device__ __forceinline__ void stg_store_t(const uint4* stg, const int lane, const CoalRows& c, __half* base) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    if (c.okmask & (1u << i)) *reinterpret_cast<uint4*>(base + c.ooff[i]) = stg[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
+  }
+}
+
+// rg / rgl: residual (hi / lo half) of this warp's first chunk in the transposed role, requested by the caller.
+// Split tensors (p.split): residual = hi + lo, the result is re-split into hi = fp16(v), lo = fp16(v - hi), and both
+// halves cross the staging tile one after the other.
 template <int BN>
 __device__ __forceinline__ void epilogue_coalesced(const ConvTcParams& p, const uint32_t taddr, const CoalRows& c,
                                                    const int n0, const int half, const int lane, uint4* stg,
-                                                   uint4 (&rg)[4]) {
-  const int q = lane & 3, rsub = lane >> 2;
+                                                   uint4 (&rg)[4], uint4 (&rgl)[4]) {
   const bool has_res = p.res != nullptr;
+  const bool split = p.split != 0;
 #pragma unroll 1
   for (int ch = half; ch < BN / 32; ch += 2) {
     uint32_t v[32];
     tmem_ld32(taddr + ch * 32, v);
-    uint4 rr[4];
+    uint4 rr[4], rl[4];
     if (has_res) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { const int r = i * 8 + rsub; stg[r * 4 + (q ^ ((r >> 1) & 3))] = rg[i]; }
+      stg_put_t(stg, lane, rg);
       __syncwarp();
-#pragma unroll
-      for (int k = 0; k < 4; ++k) rr[k] = stg[lane * 4 + (k ^ ((lane >> 1) & 3))];
-      if (ch + 2 < BN / 32) coal_load_res(p, c, ch + 2, rg);          // next chunk's residual while this one computes
+      stg_get_o(stg, lane, rr);
+      if (split) {
+        __syncwarp();
+        stg_put_t(stg, lane, rgl);
+        __syncwarp();
+        stg_get_o(stg, lane, rl);
+      }
+      if (ch + 2 < BN / 32) {                                        // next chunk's residual while this one computes
+        coal_load_res(p, c, ch + 2, 0, rg);
+        if (split) coal_load_res(p, c, ch + 2, p.res_lo, rgl);
+      }
     }
     tmem_ld_wait();
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
     uint32_t* pk = reinterpret_cast<uint32_t*>(rr);                  // results overwrite the residual registers in place
-    const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
+    uint32_t* pl = reinterpret_cast<uint32_t*>(rl);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float4 b = p.bias ? __ldg(b4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
       float f0 = __uint_as_float(v[k * 4 + 0]) + b.x, f1 = __uint_as_float(v[k * 4 + 1]) + b.y;
       float f2 = __uint_as_float(v[k * 4 + 2]) + b.z, f3 = __uint_as_float(v[k * 4 + 3]) + b.w;
       if (has_res) {
-        const __half2 r0 = *reinterpret_cast<const __half2*>(&rw[k * 2]);
-        const __half2 r1 = *reinterpret_cast<const __half2*>(&rw[k * 2 + 1]);
+        const __half2 r0 = *reinterpret_cast<const __half2*>(&pk[k * 2]);
+        const __half2 r1 = *reinterpret_cast<const __half2*>(&pk[k * 2 + 1]);
         f0 += __low2float(r0); f1 += __high2float(r0); f2 += __low2float(r1); f3 += __high2float(r1);
+        if (split) {
+          const __half2 l0 = *reinterpret_cast<const __half2*>(&pl[k * 2]);
+          const __half2 l1 = *reinterpret_cast<const __half2*>(&pl[k * 2 + 1]);
+          f0 += __low2float(l0); f1 += __high2float(l0); f2 += __low2float(l1); f3 += __high2float(l1);
+        }
       }
       if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
       const __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
       pk[k * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h0);
       pk[k * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+      if (split) {                                                   // lo = fp16(v - hi)
+        const __half2 g0 = __floats2half2_rn(f0 - __low2float(h0), f1 - __high2float(h0));
+        const __half2 g1 = __floats2half2_rn(f2 - __low2float(h1), f3 - __high2float(h1));
+        pl[k * 2 + 0] = *reinterpret_cast<const uint32_t*>(&g0);
+        pl[k * 2 + 1] = *reinterpret_cast<const uint32_t*>(&g1);
+      }
     }
-    __syncwarp();                                                    // every lane has read its residual row
-#pragma unroll
-    for (int k = 0; k < 4; ++k) stg[lane * 4 + (k ^ ((lane >> 1) & 3))] = rr[k];
+    __syncwarp();                                                    // every lane has read its residual row(s)
+    stg_put_o(stg, lane, rr);
     __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = i * 8 + rsub;
-      if (c.okmask & (1u << i))
-        *reinterpret_cast<uint4*>(p.out + c.ooff[i] + ch * 32) = stg[r * 4 + (q ^ ((r >> 1) & 3))];
+    stg_store_t(stg, lane, c, p.out + ch * 32);
+    if (split) {
+      __syncwarp();
+      stg_put_o(stg, lane, rl);
+      __syncwarp();
+      stg_store_t(stg, lane, c, p.out + p.out_lo + ch * 32);
     }
     __syncwarp();                                                    // staging tile free for the next chunk
   }
@@ -657,11 +701,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (COAL) {
         CoalRows cr;
         coal_rows<4>(p, img, ty0, tx0, n0, quad, lane, cr);   // TC_BW = 16
-        uint4 rg[4];
-        if (p.res) coal_load_res(p, cr, half, rg);   // first chunk's residual: in flight while the MMAs still run
+        uint4 rg[4], rgl[4];
+        if (p.res) {                                 // first chunk's residual: in flight while the MMAs still run
+          coal_load_res(p, cr, half, 0, rg);
+          if (p.split) coal_load_res(p, cr, half, p.res_lo, rgl);
+        }
         mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
         tc_fence_after();
-        epilogue_coalesced<BN>(p, taddr, cr, n0, half, lane, reinterpret_cast<uint4*>(tail) + (warp - 2) * 128, rg);
+        epilogue_coalesced<BN>(p, taddr, cr, n0, half, lane, reinterpret_cast<uint4*>(tail) + (warp - 2) * 128, rg, rgl);
       } else {
       ResChunk rfirst;
       {   // residual of the first chunk: requested while the MMAs of this tile are still running
@@ -910,10 +957,13 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
           if (COAL) {     // line-coalesced stores / residual loads through the warp's staging tile (8-pixel-wide sub-tile)
             CoalRows cr;
             coal_rows<3>(p, img, ty0, tx0 + 8 * j, n_tile * BN, quad, lane, cr);
-            uint4 rg[4];
-            if (p.res) coal_load_res(p, cr, half, rg);
+            uint4 rg[4], rgl[4];
+            if (p.res) {
+              coal_load_res(p, cr, half, 0, rg);
+              if (p.split) coal_load_res(p, cr, half, p.res_lo, rgl);
+            }
             epilogue_coalesced<BN>(p, taddr, cr, n_tile * BN, half, lane, reinterpret_cast<uint4*>(tail) + (warp - 4) * 128,
-                                   rg);
+                                   rg, rgl);
           } else {
             epilogue_rows<BN, false>(p, taddr, img, y, xb + 8 * j, n_tile, n_tile * BN, half, proj_w);
           }
@@ -1095,7 +1145,10 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
     const long long res_elems = op.res.n ? (long long)op.res.n * op.res.h * op.res.w * op.res.pitch : 0;
     static int coal_halo_env = -1;   // CPN_COALESCE_HALO=0: keep the direct epilogue in conv_halo_kernel only (A/B switch)
     if (coal_halo_env < 0) { const char* e = getenv("CPN_COALESCE_HALO"); coal_halo_env = (e && atoi(e) == 0) ? 0 : 1; }
-    p.coalesce = (coal_env && !split && (coal_halo_env || !p.halo) && out_elems < (1ll << 31) && res_elems < (1ll << 31)) ? 1 : 0;
+    static int coal_split_env = -1;  // CPN_COALESCE_SPLIT=0: direct epilogue for the split-precision engine (A/B switch)
+    if (coal_split_env < 0) { const char* e = getenv("CPN_COALESCE_SPLIT"); coal_split_env = (e && atoi(e) == 0) ? 0 : 1; }
+    p.coalesce = (coal_env && (coal_split_env || !split) && (coal_halo_env || !p.halo) && out_elems < (1ll << 31) &&
+                  res_elems < (1ll << 31)) ? 1 : 0;
   }
   pl->smem_bytes = pl->stages * stage_bytes + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
   if (p.halo) pl->smem_bytes = p.nb_stages * bn * TC_BK * 2 + 2 * 8 * p.plane_stride + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
