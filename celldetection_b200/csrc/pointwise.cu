@@ -3,6 +3,7 @@
 // channel axis, 8-byte or 16-byte vector accesses where the pitch allows, grid sized in multiples of the SM count.
 #include "common.cuh"
 #include <cstring>
+#include <cstdlib>
 
 namespace cpn {
 
@@ -119,11 +120,103 @@ __global__ void __launch_bounds__(256) prep_im2col_kernel(const void* __restrict
   if (bad) atomicOr(flags, 1);
 }
 
+// Tiled variant: a CTA stages the input window of a TY x TX tile of output pixels in shared memory with coalesced loads
+// (each input value is needed by up to k*k / stride^2 output pixels: the direct kernel re-fetched it with scattered 4-byte
+// loads and ran at 0.9 TB/s of output, ncu r01: 10.8 % DRAM) and then writes the K-major operand rows with 16-byte stores,
+// consecutive threads on consecutive 8-channel chunks of one pixel.
+constexpr int PREP_TY = 4, PREP_TX = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256) prep_im2col_tiled_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out,
+                                                                int N, int C, int H, int W, int Ho, int Wo, int Kp,
+                                                                int pitch, int k, int stride, int pad,
+                                                                int32_t* __restrict__ flags, int lo_delta, int WH, int WW) {
+  extern __shared__ float prep_sm[];                  // [C][WH][WW] window, then int off_sm[Kp]
+  int* off_sm = reinterpret_cast<int*>(prep_sm + C * WH * WW);
+  const int kk = k * k * C;
+  for (int e = threadIdx.x; e < Kp; e += blockDim.x) {
+    const int tap = e / C, c = e - tap * C;
+    const int r = tap / k, s_ = tap - r * k;
+    off_sm[e] = e < kk ? (c * WH + r) * WW + s_ : -1;
+  }
+  const int tiles_x = (Wo + PREP_TX - 1) / PREP_TX, tiles_y = (Ho + PREP_TY - 1) / PREP_TY;
+  int b = blockIdx.x;
+  const int tx = b % tiles_x; b /= tiles_x;
+  const int ty = b % tiles_y;
+  const int n = b / tiles_y;
+  const int oy0 = ty * PREP_TY, ox0 = tx * PREP_TX;
+  const int iy0 = oy0 * stride - pad, ix0 = ox0 * stride - pad;
+  bool bad = false;
+  for (int i = threadIdx.x; i < C * WH * WW; i += blockDim.x) {
+    const int wx = i % WW, t = i / WW, wy = t % WH, c = t / WH;
+    const int iy = iy0 + wy, ix = ix0 + wx;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      if (fmt == CPN_IN_F32_NCHW) {
+        v = __ldg(reinterpret_cast<const float*>(in) + (((long long)n * C + c) * H + iy) * W + ix);
+        bad |= !(v >= 0.f && v <= 1.f);
+      } else if (fmt == CPN_IN_U8_NCHW) {
+        v = (float)__ldg(reinterpret_cast<const uint8_t*>(in) + (((long long)n * C + c) * H + iy) * W + ix) / 255.f;
+      } else {
+        v = (float)__ldg(reinterpret_cast<const uint8_t*>(in) + (((long long)n * H + iy) * W + ix) * C + c) / 255.f;
+      }
+    }
+    prep_sm[i] = v;
+  }
+  __syncthreads();
+  const int chunks = Kp / 8;
+  for (int i = threadIdx.x; i < PREP_TY * PREP_TX * chunks; i += blockDim.x) {
+    const int ch = i % chunks, pxl = i / chunks;
+    const int px = pxl % PREP_TX, py = pxl / PREP_TX;
+    const int oy = oy0 + py, ox = ox0 + px;
+    if (oy >= Ho || ox >= Wo) continue;
+    const float* win = prep_sm + (py * stride) * WW + px * stride;
+    __align__(16) T vals[8];
+    __align__(16) T vlo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = off_sm[ch * 8 + j];
+      const float v = o >= 0 ? win[o] : 0.f;
+      vals[j] = from_f32<T>(v);
+      vlo[j] = from_f32<T>(v - to_f32<T>(vals[j]));
+    }
+    T* o = out + (((long long)n * Ho + oy) * Wo + ox) * pitch + ch * 8;
+    if (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(vals);
+      if (lo_delta > 0) *reinterpret_cast<uint4*>(o + lo_delta) = *reinterpret_cast<const uint4*>(vlo);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = vals[j];
+    }
+  }
+  if (bad) atomicOr(flags, 1);
+}
+
 int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* dst, int32_t* flags, cudaStream_t st) {
   CPN_REQUIRE(input_format >= 0 && input_format <= 2, "prep: bad input format %d", input_format);
   if (op.r > 0) {  // im2col mode: src view describes the logical input (n, h, w, c)
     CPN_REQUIRE(op.dst.c % 8 == 0 && op.dst.pitch % 8 == 0 && op.dst.c >= op.r * op.r * op.src.c && op.dst.c <= 512,
                 "prep(im2col): dst channels %d must be a multiple of 8, >= k*k*c and <= 512", op.dst.c);
+    {
+      // tiled path (CPN_PREP_TILED=0 selects the direct kernel): window of a PREP_TY x PREP_TX output tile in smem
+      static int tiled_env = -1;
+      if (tiled_env < 0) { const char* e = getenv("CPN_PREP_TILED"); tiled_env = (e && atoi(e) == 0) ? 0 : 1; }
+      const int WH = (PREP_TY - 1) * op.stride + op.r, WW = (PREP_TX - 1) * op.stride + op.r;
+      const size_t smem = ((size_t)op.src.c * WH * WW + op.dst.c) * 4;
+      const long long blocks = (long long)op.dst.n * ((op.dst.h + PREP_TY - 1) / PREP_TY) * ((op.dst.w + PREP_TX - 1) / PREP_TX);
+      if (tiled_env && smem <= 48 * 1024 && blocks < (1ll << 31)) {
+        if (op.dst.dtype == CPN_DT_F32)
+          prep_im2col_tiled_kernel<float><<<(int)blocks, 256, smem, st>>>(
+              input, input_format, (float*)dst, op.src.n, op.src.c, op.src.h, op.src.w, op.dst.h, op.dst.w, op.dst.c,
+              op.dst.pitch, op.r, op.stride, op.pad, flags, 0, WH, WW);
+        else
+          prep_im2col_tiled_kernel<__half><<<(int)blocks, 256, smem, st>>>(
+              input, input_format, (__half*)dst, op.src.n, op.src.c, op.src.h, op.src.w, op.dst.h, op.dst.w, op.dst.c,
+              op.dst.pitch, op.r, op.stride, op.pad, flags, op.dst.dtype == CPN_DT_F16X2 ? op.dst.lo_delta : 0, WH, WW);
+        CPN_CHECK_LAUNCH();
+        return 0;
+      }
+    }
     const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * (op.dst.c / 8);
     const int grid = grid_for(total, 256);
     if (op.dst.dtype == CPN_DT_F32)

@@ -104,9 +104,12 @@ def test_fp16_tensor_core_model_close_to_reference(name):
     assert st['vertices_within_half_px'] >= 0.95 * st['vertices'], st
 
 
-def test_input_contract_and_uint8_path():
-    z = load_npz(MODEL_FIXTURES[0])
-    m, (n, h, w) = _model(z, 'fp32')
+@pytest.mark.parametrize('precision,fixture', [('fp32', 0), ('fp16', 0), ('fp16x3', 2)])
+def test_input_contract_and_uint8_path(precision, fixture):
+    """Range assertion and the three input formats, through the plain prep kernel (fp32 engine) and the tiled im2col
+    prep of the tensor-core stems (3x3 s1 for U22, 7x7 s2 for the ResNeXt encoder)."""
+    z = load_npz(MODEL_FIXTURES[fixture])
+    m, (n, h, w) = _model(z, precision)
     x = torch.from_numpy(z['x']).cuda()
     with pytest.raises(AssertionError):
         m(x * 1.5)                                        # commons.py:695-697
@@ -391,3 +394,33 @@ def test_apply_model_ensemble_mask_and_voting():
     ok = ~torch.isnan(dense)
     assert torch.isnan(all_votes.cpu()[~ok]).all() and (~ok).sum() == 1
     assert (all_votes.cpu()[ok] - dense[ok]).abs().max() < 1e-5
+
+
+def test_tiled_im2col_prep_equals_direct_kernel():
+    """The shared-memory tiled im2col producer writes bit-identical operands to the direct gather kernel
+    (CPN_PREP_TILED=0), for float, uint8 NCHW and uint8 NHWC inputs at a ragged size; checked through the stem output."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys, torch, hashlib\n"
+        "sys.path.insert(0, %r)\n"
+        "import celldetection_b200 as cd\n"
+        "from celldetection_b200.utils.synth import synth_state_dict\n"
+        "torch.manual_seed(3)\n"
+        "m = cd.models.CpnResNet18FPN(3, precision='fp16')\n"
+        "m.load_state_dict(synth_state_dict(m._spec, seed=5)); m = m.cuda()\n"
+        "x = torch.rand(2, 3, 90, 150).cuda()\n"
+        "u8 = (x * 255).round().to(torch.uint8)\n"
+        "h = hashlib.sha256()\n"
+        "for inp, fmt in ((x, None), (u8, None), (u8.permute(0, 2, 3, 1).contiguous(), cd._lib.IN_U8_NHWC)):\n"
+        "    plan, outs, hw = m._run_plan(inp, fmt)\n"
+        "    torch.cuda.synchronize()\n"
+        "    for o in outs: h.update(o.cpu().numpy().tobytes())\n"
+        "print('DIGEST', h.hexdigest())\n") % ROOT
+    digests = []
+    for tiled in ('1', '0'):
+        env = dict(os.environ, CPN_PREP_TILED=tiled)
+        r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append([l for l in r.stdout.splitlines() if l.startswith('DIGEST')][0])
+    assert digests[0] == digests[1]
