@@ -285,8 +285,8 @@ class CPN(nn.Module):
                 L.check(lib.cpn_nms_weights(L.ptr(sel_scores), L.ptr(uncertainty), L.ptr(idx), P, L.ptr(weights), st),
                         'nms_weights')
             keep, counts = O.nms_segments(boxes, weights, seg, n, float(self.nms_thresh), O.NMS_BATCH_SIZE)
-            seg_h = seg.tolist()                          # host sync #2: per-image sizes of the returned lists
-            counts_h = counts.tolist()
+            both = torch.cat((seg, counts.to(seg.dtype))).tolist()   # host sync #2 (one copy): per-image offsets + kept counts
+            seg_h, counts_h = both[:n + 1], both[n + 1:]
             sel_rows = torch.cat([keep[seg_h[i]:seg_h[i] + counts_h[i]] for i in range(n)]) if P > 0 else keep[:0]
             K = int(sel_rows.numel())
             out = OrderedDict()
