@@ -173,9 +173,11 @@ res = OrderedDict(contours=torch.rand(K, 8, 2, generator=g), boxes=torch.rand(K,
                   scores=torch.rand(K, generator=g), classes=torch.ones(K, dtype=torch.long),
                   locations=torch.rand(K, 2, generator=g), fourier=torch.rand(K, 5, 4, generator=g),
                   contour_proposals=torch.rand(K, 8, 2, generator=g),
+                  box_uncertainties=torch.rand(K, 4, generator=g),      # models with an uncertainty head carry this key
                   order_key=torch.stack((torch.arange(K).float() * 2 + rank, torch.arange(K).float()), 1))
 out = allgather_detections(res)
 assert out['scores'].shape[0] == 8 and out['classes'].dtype == torch.long
+assert list(out.keys()) == list(res.keys()) and out['box_uncertainties'].shape == (8, 4)
 for r, (a, b) in enumerate(((0, 3), (3, 8))):
     gg = torch.Generator().manual_seed(100 + r)
     kk = b - a
@@ -225,3 +227,23 @@ def test_synth_state_dict_is_deterministic_and_complete():
     assert all(torch.equal(a[k], b[k]) and tuple(a[k].shape) == tuple(spec[k]) for k in spec)
     c = synth_state_dict(spec, seed=4)
     assert not torch.equal(a['core.score_head.block.0.weight'], c['core.score_head.block.0.weight'])
+
+
+def test_tile_bounds_follow_the_reference_tile_loader():
+    """TileLoader.__getitem__ (cpn_inference.py:93-111): mask crop -> upper bound, clipped point-mask crop -> lower bound
+    (and upper, when exclusive); a tile whose crop is empty is skipped."""
+    from celldetection_b200.inference import _tile_bounds
+    mask = np.zeros((8, 8), bool)
+    mask[:4, :4] = True
+    pm = np.zeros((8, 8), np.float32)
+    pm[1, 1] = 3.
+    sl_in, sl_out = (slice(0, 4), slice(0, 4)), (slice(4, 8), slice(4, 8))
+    up, lo = _tile_bounds(mask, None, False, sl_in)
+    assert lo is None and up.shape == (4, 4, 1) and up.dtype == np.float32 and up.all()
+    assert _tile_bounds(mask, None, False, sl_out) is False
+    up, lo = _tile_bounds(None, pm, False, sl_in)
+    assert up is None and lo.shape == (4, 4, 1) and lo.max() == 1. and lo.sum() == 1.
+    up, lo = _tile_bounds(mask, pm, True, sl_in)
+    assert up is lo
+    assert _tile_bounds(mask, pm, False, sl_out) is False
+    assert _tile_bounds(None, None, False, sl_in) == (None, None)
