@@ -10,6 +10,8 @@ from . import _lib as L
 
 __all__ = ['contours2labels', 'resolve_label_channels']
 
+_channel_hint = {}   # (H, W) -> channels that sufficed in the previous contours2labels call
+
 
 def contours2labels(contours, size, rounded=True, clip=True, initial_depth=1, gap=3, dtype='int32', ioa_thresh=None,
                     sort_by=None, sort_descending=True, return_indices=False, device=None):
@@ -51,7 +53,8 @@ def contours2labels(contours, size, rounded=True, clip=True, initial_depth=1, ga
     dev = con.device
     ws = torch.empty((int(lib.cpn_contours2labels_workspace_bytes(K, S)),), dtype=torch.uint8, device=dev)
     info = torch.zeros((4,), dtype=torch.int32, device=dev)
-    channels = max(int(initial_depth), 4)
+    # start from the channel count that sufficed last time for this image size (each retry re-zeroes the whole image)
+    channels = max(int(initial_depth), 4, _channel_hint.get((H, W), 0))
     while True:
         labels = torch.empty((H, W, channels), dtype=torch.int32, device=dev)
         L.check(lib.cpn_contours2labels(L.ptr(con), K, S, H, W, int(bool(rounded)), int(bool(clip)), int(gap),
@@ -65,6 +68,7 @@ def contours2labels(contours, size, rounded=True, clip=True, initial_depth=1, ga
         if channels >= 64:
             raise RuntimeError('contours2labels: more than 64 label channels needed')
         channels = min(64, max(needed, 2 * channels))
+    _channel_hint[(H, W)] = channels if used > channels // 2 else max(4, channels // 2)
     labels = labels[:, :, :max(used, int(initial_depth))]
     if as_numpy:
         return labels.cpu().numpy().astype(dtype)
