@@ -1,5 +1,6 @@
 #!/bin/bash
-# Coalesced-epilogue A/B: conv parity tests, model tests, bench + per-op profile with the new epilogue and with CPN_COALESCE=0.
+# Coalesced-epilogue A/B (same box): conv parity tests, model tests, bench + per-op profile with the line-coalesced epilogue
+# and with it switched off in the halo kernel (CPN_COALESCE_HALO=0; CPN_COALESCE=0 switches it off everywhere).
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out; OUT=gpurun_out
 timeout -s KILL 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_model.py -m gpu -q --timeout 600 -x -p no:cacheprovider > $OUT/pytest_d.log 2>&1
