@@ -247,3 +247,35 @@ def test_tile_bounds_follow_the_reference_tile_loader():
     assert up is lo
     assert _tile_bounds(mask, pm, False, sl_out) is False
     assert _tile_bounds(None, None, False, sl_in) == (None, None)
+
+
+def test_trace_variants_widen_the_heads_like_the_reference():
+    """models/cpn.py:177-234: score head -> `classes` channels (classes > 2), refinement head -> 2 * buckets channels,
+    uncertainty head = a fourth ReadOut with 4 sigmoid outputs on the head features; the merged 7x7 head convolution
+    grows to 4 x C_head and every projection reads its own C_head-wide slice."""
+    g0 = G.trace('CpnResNeXt101UNet', 1, 128, 128)
+    g1 = G.trace('CpnResNeXt101UNet', 1, 128, 128, score_channels=5, refinement_buckets=6, uncertainty_head=True)
+    assert list(g0.outputs) == ['scores', 'locfou', 'refinement']
+    assert list(g1.outputs) == ['scores', 'locfou', 'refinement', 'uncertainty']
+    assert (g1.outputs['scores'].c, g1.outputs['refinement'].c, g1.outputs['uncertainty'].c) == (5, 12, 4)
+    heads0 = [o for o in g0.ops if o.name == 'heads.block.0'][0]
+    heads1 = [o for o in g1.ops if o.name == 'heads.block.0'][0]
+    assert heads0.dst.c == 3 * 256 and heads1.dst.c == 4 * 256
+    projs = [o for o in g1.ops if o.kind == 'proj' and o.src is heads1.dst]
+    assert [(o.cin_off, o.cin, o.dst.c, o.act) for o in projs] == [(0, 256, 5, 'none'), (256, 256, 2, 'none'),
+                                                                   (512, 256, 20, 'none'), (768, 256, 4, 'sigmoid')]
+    assert [o.dst.binding for o in projs] == [0, 1, 1, 3]
+    keys = list(g1.spec)
+    assert keys.index('core.uncertainty_head.block.0.weight') > keys.index('core.fourier_head.block.4.bias')
+    assert keys.index('core.uncertainty_head.block.4.bias') < keys.index('core.refinement_head.block.0.weight')
+    assert g1.spec['core.refinement_head.block.4.weight'][0] == (12, 64, 1, 1)
+
+
+def test_every_architecture_is_tensor_core_eligible():
+    """All convolutions of all 19 architectures satisfy the tcgen05 engine's layout constraints (64-multiples after the
+    im2col stem), which is what lets the fp16x3 parity engine run them."""
+    for arch in G.ARCHS:
+        g = G.trace(arch, 1, 64, 64, stem_im2col=True)
+        for op in g.ops:
+            if op.kind == 'conv':
+                assert PL.engine_for(op, True, op.src.c) == _lib.ENGINE_TCGEN05, (arch, op.name)
