@@ -1,0 +1,89 @@
+"""Numerical feasibility study (CPU, not collected by pytest): can the two CORRECTION passes of the fp16x3 engine
+(A_lo*W_hi + A_hi*W_lo) run in an 8-bit float format, i.e. as ONE `kind::f8f6f4` pass over K-concatenated operands,
+so that the parity engine costs 2 instead of 3 pass-equivalents?
+
+Every convolution of the oracle is replaced by an emulation of the candidate arithmetic (exact products, wide
+accumulation -- what the tensor core does up to its accumulator rounding):
+    y = conv(a_hi, w_hi) + conv(q(a_lo * sa), q(w_hi * sw)) / (sa * sw) + conv(q(a_hi * ta), q(w_lo * tw)) / (ta * tw)
+with a = a_hi + a_lo, w = w_hi + w_lo split in fp16, q = rounding to the 8-bit format and power-of-two per-tensor scales
+that put the largest magnitude at `target`.  Usage:  python tests/study_fp8_corrections.py [fixture]
+"""
+import sys
+import os
+
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'oracle'))
+sys.path.insert(0, os.path.dirname(HERE))
+import conftest  # noqa: F401,E402
+import cpn_oracle as orc  # noqa: E402
+from helpers import load_npz, fixture_state_dict  # noqa: E402
+
+
+def pow2_scale(t, target):
+    m = float(t.abs().max())
+    if m == 0:
+        return 1.
+    return 2. ** torch.floor(torch.log2(torch.tensor(target / m))).item()
+
+
+def q8(t, fmt):
+    if fmt == 'fp16':
+        return t.half().float()
+    dt = dict(e4m3=torch.float8_e4m3fn, e5m2=torch.float8_e5m2)[fmt]
+    return t.to(dt).float()
+
+
+def make_conv(mode):
+    """mode: 'fp32' | 'fp16' (single pass) | 'fp16x3' | 'e4m3' | 'e5m2' (8-bit corrections)"""
+    def conv(x, sd, key, stride=1, padding=0, groups=1):
+        w, b = sd[key + '.weight'], sd.get(key + '.bias')
+        kw = dict(stride=stride, padding=padding, groups=groups)
+        if mode == 'fp32':
+            return F.conv2d(x, w, b, **kw)
+        xd, wd = x.double(), w.double()
+        a_hi, w_hi = x.half().double(), w.half().double()
+        y = F.conv2d(a_hi, w_hi, None, **kw)
+        if mode != 'fp16':
+            a_lo, w_lo = (xd - a_hi).half().double(), (wd - w_hi).half().double()
+            if mode == 'fp16x3':
+                y = y + F.conv2d(a_lo, w_hi, None, **kw) + F.conv2d(a_hi, w_lo, None, **kw)
+            else:
+                target = 256. if mode == 'e4m3' else 16384.
+                for a, ww in ((a_lo, w_hi), (a_hi, w_lo)):
+                    sa, sw = pow2_scale(a, target), pow2_scale(ww, target)
+                    y = y + F.conv2d(q8((a * sa).float(), mode).double(), q8((ww * sw).float(), mode).double(), None,
+                                     **kw) / (sa * sw)
+        if b is not None:
+            y = y + b.double().view(1, -1, 1, 1)
+        return y.float()
+    return conv
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else 'model_cpnresnext101unet_n1_128'
+    z = load_npz(name)
+    arch = str(z['arch'])
+    sd = fixture_state_dict(z, arch, int(z['meta'][3]))
+    x = torch.from_numpy(z['x'])
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    orig = orc._conv
+    ref = None
+    for mode in ('fp32', 'fp16', 'fp16x3', 'e5m2', 'e4m3'):
+        orc._conv = make_conv(mode)
+        with torch.no_grad():
+            out = orc.cpn_core(x, sd, arch)
+        orc._conv = orig
+        if ref is None:
+            ref = out
+            continue
+        errs = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(out, ref)]
+        print(f'{name} {mode:7s} scores {errs[0]:.2e} locations {errs[1]:.2e} refinement {errs[2]:.2e} fourier {errs[3]:.2e}',
+              flush=True)
+
+
+if __name__ == '__main__':
+    main()
