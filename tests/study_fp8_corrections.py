@@ -38,7 +38,7 @@ def q8(t, fmt):
 
 
 def make_conv(mode):
-    """mode: 'fp32' | 'fp16' (single pass) | 'fp16x3' | 'e4m3' | 'e5m2' (8-bit corrections)"""
+    """mode: 'fp32' | 'fp16' (single pass) | 'fp16x3' | 'e4m3' | 'e5m2' | 'e4m3fixed' (8-bit corrections)"""
     def conv(x, sd, key, stride=1, padding=0, groups=1):
         w, b = sd[key + '.weight'], sd.get(key + '.bias')
         kw = dict(stride=stride, padding=padding, groups=groups)
@@ -51,6 +51,14 @@ def make_conv(mode):
             a_lo, w_lo = (xd - a_hi).half().double(), (wd - w_hi).half().double()
             if mode == 'fp16x3':
                 y = y + F.conv2d(a_lo, w_hi, None, **kw) + F.conv2d(a_hi, w_lo, None, **kw)
+            elif mode == 'e4m3fixed':
+                # deployable variant: DATA-INDEPENDENT activation scales (a_lo * 2^8, a_hi * 2^-2, chosen once for O(1..16)
+                # activations), per-layer power-of-two weight scales from max|w| -> one common product S per layer, so a
+                # single accumulator holds S * (main + corrections) when the main pass uses S * W_hi
+                for a, ww, s_act in ((a_lo, w_hi, 2. ** 8), (a_hi, w_lo, 2. ** -2)):
+                    sw = pow2_scale(ww, 256.)
+                    y = y + F.conv2d(q8((a * s_act).float(), 'e4m3').double(), q8((ww * sw).float(), 'e4m3').double(), None,
+                                     **kw) / (s_act * sw)
             else:
                 target = 256. if mode == 'e4m3' else 16384.
                 for a, ww in ((a_lo, w_hi), (a_hi, w_lo)):
@@ -64,7 +72,8 @@ def make_conv(mode):
 
 
 def main():
-    name = sys.argv[1] if len(sys.argv) > 1 else 'model_cpnresnext101unet_n1_128'
+    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    name = args[0] if args else 'model_cpnresnext101unet_n1_128'
     z = load_npz(name)
     arch = str(z['arch'])
     sd = fixture_state_dict(z, arch, int(z['meta'][3]))
@@ -72,7 +81,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     orig = orc._conv
     ref = None
-    for mode in ('fp32', 'fp16', 'fp16x3', 'e5m2', 'e4m3'):
+    for mode in ('fp32', 'e4m3fixed') if '--fixed' in sys.argv else ('fp32', 'fp16', 'fp16x3', 'e5m2', 'e4m3', 'e4m3fixed'):
         orc._conv = make_conv(mode)
         with torch.no_grad():
             out = orc.cpn_core(x, sd, arch)
