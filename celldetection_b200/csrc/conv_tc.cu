@@ -23,8 +23,11 @@
 // (+ ReLU) -> fp16 NHWC store, or -> fused ReadOut projection (+ 3*tanh) -> fp32 head records.
 // Split-precision mode (CPN_DT_F16X2): three passes per K block, A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, outputs re-split.
 // Grouped convolutions use BN = 64 and contract only over their 64-channel block-diagonal slab (cpn_op_t::kslab).
+// Layers without a fused projection use the COAL kernel variants: a line-coalesced, shared-memory-staged epilogue
+// (epilogue_coalesced) for residual loads and output stores.
 // Environment switches (experiments, see profiles/r01_summary.md): CPN_HALO=0, CPN_HALO_ALL=0, CPN_HALO_SW128=0,
-// CPN_HALO_BASEOFF=1, CPN_HALO_SWAP=1, CPN_ROTATE=1.
+// CPN_HALO_BASEOFF=1, CPN_HALO_SWAP=1, CPN_ROTATE=1, CPN_COALESCE=0, CPN_COALESCE_HALO=0, CPN_COALESCE_SPLIT=0,
+// CPN_SPLIT_LOFIRST=0.
 #include "common.cuh"
 #include <cstdlib>
 #include <cstring>
