@@ -363,6 +363,17 @@ def run_b200(args):
             line['cpu_baseline'] = cpu
         if parity_engine is not None:
             line['parity_engine'] = parity_engine
+        if args.precision == 'fp16':
+            # measured on the reference-minted goldens (profiles/r01_parity_report.json, tests/test_gpu_model.py): the
+            # headline engine is the arithmetic north_star names (fp16 storage, fp32 accumulate) and does NOT meet its 1e-3
+            # tensor gate -- no single-pass fp16 layer can (tests/test_precision_budget.py); the fp16x3 engine does
+            line['parity'] = dict(
+                gate='head tensors within 1e-3 rel (max|a-b| / max|b|), contour vertices within 0.5 px, identical instance count',
+                headline_engine=dict(precision='fp16', head_tensor_rel_err='1.3e-3 .. 1e-2', instance_counts='identical or +-1',
+                                     decoded_vertex_err_px='<= 0.03', meets_tensor_gate=False),
+                parity_engine=dict(precision='fp16x3', head_tensor_rel_err='1.4e-5 .. 2e-4', instance_counts='identical',
+                                   decoded_vertex_err_px='<= 0.01', meets_tensor_gate=True),
+                source='profiles/r01_parity_report.json')
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
