@@ -287,7 +287,7 @@ def run_b200(args):
     hms = e0.elapsed_time(e1) / reps
     hflops = 2. * BATCH * hop.dst.h * hop.dst.w * hop.dst.c * hop.src.c * hop.k * hop.k
     achieved = hflops / (hms / 1e3) / 1e12
-    if args.precision in ('fp16', 'fp16x3'):
+    if args.precision in ('fp16f8', 'fp16', 'fp16x3'):
         traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
         ncu_json = os.path.join(ROOT, 'profiles', 'r01_ncu_heads_conv.json')
         if os.path.exists(ncu_json):
@@ -345,7 +345,7 @@ def run_b200(args):
                        sample=f'3 steps x 1 tile of 3x{TILE}x{TILE} (+1 warm-up), oracle/cpn_oracle.py torch-CPU fp32')
         line = dict(metric=METRIC, value=value, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                    dtype={'fp16': 'f16', 'fp16x3': 'f16x3', 'fp32': 'f32'}[args.precision], data='synthetic',
+                    dtype={'fp16f8': 'f16+e4m3', 'fp16': 'f16', 'fp16x3': 'f16x3', 'fp32': 'f32'}[args.precision], data='synthetic',
                     config=dict(workload=f'{ARCH} random-init (synthetic weights seed {SEED}, heads calibrated to '
                                          f'{FG_FRACTION:.0%} foreground), batch {BATCH}x3x{TILE}x{TILE} per GPU',
                                 global_batch=tiles, tile=TILE, parallelism=f'tile-parallel x{world}',
@@ -385,7 +385,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp16x3', 'fp32'])
+    ap.add_argument('--precision', default='fp16f8', choices=['fp16f8', 'fp16', 'fp16x3', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

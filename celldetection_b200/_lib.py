@@ -10,10 +10,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcpn_b200.so')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # ---- enums (mirror include/cpn_b200.h) -------------------------------------------------------------------------------
-DT_F32, DT_F16, DT_U8, DT_F16X2 = 0, 1, 2, 3
+DT_F32, DT_F16, DT_U8, DT_F16X2, DT_F16F8 = 0, 1, 2, 3, 4
 OP_PREP, OP_CONV, OP_MAXPOOL, OP_UPSAMPLE, OP_BILINEAR, OP_PROJ = range(6)
 IN_F32_NCHW, IN_U8_NCHW, IN_U8_NHWC = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SCALED_TANH, ACT_SIGMOID = 0, 1, 2, 3
@@ -23,7 +23,7 @@ ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
 class View(ctypes.Structure):
     _fields_ = [('offset', ctypes.c_int64), ('n', ctypes.c_int32), ('h', ctypes.c_int32), ('w', ctypes.c_int32),
                 ('c', ctypes.c_int32), ('pitch', ctypes.c_int32), ('dtype', ctypes.c_int32),
-                ('lo_delta', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('lo_delta', ctypes.c_int32), ('fp8_exp', ctypes.c_int32)]
 
 
 class Op(ctypes.Structure):
@@ -32,7 +32,8 @@ class Op(ctypes.Structure):
                 ('r', ctypes.c_int32), ('s', ctypes.c_int32), ('stride', ctypes.c_int32), ('pad', ctypes.c_int32),
                 ('kslab', ctypes.c_int32), ('slab_mode', ctypes.c_int32), ('act', ctypes.c_int32),
                 ('act_scale', ctypes.c_float), ('proj_cin_off', ctypes.c_int32), ('proj_cin', ctypes.c_int32),
-                ('out_binding', ctypes.c_int32), ('fuse_next', ctypes.c_int32)]
+                ('out_binding', ctypes.c_int32), ('fuse_next', ctypes.c_int32), ('acc_scale', ctypes.c_float),
+                ('reserved', ctypes.c_int32)]
 
 
 class SelectParams(ctypes.Structure):

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -43,7 +44,10 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     cpn::count_launch();                                                                     \
   } while (0)
 
-inline int dtype_size(int dt) { return dt == CPN_DT_F32 ? 4 : ((dt == CPN_DT_F16 || dt == CPN_DT_F16X2) ? 2 : 1); }
+inline int dtype_size(int dt) {
+  return dt == CPN_DT_F32 ? 4 : ((dt == CPN_DT_F16 || dt == CPN_DT_F16X2 || dt == CPN_DT_F16F8) ? 2 : 1);
+}
+inline bool dtype_has_lo(int dt) { return dt == CPN_DT_F16X2 || dt == CPN_DT_F16F8; }   // second block per pixel
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();  // cached SM count of the current device
@@ -101,5 +105,47 @@ template <>
 __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+#ifdef __CUDACC__
+// F16F8 helpers: four fp32 -> four e4m3 bytes (round to nearest even, saturating), four e4m3 bytes -> four fp32
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+__device__ __forceinline__ void unpack_e4m3x4(uint32_t v, float& a, float& b, float& c, float& d) {
+  const __half2_raw l = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(v & 0xffffu), __NV_E4M3);
+  const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(v >> 16), __NV_E4M3);
+  const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l));
+  const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  a = fl.x; b = fl.y; c = fh.x; d = fh.y;
+}
+// CPN_DT_F16F8 element (see cpn_b200.h): `px` = the view's first hi element of a pixel, c = channel.  8-bit chunk j =
+// c / 32 holds 32 lo8 bytes then 32 hi8 bytes.
+__device__ __forceinline__ float e4m3_to_f32(uint8_t b) {
+  const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3);
+  return __half2float(*reinterpret_cast<const __half*>(&h));
+}
+__device__ __forceinline__ uint8_t f32_to_e4m3(float v) {
+  return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ const uint8_t* f8_block(const __half* px, int lo_delta, int c) {
+  return reinterpret_cast<const uint8_t*>(px + lo_delta) + (c >> 5) * 64 + (c & 31);
+}
+__device__ __forceinline__ uint8_t* f8_block(__half* px, int lo_delta, int c) {
+  return reinterpret_cast<uint8_t*>(px + lo_delta) + (c >> 5) * 64 + (c & 31);
+}
+__device__ __forceinline__ float f16f8_load(const __half* px, int lo_delta, int c, float lo_inv) {
+  return __half2float(px[c]) + e4m3_to_f32(f8_block(px, lo_delta, c)[0]) * lo_inv;
+}
+__device__ __forceinline__ void f16f8_store(__half* px, int lo_delta, int c, float v, float lo_scale, float hi8_scale) {
+  const __half h = __float2half_rn(v);
+  const float hf = __half2float(h);
+  px[c] = h;
+  uint8_t* q = f8_block(px, lo_delta, c);
+  q[0] = f32_to_e4m3((v - hf) * lo_scale);
+  q[32] = f32_to_e4m3(hf * hi8_scale);
+}
+#endif
 
 }  // namespace cpn

@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -77,8 +78,13 @@ struct ConvTcParams {
   int halo, pw, ph, plane_stride, nb_stages, swap_lbo_sbo;
   int halo_sw128, halo_baseoff;
   int split_lofirst;                 // split mode: run the two correction passes before the main pass
-  int split, a_lo, out_lo, res_lo;   // CPN_DT_F16X2: 3 passes per 64-channel block (A_hi W_hi, A_lo W_hi, A_hi W_lo);
-                                     // element distance hi -> lo half in the A / output / residual buffers
+  int split, a_lo, out_lo, res_lo;   // split = 1, CPN_DT_F16X2: 3 passes per 64-channel block (A_hi W_hi, A_lo W_hi,
+                                     // A_hi W_lo); element distance hi -> lo half in the A / output / residual buffers.
+                                     // split = 2, CPN_DT_F16F8: 2 passes -- one kind::f8f6f4 K block over the pixel's
+                                     // 128-byte (lo8 | hi8) row, then the kind::f16 K block; *_lo = distance to the 8-bit block
+  float acc_scale;                   // accumulator scale applied first in every epilogue (1/S of the F16F8 weight packing)
+  float out_lo_scale, out_hi8_scale; // F16F8 output: lo8 = e4m3((v - hi) * out_lo_scale), hi8 = e4m3(hi * out_hi8_scale)
+  float res_lo_inv;                  // F16F8 residual: value = hi + lo8 * res_lo_inv
   int coalesce;             // conv_tc_kernel: smem-staged, line-coalesced residual loads / output stores (epilogue_coalesced)
   int rotate;               // start each CTA's K loop at a different (tap, block): de-correlates the L2 reads of the shared weights   // 1: the patch is ONE box {64, PW, PH, 1} with SWIZZLE_128B (128-byte pixel rows)
 };
@@ -177,6 +183,20 @@ __device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a,
       "setp.ne.b32 p, %4, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// e4m3 x e4m3 -> fp32 (kind::f8f6f4, K = 32 per instruction): same descriptors, same instruction-descriptor bits (format
+// code 0 is E4M3 for this kind and F16 for kind::f16), same accumulator -- the correction pass of the F16F8 engine.
+__device__ __forceinline__ void umma_f8_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -313,10 +333,10 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 b = p.bias ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + b.x;
-        f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + b.y;
-        f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + b.z;
-        f[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + b.w;
+        f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) * p.acc_scale + b.x;
+        f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) * p.acc_scale + b.y;
+        f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) * p.acc_scale + b.z;
+        f[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) * p.acc_scale + b.w;
       }
       if (p.relu) {
 #pragma unroll
@@ -370,27 +390,36 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float4 b = p.bias ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float f0 = __uint_as_float(v[q * 4 + 0]) + b.x, f1 = __uint_as_float(v[q * 4 + 1]) + b.y;
-        float f2 = __uint_as_float(v[q * 4 + 2]) + b.z, f3 = __uint_as_float(v[q * 4 + 3]) + b.w;
+        float f0 = __uint_as_float(v[q * 4 + 0]) * p.acc_scale + b.x, f1 = __uint_as_float(v[q * 4 + 1]) * p.acc_scale + b.y;
+        float f2 = __uint_as_float(v[q * 4 + 2]) * p.acc_scale + b.z, f3 = __uint_as_float(v[q * 4 + 3]) * p.acc_scale + b.w;
         if (rp) {
           const __half2 r0 = *reinterpret_cast<const __half2*>(&rw[q * 2]);
           const __half2 r1 = *reinterpret_cast<const __half2*>(&rw[q * 2 + 1]);
           f0 += __low2float(r0); f1 += __high2float(r0); f2 += __low2float(r1); f3 += __high2float(r1);
-          if (p.split) {   // residual = hi + lo
+          if (p.split == 1) {   // residual = hi + lo
             const uint2 rl = __ldg(reinterpret_cast<const uint2*>(rp + p.res_lo + ch * 32 + q * 4));
             const __half2 l0 = *reinterpret_cast<const __half2*>(&rl.x), l1 = *reinterpret_cast<const __half2*>(&rl.y);
             f0 += __low2float(l0); f1 += __high2float(l0); f2 += __low2float(l1); f3 += __high2float(l1);
+          } else if (p.split == 2) {   // residual = hi + lo8 * 2^-(8+e): the chunk's first 32 bytes are the lo8 values
+            float l0, l1, l2, l3;
+            unpack_e4m3x4(__ldg(reinterpret_cast<const uint32_t*>(rp + p.res_lo + ch * 32) + q), l0, l1, l2, l3);
+            f0 += l0 * p.res_lo_inv; f1 += l1 * p.res_lo_inv; f2 += l2 * p.res_lo_inv; f3 += l3 * p.res_lo_inv;
           }
         }
         if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
         __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
         pk[q * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
         pk[q * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-        if (p.split) {     // lo = fp16(v - hi)
+        if (p.split == 1) {     // lo = fp16(v - hi)
           __half2 g0 = __floats2half2_rn(f0 - __low2float(h0), f1 - __high2float(h0));
           __half2 g1 = __floats2half2_rn(f2 - __low2float(h1), f3 - __high2float(h1));
           pl[q * 2 + 0] = *reinterpret_cast<uint32_t*>(&g0);
           pl[q * 2 + 1] = *reinterpret_cast<uint32_t*>(&g1);
+        } else if (p.split == 2) {   // 8-bit block of the chunk: 32 x lo8 then 32 x hi8
+          const float a0 = __low2float(h0), a1 = __high2float(h0), a2 = __low2float(h1), a3 = __high2float(h1);
+          pl[q] = pack_e4m3x4((f0 - a0) * p.out_lo_scale, (f1 - a1) * p.out_lo_scale, (f2 - a2) * p.out_lo_scale,
+                              (f3 - a3) * p.out_lo_scale);
+          pl[8 + q] = pack_e4m3x4(a0 * p.out_hi8_scale, a1 * p.out_hi8_scale, a2 * p.out_hi8_scale, a3 * p.out_hi8_scale);
         }
       }
       if (PF && rp && ch + 2 < BN / 32) load_res_chunk(rp, ch + 2, rc);   // rc is dead: request the next chunk now
@@ -481,6 +510,7 @@ __device__ __forceinline__ void epilogue_coalesced(const ConvTcParams& p, const 
                                                    uint4 (&rg)[4], uint4 (&rgl)[4]) {
   const bool has_res = p.res != nullptr;
   const bool split = p.split != 0;
+  const bool f8 = p.split == 2;
 #pragma unroll 1
   for (int ch = half; ch < BN / 32; ch += 2) {
     uint32_t v[32];
@@ -508,13 +538,17 @@ __device__ __forceinline__ void epilogue_coalesced(const ConvTcParams& p, const 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float4 b = p.bias ? __ldg(b4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float f0 = __uint_as_float(v[k * 4 + 0]) + b.x, f1 = __uint_as_float(v[k * 4 + 1]) + b.y;
-      float f2 = __uint_as_float(v[k * 4 + 2]) + b.z, f3 = __uint_as_float(v[k * 4 + 3]) + b.w;
+      float f0 = __uint_as_float(v[k * 4 + 0]) * p.acc_scale + b.x, f1 = __uint_as_float(v[k * 4 + 1]) * p.acc_scale + b.y;
+      float f2 = __uint_as_float(v[k * 4 + 2]) * p.acc_scale + b.z, f3 = __uint_as_float(v[k * 4 + 3]) * p.acc_scale + b.w;
       if (has_res) {
         const __half2 r0 = *reinterpret_cast<const __half2*>(&pk[k * 2]);
         const __half2 r1 = *reinterpret_cast<const __half2*>(&pk[k * 2 + 1]);
         f0 += __low2float(r0); f1 += __high2float(r0); f2 += __low2float(r1); f3 += __high2float(r1);
-        if (split) {
+        if (f8) {                                                      // words 0..7 of the 8-bit chunk are the lo8 values
+          float l0, l1, l2, l3;
+          unpack_e4m3x4(pl[k], l0, l1, l2, l3);
+          f0 += l0 * p.res_lo_inv; f1 += l1 * p.res_lo_inv; f2 += l2 * p.res_lo_inv; f3 += l3 * p.res_lo_inv;
+        } else if (split) {
           const __half2 l0 = *reinterpret_cast<const __half2*>(&pl[k * 2]);
           const __half2 l1 = *reinterpret_cast<const __half2*>(&pl[k * 2 + 1]);
           f0 += __low2float(l0); f1 += __high2float(l0); f2 += __low2float(l1); f3 += __high2float(l1);
@@ -524,13 +558,19 @@ __device__ __forceinline__ void epilogue_coalesced(const ConvTcParams& p, const 
       const __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
       pk[k * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h0);
       pk[k * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-      if (split) {                                                   // lo = fp16(v - hi)
+      if (f8) {                                                      // 8-bit chunk: words 0..7 lo8, words 8..15 hi8
+        const float a0 = __low2float(h0), a1 = __high2float(h0), a2 = __low2float(h1), a3 = __high2float(h1);
+        pl[k] = pack_e4m3x4((f0 - a0) * p.out_lo_scale, (f1 - a1) * p.out_lo_scale, (f2 - a2) * p.out_lo_scale,
+                            (f3 - a3) * p.out_lo_scale);   // (the residual's lo8 word k was consumed above)
+        pl[8 + k] = pack_e4m3x4(a0 * p.out_hi8_scale, a1 * p.out_hi8_scale, a2 * p.out_hi8_scale, a3 * p.out_hi8_scale);
+      } else if (split) {                                            // lo = fp16(v - hi)
         const __half2 g0 = __floats2half2_rn(f0 - __low2float(h0), f1 - __high2float(h0));
         const __half2 g1 = __floats2half2_rn(f2 - __low2float(h1), f3 - __high2float(h1));
         pl[k * 2 + 0] = *reinterpret_cast<const uint32_t*>(&g0);
         pl[k * 2 + 1] = *reinterpret_cast<const uint32_t*>(&g1);
       }
     }
+
     __syncwarp();                                                    // every lane has read its residual row(s)
     stg_put_o(stg, lane, rr);
     __syncwarp();
@@ -626,7 +666,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           int tap = kk / p.cblocks, cb = kk - tap * p.cblocks;   // cb runs over 3 * logical blocks when split
           if (++kk == nk) kk = 0;
           int a_ch = cb * TC_BK;
-          if (p.split) {
+          if (p.split == 1) {
             // pass-major K order, the two correction passes first (see split_pass_order)
             const int cbl = p.cblocks / 3, per_pass = p.R * p.S * cbl;
             const int kq = tap * p.cblocks + cb, pi = kq / per_pass, rem = kq - pi * per_pass;
@@ -635,6 +675,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int c = rem - tap * cbl;
             cb = pass * cbl + c;
             a_ch = c * TC_BK + (pass == 1 ? p.a_lo : 0);
+          } else if (p.split == 2) {
+            // pass-major: the 8-bit correction blocks of every (tap, channel block) first, then the fp16 blocks.  Weight
+            // K blocks [0, cbl) are the e4m3 rows, [cbl, 2 cbl) the fp16 rows; the activations' 8-bit rows sit a_lo
+            // elements behind the fp16 ones
+            const int cbl = p.cblocks / 2, per_pass = p.R * p.S * cbl;
+            const int kq = tap * p.cblocks + cb, pi = kq / per_pass, rem = kq - pi * per_pass;
+            tap = rem / cbl;
+            const int c = rem - tap * cbl;
+            cb = pi * cbl + c;
+            a_ch = c * TC_BK + (pi == 0 ? p.a_lo : 0);
           }
           const int r = tap / p.S, s = tap - r * p.S;
           int qy = r - p.pad, qx = s - p.pad, map = 0;
@@ -671,9 +721,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
         const uint64_t da = make_sw128_kmajor_desc(sa), db = make_sw128_kmajor_desc(sb);
         // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
-        umma_f16_elect(d_tmem, da, db, idesc, (uint32_t)(kb != 0));
+        if (p.split == 2 && kb < (nk >> 1)) {   // 8-bit correction blocks (K = 32 bytes per instruction: same +2 steps)
+          umma_f8_elect(d_tmem, da, db, idesc, (uint32_t)(kb != 0));
 #pragma unroll
-        for (int k = 1; k < TC_BK / 16; ++k) umma_f16_elect(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+          for (int k = 1; k < TC_BK / 16; ++k) umma_f8_elect(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+        } else {
+          umma_f16_elect(d_tmem, da, db, idesc, (uint32_t)(kb != 0));
+#pragma unroll
+          for (int k = 1; k < TC_BK / 16; ++k) umma_f16_elect(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+        }
         umma_commit_elect(smem_u32(&bar_empty[stage]));  // frees the smem stage when these MMAs retire
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
@@ -823,10 +879,10 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
         const int n0 = (int)(tile % p.tiles_n) * BN;
         for (int cb = 0; cb < p.cblocks; ++cb) {
           int cbw = cb;                                   // K block of the (W_hi | W_hi | W_lo) weight tensor
-          if (p.split) {
+          if (p.split == 1) {
             const int cbl = p.cblocks / 3, pi = cb / cbl;
             cbw = split_pass_order(pi, p.split_lofirst) * cbl + (cb - pi * cbl);
-          }
+          }                                               // split == 2: (W8 | W16) is already in issue order
           int tap = p.rotate ? (int)(blockIdx.x % (unsigned)taps) : 0;
           for (int it = 0; it < taps; ++it, tap = (tap + 1 == taps ? 0 : tap + 1)) {
             mbar_wait(smem_u32(&bar_bempty[sb]), phb ^ 1);
@@ -852,9 +908,12 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
         const int cbase = p.slab_mode ? (n0 / p.kslab) * p.kslab : 0;   // grouped: this N tile's 64-channel slab
         for (int cb = 0; cb < p.cblocks; ++cb) {
           int a_ch = cb * TC_BK;
-          if (p.split) {
+          if (p.split == 1) {
             const int cbl = p.cblocks / 3, pi = cb / cbl, pass = split_pass_order(pi, p.split_lofirst);
             a_ch = (cb - pi * cbl) * TC_BK + (pass == 1 ? p.a_lo : 0);
+          } else if (p.split == 2) {
+            const int cbl = p.cblocks / 2;
+            a_ch = cb < cbl ? cb * TC_BK + p.a_lo : (cb - cbl) * TC_BK;
           }
           mbar_wait(smem_u32(&bar_aempty[ab]), pha ^ 1);
           const uint32_t full = smem_u32(&bar_afull[ab]);
@@ -900,6 +959,17 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
             // sub-tile j starts 8 pixel rows (1024 B -> +64 in the >>4 field) further, K steps +32 B (+2)
             const uint64_t da0 = make_sw128_kmajor_desc_ex(patch + (uint32_t)((r * p.pw + s_) * 128),
                                                            (uint32_t)(p.pw * 128), 0);
+            if (p.split == 2 && cb < (p.cblocks >> 1)) {   // 8-bit correction block: the patch rows are (lo8 | hi8) bytes
+#pragma unroll
+              for (int jj = 0; jj < JN; ++jj) {
+                const int j = jb + jj;
+                const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MSUB + j) * BN);
+                umma_f8_elect(d_tmem, da0 + (uint64_t)(j * 64), db, idesc, first);
+#pragma unroll
+                for (int k = 1; k < TC_BK / 16; ++k)
+                  umma_f8_elect(d_tmem, da0 + (uint64_t)(j * 64 + k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+              }
+            } else {
 #pragma unroll
             for (int jj = 0; jj < JN; ++jj) {
               const int j = jb + jj;
@@ -908,6 +978,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
 #pragma unroll
               for (int k = 1; k < TC_BK / 16; ++k)
                 umma_f16_elect(d_tmem, da0 + (uint64_t)(j * 64 + k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+            }
             }
           } else {
 #pragma unroll
@@ -1026,9 +1097,13 @@ static int pick_bn(int cout, int slab_mode) {
 
 int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const void* res, const void* wgt,
                         const float* bias, ConvTcPlan** out) {
-  const bool split = op.src.dtype == CPN_DT_F16X2;
+  const bool f16f8 = op.src.dtype == CPN_DT_F16F8;
+  const bool split = op.src.dtype == CPN_DT_F16X2 || f16f8;    // tensors with a second (lo / 8-bit) block per pixel
+  const int npass = f16f8 ? 2 : (split ? 3 : 1);
   CPN_REQUIRE((op.src.dtype == CPN_DT_F16 || split) && op.dst.dtype == op.src.dtype,
-              "conv_tc: fp16 (or split fp16) activations required");
+              "conv_tc: fp16 (or split fp16 / fp16+e4m3) activations required");
+  CPN_REQUIRE(!f16f8 || (op.src.lo_delta % 32 == 0 && op.dst.lo_delta % 32 == 0 && (op.res.n == 0 || op.res.lo_delta % 32 == 0)),
+              "conv_tc: fp16+e4m3 tensors need lo_delta multiples of 32 elements");
   CPN_REQUIRE(op.res.n == 0 || op.res.dtype == op.src.dtype, "conv_tc: residual dtype must match");
   CPN_REQUIRE(!split || (op.src.lo_delta % 8 == 0 && op.dst.lo_delta % 8 == 0 && (op.res.n == 0 || op.res.lo_delta % 8 == 0)),
               "conv_tc: lo_delta must be a multiple of 8 elements");
@@ -1070,7 +1145,7 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   }
   for (int m = nmaps; m < 4; ++m) p.tmA[m] = p.tmA[0];
   {
-    const cuuint64_t kw = (cuuint64_t)op.kslab * (split ? 3 : 1);   // split: weights are (W_hi | W_hi | W_lo) along K
+    const cuuint64_t kw = (cuuint64_t)op.kslab * npass;   // F16X2: (W_hi | W_hi | W_lo) along K; F16F8: (W8 | S * W_hi)
     cuuint64_t dims[3] = {kw, (cuuint64_t)op.dst.c, (cuuint64_t)(op.r * op.s)};
     cuuint64_t strides[2] = {kw * 2, kw * op.dst.c * 2};
     cuuint32_t box[3] = {TC_BK, (cuuint32_t)bn, 1};
@@ -1083,8 +1158,12 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   p.res_h = op.res.n ? op.res.h : 0; p.res_w = op.res.n ? op.res.w : 0;
   p.N = op.dst.n; p.Ho = op.dst.h; p.Wo = op.dst.w; p.cout = op.dst.c;
   p.R = op.r; p.S = op.s; p.stride = op.stride; p.pad = op.pad;
-  p.cblocks = op.kslab / TC_BK * (split ? 3 : 1); p.kslab = op.kslab; p.slab_mode = op.slab_mode;
-  p.split = split ? 1 : 0; p.a_lo = op.src.lo_delta; p.out_lo = op.dst.lo_delta; p.res_lo = op.res.n ? op.res.lo_delta : 0;
+  p.cblocks = op.kslab / TC_BK * npass; p.kslab = op.kslab; p.slab_mode = op.slab_mode;
+  p.split = f16f8 ? 2 : (split ? 1 : 0); p.a_lo = op.src.lo_delta; p.out_lo = op.dst.lo_delta;
+  p.res_lo = op.res.n ? op.res.lo_delta : 0;
+  p.acc_scale = op.acc_scale != 0.f ? op.acc_scale : 1.f;
+  p.out_lo_scale = ldexpf(1.f, 8 + op.dst.fp8_exp); p.out_hi8_scale = ldexpf(1.f, -2 + op.dst.fp8_exp);
+  p.res_lo_inv = ldexpf(1.f, -(8 + (op.res.n ? op.res.fp8_exp : 0)));
   p.relu = op.act == CPN_ACT_RELU;
   {
     static int rot_env = -1;
@@ -1127,6 +1206,7 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
         cuuint32_t box[4] = {(cuuint32_t)(sw128_env ? 64 : 8), (cuuint32_t)pw, (cuuint32_t)ph, 1};
         if (encode_map(&p.tmH, const_cast<void*>(src), 4, dims, strides, box, sw128_env != 0)) { delete pl; return 1; }
         p.halo_sw128 = sw128_env; p.halo_baseoff = baseoff_env;
+        CPN_REQUIRE(!f16f8 || sw128_env, "conv_tc: the fp16+e4m3 engine needs the SWIZZLE_128B halo patch (CPN_HALO_SW128)");
         p.halo = 1; p.pw = pw; p.ph = ph; p.plane_stride = plane_stride; p.nb_stages = nbs; p.swap_lbo_sbo = swap_env;
         pl->msub = msub;
         p.tiles_x = (op.dst.w + 8 * msub - 1) / (8 * msub);

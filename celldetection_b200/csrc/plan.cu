@@ -71,15 +71,17 @@ extern "C" int cpn_device_info(char* name_host, int n, int* sm_count_host, int* 
 
 static size_t view_bytes(const cpn_view_t& v) {
   if (v.n == 0) return 0;
-  const size_t last = (size_t)v.c + (v.dtype == CPN_DT_F16X2 ? (size_t)v.lo_delta : 0);   // one past the last element
+  const size_t last = (size_t)v.c + (dtype_has_lo(v.dtype) ? (size_t)v.lo_delta : 0);   // one past the last element
   return ((size_t)v.n * v.h * v.w - 1) * (size_t)v.pitch * dtype_size(v.dtype) + last * dtype_size(v.dtype);
 }
 
 static int check_view(const cpn_view_t& v, size_t limit, const char* what, int i) {
   CPN_REQUIRE(v.n > 0 && v.h > 0 && v.w > 0 && v.c > 0 && v.pitch >= v.c, "op %d: bad %s view (%d,%d,%d,%d pitch %d)", i,
               what, v.n, v.h, v.w, v.c, v.pitch);
-  CPN_REQUIRE(v.dtype != CPN_DT_F16X2 || (v.lo_delta >= v.c && v.lo_delta + v.c <= v.pitch),
+  CPN_REQUIRE(!dtype_has_lo(v.dtype) || (v.lo_delta >= v.c && v.lo_delta + v.c <= v.pitch),
               "op %d: bad %s split view (c %d lo_delta %d pitch %d)", i, what, v.c, v.lo_delta, v.pitch);
+  CPN_REQUIRE(v.dtype != CPN_DT_F16F8 || (v.lo_delta % 32 == 0 && v.c % 32 == 0 && v.fp8_exp >= -64 && v.fp8_exp <= 64),
+              "op %d: bad %s fp16+e4m3 view (c %d lo_delta %d fp8_exp %d)", i, what, v.c, v.lo_delta, v.fp8_exp);
   CPN_REQUIRE(v.offset >= 0 && (size_t)v.offset + view_bytes(v) <= limit,
               "op %d: %s view [%lld, +%zu) exceeds its buffer of %zu bytes", i, what, (long long)v.offset,
               view_bytes(v), limit);

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <cstring>
 #include <cstdlib>
+#include <cmath>
 
 namespace cpn {
 
@@ -25,9 +26,36 @@ __device__ __forceinline__ void split_store(__half* o, int lo_delta, float v) {
   o[lo_delta] = __float2half_rn(v - __half2float(h));
 }
 
+// Second block of a pixel: none (lo_delta == 0), fp16 lo halves (CPN_DT_F16X2) or the e4m3 (lo8 | hi8) chunks of
+// CPN_DT_F16F8 with their power-of-two scales.
+struct LoFmt {
+  int lo_delta;
+  int f8;
+  float lo_scale, hi8_scale, lo_inv;
+};
+static LoFmt lo_fmt(const cpn_view_t& v) {
+  LoFmt f;
+  f.lo_delta = dtype_has_lo(v.dtype) ? v.lo_delta : 0;
+  f.f8 = v.dtype == CPN_DT_F16F8;
+  f.lo_scale = ldexpf(1.f, 8 + v.fp8_exp); f.hi8_scale = ldexpf(1.f, -2 + v.fp8_exp); f.lo_inv = ldexpf(1.f, -(8 + v.fp8_exp));
+  return f;
+}
+// 8 consecutive channels (c0 % 8 == 0) of a CPN_DT_F16F8 pixel: hi halves + 8 lo8 bytes + 8 hi8 bytes
+__device__ __forceinline__ void f16f8_store8(__half* px, const LoFmt& F, int c0, const float (&v)[8]) {
+  __align__(16) __half h[8];
+  float lo[8], hf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { h[j] = __float2half_rn(v[j]); hf[j] = __half2float(h[j]); lo[j] = (v[j] - hf[j]) * F.lo_scale; hf[j] *= F.hi8_scale; }
+  *reinterpret_cast<uint4*>(px + c0) = *reinterpret_cast<const uint4*>(h);
+  uint8_t* q = f8_block(px, F.lo_delta, c0);
+  *reinterpret_cast<uint2*>(q) = make_uint2(pack_e4m3x4(lo[0], lo[1], lo[2], lo[3]), pack_e4m3x4(lo[4], lo[5], lo[6], lo[7]));
+  *reinterpret_cast<uint2*>(q + 32) = make_uint2(pack_e4m3x4(hf[0], hf[1], hf[2], hf[3]), pack_e4m3x4(hf[4], hf[5], hf[6], hf[7]));
+}
+
 template <typename T>
 __global__ void prep_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out, int N, int C, int H, int W,
-                            int pitch, int32_t* __restrict__ flags, int lo_delta) {
+                            int pitch, int32_t* __restrict__ flags, const LoFmt F) {
+  const int lo_delta = F.lo_delta;
   const long long total = (long long)N * H * W;
   bool bad = false;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -44,6 +72,7 @@ __global__ void prep_kernel(const void* __restrict__ in, int fmt, T* __restrict_
       } else {
         v = (float)reinterpret_cast<const uint8_t*>(in)[i * C + c] / 255.f;
       }
+      if (sizeof(T) == 2 && F.f8) { f16f8_store(reinterpret_cast<__half*>(o), lo_delta, c, v, F.lo_scale, F.hi8_scale); continue; }
       o[c] = from_f32<T>(v);
       if (sizeof(T) == 2 && lo_delta > 0) o[c + lo_delta] = from_f32<T>(v - to_f32<T>(o[c]));
     }
@@ -59,7 +88,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) prep_im2col_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out, int N,
                                                           int C, int H, int W, int Ho, int Wo, int Kp, int pitch, int k,
                                                           int stride, int pad, int32_t* __restrict__ flags,
-                                                          int lo_delta) {
+                                                          const LoFmt F) {
+  const int lo_delta = F.lo_delta;
   // per-entry tables: e -> (dy, dx, c) and the NCHW / NHWC offsets relative to the window origin
   __shared__ int off_nchw[512], off_nhwc[512];
   __shared__ signed char dys[512], dxs[512];
@@ -88,6 +118,7 @@ __global__ void __launch_bounds__(256) prep_im2col_kernel(const void* __restrict
     const long long base_nhwc = (((long long)n * H + iy0) * W + ix0) * C;
     __align__(16) T vals[8];
     __align__(16) T vlo[8];
+    float vf[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int e = ch * 8 + j;
@@ -107,9 +138,12 @@ __global__ void __launch_bounds__(256) prep_im2col_kernel(const void* __restrict
       }
       vals[j] = from_f32<T>(v);
       vlo[j] = from_f32<T>(v - to_f32<T>(vals[j]));
+      vf[j] = v;
     }
     T* o = out + (((long long)n * Ho + oy) * Wo + ox) * pitch + ch * 8;
-    if (sizeof(T) == 2) {
+    if (sizeof(T) == 2 && F.f8) {
+      f16f8_store8(reinterpret_cast<__half*>(o) - ch * 8, F, ch * 8, vf);
+    } else if (sizeof(T) == 2) {
       *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(vals);
       if (lo_delta > 0) *reinterpret_cast<uint4*>(o + lo_delta) = *reinterpret_cast<const uint4*>(vlo);
     } else {
@@ -130,7 +164,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) prep_im2col_tiled_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out,
                                                                 int N, int C, int H, int W, int Ho, int Wo, int Kp,
                                                                 int pitch, int k, int stride, int pad,
-                                                                int32_t* __restrict__ flags, int lo_delta, int WH, int WW) {
+                                                                int32_t* __restrict__ flags, const LoFmt F, int WH, int WW) {
+  const int lo_delta = F.lo_delta;
   extern __shared__ float prep_sm[];                  // [C][WH][WW] window, then int off_sm[Kp]
   int* off_sm = reinterpret_cast<int*>(prep_sm + C * WH * WW);
   const int kk = k * k * C;
@@ -173,15 +208,19 @@ __global__ void __launch_bounds__(256) prep_im2col_tiled_kernel(const void* __re
     const float* win = prep_sm + (py * stride) * WW + px * stride;
     __align__(16) T vals[8];
     __align__(16) T vlo[8];
+    float vf[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int o = off_sm[ch * 8 + j];
       const float v = o >= 0 ? win[o] : 0.f;
       vals[j] = from_f32<T>(v);
       vlo[j] = from_f32<T>(v - to_f32<T>(vals[j]));
+      vf[j] = v;
     }
     T* o = out + (((long long)n * Ho + oy) * Wo + ox) * pitch + ch * 8;
-    if (sizeof(T) == 2) {
+    if (sizeof(T) == 2 && F.f8) {
+      f16f8_store8(reinterpret_cast<__half*>(o) - ch * 8, F, ch * 8, vf);
+    } else if (sizeof(T) == 2) {
       *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(vals);
       if (lo_delta > 0) *reinterpret_cast<uint4*>(o + lo_delta) = *reinterpret_cast<const uint4*>(vlo);
     } else {
@@ -195,6 +234,7 @@ __global__ void __launch_bounds__(256) prep_im2col_tiled_kernel(const void* __re
 int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* dst, int32_t* flags, cudaStream_t st) {
   CPN_REQUIRE(input_format >= 0 && input_format <= 2, "prep: bad input format %d", input_format);
   if (op.r > 0) {  // im2col mode: src view describes the logical input (n, h, w, c)
+    CPN_REQUIRE(op.dst.dtype != CPN_DT_F16F8 || op.dst.lo_delta % 32 == 0, "prep: fp16+e4m3 lo_delta must be a multiple of 32");
     CPN_REQUIRE(op.dst.c % 8 == 0 && op.dst.pitch % 8 == 0 && op.dst.c >= op.r * op.r * op.src.c && op.dst.c <= 512,
                 "prep(im2col): dst channels %d must be a multiple of 8, >= k*k*c and <= 512", op.dst.c);
     {
@@ -208,11 +248,11 @@ int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* d
         if (op.dst.dtype == CPN_DT_F32)
           prep_im2col_tiled_kernel<float><<<(int)blocks, 256, smem, st>>>(
               input, input_format, (float*)dst, op.src.n, op.src.c, op.src.h, op.src.w, op.dst.h, op.dst.w, op.dst.c,
-              op.dst.pitch, op.r, op.stride, op.pad, flags, 0, WH, WW);
+              op.dst.pitch, op.r, op.stride, op.pad, flags, LoFmt{0, 0, 1.f, 1.f, 1.f}, WH, WW);
         else
           prep_im2col_tiled_kernel<__half><<<(int)blocks, 256, smem, st>>>(
               input, input_format, (__half*)dst, op.src.n, op.src.c, op.src.h, op.src.w, op.dst.h, op.dst.w, op.dst.c,
-              op.dst.pitch, op.r, op.stride, op.pad, flags, op.dst.dtype == CPN_DT_F16X2 ? op.dst.lo_delta : 0, WH, WW);
+              op.dst.pitch, op.r, op.stride, op.pad, flags, lo_fmt(op.dst), WH, WW);
         CPN_CHECK_LAUNCH();
         return 0;
       }
@@ -222,12 +262,11 @@ int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* d
     if (op.dst.dtype == CPN_DT_F32)
       prep_im2col_kernel<float><<<grid, 256, 0, st>>>(input, input_format, (float*)dst, op.src.n, op.src.c, op.src.h,
                                                       op.src.w, op.dst.h, op.dst.w, op.dst.c, op.dst.pitch, op.r,
-                                                      op.stride, op.pad, flags, 0);
+                                                      op.stride, op.pad, flags, LoFmt{0, 0, 1.f, 1.f, 1.f});
     else
       prep_im2col_kernel<__half><<<grid, 256, 0, st>>>(input, input_format, (__half*)dst, op.src.n, op.src.c, op.src.h,
                                                        op.src.w, op.dst.h, op.dst.w, op.dst.c, op.dst.pitch, op.r,
-                                                       op.stride, op.pad, flags,
-                                                       op.dst.dtype == CPN_DT_F16X2 ? op.dst.lo_delta : 0);
+                                                       op.stride, op.pad, flags, lo_fmt(op.dst));
     CPN_CHECK_LAUNCH();
     return 0;
   }
@@ -235,11 +274,10 @@ int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* d
   const int grid = grid_for(total, 256);
   if (op.dst.dtype == CPN_DT_F32)
     prep_kernel<float><<<grid, 256, 0, st>>>(input, input_format, (float*)dst, op.dst.n, op.dst.c, op.dst.h, op.dst.w,
-                                             op.dst.pitch, flags, 0);
+                                             op.dst.pitch, flags, LoFmt{0, 0, 1.f, 1.f, 1.f});
   else
     prep_kernel<__half><<<grid, 256, 0, st>>>(input, input_format, (__half*)dst, op.dst.n, op.dst.c, op.dst.h,
-                                              op.dst.w, op.dst.pitch, flags,
-                                              op.dst.dtype == CPN_DT_F16X2 ? op.dst.lo_delta : 0);
+                                              op.dst.w, op.dst.pitch, flags, lo_fmt(op.dst));
   CPN_CHECK_LAUNCH();
   return 0;
 }
@@ -310,7 +348,8 @@ __global__ void maxpool_kernel(const T* __restrict__ src, T* __restrict__ dst, i
 
 // split fp16 pairs: the maximum is taken on the reconstructed value hi + lo and the winning PAIR is copied
 __global__ void maxpool_split_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int H, int W, int C,
-                                     int sp, int slo, int Ho, int Wo, int dp, int dlo, int k, int stride, int pad) {
+                                     int sp, int slo, int Ho, int Wo, int dp, int dlo, int k, int stride, int pad,
+                                     int f8, float lo_inv) {
   const long long total = (long long)N * Ho * Wo * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -321,6 +360,7 @@ __global__ void maxpool_split_kernel(const __half* __restrict__ src, __half* __r
     const int n = (int)(pix / Ho);
     float best = -INFINITY;
     __half bh = __float2half(0.f), bl = __float2half(0.f);
+    uint8_t b8lo = 0, b8hi = 0;
     for (int dy = 0; dy < k; ++dy) {
       const int iy = oy * stride - pad + dy;
       if (iy < 0 || iy >= H) continue;
@@ -328,6 +368,12 @@ __global__ void maxpool_split_kernel(const __half* __restrict__ src, __half* __r
         const int ix = ox * stride - pad + dx;
         if (ix < 0 || ix >= W) continue;
         const __half* q = src + (((long long)n * H + iy) * W + ix) * sp + c;
+        if (f8) {   // the winning (hi, lo8, hi8) triple is copied (source and destination share the scales)
+          const uint8_t* q8 = f8_block(q - c, slo, c);
+          const float v = __half2float(q[0]) + e4m3_to_f32(q8[0]) * lo_inv;
+          if (v > best) { best = v; bh = q[0]; b8lo = q8[0]; b8hi = q8[32]; }
+          continue;
+        }
         const __half h = q[0], l = q[slo];
         const float v = __half2float(h) + __half2float(l);
         if (v > best) { best = v; bh = h; bl = l; }
@@ -335,18 +381,24 @@ __global__ void maxpool_split_kernel(const __half* __restrict__ src, __half* __r
     }
     __half* o = dst + (((long long)n * Ho + oy) * Wo + ox) * dp + c;
     o[0] = bh;
+    if (f8) {
+      uint8_t* o8 = f8_block(o - c, dlo, c);
+      o8[0] = b8lo; o8[32] = b8hi;
+      continue;
+    }
     o[dlo] = bl;
   }
 }
 
 int maxpool_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st) {
-  if (op.src.dtype == CPN_DT_F16X2) {
-    CPN_REQUIRE(op.dst.dtype == CPN_DT_F16X2 && op.src.c == op.dst.c, "maxpool: split dtype/channel mismatch");
+  if (dtype_has_lo(op.src.dtype)) {
+    CPN_REQUIRE(op.dst.dtype == op.src.dtype && op.src.c == op.dst.c && op.src.fp8_exp == op.dst.fp8_exp,
+                "maxpool: split dtype/channel/scale mismatch");
     const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * op.dst.c;
     maxpool_split_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __half*)src, (__half*)dst, op.src.n, op.src.h,
                                                               op.src.w, op.src.c, op.src.pitch, op.src.lo_delta, op.dst.h,
                                                               op.dst.w, op.dst.pitch, op.dst.lo_delta, op.r, op.stride,
-                                                              op.pad);
+                                                              op.pad, op.src.dtype == CPN_DT_F16F8, lo_fmt(op.src).lo_inv);
     CPN_CHECK_LAUNCH();
     return 0;
   }
@@ -409,8 +461,9 @@ __global__ void __launch_bounds__(256) upsample_int_kernel(const uint4* __restri
 }
 
 int upsample_launch(const cpn_op_t& op_in, const void* src, void* dst, cudaStream_t st) {
-  if (op_in.src.dtype == CPN_DT_F16X2) {   // nearest copy is exact per half: run the fp16 kernel on the hi and lo planes
-    CPN_REQUIRE(op_in.dst.dtype == CPN_DT_F16X2, "upsample: split dtype mismatch");
+  if (dtype_has_lo(op_in.src.dtype)) {   // nearest copy is exact per block: run the fp16 kernel on the hi and the lo / 8-bit
+                                         // planes (the latter as opaque 2-byte slots)
+    CPN_REQUIRE(op_in.dst.dtype == op_in.src.dtype && op_in.src.fp8_exp == op_in.dst.fp8_exp, "upsample: split dtype mismatch");
     cpn_op_t o = op_in;
     o.src.dtype = o.dst.dtype = CPN_DT_F16;
     if (upsample_launch(o, src, dst, st)) return 1;
@@ -518,7 +571,7 @@ __global__ void __launch_bounds__(256) bilinear_h8_kernel(const uint4* __restric
 
 // split fp16 pairs: blend the reconstructed values in fp32, split the result again
 __global__ void bilinear_split_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int H, int W, int C,
-                                      int sp, int slo, int Ho, int Wo, int dp, int dlo) {
+                                      int sp, int slo, int Ho, int Wo, int dp, int dlo, const LoFmt FS, const LoFmt FD) {
   const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
   const long long total = (long long)N * Ho * Wo * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -538,21 +591,25 @@ __global__ void bilinear_split_kernel(const __half* __restrict__ src, __half* __
     const __half* b = src + (long long)n * H * W * sp + c;
     auto val = [&](int y, int x) {
       const __half* q = b + ((long long)y * W + x) * sp;
+      if (FS.f8) return f16f8_load(q - c, slo, c, FS.lo_inv);
       return __half2float(q[0]) + __half2float(q[slo]);
     };
     const float v = hy * (hx * val(y0, x0) + lx * val(y0, x1)) + ly * (hx * val(y1, x0) + lx * val(y1, x1));
-    split_store(dst + (((long long)n * Ho + oy) * Wo + ox) * dp + c, dlo, v);
+    __half* o = dst + (((long long)n * Ho + oy) * Wo + ox) * dp + c;
+    if (FD.f8) f16f8_store(o - c, dlo, c, v, FD.lo_scale, FD.hi8_scale);
+    else split_store(o, dlo, v);
   }
 }
 
 int bilinear_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st) {
   CPN_REQUIRE(op.src.c == op.dst.c, "bilinear: channel mismatch");
-  if (op.src.dtype == CPN_DT_F16X2) {
-    CPN_REQUIRE(op.dst.dtype == CPN_DT_F16X2, "bilinear: split dtype mismatch");
+  if (dtype_has_lo(op.src.dtype)) {
+    CPN_REQUIRE(op.dst.dtype == op.src.dtype, "bilinear: split dtype mismatch");
     const long long tot = (long long)op.dst.n * op.dst.h * op.dst.w * op.dst.c;
     bilinear_split_kernel<<<grid_for(tot, 256), 256, 0, st>>>((const __half*)src, (__half*)dst, op.src.n, op.src.h,
                                                              op.src.w, op.src.c, op.src.pitch, op.src.lo_delta, op.dst.h,
-                                                             op.dst.w, op.dst.pitch, op.dst.lo_delta);
+                                                             op.dst.w, op.dst.pitch, op.dst.lo_delta, lo_fmt(op.src),
+                                                             lo_fmt(op.dst));
     CPN_CHECK_LAUNCH();
     return 0;
   }
@@ -588,7 +645,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) proj_kernel(const T* __restrict__ src, float* __restrict__ dst,
                                                    const float* __restrict__ wgt, const float* __restrict__ bias,
                                                    long long pixels, int sp, int cin_off, int cin, int cout, int dp,
-                                                   int act, float act_scale, int lo_delta) {
+                                                   int act, float act_scale, int lo_delta, int f8, float lo_inv) {
   extern __shared__ float wsm[];  // [cout][cin]
   for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) wsm[i] = wgt[i];
   __syncthreads();
@@ -600,10 +657,17 @@ __global__ void __launch_bounds__(256) proj_kernel(const T* __restrict__ src, fl
     for (int j = 0; j < 32; ++j) acc[j] = 0.f;
     for (int cc = lane * 4; cc < (lo_delta > 0 ? 2 * cin : cin); cc += 128) {
       const int c = cc < cin ? cc : cc - cin;            // split sources: second sweep adds the lo halves
-      Pack4<T> pk;
-      pk.load(sp_ + c + (cc < cin ? 0 : lo_delta));
       float f[4];
-      pk.get(f);
+      if (sizeof(T) == 2 && f8 && cc >= cin) {           // CPN_DT_F16F8: four lo8 bytes of channels cin_off + c ..
+        const uint8_t* q = f8_block(reinterpret_cast<const __half*>(src) + pix * sp, lo_delta, cin_off + c);
+        unpack_e4m3x4(*reinterpret_cast<const uint32_t*>(q), f[0], f[1], f[2], f[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] *= lo_inv;
+      } else {
+        Pack4<T> pk;
+        pk.load(sp_ + c + (cc < cin ? 0 : lo_delta));
+        pk.get(f);
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         if (j < cout) {
@@ -654,12 +718,13 @@ int proj_launch(const cpn_op_t& op, const void* src, void* dst, const float* wgt
   if (op.src.dtype == CPN_DT_F32)
     proj_kernel<float><<<(int)blocks, 256, smem, st>>>((const float*)src, (float*)dst, wgt, bias, pixels, op.src.pitch,
                                                        op.proj_cin_off, op.proj_cin, op.dst.c, op.dst.pitch, op.act,
-                                                       op.act_scale, 0);
+                                                       op.act_scale, 0, 0, 1.f);
   else
     proj_kernel<__half><<<(int)blocks, 256, smem, st>>>((const __half*)src, (float*)dst, wgt, bias, pixels,
                                                         op.src.pitch, op.proj_cin_off, op.proj_cin, op.dst.c,
                                                         op.dst.pitch, op.act, op.act_scale,
-                                                        op.src.dtype == CPN_DT_F16X2 ? op.src.lo_delta : 0);
+                                                        dtype_has_lo(op.src.dtype) ? op.src.lo_delta : 0,
+                                                        op.src.dtype == CPN_DT_F16F8, lo_fmt(op.src).lo_inv);
   CPN_CHECK_LAUNCH();
   return 0;
 }

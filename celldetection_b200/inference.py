@@ -305,6 +305,28 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
     return results
 
 
+def _parse_model_parameters(model_parameters):
+    """``{'nms_thresh': 0.3}`` or the CLI form ``'nms_thresh=0.3,certainty_thresh=None,refinement=False'``
+    (cpn_inference.py:583-590): values of the string form are Python literals (bool / None / numbers), anything that
+    does not parse stays a string."""
+    import ast
+    if isinstance(model_parameters, dict):
+        return [(str(k).strip(), v) for k, v in model_parameters.items()]
+    out = []
+    for kv in str(model_parameters).split(','):
+        if not kv.strip():
+            continue
+        k, sep, v = kv.partition('=')
+        if not sep:
+            raise ValueError(f'model parameter {kv!r} is not of the form key=value')
+        try:
+            val = ast.literal_eval(v.strip())
+        except (ValueError, SyntaxError):
+            val = v.strip()
+        out.append((k.strip(), val))
+    return out
+
+
 def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, border_removal=4, stitching_rule='nms',
                   batch_size=1, devices='auto', precision=None, return_results=True, model_parameters=None,
                   labels=False, flat_labels=False, verbose=False, **kwargs):
@@ -323,14 +345,21 @@ def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, bord
     for i, model in enumerate(models):
         if model.device.type != 'cuda':
             models[i] = model = model.cuda()
-        if precision in ('32-true', 'fp32'):
-            model.precision = 'fp32'
-        elif precision in ('16-mixed', 'fp16', '16-true'):
+        # Lightning precision strings of the reference (cpn_inference.py:446,512): '32-true' is the tensor-core engine
+        # that meets the fp32 results to 1e-3, the 16-bit modes the single-pass fp16 engine
+        if precision in ('32-true', '32', 'fp16f8'):
+            model.precision = 'fp16f8'
+        elif precision in ('16-mixed', 'bf16-mixed', 'fp16', '16-true'):
             model.precision = 'fp16'
+        elif precision in ('fp32', 'fp16x3'):
+            model.precision = precision
+        elif precision is not None:
+            raise ValueError(f'Unknown precision: {precision!r}')
         if model_parameters:
-            for k, v in (model_parameters.items() if isinstance(model_parameters, dict) else
-                         [kv.split('=') for kv in model_parameters.split(',')]):
-                setattr(model, k.strip(), type(getattr(model, k.strip()))(v))
+            for k, v in _parse_model_parameters(model_parameters):
+                if not hasattr(model, k):
+                    raise AttributeError(f'model has no parameter {k!r}')
+                setattr(model, k, v)
     results = OrderedDict()
     for i, img in enumerate(inputs):
         if isinstance(img, str):

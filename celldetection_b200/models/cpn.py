@@ -21,10 +21,11 @@ from torch import Tensor
 from .. import _lib as L
 from ..ops import cpn as O
 from .graph import trace, ARCHS
-from .plan import Plan, WeightPack
+from .plan import Plan, WeightPack, SPLIT_NONE, SPLIT_X3, SPLIT_F8
 
 
-PRECISIONS = ('fp16', 'fp16x3', 'fp32')
+PRECISIONS = ('fp16f8', 'fp16', 'fp16x3', 'fp32')
+_SPLIT = dict(fp16f8=SPLIT_F8, fp16=SPLIT_NONE, fp16x3=SPLIT_X3)
 
 
 class _Node(nn.Module):
@@ -48,7 +49,7 @@ class CPN(nn.Module):
                  score_thresh: float = .9, certainty_thresh: float = None, samples: int = 32, classes: int = 2,
                  refinement: bool = True, refinement_iterations: int = 4, refinement_margin: float = 3.,
                  refinement_buckets: int = 1, uncertainty_head=False, uncertainty_nms=False,
-                 precision: str = 'fp16', **kwargs):
+                 precision: str = 'fp16f8', **kwargs):
         """Contour Proposal Network (inference).
 
         Args:
@@ -56,10 +57,13 @@ class CPN(nn.Module):
                 (the reference takes a backbone *module*; here the backbone is part of the compiled plan).
             order, nms_thresh, score_thresh, samples, classes, refinement, refinement_iterations, refinement_margin,
                 refinement_buckets: as in the reference (models/cpn.py:288-321).
-            precision: ``'fp16'`` -- tcgen05 tensor-core engine, fp16 activations/weights, fp32 accumulation (default);
-                ``'fp16x3'`` -- the same engine with activations and weights split into fp16 (hi, lo) pairs and three
-                tensor-core passes per K block (hi*hi + lo*hi + hi*lo), i.e. fp32-level accuracy at a third of the
-                tensor throughput; ``'fp32'`` -- strict CUDA-core fp32 engine (reference for parity gating).
+            precision: ``'fp16f8'`` (default) -- tcgen05 tensor-core engine that meets the reference's fp32 results to
+                1e-3: fp16 activations / weights plus e4m3 copies of their rounding residuals, one ``kind::f16`` pass and
+                one ``kind::f8f6f4`` correction pass per K block into the same fp32 accumulator (2 pass-equivalents);
+                ``'fp16'`` -- the single-pass engine (fp16 operands, fp32 accumulation): fastest, head tensors only
+                within ~1e-2 of the reference (opt-in); ``'fp16x3'`` -- activations and weights as fp16 (hi, lo) pairs,
+                three fp16 passes (hi*hi + lo*hi + hi*lo): fp32-level accuracy at a third of the tensor throughput;
+                ``'fp32'`` -- strict CUDA-core fp32 engine.
         """
         super().__init__()
         if backbone not in ARCHS:
@@ -166,8 +170,8 @@ class CPN(nn.Module):
         if dev.type != 'cuda':
             raise RuntimeError('celldetection_b200.CPN runs on CUDA (sm_100a) only: move the model with .cuda(). '
                                'There is no CPU fallback.')
-        fast = self.precision in ('fp16', 'fp16x3')
-        split = self.precision == 'fp16x3'
+        fast = self.precision in _SPLIT
+        split = _SPLIT.get(self.precision, SPLIT_NONE)
         key = (n, h, w, self.precision)
         plan = self._plans.get(key)
         if plan is None:

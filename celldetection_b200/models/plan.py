@@ -2,10 +2,14 @@
 convolutions expanded to block-diagonal 64-channel slabs), activation-arena assignment by live ranges, and the
 ``cpn_op_t`` array handed to ``cpn_plan_create``.
 
+Weight packing is host work done once per (model, precision): everything is computed on the CPU and the finished blob
+reaches the device with ONE host-to-device copy (no device kernels at model load).
+
 BatchNorm folding follows SURVEY.md appendix B (eval mode): ``w' = w * gamma / sqrt(var + eps)``,
 ``b' = (b - mean) * gamma / sqrt(var + eps) + beta`` in fp32, then cast.
 """
 import ctypes
+import math
 from collections import OrderedDict
 
 import torch
@@ -15,6 +19,9 @@ from .graph import TT, LOp, Tracer
 
 ALIGN = 256
 BN_EPS = 1e-5
+# activation storage of the tensor-core engines (cpn_b200.h): plain fp16, (hi | lo) fp16 pairs, fp16 + e4m3 corrections
+SPLIT_NONE, SPLIT_X3, SPLIT_F8 = 0, 1, 2
+E4M3_MAX = 448.
 
 
 def _align(v, a=ALIGN):
@@ -72,22 +79,51 @@ def engine_for(op: LOp, fast, cin):
     return L.ENGINE_SIMT
 
 
-class WeightPack:
-    """Device blob with every conv / projection weight of a model in one precision mode.  ``split``: weights of the
-    3-pass engine, ``(W_hi | W_hi | W_lo)`` along K with ``W_hi = fp16(W)``, ``W_lo = fp16(W - W_hi)``."""
+def pack_f16f8(wp, src_exp=0):
+    """Weights of the 2-pass engine (cpn_b200.h, CPN_DT_F16F8).  ``wp``: fp32 ``[taps, cout, kslab]``.  Returns
+    (uint8 ``[taps, cout, 4 * kslab]``, acc_scale): along K first the e4m3 block -- per 32-channel chunk 32 bytes
+    ``e4m3(W_hi * 2^a)`` (pairing with the activations' lo8 bytes) then 32 bytes ``e4m3(W_lo * 2^(a+10))`` (pairing with
+    hi8) -- then ``fp16(S * W_hi)``, with ``W_hi = fp16(W)``, ``W_lo = W - W_hi`` and one power of two ``a`` per layer that
+    puts ``max|W| * 2^a`` in [64, 128).  Both halves of the 8-bit product then carry the scale of the main pass,
+    ``S = 2^(8 + src_exp + a)``, so a single fp32 accumulator holds ``S * (A_hi W_hi + A_lo W_hi + A_hi W_lo)`` and the
+    epilogue multiplies by ``acc_scale = 1 / S``."""
+    taps, cout, kslab = wp.shape
+    assert kslab % 32 == 0
+    amax = float(wp.abs().max())
+    a = (6 - math.floor(math.log2(amax)) if amax > 0 else 0) - max(int(src_exp), 0)
+    a = max(min(a, 40), -40)
+    hi = wp.half()
+    hif = hi.float()
+    lo = wp - hif
+    s_main = 2. ** (8 + src_exp + a)
+    w16 = (hif * s_main).half()
+    assert bool(torch.isfinite(w16.float()).all()), 'fp16 overflow in the scaled main-pass weights'
+    h8 = (hif * 2. ** a).clamp_(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn).view(torch.uint8)
+    l8 = (lo * 2. ** (a + 10)).clamp_(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn).view(torch.uint8)
+    w8 = torch.stack((h8.reshape(taps, cout, kslab // 32, 32), l8.reshape(taps, cout, kslab // 32, 32)), 3)
+    out = torch.cat((w8.reshape(taps, cout, 2 * kslab), w16.view(torch.uint8).reshape(taps, cout, 2 * kslab)), 2)
+    return out.contiguous(), 1. / s_main
 
-    def __init__(self, g: Tracer, sd, fast, device, split=False):
+
+class WeightPack:
+    """Device blob with every conv / projection weight of a model in one precision mode.  ``split``: SPLIT_X3 -- weights
+    of the 3-pass engine, ``(W_hi | W_hi | W_lo)`` along K with ``W_hi = fp16(W)``, ``W_lo = fp16(W - W_hi)``; SPLIT_F8 --
+    weights of the 2-pass engine (``pack_f16f8``).  Packed on the CPU, uploaded with one copy."""
+
+    def __init__(self, g: Tracer, sd, fast, device, split=SPLIT_NONE):
+        split = int(split)
         chunks, off = [], 0
         self.entries = {}
+        self.acc_scale = {}
+        sd = {k: v.detach().to('cpu') for k, v in sd.items()}
         for i, op in enumerate(g.ops):
             if op.kind not in ('conv', 'proj'):
                 continue
             w, b = fold_conv(sd, op.params)
-            w, b = w.to(device), b.to(device)
             if op.kind == 'conv' and op.im2col is not None:   # [cout, cin, k, k] -> [cout, (r*k+s)*cin + c] padded
                 cout_ = w.shape[0]
                 wk = w.permute(0, 2, 3, 1).reshape(cout_, -1)
-                w = torch.zeros(cout_, op.src.c, 1, 1, dtype=w.dtype, device=device)
+                w = torch.zeros(cout_, op.src.c, 1, 1, dtype=w.dtype)
                 w[:, :wk.shape[1], 0, 0] = wk
             if op.kind == 'proj':
                 wp = w.reshape(w.shape[0], w.shape[1]).contiguous().float()
@@ -102,11 +138,12 @@ class WeightPack:
                 cout, kslab, kh, kw = w.shape
                 if eng == L.ENGINE_TCGEN05:   # [R*S][cout][kslab] fp16
                     wp = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, kslab).contiguous()
-                    if split:
-                        assert eng == L.ENGINE_TCGEN05
+                    if split == SPLIT_X3:
                         hi = wp.half()
                         lo = (wp - hi.float()).half()
                         wp = torch.cat((hi, hi, lo), 2).contiguous()
+                    elif split == SPLIT_F8:
+                        wp, self.acc_scale[i] = pack_f16f8(wp)
                     else:
                         wp = wp.half()
                 else:                          # [R*S][kslab][cout] fp32
@@ -120,21 +157,25 @@ class WeightPack:
             chunks.append((w_off, wb))
             chunks.append((b_off, bb))
             self.entries[i] = (w_off, b_off, eng)
-        self.blob = torch.zeros(max(off, ALIGN), dtype=torch.uint8, device=device)
+        host = torch.zeros(max(off, ALIGN), dtype=torch.uint8)
         for o, c in chunks:
-            self.blob[o:o + c.numel()] = c
+            host[o:o + c.numel()] = c
+        self.blob = host.to(device)          # the one host-to-device copy of the model's weights
         self.bytes = off
 
 
-def _pitch(c, split=False):
-    """Physical pixel pitch (elements) of a root buffer with c logical channels; split buffers hold (hi | lo) halves."""
+def _pitch(c, split=SPLIT_NONE):
+    """Physical pixel pitch (elements) of a root buffer with c logical channels; split buffers hold (hi | lo) halves,
+    fp16+e4m3 buffers (hi | 8-bit chunks of 32 channels)."""
     p = c if c % 4 == 0 else _align(c, 4)
-    if split:
+    if split == SPLIT_X3:
         p = 2 * (p if p % 8 == 0 else _align(p, 8))
+    elif split == SPLIT_F8:
+        p = 2 * _align(p, 32)
     return p
 
 
-def assign_arena(g: Tracer, elem_size, split=False):
+def assign_arena(g: Tracer, elem_size, split=SPLIT_NONE):
     """First-fit placement of root buffers by live range.  Returns ({tensor id: byte offset of its root}, bytes)."""
     roots = []
     for t in g.tensors:
@@ -160,7 +201,8 @@ def assign_arena(g: Tracer, elem_size, split=False):
 
 def _view(t: TT, n, root_off, elem_size, dtype):
     r, coff = t.root()
-    split = dtype == L.DT_F16X2
+    split = {L.DT_F16X2: SPLIT_X3, L.DT_F16F8: SPLIT_F8}.get(dtype, SPLIT_NONE)
+    assert split != SPLIT_F8 or coff % 32 == 0, 'fp16+e4m3 channel slices must start at multiples of 32'
     pitch = _pitch(r.c, split)
     v = L.View()
     v.offset = root_off.get(r.id, 0) + coff * elem_size
@@ -172,10 +214,12 @@ def _view(t: TT, n, root_off, elem_size, dtype):
 class Plan:
     """A compiled (architecture, N, H, W, precision) instance: C plan + arena + output buffers."""
 
-    def __init__(self, g: Tracer, pack: WeightPack, fast, device, split=False):
+    def __init__(self, g: Tracer, pack: WeightPack, fast, device, split=SPLIT_NONE):
         lib = L.load()
+        split = int(split)
         self.g, self.pack, self.fast, self.device, self.split = g, pack, fast, device, split
-        act_dt, es = ((L.DT_F16X2 if split else L.DT_F16), 2) if fast else (L.DT_F32, 4)
+        act_dt, es = ({SPLIT_NONE: L.DT_F16, SPLIT_X3: L.DT_F16X2, SPLIT_F8: L.DT_F16F8}[split], 2) if fast \
+            else (L.DT_F32, 4)
         offsets, arena_bytes = assign_arena(g, es, split)
         self.arena = torch.empty(max(arena_bytes, ALIGN), dtype=torch.uint8, device=device)
         self.flags = torch.zeros(4, dtype=torch.int32, device=device)
@@ -215,6 +259,7 @@ class Plan:
                 o.w_offset, o.b_offset = w_off, b_off
                 if lop.kind == 'conv':
                     o.engine = eng
+                    o.acc_scale = pack.acc_scale.get(i, 1.)
                     o.kslab, o.slab_mode = slab_of(lop.src.c, lop.dst.c, lop.params.groups)
                     self.engines.append(eng)
                 else:
@@ -281,8 +326,12 @@ class Plan:
         base = offsets[r.id]
         buf = self.arena[base:base + nbytes].view(dt).reshape(self.g.n, t.h, t.w, pitch)
         out = buf[..., coff:coff + t.c].float()
-        if self.split:
+        if self.split == SPLIT_X3:
             out = out + buf[..., pitch // 2 + coff:pitch // 2 + coff + t.c].float()
+        elif self.split == SPLIT_F8:     # 8-bit block: per 32-channel chunk 32 lo8 bytes then 32 hi8 bytes
+            b8 = buf[..., pitch // 2:].contiguous().view(torch.uint8).reshape(self.g.n, t.h, t.w, -1, 2, 32)
+            lo8 = b8[..., 0, :].reshape(self.g.n, t.h, t.w, -1)[..., coff:coff + t.c]
+            out = out + lo8.contiguous().view(torch.float8_e4m3fn).float() * 2. ** -8
         return out.permute(0, 3, 1, 2).contiguous()
 
     def __del__(self):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CPN_B200_ABI_VERSION 3
+#define CPN_B200_ABI_VERSION 4
 
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* status / diagnostics                                                                                             */
@@ -44,9 +44,17 @@ enum {
   CPN_DT_F32 = 0,
   CPN_DT_F16 = 1,
   CPN_DT_U8 = 2,
-  CPN_DT_F16X2 = 3 /* split fp16 pair: value = hi + lo, hi = fp16(v), lo = fp16(v - hi); channel c of a view lives at
+  CPN_DT_F16X2 = 3, /* split fp16 pair: value = hi + lo, hi = fp16(v), lo = fp16(v - hi); channel c of a view lives at
                       element c (hi) and c + lo_delta (lo) of the pixel.  Used by the 3-pass tensor-core engine
                       (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate) that reaches fp32-level accuracy. */
+  CPN_DT_F16F8 = 4 /* fp16 value + two e4m3 correction operands (the 2-pass tensor-core engine: one kind::f16 pass
+                      A_hi*W_hi and ONE kind::f8f6f4 pass over the K-concatenated (A_lo | A_hi) x (W_hi ; W_lo) e4m3
+                      operands, both into the same fp32 accumulator).  Channel c of a view lives at element c (hi =
+                      fp16(v)); the pixel's 8-bit block starts lo_delta elements after the view's first element and
+                      holds, per 32-channel chunk j, 64 bytes: 32 x e4m3((v - hi) * 2^(8+fp8_exp)) followed by
+                      32 x e4m3(hi * 2^(-2+fp8_exp)) (round to nearest even, saturating at +-448), so a 64-channel
+                      K block is one 128-byte row for either instruction kind.  Channel offsets of views must be
+                      multiples of 32.  Same 4 bytes per element as CPN_DT_F16X2. */
 };
 
 /* NHWC view into the activation arena: element (n,y,x,c) lives at
@@ -58,8 +66,10 @@ typedef struct {
   int32_t n, h, w, c;
   int32_t pitch;
   int32_t dtype;  /* CPN_DT_* */
-  int32_t lo_delta; /* CPN_DT_F16X2: elements from a channel's hi half to its lo half (0 otherwise) */
-  int32_t reserved;
+  int32_t lo_delta; /* CPN_DT_F16X2: elements from a channel's hi half to its lo half; CPN_DT_F16F8: elements from the
+                       view's first hi element to its 8-bit block (0 otherwise) */
+  int32_t fp8_exp;  /* CPN_DT_F16F8: power-of-two exponent of the tensor's 8-bit operand scales (0 suits O(1e-3..1e3)
+                       activations); all views of one buffer carry the same value */
 } cpn_view_t;
 
 enum {
@@ -90,7 +100,10 @@ typedef struct {
   int64_t w_offset;      /* CONV/PROJ: bytes into the weight blob.
                             SIMT   : float  [R*S][kslab][cout]
                             TCGEN05: __half [R*S][cout][kslab]   (K-major, TMA box {64, BN, 1}); for CPN_DT_F16X2
-                                     activations [R*S][cout][3*kslab] = (W_hi | W_hi | W_lo) along K
+                                     activations [R*S][cout][3*kslab] = (W_hi | W_hi | W_lo) along K; for CPN_DT_F16F8
+                                     [R*S][cout][2*kslab] half slots = (W8 | fp16(S * W_hi)) along K, W8 holding per
+                                     32-channel chunk 32 x e4m3(W_hi * 2^a) then 32 x e4m3(W_lo * 2^(a+10)) (pairing
+                                     with the activations' (lo | hi) bytes), S = 2^(8 + src.fp8_exp + a) = 1/acc_scale
                             PROJ   : float  [cout][cin_slice]    */
   int64_t b_offset;      /* CONV/PROJ: bytes into the weight blob of float bias[cout] (-1 -> no bias) */
   int32_t r, s, stride, pad;
@@ -105,6 +118,9 @@ typedef struct {
   int32_t fuse_next;     /* CONV (TCGEN05): number of immediately following PROJ ops computed inside this
                             convolution's epilogue (one per output-channel tile, in tile order); they are skipped by
                             cpn_plan_forward and the convolution's own dst is then not written */
+  float acc_scale;       /* CONV (TCGEN05): the fp32 accumulator is multiplied by this before bias / residual / activation
+                            (1/S of the CPN_DT_F16F8 weight packing; 0 is read as 1) */
+  int32_t reserved;
 } cpn_op_t;
 
 typedef struct cpn_plan cpn_plan_t;

@@ -36,7 +36,7 @@ CASES = [
 def run(engine, idx):
     cin, cout, k, stride, groups, n, h, w, res, relu, bias = CASES[idx]
     g = torch.Generator().manual_seed(idx)
-    half = engine not in ('simt32', 'tcgen05x3')
+    half = engine not in ('simt32', 'tcgen05x3', 'tcgen05f8')
     x = torch.randn(n, cin, h, w, generator=g)
     wt = torch.randn(cout, cin // groups, k, k, generator=g) * (2. / (cin // groups * k * k)) ** .5
     b = torch.randn(cout, generator=g) * 0.1 if bias else None
@@ -56,7 +56,7 @@ def run(engine, idx):
         ref = ref + rr
     if relu:
         ref = F.relu(ref)
-    eng = engine if engine in ('tcgen05', 'tcgen05x3') else 'simt'
+    eng = engine if engine in ('tcgen05', 'tcgen05x3', 'tcgen05f8') else 'simt'
     out = conv2d(x.cuda(), wt.cuda(), None if b is None else b.cuda(), stride=stride, padding=pad, groups=groups,
                  residual=None if r is None else r.cuda(), relu=relu, engine=eng, half=half)
     torch.cuda.synchronize()

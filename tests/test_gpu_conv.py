@@ -50,3 +50,13 @@ def test_conv_tcgen05_split_fp16x3_matches_fp32():
         cin, cout, k, stride, groups = r['shape'][:5]
         kk = (cin // groups) * k * k if groups == 1 else 64 * k * k
         assert r['rel_err'] < max(5e-6, 1e-8 * kk) and not r['nan'], r
+
+
+@pytest.mark.gpu
+def test_conv_tcgen05_fp16_plus_e4m3_corrections_matches_fp32():
+    """Two-pass engine (one kind::f16 pass + one kind::f8f6f4 correction pass over the e4m3 residual operands, same fp32
+    accumulator) on unrounded fp32 operands.  The corrections carry 4 significant bits, so the operand error falls from
+    2^-11 (single-pass fp16, ~3e-4 per layer) to ~2^-15 per element; what remains averages over K."""
+    for r in _run('tcgen05f8', TC_CASES):
+        assert 'error' not in r, r
+        assert r['rel_err'] < 6e-5 and not r['nan'], r

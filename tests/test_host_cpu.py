@@ -69,7 +69,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     import ctypes
     assert ctypes.sizeof(_lib.View) == 40
-    assert ctypes.sizeof(_lib.Op) == 8 + 3 * 40 + 16 + 4 * 4 + 8 * 4
+    assert ctypes.sizeof(_lib.Op) == 8 + 3 * 40 + 16 + 4 * 4 + 8 * 4 + 8
 
 
 def test_no_cpu_fallback():
@@ -279,3 +279,36 @@ def test_every_architecture_is_tensor_core_eligible():
         for op in g.ops:
             if op.kind == 'conv':
                 assert PL.engine_for(op, True, op.src.c) == _lib.ENGINE_TCGEN05, (arch, op.name)
+
+
+def test_f16f8_packing_reproduces_fp32_products():
+    """CPU emulation of the 2-pass engine's arithmetic from the PACKED operands (celldetection_b200.models.plan.pack_f16f8
+    for the weights, ops.conv._f16f8_nhwc for the activations, i.e. the byte layouts of cpn_b200.h CPN_DT_F16F8):
+    acc = A_hi x fp16(S W_hi) + (lo8 | hi8) x (W_hi8 ; W_lo8), out = acc * acc_scale.  Checks the chunk pairing and that
+    both halves of the 8-bit product carry the main pass's scale; the result must sit ~2^4 closer to the fp32 product
+    than single-pass fp16."""
+    from celldetection_b200.models.plan import pack_f16f8
+    from celldetection_b200.ops.conv import _f16f8_nhwc
+    g = torch.Generator().manual_seed(0)
+    for amp in (0.02, 1.0, 37.):
+        k, cout, npx = 128, 64, 50
+        w = torch.randn(1, cout, k, generator=g) * amp
+        x = torch.randn(npx, k, 1, 1, generator=g) * 3.
+        blob, acc_scale = pack_f16f8(w)
+        w8 = blob[0, :, :2 * k].reshape(cout, k // 32, 2, 32)
+        wh8 = w8[:, :, 0].reshape(cout, k).contiguous().view(torch.float8_e4m3fn).double()
+        wl8 = w8[:, :, 1].reshape(cout, k).contiguous().view(torch.float8_e4m3fn).double()
+        w16 = blob[0, :, 2 * k:].contiguous().view(torch.float16).double()
+        px = _f16f8_nhwc(x, k)[:, 0, 0]                       # [npx, 2k] fp16-typed
+        a_hi = px[:, :k].double()
+        a8 = px[:, k:].contiguous().view(torch.uint8).reshape(npx, k // 32, 2, 32)
+        a_lo8 = a8[:, :, 0].reshape(npx, k).contiguous().view(torch.float8_e4m3fn).double()
+        a_hi8 = a8[:, :, 1].reshape(npx, k).contiguous().view(torch.float8_e4m3fn).double()
+        acc = a_hi @ w16.T + a_lo8 @ wh8.T + a_hi8 @ wl8.T
+        got = acc * acc_scale
+        want = x[:, :, 0, 0].double() @ w[0].double().T
+        single = x[:, :, 0, 0].half().double() @ w[0].half().double().T
+        e2 = float((got - want).abs().max() / want.abs().max())
+        e1 = float((single - want).abs().max() / want.abs().max())
+        assert e2 < 3e-5 and e2 < e1 / 8, (amp, e1, e2)
+        assert float(w16.abs().max()) < 65504 and float(wh8.abs().max()) <= 448
