@@ -65,7 +65,8 @@ def pack_records(res: OrderedDict):
     """Flat per-detection float32 records [K, L] of every key of ``res`` (classes are stored as float; exact for
     small ints).  Returns (records, [(key, width), ...])."""
     K = int(res['scores'].shape[0])
-    cols = [(k, v.reshape(K, -1).float()) for k, v in res.items()]
+    # explicit widths: reshape(K, -1) cannot infer a width for K == 0 (a rank without detections)
+    cols = [(k, v.reshape(K, int(np.prod(v.shape[1:], dtype=np.int64))).float()) for k, v in res.items()]
     return torch.cat([c for _, c in cols], 1).contiguous(), [(k, c.shape[1]) for k, c in cols]
 
 
@@ -89,23 +90,23 @@ def canonical_order(res: OrderedDict):
 
 
 def allgather_detections(res: OrderedDict, group=None):
-    """One collective for all keys: all_gather of per-rank counts (world ints) + ONE all_gather of the packed,
-    max-count-padded record buffer; returns the concatenation in rank order on every rank."""
+    """One collective for all keys: all_gather of the per-rank counts (one small tensor, ONE host read-back for all
+    ranks) + ONE all_gather of the packed, max-count-padded record buffer; returns the concatenation in rank order on
+    every rank.  Ranks without detections take part with a zero count."""
     dist, rank, world = _dist()
     if dist is None or world == 1:
         return res
     rec, widths = pack_records(res)
     dev = rec.device
-    cnt = torch.tensor([rec.shape[0]], dtype=torch.int64, device=dev)
-    cnts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(cnts, cnt, group=group)
-    counts = [int(c.item()) for c in cnts]
+    cnts = torch.zeros((world,), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(cnts, torch.tensor([rec.shape[0]], dtype=torch.int64, device=dev), group=group)
+    counts = cnts.tolist()                               # the exchange's only host synchronisation
     mx = max(max(counts), 1)
     padded = torch.zeros((mx, rec.shape[1]), dtype=torch.float32, device=dev)
     padded[:rec.shape[0]] = rec
-    gathered = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(gathered, padded, group=group)     # the one payload collective (NCCL over NVLink on the GPU box)
-    parts = [gathered[r][:counts[r]] for r in range(world)]
+    gathered = torch.empty((world * mx, rec.shape[1]), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(gathered, padded, group=group)   # the one payload collective (NCCL over NVLink)
+    parts = [gathered[r * mx:r * mx + counts[r]] for r in range(world)]
     return unpack_records(torch.cat(parts, 0), widths, res)
 
 
@@ -137,10 +138,14 @@ def _tile_bounds(mask, point_mask, point_mask_exclusive, sl):
 
 
 def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size, strides, batch_size, border_removal,
-                  rules, stitching_rule, nms_thresh, dev):
+                  rules, stitching_rule, nms_thresh, dev, timings=None):
     """One model over all tiles of ``img`` (this rank's share), border removal, exchange, stitch NMS
-    (cpn_inference.py:354-411)."""
-    H, W = img.shape[:2]
+    (cpn_inference.py:354-411).  ``img``: ``Array[h, w, c]`` on the host (crops are staged through double-buffered pinned
+    memory by a helper thread) or a uint8 / float32 CUDA tensor ``[h, w, c]`` already resident on ``dev`` (crops are device
+    slices).  The per-tile border test only marks rows; compaction, the order keys and the exchange run ONCE after the
+    last batch, so the tile loop has no host synchronisation besides the model's own."""
+    on_device = isinstance(img, torch.Tensor)
+    H, W = int(img.shape[0]), int(img.shape[1])
     slices, overlaps, (h_tiles, w_tiles) = get_tiling_slices((H, W), tuple(crop_size), tuple(strides),
                                                              return_overlaps=True)
     slices, overlaps = list(slices), list(overlaps)
@@ -157,80 +162,91 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
                 todo.append(t)
     mine = todo[rank::world]
     th, tw = (slices[0][0].stop - slices[0][0].start), (slices[0][1].stop - slices[0][1].start)
-    is_u8 = img.dtype == np.uint8
-    C = img.shape[-1]
-    # double-buffered pinned staging
-    stage = [torch.empty((batch_size, th, tw, C), dtype=torch.uint8 if is_u8 else torch.float32).pin_memory()
-             for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    is_u8 = img.dtype in (np.uint8, torch.uint8)
+    C = int(img.shape[-1])
+    lib = L.load()
     main = torch.cuda.current_stream(dev)
-    acc = []
-
-    def load(bi, slot):
-        ids = mine[bi * batch_size:(bi + 1) * batch_size]
-        buf = stage[slot]
-        for j, t in enumerate(ids):
-            buf[j].copy_(torch.from_numpy(np.ascontiguousarray(img[slices[t]])))
-        with torch.cuda.stream(copy_stream):
-            d = buf[:len(ids)].to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return ids, d, ev
-
-    # Crops are staged by a helper thread (numpy slicing + the pinned copy release the GIL) while the main thread drives
-    # the GPU: model calls block on the proposal count, so same-thread staging would serialise with the GPU.
-    from concurrent.futures import ThreadPoolExecutor
     nb = (len(mine) + batch_size - 1) // batch_size
-    pool = ThreadPoolExecutor(max_workers=1)
-    cur_dev = torch.cuda.current_device()
+    acc = []          # per batch: (flat dict, keep mask [K] uint8, tile id of each row [K] float, K)
+    pool = None
+    t_start = _now(dev, timings)
 
-    def load_in_thread(bi, slot):
-        torch.cuda.set_device(cur_dev)
-        return load(bi, slot)
+    if not on_device:
+        # double-buffered pinned staging; crops are staged by a helper thread (numpy slicing + the pinned copy release
+        # the GIL) while the main thread drives the GPU: model calls block on the proposal count, so same-thread staging
+        # would serialise with the GPU
+        stage = [torch.empty((batch_size, th, tw, C), dtype=torch.uint8 if is_u8 else torch.float32).pin_memory()
+                 for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        cur_dev = torch.cuda.current_device()
 
-    nxt = pool.submit(load_in_thread, 0, 0) if nb else None
-    for bi in range(nb):
-        ids, d, ev = nxt.result()
-        main.wait_event(ev)
-        if bi + 1 < nb:
-            # the other staging slot was consumed two batches ago (its copy finished before the previous forward)
-            nxt = pool.submit(load_in_thread, bi + 1, (bi + 1) % 2)
-        offs = torch.tensor([[slices[t][1].start, slices[t][0].start] for t in ids], dtype=torch.float32, device=dev)
-        kw = dict(offsets=offs)
-        if bounds:       # [B,1,th,tw] score bounds at input resolution (resized by the model, cpn.py:118-123)
-            for j, name in ((0, 'scores_upper_bound'), (1, 'scores_lower_bound')):
-                if bounds[ids[0]][j] is not None:
-                    b_np = np.stack([bounds[t][j][..., 0] for t in ids], 0)[:, None]
-                    kw[name] = torch.from_numpy(np.ascontiguousarray(b_np)).to(dev)
-        if is_u8:
-            flat, counts = model.forward_flat(d, L.IN_U8_NHWC, **kw)
-        else:
-            flat, counts = model.forward_flat(d.permute(0, 3, 1, 2).contiguous(), L.IN_F32_NCHW, **kw)
-        K = int(sum(counts))
-        if K == 0:
-            continue
-        meta = []
-        for t in ids:
-            h_i, w_i = np.unravel_index(t, (h_tiles, w_tiles))
-            (_, ov_y1), (_, ov_x1) = overlaps[t]      # right/bottom overlaps (cpn_inference.py:382-385)
-            meta.append([slices[t][1].start, slices[t][0].start, th, tw, float(h_i > 0), float(w_i < w_tiles - 1),
-                         float(h_i < h_tiles - 1), float(w_i > 0), ex_br, float(tw - ov_x1), float(th - ov_y1), 0.])
-        meta = torch.tensor(meta, dtype=torch.float32, device=dev)
-        tile_of_row = torch.repeat_interleave(torch.arange(len(ids), dtype=torch.int32, device=dev),
-                                              torch.tensor(counts, device=dev))
-        keep = torch.empty((K,), dtype=torch.uint8, device=dev)
-        lib = L.load()
-        L.check(lib.cpn_border_filter(L.ptr(flat['contours']), L.ptr(tile_of_row), L.ptr(meta), K,
-                                      int(flat['contours'].shape[1]), float(border_removal), L.ptr(keep),
-                                      L.stream_ptr()), 'border_filter')
-        sel = torch.nonzero(keep, as_tuple=False).reshape(-1)
-        part = OrderedDict((k, v[sel]) for k, v in flat.items())
-        tile_ids = torch.tensor(ids, dtype=torch.float32, device=dev)[tile_of_row.long()][sel]
-        part['order_key'] = torch.stack((tile_ids, sel.to(torch.float32)), 1)   # (global tile index, row in batch)
-        acc.append(part)
-    pool.shutdown(wait=True)
+        def load(bi, slot):
+            torch.cuda.set_device(cur_dev)
+            ids = mine[bi * batch_size:(bi + 1) * batch_size]
+            buf = stage[slot]
+            for j, t in enumerate(ids):
+                buf[j].copy_(torch.from_numpy(np.ascontiguousarray(img[slices[t]])))
+            with torch.cuda.stream(copy_stream):
+                d = buf[:len(ids)].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return ids, d, ev
+
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=1)
+    try:
+        nxt = pool.submit(load, 0, 0) if (pool is not None and nb) else None
+        for bi in range(nb):
+            if on_device:
+                ids = mine[bi * batch_size:(bi + 1) * batch_size]
+                d = torch.stack([img[slices[t]] for t in ids], 0)
+            else:
+                ids, d, ev = nxt.result()
+                main.wait_event(ev)
+                d.record_stream(main)        # allocated on the copy stream, consumed on the main stream
+                if bi + 1 < nb:
+                    # the other staging slot was consumed two batches ago (its copy finished before the previous forward)
+                    nxt = pool.submit(load, bi + 1, (bi + 1) % 2)
+            offs = torch.tensor([[slices[t][1].start, slices[t][0].start] for t in ids], dtype=torch.float32).to(
+                dev, non_blocking=True)
+            kw = dict(offsets=offs)
+            if bounds:       # [B,1,th,tw] score bounds at input resolution (resized by the model, cpn.py:118-123)
+                for j, name in ((0, 'scores_upper_bound'), (1, 'scores_lower_bound')):
+                    if bounds[ids[0]][j] is not None:
+                        b_np = np.stack([bounds[t][j][..., 0] for t in ids], 0)[:, None]
+                        kw[name] = torch.from_numpy(np.ascontiguousarray(b_np)).to(dev)
+            if is_u8:
+                flat, counts = model.forward_flat(d, L.IN_U8_NHWC, **kw)
+            else:
+                flat, counts = model.forward_flat(d.permute(0, 3, 1, 2).contiguous(), L.IN_F32_NCHW, **kw)
+            K = int(sum(counts))
+            if K == 0:
+                continue
+            meta = []
+            for t in ids:
+                h_i, w_i = np.unravel_index(t, (h_tiles, w_tiles))
+                (_, ov_y1), (_, ov_x1) = overlaps[t]      # right/bottom overlaps (cpn_inference.py:382-385)
+                meta.append([slices[t][1].start, slices[t][0].start, th, tw, float(h_i > 0), float(w_i < w_tiles - 1),
+                             float(h_i < h_tiles - 1), float(w_i > 0), ex_br, float(tw - ov_x1), float(th - ov_y1), 0.])
+            meta = torch.tensor(meta, dtype=torch.float32).to(dev, non_blocking=True)
+            tile_of_row = torch.repeat_interleave(torch.arange(len(ids), dtype=torch.int32),
+                                                  torch.tensor(counts)).to(dev, non_blocking=True)
+            keep = torch.empty((K,), dtype=torch.uint8, device=dev)
+            L.check(lib.cpn_border_filter(L.ptr(flat['contours']), L.ptr(tile_of_row), L.ptr(meta), K,
+                                          int(flat['contours'].shape[1]), float(border_removal), L.ptr(keep),
+                                          L.stream_ptr()), 'border_filter')
+            tile_ids = torch.repeat_interleave(torch.tensor(ids, dtype=torch.float32), torch.tensor(counts))
+            rows = torch.arange(K, dtype=torch.float32)
+            acc.append((flat, keep, torch.stack((tile_ids, rows), 1).to(dev, non_blocking=True)))
+    finally:
+        if pool is not None:
+            pool.shutdown(wait=True)
+    t_tiles = _now(dev, timings)
     if acc:
-        res = OrderedDict((k, torch.cat([a[k] for a in acc], 0)) for k in acc[0].keys())
+        keep_all = torch.cat([a[1] for a in acc], 0)
+        sel = torch.nonzero(keep_all, as_tuple=False).reshape(-1)          # the one compaction of this rank's detections
+        res = OrderedDict((k, torch.cat([a[0][k] for a in acc], 0)[sel]) for k in acc[0][0].keys())
+        res['order_key'] = torch.cat([a[2] for a in acc], 0)[sel]          # (global tile index, row in batch)
     else:
         S, order = int(model.samples), int(min(model.order, model.core_order))
         z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
@@ -243,24 +259,40 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
     if world > 1:
         res = canonical_order(res)      # 1-GPU and N-GPU runs feed the global NMS the same sequence
     res.pop('order_key')
+    t_gather = _now(dev, timings)
     if 'nms' in rules and res['boxes'].shape[0] > 0:
         keep = O.nms(res['boxes'], res['scores'], nms_thresh)
         res = OrderedDict((k, v[keep]) for k, v in res.items())
+    if timings is not None:
+        t_end = _now(dev, timings)
+        timings.update(tiles_s=t_tiles - t_start, exchange_s=t_gather - t_tiles, stitch_s=t_end - t_gather,
+                       tiles_mine=len(mine), tiles_total=len(slices))
     return res
+
+
+def _now(dev, timings):
+    """Device-synchronised wall clock for the optional stage breakdown (no synchronisation unless timings are asked)."""
+    if timings is None:
+        return 0.
+    import time
+    torch.cuda.synchronize(dev)
+    return time.perf_counter()
 
 
 @torch.no_grad()
 def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size=(768, 768), strides=(384, 384),
                 reps=1, transforms=None, model_kwargs_list=None, batch_size=1, num_workers=0, pin_memory=False,
                 border_removal=4, min_vote=1, stitching_rule='nms', point_mask_exclusive=False, verbose=False,
-                device=None, **kwargs):
+                device=None, timings=None, **kwargs):
     """cpn_inference.py:311-429.  ``img``: uint8 or float ``Array[h, w, (c)]``; ``models``: a ``CPN`` instance or a
     list of them (an ensemble: every model is run over all tiles, the concatenated detections are filtered by
     ``filter_by_box_voting(boxes, nms_thresh, min_vote)`` when ``min_vote > 1`` and de-duplicated by one more NMS,
     :417-427).  ``mask`` / ``point_mask``: ``Array[h, w]`` upper / lower score bounds; tiles whose crop is empty are
     skipped (TileLoader, :93-111).  Returns the flat dict of concatenated tensors (contours, boxes, scores, classes,
     locations, fourier, contour_proposals[, box_uncertainties][, votes]) after border removal and global NMS --
-    identical on every rank when distributed."""
+    identical on every rank when distributed.  ``img`` may also be a ``[h, w, c]`` uint8 / float32 CUDA tensor (the slide
+    already resident in HBM).  ``timings``: optional dict that receives a device-synchronised stage breakdown (tile loop,
+    exchange, stitch) of the last model."""
     if not isinstance(models, (list, tuple)):
         models = [models]
     assert len(models) >= 1, 'Please specify at least one model.'
@@ -278,18 +310,24 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
         crop_size = (crop_size,) * 2
     if not isinstance(strides, (tuple, list)):
         strides = (strides,) * 2
-    img = _to_rgb(np.asarray(img))
-    if img.dtype.kind == 'f':
-        img = img.astype(np.float32)
-    elif img.dtype != np.uint8:
-        raise ValueError('image must be uint8 or floating point')
+    if isinstance(img, torch.Tensor) and img.is_cuda:       # slide already resident in HBM: [h, w, c] uint8 / float32
+        if img.dim() != 3 or img.dtype not in (torch.uint8, torch.float32) or img.device != dev:
+            raise ValueError('a device-resident image must be a [h, w, c] uint8 or float32 tensor on the model device')
+        if img.shape[-1] == 1:
+            img = img.expand(-1, -1, 3)
+    else:
+        img = _to_rgb(np.asarray(img))
+        if img.dtype.kind == 'f':
+            img = img.astype(np.float32)
+        elif img.dtype != np.uint8:
+            raise ValueError('image must be uint8 or floating point')
     mask = None if mask is None else np.asarray(mask)
     point_mask = None if point_mask is None else np.asarray(point_mask)
     results, nms_thresh = None, None
     for model in models:
         nms_thresh = kwargs.get('nms_thresh', model.nms_thresh)
         res = _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size, strides, batch_size,
-                            border_removal, rules, stitching_rule, nms_thresh, dev)
+                            border_removal, rules, stitching_rule, nms_thresh, dev, timings=timings)
         if results is None:
             results = res
         else:                      # keys shared by all models (an uncertainty head may be missing in some)

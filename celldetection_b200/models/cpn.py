@@ -20,7 +20,7 @@ from torch import Tensor
 
 from .. import _lib as L
 from ..ops import cpn as O
-from .graph import trace, ARCHS
+from .graph import trace, ARCHS, HEAD_KERNEL_KEYS
 from .plan import Plan, WeightPack, SPLIT_NONE, SPLIT_X3, SPLIT_F8
 
 
@@ -44,11 +44,33 @@ def _get_node(root: nn.Module, path):
     return m
 
 
+# Constructor options of the reference (models/cpn.py:288-321, CPNCore :126-149) that do not change the inference
+# arithmetic when left at these values; any other value is rejected (never silently ignored).
+_NOOP_DEFAULTS = dict(contour_features='1', location_features='1', uncertainty_features='1', score_features='1',
+                      refinement_features='0', order_weights=True, refinement_interpolation='bilinear',
+                      head_activation='relu', head_activation_score='relu', head_activation_location='relu',
+                      head_activation_fourier='relu', head_activation_uncertainty='relu',
+                      head_activation_refinement='relu', fuse_kwargs={}, encoder_channels=None, pretrained=False,
+                      encoder_prefix='encoder.')
+_TRAINING_ONLY = ('uncertainty_factor', 'score_target_dtype')          # used by compute_loss only
+# backbone_kwargs of the ResNet U-Net / FPN backbones (unet.py:251-272, fpn.py:137-170) that are the identity here
+_BACKBONE_NOOPS = dict(pretrained=False, normalize=True, inputs_mean=0., inputs_std=1., assert_range=(0., 1.),
+                       interpolate='nearest', nd=2, block=None, block_kwargs=None, final_activation=None)
+
+
+def _same(a, b):
+    if isinstance(a, (list, tuple)) or isinstance(b, (list, tuple)):
+        return a is not None and b is not None and list(a) == list(b)
+    return a == b or (a is None and b in (False, {}, None)) or (b is None and a in (False, {}, None))
+
+
 class CPN(nn.Module):
     def __init__(self, backbone: str, in_channels: int = 3, order: int = 5, nms_thresh: float = .2,
                  score_thresh: float = .9, certainty_thresh: float = None, samples: int = 32, classes: int = 2,
                  refinement: bool = True, refinement_iterations: int = 4, refinement_margin: float = 3.,
                  refinement_buckets: int = 1, uncertainty_head=False, uncertainty_nms=False,
+                 contour_head_channels: int = None, contour_head_stride: int = 1, refinement_head_channels: int = None,
+                 refinement_head_stride: int = 1, refinement_full_res: bool = True, backbone_kwargs: dict = None,
                  precision: str = 'fp16f8', **kwargs):
         """Contour Proposal Network (inference).
 
@@ -74,6 +96,32 @@ class CPN(nn.Module):
             raise ValueError('refinement_buckets must be in [1, 12]')
         if precision not in PRECISIONS:
             raise ValueError(f'precision must be one of {PRECISIONS}')
+        # ---- shape-changing head options (models/cpn.py:177-234): honoured; everything else must be a no-op ----
+        extra = dict(kwargs)
+        self.kernel_sizes = {k: int(kwargs.pop(f'kernel_size_{k}', 7)) for k in HEAD_KERNEL_KEYS}
+        for k in _TRAINING_ONLY:
+            kwargs.pop(k, None)
+        for k, dflt in _NOOP_DEFAULTS.items():
+            if k in kwargs and not _same(kwargs[k], dflt):
+                raise NotImplementedError(f'{k}={kwargs[k]!r} is outside the accelerated path (only {dflt!r} is supported)')
+            kwargs.pop(k, None)
+        if kwargs:
+            raise TypeError(f'unsupported CPN options: {sorted(kwargs)} (they would change the network and are not '
+                            f'implemented here)')
+        bkw = dict(backbone_kwargs or {})
+        self.fpn_channels = int(bkw.pop('fpn_channels', 256))
+        if self.fpn_channels != 256 and not backbone.endswith('FPN'):
+            raise ValueError('fpn_channels applies to the FPN backbones only')
+        for k, v in bkw.items():
+            if k not in _BACKBONE_NOOPS or not _same(v, _BACKBONE_NOOPS[k]):
+                raise NotImplementedError(f'backbone_kwargs[{k!r}]={v!r} is outside the accelerated path')
+        for nm, v in (('contour_head_stride', contour_head_stride), ('refinement_head_stride', refinement_head_stride)):
+            if int(v) not in (1, 2):
+                raise NotImplementedError(f'{nm}={v}: strides 1 and 2 are supported')
+        self.contour_head_channels = None if not contour_head_channels else int(contour_head_channels)
+        self.refinement_head_channels = None if not refinement_head_channels else int(refinement_head_channels)
+        self.contour_head_stride, self.refinement_head_stride = int(contour_head_stride), int(refinement_head_stride)
+        self.refinement_full_res = bool(refinement_full_res)
         self.arch = backbone
         self.in_channels = in_channels
         self.order = order
@@ -94,7 +142,13 @@ class CPN(nn.Module):
                             samples=samples, classes=classes, refinement=refinement,
                             refinement_iterations=refinement_iterations, refinement_margin=refinement_margin,
                             refinement_buckets=refinement_buckets, uncertainty_head=uncertainty_head,
-                            uncertainty_nms=uncertainty_nms, certainty_thresh=certainty_thresh, **kwargs)
+                            uncertainty_nms=uncertainty_nms, certainty_thresh=certainty_thresh,
+                            contour_head_channels=contour_head_channels, contour_head_stride=contour_head_stride,
+                            refinement_head_channels=refinement_head_channels,
+                            refinement_head_stride=refinement_head_stride, refinement_full_res=refinement_full_res,
+                            **extra)
+        if backbone_kwargs:
+            self.hparams['backbone_kwargs'] = dict(backbone_kwargs)
         # ---- parameters / buffers with the reference's state_dict keys ----
         g = trace(backbone, 1, 64, 64, in_channels=in_channels, order=order, refinement_margin=refinement_margin,
                   **self._variant())
@@ -141,7 +195,11 @@ class CPN(nn.Module):
 
     def _variant(self):
         return dict(score_channels=self.score_channels, refinement_buckets=self.refinement_buckets,
-                    uncertainty_head=self.uncertainty_head)
+                    uncertainty_head=self.uncertainty_head, kernel_sizes=self.kernel_sizes,
+                    contour_head_channels=self.contour_head_channels,
+                    refinement_head_channels=self.refinement_head_channels,
+                    contour_head_stride=self.contour_head_stride, refinement_head_stride=self.refinement_head_stride,
+                    refinement_full_res=self.refinement_full_res, fpn_channels=self.fpn_channels)
 
     # ---- plan management ------------------------------------------------------------------------------------------
     def invalidate_plans(self):
@@ -327,7 +385,15 @@ class CPN(nn.Module):
         plan = self._plan(n, h, w)
         x = inputs.contiguous() if inputs.dtype == torch.uint8 else inputs.contiguous().float()
         plan.flags.zero_()
-        return plan, plan.forward(x, fmt), (h, w)
+        outs = plan.forward(x, fmt)
+        rf = outs[2]
+        if tuple(rf.shape[1:3]) != (h, w):       # strided / low-res refinement head: _equal_size to the input (cpn.py:279)
+            full = torch.empty((n, h, w, rf.shape[3]), dtype=torch.float32, device=rf.device)
+            L.check(L.load().cpn_resize_bilinear(L.ptr(rf), n, int(rf.shape[1]), int(rf.shape[2]), int(rf.shape[3]),
+                                                 L.ptr(full), h, w, L.stream_ptr()), 'resize_bilinear')
+            outs = list(outs)
+            outs[2] = full
+        return plan, outs, (h, w)
 
     def _post_kwargs(self, plan, outs, kwargs):
         return dict(offsets=kwargs.get('offsets'), scores_lower_bound=kwargs.get('scores_lower_bound'),
@@ -355,13 +421,12 @@ def _make(arch):
         def __init__(self, in_channels: int = 3, order: int = 5, nms_thresh: float = .2, score_thresh: float = .9,
                      samples: int = 32, classes: int = 2, refinement: bool = True, refinement_iterations: int = 4,
                      refinement_margin: float = 3., refinement_buckets: int = 1, backbone_kwargs: dict = None,
-                     **kwargs):   # kwargs: uncertainty_head, uncertainty_nms, certainty_thresh, precision (cpn.py:288-321)
-            if backbone_kwargs:
-                raise NotImplementedError('backbone_kwargs are outside the accelerated path.')
+                     **kwargs):   # kwargs: uncertainty_head, uncertainty_nms, certainty_thresh, precision, the head
+                                  # options of CPN.__init__ (cpn.py:288-321)
             super().__init__(arch, in_channels=in_channels, order=order, nms_thresh=nms_thresh,
                              score_thresh=score_thresh, samples=samples, classes=classes, refinement=refinement,
                              refinement_iterations=refinement_iterations, refinement_margin=refinement_margin,
-                             refinement_buckets=refinement_buckets, **kwargs)
+                             refinement_buckets=refinement_buckets, backbone_kwargs=backbone_kwargs, **kwargs)
     _Cpn.__name__ = _Cpn.__qualname__ = arch
     return _Cpn
 

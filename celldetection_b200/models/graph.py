@@ -365,16 +365,29 @@ def _read_out_spec(g, p, cin, cmid, cout, k=7):
     g.conv_spec(f'{p}.block.4', cmid, cout, 1, True)
 
 
+HEAD_KERNEL_KEYS = ('score', 'location', 'fourier', 'uncertainty', 'refinement')
+
+
 def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_margin=3., refinement_buckets=1,
-          uncertainty_head=False, stem_im2col=False):
+          uncertainty_head=False, stem_im2col=False, kernel_sizes=None, contour_head_channels=None,
+          refinement_head_channels=None, contour_head_stride=1, refinement_head_stride=1, refinement_full_res=True,
+          fpn_channels=256):
     """Trace architecture `arch` for an [n, in_channels, h, w] input.  Returns the Tracer; ``g.outputs`` maps
     'scores' / 'locfou' / 'refinement' (/ 'uncertainty') to fp32 output tensors (bindings 0 / 1 / 2 (/ 3)).
 
     Variants of models/cpn.py:177-234: ``score_channels`` > 1 widens the score head (classes > 2, :372),
     ``refinement_buckets`` > 1 widens the refinement head to 2 * buckets channels (:222-234), ``uncertainty_head``
-    adds a fourth ReadOut with 4 sigmoid outputs on the head features (:208-219)."""
+    adds a fourth ReadOut with 4 sigmoid outputs on the head features (:208-219).  Shape-changing head options:
+    ``kernel_sizes`` (dict over HEAD_KERNEL_KEYS, default 7 each: ``kernel_size_<head>``, :179-229), the ReadOut mid
+    widths ``contour_head_channels`` / ``refinement_head_channels`` (default: the input width), the head strides
+    ``contour_head_stride`` / ``refinement_head_stride``, ``refinement_full_res`` (:277-279) and ``fpn_channels``
+    (fpn.py:240-322).  Contour heads that share a kernel size run as one merged convolution; the refinement tensor is
+    produced at the head's own resolution ``g.ref_hw`` (the caller resizes it to the input size when they differ, :279)."""
     assert arch in ARCHS, arch
     assert score_channels >= 1 and refinement_buckets >= 1
+    ks = dict.fromkeys(HEAD_KERNEL_KEYS, 7)
+    ks.update(kernel_sizes or {})
+    assert all(int(k) % 2 == 1 and 1 <= int(k) <= 15 for k in ks.values()), 'head kernel sizes must be odd, <= 15'
     g = Tracer(n, h, w, stem_im2col=stem_im2col)
     g.spec['order_weights'] = ((order, 1), 'order_weights')   # buffer of CPN (cpn.py:406-412)
     bb = 'core.backbone'
@@ -390,20 +403,22 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
         head_feat, head_c, ref_feat, ref_c = res[1], out_ch[1], res[0], out_ch[0]
     else:
         feats, chans = _resnet_encoder(g, x, f'{bb}.body', in_channels, enc)
-        res = _fpn_decoder(g, feats, chans, f'{bb}.fpn')
-        head_feat, head_c, ref_feat, ref_c = res[1], 256, res[0], 256
+        res = _fpn_decoder(g, feats, chans, f'{bb}.fpn', fpn_channels=fpn_channels)
+        head_feat, head_c, ref_feat, ref_c = res[1], fpn_channels, res[0], fpn_channels
     # ---- heads (models/cpn.py:177-234, 238-283); module order: score, location, fourier, (uncertainty), refinement ----
-    heads = [('core.score_head', score_channels, 'none'), ('core.location_head', 2, 'none'),
-             ('core.fourier_head', order * 4, 'none')]
+    heads = [('core.score_head', score_channels, 'none', int(ks['score'])),
+             ('core.location_head', 2, 'none', int(ks['location'])),
+             ('core.fourier_head', order * 4, 'none', int(ks['fourier']))]
     if uncertainty_head:
-        heads.append(('core.uncertainty_head', 4, 'sigmoid'))
-    for hp, co, _ in heads:
-        _read_out_spec(g, hp, head_c, head_c, co)
-    _read_out_spec(g, 'core.refinement_head', ref_c, ref_c, 2 * refinement_buckets)
-    pm = ConvParams([f'{hp}.block.0.weight' for hp, _, _ in heads], [f'{hp}.block.0.bias' for hp, _, _ in heads],
-                    [f'{hp}.block.1' for hp, _, _ in heads])
-    mid = g.conv(head_feat, len(heads) * head_c, 7, act='relu', params=pm, name='heads.block.0')
-    hh, hw_ = head_feat.h, head_feat.w
+        heads.append(('core.uncertainty_head', 4, 'sigmoid', int(ks['uncertainty'])))
+    head_mid = int(contour_head_channels) if contour_head_channels else head_c
+    ref_mid = int(refinement_head_channels) if refinement_head_channels else ref_c
+    for hp, co, _, k in heads:
+        _read_out_spec(g, hp, head_c, head_mid, co, k)
+    _read_out_spec(g, 'core.refinement_head', ref_c, ref_mid, 2 * refinement_buckets, int(ks['refinement']))
+    cs = int(contour_head_stride)
+    hh = (head_feat.h + 2 * (heads[0][3] // 2) - heads[0][3]) // cs + 1
+    hw_ = (head_feat.w + 2 * (heads[0][3] // 2) - heads[0][3]) // cs + 1
     scores = g.tensor(score_channels, hh, hw_, f32=True, binding=0)
     locfou = g.tensor(2 + 4 * order, hh, hw_, f32=True, binding=1)
     loc_t = g.tensor(2, hh, hw_, f32=True, parent=locfou, c_off=0, binding=1)
@@ -413,22 +428,32 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
     if uncertainty_head:
         uncertainty = g.tensor(4, hh, hw_, f32=True, binding=3)
         dsts.append(uncertainty)
-    for j, ((hp, co, act), dst) in enumerate(zip(heads, dsts)):
-        pp = ConvParams([f'{hp}.block.4.weight'], [f'{hp}.block.4.bias'], [None])
-        g.proj(mid, dst, j * head_c, head_c, pp, act=act, name=f'{hp}.block.4')
-    if (ref_feat.h, ref_feat.w) != (h, w):       # refinement_full_res (cpn.py:277-278)
+    # heads with the same kernel size share one convolution (concatenated output channels, in module order)
+    for k in sorted({hd[3] for hd in heads}, reverse=True):
+        grp = [(hd, dst) for hd, dst in zip(heads, dsts) if hd[3] == k]
+        pm = ConvParams([f'{hd[0]}.block.0.weight' for hd, _ in grp], [f'{hd[0]}.block.0.bias' for hd, _ in grp],
+                        [f'{hd[0]}.block.1' for hd, _ in grp])
+        name = 'heads.block.0' if len(grp) == len(heads) else 'heads.block.0.k%d' % k
+        mid = g.conv(head_feat, len(grp) * head_mid, k, stride=cs, act='relu', params=pm, name=name)
+        assert (mid.h, mid.w) == (hh, hw_)
+        for j, ((hp, co, act, _), dst) in enumerate(grp):
+            pp = ConvParams([f'{hp}.block.4.weight'], [f'{hp}.block.4.bias'], [None])
+            g.proj(mid, dst, j * head_mid, head_mid, pp, act=act, name=f'{hp}.block.4')
+    if refinement_full_res and (ref_feat.h, ref_feat.w) != (h, w):       # refinement_full_res (cpn.py:277-278)
         ref_feat = g.bilinear(ref_feat, h, w)
     pr = ConvParams(['core.refinement_head.block.0.weight'], ['core.refinement_head.block.0.bias'],
                     ['core.refinement_head.block.1'])
-    rmid = g.conv(ref_feat, ref_c, 7, act='relu', params=pr, name='core.refinement_head.block.0')
-    refinement = g.tensor(2 * refinement_buckets, h, w, f32=True, binding=2)
+    rmid = g.conv(ref_feat, ref_mid, int(ks['refinement']), stride=int(refinement_head_stride), act='relu', params=pr,
+                  name='core.refinement_head.block.0')
+    refinement = g.tensor(2 * refinement_buckets, rmid.h, rmid.w, f32=True, binding=2)
     pp = ConvParams(['core.refinement_head.block.4.weight'], ['core.refinement_head.block.4.bias'], [None])
-    g.proj(rmid, refinement, 0, ref_c, pp, act='scaled_tanh', act_scale=float(refinement_margin),
+    g.proj(rmid, refinement, 0, ref_mid, pp, act='scaled_tanh', act_scale=float(refinement_margin),
            name='core.refinement_head.block.4')
     g.outputs = OrderedDict(scores=scores, locfou=locfou, refinement=refinement)
     if uncertainty is not None:
         g.outputs['uncertainty'] = uncertainty
     g.head_hw = (hh, hw_)
+    g.ref_hw = (rmid.h, rmid.w)
     g.finalize()
     return g
 

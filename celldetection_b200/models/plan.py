@@ -292,7 +292,7 @@ class Plan:
         sc = g.outputs['scores'].c      # score maps keep the historical [N,h,w] shape for a single channel
         self.out_shapes = OrderedDict(scores=(g.n, hh, hw) if sc == 1 else (g.n, hh, hw, sc),
                                       locfou=(g.n, hh, hw, g.outputs['locfou'].c),
-                                      refinement=(g.n, g.h, g.w, g.outputs['refinement'].c))
+                                      refinement=(g.n,) + tuple(getattr(g, 'ref_hw', (g.h, g.w))) + (g.outputs['refinement'].c,))
         if 'uncertainty' in g.outputs:
             self.out_shapes['uncertainty'] = (g.n, hh, hw, 4)
 

@@ -181,7 +181,8 @@ def nms_grid(boxes: Tensor, scores: Tensor, iou_threshold: float, return_rounds=
     count = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
     ws = torch.empty((int(lib.cpn_nms_grid_workspace_bytes(P)),), dtype=torch.uint8, device=boxes.device)
     rounds = ctypes.c_int(0)
-    L.check(lib.cpn_nms_grid(L.ptr(boxes.contiguous().float()), L.ptr(scores.contiguous().float()), P,
+    boxes, scores = boxes.contiguous().float(), scores.contiguous().float()   # named: temporaries must outlive the launch
+    L.check(lib.cpn_nms_grid(L.ptr(boxes), L.ptr(scores), P,
                              float(iou_threshold), L.ptr(ws), L.ptr(keep), L.ptr(count), ctypes.byref(rounds),
                              L.stream_ptr()), 'nms_grid')
     out = keep[:int(count.item())].long()
@@ -240,7 +241,8 @@ def remove_border_contours(contours, size, padding=1, top=True, right=True, bott
     meta = torch.tensor([[off[0], off[1], float(h), float(w), float(top), float(right), float(bottom), float(left),
                           0., 0., 0., 0.]], dtype=torch.float32, device=contours.device)
     tile = torch.zeros((K,), dtype=torch.int32, device=contours.device)
-    L.check(lib.cpn_border_filter(L.ptr(contours.contiguous().float()), L.ptr(tile), L.ptr(meta), K, S,
+    contours = contours.contiguous().float()
+    L.check(lib.cpn_border_filter(L.ptr(contours), L.ptr(tile), L.ptr(meta), K, S,
                                   float(padding), L.ptr(keep), L.stream_ptr()), 'border_filter')
     return keep.bool()
 
@@ -262,7 +264,8 @@ def filter_contours_by_stitching_rule(contours, tile_size, overlaps, rule='ex_br
         meta = torch.tensor([[off[0], off[1], float(ts[0]), float(ts[1]), 0., 0., 0., 0., 1., float(stop_x),
                               float(stop_y), 0.]], dtype=torch.float32, device=contours.device)
         tile = torch.zeros((K,), dtype=torch.int32, device=contours.device)
-        L.check(lib.cpn_border_filter(L.ptr(contours.contiguous().float()), L.ptr(tile), L.ptr(meta), K, S, 0.,
+        contours = contours.contiguous().float()
+        L.check(lib.cpn_border_filter(L.ptr(contours), L.ptr(tile), L.ptr(meta), K, S, 0.,
                                       L.ptr(keep), L.stream_ptr()), 'border_filter')
     keep = keep.bool()
     return torch.where(keep)[0] if indices else keep

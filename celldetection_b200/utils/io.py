@@ -28,8 +28,8 @@ def dict2model(conf, **kwargs):
     kw = dict(meta.get('kwargs', {})) if isinstance(meta, dict) else {}
     kw.update(meta.get('updated_kwargs', {}) if isinstance(meta, dict) else {})
     kw.update(kwargs)
-    kw.pop('pretrained', None)
-    kw.pop('backbone_kwargs', None)
+    # nothing is dropped silently: the constructors accept the options that are identities on this path (pretrained=False,
+    # default backbone_kwargs, ...) and raise for every option that would change the network
     model = getattr(models, name)(**kw)
     model.load_state_dict(conf['state_dict'])
     return model.eval()

@@ -179,10 +179,12 @@ def fpn_decoder(feats, sd, p):
     return OrderedDict(zip(names, results))
 
 
-def read_out(x, sd, p, final=None):
-    """models/commons.py:461-511: conv kxk (bias) -> BN -> ReLU -> Dropout2d (identity in eval) -> conv1x1 (bias)."""
+def read_out(x, sd, p, final=None, stride=1):
+    """models/commons.py:461-511: conv kxk (bias, stride) -> BN -> ReLU -> Dropout2d (identity in eval) -> conv1x1 (bias).
+    The kernel size (``kernel_size_<head>``, models/cpn.py:179-229) and the mid width (``*_head_channels``) are read off
+    the state_dict."""
     k = sd[f'{p}.block.0.weight'].shape[-1]
-    x = F.relu(_bn(_conv(x, sd, f'{p}.block.0', padding=k // 2), sd, f'{p}.block.1'))
+    x = F.relu(_bn(_conv(x, sd, f'{p}.block.0', stride=stride, padding=k // 2), sd, f'{p}.block.1'))
     x = _conv(x, sd, f'{p}.block.4')
     if final is not None:
         x = final(x)
@@ -208,28 +210,35 @@ def _equal_size(x, ref_hw):
     return x
 
 
-def cpn_core5(x, sd, arch, refinement_margin=3.):
+CORE_KW = ('refinement_margin', 'contour_head_stride', 'refinement_head_stride', 'refinement_full_res')
+
+
+def cpn_core5(x, sd, arch, refinement_margin=3., contour_head_stride=1, refinement_head_stride=1,
+              refinement_full_res=True):
     """models/cpn.py:238-283 -> scores, locations, refinement, fourier, uncertainty (raw head tensors, NCHW fp32).
     The variants are read off the state_dict: score head width (classes > 2), refinement head width (2 * buckets),
     presence of ``core.uncertainty_head`` (4 sigmoid outputs, cpn.py:208-219)."""
     cfg = ARCHS[arch]
     feats = backbone(x, sd, arch)
     hf, rf = feats[cfg['head_key']], feats[cfg['ref_key']]
-    scores = read_out(hf, sd, 'core.score_head')
-    locations = read_out(hf, sd, 'core.location_head')
-    fourier = read_out(hf, sd, 'core.fourier_head')
+    cs = contour_head_stride
+    scores = read_out(hf, sd, 'core.score_head', stride=cs)
+    locations = read_out(hf, sd, 'core.location_head', stride=cs)
+    fourier = read_out(hf, sd, 'core.fourier_head', stride=cs)
     uncertainty = None
     if 'core.uncertainty_head.block.0.weight' in sd:
-        uncertainty = read_out(hf, sd, 'core.uncertainty_head', final=torch.sigmoid)
-    rf = _equal_size(rf, x.shape[2:])
-    refinement = read_out(rf, sd, 'core.refinement_head', final=lambda t: torch.tanh(t) * refinement_margin + 0.)
+        uncertainty = read_out(hf, sd, 'core.uncertainty_head', final=torch.sigmoid, stride=cs)
+    if refinement_full_res:                       # models/cpn.py:277-278
+        rf = _equal_size(rf, x.shape[2:])
+    refinement = read_out(rf, sd, 'core.refinement_head', final=lambda t: torch.tanh(t) * refinement_margin + 0.,
+                          stride=refinement_head_stride)
     refinement = _equal_size(refinement, x.shape[2:])
     return scores, locations, refinement, fourier, uncertainty
 
 
-def cpn_core(x, sd, arch, refinement_margin=3.):
+def cpn_core(x, sd, arch, refinement_margin=3., **core_kw):
     """``cpn_core5`` without the uncertainty map."""
-    return cpn_core5(x, sd, arch, refinement_margin)[:4]
+    return cpn_core5(x, sd, arch, refinement_margin, **core_kw)[:4]
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -439,8 +448,9 @@ def cpn_post(scores, locations, refinement, fourier, original_size, order=5, sam
 def cpn_forward(x, sd, arch, **kw):
     """``model(x)`` of the reference in eval mode: core + post chain.  ``kw`` are the mutable CPN attributes."""
     x = torch.as_tensor(x, dtype=torch.float32)
+    core_kw = {k: kw.pop(k) for k in CORE_KW if k in kw}      # constructor options that shape the core
     with torch.no_grad():
-        scores, locations, refinement, fourier, uncertainty = cpn_core5(x, sd, arch)
+        scores, locations, refinement, fourier, uncertainty = cpn_core5(x, sd, arch, **core_kw)
         return cpn_post(scores, locations, refinement, fourier, x.shape[-2:], uncertainty=uncertainty, **kw)
 
 

@@ -42,6 +42,13 @@ VARIANT_CASES = [
      dict(uncertainty_head=True, refinement_buckets=4), dict(certainty_thresh=0.47)),
     ('cpnresnet18fpn_c3_b2', 'CpnResNet18FPN', 1, 128, 128, 8, 0.2,
      dict(classes=3, refinement_buckets=2), dict()),
+    # shape-changing head options (models/cpn.py:177-234): per-head kernel sizes, narrowed ReadOut mid widths, strided heads
+    ('cpnu22_k357_mid64', 'CpnU22', 1, 128, 128, 9, 0.2,
+     dict(kernel_size_score=3, kernel_size_location=5, kernel_size_fourier=5, kernel_size_refinement=3,
+          contour_head_channels=64), dict()),
+    ('cpnresnet18fpn_mid_stride2', 'CpnResNet18FPN', 2, 128, 160, 10, 0.3,
+     dict(contour_head_channels=128, refinement_head_channels=64, contour_head_stride=2, refinement_head_stride=2,
+          kernel_size_refinement=5, backbone_kwargs=dict(fpn_channels=128)), dict()),
 ]
 
 
@@ -146,13 +153,14 @@ def mint_variant_case(cd, name, arch, n, h, w, seed, fg, ctor, attrs):
         scores, locations, refinement, fourier, unc = model.core(x)
         out = model(x) if offsets is None else model(x, offsets=offsets)
         out_nonms = model(x, nms=False)
-    o = orc.cpn_core5(x, sd, arch)
+    core_kw = {k: ctor[k] for k in orc.CORE_KW if k in ctor}
+    o = orc.cpn_core5(x, sd, arch, **core_kw)
     for nm, a, b in zip(('scores', 'locations', 'refinement', 'fourier', 'uncertainty'), o,
                         (scores, locations, refinement, fourier, unc)):
         if b is not None:
             check_close(f'{name}/{nm}', to_np(a), to_np(b), 1e-5)
     okw = dict(offsets=offsets, order=model.order, samples=model.samples, certainty_thresh=model.certainty_thresh,
-               uncertainty_nms=model.uncertainty_nms)
+               uncertainty_nms=model.uncertainty_nms, **core_kw)
     o_out = orc.cpn_forward(x, sd, arch, **okw)
     keys = ['contours', 'boxes', 'scores', 'classes', 'locations', 'fourier', 'contour_proposals']
     if unc is not None:

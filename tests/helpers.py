@@ -25,7 +25,9 @@ def key_spec(arch):
     return OrderedDict((k, tuple(s)) for k, s in keys)
 
 
-VARIANT_FIXTURES = ['model_cpnu22_c4_unc_b6', 'model_cpnresnext101unet_unc_b4', 'model_cpnresnet18fpn_c3_b2']
+VARIANT_FIXTURES = ['model_cpnu22_c4_unc_b6', 'model_cpnresnext101unet_unc_b4', 'model_cpnresnet18fpn_c3_b2',
+                    # shape-changing head options: per-head kernel sizes / mid widths / strides / fpn_channels
+                    'model_cpnu22_k357_mid64', 'model_cpnresnet18fpn_mid_stride2']
 
 
 def fixture_ctor(z):

@@ -430,3 +430,136 @@ def test_tiled_im2col_prep_equals_direct_kernel():
         assert r.returncode == 0, r.stderr[-2000:]
         digests.append([l for l in r.stdout.splitlines() if l.startswith('DIGEST')][0])
     assert digests[0] == digests[1]
+
+
+def _calibrated_sd(arch, x, fg=0.02, fourier_std=3.0, location_std=1.0, seed=0):
+    from helpers import key_spec
+    from celldetection_b200.utils.synth import synth_state_dict, calibrate_heads_
+    sd = synth_state_dict(key_spec(arch), seed=seed)
+
+    def core_fn(xx, sd_):
+        s, l, r, f = orc.cpn_core(xx, sd_, arch)
+        return dict(scores=s, locations=l, fourier=f, refinement=r)
+
+    with torch.no_grad():
+        calibrate_heads_(sd, core_fn, x, fg_fraction=fg, fourier_std=fourier_std, location_std=location_std)
+    return sd
+
+
+def test_full_size_c2_batch_against_oracle():
+    """BASELINE config C2 at full tile size: CpnResNet18FPN on 3x512x512 tiles (batch 2) through the default engine against
+    the oracle on the CPU -- 1e-3 tensor gate, identical instance counts, decoded vertices within 0.5 px.  Exercises the
+    bilinear x2 of the 256-channel refinement features and the 7x7 refinement head at 512x512."""
+    arch = 'CpnResNet18FPN'
+    torch.manual_seed(5)
+    torch.set_num_threads(max(1, min(32, (os.cpu_count() or 8) // 2)))
+    x = torch.rand(2, 3, 512, 512)
+    sd = _calibrated_sd(arch, x[:1], seed=2)
+    with torch.no_grad():
+        s, l, r, f = orc.cpn_core(x, sd, arch)
+        want = orc.cpn_post(s, l, r, f, (512, 512))
+    m = getattr(cd.models, arch)(3)
+    assert m.precision == 'fp16f8'
+    m.load_state_dict(sd)
+    m = m.cuda()
+    raw = m.core_forward(x.cuda())
+    errs = {k: rel_err(raw[k].cpu().numpy(), ref.numpy()) for k, ref in
+            (('scores', s), ('locations', l), ('refinement', r), ('fourier', f))}
+    _report('c2_512/fp16f8_vs_oracle_raw_rel_err', errs)
+    for k, e in errs.items():
+        assert e < 1e-3, (k, e)
+    out = m(x.cuda())
+    assert [len(v) for v in out['scores']] == [len(v) for v in want['scores']]
+    for i in range(2):
+        pairs = match_by_box(out['boxes'][i].cpu().numpy(), want['boxes'][i].numpy())
+        assert len(pairs) == len(want['scores'][i]) > 0
+        err = max(float(np.abs(out['contour_proposals'][i][a].cpu().numpy() - want['contour_proposals'][i][b].numpy()).max())
+                  for a, b in pairs)
+        assert err < 0.5, err
+
+
+@pytest.mark.parametrize('stride', [384, 512])
+def test_tiled_driver_flagship_2048_against_oracle(stride):
+    """cd.apply_model with the flagship (CpnResNeXt101UNet, default engine) on a 2048x2048 uint8
+    image at crop 512 / stride 384 (25 tiles) and 512 (16 tiles) against the oracle's apply_model on the CPU: same stitched
+    instance count (a handful of score-threshold / IoU-threshold ties may flip: |difference| <= 2), every matched
+    contour's decoded vertices within 0.5 px, >= 99 % of the refined vertices within 0.5 px; and the device-resident
+    slide path returns the identical result."""
+    arch = 'CpnResNeXt101UNet'
+    torch.set_num_threads(max(1, min(32, (os.cpu_count() or 8) // 2)))
+    rng = np.random.RandomState(11)
+    img = rng.randint(0, 256, size=(2048, 2048, 3), dtype=np.uint8)
+    torch.manual_seed(0)
+    sd = _calibrated_sd(arch, torch.rand(1, 3, 512, 512), seed=0)
+    with torch.no_grad():
+        want = orc.apply_model(img, sd, arch, 512, stride, border_removal=4)
+    m = getattr(cd.models, arch)(3)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    got = cd.apply_model(img, [m], crop_size=512, strides=stride, border_removal=4, batch_size=8)
+    k, k_ref = len(got['scores']), len(want['scores'])
+    _report(f'tiled_2048_s{stride}/counts', dict(oracle=k_ref, got=k))
+    assert k_ref > 100 and abs(k - k_ref) <= 2, (k, k_ref)
+    pairs = match_by_box(got['boxes'].cpu().numpy(), want['boxes'].numpy())
+    assert len(pairs) >= k_ref - 2
+    gp, gc = got['contour_proposals'].cpu().numpy(), got['contours'].cpu().numpy()
+    wp, wc = want['contour_proposals'].numpy(), want['contours'].numpy()
+    perr = max(float(np.abs(gp[a] - wp[b]).max()) for a, b in pairs)
+    d = np.concatenate([np.abs(gc[a] - wc[b]).max(-1) for a, b in pairs])
+    _report(f'tiled_2048_s{stride}/errors', dict(max_decoded_vertex_err=perr, refined_within_half_px=float((d < 0.5).mean())))
+    assert perr < 0.5
+    assert (d < 0.5).mean() >= 0.99
+    dev = cd.apply_model(torch.from_numpy(img).cuda(), [m], crop_size=512, strides=stride, border_removal=4, batch_size=8)
+    for key in ('contours', 'boxes', 'scores'):
+        assert torch.equal(dev[key], got[key]), key
+
+
+_NCCL_WORKER = r'''
+import os, sys, hashlib
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch
+import celldetection_b200 as cd
+from celldetection_b200.utils.synth import synth_state_dict
+world = int(os.environ.get('WORLD_SIZE', '1'))
+local = int(os.environ.get('LOCAL_RANK', '0'))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+m = cd.models.CpnU22(3)
+sd = synth_state_dict(m._spec, seed=21)
+sd['core.score_head.block.4.bias'] = sd['core.score_head.block.4.bias'] + 1.5      # plenty of detections
+m.load_state_dict(sd)
+m = m.cuda()
+img = np.random.RandomState(5).randint(0, 256, size=(700, 900, 3), dtype=np.uint8)
+res = cd.apply_model(img, [m], crop_size=256, strides=192, batch_size=4)
+h = hashlib.sha256()
+for k in ('boxes', 'scores', 'contours', 'classes', 'locations', 'fourier', 'contour_proposals'):
+    h.update(res[k].cpu().numpy().tobytes())
+print('DIGEST', int(res['scores'].shape[0]), h.hexdigest(), flush=True)
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_sharded_slide_is_bit_identical_to_single_gpu(tmp_path):
+    """1-GPU result == 2-GPU result bit for bit (SURVEY appendix C.6): the same image through cd.apply_model in one
+    process and sharded over two NCCL ranks; every rank of the sharded run must print the single-process digest."""
+    import subprocess
+    import sys
+    script = tmp_path / 'worker.py'
+    script.write_text(_NCCL_WORKER)
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+    one = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600, env=env)
+    assert one.returncode == 0, one.stderr[-2000:]
+    want = [l for l in one.stdout.splitlines() if l.startswith('DIGEST')]
+    port = str(29600 + os.getpid() % 300)
+    two = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', port, str(script), ROOT],
+                         capture_output=True, text=True, timeout=900, env=env)
+    assert two.returncode == 0, two.stderr[-2000:]
+    got = [l for l in two.stdout.splitlines() if l.startswith('DIGEST')]
+    assert len(want) == 1 and len(got) == 2 and int(want[0].split()[1]) > 50
+    assert got[0] == got[1] == want[0], (want, got)

@@ -167,7 +167,8 @@ from collections import OrderedDict
 from celldetection_b200.inference import allgather_detections, canonical_order
 dist.init_process_group('gloo', init_method='tcp://127.0.0.1:' + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank = dist.get_rank()
-K = 3 if rank == 0 else 5
+KS = [int(v) for v in sys.argv[5].split(',')]
+K = KS[rank]
 g = torch.Generator().manual_seed(100 + rank)
 res = OrderedDict(contours=torch.rand(K, 8, 2, generator=g), boxes=torch.rand(K, 4, generator=g),
                   scores=torch.rand(K, generator=g), classes=torch.ones(K, dtype=torch.long),
@@ -176,28 +177,34 @@ res = OrderedDict(contours=torch.rand(K, 8, 2, generator=g), boxes=torch.rand(K,
                   box_uncertainties=torch.rand(K, 4, generator=g),      # models with an uncertainty head carry this key
                   order_key=torch.stack((torch.arange(K).float() * 2 + rank, torch.arange(K).float()), 1))
 out = allgather_detections(res)
-assert out['scores'].shape[0] == 8 and out['classes'].dtype == torch.long
-assert list(out.keys()) == list(res.keys()) and out['box_uncertainties'].shape == (8, 4)
-for r, (a, b) in enumerate(((0, 3), (3, 8))):
+T = sum(KS)
+assert out['scores'].shape[0] == T and out['classes'].dtype == torch.long
+assert list(out.keys()) == list(res.keys()) and out['box_uncertainties'].shape == (T, 4)
+assert out['contours'].shape == (T, 8, 2) and out['fourier'].shape == (T, 5, 4)
+for r, (a, b) in enumerate(((0, KS[0]), (KS[0], T))):
     gg = torch.Generator().manual_seed(100 + r)
     kk = b - a
     want = torch.rand(kk, 8, 2, generator=gg)
     assert torch.equal(out['contours'][a:b], want), r
 can = canonical_order(out)                       # tiles were dealt round-robin: rank 0 -> 0,2,4  rank 1 -> 1,3,5,7,9
-assert can['order_key'][:, 0].tolist() == [0., 1., 2., 3., 4., 5., 7., 9.]
-assert torch.equal(can['contours'][1], out['contours'][3])
+if KS == [3, 5]:
+    assert can['order_key'][:, 0].tolist() == [0., 1., 2., 3., 4., 5., 7., 9.]
+    assert torch.equal(can['contours'][1], out['contours'][3])
+assert can['scores'].shape[0] == T
 torch.save({k: v for k, v in out.items()}, sys.argv[4] + f'.{rank}')
 dist.destroy_process_group()
 '''
 
 
-def test_allgather_detections_world2_gloo(tmp_path):
-    """N > 1 exchange step (SURVEY 8e) on CPU: both ranks end up with the identical rank-ordered concatenation."""
+@pytest.mark.parametrize('counts', ['3,5', '0,5', '4,0', '0,0'])
+def test_allgather_detections_world2_gloo(tmp_path, counts):
+    """N > 1 exchange step (SURVEY 8e) on CPU: both ranks end up with the identical rank-ordered concatenation --
+    including when one rank or every rank has no detections (fewer tiles than ranks, blank tiles, masked-out tiles)."""
     script = tmp_path / 'worker.py'
     script.write_text(_WORKER)
-    port = str(29500 + os.getpid() % 2000)
+    port = str(29500 + (os.getpid() * 7 + sum(int(c) for c in counts.split(',')) * 13 + len(counts)) % 2000)
     out = str(tmp_path / 'res')
-    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), out]) for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), out, counts]) for r in range(2)]
     for p in procs:
         assert p.wait(timeout=240) == 0
     a, b = torch.load(out + '.0'), torch.load(out + '.1')
@@ -312,3 +319,33 @@ def test_f16f8_packing_reproduces_fp32_products():
         e1 = float((single - want).abs().max() / want.abs().max())
         assert e2 < 3e-5 and e2 < e1 / 8, (amp, e1, e2)
         assert float(w16.abs().max()) < 65504 and float(wh8.abs().max()) <= 448
+
+
+def test_constructor_options_are_honoured_or_rejected():
+    """Reference constructor options (models/cpn.py:288-321, CPNCore :126-149) are either honoured -- the shape-changing
+    head options, visible in the state_dict shapes and the traced plan -- or rejected; none is silently swallowed."""
+    m = cd.models.CpnResNet18FPN(3, kernel_size_score=3, kernel_size_refinement=5, contour_head_channels=128,
+                                 refinement_head_channels=64, contour_head_stride=2, refinement_head_stride=2,
+                                 backbone_kwargs=dict(fpn_channels=128, pretrained=False), pretrained=False,
+                                 uncertainty_factor=7., order_weights=True, contour_features='1')
+    sd = m.state_dict()
+    assert tuple(sd['core.score_head.block.0.weight'].shape) == (128, 128, 3, 3)
+    assert tuple(sd['core.fourier_head.block.0.weight'].shape) == (128, 128, 7, 7)
+    assert tuple(sd['core.refinement_head.block.0.weight'].shape) == (64, 128, 5, 5)
+    assert tuple(sd['core.backbone.fpn.inner_blocks.0.0.weight'].shape) == (128, 64, 1, 1)
+    g = G.trace(m.arch, 1, 128, 128, **m._variant())
+    convs = {o.name: o for o in g.ops if o.kind == 'conv'}
+    assert convs['heads.block.0.k7'].dst.c == 256 and convs['heads.block.0.k7'].stride == 2      # location + fourier merged
+    assert convs['heads.block.0.k3'].dst.c == 128 and convs['heads.block.0.k3'].k == 3
+    assert g.head_hw == (16, 16) and g.ref_hw == (64, 64)
+    assert m.hparams['kernel_size_score'] == 3 and m.hparams['backbone_kwargs']['fpn_channels'] == 128
+    for bad, exc in ((dict(contour_features=['0', '1']), NotImplementedError), (dict(foo=1), TypeError),
+                     (dict(backbone_kwargs=dict(inputs_mean=0.5)), NotImplementedError),
+                     (dict(refinement_interpolation='nearest'), NotImplementedError),
+                     (dict(head_activation='gelu'), NotImplementedError), (dict(contour_head_stride=4), NotImplementedError),
+                     (dict(backbone_kwargs=dict(fpn_channels=128)), ValueError)):
+        with pytest.raises(exc):
+            cd.models.CpnU22(3, **bad)
+    from celldetection_b200.inference import _parse_model_parameters
+    assert _parse_model_parameters('nms_thresh=0.3, certainty_thresh=None,refinement=False,tag=a=b') == [
+        ('nms_thresh', 0.3), ('certainty_thresh', None), ('refinement', False), ('tag', 'a=b')]

@@ -54,7 +54,7 @@ def test_oracle_variant_models_match_reference_golden(name):
     x = torch.from_numpy(z['x'])
     torch.set_num_threads(8)
     with torch.no_grad():
-        raw = orc.cpn_core5(x, sd, arch)
+        raw = orc.cpn_core5(x, sd, arch, **{k: ctor[k] for k in orc.CORE_KW if k in ctor})
     for nm, t in zip(('scores', 'locations', 'refinement', 'fourier', 'uncertainty'), raw):
         if t is not None:
             assert rel_err(t, z['raw_' + nm]) < 1e-5, nm

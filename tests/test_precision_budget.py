@@ -16,7 +16,8 @@ from helpers import load_npz, fixture_state_dict
 def _core_with_fp16_heads(x, sd, arch, round_act=True, round_w=True):
     orig = orc.read_out
 
-    def ro(xx, sd_, p, final=None):
+    def ro(xx, sd_, p, final=None, stride=1):
+        assert stride == 1
         k = sd_[f'{p}.block.0.weight'].shape[-1]
         g = sd_[f'{p}.block.1.weight'] / torch.sqrt(sd_[f'{p}.block.1.running_var'] + 1e-5)
         w = sd_[f'{p}.block.0.weight'] * g[:, None, None, None]
