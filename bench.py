@@ -467,6 +467,15 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()
     peaks = measured_peaks()
+    c5 = None
+    if world == 1 and args.workload in ('auto', 'c3') and not args.quick:
+        # the decode micro-benchmark is a kernel timed alone: run it before the long tensor-core loops pull the clocks
+        # down to the power cap (measured: 0.29 ms on an idle GPU, 0.45 ms right after the C2 / C3 legs)
+        try:
+            c5 = config_c5(dev, peaks)
+        except Exception as e:
+            c5 = dict(error=f'{type(e).__name__}: {e}'[:300])
+        torch.cuda.empty_cache()
     model, sd = make_model(ARCH, args.precision, dev)
 
     def barrier():
@@ -598,9 +607,9 @@ def run_b200(args):
                                                 'from the reference, outside the 1e-3 gate')
                 del fast
             try:
-                line['configs'] = dict(C2=config_c2(dev, peaks), C5=config_c5(dev, peaks))
+                line['configs'] = dict(C2=config_c2(dev, peaks), C5=c5)
             except Exception as e:
-                line['configs'] = dict(error=f'{type(e).__name__}: {e}'[:300])
+                line['configs'] = dict(error=f'{type(e).__name__}: {e}'[:300], C5=c5)
         if world == 1 and not args.no_cpu_baseline:
             sd_cpu = {k: v.cpu() for k, v in sd.items()}
             v, cms, cores, kept = cpu_reference_tiles_per_sec(sd_cpu, 3, 1)
