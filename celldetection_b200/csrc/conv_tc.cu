@@ -85,12 +85,14 @@ struct ConvTcParams {
   float acc_scale;                   // accumulator scale applied first in every epilogue (1/S of the F16F8 weight packing)
   float out_lo_scale, out_hi8_scale; // F16F8 output: lo8 = e4m3((v - hi) * out_lo_scale), hi8 = e4m3(hi * out_hi8_scale)
   float res_lo_inv;                  // F16F8 residual: value = hi + lo8 * res_lo_inv
+  int dbg_epi;              // experiment switch CPN_DBG_EPI=1: the coalesced epilogue skips its global loads / stores
   int coalesce;             // conv_tc_kernel: smem-staged, line-coalesced residual loads / output stores (epilogue_coalesced)
   int rotate;               // start each CTA's K loop at a different (tap, block): de-correlates the L2 reads of the shared weights   // 1: the patch is ONE box {64, PW, PH, 1} with SWIZZLE_128B (128-byte pixel rows)
 };
 
 struct ConvTcPlan {
   ConvTcParams p;
+  int pair;               // 1: conv_pair_kernel (CTA pairs, tcgen05 cta_group::2, M = 256 per instruction)
   int proj_smem_bytes;
   int msub;
   int bn;
@@ -287,7 +289,7 @@ __device__ __forceinline__ int split_pass_order(int i, int lofirst) { return lof
 // of a different spatial size is read through the nearest-neighbour index map (torchvision FPN top-down path).
 __device__ __forceinline__ const __half* residual_row(const ConvTcParams& p, const int img, const int y, const int x,
                                                       const int n0) {
-  if (!p.res || y >= p.Ho || x >= p.Wo) return nullptr;
+  if (!p.res || y >= p.Ho || x >= p.Wo || img >= p.N) return nullptr;
   const int ry = (p.res_h == p.Ho) ? y : (int)(((long long)y * p.res_h) / p.Ho);
   const int rx = (p.res_w == p.Wo) ? x : (int)(((long long)x * p.res_w) / p.Wo);
   return p.res + (((long long)img * p.res_h + ry) * p.res_w + rx) * p.res_pitch + n0;
@@ -311,7 +313,7 @@ template <int BN, bool PF>
 __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint32_t taddr, const int img, const int y,
                                               const int x, const int n_tile, const int n0, const int half,
                                               const float* proj_w, const ResChunk* rfirst = nullptr) {
-  const bool valid = (y < p.Ho) && (x < p.Wo);
+  const bool valid = (y < p.Ho) && (x < p.Wo) && (img < p.N);
   __half* op = p.out + (((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0;
   const __half* rp = residual_row(p, img, y, x, n0);
   if (p.nproj > 0) {
@@ -460,7 +462,7 @@ __device__ __forceinline__ void coal_rows(const ConvTcParams& p, const int img, 
   for (int i = 0; i < 4; ++i) {
     const int r = quad * 32 + i * 8 + (lane >> 2);
     const int y = ty0 + (r >> WLOG2), x = tx0 + (r & ((1 << WLOG2) - 1));
-    const bool ok = y < p.Ho && x < p.Wo;
+    const bool ok = y < p.Ho && x < p.Wo && img < p.N;     // (img == N: the phantom second tile of an odd CTA pair)
     c.okmask |= ok ? (1u << i) : 0u;
     c.ooff[i] = ok ? (uint32_t)((((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0 + (lane & 3) * 8) : 0u;
     c.roff[i] = 0u;
@@ -475,6 +477,7 @@ __device__ __forceinline__ void coal_rows(const ConvTcParams& p, const int img, 
 // lo_delta: 0 for the hi (or only) half of the residual, p.res_lo for the lo half of a split (CPN_DT_F16X2) tensor
 __device__ __forceinline__ void coal_load_res(const ConvTcParams& p, const CoalRows& c, const int ch, const int lo_delta,
                                               uint4 (&rg)[4]) {
+  if (p.dbg_epi) return;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if (c.okmask & (1u << i)) rg[i] = __ldg(reinterpret_cast<const uint4*>(p.res + c.roff[i] + lo_delta + ch * 32));
@@ -572,6 +575,7 @@ __device__ __forceinline__ void epilogue_coalesced(const ConvTcParams& p, const 
     }
 
     __syncwarp();                                                    // every lane has read its residual row(s)
+    if (p.dbg_epi) continue;
     stg_put_o(stg, lane, rr);
     __syncwarp();
     stg_store_t(stg, lane, c, p.out + ch * 32);
@@ -794,6 +798,291 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair kernel (tcgen05 cta_group::2): the 1x1 layers of the encoder / decoder with C_out % 256 == 0.
+// Hypothesis tested in round 2: the 1x1 layers (tensor pipe 41-44 % active, DRAM 23 %, L2 28 % in ncu) are bound by operand
+// delivery -- every CTA of conv_tc_kernel<256> pulls 16 KB of activations + 32 KB of weights per K block.  Result: NOT
+// confirmed.  This kernel moves a third fewer bytes per CTA and is 3 % (ncu, cold) to 20 % (back-to-back launches) slower,
+// so it is opt-in (CPN_PAIR=1) and kept as a verified cta_group::2 building block.  Two CTAs of a cluster (the two SMs of a
+// TPC) share ONE 256 x 256 accumulator tile: each loads the activations of its own 128 pixels and only HALF of the weight tile
+// (128 of the 256 output channels), the leader issues M = 256 instructions that read both halves, and each CTA finds its
+// 128 rows x 256 columns of the result in its own tensor memory: 32 KB per CTA and K block (-33 %), six stages instead of four.
+//   barriers  full[stage]   leader only; expect_tx covers the bytes of BOTH CTAs (their TMA loads signal the leader's barrier)
+//             empty[stage]  one per CTA, released by the leader's multicast commit
+//             tfull[acc]    one per CTA, multicast commit after the tile's last K block
+//             tempty[acc]   leader only; the epilogue warps of both CTAs arrive (the peer through its cluster address)
+// Tiles: pair tile = (two consecutive M tiles, one N tile), N fastest; CTA rank r owns M tile 2 * mp + r (an odd tile count
+// leaves a phantom tile: its TMA boxes are out of bounds = zero filled, its epilogue stores nothing).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: the data lands in the executing CTA's shared memory, the bytes are counted on `bar` (a
+// shared::cluster address: the leader's barrier)
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <bool F8>
+__device__ __forceinline__ void umma_pair_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  if (F8) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs once the pair's previously issued MMAs have retired
+__device__ __forceinline__ void umma_commit_pair_elect(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      ".reg .b16 m;\n"
+      "mov.b16 m, 3;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+      "}\n" ::"r"(bar)
+      : "memory");
+}
+
+constexpr int TCP_BN = 256;                         // N of the pair's accumulator tile
+constexpr uint32_t TCP_A_BYTES = TC_BM * TC_BK * 2;           // 16 KB: this CTA's 128 pixels x 64 channels
+constexpr uint32_t TCP_B_BYTES = (TCP_BN / 2) * TC_BK * 2;    // 16 KB: this CTA's half of the weight tile
+constexpr uint32_t TCP_STAGE_BYTES = TCP_A_BYTES + TCP_B_BYTES;
+
+template <bool COAL>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_pair_kernel(const __grid_constant__ ConvTcParams p, int stages) {
+  constexpr int BN = TCP_BN;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr int MAX_STAGES = 8;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int nk = p.R * p.S * p.cblocks;
+  uint8_t* tail = smem_raw + ((smem_base - smem_u32(smem_raw)) + stages * TCP_STAGE_BYTES);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA[0]);
+    prefetch_tmap(&p.tmB);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(smem_u32(&bar_full[i]), 1);
+      mbar_init(smem_u32(&bar_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_tfull[i]), 1);
+      mbar_init(smem_u32(&bar_tempty[i]), 2 * TC_EPI_WARPS);      // the epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {      // the same warp of both CTAs allocates the pair's tensor memory
+    tmem_alloc_pair(smem_u32(&tmem_base_slot), TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const long long m_tiles = (long long)p.N * tiles_per_img;
+  const long long pair_tiles = ((m_tiles + 1) >> 1) * p.tiles_n;
+  const long long first = blockIdx.x >> 1, step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = first; tile < pair_tiles; tile += step) {
+        const int n_tile = (int)(tile % p.tiles_n);
+        const long long m_tile = (tile / p.tiles_n) * 2 + rank;
+        const int img = (int)(m_tile / tiles_per_img);                 // == N for the phantom tile: out of bounds, zeros
+        const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
+        const int y0 = (t_in / p.tiles_x) * TC_BH, x0 = (t_in % p.tiles_x) * TC_BW;
+        const int n0 = n_tile * BN;
+        for (int it = 0; it < nk; ++it) {
+          int tap = it / p.cblocks, cb = it - tap * p.cblocks;
+          int a_ch = cb * TC_BK;
+          if (p.split == 1) {
+            const int cbl = p.cblocks / 3, per_pass = p.R * p.S * cbl;
+            const int pi = it / per_pass, rem = it - pi * per_pass;
+            const int pass = split_pass_order(pi, p.split_lofirst);
+            tap = rem / cbl;
+            const int c = rem - tap * cbl;
+            cb = pass * cbl + c;
+            a_ch = c * TC_BK + (pass == 1 ? p.a_lo : 0);
+          } else if (p.split == 2) {
+            const int cbl = p.cblocks / 2, per_pass = p.R * p.S * cbl;
+            const int pi = it / per_pass, rem = it - pi * per_pass;
+            tap = rem / cbl;
+            const int c = rem - tap * cbl;
+            cb = pi * cbl + c;
+            a_ch = c * TC_BK + (pi == 0 ? p.a_lo : 0);
+          }
+          const int r = tap / p.S, s = tap - r * p.S;
+          int qy = r - p.pad, qx = s - p.pad, map = 0;
+          if (p.stride == 2) {
+            const int py = qy & 1, px = qx & 1;
+            map = py * 2 + px;
+            qy = (qy - py) >> 1;
+            qx = (qx - px) >> 1;
+          }
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+          const uint32_t full = mapa_u32(smem_u32(&bar_full[stage]), 0);       // the leader's barrier
+          const uint32_t sa = smem_base + stage * TCP_STAGE_BYTES, sb = sa + TCP_A_BYTES;
+          if (leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * TCP_STAGE_BYTES);
+          tma_load_4d_pair(sa, &p.tmA[map], full, a_ch, x0 + qx, y0 + qy, img);
+          tma_load_3d_pair(sb, &p.tmB, full, cb * TC_BK, n0 + (int)rank * (BN / 2), tap);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * TC_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long tile = first; tile < pair_tiles; tile += step) {
+        mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * TCP_STAGE_BYTES, sb = sa + TCP_A_BYTES;
+          const uint64_t da = make_sw128_kmajor_desc(sa), db = make_sw128_kmajor_desc(sb);
+          if (p.split == 2 && kb < (nk >> 1)) {
+            umma_pair_elect<true>(d_tmem, da, db, idesc, (uint32_t)(kb != 0));
+#pragma unroll
+            for (int k = 1; k < TC_BK / 16; ++k) umma_pair_elect<true>(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+          } else {
+            umma_pair_elect<false>(d_tmem, da, db, idesc, (uint32_t)(kb != 0));
+#pragma unroll
+            for (int k = 1; k < TC_BK / 16; ++k) umma_pair_elect<false>(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+          }
+          umma_commit_pair_elect(smem_u32(&bar_empty[stage]));   // frees this stage in both CTAs
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair_elect(smem_u32(&bar_tfull[acc]));       // accumulator complete -> both epilogues
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================ epilogue (8 warps per CTA) ================================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int py = row / TC_BW, px = row % TC_BW;
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&bar_tempty[0]), 0), tempty_leader1 = mapa_u32(smem_u32(&bar_tempty[1]), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = first; tile < pair_tiles; tile += step) {
+      const int n_tile = (int)(tile % p.tiles_n);
+      const long long m_tile = (tile / p.tiles_n) * 2 + rank;
+      const int img = (int)(m_tile / tiles_per_img);
+      const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
+      const int ty0 = (t_in / p.tiles_x) * TC_BH, tx0 = (t_in % p.tiles_x) * TC_BW;
+      const int n0 = n_tile * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * BN;
+      if (COAL) {
+        CoalRows cr;
+        coal_rows<4>(p, img, ty0, tx0, n0, quad, lane, cr);
+        uint4 rg[4], rgl[4];
+        if (p.res) {
+          coal_load_res(p, cr, half, 0, rg);
+          if (p.split) coal_load_res(p, cr, half, p.res_lo, rgl);
+        }
+        mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
+        tc_fence_after();
+        epilogue_coalesced<BN>(p, taddr, cr, n0, half, lane, reinterpret_cast<uint4*>(tail) + (warp - 2) * 128, rg, rgl);
+      } else {
+        ResChunk rfirst;
+        {
+          const __half* rp0 = residual_row(p, img, ty0 + py, tx0 + px, n0);
+          if (rp0) load_res_chunk(rp0, half, rfirst);
+        }
+        mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
+        tc_fence_after();
+        epilogue_rows<BN, true>(p, taddr, img, ty0 + py, tx0 + px, n_tile, n0, half, nullptr, &rfirst);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // nobody leaves while the peer may still read its shared memory or signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Halo kernel: stride-1 kxk convolutions with operand reuse across filter taps.
@@ -1123,7 +1412,15 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   ConvTcPlan* pl = new ConvTcPlan();
   ConvTcParams& p = pl->p;
   memset(&p, 0, sizeof(p));
-  const int bn = pick_bn(op.dst.c, op.slab_mode);
+  int bn = pick_bn(op.dst.c, op.slab_mode);
+  {
+    // experiment switch: N tile of the 1x1 layers (CPN_BN_1X1=128|64); smaller tiles = more pipeline stages in flight
+    static int bn1x1_env = -1;
+    if (bn1x1_env < 0) { const char* e = getenv("CPN_BN_1X1"); bn1x1_env = e ? atoi(e) : 0; }
+    if (bn1x1_env > 0 && op.r * op.s == 1 && !op.slab_mode && op.fuse_next == 0 && op.dst.c % bn1x1_env == 0 &&
+        (bn1x1_env == 64 || bn1x1_env == 128 || bn1x1_env == 256))
+      bn = bn1x1_env;
+  }
   pl->bn = bn;
   // --- A maps: (C, W, H, N) with box {64, 16, 8, 1}; stride 2 -> four parity views
   const int nmaps = op.stride == 2 ? 4 : 1;
@@ -1218,6 +1515,11 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   const int stage_bytes = TC_BM * TC_BK * 2 + bn * TC_BK * 2;
   pl->stages = TC_SMEM_BUDGET / stage_bytes;
   if (pl->stages > 8) pl->stages = 8;
+  {
+    static int stages_env = -1;   // experiment switch: cap the operand ring (CPN_TC_STAGES)
+    if (stages_env < 0) { const char* e = getenv("CPN_TC_STAGES"); stages_env = e ? atoi(e) : 0; }
+    if (stages_env >= 2 && stages_env < pl->stages) pl->stages = stages_env;
+  }
   pl->proj_smem_bytes = 0;
   {
     // line-coalesced epilogue (CPN_COALESCE=0 disables): single-precision-storage layers whose tensors can be
@@ -1228,6 +1530,9 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
     const long long res_elems = op.res.n ? (long long)op.res.n * op.res.h * op.res.w * op.res.pitch : 0;
     static int coal_halo_env = -1;   // CPN_COALESCE_HALO=0: keep the direct epilogue in conv_halo_kernel only (A/B switch)
     if (coal_halo_env < 0) { const char* e = getenv("CPN_COALESCE_HALO"); coal_halo_env = (e && atoi(e) == 0) ? 0 : 1; }
+    static int dbg_epi_env = -1;
+    if (dbg_epi_env < 0) { const char* e = getenv("CPN_DBG_EPI"); dbg_epi_env = (e && atoi(e) == 1) ? 1 : 0; }
+    p.dbg_epi = dbg_epi_env;
     static int coal_split_env = -1;  // CPN_COALESCE_SPLIT=0: direct epilogue for the split-precision engine (A/B switch)
     if (coal_split_env < 0) { const char* e = getenv("CPN_COALESCE_SPLIT"); coal_split_env = (e && atoi(e) == 0) ? 0 : 1; }
     p.coalesce = (coal_env && (coal_split_env || !split) && (coal_halo_env || !p.halo) && out_elems < (1ll << 31) &&
@@ -1237,7 +1542,56 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   if (p.halo) pl->smem_bytes = p.nb_stages * bn * TC_BK * 2 + 2 * 8 * p.plane_stride + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
   const long long sms = sm_count();
   pl->grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  {
+    // CTA-pair kernel for the 1x1 layers with 256-wide N tiles: opt-in (CPN_PAIR=1).  Measured on B200 (profiles/
+    // r02_summary.md): bit-identical results, but 3-20 % SLOWER than conv_tc_kernel<256> per layer although it moves a
+    // third fewer operand bytes per CTA -- these layers are not bound by operand bytes (see the kernel's header).
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("CPN_PAIR"); pair_env = (e && atoi(e) == 1) ? 1 : 0; }
+    const long long m_tiles = (long long)op.dst.n * p.tiles_x * p.tiles_y;
+    pl->pair = 0;
+    if (pair_env && !p.halo && bn == TCP_BN && op.r * op.s == 1 && op.fuse_next == 0 && m_tiles >= 2 && sms >= 2) {
+      {   // each CTA of a pair loads HALF of the weight tile: box of 128 output channels
+        const cuuint64_t kw = (cuuint64_t)op.kslab * npass;
+        cuuint64_t dims[3] = {kw, (cuuint64_t)op.dst.c, (cuuint64_t)(op.r * op.s)};
+        cuuint64_t strides[2] = {kw * 2, kw * op.dst.c * 2};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)(TCP_BN / 2), 1};
+        if (encode_map(&p.tmB, const_cast<void*>(wgt), 3, dims, strides, box)) { delete pl; return 1; }
+      }
+      pl->pair = 1;
+      pl->stages = TC_SMEM_BUDGET / (int)TCP_STAGE_BYTES;
+      if (pl->stages > 8) pl->stages = 8;
+      pl->smem_bytes = pl->stages * (int)TCP_STAGE_BYTES + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
+      const long long pair_tiles = ((m_tiles + 1) / 2) * p.tiles_n;
+      const long long pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+      pl->grid = (int)(2 * pairs);
+    }
+  }
   *out = pl;
+  return 0;
+}
+
+template <bool COAL>
+static int launch_pair2(const ConvTcPlan* pl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv_pair_kernel<COAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TC_SMEM_BUDGET + 1024 + TC_PROJ_SMEM_MAX));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)pl->grid, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)pl->smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CPN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<COAL>, pl->p, pl->stages));
+  CPN_CHECK_LAUNCH();
   return 0;
 }
 
@@ -1278,6 +1632,7 @@ static int launch_halo(const ConvTcPlan* pl, cudaStream_t st) {
 }
 
 int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t st) {
+  if (pl->pair) return pl->p.coalesce ? launch_pair2<true>(pl, st) : launch_pair2<false>(pl, st);
   if (pl->p.halo) {
     if (pl->bn == 64 && pl->msub == 2) return launch_halo<64, 2>(pl, st);
     if (pl->bn == 128 && pl->msub == 2) return launch_halo<128, 2>(pl, st);

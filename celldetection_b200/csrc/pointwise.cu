@@ -390,7 +390,71 @@ __global__ void maxpool_split_kernel(const __half* __restrict__ src, __half* __r
   }
 }
 
+// CPN_DT_F16F8, C % 8 == 0: one thread owns 8 consecutive channels of one output pixel -- per window pixel one 16-byte
+// load of the hi halves and one 8-byte load of the lo8 bytes (the hi8 bytes are fetched only for the eight winners)
+__global__ void __launch_bounds__(256) maxpool_f16f8_v8_kernel(const __half* __restrict__ src, __half* __restrict__ dst,
+                                                               int N, int H, int W, int c8, int sp, int slo, int Ho, int Wo,
+                                                               int dp, int dlo, int k, int stride, int pad, float lo_inv) {
+  const long long total = (long long)N * Ho * Wo * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8) * 8;
+    long long pix = i / c8;
+    const int ox = (int)(pix % Wo);
+    pix /= Wo;
+    const int oy = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    float best[8];
+    uint16_t bh[8];
+    uint8_t bl[8];
+    int bpos[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bh[j] = 0; bl[j] = 0; bpos[j] = -1; }
+    for (int dy = 0; dy < k; ++dy) {
+      const int iy = oy * stride - pad + dy;
+      if (iy < 0 || iy >= H) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        const int ix = ox * stride - pad + dx;
+        if (ix < 0 || ix >= W) continue;
+        const __half* q = src + (((long long)n * H + iy) * W + ix) * sp;
+        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(q + c));
+        const uint2 lv = __ldg(reinterpret_cast<const uint2*>(f8_block(q, slo, c)));
+        const uint16_t* hh = reinterpret_cast<const uint16_t*>(&hv);
+        const uint8_t* ll = reinterpret_cast<const uint8_t*>(&lv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = __half2float(__ushort_as_half(hh[j])) + e4m3_to_f32(ll[j]) * lo_inv;
+          if (v > best[j]) { best[j] = v; bh[j] = hh[j]; bl[j] = ll[j]; bpos[j] = iy * W + ix; }
+        }
+      }
+    }
+    __half* o = dst + (((long long)n * Ho + oy) * Wo + ox) * dp;
+    __align__(16) uint16_t oh[8];
+    __align__(8) uint8_t ol[8], o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      oh[j] = bh[j]; ol[j] = bl[j];
+      o8[j] = bpos[j] >= 0 ? f8_block(src + ((long long)n * H * W + bpos[j]) * sp, slo, c + j)[32] : (uint8_t)0;
+    }
+    *reinterpret_cast<uint4*>(o + c) = *reinterpret_cast<const uint4*>(oh);
+    uint8_t* q8 = f8_block(o, dlo, c);
+    *reinterpret_cast<uint2*>(q8) = *reinterpret_cast<const uint2*>(ol);
+    *reinterpret_cast<uint2*>(q8 + 32) = *reinterpret_cast<const uint2*>(o8);
+  }
+}
+
 int maxpool_launch(const cpn_op_t& op, const void* src, void* dst, cudaStream_t st) {
+  if (op.src.dtype == CPN_DT_F16F8 && op.dst.dtype == CPN_DT_F16F8 && op.src.c == op.dst.c && op.src.c % 8 == 0 &&
+      op.src.fp8_exp == op.dst.fp8_exp && op.src.pitch % 8 == 0 && op.dst.pitch % 8 == 0 && op.src.lo_delta % 32 == 0 &&
+      op.dst.lo_delta % 32 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0 &&
+      (long long)op.src.h * op.src.w < (1ll << 31)) {
+    const long long total = (long long)op.dst.n * op.dst.h * op.dst.w * (op.dst.c / 8);
+    maxpool_f16f8_v8_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __half*)src, (__half*)dst, op.src.n, op.src.h,
+                                                                 op.src.w, op.src.c / 8, op.src.pitch, op.src.lo_delta,
+                                                                 op.dst.h, op.dst.w, op.dst.pitch, op.dst.lo_delta, op.r,
+                                                                 op.stride, op.pad, lo_fmt(op.src).lo_inv);
+    CPN_CHECK_LAUNCH();
+    return 0;
+  }
   if (dtype_has_lo(op.src.dtype)) {
     CPN_REQUIRE(op.dst.dtype == op.src.dtype && op.src.c == op.dst.c && op.src.fp8_exp == op.dst.fp8_exp,
                 "maxpool: split dtype/channel/scale mismatch");

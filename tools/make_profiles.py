@@ -56,7 +56,8 @@ def ncu_raw(rep, keys):
     return res
 
 
-KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+KEYS = ['gpu__time_duration.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_uniform.sum', 'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__t_sectors_op_read.sum', 'lts__t_sectors_op_write.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic', 'sm__warps_active.avg.pct_of_peak_sustained_active',
@@ -77,7 +78,8 @@ def main():
                 with open(os.path.join(PROF, f'{TAG}_{name}.json'), 'w') as f:
                     json.dump(res, f, indent=1)
     # one `ncu --set full` capture per kernel class (tools/gpu_r01b.sh): compact table of the roofline-relevant metrics
-    for rep, name in (('prof_convs.ncu-rep', 'ncu_conv_classes'), ('prof_post.ncu-rep', 'ncu_post_chain')):
+    for rep, name in (('prof_convs.ncu-rep', 'ncu_conv_classes'), ('prof_convs_f8.ncu-rep', 'ncu_conv_classes_fp16f8'),
+                      ('prof_post.ncu-rep', 'ncu_post_chain')):
         path = os.path.join(OUT, rep)
         if not os.path.exists(path):
             continue
