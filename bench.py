@@ -394,6 +394,28 @@ def quick_rate(model, xs, steps=5, warmup=2):
     return ms, int(sum(counts))
 
 
+def batch1_latency(model, x1):
+    """Device-synchronised latency of ``model(x)`` for ONE 3x512x512 tile (median of 20), launched kernel by kernel and as a
+    CUDA-graph replay of the plan."""
+    out = {}
+    for name, flag in (('eager_ms', False), ('cuda_graph_ms', True)):
+        model.cuda_graph = flag
+        for _ in range(3):
+            model(x1)
+        ts = []
+        for _ in range(20):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            model(x1)
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts.sort()
+        out[name] = ts[len(ts) // 2]
+    model.cuda_graph = False
+    out['note'] = 'one tile, host wall clock around model(x) incl. the post-head chain and its host read-backs'
+    return out
+
+
 def config_c2(dev, peaks):
     """BASELINE configs[1]: CpnResNet18FPN, batch 32x3x512x512, headline engine (side leg, a few steps)."""
     from celldetection_b200.models.graph import conv_flops
@@ -598,6 +620,10 @@ def run_b200(args):
         line['roofline'] = heads_roofline(model, xs[0], args.precision)
         line['parity'] = measured_parity(args.precision, dev)
         if world == 1 and workload == 'c3' and not args.quick:
+            try:
+                line['latency_batch1'] = batch1_latency(model, xs[0][:1].contiguous())
+            except Exception as e:
+                line['latency_batch1'] = dict(error=f'{type(e).__name__}: {e}'[:300])
             if args.precision == HEADLINE:
                 fast = sibling(ARCH, 'fp16', sd, dev)
                 fms, fkept = quick_rate(fast, xs)

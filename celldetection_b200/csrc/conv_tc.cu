@@ -85,6 +85,7 @@ struct ConvTcParams {
   float acc_scale;                   // accumulator scale applied first in every epilogue (1/S of the F16F8 weight packing)
   float out_lo_scale, out_hi8_scale; // F16F8 output: lo8 = e4m3((v - hi) * out_lo_scale), hi8 = e4m3(hi * out_hi8_scale)
   float res_lo_inv;                  // F16F8 residual: value = hi + lo8 * res_lo_inv
+  int tap2;                 // conv_tap2_kernel: 64-wide layers, two horizontally adjacent filter taps per N = 128 instruction
   int dbg_epi;              // experiment switch CPN_DBG_EPI=1: the coalesced epilogue skips its global loads / stores
   int coalesce;             // conv_tc_kernel: smem-staged, line-coalesced residual loads / output stores (epilogue_coalesced)
   int rotate;               // start each CTA's K loop at a different (tap, block): de-correlates the L2 reads of the shared weights   // 1: the patch is ONE box {64, PW, PH, 1} with SWIZZLE_128B (128-byte pixel rows)
@@ -229,6 +230,42 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// conv_tap2_kernel: an accumulator of sub-tile j holds 128 columns per pixel row -- [0, 64) the sums of the taps issued in
+// the "lo" half, [64, 128) the sums of their right-hand neighbour taps, which belong to the output pixel one to the LEFT
+// (see the kernel's header).  Output (y, x) = lo(y, x) + hi(y, x + 1): lane + 1 inside an 8-pixel row group, lane - 7 of
+// the NEXT sub-tile's accumulator for x == 7.  Returns the 32 combined fp32 values of chunk `ch` (wait included).
+__device__ __forceinline__ void tap2_combine32(const uint32_t taddr, const int ch, const int j, const int lane,
+                                               uint32_t (&v)[32]) {
+  const bool inner = (lane & 7) < 7;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t lo[16], hi[16], hn[16];
+    tmem_ld16(taddr + ch * 32 + h * 16, lo);
+    tmem_ld16(taddr + 64 + ch * 32 + h * 16, hi);
+    if (j == 0) {
+      tmem_ld16(taddr + 128 + 64 + ch * 32 + h * 16, hn);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) hn[c] = 0u;
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float r1 = __shfl_down_sync(0xffffffffu, __uint_as_float(hi[c]), 1);
+      const float r2 = __shfl_sync(0xffffffffu, __uint_as_float(hn[c]), lane & ~7);
+      v[h * 16 + c] = __float_as_uint(__uint_as_float(lo[c]) + (inner ? r1 : r2));
+    }
+  }
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
 // LBO >> 4 in [16,30) (= 1, unused for swizzled K-major), SBO >> 4 in [32,46) (= 1024 B between 8-row groups),
@@ -309,11 +346,12 @@ __device__ __forceinline__ void load_res_chunk(const __half* rp, const int ch, R
 // the next TMEM load and its wait.  Without it the epilogue of a 1x1 + residual layer, whose mainloop is only 4-16 K
 // blocks long, exposed one global-memory latency per chunk and ran longer than the mainloop (ncu: 72.8 us with the
 // residual vs 49.6 us without, same 1024 -> 1024 shape).
-template <int BN, bool PF>
+template <int BN, bool PF, bool TAP2 = false>
 __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint32_t taddr, const int img, const int y,
                                               const int x, const int n_tile, const int n0, const int half,
-                                              const float* proj_w, const ResChunk* rfirst = nullptr) {
-  const bool valid = (y < p.Ho) && (x < p.Wo) && (img < p.N);
+                                              const float* proj_w, const ResChunk* rfirst = nullptr, const int tapj = 0,
+                                              const int lane = 0, const bool keep = true) {
+  const bool valid = (y < p.Ho) && (x < p.Wo) && (img < p.N) && keep;
   __half* op = p.out + (((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0;
   const __half* rp = residual_row(p, img, y, x, n0);
   if (p.nproj > 0) {
@@ -328,8 +366,12 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
       uint32_t v[32];
-      tmem_ld32(taddr + ch * 32, v);
-      tmem_ld_wait();
+      if (TAP2) {
+        tap2_combine32(taddr, ch, tapj, lane, v);
+      } else {
+        tmem_ld32(taddr + ch * 32, v);
+        tmem_ld_wait();
+      }
       float f[32];
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
 #pragma unroll
@@ -380,9 +422,14 @@ __device__ __forceinline__ void epilogue_rows(const ConvTcParams& p, const uint3
 #pragma unroll 1
   for (int ch = half; ch < BN / 32; ch += 2) {
     uint32_t v[32];
-    tmem_ld32(taddr + ch * 32, v);
-    if (!PF && rp) load_res_chunk(rp, ch, rc);
-    tmem_ld_wait();
+    if (TAP2) {
+      if (!PF && rp) load_res_chunk(rp, ch, rc);
+      tap2_combine32(taddr, ch, tapj, lane, v);
+    } else {
+      tmem_ld32(taddr + ch * 32, v);
+      if (!PF && rp) load_res_chunk(rp, ch, rc);
+      tmem_ld_wait();
+    }
     if (valid) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
       uint4 packed[4], packed_lo[4];
@@ -456,13 +503,14 @@ struct CoalRows {
 // WLOG2: log2 of the accumulator's pixel-tile width (row r of the accumulator is pixel (r >> WLOG2, r & (2^WLOG2 - 1)))
 template <int WLOG2>
 __device__ __forceinline__ void coal_rows(const ConvTcParams& p, const int img, const int ty0, const int tx0,
-                                          const int n0, const int quad, const int lane, CoalRows& c) {
+                                          const int n0, const int quad, const int lane, CoalRows& c,
+                                          const int x_limit = 0x7fffffff) {
   c.okmask = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = quad * 32 + i * 8 + (lane >> 2);
     const int y = ty0 + (r >> WLOG2), x = tx0 + (r & ((1 << WLOG2) - 1));
-    const bool ok = y < p.Ho && x < p.Wo && img < p.N;     // (img == N: the phantom second tile of an odd CTA pair)
+    const bool ok = y < p.Ho && x < p.Wo && x < x_limit && img < p.N;   // (img == N: phantom tile of an odd CTA pair)
     c.okmask |= ok ? (1u << i) : 0u;
     c.ooff[i] = ok ? (uint32_t)((((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0 + (lane & 3) * 8) : 0u;
     c.roff[i] = 0u;
@@ -507,17 +555,18 @@ __device__ __forceinline__ void stg_store_t(const uint4* stg, const int lane, co
 // rg / rgl: residual (hi / lo half) of this warp's first chunk in the transposed role, requested by the caller.
 // Split tensors (p.split): residual = hi + lo, the result is re-split into hi = fp16(v), lo = fp16(v - hi), and both
 // halves cross the staging tile one after the other.
-template <int BN>
+template <int BN, bool TAP2 = false>
 __device__ __forceinline__ void epilogue_coalesced(const ConvTcParams& p, const uint32_t taddr, const CoalRows& c,
                                                    const int n0, const int half, const int lane, uint4* stg,
-                                                   uint4 (&rg)[4], uint4 (&rgl)[4]) {
+                                                   uint4 (&rg)[4], uint4 (&rgl)[4], const int tapj = 0) {
   const bool has_res = p.res != nullptr;
   const bool split = p.split != 0;
   const bool f8 = p.split == 2;
 #pragma unroll 1
   for (int ch = half; ch < BN / 32; ch += 2) {
     uint32_t v[32];
-    tmem_ld32(taddr + ch * 32, v);
+    if (TAP2) tap2_combine32(taddr, ch, tapj, lane, v);
+    else tmem_ld32(taddr + ch * 32, v);
     uint4 rr[4], rl[4];
     if (has_res) {
       stg_put_t(stg, lane, rg);
@@ -534,7 +583,7 @@ __device__ __forceinline__ void epilogue_coalesced(const ConvTcParams& p, const 
         if (split) coal_load_res(p, c, ch + 2, p.res_lo, rgl);
       }
     }
-    tmem_ld_wait();
+    if (!TAP2) tmem_ld_wait();
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
     uint32_t* pk = reinterpret_cast<uint32_t*>(rr);                  // results overwrite the residual registers in place
     uint32_t* pl = reinterpret_cast<uint32_t*>(rl);
@@ -1348,6 +1397,235 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Tap-pair kernel: the 64-wide stride-1 kxk layers (7x7 refinement head 64 -> 64 @512^2, the 3x3 64 -> 64 decoder convs,
+// the grouped 3x3 convs whose N tile is one 64-channel slab).
+// An M128 x N64 x K16 instruction occupies the tensor pipe for 32 cycles but reads 4 KB (A) + 2 KB (B) of shared memory,
+// 48 cycles at 128 B/cycle: conv_halo_kernel<64, 2> tops out at ~2/3 of the pipe (ncu: 38-45 % active).  Here ONE
+// instruction handles TWO horizontally adjacent taps (r, s) and (r, s + 1) over the same activation window: B stacks their
+// weight tiles (rows 0-63 / 64-127, two consecutive taps of the K-major weight tensor = one 16 KB ring slot), N = 128,
+// 4 KB + 4 KB per 64 cycles.  Columns 64-127 of the accumulator then hold A(p + (r, s)) W(r, s + 1): the contribution of
+// tap (r, s + 1) to the output pixel one to the LEFT of p, so the epilogue adds lo(y, x) + hi(y, x + 1) (tap2_combine32:
+// a lane shuffle, across the two sub-tiles at x = 7).  The last column of a 16-pixel-wide tile has no right neighbour in
+// the tile: tiles advance by 15 columns and column 15 is recomputed by the next tile (6 % extra work).  An odd S leaves
+// one single tap per filter row, issued as an N = 64 instruction into the lo columns.  k = 7: 4 instead of 7 issue slots
+// per row, k = 3: 2 instead of 3.  Same warp roles and barrier protocol as conv_halo_kernel<64, 2> (two MMA issuers, one
+// per sub-tile); TMEM: 2 accumulator sets x 2 sub-tiles x 128 columns = 512.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TAP2_TW = 15;      // output columns per tile (of 16 accumulator columns)
+
+template <bool COAL>
+__global__ void __launch_bounds__(TCH_THREADS, 1) conv_tap2_kernel(const __grid_constant__ ConvTcParams p) {
+  constexpr int BN = 64, ACC = 128, MSUB = 2;
+  constexpr uint32_t SLOT_BYTES = 2 * BN * TC_BK * 2;    // two taps
+  constexpr uint32_t TAP_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t TMEM_COLS = 2 * MSUB * ACC;
+  constexpr int MAX_NB = 8;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bar_bfull[MAX_NB];
+  __shared__ __align__(8) uint64_t bar_bempty[MAX_NB];
+  __shared__ __align__(8) uint64_t bar_afull[2];
+  __shared__ __align__(8) uint64_t bar_aempty[2];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = p.nb_stages;
+  const uint32_t patch_bytes = 8u * (uint32_t)p.plane_stride;
+  const uint32_t a_base = smem_base + nb * SLOT_BYTES;
+  const uint32_t a_tx = 8u * (uint32_t)(p.ph * p.pw * 16);
+  uint8_t* tail = smem_raw + ((a_base - smem_u32(smem_raw)) + 2 * patch_bytes);
+  float* proj_w = reinterpret_cast<float*>(tail);
+  if (!COAL && p.nproj > 0) {
+    int off = 0;
+    for (int h = 0; h < p.nproj; ++h) {
+      const int nw = p.proj[h].cout * BN;
+      for (int i = threadIdx.x; i < nw; i += blockDim.x) proj_w[off + i] = p.proj[h].w[i];
+      off += nw;
+    }
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmH);
+    prefetch_tmap(&p.tmB);
+    for (int i = 0; i < nb; ++i) { mbar_init(smem_u32(&bar_bfull[i]), 1); mbar_init(smem_u32(&bar_bempty[i]), 2); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_afull[i]), 1);
+      mbar_init(smem_u32(&bar_aempty[i]), 2);
+      mbar_init(smem_u32(&bar_tfull[i]), 2);
+      mbar_init(smem_u32(&bar_tempty[i]), p.nproj > 0 ? 4 : TC_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int npair = (p.S + 1) >> 1;                  // issue slots per filter row
+  constexpr int TH = 16;
+
+  if (warp == 0) {
+    // ================================ B (weights) producer: one slot = taps (r, 2q) and (r, 2q + 1) ================================
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t phb = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (int)(tile % p.tiles_n) * BN;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          int cbw = cb;
+          if (p.split == 1) {
+            const int cbl = p.cblocks / 3, pi = cb / cbl;
+            cbw = split_pass_order(pi, p.split_lofirst) * cbl + (cb - pi * cbl);
+          }
+          for (int r = 0; r < p.R; ++r) {
+            for (int q = 0; q < npair; ++q) {
+              const int s0 = 2 * q;
+              const bool two = s0 + 1 < p.S;
+              mbar_wait(smem_u32(&bar_bempty[sb]), phb ^ 1);
+              const uint32_t full = smem_u32(&bar_bfull[sb]);
+              mbar_expect_tx(full, two ? SLOT_BYTES : TAP_BYTES);
+              tma_load_3d(smem_base + sb * SLOT_BYTES, &p.tmB, full, cbw * TC_BK, n0, r * p.S + s0);
+              if (two) tma_load_3d(smem_base + sb * SLOT_BYTES + TAP_BYTES, &p.tmB, full, cbw * TC_BK, n0, r * p.S + s0 + 1);
+              if (++sb == nb) { sb = 0; phb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ A (activation patch) producer ================================
+    if (lane == 0) {
+      int ab = 0;
+      uint32_t pha = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const long long m_tile = tile / p.tiles_n;
+        const int img = (int)(m_tile / tiles_per_img);
+        const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
+        const int y0 = (t_in / p.tiles_x) * TH, x0 = (t_in % p.tiles_x) * TAP2_TW;
+        const int n0 = (int)(tile % p.tiles_n) * BN;
+        const int cbase = p.slab_mode ? (n0 / p.kslab) * p.kslab : 0;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          int a_ch = cb * TC_BK;
+          if (p.split == 1) {
+            const int cbl = p.cblocks / 3, pi = cb / cbl, pass = split_pass_order(pi, p.split_lofirst);
+            a_ch = (cb - pi * cbl) * TC_BK + (pass == 1 ? p.a_lo : 0);
+          } else if (p.split == 2) {
+            const int cbl = p.cblocks / 2;
+            a_ch = cb < cbl ? cb * TC_BK + p.a_lo : (cb - cbl) * TC_BK;
+          }
+          mbar_wait(smem_u32(&bar_aempty[ab]), pha ^ 1);
+          const uint32_t full = smem_u32(&bar_afull[ab]);
+          mbar_expect_tx(full, a_tx);
+          tma_load_4d(a_base + ab * patch_bytes, &p.tmH, full, cbase + a_ch, x0 - p.pad, y0 - p.pad, img);
+          ab ^= 1;
+          if (ab == 0) pha ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ================================ MMA issuers: warp 1 -> sub-tile 0, warp 3 -> sub-tile 1 ================================
+    constexpr uint32_t idesc2 = make_idesc_f16(TC_BM, ACC), idesc1 = make_idesc_f16(TC_BM, BN);
+    const int j = (warp == 3) ? 1 : 0;
+    int sb = 0, ab = 0, acc = 0;
+    uint32_t phb = 0, pha = 0, acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MSUB + j) * ACC);
+      for (int cb = 0; cb < p.cblocks; ++cb) {
+        mbar_wait(smem_u32(&bar_afull[ab]), pha);
+        tc_fence_after();
+        const uint32_t patch = a_base + ab * patch_bytes;
+        const bool f8 = p.split == 2 && cb < (p.cblocks >> 1);
+        for (int r = 0; r < p.R; ++r) {
+          for (int q = 0; q < npair; ++q) {
+            const int s0 = 2 * q;
+            const bool two = s0 + 1 < p.S;
+            mbar_wait(smem_u32(&bar_bfull[sb]), phb);
+            tc_fence_after();
+            const uint64_t db = make_sw128_kmajor_desc(smem_base + sb * SLOT_BYTES);
+            const uint64_t da = make_sw128_kmajor_desc_ex(patch + (uint32_t)((r * p.pw + s0) * 128), (uint32_t)(p.pw * 128), 0)
+                                + (uint64_t)(j * 64);
+            const uint32_t first = (uint32_t)((cb | r | q) != 0);
+            const uint32_t idesc = two ? idesc2 : idesc1;
+            if (f8) {
+              umma_f8_elect(d_tmem, da, db, idesc, first);
+#pragma unroll
+              for (int k = 1; k < TC_BK / 16; ++k) umma_f8_elect(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+            } else {
+              umma_f16_elect(d_tmem, da, db, idesc, first);
+#pragma unroll
+              for (int k = 1; k < TC_BK / 16; ++k) umma_f16_elect(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+            }
+            umma_commit_elect(smem_u32(&bar_bempty[sb]));
+            if (++sb == nb) { sb = 0; phb ^= 1; }
+          }
+        }
+        umma_commit_elect(smem_u32(&bar_aempty[ab]));
+        ab ^= 1;
+        if (ab == 0) pha ^= 1;
+      }
+      umma_commit_elect(smem_u32(&bar_tfull[acc]));
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    if (COAL || !(p.nproj > 0 && half == 1)) {
+      const int row = quad * 32 + lane;
+      const int py = row >> 3, px = row & 7;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = (int)(tile % p.tiles_n);
+        const long long m_tile = tile / p.tiles_n;
+        const int img = (int)(m_tile / tiles_per_img);
+        const int t_in = (int)(m_tile - (long long)img * tiles_per_img);
+        const int ty0 = (t_in / p.tiles_x) * TH, tx0 = (t_in % p.tiles_x) * TAP2_TW;
+        mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < MSUB; ++j) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * MSUB + j) * ACC);
+          if (COAL) {
+            CoalRows cr;
+            coal_rows<3>(p, img, ty0, tx0 + 8 * j, n_tile * BN, quad, lane, cr, tx0 + TAP2_TW);
+            uint4 rg[4], rgl[4];
+            if (p.res) {
+              coal_load_res(p, cr, half, 0, rg);
+              if (p.split) coal_load_res(p, cr, half, p.res_lo, rgl);
+            }
+            epilogue_coalesced<BN, true>(p, taddr, cr, n_tile * BN, half, lane,
+                                         reinterpret_cast<uint4*>(tail) + (warp - 4) * 128, rg, rgl, j);
+          } else {
+            epilogue_rows<BN, false, true>(p, taddr, img, ty0 + py, tx0 + px + 8 * j, n_tile, n_tile * BN, half, proj_w,
+                                           nullptr, j, lane, px + 8 * j < TAP2_TW);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Host side: tensor maps + launch configuration
 // ---------------------------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -1509,6 +1787,21 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
         p.tiles_x = (op.dst.w + 8 * msub - 1) / (8 * msub);
         p.tiles_y = (op.dst.h + 15) / 16;
         p.total_tiles = (long long)op.dst.n * p.tiles_x * p.tiles_y * p.tiles_n;
+        {
+          // tap-pair kernel for the 64-wide tiles: two taps per N = 128 instruction.  Measured (profiles/r02h_ab_tap2.log):
+          // 7x7 refinement head 3.93 -> 2.52 ms (2-pass engine), 2.08 -> 1.88 ms (fp16); 3x3 layers get SLOWER (1.02 ->
+          // 1.15 ms: 2 instead of 3 issue slots per filter row do not pay for the three-fold TMEM read + shuffles of the
+          // epilogue), so it is used for >= 25 taps only.  CPN_TAP2=0 disables it, CPN_TAP2=2 forces it for every k >= 3.
+          static int tap2_env = -1;
+          if (tap2_env < 0) { const char* e = getenv("CPN_TAP2"); tap2_env = e ? atoi(e) : 1; }
+          const int nbs2 = (TC_SMEM_BUDGET - 2 * patch) / (2 * b_bytes);
+          if (tap2_env && (op.r * op.s >= 25 || tap2_env == 2) && bn == 64 && msub == 2 && sw128_env && op.s >= 3 && nbs2 >= 2) {
+            p.tap2 = 1;
+            p.nb_stages = nbs2 > 8 ? 8 : nbs2;
+            p.tiles_x = (op.dst.w + TAP2_TW - 1) / TAP2_TW;
+            p.total_tiles = (long long)op.dst.n * p.tiles_x * p.tiles_y * p.tiles_n;
+          }
+        }
       }
     }
   }
@@ -1539,7 +1832,8 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
                   res_elems < (1ll << 31)) ? 1 : 0;
   }
   pl->smem_bytes = pl->stages * stage_bytes + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
-  if (p.halo) pl->smem_bytes = p.nb_stages * bn * TC_BK * 2 + 2 * 8 * p.plane_stride + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
+  if (p.halo) pl->smem_bytes = p.nb_stages * bn * TC_BK * 2 * (p.tap2 ? 2 : 1) + 2 * 8 * p.plane_stride + 1024 +
+                               (p.coalesce ? TC_STAGING_BYTES : 0);
   const long long sms = sm_count();
   pl->grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
   {
@@ -1631,8 +1925,22 @@ static int launch_halo(const ConvTcPlan* pl, cudaStream_t st) {
   return pl->p.coalesce ? launch_halo2<BN, MSUB, true>(pl, st) : launch_halo2<BN, MSUB, false>(pl, st);
 }
 
+template <bool COAL>
+static int launch_tap2(const ConvTcPlan* pl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv_tap2_kernel<COAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TC_SMEM_BUDGET + 1024 + TC_PROJ_SMEM_MAX));
+    attr_set = true;
+  }
+  conv_tap2_kernel<COAL><<<pl->grid, TCH_THREADS, pl->smem_bytes, st>>>(pl->p);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
 int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t st) {
   if (pl->pair) return pl->p.coalesce ? launch_pair2<true>(pl, st) : launch_pair2<false>(pl, st);
+  if (pl->p.halo && pl->p.tap2) return pl->p.coalesce ? launch_tap2<true>(pl, st) : launch_tap2<false>(pl, st);
   if (pl->p.halo) {
     if (pl->bn == 64 && pl->msub == 2) return launch_halo<64, 2>(pl, st);
     if (pl->bn == 128 && pl->msub == 2) return launch_halo<128, 2>(pl, st);

@@ -138,6 +138,7 @@ class CPN(nn.Module):
         self.certainty_thresh = certainty_thresh
         self.uncertainty_nms = uncertainty_nms
         self.precision = precision
+        self.cuda_graph = False     # True: replay the backbone + heads as one CUDA graph (static buffers; see Plan.forward_graph)
         self.hparams = dict(in_channels=in_channels, order=order, nms_thresh=nms_thresh, score_thresh=score_thresh,
                             samples=samples, classes=classes, refinement=refinement,
                             refinement_iterations=refinement_iterations, refinement_margin=refinement_margin,
@@ -251,6 +252,8 @@ class CPN(nn.Module):
         """Raw head tensors in the reference's layout: scores [N,C,h,w], locations [N,2,h,w], refinement [N,2B,H,W],
         fourier [N,4*order,h,w] (+ uncertainty [N,4,h,w] with an uncertainty head) (CPNCore.forward, cpn.py:238-283)."""
         plan, outs, _ = self._run_plan(inputs)
+        if self.cuda_graph:
+            outs = [o.clone() for o in outs]       # the graph's static outputs are overwritten by the next call
         sc, lf, rf = outs[:3]
         if int(plan.flags[0].item()) & 1:
             raise AssertionError('Inputs should be in interval (0.0, 1.0)')
@@ -385,7 +388,7 @@ class CPN(nn.Module):
         plan = self._plan(n, h, w)
         x = inputs.contiguous() if inputs.dtype == torch.uint8 else inputs.contiguous().float()
         plan.flags.zero_()
-        outs = plan.forward(x, fmt)
+        outs = plan.forward_graph(x, fmt) if self.cuda_graph else plan.forward(x, fmt)
         rf = outs[2]
         if tuple(rf.shape[1:3]) != (h, w):       # strided / low-res refinement head: _equal_size to the input (cpn.py:279)
             full = torch.empty((n, h, w, rf.shape[3]), dtype=torch.float32, device=rf.device)

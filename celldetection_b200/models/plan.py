@@ -309,6 +309,29 @@ class Plan:
                 'plan_forward')
         return outputs
 
+    def forward_graph(self, x, input_format):
+        """CUDA-graph replay of the whole plan (one graph launch instead of ``n_launches`` kernel launches): the input is
+        copied into a static buffer, the graph is replayed on the current stream and the STATIC output tensors are
+        returned -- they are overwritten by the next replay, so the caller consumes them first (the model's post-head
+        chain does, on the same stream).  Captured on first use per (format, dtype, shape)."""
+        key = (int(input_format), x.dtype, tuple(x.shape))
+        graphs = self.__dict__.setdefault('_graphs', {})
+        ent = graphs.get(key)
+        if ent is None:
+            static_x = torch.empty_like(x)
+            static_out = self.new_outputs()
+            static_x.copy_(x)
+            self.forward(static_x, input_format, static_out)      # warm-up outside the capture (function attributes, ...)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.forward(static_x, input_format, static_out)
+            ent = graphs[key] = (graph, static_x, static_out)
+        graph, static_x, static_out = ent
+        static_x.copy_(x, non_blocking=True)
+        graph.replay()
+        return static_out
+
     def run_op(self, index, x, input_format, outputs):
         lib = L.load()
         arr = (ctypes.c_void_p * len(outputs))(*[o.data_ptr() for o in outputs])

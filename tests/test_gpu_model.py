@@ -568,3 +568,29 @@ def test_sharded_slide_is_bit_identical_to_single_gpu(tmp_path):
     got = [l for l in two.stdout.splitlines() if l.startswith('DIGEST')]
     assert len(want) == 1 and len(got) == 2 and int(want[0].split()[1]) > 50
     assert got[0] == got[1] == want[0], (want, got)
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """``model.cuda_graph = True`` replays the plan as one CUDA graph (static input / output buffers): same bits as the
+    eager launch sequence, for repeated calls with different inputs and for both input formats."""
+    z = load_npz('model_cpnu22_n2_96x160_s64')
+    m, (n, h, w) = _model(z, 'fp16f8')
+    x = torch.from_numpy(z['x']).cuda()
+    x2 = x.flip(0).contiguous()
+    eager = [m(x), m(x2)]
+    raw = m.core_forward(x)
+    m.cuda_graph = True
+    for _ in range(2):
+        got = [m(x), m(x2)]
+        for a, b in zip(eager, got):
+            for i in range(n):
+                assert torch.equal(a['contours'][i], b['contours'][i]) and torch.equal(a['scores'][i], b['scores'][i])
+    raw_g = m.core_forward(x)
+    m.core_forward(x2)                                       # must not clobber the tensors returned above
+    for k in raw:
+        assert torch.equal(raw[k], raw_g[k]), k
+    u8 = (x * 255).round().to(torch.uint8)
+    a = m(u8)
+    m.cuda_graph = False
+    b = m(u8)
+    assert torch.equal(a['contours'][0], b['contours'][0])
