@@ -18,6 +18,7 @@ OP_PREP, OP_CONV, OP_MAXPOOL, OP_UPSAMPLE, OP_BILINEAR, OP_PROJ = range(6)
 IN_F32_NCHW, IN_U8_NCHW, IN_U8_NHWC = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SCALED_TANH, ACT_SIGMOID = 0, 1, 2, 3
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
+CONV_UP2 = 1
 
 
 class View(ctypes.Structure):
@@ -33,7 +34,7 @@ class Op(ctypes.Structure):
                 ('kslab', ctypes.c_int32), ('slab_mode', ctypes.c_int32), ('act', ctypes.c_int32),
                 ('act_scale', ctypes.c_float), ('proj_cin_off', ctypes.c_int32), ('proj_cin', ctypes.c_int32),
                 ('out_binding', ctypes.c_int32), ('fuse_next', ctypes.c_int32), ('acc_scale', ctypes.c_float),
-                ('reserved', ctypes.c_int32)]
+                ('flags', ctypes.c_int32)]
 
 
 class SelectParams(ctypes.Structure):

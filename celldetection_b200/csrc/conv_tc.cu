@@ -85,6 +85,9 @@ struct ConvTcParams {
   float acc_scale;                   // accumulator scale applied first in every epilogue (1/S of the F16F8 weight packing)
   float out_lo_scale, out_hi8_scale; // F16F8 output: lo8 = e4m3((v - hi) * out_lo_scale), hi8 = e4m3(hi * out_hi8_scale)
   float res_lo_inv;                  // F16F8 residual: value = hi + lo8 * res_lo_inv
+  int up2;                  // CPN_CONV_UP2: the accumulator's 4 x 64-channel column groups are the four phases of a 2x
+                            // up-sampled output: pixel (y, x), column (2a+b)*cup + c -> out[(2y+a, 2x+b), c]
+  int cup, Ho2, Wo2;        // up2: channels per phase, output extent
   int tap2;                 // conv_tap2_kernel: 64-wide layers, two horizontally adjacent filter taps per N = 128 instruction
   int dbg_epi;              // experiment switch CPN_DBG_EPI=1: the coalesced epilogue skips its global loads / stores
   int coalesce;             // conv_tc_kernel: smem-staged, line-coalesced residual loads / output stores (epilogue_coalesced)
@@ -513,6 +516,8 @@ __device__ __forceinline__ void coal_rows(const ConvTcParams& p, const int img, 
     const bool ok = y < p.Ho && x < p.Wo && x < x_limit && img < p.N;   // (img == N: phantom tile of an odd CTA pair)
     c.okmask |= ok ? (1u << i) : 0u;
     c.ooff[i] = ok ? (uint32_t)((((long long)img * p.Ho + y) * p.Wo + x) * p.out_pitch + n0 + (lane & 3) * 8) : 0u;
+    if (p.up2 && ok)    // phase (0, 0) pixel of the up-sampled output; the chunk's phase / channel offset is added at the store
+      c.ooff[i] = (uint32_t)((((long long)img * p.Ho2 + 2 * y) * p.Wo2 + 2 * x) * p.out_pitch + (lane & 3) * 8);
     c.roff[i] = 0u;
     if (p.res && ok) {
       const int ry = (p.res_h == p.Ho) ? y : (int)(((long long)y * p.res_h) / p.Ho);
@@ -625,14 +630,19 @@ __device__ __forceinline__ void epilogue_coalesced(const ConvTcParams& p, const 
 
     __syncwarp();                                                    // every lane has read its residual row(s)
     if (p.dbg_epi) continue;
+    long long obase = ch * 32;
+    if (p.up2) {                                                     // global column n0 + ch * 32 -> (phase, channel)
+      const int col = n0 + ch * 32, ph = col / p.cup, cc = col - ph * p.cup;
+      obase = ((long long)(ph >> 1) * p.Wo2 + (ph & 1)) * p.out_pitch + cc;
+    }
     stg_put_o(stg, lane, rr);
     __syncwarp();
-    stg_store_t(stg, lane, c, p.out + ch * 32);
+    stg_store_t(stg, lane, c, p.out + obase);
     if (split) {
       __syncwarp();
       stg_put_o(stg, lane, rl);
       __syncwarp();
-      stg_store_t(stg, lane, c, p.out + p.out_lo + ch * 32);
+      stg_store_t(stg, lane, c, p.out + p.out_lo + obase);
     }
     __syncwarp();                                                    // staging tile free for the next chunk
   }
@@ -1662,8 +1672,9 @@ static int pick_bn(int cout, int slab_mode) {
   return 64;
 }
 
-int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const void* res, const void* wgt,
+int conv_tc_plan_create(const cpn_op_t& op_in, const void* src, void* dst, const void* res, const void* wgt,
                         const float* bias, ConvTcPlan** out) {
+  cpn_op_t op = op_in;      // (CPN_CONV_UP2 rewrites the logical output dims below)
   const bool f16f8 = op.src.dtype == CPN_DT_F16F8;
   const bool split = op.src.dtype == CPN_DT_F16X2 || f16f8;    // tensors with a second (lo / 8-bit) block per pixel
   const int npass = f16f8 ? 2 : (split ? 3 : 1);
@@ -1682,6 +1693,15 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
   CPN_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0) && ((uintptr_t)wgt % 16 == 0) &&
                   (res == nullptr || (uintptr_t)res % 16 == 0) && (bias == nullptr || (uintptr_t)bias % 16 == 0),
               "conv_tc: base pointers must be 16-byte aligned");
+  const bool up2 = (op_in.flags & CPN_CONV_UP2) != 0;
+  if (up2) {
+    // the GEMM runs at the source resolution with 4 * cout columns; only the epilogue knows about the 2x output
+    CPN_REQUIRE(op_in.r == 3 && op_in.s == 3 && op_in.stride == 1 && op_in.pad == 1 && op_in.res.n == 0 && op_in.slab_mode == 0 &&
+                    op_in.fuse_next == 0 && op_in.dst.h == 2 * op_in.src.h && op_in.dst.w == 2 * op_in.src.w &&
+                    (4 * op_in.dst.c) % 256 == 0 && op_in.dst.c % 32 == 0,
+                "conv_tc: CPN_CONV_UP2 needs a 3x3/s1/p1 dense conv without residual, dst = 2x src, 4*cout %% 256 == 0");
+    op.dst.h = op_in.src.h; op.dst.w = op_in.src.w; op.dst.c = 4 * op_in.dst.c;
+  }
   const int eh = (op.src.h + 2 * op.pad - op.r) / op.stride + 1, ew = (op.src.w + 2 * op.pad - op.s) / op.stride + 1;
   CPN_REQUIRE(eh == op.dst.h && ew == op.dst.w && op.src.n == op.dst.n,
               "conv_tc: output shape mismatch (%dx%d expected %dx%d)", op.dst.h, op.dst.w, eh, ew);
@@ -1819,7 +1839,7 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
     // addressed with 32-bit element offsets; conv_tc_fuse_proj switches it off again for fused ReadOut heads
     static int coal_env = -1;
     if (coal_env < 0) { const char* e = getenv("CPN_COALESCE"); coal_env = (e && atoi(e) == 0) ? 0 : 1; }
-    const long long out_elems = (long long)op.dst.n * op.dst.h * op.dst.w * op.dst.pitch;
+    const long long out_elems = (long long)op_in.dst.n * op_in.dst.h * op_in.dst.w * op_in.dst.pitch;
     const long long res_elems = op.res.n ? (long long)op.res.n * op.res.h * op.res.w * op.res.pitch : 0;
     static int coal_halo_env = -1;   // CPN_COALESCE_HALO=0: keep the direct epilogue in conv_halo_kernel only (A/B switch)
     if (coal_halo_env < 0) { const char* e = getenv("CPN_COALESCE_HALO"); coal_halo_env = (e && atoi(e) == 0) ? 0 : 1; }
@@ -1830,6 +1850,10 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
     if (coal_split_env < 0) { const char* e = getenv("CPN_COALESCE_SPLIT"); coal_split_env = (e && atoi(e) == 0) ? 0 : 1; }
     p.coalesce = (coal_env && (coal_split_env || !split) && (coal_halo_env || !p.halo) && out_elems < (1ll << 31) &&
                   res_elems < (1ll << 31)) ? 1 : 0;
+  }
+  if (up2) {
+    CPN_REQUIRE(p.halo && p.coalesce && !p.tap2, "conv_tc: CPN_CONV_UP2 needs the halo kernel with the coalesced epilogue");
+    p.up2 = 1; p.cup = op_in.dst.c; p.Ho2 = op_in.dst.h; p.Wo2 = op_in.dst.w;
   }
   pl->smem_bytes = pl->stages * stage_bytes + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
   if (p.halo) pl->smem_bytes = p.nb_stages * bn * TC_BK * 2 * (p.tap2 ? 2 : 1) + 2 * 8 * p.plane_stride + 1024 +

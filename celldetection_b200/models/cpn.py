@@ -13,6 +13,7 @@ Nothing here computes on the CPU or with PyTorch operators: modules only *hold* 
 """
 from collections import OrderedDict
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -235,7 +236,8 @@ class CPN(nn.Module):
         plan = self._plans.get(key)
         if plan is None:
             g = trace(self.arch, n, h, w, in_channels=self.in_channels, order=self.core_order,
-                      refinement_margin=self.refinement_margin, stem_im2col=fast, **self._variant())
+                      refinement_margin=self.refinement_margin, stem_im2col=fast,
+                      fuse_up2=fast and os.environ.get('CPN_UP2', '1') != '0', **self._variant())
             pack = self._packs.get(self.precision)
             if pack is None:
                 with torch.no_grad():

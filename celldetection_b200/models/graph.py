@@ -99,12 +99,14 @@ class LOp:
     name: str = ''
     im2col: Optional[Tuple[int, int]] = None   # (k, cin) of the original convolution when it runs as a 1x1 on an
                                                # im2col'd input (tensor-core stem), or of the prep op producing it
+    up2: bool = False                          # 3x3 conv on the 2x nearest-up-sampled src, computed from the low-res src
 
 
 class Tracer:
-    def __init__(self, n, h, w, stem_im2col=False):
+    def __init__(self, n, h, w, stem_im2col=False, fuse_up2=False):
         self.n, self.h, self.w = n, h, w
         self.stem_im2col = stem_im2col   # run C_in<=4 stem convolutions on the tensor cores via an im2col'd input
+        self.fuse_up2 = fuse_up2         # nearest x2 + 3x3 conv (the U-Net bridge block) as one phase-decomposed convolution
         self.tensors: List[TT] = []
         self.ops: List[LOp] = []
         self.spec = OrderedDict()   # state_dict key -> (shape, role)
@@ -165,6 +167,12 @@ class Tracer:
         ho, wo = (x.h + 2 * pad - k) // stride + 1, (x.w + 2 * pad - k) // stride + 1
         return self._emit(LOp('conv', src=x, dst=self.tensor(cout, ho, wo), res=res, k=k, stride=stride, pad=pad,
                               act=act, params=params, name=name))
+
+    def conv_up2(self, x, cout, act='none', params=None, name=''):
+        """``conv3x3(pad 1)(interpolate(x, scale_factor=2, mode='nearest'))`` without the up-sampled tensor
+        (plan.up2_weights; tensor-core engines only)."""
+        return self._emit(LOp('conv', src=x, dst=self.tensor(cout, 2 * x.h, 2 * x.w), k=3, stride=1, pad=1, act=act,
+                              params=params, name=name, up2=True))
 
     def maxpool(self, x, k, stride, pad):
         ho, wo = (x.h + 2 * pad - k) // stride + 1, (x.w + 2 * pad - k) // stride + 1
@@ -322,16 +330,24 @@ def _unet_decoder(g, feats, chans, p, bridges):
             pr = ConvParams([f'{p}.inner_blocks.{i}.weight'], [f'{p}.inner_blocks.{i}.bias'], [None])
             top = g.conv(top, ouc, 1, act='none', params=pr, name=f'{p}.inner_blocks.{i}')
             last_c = ouc
-        if lateral is not None:
-            up = g.upsample(top, lateral.h, lateral.w)
-            x = g.cat(lateral, up)               # cat_order 0: (lateral, top_down) (unet.py:219-224)
-        else:
-            x = g.upsample(top, top.h * 2, top.w * 2)
         cin, ouc, bias = blocks[i]
-        assert x.c == cin, (x.c, cin)
         bp = f'{p}.layer_blocks.{i}'
         pa = ConvParams([f'{bp}.0.weight'], [f'{bp}.0.bias' if bias else None], [f'{bp}.1'])
         pb = ConvParams([f'{bp}.3.weight'], [f'{bp}.3.bias' if bias else None], [f'{bp}.4'])
+        if lateral is not None:
+            up = g.upsample(top, lateral.h, lateral.w)
+            x = g.cat(lateral, up)               # cat_order 0: (lateral, top_down) (unet.py:219-224)
+        elif g.fuse_up2 and top.c % 64 == 0 and ouc % 64 == 0:
+            # bridge level: nearest x2 followed by the block's first 3x3 conv -> four phase kernels on the low-res map
+            assert top.c == cin, (top.c, cin)
+            x = g.conv_up2(top, ouc, act='relu', params=pa, name=f'{bp}.0')
+            x = g.conv(x, ouc, 3, act='relu', params=pb, name=f'{bp}.3')
+            last, last_c = x, ouc
+            results[i] = x
+            continue
+        else:
+            x = g.upsample(top, top.h * 2, top.w * 2)
+        assert x.c == cin, (x.c, cin)
         x = g.conv(x, ouc, 3, act='relu', params=pa, name=f'{bp}.0')
         x = g.conv(x, ouc, 3, act='relu', params=pb, name=f'{bp}.3')
         last, last_c = x, ouc
@@ -371,7 +387,7 @@ HEAD_KERNEL_KEYS = ('score', 'location', 'fourier', 'uncertainty', 'refinement')
 def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_margin=3., refinement_buckets=1,
           uncertainty_head=False, stem_im2col=False, kernel_sizes=None, contour_head_channels=None,
           refinement_head_channels=None, contour_head_stride=1, refinement_head_stride=1, refinement_full_res=True,
-          fpn_channels=256):
+          fpn_channels=256, fuse_up2=False):
     """Trace architecture `arch` for an [n, in_channels, h, w] input.  Returns the Tracer; ``g.outputs`` maps
     'scores' / 'locfou' / 'refinement' (/ 'uncertainty') to fp32 output tensors (bindings 0 / 1 / 2 (/ 3)).
 
@@ -388,7 +404,7 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
     ks = dict.fromkeys(HEAD_KERNEL_KEYS, 7)
     ks.update(kernel_sizes or {})
     assert all(int(k) % 2 == 1 and 1 <= int(k) <= 15 for k in ks.values()), 'head kernel sizes must be odd, <= 15'
-    g = Tracer(n, h, w, stem_im2col=stem_im2col)
+    g = Tracer(n, h, w, stem_im2col=stem_im2col, fuse_up2=fuse_up2)
     g.spec['order_weights'] = ((order, 1), 'order_weights')   # buffer of CPN (cpn.py:406-412)
     bb = 'core.backbone'
     x = g.prep(in_channels)

@@ -70,6 +70,23 @@ def expand_grouped(w, groups):
     return out
 
 
+def up2_weights(w, b):
+    """Phase kernels of ``conv3x3(pad 1) o nearest-upsample(x2)`` (cpn_b200.h, CPN_CONV_UP2).  ``w`` [cout, cin, 3, 3],
+    ``b`` [cout] -> ([4 * cout, cin, 3, 3], [4 * cout]): output pixel (2y + a, 2x + b') reads the up-sampled rows
+    2y + a + t, t in {-1, 0, 1}, i.e. the source rows y + floor((a + t) / 2); taps that land on the same source pixel are
+    summed.  Zero padding of the up-sampled image coincides with zero padding of the source, so the identity holds at the
+    borders too (exactly, up to the rounding of the summed weights)."""
+    cout, cin = w.shape[:2]
+    out = torch.zeros(4, cout, cin, 3, 3, dtype=w.dtype)
+    for a in range(2):
+        for bb in range(2):
+            for r in range(3):
+                for s_ in range(3):
+                    dy, dx = (a + r - 1) // 2, (bb + s_ - 1) // 2          # floor division
+                    out[2 * a + bb, :, :, dy + 1, dx + 1] += w[:, :, r, s_]
+    return out.reshape(4 * cout, cin, 3, 3), b.repeat(4)
+
+
 def engine_for(op: LOp, fast, cin):
     if not fast:
         return L.ENGINE_SIMT
@@ -120,6 +137,8 @@ class WeightPack:
             if op.kind not in ('conv', 'proj'):
                 continue
             w, b = fold_conv(sd, op.params)
+            if op.kind == 'conv' and getattr(op, 'up2', False):
+                w, b = up2_weights(w, b)
             if op.kind == 'conv' and op.im2col is not None:   # [cout, cin, k, k] -> [cout, (r*k+s)*cin + c] padded
                 cout_ = w.shape[0]
                 wk = w.permute(0, 2, 3, 1).reshape(cout_, -1)
@@ -259,6 +278,7 @@ class Plan:
                 o.w_offset, o.b_offset = w_off, b_off
                 if lop.kind == 'conv':
                     o.engine = eng
+                    o.flags = L.CONV_UP2 if getattr(lop, 'up2', False) else 0
                     o.acc_scale = pack.acc_scale.get(i, 1.)
                     o.kslab, o.slab_mode = slab_of(lop.src.c, lop.dst.c, lop.params.groups)
                     self.engines.append(eng)

@@ -87,6 +87,15 @@ enum {
 enum { CPN_IN_F32_NCHW = 0, CPN_IN_U8_NCHW = 1, CPN_IN_U8_NHWC = 2 };
 enum { CPN_ACT_NONE = 0, CPN_ACT_RELU = 1, CPN_ACT_SCALED_TANH = 2,
        CPN_ACT_SIGMOID = 3 /* ReadOut(final_activation='sigmoid') of the uncertainty head, models/cpn.py:208-219 */ };
+/* cpn_op_t::flags */
+enum { CPN_CONV_UP2 = 1 /* F.interpolate(scale 2, 'nearest') followed by this 3x3 / stride 1 / pad 1 convolution
+                           (models/unet.py:213-217 + the bridge block :95-98), computed WITHOUT materialising the
+                           up-sampled tensor: src is the low-resolution input [n,h,w,cin], dst the high-resolution output
+                           [n,2h,2w,cout], and the weights are the four phase kernels of the composition,
+                           [3*3][4*cout][kslab] with output channel (2a+b)*cout + c = output pixel (2y+a, 2x+b), channel
+                           c (each phase kernel sums the taps of the original kernel that read the same source pixel;
+                           zero padding of the up-sampled image equals zero padding of the source).  The bias holds
+                           4*cout values.  Needs 4*cout % 256 == 0. */ };
 /* conv engines */
 enum { CPN_ENGINE_SIMT = 0, CPN_ENGINE_TCGEN05 = 1 };
 
@@ -120,7 +129,7 @@ typedef struct {
                             cpn_plan_forward and the convolution's own dst is then not written */
   float acc_scale;       /* CONV (TCGEN05): the fp32 accumulator is multiplied by this before bias / residual / activation
                             (1/S of the CPN_DT_F16F8 weight packing; 0 is read as 1) */
-  int32_t reserved;
+  int32_t flags;         /* CONV (TCGEN05): CPN_CONV_UP2 */
 } cpn_op_t;
 
 typedef struct cpn_plan cpn_plan_t;

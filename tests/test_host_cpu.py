@@ -349,3 +349,27 @@ def test_constructor_options_are_honoured_or_rejected():
     from celldetection_b200.inference import _parse_model_parameters
     assert _parse_model_parameters('nms_thresh=0.3, certainty_thresh=None,refinement=False,tag=a=b') == [
         ('nms_thresh', 0.3), ('certainty_thresh', None), ('refinement', False), ('tag', 'a=b')]
+
+
+def test_up2_phase_kernels_equal_upsample_then_conv():
+    """CPN_CONV_UP2 (cpn_b200.h): conv3x3(pad 1) after a nearest x2 up-sampling equals four phase kernels on the low-res
+    input followed by a pixel shuffle -- exactly, borders included; the tensor-core traces use it for the U-Net bridge
+    block (one op fewer, same FLOP census, same parameters)."""
+    import torch.nn.functional as F
+    from celldetection_b200.models.plan import up2_weights
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 7, 9, generator=g, dtype=torch.float64)
+    w = torch.randn(6, 5, 3, 3, generator=g, dtype=torch.float64)
+    b = torch.randn(6, generator=g, dtype=torch.float64)
+    want = F.conv2d(F.interpolate(x, scale_factor=2, mode='nearest'), w, b, padding=1)
+    we, be = up2_weights(w, b)
+    y = F.conv2d(x, we, be, padding=1)
+    n, _, h, ww = y.shape
+    got = y.reshape(n, 2, 2, 6, h, ww).permute(0, 3, 4, 1, 5, 2).reshape(n, 6, 2 * h, 2 * ww)
+    assert float((got - want).abs().max()) < 1e-12
+    a = G.trace('CpnResNeXt101UNet', 1, 128, 128, stem_im2col=True)
+    c = G.trace('CpnResNeXt101UNet', 1, 128, 128, stem_im2col=True, fuse_up2=True)
+    assert len(c.ops) == len(a.ops) - 1 and G.conv_flops(a) == G.conv_flops(c) and list(a.spec) == list(c.spec)
+    up = [o for o in c.ops if o.up2]
+    assert len(up) == 1 and up[0].name.endswith('layer_blocks.0.0') and (up[0].dst.h, up[0].dst.w) == (128, 128)
+    assert not any(o.up2 for o in G.trace('CpnU22', 1, 64, 64, stem_im2col=True, fuse_up2=True).ops)   # no bridge level
