@@ -335,13 +335,16 @@ def heads_roofline(model, x, precision):
                 traffic = None
     act_bytes = {'fp16f8': 4, 'fp16': 2, 'fp16x3': 4}[precision]      # bytes per activation / weight element as stored
     return dict(bound='tensor',
-                kernel=f'conv_halo_kernel<256,1>: merged 7x7 heads 256->768 @256x256 + fused ReadOut projections, batch '
-                       f'{BATCH}, {passes} tcgen05 pass-equivalent(s) per K block'
+                kernel=f'conv_halo_kernel<256,1>: 7x7 head convolution {hop.src.c}->{hop.dst.c} @{hop.dst.h}x{hop.dst.w} + fused '
+                       f'ReadOut projection(s)' + (' (score head; location / fourier heads are evaluated at proposals only)'
+                                                   if getattr(plan.g, 'sparse', False) else ' (merged score / location / fourier heads)')
+                       + f', batch {BATCH}, {passes} tcgen05 pass-equivalent(s) per K block'
                        + (' (kind::f8f6f4 e4m3 correction pass, then kind::f16; one fp32 accumulator)' if precision == 'fp16f8' else ''),
                 achieved=achieved, peak=peaks['tflops'], unit='TFLOP/s', frac=achieved / peaks['tflops'],
                 traffic=traffic, traffic_source=src,
                 algorithmic_bytes=BATCH * hop.src.h * hop.src.w * hop.src.c * act_bytes
-                + hop.dst.c * hop.src.c * hop.k * hop.k * act_bytes + BATCH * hop.dst.h * hop.dst.w * 23 * 4,
+                + hop.dst.c * hop.src.c * hop.k * hop.k * act_bytes
+                + BATCH * hop.dst.h * hop.dst.w * (1 if getattr(plan.g, 'sparse', False) else 23) * 4,
                 peak_source=peaks['source'] + ', burst cuBLAS bf16', ms_per_launch=hms, flops_per_launch=hflops,
                 executed_tflops_pass_equivalents=achieved * passes,
                 executed_frac_of_peak=achieved * passes / peaks['tflops'])
@@ -534,15 +537,22 @@ def run_b200(args):
         d2h = sum(t.numel() * t.element_size() for v in last_e[0].values() for t in v)
         h2d = int(host[0].numel() * 4)
         plan = model._plan(BATCH, TILE, TILE)
-        total_flops = conv_flops(plan.g)
-        net_tflops = total_flops * args.steps / (ms / 1e3) / 1e12
+        from celldetection_b200.models.graph import trace as _trace
+        algo_flops = conv_flops(_trace(ARCH, BATCH, TILE, TILE, stem_im2col=True))     # every head on every pixel
+        total_flops = conv_flops(plan.g)                                                # what the plan executes per step
+        sparse_rows = getattr(model, 'last_sparse_rows', 0) if getattr(plan.g, 'sparse', False) else 0
+        if sparse_rows:                                                                 # + the heads at the proposals
+            total_flops += 2. * sparse_rows * 2 * plan.g.head_mid * plan.g.head_feat.c * plan.g.head_k ** 2
+        net_tflops = algo_flops * args.steps / (ms / 1e3) / 1e12
+        exe_tflops = total_flops * args.steps / (ms / 1e3) / 1e12
         cfg = dict(workload=f'C3: {ARCH} random-init (synthetic weights seed {SEED}, heads calibrated to '
                             f'{FG_FRACTION:.0%} foreground), batch {BATCH}x3x{TILE}x{TILE} per GPU',
                    global_batch=tiles, tile=TILE, parallelism=f'tile-parallel x{world}',
                    l2='4 rotating input batches; per-step activations >> 126 MB L2',
                    proposals_last_step=int(sum(model.forward_flat(xs[0], nms=False)[1])),
                    kept_last_step=int(sum(counts)), precision=args.precision,
-                   conv_gflop_per_tile=total_flops / BATCH / 1e9)
+                   conv_gflop_per_tile=algo_flops / BATCH / 1e9, conv_gflop_per_tile_executed=total_flops / BATCH / 1e9,
+                   sparse_heads=bool(getattr(plan.g, 'sparse', False)), sparse_head_rows_last_step=int(sparse_rows))
         line = dict(metric=METRIC, value=value, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype=DTYPE[args.precision], data='synthetic', config=cfg, clocks=clk.result,
@@ -551,9 +561,13 @@ def run_b200(args):
                     gpu_launches=int(launches),
                     network=dict(conv_tflops=net_tflops, frac_of_sustained_peak=net_tflops / peaks['tflops_sustained'],
                                  frac_of_burst_peak=net_tflops / peaks['tflops'],
+                                 conv_tflops_executed=exe_tflops,
+                                 executed_frac_of_sustained_peak=exe_tflops / peaks['tflops_sustained'],
                                  launches_per_step=launches / args.steps,
-                                 note='algorithmic conv FLOPs of the reference formulation minus the commuted 1x1 (2347.7 GF '
-                                      'per tile) / step time; the 2-pass engine executes 2 tensor-core pass-equivalents'))
+                                 note='conv_tflops: ALGORITHMIC conv FLOPs (every head on every pixel, like the reference: '
+                                      '2347.7 GF per tile after the commuted 1x1) / step time.  conv_tflops_executed: the '
+                                      'FLOPs the plan really contracts (location / fourier heads only at the proposals), before '
+                                      'the factor 2 of the 2-pass engine'))
     else:
         # ---- C4: one slide, tiles sharded over the ranks, all-gather + stitch on every rank ----
         import numpy as np
@@ -624,6 +638,12 @@ def run_b200(args):
                 line['latency_batch1'] = batch1_latency(model, xs[0][:1].contiguous())
             except Exception as e:
                 line['latency_batch1'] = dict(error=f'{type(e).__name__}: {e}'[:300])
+            if getattr(model, 'sparse_heads', False):      # same engine, every head on every pixel (round-2 start)
+                model.sparse_heads = False
+                dms, dkept = quick_rate(model, xs)
+                model.sparse_heads = True
+                line['dense_heads'] = dict(value=BATCH / (dms / 1e3), unit='tiles/s', ms_per_step=dms, kept_last_step=dkept,
+                                           note='location / fourier heads computed on every pixel like the reference does')
             if args.precision == HEADLINE:
                 fast = sibling(ARCH, 'fp16', sd, dev)
                 fms, fkept = quick_rate(fast, xs)

@@ -67,6 +67,9 @@ SYMBOLS = {
     'cpn_decode_refine_buckets': (_I, [_P, _I64, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P,
                                        _P, _P, _P, _P]),
     'cpn_decode_refine': (_I, [_P, _I64, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
+    'cpn_decode_refine_rows': (_I, [_P, _I64, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P,
+                                    _P, _P, _P, _P]),
+    'cpn_gather_patches': (_I, [_P, ctypes.POINTER(View), _P, _I64, _I, _P, ctypes.POINTER(View), _P]),
     'cpn_fouriers2contours': (_I, [_P, _P, _I64, _I, _I, _P, _P, _P, _P]),
     'cpn_nms_workspace_bytes': (_SZ, [_I64, _I]),
     'cpn_nms_segments': (_I, [_P, _P, _P, _I, _I64, _F, _I, _P, _P, _P, _P]),

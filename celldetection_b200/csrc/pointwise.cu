@@ -795,6 +795,65 @@ int proj_launch(const cpn_op_t& op, const void* src, void* dst, const float* wgt
 
 }  // namespace cpn
 
+// ---------------------------------------------------------------------------------------------------------------------
+// GATHER PATCHES: the k x k x C neighbourhood of P selected pixels of an NHWC feature map as rows of a [P, k*k*C] matrix
+// (same element format as the source; zero outside the image = the convolution's zero padding), channel order
+// [C/64 blocks][k*k taps][64 channels] -- the K order in which the dense k x k convolution contracts, so that a 1x1
+// convolution over these rows reproduces it term by term.  Sparse evaluation of the location / fourier ReadOut heads:
+// the reference computes them on every pixel (models/cpn.py:253-263) but reads them only where the score selects a
+// proposal (:620-623).  One thread moves 16 bytes; 128 contiguous bytes (64 fp16 values, or the 64 channels' 8-bit chunks
+// / lo halves) per (pixel, block, tap).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace cpn {
+__global__ void __launch_bounds__(256) gather_patches_kernel(const __half* __restrict__ src, const int32_t* __restrict__ idx,
+                                                             long long P, int H, int W, int sp, int slo, int cblocks, int k,
+                                                             int pad, __half* __restrict__ dst, int dp, int dlo, int has_lo) {
+  const int taps = k * k;
+  const long long per_row = (long long)cblocks * taps * (has_lo ? 2 : 1) * 8;      // 16-byte items per gathered row
+  const long long total = P * per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pr = i / per_row;
+    int rem = (int)(i - pr * per_row);
+    const int seg = rem & 7;
+    rem >>= 3;
+    const int blk = has_lo ? (rem & 1) : 0;          // 0: fp16 values, 1: second block (8-bit chunks / lo halves)
+    if (has_lo) rem >>= 1;
+    const int tap = rem % taps, cb = rem / taps;
+    const long long pix = idx[pr];
+    const long long hw = (long long)H * W;
+    const int b = (int)(pix / hw);
+    const int r2 = (int)(pix - (long long)b * hw);
+    const int y = r2 / W + tap / k - pad, x = r2 % W + tap % k - pad;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && x >= 0 && x < W)
+      v = __ldg(reinterpret_cast<const uint4*>(src + ((long long)b * hw + (long long)y * W + x) * sp + (blk ? slo : 0) + cb * 64) + seg);
+    reinterpret_cast<uint4*>(dst + pr * dp + (blk ? dlo : 0) + (long long)(cb * taps + tap) * 64)[seg] = v;
+  }
+}
+}  // namespace cpn
+
+extern "C" int cpn_gather_patches(const void* src, const cpn_view_t* src_view_host, const int32_t* idx, int64_t P, int k,
+                                  void* dst, const cpn_view_t* dst_view_host, void* stream) {
+  using namespace cpn;
+  CPN_REQUIRE(src && src_view_host && dst && dst_view_host && k >= 1 && (k & 1), "gather_patches: bad arguments");
+  const cpn_view_t& sv = *src_view_host;
+  const cpn_view_t& dv = *dst_view_host;
+  CPN_REQUIRE(sv.dtype == dv.dtype && (sv.dtype == CPN_DT_F16 || dtype_has_lo(sv.dtype)), "gather_patches: fp16-family views required");
+  CPN_REQUIRE(sv.c % 64 == 0 && dv.c == sv.c * k * k && sv.pitch % 8 == 0 && dv.pitch % 8 == 0 && sv.lo_delta % 8 == 0 &&
+                  dv.lo_delta % 8 == 0 && (long long)dv.n * dv.h * dv.w >= P,
+              "gather_patches: channel / pitch mismatch (src c %d, dst c %d, k %d)", sv.c, dv.c, k);
+  CPN_REQUIRE(sv.dtype != CPN_DT_F16F8 || sv.fp8_exp == dv.fp8_exp, "gather_patches: fp8 scales must match");
+  if (P <= 0) return 0;
+  const int has_lo = dtype_has_lo(sv.dtype) ? 1 : 0;
+  const long long items = P * (long long)(sv.c / 64) * k * k * (has_lo ? 2 : 1) * 8;
+  gather_patches_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __half*>(reinterpret_cast<const char*>(src) + sv.offset), idx, P, sv.h, sv.w, sv.pitch,
+      sv.lo_delta, sv.c / 64, k, k / 2, reinterpret_cast<__half*>(reinterpret_cast<char*>(dst) + dv.offset), dv.pitch,
+      dv.lo_delta, has_lo);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
 // F.interpolate(x, size, mode='bilinear', align_corners=False) on a stand-alone fp32 NHWC tensor: the resize of the
 // score bounds in _apply_score_bounds / _equal_size (models/cpn.py:109-123; c == 1 makes NHWC and NCHW coincide).
 extern "C" int cpn_resize_bilinear(const float* src, int n, int h, int w, int c, float* dst, int ho, int wo,

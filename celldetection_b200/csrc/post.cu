@@ -315,6 +315,7 @@ struct DecodeParams {
   int buckets;                  // refinement_buckets (1: plain [N,H,W,2] map)
   const int32_t* bucket_idx;    // [samples][3]
   const float* bucket_w;        // [samples][3]
+  int records_by_row;           // locfou holds one record per PROPOSAL (sparse heads) instead of one per pixel
 };
 
 __global__ void __launch_bounds__(DEC_WARPS * 32) decode_refine_kernel(const DecodeParams p) {
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_refine_kernel(const Dec
     const int rem = (int)(pix - (long long)b * hw);
     const int py = rem / p.w, px = rem - py * p.w;
     __syncwarp();
-    for (int i = lane; i < rec_len; i += 32) rec[i] = p.locfou[pix * rec_core + i];
+    for (int i = lane; i < rec_len; i += 32) rec[i] = p.locfou[(p.records_by_row ? pr : pix) * rec_core + i];
     __syncwarp();
     // rel -> abs location (ops/cpn.py:15-41): x += column index, y += row index
     const float lx = rec[0] + (float)px, ly = rec[1] + (float)py;
@@ -733,6 +734,17 @@ extern "C" int cpn_decode_refine_buckets(const int32_t* idx, int64_t P, const fl
                                          const float* bucket_w, const float* offsets, float* contours,
                                          float* proposals, float* boxes, float* locations, float* fourier_out,
                                          void* stream) {
+  return cpn_decode_refine_rows(idx, P, locfou, 0, order_core, order, n_images, h, w, H, W, trig, samples, refinement,
+                                iters, buckets, bucket_idx, bucket_w, offsets, contours, proposals, boxes, locations,
+                                fourier_out, stream);
+}
+
+extern "C" int cpn_decode_refine_rows(const int32_t* idx, int64_t P, const float* locfou, int records_by_row,
+                                      int order_core, int order, int n_images, int h, int w, int H, int W,
+                                      const float* trig, int samples, const float* refinement, int iters, int buckets,
+                                      const int32_t* bucket_idx, const float* bucket_w, const float* offsets,
+                                      float* contours, float* proposals, float* boxes, float* locations,
+                                      float* fourier_out, void* stream) {
   CPN_REQUIRE(buckets >= 1, "decode: refinement buckets must be >= 1");
   CPN_REQUIRE(buckets == 1 || refinement == nullptr || iters <= 0 || (bucket_idx != nullptr && bucket_w != nullptr),
               "decode: bucketed refinement needs the bucket tables");
@@ -746,6 +758,7 @@ extern "C" int cpn_decode_refine_buckets(const int32_t* idx, int64_t P, const fl
   p.offsets = offsets; p.contours = contours; p.proposals = proposals; p.boxes = boxes; p.locations = locations;
   p.fourier_out = fourier_out;
   p.buckets = buckets; p.bucket_idx = bucket_idx; p.bucket_w = bucket_w;
+  p.records_by_row = records_by_row ? 1 : 0;
   const size_t trig_bytes = (size_t)2 * order * samples * sizeof(float);
   const size_t rec_bytes = (size_t)DEC_WARPS * (2 + 4 * DEC_MAX_ORDER) * sizeof(float);
   p.trig_in_smem = trig_bytes + rec_bytes <= 48 * 1024;

@@ -12,6 +12,7 @@ Nothing here computes on the CPU or with PyTorch operators: modules only *hold* 
 ``cpn_plan_forward`` + the post-head C entry points.  PyTorch supplies device memory, the stream and list plumbing.
 """
 from collections import OrderedDict
+import ctypes
 import math
 import os
 
@@ -21,7 +22,7 @@ from torch import Tensor
 
 from .. import _lib as L
 from ..ops import cpn as O
-from .graph import trace, ARCHS, HEAD_KERNEL_KEYS
+from .graph import trace, trace_sparse_heads, ARCHS, HEAD_KERNEL_KEYS
 from .plan import Plan, WeightPack, SPLIT_NONE, SPLIT_X3, SPLIT_F8
 
 
@@ -139,6 +140,10 @@ class CPN(nn.Module):
         self.certainty_thresh = certainty_thresh
         self.uncertainty_nms = uncertainty_nms
         self.precision = precision
+        # Location / fourier heads only where the score selects a proposal (the reference computes them on every pixel,
+        # models/cpn.py:253-263, and reads them at the selected pixels only, :620-623): same outputs, ~2/3 of the head
+        # convolution's work gone.  ``core_forward`` (raw head tensors) always runs the dense plan.
+        self.sparse_heads = True
         self.cuda_graph = False     # True: replay the backbone + heads as one CUDA graph (static buffers; see Plan.forward_graph)
         self.hparams = dict(in_channels=in_channels, order=order, nms_thresh=nms_thresh, score_thresh=score_thresh,
                             samples=samples, classes=classes, refinement=refinement,
@@ -193,6 +198,7 @@ class CPN(nn.Module):
         self.eval()
         self._packs = {}
         self._plans = {}
+        self._sparse_plans = {}
         self._ws = {}
 
     def _variant(self):
@@ -208,6 +214,7 @@ class CPN(nn.Module):
         """Drop packed weights / compiled plans (call after modifying parameters in place)."""
         self._packs.clear()
         self._plans.clear()
+        self._sparse_plans.clear()
         self._ws.clear()
 
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -225,25 +232,73 @@ class CPN(nn.Module):
     def device(self):
         return self.order_weights.device
 
-    def _plan(self, n, h, w) -> Plan:
+    SPARSE_ROWS = 16384      # proposals per sparse-heads launch (the gathered matrix holds 50 KB per row at k = 7, C = 256)
+
+    def _sparse_plan(self, rows) -> Plan:
+        """Plan of the location + fourier heads on `rows` gathered patches (graph.trace_sparse_heads)."""
+        key = (rows, self.precision)
+        plan = self._sparse_plans.get(key)
+        if plan is None:
+            ref = self._sparse_ref
+            g = trace_sparse_heads(rows, ref['head_c'], ref['head_mid'], ref['k'], self.core_order)
+            pk = ('sparse', self.precision)
+            pack = self._packs.get(pk)
+            if pack is None:
+                with torch.no_grad():
+                    pack = WeightPack(g, self.state_dict(), True, self.device, split=_SPLIT[self.precision])
+                self._packs[pk] = pack
+            plan = Plan(g, pack, True, self.device, split=_SPLIT[self.precision])
+            self._sparse_plans[key] = plan
+        return plan
+
+    def _sparse_records(self, plan: Plan, idx: Tensor, P: int) -> Tensor:
+        """Head records [>= P, 2 + 4*order_core] (loc_x, loc_y, fourier...) of the P proposals `idx` of `plan`'s head
+        feature map: cpn_gather_patches + the sparse-heads plan, at most SPARSE_ROWS proposals per launch."""
+        lib = L.load()
+        g = plan.g
+        self._sparse_ref = dict(head_c=g.head_feat.c, head_mid=g.head_mid, k=g.head_k)
+        width = 2 + 4 * int(self.core_order)
+        chunks, start = [], 0
+        while start < P:
+            n = min(self.SPARSE_ROWS, P - start)
+            rows = 128
+            while rows < n:
+                rows *= 2
+            chunks.append((start, n, rows))
+            start += n
+        rec = torch.empty((chunks[-1][0] + chunks[-1][2], width), dtype=torch.float32, device=idx.device)
+        src_view = plan.view_of(g.head_feat)
+        for start, n, rows in chunks:                      # in order: a chunk's padding rows are overwritten by the next
+            sp = self._sparse_plan(rows)
+            dst_view = sp.view_of(sp.g.input_tensor)
+            L.check(lib.cpn_gather_patches(L.ptr(plan.arena), ctypes.byref(src_view), L.ptr(idx[start:]), n, g.head_k,
+                                           L.ptr(sp.arena), ctypes.byref(dst_view), L.stream_ptr()), 'gather_patches')
+            sp.forward(None, L.IN_F32_NCHW, [rec[start:]])
+        self.last_sparse_rows = sum(c[2] for c in chunks)
+        return rec
+
+    def _plan(self, n, h, w, dense=False) -> Plan:
         dev = self.device
         if dev.type != 'cuda':
             raise RuntimeError('celldetection_b200.CPN runs on CUDA (sm_100a) only: move the model with .cuda(). '
                                'There is no CPU fallback.')
         fast = self.precision in _SPLIT
         split = _SPLIT.get(self.precision, SPLIT_NONE)
-        key = (n, h, w, self.precision)
+        sparse = bool(self.sparse_heads) and fast and not dense
+        key = (n, h, w, self.precision, sparse)
         plan = self._plans.get(key)
         if plan is None:
             g = trace(self.arch, n, h, w, in_channels=self.in_channels, order=self.core_order,
                       refinement_margin=self.refinement_margin, stem_im2col=fast,
-                      fuse_up2=fast and os.environ.get('CPN_UP2', '1') != '0', **self._variant())
-            pack = self._packs.get(self.precision)
+                      fuse_up2=fast and os.environ.get('CPN_UP2', '1') != '0', sparse_heads=sparse,
+                      **self._variant())
+            pk = (self.precision, bool(g.sparse))
+            pack = self._packs.get(pk)
             if pack is None:
                 with torch.no_grad():
                     pack = WeightPack(g, self.state_dict(), fast, dev, split=split)
-                self._packs[self.precision] = pack
-            if len(self._plans) >= 4:
+                self._packs[pk] = pack
+            if len(self._plans) >= 8:
                 self._plans.pop(next(iter(self._plans)))
             plan = Plan(g, pack, fast, dev, split=split)
             self._plans[key] = plan
@@ -253,7 +308,7 @@ class CPN(nn.Module):
     def core_forward(self, inputs: Tensor):
         """Raw head tensors in the reference's layout: scores [N,C,h,w], locations [N,2,h,w], refinement [N,2B,H,W],
         fourier [N,4*order,h,w] (+ uncertainty [N,4,h,w] with an uncertainty head) (CPNCore.forward, cpn.py:238-283)."""
-        plan, outs, _ = self._run_plan(inputs)
+        plan, outs, _ = self._run_plan(inputs, dense=True)
         if self.cuda_graph:
             outs = [o.clone() for o in outs]       # the graph's static outputs are overwritten by the next call
         sc, lf, rf = outs[:3]
@@ -268,7 +323,8 @@ class CPN(nn.Module):
 
     # ---- post-head chain on head tensors --------------------------------------------------------------------------
     def post_flat(self, scores: Tensor, locfou: Tensor, refinement: Tensor, original_size, nms=True, offsets=None,
-                  scores_lower_bound=None, scores_upper_bound=None, flags: Tensor = None, uncertainty: Tensor = None):
+                  scores_lower_bound=None, scores_upper_bound=None, flags: Tensor = None, uncertainty: Tensor = None,
+                  plan: Plan = None):
         """models/cpn.py:575-734 on device tensors: scores [N,h,w] logits ([N,h,w,C] for classes > 2), locfou
         [N,h,w,2+4*order_core] records, refinement [N,H,W,2*buckets] (or None), uncertainty [N,h,w,4] (or None).
         Returns (flat dict of concatenated tensors, rows per image)."""
@@ -332,8 +388,13 @@ class CPN(nn.Module):
         if P > 0:
             trig = O.trig_table(order, samples, dev)
             bidx, bw = O.bucket_table(samples, buckets, dev) if (use_ref and buckets > 1) else (None, None)
-            L.check(lib.cpn_decode_refine_buckets(
-                L.ptr(idx), P, L.ptr(locfou), int(self.core_order), order, n, h, w, H, W, L.ptr(trig), samples,
+            by_row = locfou is None        # sparse heads: the records are computed now, for the selected pixels only
+            if by_row:
+                if plan is None or not getattr(plan.g, 'sparse', False):
+                    raise ValueError('post_flat needs the dense locfou tensor or the sparse-heads plan that produced the scores')
+                locfou = self._sparse_records(plan, idx, P)
+            L.check(lib.cpn_decode_refine_rows(
+                L.ptr(idx), P, L.ptr(locfou), int(by_row), int(self.core_order), order, n, h, w, H, W, L.ptr(trig), samples,
                 L.ptr(refinement) if use_ref else None, int(self.refinement_iterations) if use_ref else 0, buckets,
                 L.ptr(bidx), L.ptr(bw), L.ptr(off), L.ptr(contours), L.ptr(proposals), L.ptr(boxes), L.ptr(locations),
                 L.ptr(fourier), st), 'decode_refine')
@@ -374,7 +435,7 @@ class CPN(nn.Module):
         out.setdefault('box_uncertainties', None)
         return out
 
-    def _run_plan(self, inputs, fmt=None):
+    def _run_plan(self, inputs, fmt=None, dense=False):
         if not isinstance(inputs, Tensor) or inputs.dim() != 4:
             raise ValueError('inputs must be a 4-d Tensor')
         if not inputs.is_cuda:
@@ -387,7 +448,7 @@ class CPN(nn.Module):
             n, c, h, w = inputs.shape
         if c != self.in_channels:
             raise ValueError(f'expected {self.in_channels} input channels, got {c}')
-        plan = self._plan(n, h, w)
+        plan = self._plan(n, h, w, dense=dense)
         x = inputs.contiguous() if inputs.dtype == torch.uint8 else inputs.contiguous().float()
         plan.flags.zero_()
         outs = plan.forward_graph(x, fmt) if self.cuda_graph else plan.forward(x, fmt)
@@ -403,7 +464,7 @@ class CPN(nn.Module):
     def _post_kwargs(self, plan, outs, kwargs):
         return dict(offsets=kwargs.get('offsets'), scores_lower_bound=kwargs.get('scores_lower_bound'),
                     scores_upper_bound=kwargs.get('scores_upper_bound'), flags=plan.flags,
-                    uncertainty=outs[3] if len(outs) > 3 else None)
+                    uncertainty=outs[3] if len(outs) > 3 else None, plan=plan)
 
     def forward_flat(self, inputs, fmt=None, nms=True, **kwargs):
         """Like ``forward`` but returns (flat dict of concatenated tensors, rows per image); accepts uint8 NHWC

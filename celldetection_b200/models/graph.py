@@ -100,6 +100,8 @@ class LOp:
     im2col: Optional[Tuple[int, int]] = None   # (k, cin) of the original convolution when it runs as a 1x1 on an
                                                # im2col'd input (tensor-core stem), or of the prep op producing it
     up2: bool = False                          # 3x3 conv on the 2x nearest-up-sampled src, computed from the low-res src
+    gather: Optional[Tuple[int, int]] = None   # (k, cin): 1x1 conv over rows written by cpn_gather_patches, i.e. the
+                                               # k x k convolution evaluated at selected pixels only
 
 
 class Tracer:
@@ -139,6 +141,12 @@ class Tracer:
         op.dst.first = min(op.dst.first, i)
         op.dst.last = max(op.dst.last, i)
         return op.dst
+
+    def external(self, c, h, w):
+        """A tensor filled from outside the plan (no producing op): placed for the whole plan."""
+        t = self.tensor(c, h, w)
+        t.first, t.last = 0, 1 << 29
+        return t
 
     def prep(self, c):
         t = self._emit(LOp('prep', dst=self.tensor(c, self.h, self.w), name='input'))
@@ -387,7 +395,7 @@ HEAD_KERNEL_KEYS = ('score', 'location', 'fourier', 'uncertainty', 'refinement')
 def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_margin=3., refinement_buckets=1,
           uncertainty_head=False, stem_im2col=False, kernel_sizes=None, contour_head_channels=None,
           refinement_head_channels=None, contour_head_stride=1, refinement_head_stride=1, refinement_full_res=True,
-          fpn_channels=256, fuse_up2=False):
+          fpn_channels=256, fuse_up2=False, sparse_heads=False):
     """Trace architecture `arch` for an [n, in_channels, h, w] input.  Returns the Tracer; ``g.outputs`` maps
     'scores' / 'locfou' / 'refinement' (/ 'uncertainty') to fp32 output tensors (bindings 0 / 1 / 2 (/ 3)).
 
@@ -398,7 +406,12 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
     widths ``contour_head_channels`` / ``refinement_head_channels`` (default: the input width), the head strides
     ``contour_head_stride`` / ``refinement_head_stride``, ``refinement_full_res`` (:277-279) and ``fpn_channels``
     (fpn.py:240-322).  Contour heads that share a kernel size run as one merged convolution; the refinement tensor is
-    produced at the head's own resolution ``g.ref_hw`` (the caller resizes it to the input size when they differ, :279)."""
+    produced at the head's own resolution ``g.ref_hw`` (the caller resizes it to the input size when they differ, :279).
+
+    ``sparse_heads``: the location and fourier heads are NOT part of this plan -- they are only read at proposals
+    (cpn.py:620-623) and are evaluated there by ``trace_sparse_heads`` after the selection; the head feature map stays
+    alive until the end of the plan (``g.head_feat``) and ``g.outputs`` has no 'locfou'.  ``g.sparse`` tells whether the
+    option could be applied (stride-1 contour heads, equal location / fourier kernel sizes)."""
     assert arch in ARCHS, arch
     assert score_channels >= 1 and refinement_buckets >= 1
     ks = dict.fromkeys(HEAD_KERNEL_KEYS, 7)
@@ -444,12 +457,18 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
     if uncertainty_head:
         uncertainty = g.tensor(4, hh, hw_, f32=True, binding=3)
         dsts.append(uncertainty)
+    g.sparse = bool(sparse_heads and cs == 1 and ks['location'] == ks['fourier'] and head_c % 64 == 0)
+    g.head_feat, g.head_mid, g.head_k = head_feat, head_mid, int(ks['location'])
+    dense = list(zip(heads, dsts))
+    if g.sparse:
+        dense = [(hd, dst) for hd, dst in dense if hd[0] not in ('core.location_head', 'core.fourier_head')]
+        head_feat.last = 1 << 29           # read by cpn_gather_patches after the plan
     # heads with the same kernel size share one convolution (concatenated output channels, in module order)
-    for k in sorted({hd[3] for hd in heads}, reverse=True):
-        grp = [(hd, dst) for hd, dst in zip(heads, dsts) if hd[3] == k]
+    for k in sorted({hd[3] for hd, _ in dense}, reverse=True):
+        grp = [(hd, dst) for hd, dst in dense if hd[3] == k]
         pm = ConvParams([f'{hd[0]}.block.0.weight' for hd, _ in grp], [f'{hd[0]}.block.0.bias' for hd, _ in grp],
                         [f'{hd[0]}.block.1' for hd, _ in grp])
-        name = 'heads.block.0' if len(grp) == len(heads) else 'heads.block.0.k%d' % k
+        name = 'heads.block.0' if len(grp) == len(dense) else 'heads.block.0.k%d' % k
         mid = g.conv(head_feat, len(grp) * head_mid, k, stride=cs, act='relu', params=pm, name=name)
         assert (mid.h, mid.w) == (hh, hw_)
         for j, ((hp, co, act, _), dst) in enumerate(grp):
@@ -466,10 +485,38 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
     g.proj(rmid, refinement, 0, ref_mid, pp, act='scaled_tanh', act_scale=float(refinement_margin),
            name='core.refinement_head.block.4')
     g.outputs = OrderedDict(scores=scores, locfou=locfou, refinement=refinement)
+    if g.sparse:
+        del g.outputs['locfou']
     if uncertainty is not None:
         g.outputs['uncertainty'] = uncertainty
     g.head_hw = (hh, hw_)
     g.ref_hw = (rmid.h, rmid.w)
+    g.finalize()
+    return g
+
+
+def trace_sparse_heads(rows, head_c, head_mid, k, order):
+    """The location + fourier ReadOut heads (models/commons.py:461-511) on ``rows`` gathered k x k x head_c patches
+    (``cpn_gather_patches``; rows is a multiple of 128): ONE 1x1 convolution over K = k*k*head_c (the dense k x k
+    convolution's own contraction, in its K order) + BN + ReLU with the two final projections fused -> 'locfou' records
+    [rows, 2 + 4*order].  The gathered matrix is an external tensor [1, rows/16, 16, k*k*head_c]."""
+    assert rows % 128 == 0
+    g = Tracer(1, rows // 16, 16)
+    a = g.external(k * k * head_c, rows // 16, 16)
+    heads = [('core.location_head', 2), ('core.fourier_head', order * 4)]
+    pm = ConvParams([f'{hp}.block.0.weight' for hp, _ in heads], [f'{hp}.block.0.bias' for hp, _ in heads],
+                    [f'{hp}.block.1' for hp, _ in heads])
+    mid = g._emit(LOp('conv', src=a, dst=g.tensor(2 * head_mid, rows // 16, 16), k=1, stride=1, pad=0, act='relu',
+                      params=pm, name='sparse_heads.block.0', gather=(k, head_c)))
+    locfou = g.tensor(2 + 4 * order, rows // 16, 16, f32=True, binding=0)
+    loc_t = g.tensor(2, rows // 16, 16, f32=True, parent=locfou, c_off=0, binding=0)
+    fou_t = g.tensor(4 * order, rows // 16, 16, f32=True, parent=locfou, c_off=2, binding=0)
+    for j, ((hp, co), dst) in enumerate(zip(heads, (loc_t, fou_t))):
+        pp = ConvParams([f'{hp}.block.4.weight'], [f'{hp}.block.4.bias'], [None])
+        g.proj(mid, dst, j * head_mid, head_mid, pp, name=f'{hp}.block.4')
+    g.outputs = OrderedDict(locfou=locfou)
+    g.input_tensor = a
+    g.head_hw = (rows // 16, 16)
     g.finalize()
     return g
 
@@ -481,6 +528,8 @@ def conv_flops(g: Tracer):
     for op in g.ops:
         if op.kind == 'conv':
             kk = op.im2col[0] ** 2 * op.im2col[1] if op.im2col else (op.src.c // op.params.groups) * op.k * op.k
+            if op.gather:
+                kk = op.gather[0] ** 2 * op.gather[1]
             total += 2 * g.n * op.dst.h * op.dst.w * op.dst.c * kk
         elif op.kind == 'proj':
             total += 2 * g.n * op.dst.h * op.dst.w * op.dst.c * op.cin

@@ -139,6 +139,10 @@ class WeightPack:
             w, b = fold_conv(sd, op.params)
             if op.kind == 'conv' and getattr(op, 'up2', False):
                 w, b = up2_weights(w, b)
+            if op.kind == 'conv' and getattr(op, 'gather', None):     # k x k conv as a 1x1 over gathered patches:
+                k_, cin_ = op.gather                                   # K order [cin/64 blocks][k*k taps][64 channels]
+                cout_ = w.shape[0]
+                w = w.reshape(cout_, cin_ // 64, 64, k_, k_).permute(0, 1, 3, 4, 2).reshape(cout_, -1, 1, 1).contiguous()
             if op.kind == 'conv' and op.im2col is not None:   # [cout, cin, k, k] -> [cout, (r*k+s)*cin + c] padded
                 cout_ = w.shape[0]
                 wk = w.permute(0, 2, 3, 1).reshape(cout_, -1)
@@ -303,28 +307,41 @@ class Plan:
                     ops[i].fuse_next = nt
                     self.fused.update(range(i + 1, i + 1 + nt))
         self.ops = ops
+        self.views = dict(offsets=offsets, es=es, act_dt=act_dt)
         handle = ctypes.c_void_p()
         L.check(lib.cpn_plan_create(ops, len(g.ops), L.ptr(pack.blob), pack.blob.numel(), L.ptr(self.arena),
                                     self.arena.numel(), L.ptr(self.flags), ctypes.byref(handle)), 'plan_create')
         self.handle = handle
         self.n_launches = lib.cpn_plan_num_launches(handle)
         hh, hw = g.head_hw
-        sc = g.outputs['scores'].c      # score maps keep the historical [N,h,w] shape for a single channel
-        self.out_shapes = OrderedDict(scores=(g.n, hh, hw) if sc == 1 else (g.n, hh, hw, sc),
-                                      locfou=(g.n, hh, hw, g.outputs['locfou'].c),
-                                      refinement=(g.n,) + tuple(getattr(g, 'ref_hw', (g.h, g.w))) + (g.outputs['refinement'].c,))
-        if 'uncertainty' in g.outputs:
-            self.out_shapes['uncertainty'] = (g.n, hh, hw, 4)
+        self.out_shapes = OrderedDict()      # key -> shape; the list handed to the C plan is indexed by output binding
+        for key, t in g.outputs.items():
+            if key == 'scores':              # score maps keep the historical [N,h,w] shape for a single channel
+                self.out_shapes[key] = (g.n, hh, hw) if t.c == 1 else (g.n, hh, hw, t.c)
+            elif key == 'refinement':
+                self.out_shapes[key] = (g.n,) + tuple(getattr(g, 'ref_hw', (g.h, g.w))) + (t.c,)
+            else:
+                self.out_shapes[key] = (g.n, t.h, t.w, t.c)
+        self.out_bindings = {key: t.binding for key, t in g.outputs.items()}
 
     def new_outputs(self):
-        return [torch.empty(s, dtype=torch.float32, device=self.device) for s in self.out_shapes.values()]
+        """Output tensors indexed by binding (0 scores, 1 locfou, 2 refinement, 3 uncertainty; ``None`` where the plan has
+        no such output, e.g. 'locfou' of a sparse-heads plan)."""
+        outs = [None] * (max(self.out_bindings.values()) + 1)
+        for key, shape in self.out_shapes.items():
+            outs[self.out_bindings[key]] = torch.empty(shape, dtype=torch.float32, device=self.device)
+        return outs
+
+    def view_of(self, t: TT):
+        """C view of logical tensor `t` inside this plan's arena (for entry points that read / fill plan tensors)."""
+        return _view(t, self.g.n, self.views['offsets'], self.views['es'], self.views['act_dt'])
 
     def forward(self, x, input_format, outputs=None):
         """Enqueue the backbone + heads on the current stream.  Returns [scores, locfou, refinement(, uncertainty)]
         (fp32, in the order of ``out_shapes``)."""
         lib = L.load()
         outputs = self.new_outputs() if outputs is None else outputs
-        arr = (ctypes.c_void_p * len(outputs))(*[o.data_ptr() for o in outputs])
+        arr = (ctypes.c_void_p * len(outputs))(*[None if o is None else o.data_ptr() for o in outputs])
         L.check(lib.cpn_plan_forward(self.handle, L.ptr(x), input_format, arr, len(outputs), L.stream_ptr()),
                 'plan_forward')
         return outputs
@@ -354,7 +371,7 @@ class Plan:
 
     def run_op(self, index, x, input_format, outputs):
         lib = L.load()
-        arr = (ctypes.c_void_p * len(outputs))(*[o.data_ptr() for o in outputs])
+        arr = (ctypes.c_void_p * len(outputs))(*[None if o is None else o.data_ptr() for o in outputs])
         L.check(lib.cpn_plan_run_op(self.handle, index, L.ptr(x), input_format, arr, len(outputs), L.stream_ptr()),
                 'plan_run_op')
 

@@ -234,6 +234,24 @@ int cpn_decode_refine_buckets(const int32_t* idx, int64_t P, const float* locfou
                               const float* bucket_w, const float* offsets, float* contours, float* proposals,
                               float* boxes, float* locations, float* fourier_out, void* stream);
 
+/* cpn_decode_refine_buckets whose locfou holds one record per PROPOSAL (row i belongs to idx[i]) when records_by_row != 0
+ * -- the output of the sparse location / fourier heads (cpn_gather_patches + a 1x1 plan) -- instead of one per pixel. */
+int cpn_decode_refine_rows(const int32_t* idx, int64_t P, const float* locfou, int records_by_row, int order_core,
+                           int order, int n_images, int h, int w, int H, int W, const float* trig, int samples,
+                           const float* refinement, int iters, int buckets, const int32_t* bucket_idx,
+                           const float* bucket_w, const float* offsets, float* contours, float* proposals, float* boxes,
+                           float* locations, float* fourier_out, void* stream);
+
+/* Sparse evaluation of the ReadOut heads that are only read at proposals (location, fourier: models/cpn.py:253-263 compute
+ * them on every pixel, :620-623 gather them at the selected pixels).  For the P flat pixel indices idx (n*h*w + y*w + x,
+ * as written by cpn_select_write) of the head feature map `src` (view: fp16-family NHWC, c % 64 == 0) writes the k x k x c
+ * neighbourhood of every pixel as row i of `dst` (view with c_dst = k*k*c channels and at least P pixels, same dtype):
+ * zero outside the image, channel order [c/64 blocks][k*k taps][64 channels] -- the order in which the dense k x k
+ * convolution contracts.  A plan holding ONE 1x1 convolution over dst (weights in the same K order) plus the fused
+ * projections then yields the head records of the P proposals only.  View offsets are relative to src / dst. */
+int cpn_gather_patches(const void* src, const cpn_view_t* src_view_host, const int32_t* idx, int64_t P, int k, void* dst,
+                       const cpn_view_t* dst_view_host, void* stream);
+
 /* ops.cpn.fouriers2contours (ops/cpn.py:44-95): fourier [P,order,4], locations [P,2] -> out [P,samples,2].
  * trig as above; or sampling [P,samples] (per-proposal t, :67-71) with trig == NULL. */
 int cpn_fouriers2contours(const float* fourier, const float* locations, int64_t P, int order, int samples,

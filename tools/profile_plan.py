@@ -90,8 +90,8 @@ def timeit(fn, reps=5):
 
 import time
 t_plan = timeit(lambda: plan.forward(x, L.IN_F32_NCHW, outs))
-sc, lf, rf = outs
-t_post = timeit(lambda: m.post_flat(sc, lf, rf, (H, H)))
+sc, lf, rf = outs[:3]
+t_post = timeit(lambda: m.post_flat(sc, lf, rf, (H, H), plan=plan))   # (uncalibrated synthetic heads: few or no proposals)
 t_full = timeit(lambda: m.forward_flat(x))
 t0 = time.perf_counter()
 for _ in range(5):
