@@ -232,7 +232,7 @@ class CPN(nn.Module):
     def device(self):
         return self.order_weights.device
 
-    SPARSE_ROWS = 16384      # proposals per sparse-heads launch (the gathered matrix holds 50 KB per row at k = 7, C = 256)
+    SPARSE_ROWS = 32768      # proposals per sparse-heads launch (the gathered matrix holds 50 KB per row at k = 7, C = 256)
 
     def _sparse_plan(self, rows) -> Plan:
         """Plan of the location + fourier heads on `rows` gathered patches (graph.trace_sparse_heads)."""
