@@ -38,13 +38,16 @@ RESNETS = {
 # no CpnWideResNet*UNet.  The three BASELINE configurations come first.
 ARCHS = ('CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet') + tuple(
     f'Cpn{e}{d}' for d in ('UNet', 'FPN') for e in RESNETS
-    if not (d == 'UNet' and e.startswith('Wide')) and f'Cpn{e}{d}' not in ('CpnResNet18FPN', 'CpnResNeXt101UNet'))
+    if not (d == 'UNet' and e.startswith('Wide')) and f'Cpn{e}{d}' not in ('CpnResNet18FPN', 'CpnResNeXt101UNet')) + (
+    'CpnWideU22',)      # models/cpn.py:890-929, unet.py:497-524: U22 with doubled widths (128 ... 2048)
+# U-Net encoders of models/unet.py:405-524 by base width (CpnSlimU22's 32-channel layers are below the 64-wide MMA tile)
+U22_BASE = {'U22': 64, 'WideU22': 128}
 
 
 def split_arch(arch):
     """'CpnResNet50FPN' -> ('ResNet50', 'FPN'); 'CpnU22' -> ('U22', 'UNet')."""
-    if arch == 'CpnU22':
-        return 'U22', 'UNet'
+    if arch in ('CpnU22', 'CpnWideU22'):
+        return arch[3:], 'UNet'
     for d in ('UNet', 'FPN'):
         if arch.endswith(d) and arch[3:-len(d)] in RESNETS:
             return arch[3:-len(d)], d
@@ -422,8 +425,8 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
     bb = 'core.backbone'
     x = g.prep(in_channels)
     enc, dec = split_arch(arch)
-    if enc == 'U22':
-        feats, chans = _unet_encoder(g, x, f'{bb}.body', in_channels)
+    if enc in U22_BASE:
+        feats, chans = _unet_encoder(g, x, f'{bb}.body', in_channels, base=U22_BASE[enc])
         res, out_ch = _unet_decoder(g, feats, chans, f'{bb}.unet', bridges=0)
         head_feat, head_c, ref_feat, ref_c = res[1], out_ch[1], res[0], out_ch[0]
     elif dec == 'UNet':

@@ -51,7 +51,9 @@ RESNETS = {
     'ResNeXt152': ((3, 8, 36, 3), True, 32, 8),
     'WideResNet50': ((3, 4, 6, 3), True, 1, 128), 'WideResNet101': ((3, 4, 23, 3), True, 1, 128),
 }
-ARCHS = {'CpnU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0')}
+ARCHS = {'CpnU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0'),
+         # models/cpn.py:890-929 / unet.py:497-524: U22 with doubled channel widths (the widths are read off the state_dict)
+         'CpnWideU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0')}
 for _e in RESNETS:                       # models/cpn.py:930-1637 (the reference has no CpnWideResNet*UNet)
     ARCHS[f'Cpn{_e}FPN'] = dict(decoder='fpn', encoder=_e, head_key='1', ref_key='0')
     if not _e.startswith('Wide'):

@@ -248,7 +248,8 @@ def test_gate_passing_tensor_core_engines_meet_parity_gate(name, precision):
                                      ('CpnResNet50FPN', (96, 128)), ('CpnResNet101FPN', (64, 64)),
                                      ('CpnResNet152FPN', (64, 64)), ('CpnResNeXt50FPN', (96, 128)),
                                      ('CpnResNeXt101FPN', (64, 96)), ('CpnResNeXt152FPN', (64, 64)),
-                                     ('CpnWideResNet50FPN', (96, 128)), ('CpnWideResNet101FPN', (64, 64))])
+                                     ('CpnWideResNet50FPN', (96, 128)), ('CpnWideResNet101FPN', (64, 64)),
+                                     ('CpnWideU22', (80, 112))])
 def test_ragged_input_sizes_against_oracle(arch, hw):
     """Sizes that are not multiples of the encoder stride: partial conv tiles, non-integer nearest up-sampling factors
     (floor(dst * in / out)), odd max-pool extents, bilinear resize for the FPN refinement features.  Checked directly
@@ -668,3 +669,19 @@ def test_gather_patches_matches_unfold():
                         got = d_cpu[r, blk * ct + (cb * k * k + t) * 64: blk * ct + (cb * k * k + t) * 64 + 64]
                         assert torch.equal(got, want), (dtype, blk, r, cb, t)
         assert float(d_cpu[P:].min()) == 7.            # rows beyond P untouched
+
+
+def test_sparse_heads_chunking_is_invariant():
+    """More proposals than one sparse-heads launch holds (SPARSE_ROWS): the chunked evaluation returns the same records."""
+    z = load_npz('model_cpnu22_n2_96x160_s64')
+    m, (n, h, w) = _model(z, 'fp16f8')
+    x = torch.from_numpy(z['x']).cuda()
+    a = m(x, nms=False)
+    total = sum(len(s) for s in a['scores'])
+    assert total > 600
+    m.SPARSE_ROWS = 256                      # instance attribute: forces ceil(total / 256) launches
+    b = m(x, nms=False)
+    assert m.last_sparse_rows >= total and m.last_sparse_rows % 128 == 0
+    for i in range(n):
+        for key in ('scores', 'locations', 'fourier', 'contours'):
+            assert torch.equal(a[key][i], b[key][i]), key
