@@ -53,6 +53,7 @@ SYMBOLS = {
     'cpn_device_info': (_I, [ctypes.c_char_p, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     'cpn_plan_create': (_I, [ctypes.POINTER(Op), _I, _P, _SZ, _P, _SZ, _P, ctypes.POINTER(_P)]),
     'cpn_plan_forward': (_I, [_P, _P, _I, ctypes.POINTER(_P), _I, _P]),
+    'cpn_plan_forward_range': (_I, [_P, _I, _I, _P, _I, ctypes.POINTER(_P), _I, _P]),
     'cpn_plan_num_launches': (_I, [_P]),
     'cpn_plan_run_op': (_I, [_P, _I, _P, _I, ctypes.POINTER(_P), _I, _P]),
     'cpn_plan_destroy': (None, [_P]),

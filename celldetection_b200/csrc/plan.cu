@@ -182,8 +182,16 @@ static int run_op(cpn_plan* pl, int i, const void* input, int input_format, void
 extern "C" int cpn_plan_forward(cpn_plan_t* plan, const void* input, int input_format, void* const* outputs_host,
                                 int n_outputs, void* stream) {
   CPN_REQUIRE(plan, "plan_forward: NULL plan");
+  return cpn_plan_forward_range(plan, 0, (int)plan->ops.size(), input, input_format, outputs_host, n_outputs, stream);
+}
+
+extern "C" int cpn_plan_forward_range(cpn_plan_t* plan, int first_op, int end_op, const void* input, int input_format,
+                                      void* const* outputs_host, int n_outputs, void* stream) {
+  CPN_REQUIRE(plan, "plan_forward_range: NULL plan");
+  CPN_REQUIRE(first_op >= 0 && first_op <= end_op && end_op <= (int)plan->ops.size(), "plan_forward_range: bad range [%d, %d)",
+              first_op, end_op);
   cudaStream_t st = (cudaStream_t)stream;
-  for (int i = 0; i < (int)plan->ops.size(); ++i) {
+  for (int i = first_op; i < end_op; ++i) {
     if (run_op(plan, i, input, input_format, outputs_host, n_outputs, st)) return 1;
     const cpn_op_t& op = plan->ops[i];
     if (op.kind == CPN_OP_CONV && op.engine == CPN_ENGINE_TCGEN05) i += op.fuse_next;  // ran inside the epilogue

@@ -324,7 +324,7 @@ class CPN(nn.Module):
     # ---- post-head chain on head tensors --------------------------------------------------------------------------
     def post_flat(self, scores: Tensor, locfou: Tensor, refinement: Tensor, original_size, nms=True, offsets=None,
                   scores_lower_bound=None, scores_upper_bound=None, flags: Tensor = None, uncertainty: Tensor = None,
-                  plan: Plan = None):
+                  plan: Plan = None, after_count=None):
         """models/cpn.py:575-734 on device tensors: scores [N,h,w] logits ([N,h,w,C] for classes > 2), locfou
         [N,h,w,2+4*order_core] records, refinement [N,H,W,2*buckets] (or None), uncertainty [N,h,w,4] (or None).
         Returns (flat dict of concatenated tensors, rows per image)."""
@@ -365,7 +365,21 @@ class CPN(nn.Module):
         L.check(lib.cpn_select_count_ex(sel, pixels, L.ptr(ws), L.ptr(meta), st), 'select_count')
         if flags is not None:
             meta[1:2].copy_(flags[:1].to(torch.int64))
-        total, flag = meta.tolist()                       # host sync #1 (the reference syncs at torch.where)
+        # host sync #1 (the reference syncs at torch.where): the count travels to pinned memory asynchronously; whatever
+        # `after_count` enqueues (the rest of a staged plan: full-resolution branch + refinement head) keeps the GPU busy
+        # while the host waits for the count and queues the proposal-dependent kernels behind it
+        host_meta = self.__dict__.get('_meta_host')
+        if host_meta is None:
+            host_meta = self.__dict__['_meta_host'] = torch.empty((2,), dtype=torch.int64).pin_memory()
+        host_meta.copy_(meta, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        if after_count is not None:
+            late = after_count()
+            if late is not None:
+                refinement = late
+        ready.synchronize()
+        total, flag = host_meta.tolist()
         if flag & 1:
             raise AssertionError('Inputs should be in interval (0.0, 1.0)')
         P = int(total)
@@ -435,7 +449,7 @@ class CPN(nn.Module):
         out.setdefault('box_uncertainties', None)
         return out
 
-    def _run_plan(self, inputs, fmt=None, dense=False):
+    def _run_plan(self, inputs, fmt=None, dense=False, staged=False):
         if not isinstance(inputs, Tensor) or inputs.dim() != 4:
             raise ValueError('inputs must be a 4-d Tensor')
         if not inputs.is_cuda:
@@ -451,15 +465,31 @@ class CPN(nn.Module):
         plan = self._plan(n, h, w, dense=dense)
         x = inputs.contiguous() if inputs.dtype == torch.uint8 else inputs.contiguous().float()
         plan.flags.zero_()
-        outs = plan.forward_graph(x, fmt) if self.cuda_graph else plan.forward(x, fmt)
-        rf = outs[2]
-        if tuple(rf.shape[1:3]) != (h, w):       # strided / low-res refinement head: _equal_size to the input (cpn.py:279)
+
+        def full_res(rf):
+            if tuple(rf.shape[1:3]) == (h, w):
+                return rf
+            # strided / low-res refinement head: _equal_size to the input (cpn.py:279)
             full = torch.empty((n, h, w, rf.shape[3]), dtype=torch.float32, device=rf.device)
             L.check(L.load().cpn_resize_bilinear(L.ptr(rf), n, int(rf.shape[1]), int(rf.shape[2]), int(rf.shape[3]),
                                                  L.ptr(full), h, w, L.stream_ptr()), 'resize_bilinear')
-            outs = list(outs)
-            outs[2] = full
-        return plan, outs, (h, w)
+            return full
+
+        split = getattr(plan.g, 'split_index', None)
+        # staged execution is opt-in (CPN_STAGED=1): measured 343.5 / 343.7 tiles/s without vs 342.6 / 342.6 with it
+        # (profiles/r02n_*): the step's tail is GPU work of the proposal kernels, not host gaps
+        if staged and split and not self.cuda_graph and os.environ.get('CPN_STAGED', '0') == '1':
+            # stage 1: everything up to the dense heads; stage 2 (`rest`) is enqueued by post_flat right after the
+            # proposal count has been requested
+            outs = plan.forward(x, fmt, None, 0, split)
+
+            def rest():
+                plan.forward(x, fmt, outs, split, None)
+                return full_res(outs[2])
+            return plan, outs, (h, w), rest
+        outs = list(plan.forward_graph(x, fmt) if self.cuda_graph else plan.forward(x, fmt))
+        outs[2] = full_res(outs[2])
+        return (plan, outs, (h, w), None) if staged else (plan, outs, (h, w))
 
     def _post_kwargs(self, plan, outs, kwargs):
         return dict(offsets=kwargs.get('offsets'), scores_lower_bound=kwargs.get('scores_lower_bound'),
@@ -469,8 +499,9 @@ class CPN(nn.Module):
     def forward_flat(self, inputs, fmt=None, nms=True, **kwargs):
         """Like ``forward`` but returns (flat dict of concatenated tensors, rows per image); accepts uint8 NHWC
         batches (``fmt=_lib.IN_U8_NHWC``) so tile crops need no host-side transpose."""
-        plan, outs, hw = self._run_plan(inputs, fmt)
-        return self.post_flat(outs[0], outs[1], outs[2], hw, nms=nms, **self._post_kwargs(plan, outs, kwargs))
+        plan, outs, hw, rest = self._run_plan(inputs, fmt, staged=True)
+        return self.post_flat(outs[0], outs[1], outs[2], hw, nms=nms, after_count=rest,
+                              **self._post_kwargs(plan, outs, kwargs))
 
     # ---- model(x) ---------------------------------------------------------------------------------------------------
     def forward(self, inputs: Tensor, targets=None, nms=True, **kwargs):
@@ -478,8 +509,8 @@ class CPN(nn.Module):
             if self.training and targets is None:
                 raise ValueError('In training mode, targets should be passed')
             raise NotImplementedError('celldetection_b200 accelerates CPN inference only (use .eval()).')
-        plan, outs, hw = self._run_plan(inputs)
-        return self.post(outs[0], outs[1], outs[2], hw, nms=nms, **self._post_kwargs(plan, outs, kwargs))
+        plan, outs, hw, rest = self._run_plan(inputs, staged=True)
+        return self.post(outs[0], outs[1], outs[2], hw, nms=nms, after_count=rest, **self._post_kwargs(plan, outs, kwargs))
 
 
 def _make(arch):

@@ -209,6 +209,30 @@ class Tracer:
         return self._emit(LOp('proj', src=x, dst=dst, cin_off=cin_off, cin=cin, params=params, act=act,
                               act_scale=act_scale, name=name))
 
+    def move_ops(self, names, after_tensor):
+        """Reorder: the ops named `names` (in their current order) move directly behind the LAST op that writes
+        `after_tensor`; access ranges are recomputed.  Returns the index one past the moved block."""
+        moved = [o for o in self.ops if o.name in names]
+        rest = [o for o in self.ops if o.name not in names]
+        pos = max(i for i, o in enumerate(rest) if o.dst is after_tensor) + 1
+        self.ops = rest[:pos] + moved + rest[pos:]
+        keep = {t.id: (t.first, t.last) for t in self.tensors if t.last >= (1 << 29) or (t.first == 0 and t.last >= (1 << 29))}
+        for t in self.tensors:
+            t.first, t.last = 1 << 30, -1
+        for i, op in enumerate(self.ops):
+            for t in (op.src, op.res):
+                if t is not None:
+                    t.last = max(t.last, i)
+            op.dst.first = min(op.dst.first, i)
+            op.dst.last = max(op.dst.last, i)
+        for t in self.tensors:
+            if t.id in keep:
+                t.first, t.last = min(t.first, keep[t.id][0]), keep[t.id][1]
+            if t.parent is not None:                       # cat: the shared buffer spans its slices
+                r = t.root()[0]
+                r.first, r.last = min(r.first, t.first), max(r.last, t.last)
+        return pos + len(moved)
+
     def finalize(self):
         # propagate access ranges of slices to their roots
         for t in self.tensors:
@@ -494,6 +518,13 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
         g.outputs['uncertainty'] = uncertainty
     g.head_hw = (hh, hw_)
     g.ref_hw = (rmid.h, rmid.w)
+    g.split_index = None
+    if g.sparse:
+        # the dense heads (score, uncertainty) run as soon as their features exist: the host reads the proposal count
+        # while the GPU is still busy with the full-resolution branch and the refinement head (ops [split_index, end))
+        head_ops = [o.name for o in g.ops if o.name.startswith('heads.block.0') or
+                    o.name in ('core.score_head.block.4', 'core.uncertainty_head.block.4')]
+        g.split_index = g.move_ops(head_ops, head_feat)
     g.finalize()
     return g
 

@@ -336,14 +336,19 @@ class Plan:
         """C view of logical tensor `t` inside this plan's arena (for entry points that read / fill plan tensors)."""
         return _view(t, self.g.n, self.views['offsets'], self.views['es'], self.views['act_dt'])
 
-    def forward(self, x, input_format, outputs=None):
-        """Enqueue the backbone + heads on the current stream.  Returns [scores, locfou, refinement(, uncertainty)]
-        (fp32, in the order of ``out_shapes``)."""
+    def forward(self, x, input_format, outputs=None, first=0, end=None):
+        """Enqueue the backbone + heads (or only ops [first, end)) on the current stream.  Returns the output list
+        indexed by binding: [scores, locfou, refinement(, uncertainty)] (fp32)."""
         lib = L.load()
         outputs = self.new_outputs() if outputs is None else outputs
         arr = (ctypes.c_void_p * len(outputs))(*[None if o is None else o.data_ptr() for o in outputs])
-        L.check(lib.cpn_plan_forward(self.handle, L.ptr(x), input_format, arr, len(outputs), L.stream_ptr()),
-                'plan_forward')
+        if first == 0 and end is None:
+            L.check(lib.cpn_plan_forward(self.handle, L.ptr(x), input_format, arr, len(outputs), L.stream_ptr()),
+                    'plan_forward')
+        else:
+            L.check(lib.cpn_plan_forward_range(self.handle, int(first), len(self.g.ops) if end is None else int(end),
+                                               L.ptr(x), input_format, arr, len(outputs), L.stream_ptr()),
+                    'plan_forward_range')
         return outputs
 
     def forward_graph(self, x, input_format):

@@ -144,6 +144,11 @@ int cpn_plan_create(const cpn_op_t* ops_host, int n_ops, const void* weights, si
  * pointer bound to ops with out_binding == k. */
 int cpn_plan_forward(cpn_plan_t* plan, const void* input, int input_format, void* const* outputs_host, int n_outputs,
                      void* stream);
+/* Runs ops [first_op, end_op) only (fused projections travel with their convolution and must not be split from it).  The
+ * host uses it to enqueue the score head first, start the read-back of the proposal count, and enqueue the rest of the plan
+ * (the full-resolution branch and the refinement head) while that read-back is in flight. */
+int cpn_plan_forward_range(cpn_plan_t* plan, int first_op, int end_op, const void* input, int input_format,
+                           void* const* outputs_host, int n_outputs, void* stream);
 /* Kernel launches one forward of this plan issues. */
 int cpn_plan_num_launches(const cpn_plan_t* plan);
 /* Debug/profiling: run only op `index` (same bindings as forward). */
