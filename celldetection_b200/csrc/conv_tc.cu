@@ -88,6 +88,7 @@ struct ConvTcParams {
   int up2;                  // CPN_CONV_UP2: the accumulator's 4 x 64-channel column groups are the four phases of a 2x
                             // up-sampled output: pixel (y, x), column (2a+b)*cup + c -> out[(2y+a, 2x+b), c]
   int cup, Ho2, Wo2;        // up2: channels per phase, output extent
+  int up2_skip;             // up2 with cup % BN == 0: an N tile is ONE phase (a, b) and needs only its 2 x 2 of the 3 x 3 taps
   int tap2;                 // conv_tap2_kernel: 64-wide layers, two horizontally adjacent filter taps per N = 128 instruction
   int dbg_epi;              // experiment switch CPN_DBG_EPI=1: the coalesced epilogue skips its global loads / stores
   int coalesce;             // conv_tc_kernel: smem-staged, line-coalesced residual loads / output stores (epilogue_coalesced)
@@ -1237,7 +1238,10 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
             cbw = split_pass_order(pi, p.split_lofirst) * cbl + (cb - pi * cbl);
           }                                               // split == 2: (W8 | W16) is already in issue order
           int tap = p.rotate ? (int)(blockIdx.x % (unsigned)taps) : 0;
-          for (int it = 0; it < taps; ++it, tap = (tap + 1 == taps ? 0 : tap + 1)) {
+          const int ph_ = p.up2_skip ? n0 / p.cup : 0;                 // phase (a, b) of this N tile
+          const int ntap = p.up2_skip ? 4 : taps;
+          for (int it = 0; it < ntap; ++it, tap = (tap + 1 == taps ? 0 : tap + 1)) {
+            if (p.up2_skip) tap = ((ph_ >> 1) + (it >> 1)) * 3 + (ph_ & 1) + (it & 1);   // rows a, a+1 x columns b, b+1
             mbar_wait(smem_u32(&bar_bempty[sb]), phb ^ 1);
             const uint32_t full = smem_u32(&bar_bfull[sb]);
             mbar_expect_tx(full, B_BYTES);
@@ -1301,7 +1305,10 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_halo_kernel(const __grid_
         tc_fence_after();
         const uint32_t patch = a_base + ab * patch_bytes;
         int tap = p.rotate ? (int)(blockIdx.x % (unsigned)taps) : 0;
-        for (int it = 0; it < taps; ++it, tap = (tap + 1 == taps ? 0 : tap + 1)) {
+        const int ph_ = p.up2_skip ? (int)(tile % p.tiles_n) * BN / p.cup : 0;
+        const int ntap = p.up2_skip ? 4 : taps;
+        for (int it = 0; it < ntap; ++it, tap = (tap + 1 == taps ? 0 : tap + 1)) {
+          if (p.up2_skip) tap = ((ph_ >> 1) + (it >> 1)) * 3 + (ph_ & 1) + (it & 1);
           const int r = tap / p.S, s_ = tap - r * p.S;
           mbar_wait(smem_u32(&bar_bfull[sb]), phb);
           tc_fence_after();
@@ -1859,6 +1866,11 @@ int conv_tc_plan_create(const cpn_op_t& op_in, const void* src, void* dst, const
   if (up2) {
     CPN_REQUIRE(p.halo && p.coalesce && !p.tap2, "conv_tc: CPN_CONV_UP2 needs the halo kernel with the coalesced epilogue");
     p.up2 = 1; p.cup = op_in.dst.c; p.Ho2 = op_in.dst.h; p.Wo2 = op_in.dst.w;
+    {
+      static int skip_env = -1;   // CPN_UP2_SKIP=0: issue all nine taps for every phase (A/B switch)
+      if (skip_env < 0) { const char* e = getenv("CPN_UP2_SKIP"); skip_env = (e && atoi(e) == 0) ? 0 : 1; }
+      p.up2_skip = (skip_env && p.cup % bn == 0 && !p.rotate) ? 1 : 0;
+    }
   }
   pl->smem_bytes = pl->stages * stage_bytes + 1024 + (p.coalesce ? TC_STAGING_BYTES : 0);
   if (p.halo) pl->smem_bytes = p.nb_stages * bn * TC_BK * 2 * (p.tap2 ? 2 : 1) + 2 * 8 * p.plane_stride + 1024 +

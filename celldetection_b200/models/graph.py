@@ -83,6 +83,8 @@ class ConvParams:
     bias: List[Optional[str]]
     bn: List[Optional[str]]           # BatchNorm prefix per weight key
     groups: int = 1
+    cin_range: Optional[Tuple[int, int]] = None   # contract over this slice of the (folded) weight's input channels only
+    no_bias: bool = False                         # the folded bias is applied by another op of the same convolution
 
 
 @dataclass
@@ -184,6 +186,18 @@ class Tracer:
         (plan.up2_weights; tensor-core engines only)."""
         return self._emit(LOp('conv', src=x, dst=self.tensor(cout, 2 * x.h, 2 * x.w), k=3, stride=1, pad=1, act=act,
                               params=params, name=name, up2=True))
+
+    def conv_cat_up2(self, lateral, top, cout, act, params, name):
+        """``conv3x3(cat(lateral, interpolate(top, x2 nearest)))`` (models/unet.py:213-224 + the block's first conv) as two
+        convolutions over the two halves of its input channels: the up-sampled half runs as phase kernels on the low-res
+        `top` (each output phase needs 2 x 2 of the 3 x 3 low-res taps: 16 instead of 36 tap-products per source pixel) and
+        writes the partial sum; the lateral half adds it through the residual input, with the bias and the activation.
+        Neither the up-sampled tensor nor the concatenation exists."""
+        from dataclasses import replace
+        part = self.conv_up2(top, cout, act='none', name=name + '.up',
+                             params=replace(params, cin_range=(lateral.c, lateral.c + top.c), no_bias=True))
+        return self._emit(LOp('conv', src=lateral, dst=self.tensor(cout, lateral.h, lateral.w), res=part, k=3, stride=1,
+                              pad=1, act=act, params=replace(params, cin_range=(0, lateral.c)), name=name))
 
     def maxpool(self, x, k, stride, pad):
         ho, wo = (x.h + 2 * pad - k) // stride + 1, (x.w + 2 * pad - k) // stride + 1
@@ -369,6 +383,14 @@ def _unet_decoder(g, feats, chans, p, bridges):
         bp = f'{p}.layer_blocks.{i}'
         pa = ConvParams([f'{bp}.0.weight'], [f'{bp}.0.bias' if bias else None], [f'{bp}.1'])
         pb = ConvParams([f'{bp}.3.weight'], [f'{bp}.3.bias' if bias else None], [f'{bp}.4'])
+        if (lateral is not None and g.fuse_up2 and (lateral.h, lateral.w) == (2 * top.h, 2 * top.w) and
+                lateral.parent is None and lateral.c % 64 == 0 and top.c % 64 == 0 and ouc % 256 == 0 and
+                lateral.c + top.c == cin):
+            x = g.conv_cat_up2(lateral, top, ouc, 'relu', pa, f'{bp}.0')
+            x = g.conv(x, ouc, 3, act='relu', params=pb, name=f'{bp}.3')
+            last, last_c = x, ouc
+            results[i] = x
+            continue
         if lateral is not None:
             up = g.upsample(top, lateral.h, lateral.w)
             x = g.cat(lateral, up)               # cat_order 0: (lateral, top_down) (unet.py:219-224)
@@ -562,6 +584,8 @@ def conv_flops(g: Tracer):
     for op in g.ops:
         if op.kind == 'conv':
             kk = op.im2col[0] ** 2 * op.im2col[1] if op.im2col else (op.src.c // op.params.groups) * op.k * op.k
+            if op.up2 and op.params.cin_range is not None:
+                kk = kk * 4 // 9          # phase N tiles issue their 2 x 2 taps only (the reference formulation: 9 taps)
             if op.gather:
                 kk = op.gather[0] ** 2 * op.gather[1]
             total += 2 * g.n * op.dst.h * op.dst.w * op.dst.c * kk

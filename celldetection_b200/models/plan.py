@@ -42,7 +42,12 @@ def fold_conv(sd, params):
             b = (b - mean) * scale + beta
         ws.append(w)
         bs.append(b)
-    return torch.cat(ws, 0), torch.cat(bs, 0)
+    w, b = torch.cat(ws, 0), torch.cat(bs, 0)
+    if getattr(params, 'cin_range', None) is not None:       # this op contracts over a slice of the input channels
+        w = w[:, params.cin_range[0]:params.cin_range[1]].contiguous()
+    if getattr(params, 'no_bias', False):
+        b = torch.zeros_like(b)
+    return w, b
 
 
 def slab_of(cin, cout, groups):
