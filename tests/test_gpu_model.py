@@ -547,7 +547,8 @@ res = cd.apply_model(img, [m], crop_size=256, strides=192, batch_size=4)
 h = hashlib.sha256()
 for k in ('boxes', 'scores', 'contours', 'classes', 'locations', 'fourier', 'contour_proposals'):
     h.update(res[k].cpu().numpy().tobytes())
-print('DIGEST', int(res['scores'].shape[0]), h.hexdigest(), flush=True)
+with open(sys.argv[2] + '.%d' % int(os.environ.get('RANK', '0')), 'w') as f:     # (ranks' prints may interleave on stdout)
+    f.write('%d %s' % (int(res['scores'].shape[0]), h.hexdigest()))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
@@ -563,16 +564,17 @@ def test_sharded_slide_is_bit_identical_to_single_gpu(tmp_path):
     script = tmp_path / 'worker.py'
     script.write_text(_NCCL_WORKER)
     env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
-    one = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600, env=env)
+    one = subprocess.run([sys.executable, str(script), ROOT, str(tmp_path / 'one')], capture_output=True, text=True,
+                         timeout=600, env=env)
     assert one.returncode == 0, one.stderr[-2000:]
-    want = [l for l in one.stdout.splitlines() if l.startswith('DIGEST')]
+    want = [(tmp_path / 'one.0').read_text()]
     port = str(29600 + os.getpid() % 300)
     two = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-                          '--master-addr', '127.0.0.1', '--master-port', port, str(script), ROOT],
+                          '--master-addr', '127.0.0.1', '--master-port', port, str(script), ROOT, str(tmp_path / 'two')],
                          capture_output=True, text=True, timeout=900, env=env)
     assert two.returncode == 0, two.stderr[-2000:]
-    got = [l for l in two.stdout.splitlines() if l.startswith('DIGEST')]
-    assert len(want) == 1 and len(got) == 2 and int(want[0].split()[1]) > 50
+    got = [(tmp_path / ('two.%d' % r)).read_text() for r in range(2)]
+    assert len(want) == 1 and len(got) == 2 and int(want[0].split()[0]) > 50
     assert got[0] == got[1] == want[0], (want, got)
 
 
