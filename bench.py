@@ -422,7 +422,6 @@ def batch1_latency(model, x1):
 def config_c2(dev, peaks):
     """BASELINE configs[1]: CpnResNet18FPN, batch 32x3x512x512, headline engine (side leg, a few steps)."""
     from celldetection_b200.models.graph import conv_flops
-    global ARCH
     arch = 'CpnResNet18FPN'
     m, _ = make_model(arch, HEADLINE, dev, seed_offset=5)
     g = torch.Generator().manual_seed(SEED + 31)

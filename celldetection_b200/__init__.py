@@ -10,5 +10,6 @@ from . import models
 from . import data
 from .utils import load_model, fetch_model, save_fetchable_model, synth_state_dict, calibrate_heads_
 from .inference import get_tiling_slices, apply_model, cpn_inference
+from .preprocessing import preprocess
 
 __version__ = '0.1.0'

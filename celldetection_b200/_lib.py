@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libcpn_b200.so')
 ABI_VERSION = 4
 
 # ---- enums (mirror include/cpn_b200.h) -------------------------------------------------------------------------------
-DT_F32, DT_F16, DT_U8, DT_F16X2, DT_F16F8 = 0, 1, 2, 3, 4
+DT_F32, DT_F16, DT_U8, DT_F16X2, DT_F16F8, DT_U16 = 0, 1, 2, 3, 4, 5
 OP_PREP, OP_CONV, OP_MAXPOOL, OP_UPSAMPLE, OP_BILINEAR, OP_PROJ = range(6)
 IN_F32_NCHW, IN_U8_NCHW, IN_U8_NHWC = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SCALED_TANH, ACT_SIGMOID = 0, 1, 2, 3
@@ -84,6 +84,9 @@ SYMBOLS = {
     'cpn_resolve_label_channels_workspace_bytes': (_SZ, [_I, _I]),
     'cpn_resolve_label_channels': (_I, [_P, _I, _I, _I, _I, _P, _P, ctypes.POINTER(_I), _P]),
     'cpn_gather_rows': (_I, [_P, _I64, _P, _I64, _P, _P]),
+    'cpn_histogram': (_I, [_P, _I, _I64, _P, _P]),
+    'cpn_apply_lut': (_I, [_P, _I, _I64, _P, _P, _P]),
+    'cpn_rgb2gray': (_I, [_P, _I, _I64, _I, _P, _P, _P]),
 }
 
 _lib = None

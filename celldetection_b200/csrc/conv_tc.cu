@@ -25,13 +25,19 @@
 // Grouped convolutions use BN = 64 and contract only over their 64-channel block-diagonal slab (cpn_op_t::kslab).
 // Layers without a fused projection use the COAL kernel variants: a line-coalesced, shared-memory-staged epilogue
 // (epilogue_coalesced) for residual loads and output stores.
-// Environment switches (experiments, see profiles/r01_summary.md): CPN_HALO=0, CPN_HALO_ALL=0, CPN_HALO_SW128=0,
-// CPN_HALO_BASEOFF=1, CPN_HALO_SWAP=1, CPN_ROTATE=1, CPN_COALESCE=0, CPN_COALESCE_HALO=0, CPN_COALESCE_SPLIT=0,
-// CPN_SPLIT_LOFIRST=0.
+// Round 2: the 2-pass engine (CPN_DT_F16F8: one kind::f8f6f4 pass over e4m3 copies of the operands' rounding residuals, then
+// the kind::f16 pass, same TMEM accumulator, epilogue scale 1/S), conv_tap2_kernel (two adjacent taps per N = 128 instruction
+// for the 64-wide 7x7 layers), CPN_CONV_UP2 (conv3x3 o nearest x2 as phase kernels on the low-res map, pixel-shuffle store,
+// 2 x 2 of 3 x 3 taps per phase N tile), conv_pair_kernel (CTA pairs, cta_group::2; opt-in).
+// Environment switches (experiments, see profiles/r01_summary.md / r02_summary.md): CPN_HALO=0, CPN_HALO_ALL=0,
+// CPN_HALO_SW128=0, CPN_HALO_BASEOFF=1, CPN_HALO_SWAP=1, CPN_ROTATE=1, CPN_COALESCE=0, CPN_COALESCE_HALO=0,
+// CPN_COALESCE_SPLIT=0, CPN_SPLIT_LOFIRST=0, CPN_PAIR=1, CPN_TAP2=0|2, CPN_UP2_SKIP=0, CPN_BN_1X1=64|128, CPN_TC_STAGES=n,
+// CPN_DBG_EPI=1 (timing experiments only: the coalesced epilogue skips its global traffic, results are garbage).
 #include "common.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <memory>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -1719,7 +1725,8 @@ int conv_tc_plan_create(const cpn_op_t& op_in, const void* src, void* dst, const
               "conv_tc: output shape mismatch (%dx%d expected %dx%d)", op.dst.h, op.dst.w, eh, ew);
   CPN_REQUIRE(op.slab_mode == 0 ? op.kslab <= op.src.c : true, "conv_tc: kslab exceeds input channels");
 
-  ConvTcPlan* pl = new ConvTcPlan();
+  std::unique_ptr<ConvTcPlan> owner(new ConvTcPlan());     // released to the caller on success only
+  ConvTcPlan* pl = owner.get();
   ConvTcParams& p = pl->p;
   memset(&p, 0, sizeof(p));
   int bn = pick_bn(op.dst.c, op.slab_mode);
@@ -1748,7 +1755,7 @@ int conv_tc_plan_create(const cpn_op_t& op_in, const void* src, void* dst, const
     cuuint64_t strides[3] = {(cuuint64_t)st * op.src.pitch * 2, (cuuint64_t)st * op.src.w * op.src.pitch * 2,
                              (cuuint64_t)op.src.h * op.src.w * op.src.pitch * 2};
     cuuint32_t box[4] = {TC_BK, TC_BW, TC_BH, 1};
-    if (encode_map(&p.tmA[m], const_cast<char*>(base), 4, dims, strides, box)) { delete pl; return 1; }
+    if (encode_map(&p.tmA[m], const_cast<char*>(base), 4, dims, strides, box)) return 1;
   }
   for (int m = nmaps; m < 4; ++m) p.tmA[m] = p.tmA[0];
   {
@@ -1756,7 +1763,7 @@ int conv_tc_plan_create(const cpn_op_t& op_in, const void* src, void* dst, const
     cuuint64_t dims[3] = {kw, (cuuint64_t)op.dst.c, (cuuint64_t)(op.r * op.s)};
     cuuint64_t strides[2] = {kw * 2, kw * op.dst.c * 2};
     cuuint32_t box[3] = {TC_BK, (cuuint32_t)bn, 1};
-    if (encode_map(&p.tmB, const_cast<void*>(wgt), 3, dims, strides, box)) { delete pl; return 1; }
+    if (encode_map(&p.tmB, const_cast<void*>(wgt), 3, dims, strides, box)) return 1;
   }
   p.out = reinterpret_cast<__half*>(dst);
   p.res = op.res.n ? reinterpret_cast<const __half*>(res) : nullptr;
@@ -1811,7 +1818,7 @@ int conv_tc_plan_create(const cpn_op_t& op_in, const void* src, void* dst, const
         cuuint64_t strides[3] = {(cuuint64_t)op.src.pitch * 2, (cuuint64_t)op.src.w * op.src.pitch * 2,
                                  (cuuint64_t)op.src.h * op.src.w * op.src.pitch * 2};
         cuuint32_t box[4] = {(cuuint32_t)(sw128_env ? 64 : 8), (cuuint32_t)pw, (cuuint32_t)ph, 1};
-        if (encode_map(&p.tmH, const_cast<void*>(src), 4, dims, strides, box, sw128_env != 0)) { delete pl; return 1; }
+        if (encode_map(&p.tmH, const_cast<void*>(src), 4, dims, strides, box, sw128_env != 0)) return 1;
         p.halo_sw128 = sw128_env; p.halo_baseoff = baseoff_env;
         CPN_REQUIRE(!f16f8 || sw128_env, "conv_tc: the fp16+e4m3 engine needs the SWIZZLE_128B halo patch (CPN_HALO_SW128)");
         p.halo = 1; p.pw = pw; p.ph = ph; p.plane_stride = plane_stride; p.nb_stages = nbs; p.swap_lbo_sbo = swap_env;
@@ -1891,7 +1898,7 @@ int conv_tc_plan_create(const cpn_op_t& op_in, const void* src, void* dst, const
         cuuint64_t dims[3] = {kw, (cuuint64_t)op.dst.c, (cuuint64_t)(op.r * op.s)};
         cuuint64_t strides[2] = {kw * 2, kw * op.dst.c * 2};
         cuuint32_t box[3] = {TC_BK, (cuuint32_t)(TCP_BN / 2), 1};
-        if (encode_map(&p.tmB, const_cast<void*>(wgt), 3, dims, strides, box)) { delete pl; return 1; }
+        if (encode_map(&p.tmB, const_cast<void*>(wgt), 3, dims, strides, box)) return 1;
       }
       pl->pair = 1;
       pl->stages = TC_SMEM_BUDGET / (int)TCP_STAGE_BYTES;
@@ -1902,7 +1909,7 @@ int conv_tc_plan_create(const cpn_op_t& op_in, const void* src, void* dst, const
       pl->grid = (int)(2 * pairs);
     }
   }
-  *out = pl;
+  *out = owner.release();
   return 0;
 }
 

@@ -868,3 +868,179 @@ extern "C" int cpn_resize_bilinear(const float* src, int n, int h, int w, int c,
   return cpn::bilinear_launch(op, src, dst, (cudaStream_t)stream);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PREPROCESS (celldetection_scripts/cpn_inference.py:196-222, cd.data.normalize_percentile data/misc.py:156-161): the
+// input-side conditioning of a whole slide before tiling.  Integer work, HBM-bound: an exact histogram (the host derives
+// np.percentile's order statistics, the image mean and every look-up table from it) and ONE table look-up per element that
+// composes percentile normalisation -> uint8, gamma and brightness / contrast.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace cpn {
+// uint8: every warp owns a private 256-bin histogram in shared memory (no inter-warp contention), 16 values per 16-byte load;
+// the block's eight copies are flushed with one global atomic per non-empty bin.
+__global__ void __launch_bounds__(256) histogram_u8_kernel(const uint8_t* __restrict__ data, long long n,
+                                                           unsigned int* __restrict__ hist) {
+  __shared__ unsigned int h[8][256];
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+  __syncthreads();
+  unsigned int* mine = h[threadIdx.x >> 5];
+  const long long nvec = (reinterpret_cast<uintptr_t>(data) & 15) ? 0 : n / 16;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const uint4* v4 = reinterpret_cast<const uint4*>(data);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 q = __ldg(v4 + i);
+    const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(mine + (w[k] & 255u), 1u);
+      atomicAdd(mine + ((w[k] >> 8) & 255u), 1u);
+      atomicAdd(mine + ((w[k] >> 16) & 255u), 1u);
+      atomicAdd(mine + (w[k] >> 24), 1u);
+    }
+  }
+  for (long long i = nvec * 16 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    atomicAdd(mine + data[i], 1u);
+  __syncthreads();
+  unsigned int total = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) total += h[k][threadIdx.x];
+  if (total) atomicAdd(hist + threadIdx.x, total);
+}
+
+// uint16: 65 536 bins live in global memory (L2 atomics); equal values inside a warp are merged first (__match_any_sync), so
+// the few bins a microscopy image concentrates on receive one atomic per warp and load instruction, not one per pixel.
+__device__ __forceinline__ void hist_merge_add(unsigned int* hist, unsigned int v, bool ok) {
+  const unsigned int peers = __match_any_sync(0xffffffffu, ok ? v : 0xffffffffu);
+  if (ok && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(hist + v, (unsigned int)__popc(peers));
+}
+__global__ void __launch_bounds__(256) histogram_u16_kernel(const uint16_t* __restrict__ data, long long n,
+                                                            unsigned int* __restrict__ hist) {
+  const long long nvec = (reinterpret_cast<uintptr_t>(data) & 15) ? 0 : n / 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nvec_pad = (nvec + 31) / 32 * 32;                 // whole warps take part in every __match_any_sync
+  const uint4* v4 = reinterpret_cast<const uint4*>(data);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_pad; i += stride) {
+    const bool ok = i < nvec;
+    const uint4 q = ok ? __ldg(v4 + i) : make_uint4(0, 0, 0, 0);
+    const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      hist_merge_add(hist, w[k] & 0xffffu, ok);
+      hist_merge_add(hist, w[k] >> 16, ok);
+    }
+  }
+  const long long tail0 = nvec * 8, n_tail = n - tail0, tail_pad = (n_tail + 31) / 32 * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tail_pad; i += stride) {
+    const bool ok = i < n_tail;
+    hist_merge_add(hist, ok ? (unsigned int)data[tail0 + i] : 0u, ok);
+  }
+}
+
+// dst[i] = lut[src[i]] with the table in shared memory; 16 input bytes per load (16 uint8 / 8 uint16 values), packed stores.
+template <typename T>
+__global__ void __launch_bounds__(256) lut_kernel(const T* __restrict__ src, long long n, const uint8_t* __restrict__ lut,
+                                                  int lut_size, uint8_t* __restrict__ dst) {
+  extern __shared__ uint8_t lut_s[];
+  for (int i = threadIdx.x * 4; i < lut_size; i += blockDim.x * 4)
+    *reinterpret_cast<unsigned int*>(lut_s + i) = __ldg(reinterpret_cast<const unsigned int*>(lut + i));
+  __syncthreads();
+  constexpr int PER = 16 / (int)sizeof(T);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  const long long nvec = aligned ? n / PER : 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const uint4* v4 = reinterpret_cast<const uint4*>(src);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 q = __ldg(v4 + i);
+    const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+    if (sizeof(T) == 1) {
+      unsigned int o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        o[k] = (unsigned int)lut_s[w[k] & 255u] | ((unsigned int)lut_s[(w[k] >> 8) & 255u] << 8) |
+               ((unsigned int)lut_s[(w[k] >> 16) & 255u] << 16) | ((unsigned int)lut_s[w[k] >> 24] << 24);
+      reinterpret_cast<uint4*>(dst)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      unsigned int o[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        o[k] = (unsigned int)lut_s[w[2 * k] & 0xffffu] | ((unsigned int)lut_s[w[2 * k] >> 16] << 8) |
+               ((unsigned int)lut_s[w[2 * k + 1] & 0xffffu] << 16) | ((unsigned int)lut_s[w[2 * k + 1] >> 16] << 24);
+      reinterpret_cast<uint2*>(dst)[i] = make_uint2(o[0], o[1]);
+    }
+  }
+  for (long long i = nvec * PER + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = lut_s[src[i]];
+}
+// cv2.COLOR_RGB2GRAY / COLOR_RGBA2GRAY for 8-bit images (OpenCV 4.x: 15-bit fixed point, pinned against the installed cv2 on
+// all 2^24 colours), applied AFTER an optional per-element table (the percentile normalisation that precedes it in the
+// reference's chain, cpn_inference.py:198-213): dst[p] = (9798 R + 19235 G + 3735 B + 2^14) >> 15.
+template <typename T>
+__global__ void __launch_bounds__(256) gray_kernel(const T* __restrict__ src, long long n_px, int channels,
+                                                   const uint8_t* __restrict__ lut, int lut_size, uint8_t* __restrict__ dst) {
+  extern __shared__ uint8_t lut_s[];
+  if (lut) {
+    for (int i = threadIdx.x; i < lut_size; i += blockDim.x) lut_s[i] = lut[i];
+    __syncthreads();
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_px; i += stride) {
+    const T* px = src + i * channels;
+    unsigned int r = px[0], g = px[1], b = px[2];
+    if (lut) { r = lut_s[r]; g = lut_s[g]; b = lut_s[b]; }
+    dst[i] = (uint8_t)((9798u * r + 19235u * g + 3735u * b + (1u << 14)) >> 15);
+  }
+}
+}  // namespace cpn
+
+extern "C" int cpn_histogram(const void* data, int dtype, int64_t n, uint32_t* hist, void* stream) {
+  using namespace cpn;
+  CPN_REQUIRE(data && hist && n >= 0 && (dtype == CPN_DT_U8 || dtype == CPN_DT_U16), "histogram: uint8 / uint16 data required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int bins = dtype == CPN_DT_U8 ? 256 : 65536;
+  CPN_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)bins * sizeof(uint32_t), st));
+  if (n == 0) return 0;
+  if (dtype == CPN_DT_U8) histogram_u8_kernel<<<grid_for(n, 256 * 64), 256, 0, st>>>((const uint8_t*)data, n, hist);
+  else histogram_u16_kernel<<<grid_for(n, 256 * 8), 256, 0, st>>>((const uint16_t*)data, n, hist);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cpn_apply_lut(const void* src, int dtype, int64_t n, const uint8_t* lut, uint8_t* dst, void* stream) {
+  using namespace cpn;
+  CPN_REQUIRE(src && lut && dst && n >= 0 && (dtype == CPN_DT_U8 || dtype == CPN_DT_U16), "apply_lut: uint8 / uint16 source required");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CPN_DT_U8) {
+    lut_kernel<uint8_t><<<grid_for(n, 256 * 16), 256, 256, st>>>((const uint8_t*)src, n, lut, 256, dst);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      CPN_CHECK_CUDA(cudaFuncSetAttribute(lut_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      attr = true;
+    }
+    lut_kernel<uint16_t><<<grid_for(n, 256 * 64), 256, 65536, st>>>((const uint16_t*)src, n, lut, 65536, dst);
+  }
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cpn_rgb2gray(const void* src, int dtype, int64_t n_px, int channels, const uint8_t* lut, uint8_t* dst,
+                            void* stream) {
+  using namespace cpn;
+  CPN_REQUIRE(src && dst && n_px >= 0 && (channels == 3 || channels == 4), "rgb2gray: 3 or 4 interleaved channels required");
+  CPN_REQUIRE(dtype == CPN_DT_U8 || (dtype == CPN_DT_U16 && lut), "rgb2gray: uint8 data, or uint16 data with a table to uint8");
+  if (n_px == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(n_px, 256);
+  if (dtype == CPN_DT_U8) {
+    gray_kernel<uint8_t><<<grid, 256, lut ? 256 : 0, st>>>((const uint8_t*)src, n_px, channels, lut, 256, dst);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      CPN_CHECK_CUDA(cudaFuncSetAttribute(gray_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      attr = true;
+    }
+    gray_kernel<uint16_t><<<grid_for(n_px, 256 * 8), 256, 65536, st>>>((const uint16_t*)src, n_px, channels, lut, 65536, dst);
+  }
+  CPN_CHECK_LAUNCH();
+  return 0;
+}

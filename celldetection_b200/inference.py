@@ -138,12 +138,17 @@ def _tile_bounds(mask, point_mask, point_mask_exclusive, sl):
 
 
 def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size, strides, batch_size, border_removal,
-                  rules, stitching_rule, nms_thresh, dev, timings=None):
+                  rules, stitching_rule, nms_thresh, dev, timings=None, reps=1, transforms=None):
     """One model over all tiles of ``img`` (this rank's share), border removal, exchange, stitch NMS
     (cpn_inference.py:354-411).  ``img``: ``Array[h, w, c]`` on the host (crops are staged through double-buffered pinned
     memory by a helper thread) or a uint8 / float32 CUDA tensor ``[h, w, c]`` already resident on ``dev`` (crops are device
     slices).  The per-tile border test only marks rows; compaction, the order keys and the exchange run ONCE after the
-    last batch, so the tile loop has no host synchronisation besides the model's own."""
+    last batch, so the tile loop has no host synchronisation besides the model's own.
+
+    Test-time repetitions (TileLoader, cpn_inference.py:85-91,114-118): every tile is one work item per ``rep_idx`` in
+    ``range(reps)`` (item = tile * reps + rep, dealt round-robin to the ranks); ``transforms(crop, rep_idx) -> (crop, meta)``
+    changes the INPUT crop on the host only -- the reference never maps detections back (``meta`` just travels with the batch),
+    all repetitions' detections meet in the global NMS."""
     on_device = isinstance(img, torch.Tensor)
     H, W = int(img.shape[0]), int(img.shape[1])
     slices, overlaps, (h_tiles, w_tiles) = get_tiling_slices((H, W), tuple(crop_size), tuple(strides),
@@ -160,7 +165,8 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
             if bnd is not False:
                 bounds[t] = bnd
                 todo.append(t)
-    mine = todo[rank::world]
+    items = [t * reps + r for t in todo for r in range(reps)]      # TileLoader.__getitem__: slice_idx = item // reps
+    mine = items[rank::world]
     th, tw = (slices[0][0].stop - slices[0][0].start), (slices[0][1].stop - slices[0][1].start)
     is_u8 = img.dtype in (np.uint8, torch.uint8)
     C = int(img.shape[-1])
@@ -184,8 +190,11 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
             torch.cuda.set_device(cur_dev)
             ids = mine[bi * batch_size:(bi + 1) * batch_size]
             buf = stage[slot]
-            for j, t in enumerate(ids):
-                buf[j].copy_(torch.from_numpy(np.ascontiguousarray(img[slices[t]])))
+            for j, it in enumerate(ids):
+                crop = img[slices[it // reps]]
+                if transforms is not None:
+                    crop = _checked_transform(transforms, crop, it % reps)
+                buf[j].copy_(torch.from_numpy(np.ascontiguousarray(crop)))
             with torch.cuda.stream(copy_stream):
                 d = buf[:len(ids)].to(dev, non_blocking=True)
                 ev = torch.cuda.Event()
@@ -199,7 +208,7 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
         for bi in range(nb):
             if on_device:
                 ids = mine[bi * batch_size:(bi + 1) * batch_size]
-                d = torch.stack([img[slices[t]] for t in ids], 0)
+                d = torch.stack([img[slices[it // reps]] for it in ids], 0)
             else:
                 ids, d, ev = nxt.result()
                 main.wait_event(ev)
@@ -207,13 +216,14 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
                 if bi + 1 < nb:
                     # the other staging slot was consumed two batches ago (its copy finished before the previous forward)
                     nxt = pool.submit(load, bi + 1, (bi + 1) % 2)
-            offs = torch.tensor([[slices[t][1].start, slices[t][0].start] for t in ids], dtype=torch.float32).to(
+            tiles = [it // reps for it in ids]
+            offs = torch.tensor([[slices[t][1].start, slices[t][0].start] for t in tiles], dtype=torch.float32).to(
                 dev, non_blocking=True)
             kw = dict(offsets=offs)
             if bounds:       # [B,1,th,tw] score bounds at input resolution (resized by the model, cpn.py:118-123)
                 for j, name in ((0, 'scores_upper_bound'), (1, 'scores_lower_bound')):
-                    if bounds[ids[0]][j] is not None:
-                        b_np = np.stack([bounds[t][j][..., 0] for t in ids], 0)[:, None]
+                    if bounds[tiles[0]][j] is not None:
+                        b_np = np.stack([bounds[t][j][..., 0] for t in tiles], 0)[:, None]
                         kw[name] = torch.from_numpy(np.ascontiguousarray(b_np)).to(dev)
             if is_u8:
                 flat, counts = model.forward_flat(d, L.IN_U8_NHWC, **kw)
@@ -223,7 +233,7 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
             if K == 0:
                 continue
             meta = []
-            for t in ids:
+            for t in tiles:
                 h_i, w_i = np.unravel_index(t, (h_tiles, w_tiles))
                 (_, ov_y1), (_, ov_x1) = overlaps[t]      # right/bottom overlaps (cpn_inference.py:382-385)
                 meta.append([slices[t][1].start, slices[t][0].start, th, tw, float(h_i > 0), float(w_i < w_tiles - 1),
@@ -270,6 +280,16 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
     return res
 
 
+def _checked_transform(transforms, crop, rep_idx):
+    """``transforms(crop, rep_idx) -> (crop, meta)`` (cpn_inference.py:118); the batch is one dense tensor, so the crop must
+    keep its shape and type."""
+    out, _meta = transforms(crop, rep_idx)
+    out = np.asarray(out)
+    if out.shape != crop.shape or out.dtype != crop.dtype:
+        raise ValueError(f'transforms must keep the crop shape and dtype: {crop.shape} {crop.dtype} -> {out.shape} {out.dtype}')
+    return out
+
+
 def _now(dev, timings):
     """Device-synchronised wall clock for the optional stage breakdown (no synchronisation unless timings are asked)."""
     if timings is None:
@@ -282,8 +302,9 @@ def _now(dev, timings):
 @torch.no_grad()
 def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size=(768, 768), strides=(384, 384),
                 reps=1, transforms=None, model_kwargs_list=None, batch_size=1, num_workers=0, pin_memory=False,
-                border_removal=4, min_vote=1, stitching_rule='nms', point_mask_exclusive=False, verbose=False,
-                device=None, timings=None, **kwargs):
+                border_removal=4, min_vote=1, stitching_rule='nms', gamma=1., contrast=1., brightness=0., percentile=None,
+                model_parameters=None, point_mask_exclusive=False, verbose=False, grayscale=False, device=None,
+                timings=None, **kwargs):
     """cpn_inference.py:311-429.  ``img``: uint8 or float ``Array[h, w, (c)]``; ``models``: a ``CPN`` instance or a
     list of them (an ensemble: every model is run over all tiles, the concatenated detections are filtered by
     ``filter_by_box_voting(boxes, nms_thresh, min_vote)`` when ``min_vote > 1`` and de-duplicated by one more NMS,
@@ -291,15 +312,19 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
     skipped (TileLoader, :93-111).  Returns the flat dict of concatenated tensors (contours, boxes, scores, classes,
     locations, fourier, contour_proposals[, box_uncertainties][, votes]) after border removal and global NMS --
     identical on every rank when distributed.  ``img`` may also be a ``[h, w, c]`` uint8 / float32 CUDA tensor (the slide
-    already resident in HBM).  ``timings``: optional dict that receives a device-synchronised stage breakdown (tile loop,
-    exchange, stitch) of the last model."""
+    already resident in HBM).  ``gamma`` / ``contrast`` / ``brightness`` / ``percentile`` / ``grayscale`` and 16-bit images go
+    through ``preprocess`` (:196-222) on the GPU first; ``reps`` / ``transforms``: test-time repetitions (see
+    ``_apply_single``).  ``timings``: optional dict that receives a device-synchronised stage breakdown (tile loop, exchange,
+    stitch) of the last model."""
     if not isinstance(models, (list, tuple)):
         models = [models]
     assert len(models) >= 1, 'Please specify at least one model.'
     assert min_vote >= 1, f'Min vote smaller than minimum: {min_vote}'
     assert len(models) >= min_vote, f'Min vote greater than number of models: {min_vote}'
-    if transforms is not None or reps != 1:
-        raise NotImplementedError('test-time transforms are outside the accelerated path.')
+    reps = int(reps)
+    assert reps >= 1, f'reps smaller than minimum: {reps}'
+    if transforms is not None and (mask is not None or point_mask is not None):
+        raise NotImplementedError('Use of masks and transforms not supported yet.')          # cpn_inference.py:116-117
     rules = stitching_rule.split(',')
     if any(r not in ('nms', 'ex_br') for r in rules):
         raise ValueError(f'Unknown stitching rule: {stitching_rule}')
@@ -310,24 +335,49 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
         crop_size = (crop_size,) * 2
     if not isinstance(strides, (tuple, list)):
         strides = (strides,) * 2
-    if isinstance(img, torch.Tensor) and img.is_cuda:       # slide already resident in HBM: [h, w, c] uint8 / float32
+    if model_parameters:                                     # resolve_model, cpn_inference.py:246-252
+        for model in models:
+            for k, v in _parse_model_parameters(model_parameters):
+                if not hasattr(model, k):
+                    raise ValueError(f'Could not find attribute {k} in model! Please check your configuration.')
+                setattr(model, k, v)
+    resident = isinstance(img, torch.Tensor) and img.is_cuda
+    if not isinstance(img, torch.Tensor):
+        img = np.asarray(img)
+    wide = img.dtype in (np.uint16, np.int16, torch.uint16, torch.int16) if not resident else img.dtype in (
+        torch.uint16, torch.int16)
+    if wide or percentile is not None or gamma != 1. or contrast != 1. or grayscale:
+        # the reference conditions the whole image on the CPU before tiling (:328-329); here it goes to the GPU once and
+        # continues as a device-resident uint8 slide
+        from .preprocessing import preprocess
+        if isinstance(img, np.ndarray) and img.dtype == np.uint16:
+            img = img.view(np.int16)
+        img = preprocess(img, gamma=gamma, contrast=contrast, brightness=brightness, percentile=percentile,
+                         grayscale=grayscale, device=dev)
+        resident = True
+    if resident:                                             # slide already resident in HBM: [h, w, c] uint8 / float32
         if img.dim() != 3 or img.dtype not in (torch.uint8, torch.float32) or img.device != dev:
             raise ValueError('a device-resident image must be a [h, w, c] uint8 or float32 tensor on the model device')
         if img.shape[-1] == 1:
             img = img.expand(-1, -1, 3)
+        if transforms is not None:
+            img = img.cpu().numpy()                          # transforms are host callables on numpy crops
     else:
         img = _to_rgb(np.asarray(img))
         if img.dtype.kind == 'f':
+            # NOTE: the reference percentile-normalises every non-uint8 image to uint8 (:200-202); floating-point images are
+            # taken as already scaled to [0, 1] here (the model's own input contract) -- 16-bit integer images are normalised
             img = img.astype(np.float32)
         elif img.dtype != np.uint8:
-            raise ValueError('image must be uint8 or floating point')
+            raise ValueError('image must be uint8, uint16 or floating point')
     mask = None if mask is None else np.asarray(mask)
     point_mask = None if point_mask is None else np.asarray(point_mask)
     results, nms_thresh = None, None
     for model in models:
         nms_thresh = kwargs.get('nms_thresh', model.nms_thresh)
         res = _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size, strides, batch_size,
-                            border_removal, rules, stitching_rule, nms_thresh, dev, timings=timings)
+                            border_removal, rules, stitching_rule, nms_thresh, dev, timings=timings, reps=reps,
+                            transforms=transforms)
         if results is None:
             results = res
         else:                      # keys shared by all models (an uncertainty head may be missing in some)

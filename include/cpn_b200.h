@@ -44,6 +44,7 @@ enum {
   CPN_DT_F32 = 0,
   CPN_DT_F16 = 1,
   CPN_DT_U8 = 2,
+  CPN_DT_U16 = 5,   /* raw 16-bit image data (cpn_histogram / cpn_apply_lut only) */
   CPN_DT_F16X2 = 3, /* split fp16 pair: value = hi + lo, hi = fp16(v), lo = fp16(v - hi); channel c of a view lives at
                       element c (hi) and c + lo_delta (lo) of the pixel.  Used by the 3-pass tensor-core engine
                       (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate) that reaches fp32-level accuracy. */
@@ -321,6 +322,21 @@ int cpn_contours2labels(const float* contours, int64_t n_contours, int samples, 
 size_t cpn_resolve_label_channels_workspace_bytes(int H, int W);
 int cpn_resolve_label_channels(const int32_t* labels, int H, int W, int channels, int max_iter, int32_t* flat,
                                void* workspace, int* sweeps_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* input-side preprocessing of a slide (celldetection_scripts/cpn_inference.py:196-222 `preprocess`,                 */
+/* cd.data.normalize_percentile data/misc.py:156-161)                                                               */
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* Exact histogram of n uint8 (CPN_DT_U8, 256 bins) or uint16 (CPN_DT_U16, 65536 bins) values into hist (uint32, zeroed by
+ * the call).  The host derives np.percentile's order statistics and the image mean from it. */
+int cpn_histogram(const void* data, int dtype, int64_t n, uint32_t* hist, void* stream);
+/* dst[i] = lut[src[i]] (lut: 256 or 65536 uint8 entries on the device): percentile normalisation to uint8, gamma and
+ * brightness / contrast adjustment composed into one table by the host. */
+int cpn_apply_lut(const void* src, int dtype, int64_t n, const uint8_t* lut, uint8_t* dst, void* stream);
+/* `grayscale` branch of preprocess (cpn_inference.py:203-213, third-party cv2.cvtColor COLOR_RGB2GRAY / COLOR_RGBA2GRAY, 8-bit
+ * fixed point (9798 R + 19235 G + 3735 B + 2^14) >> 15): src [n_px, channels] interleaved (channels 3 or 4; uint16 sources
+ * need `lut`), each element first mapped through `lut` when given (nullable), dst [n_px] uint8. */
+int cpn_rgb2gray(const void* src, int dtype, int64_t n_px, int channels, const uint8_t* lut, uint8_t* dst, void* stream);
 
 /* dst[i, :] = src[index[i], :] for rows of row_bytes (multiple of 4) bytes (resolve_keep_indices, cpn.py:53-60). */
 int cpn_gather_rows(const void* src, int64_t row_bytes, const int32_t* index, int64_t n_rows, void* dst, void* stream);

@@ -514,14 +514,26 @@ def filter_contours_by_stitching_rule(contours, tile_size, overlaps, rule='ex_br
     return ~((contours >= stop).any(-1).all(-1))
 
 
+def tta_example_transform(crop, rep_idx):
+    """A test-time transform in TileLoader's protocol (cpn_inference.py:118): repetition 0 sees the crop itself, repetition 1 its
+    horizontal mirror image, repetition 2 the vertical one with rotated channels (the reference never maps detections back, so
+    the mirrored detections are new ones).  Shared by oracle/make_golden.py and the tests."""
+    if rep_idx == 0:
+        return crop, None
+    out = crop[:, ::-1] if rep_idx % 2 else np.roll(crop[::-1], 1, axis=-1)
+    return np.ascontiguousarray(out), dict(rep=rep_idx)
+
+
 def apply_model(img, sd, arch, crop_size, strides, border_removal=4, batch_size=1, mask=None, point_mask=None,
-                point_mask_exclusive=False, **kw):
+                point_mask_exclusive=False, reps=1, transforms=None, **kw):
     """cpn_inference.py:311-411 for one model, ``stitching_rule='nms'``.
 
     ``img`` is uint8 or float HxWx3.  uint8 tiles become float/255 (lightning_base.py:774-780).  Per tile: model with
     ``offsets=[w0, h0]`` (and, with ``mask`` / ``point_mask``, the crop as upper / lower score bound; tiles whose crop
     is empty are skipped, TileLoader :93-111); border removal in tile-local coordinates with sides disabled at the
     image border (cpn_inference.py:370-387); then concat and one global NMS with the model's ``nms_thresh`` (:405-408).
+    ``reps`` / ``transforms``: every tile is inferred ``reps`` times, ``transforms(crop, rep_idx)`` changing the input crop only
+    (TileLoader :85-91,114-118; the meta it returns is never used to map detections back).
     """
     img = np.asarray(img)
     H, W = img.shape[:2]
@@ -545,18 +557,22 @@ def apply_model(img, sd, arch, crop_size, strides, border_removal=4, batch_size=
             bkw['scores_lower_bound'] = torch.as_tensor(np.clip(pc, 0., 1.).astype('float32'))[None, None]
             if point_mask_exclusive:
                 bkw['scores_upper_bound'] = bkw['scores_lower_bound']
-        crop_img = img[sl_h, sl_w]
-        x = torch.as_tensor(np.ascontiguousarray(crop_img)).permute(2, 0, 1)[None]
-        x = x.float() / 255 if crop_img.dtype == np.uint8 else x.float()
-        off = torch.as_tensor([[sl_w.start, sl_h.start]], dtype=torch.float)
-        out = cpn_forward(x, sd, arch, offsets=off, **bkw, **kw)
-        con = out['contours'][0]
-        keep = remove_border_contours(con, crop_img.shape[:2], border_removal, top=gy > 0, right=gx < grid[1] - 1,
-                                      bottom=gy < grid[0] - 1, left=gx > 0, offsets=-off[0])
-        for k, v in out.items():
-            if v is None:
-                continue
-            acc.setdefault(k, []).append(v[0][keep])
+        for rep_idx in range(reps):
+            crop_img = img[sl_h, sl_w]
+            if transforms is not None:
+                assert mask is None and point_mask is None       # cpn_inference.py:116-117
+                crop_img, _ = transforms(crop_img, rep_idx)
+            x = torch.as_tensor(np.ascontiguousarray(crop_img)).permute(2, 0, 1)[None]
+            x = x.float() / 255 if crop_img.dtype == np.uint8 else x.float()
+            off = torch.as_tensor([[sl_w.start, sl_h.start]], dtype=torch.float)
+            out = cpn_forward(x, sd, arch, offsets=off, **bkw, **kw)
+            con = out['contours'][0]
+            keep = remove_border_contours(con, crop_img.shape[:2], border_removal, top=gy > 0, right=gx < grid[1] - 1,
+                                          bottom=gy < grid[0] - 1, left=gx > 0, offsets=-off[0])
+            for k, v in out.items():
+                if v is None:
+                    continue
+                acc.setdefault(k, []).append(v[0][keep])
     res = OrderedDict((k, torch.cat(v, 0)) for k, v in acc.items())
     keep = torch.as_tensor(nms(res['boxes'].numpy(), res['scores'].numpy(), nms_thresh))
     return OrderedDict((k, v[keep]) for k, v in res.items())

@@ -269,8 +269,17 @@ def mint_apply_model(cd):
         arrays['calib/' + k] = to_np(sd[k])
     for k in ('contours', 'boxes', 'scores', 'classes', 'locations', 'fourier', 'contour_proposals'):
         arrays['out/' + k] = to_np(res[k])
+    # test-time repetitions: every tile 3x, repetition r through a host transform of the crop (TileLoader :85-91,114-118)
+    res_t = cs.apply_model(img, [lit], ref_shim.FakeTrainer(), crop_size=(64, 64), strides=(48, 48), reps=3,
+                           transforms=orc.tta_example_transform, model_kwargs_list=[{}], batch_size=2, verbose=False)
+    o_t = orc.apply_model(img, sd, 'CpnU22', 64, 48, border_removal=4, reps=3, transforms=orc.tta_example_transform)
+    assert len(o_t['scores']) == len(res_t['scores']) != len(res['scores']), (len(o_t['scores']), len(res_t['scores']))
+    for k in ('contours', 'boxes', 'scores', 'locations'):
+        check_close(f'apply_model/tta/{k}', to_np(o_t[k]), to_np(res_t[k]), 1e-5)
+    for k in ('contours', 'boxes', 'scores', 'classes', 'locations', 'fourier', 'contour_proposals'):
+        arrays['tta/' + k] = to_np(res_t[k])
     np.savez_compressed(os.path.join(GOLDEN, 'apply_model_cpnu22.npz'), **arrays)
-    print(f'apply_model: {len(res["scores"])} stitched detections')
+    print(f'apply_model: {len(res["scores"])} stitched detections, {len(res_t["scores"])} with 3 repetitions')
 
 
 def mint_apply_ensemble(cd):
@@ -385,6 +394,39 @@ def mint_contours2labels(cd):
     np.savez_compressed(os.path.join(GOLDEN, 'contours2labels.npz'), **arrays)
 
 
+def mint_preprocess(cd):
+    """Slide preprocessing (cpn_inference.py:196-222): the reference's own ``cd.data.normalize_percentile`` (float result:
+    its uint8 conversion is skimage's, absent here) pins the oracle's percentile / clip / scale step; the oracle's full
+    chain (uint8 conversion, gamma, contrast restated from the third-party sources) is stored for the GPU test."""
+    import preprocess_oracle as po
+    rng = np.random.RandomState(3)
+    arrays = {}
+    img16 = rng.gamma(2.0, 900, size=(157, 211)).clip(0, 65535).astype(np.uint16)
+    img8 = rng.gamma(2.0, 30, size=(96, 130, 3)).clip(0, 255).astype(np.uint8)
+    for name, img in (('u16', img16), ('u8', img8)):
+        arrays[f'{name}/img'] = img
+        for j, pct in enumerate((99.9, 98.0, (0.5, 99.0))):
+            ref = cd.data.normalize_percentile(img, pct, to_uint8=False)
+            got = po.normalize_percentile(img, pct, to_uint8=False)
+            assert np.array_equal(np.asarray(ref), got), (name, pct)
+            arrays[f'{name}/pct{j}'] = np.asarray(pct, dtype=np.float64).reshape(-1)
+            arrays[f'{name}/norm{j}'] = po.normalize_percentile(img, pct)
+        chains = ((0.8, 1., 0., None, 0), (1., 1.3, 0.1, 99.5, 0), (1.4, 0.7, -0.05, None, 0), (1., 1., 0., None, 1),
+                  (0.9, 1.2, 0.05, 99., 1))
+        for j, (gamma, con, bri, pct, gray) in enumerate(chains):
+            arrays[f'{name}/chain{j}/params'] = np.array([gamma, con, bri, -1. if pct is None else pct, gray])
+            arrays[f'{name}/chain{j}/out'] = po.preprocess(img, gamma, con, bri, pct, grayscale=bool(gray))
+    rgba = rng.randint(0, 256, size=(64, 80, 4)).astype(np.uint8)
+    import cv2
+    assert np.array_equal(po.rgb2gray(rgba), cv2.cvtColor(rgba, cv2.COLOR_RGBA2GRAY))
+    assert np.array_equal(po.rgb2gray(img8), cv2.cvtColor(img8, cv2.COLOR_RGB2GRAY))
+    arrays['rgba/img'] = rgba
+    arrays['rgba/chain0/params'] = np.array([1.2, 1., 0., -1., 1])
+    arrays['rgba/chain0/out'] = po.preprocess(rgba, 1.2, 1., 0., None, grayscale=True)
+    np.savez_compressed(os.path.join(GOLDEN, 'preprocess.npz'), **arrays)
+    print('preprocess: ok', sorted(arrays)[:4], '...')
+
+
 def mint_keys(cd):
     """state_dict key -> shape of the three reference models (drop-in contract)."""
     out = {}
@@ -418,7 +460,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     cd = ref_shim.import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    which = sys.argv[1:] or ['keys', 'f2c', 'tiling', 'models', 'variants', 'apply', 'ensemble', 'labels']
+    which = sys.argv[1:] or ['keys', 'f2c', 'tiling', 'models', 'variants', 'apply', 'ensemble', 'labels', 'preprocess']
     if 'keys' in which:
         mint_keys(cd)
     if 'f2c' in which:
@@ -437,6 +479,8 @@ def main():
         mint_apply_ensemble(cd)
     if 'labels' in which:
         mint_contours2labels(cd)
+    if 'preprocess' in which:
+        mint_preprocess(cd)
 
 
 if __name__ == '__main__':

@@ -174,6 +174,53 @@ def test_apply_model_matches_reference_golden():
     assert np.array_equal(rr[0]['flat_labels'].cpu().numpy(), c2l.resolve_label_channels(want))
 
 
+def test_apply_model_test_time_repetitions_match_reference_golden():
+    """reps / transforms (cpn_inference.py:85-91,114-118): every tile three times, repetitions 1 and 2 through a host
+    transform; host image and device-resident slide; reps without transforms must equal the plain result."""
+    z = load_npz('apply_model_cpnu22')
+    seed, crop, stride, border = [int(v) for v in z['meta']]
+    m = cd.models.CpnU22(3, precision='fp32')
+    m.load_state_dict(fixture_state_dict(z, 'CpnU22', seed))
+    m = m.cuda()
+    for img, bs in ((z['img'], 4), (torch.from_numpy(z['img']).cuda(), 3)):
+        res = cd.apply_model(img, [m], crop_size=crop, strides=stride, border_removal=border, batch_size=bs, reps=3,
+                             transforms=orc.tta_example_transform)
+        assert len(res['scores']) == len(z['tta/scores']) > len(z['out/scores'])
+        pairs = match_by_box(res['boxes'].cpu().numpy(), z['tta/boxes'])
+        assert len(pairs) == len(z['tta/scores'])
+        for a, b in pairs:
+            assert np.abs(res['contours'][a].cpu().numpy() - z['tta/contours'][b]).max() < 0.5
+    plain = cd.apply_model(z['img'], [m], crop_size=crop, strides=stride, border_removal=border, batch_size=2)
+    twice = cd.apply_model(z['img'], [m], crop_size=crop, strides=stride, border_removal=border, batch_size=2, reps=2)
+    for k in plain:        # identical repetitions are exact duplicates: the global NMS keeps the first of each
+        assert torch.equal(plain[k], twice[k]), k
+    with pytest.raises(NotImplementedError):
+        cd.apply_model(z['img'], [m], crop_size=crop, strides=stride, transforms=orc.tta_example_transform,
+                       mask=np.ones(z['img'].shape[:2], bool))
+
+
+def test_apply_model_preprocesses_like_the_reference_chain():
+    """gamma / contrast / percentile / 16-bit input (cpn_inference.py:328-329): apply_model on the raw image with the options
+    == apply_model on the oracle-preprocessed uint8 image."""
+    import preprocess_oracle as po
+    z = load_npz('apply_model_cpnu22')
+    seed, crop, stride, border = [int(v) for v in z['meta']]
+    m = cd.models.CpnU22(3, precision='fp32')
+    m.load_state_dict(fixture_state_dict(z, 'CpnU22', seed))
+    m = m.cuda()
+    img16 = (z['img'].astype(np.uint16) * 97 + 11)
+    total = 0
+    for img, kw in ((z['img'], dict(gamma=0.8, contrast=1.2, brightness=0.05)), (z['img'], dict(percentile=99.)),
+                    (img16, dict()), (img16, dict(percentile=[0.5, 99.5], gamma=1.1)), (z['img'], dict(grayscale=True))):
+        want = cd.apply_model(po.preprocess(img, **kw), [m], crop_size=crop, strides=stride, border_removal=border,
+                              batch_size=4)
+        got = cd.apply_model(img, [m], crop_size=crop, strides=stride, border_removal=border, batch_size=4, **kw)
+        total += len(want['scores'])
+        for k in want:
+            assert torch.equal(want[k], got[k]), (kw, k)
+    assert total > 0
+
+
 def test_full_size_c3_properties():
     """BASELINE config C3 (CpnResNeXt101UNet, 3x512x512 tiles): size-independent properties at full tile size --
     batch invariance (tile i of a batch == the same tile alone, bit for bit) and fp16-vs-fp32 engine agreement."""

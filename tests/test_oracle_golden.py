@@ -115,6 +115,19 @@ def test_oracle_apply_model_golden():
         assert rel_err(res[k].numpy(), z['out/' + k]) < 1e-5, k
 
 
+def test_oracle_apply_model_test_time_repetitions_golden():
+    """reps=3 + a host transform of the crop (TileLoader, cpn_inference.py:85-91,114-118), minted by the reference."""
+    z = load_npz('apply_model_cpnu22')
+    seed, crop, stride, border = [int(v) for v in z['meta']]
+    sd = fixture_state_dict(z, 'CpnU22', seed)
+    torch.set_num_threads(8)
+    res = orc.apply_model(z['img'], sd, 'CpnU22', crop, stride, border_removal=border, reps=3,
+                          transforms=orc.tta_example_transform)
+    assert len(res['scores']) == len(z['tta/scores']) > len(z['out/scores'])
+    for k in ('contours', 'boxes', 'scores', 'locations', 'fourier', 'contour_proposals'):
+        assert rel_err(res[k].numpy(), z['tta/' + k]) < 1e-5, k
+
+
 def test_oracle_nms_matches_torchvision():
     """The NMS restatement against the third-party op the reference calls (torchvision)."""
     import torchvision  # noqa: F401
