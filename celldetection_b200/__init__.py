@@ -8,7 +8,7 @@ from . import _lib
 from . import ops
 from . import models
 from . import data
-from .utils import load_model, fetch_model, save_fetchable_model, synth_state_dict, calibrate_heads_
+from .utils import load_model, fetch_model, save_fetchable_model, synth_state_dict, calibrate_heads_, to_h5, from_h5
 from .inference import get_tiling_slices, apply_model, cpn_inference
 from .preprocessing import preprocess
 

@@ -375,3 +375,80 @@ extern "C" int cpn_resolve_label_channels(const int32_t* labels, int H, int W, i
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LABEL PROPERTIES: the region statistics behind cd.data.labels2property_table (data/misc.py:320-345 -> third-party
+// skimage.measure.regionprops_table), as used for the csv output of cpn_inference.py:824-837.  One pass over the label
+// image (integer work, HBM-bound): per (channel, label) the pixel count, the bounding box and the coordinate sums, from
+// which the host derives area, bbox, centroid, area_bbox, extent and equivalent_diameter_area exactly (integer sums,
+// one float64 division).  Lanes that hold the same (channel, label) are merged with __match_any_sync and the hardware
+// warp reductions before they reach memory: a run of equal labels along a row costs one set of atomics per warp.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace cpn {
+__global__ void __launch_bounds__(256) label_props_kernel(const int32_t* __restrict__ labels, long long n_px, int W, int C,
+                                                          int max_label, uint32_t* __restrict__ area,
+                                                          int32_t* __restrict__ bbox,            // [.., 4] min_r, min_c, max_r, max_c
+                                                          unsigned long long* __restrict__ sums,  // [.., 2] sum_r, sum_c
+                                                          int32_t* __restrict__ flags) {
+  const long long n = n_px * C;
+  const long long n_pad = (n + 31) / 32 * 32;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const unsigned lane = threadIdx.x & 31;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+    int lab = 0;
+    if (i < n) lab = __ldg(labels + i);
+    if (lab > max_label) { atomicOr(flags, 1); lab = 0; }
+    if (!__any_sync(0xffffffffu, lab > 0)) continue;          // background (most of a label image) costs one load
+    const long long px = i / C;
+    const int ch = (int)(i - px * C);
+    const unsigned r = (unsigned)(px / W), c = (unsigned)(px - (long long)r * W);
+    const unsigned key = lab > 0 ? (unsigned)ch * (unsigned)(max_label + 1) + (unsigned)lab : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (lab > 0) {
+      const unsigned cnt = __popc(peers);
+      const unsigned sr = __reduce_add_sync(peers, r), sc = __reduce_add_sync(peers, c);
+      const unsigned r0 = __reduce_min_sync(peers, r), r1 = __reduce_max_sync(peers, r);
+      const unsigned c0 = __reduce_min_sync(peers, c), c1 = __reduce_max_sync(peers, c);
+      if ((unsigned)(__ffs(peers) - 1) == lane) {
+        atomicAdd(area + key, cnt);
+        atomicAdd(sums + 2ull * key, (unsigned long long)sr);
+        atomicAdd(sums + 2ull * key + 1, (unsigned long long)sc);
+        atomicMin(bbox + 4ull * key, (int)r0);
+        atomicMin(bbox + 4ull * key + 1, (int)c0);
+        atomicMax(bbox + 4ull * key + 2, (int)r1 + 1);
+        atomicMax(bbox + 4ull * key + 3, (int)c1 + 1);
+      }
+    }
+  }
+}
+
+__global__ void label_props_init_kernel(long long n, uint32_t* area, int32_t* bbox, unsigned long long* sums, int32_t* flags) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i == 0) flags[0] = 0;
+  if (i >= n) return;
+  area[i] = 0;
+  sums[2 * i] = 0; sums[2 * i + 1] = 0;
+  bbox[4 * i] = 0x7fffffff; bbox[4 * i + 1] = 0x7fffffff; bbox[4 * i + 2] = 0; bbox[4 * i + 3] = 0;
+}
+}  // namespace cpn
+
+extern "C" int cpn_label_props(const int32_t* labels, int H, int W, int channels, int max_label, uint32_t* area,
+                               int32_t* bbox, uint64_t* sums, int32_t* flags, void* stream) {
+  using namespace cpn;
+  CPN_REQUIRE(labels && area && bbox && sums && flags, "label_props: null pointer");
+  CPN_REQUIRE(H >= 0 && W >= 0 && channels >= 1 && max_label >= 0, "label_props: bad shape");
+  CPN_REQUIRE((long long)channels * ((long long)max_label + 1) < (1ll << 31), "label_props: channels * (max_label + 1) too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long slots = (long long)channels * ((long long)max_label + 1);
+  label_props_init_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(slots, area, bbox, (unsigned long long*)sums, flags);
+  CPN_CHECK_LAUNCH();
+  const long long n_px = (long long)H * W;
+  if (n_px == 0) return 0;
+  long long blocks = (n_px * channels + 256 * 8 - 1) / (256 * 8);
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  label_props_kernel<<<(unsigned)blocks, 256, 0, st>>>(labels, n_px, W, channels, max_label, area, bbox,
+                                                       (unsigned long long*)sums, flags);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}

@@ -8,7 +8,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ['contours2labels', 'resolve_label_channels']
+__all__ = ['contours2labels', 'resolve_label_channels', 'labels2property_table']
 
 _channel_hint = {}   # (H, W) -> channels that sufficed in the previous contours2labels call
 
@@ -98,3 +98,9 @@ def resolve_label_channels(labels, method='dilation', max_iter=999, kernel=(3, 3
     L.check(lib.cpn_resolve_label_channels(L.ptr(lab), H, W, C, int(max_iter), L.ptr(flat), L.ptr(ws), None,
                                            L.stream_ptr()), 'resolve_label_channels')
     return flat.cpu().numpy().astype(dtype) if as_numpy else flat
+
+
+def labels2property_table(labels, *properties, **kwargs):
+    """Labels to property table (data/misc.py:320-345); see ``utils.outputs.labels2property_table``."""
+    from .utils.outputs import labels2property_table as impl
+    return impl(labels, *properties, **kwargs)

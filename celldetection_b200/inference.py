@@ -12,6 +12,7 @@ same global NMS, so every rank returns the identical, complete result (the refer
 sequential send/recv).  No Lightning, no DataLoader workers: crops are staged through pinned host memory and copied
 asynchronously while the previous batch computes.
 """
+import os
 from collections import OrderedDict
 from itertools import product
 from typing import Sequence, Union
@@ -415,18 +416,43 @@ def _parse_model_parameters(model_parameters):
     return out
 
 
+def _load_image_file(path, dataset='image'):
+    """File inputs (cpn_inference.py:689-716): ``.h5`` / ``.hdf5`` -> the named dataset, anything else through OpenCV (the
+    reference's imageio / pytiff readers are third-party packages outside this image), channels as RGB."""
+    ext = os.path.splitext(path)[1].lower()
+    if ext in ('.h5', '.hdf5'):
+        from .utils.outputs import from_h5
+        return from_h5(path, dataset)
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise FileNotFoundError(f'could not read image {path}')
+    if img.ndim == 3:
+        img = img[..., [2, 1, 0] + ([3] if img.shape[-1] == 4 else [])]
+    return np.ascontiguousarray(img)
+
+
 def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, border_removal=4, stitching_rule='nms',
                   batch_size=1, devices='auto', precision=None, return_results=True, model_parameters=None,
-                  labels=False, flat_labels=False, verbose=False, **kwargs):
-    """Programmatic entry point in the spirit of cpn_inference.py:432-869: run tiled inference for each input image
-    (numpy arrays; file I/O and h5/tif export are outside the hot path).  ``models``: CPN instance(s) or a
-    filename loadable by ``load_model``; ``masks`` / ``point_masks`` / ``min_vote`` etc. are forwarded to
-    ``apply_model``.  ``labels`` / ``flat_labels`` add the rasterised label image (``[h, w, c]``, contours2labels) and
-    its channel-free form (``[h, w]``, resolve_label_channels) to each result, like cpn_inference.py:805-818.
+                  labels=False, flat_labels=False, properties=None, spacing=1., separator='-', overlay=False,
+                  inputs_dataset='image', skip_existing=False, verbose=False, **kwargs):
+    """Entry point in the spirit of cpn_inference.py:432-869: run tiled inference for each input (numpy arrays or image /
+    hdf5 file names).  ``models``: CPN instance(s) or a filename loadable by ``load_model``; ``masks`` / ``point_masks`` /
+    ``min_vote`` / ``gamma`` / ``percentile`` / ``reps`` ... are forwarded to ``apply_model``.  ``labels`` / ``flat_labels`` add
+    the rasterised label image (``[h, w, c]``, contours2labels) and its channel-free form (``[h, w]``,
+    resolve_label_channels) to each result (:805-818).  With ``outputs`` (a directory) every input's results are written like
+    the reference's (:797-851): ``<name>.h5`` with all result tensors (+ the call's arguments as json attribute of
+    ``contours``), ``<name>[_flat].csv`` region-property tables when ``properties`` are given, ``<name>_overlay.tif`` with
+    ``overlay=True``; ``<name>`` is ``ndarray_<index>`` for array inputs.  In a distributed run rank 0 writes.
     Returns ``{index: result dict}``."""
     from .utils import load_model
     if not isinstance(inputs, (list, tuple)):
         inputs = [inputs]
+    args = dict(tile_size=tile_size, stride=stride, border_removal=border_removal, stitching_rule=stitching_rule,
+                batch_size=batch_size, precision=precision, model_parameters=model_parameters, labels=labels,
+                flat_labels=flat_labels, properties=properties, spacing=spacing, separator=separator, overlay=overlay,
+                models=models if isinstance(models, str) else None,
+                **{k: v for k, v in kwargs.items() if isinstance(v, (int, float, str, bool, type(None), list, tuple))})
     if isinstance(models, str):
         models = load_model(models)
     models = list(models) if isinstance(models, (list, tuple)) else [models]
@@ -449,16 +475,29 @@ def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, bord
                     raise AttributeError(f'model has no parameter {k!r}')
                 setattr(model, k, v)
     results = OrderedDict()
+    if outputs is not None:
+        os.makedirs(outputs, exist_ok=True)
+    _, rank, _ = _dist()
     for i, img in enumerate(inputs):
         if isinstance(img, str):
-            raise NotImplementedError('file inputs need image I/O, which is outside the accelerated path')
+            dst = os.path.join(outputs, os.path.splitext(os.path.basename(img))[0] + '{ext}') if outputs is not None else None
+            if skip_existing and dst is not None and os.path.isfile(dst.format(ext='.h5')):
+                continue
+            img = _load_image_file(img, inputs_dataset)
+        else:
+            dst = os.path.join(outputs, f'ndarray_{i}' + '{ext}') if outputs is not None else None
         results[i] = y = apply_model(img, models, crop_size=tile_size, strides=stride, border_removal=border_removal,
                                      stitching_rule=stitching_rule, batch_size=batch_size, verbose=verbose, **kwargs)
+        shape = tuple(img.shape[:2])
         if labels or flat_labels:                  # cpn_inference.py:805-818
             from .data import contours2labels, resolve_label_channels
-            lab = contours2labels(y['contours'], np.asarray(img).shape[:2])
+            lab = contours2labels(y['contours'], shape)
             if labels:
                 y['labels'] = lab
             if flat_labels:
                 y['flat_labels'] = resolve_label_channels(lab)
+        if dst is not None and rank == 0:          # "(is_dist and rank == 0) or not is_dist", :801
+            from .utils.outputs import write_outputs
+            write_outputs(dst, y, shape, args=args, labels=labels, flat_labels=flat_labels, properties=properties,
+                          spacing=spacing, separator=separator, overlay=overlay)
     return results if return_results else None

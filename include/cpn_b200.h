@@ -323,6 +323,14 @@ size_t cpn_resolve_label_channels_workspace_bytes(int H, int W);
 int cpn_resolve_label_channels(const int32_t* labels, int H, int W, int channels, int max_iter, int32_t* flat,
                                void* workspace, int* sweeps_host, void* stream);
 
+/* Region statistics of a label image for the csv output (cd.data.labels2property_table, data/misc.py:320-345 -> third-party
+ * skimage.measure.regionprops_table; cpn_inference.py:824-837).  labels [H, W, channels] int32 (<= 0 = background; values >
+ * max_label set bit 0 of flags[0] and are ignored).  Slot = channel * (max_label + 1) + label: area[slot] pixel count,
+ * bbox[slot] = (min_row, min_col, max_row + 1, max_col + 1), sums[slot] = (sum of rows, sum of columns).  All outputs are
+ * initialised by the call. */
+int cpn_label_props(const int32_t* labels, int H, int W, int channels, int max_label, uint32_t* area, int32_t* bbox,
+                    uint64_t* sums, int32_t* flags, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* input-side preprocessing of a slide (celldetection_scripts/cpn_inference.py:196-222 `preprocess`,                 */
 /* cd.data.normalize_percentile data/misc.py:156-161)                                                               */
