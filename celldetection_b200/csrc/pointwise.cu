@@ -907,32 +907,61 @@ __global__ void __launch_bounds__(256) histogram_u8_kernel(const uint8_t* __rest
   if (total) atomicAdd(hist + threadIdx.x, total);
 }
 
-// uint16: 65 536 bins live in global memory (L2 atomics); equal values inside a warp are merged first (__match_any_sync), so
-// the few bins a microscopy image concentrates on receive one atomic per warp and load instruction, not one per pixel.
-__device__ __forceinline__ void hist_merge_add(unsigned int* hist, unsigned int v, bool ok) {
-  const unsigned int peers = __match_any_sync(0xffffffffu, ok ? v : 0xffffffffu);
-  if (ok && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(hist + v, (unsigned int)__popc(peers));
-}
-__global__ void __launch_bounds__(256) histogram_u16_kernel(const uint16_t* __restrict__ data, long long n,
-                                                            unsigned int* __restrict__ hist) {
-  const long long nvec = (reinterpret_cast<uintptr_t>(data) & 15) ? 0 : n / 8;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long nvec_pad = (nvec + 31) / 32 * 32;                 // whole warps take part in every __match_any_sync
+// uint16: the block counts into 65 536 PACKED 16-bit counters in shared memory (128 KB, two bins per word) and flushes them to
+// the global histogram after every round of at most 57 344 values, so no packed counter can overflow; the flush touches
+// global memory only for the bins the round actually hit (a microscopy image concentrates on a few hundred).
+constexpr int H16_THREADS = 1024;
+constexpr int H16_ROUND_VECS = 7;          // 7 x 1024 threads x 8 values = 57 344 <= 65 535
+__global__ void __launch_bounds__(H16_THREADS, 1) histogram_u16_kernel(const uint16_t* __restrict__ data, long long n,
+                                                                      unsigned int* __restrict__ hist) {
+  extern __shared__ unsigned int cnt[];    // [32768]: bin v -> half (v & 1) of word v >> 1
+  for (int i = threadIdx.x; i < 32768; i += H16_THREADS) cnt[i] = 0;
+  __syncthreads();
+  const bool aligned = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
+  const long long nvec = aligned ? n / 8 : 0;
   const uint4* v4 = reinterpret_cast<const uint4*>(data);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_pad; i += stride) {
-    const bool ok = i < nvec;
-    const uint4 q = ok ? __ldg(v4 + i) : make_uint4(0, 0, 0, 0);
-    const unsigned int w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      hist_merge_add(hist, w[k] & 0xffffu, ok);
-      hist_merge_add(hist, w[k] >> 16, ok);
+  const long long per_round = (long long)H16_ROUND_VECS * H16_THREADS;               // vectors per block and round
+  const long long rounds = (nvec + per_round - 1) / per_round;
+  auto flush = [&]() {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32768; i += H16_THREADS) {
+      const unsigned int w = cnt[i];
+      if (w) {
+        if (w & 0xffffu) atomicAdd(hist + 2 * i, w & 0xffffu);
+        if (w >> 16) atomicAdd(hist + 2 * i + 1, w >> 16);
+        cnt[i] = 0;
+      }
     }
+    __syncthreads();
+  };
+  for (long long r = blockIdx.x; r < rounds; r += gridDim.x) {
+    const long long base = r * per_round;
+#pragma unroll
+    for (int k = 0; k < H16_ROUND_VECS; ++k) {
+      const long long i = base + (long long)k * H16_THREADS + threadIdx.x;
+      if (i < nvec) {
+        const uint4 q = __ldg(v4 + i);
+        const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned int lo = w[j] & 0xffffu, hi = w[j] >> 16;
+          atomicAdd(cnt + (lo >> 1), 1u << ((lo & 1) * 16));
+          atomicAdd(cnt + (hi >> 1), 1u << ((hi & 1) * 16));
+        }
+      }
+    }
+    flush();
   }
-  const long long tail0 = nvec * 8, n_tail = n - tail0, tail_pad = (n_tail + 31) / 32 * 32;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tail_pad; i += stride) {
-    const bool ok = i < n_tail;
-    hist_merge_add(hist, ok ? (unsigned int)data[tail0 + i] : 0u, ok);
+  // scalar tail (and unaligned inputs): rounds of 57 344 values, one value per thread and step
+  const long long tail0 = nvec * 8, n_tail = n - tail0, tail_round = per_round * 8;
+  const long long tail_rounds = (n_tail + tail_round - 1) / tail_round;
+  for (long long r = blockIdx.x; r < tail_rounds; r += gridDim.x) {
+    const long long lo_i = tail0 + r * tail_round, hi_i = lo_i + tail_round < n ? lo_i + tail_round : n;
+    for (long long i = lo_i + threadIdx.x; i < hi_i; i += H16_THREADS) {
+      const unsigned int v = data[i];
+      atomicAdd(cnt + (v >> 1), 1u << ((v & 1) * 16));
+    }
+    flush();
   }
 }
 
@@ -978,36 +1007,72 @@ __global__ void __launch_bounds__(256) gray_kernel(const T* __restrict__ src, lo
                                                    const uint8_t* __restrict__ lut, int lut_size, uint8_t* __restrict__ dst) {
   extern __shared__ uint8_t lut_s[];
   if (lut) {
-    for (int i = threadIdx.x; i < lut_size; i += blockDim.x) lut_s[i] = lut[i];
+    for (int i = threadIdx.x * 4; i < lut_size; i += blockDim.x * 4)
+      *reinterpret_cast<unsigned int*>(lut_s + i) = __ldg(reinterpret_cast<const unsigned int*>(lut + i));
     __syncthreads();
   }
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_px; i += stride) {
-    const T* px = src + i * channels;
-    unsigned int r = px[0], g = px[1], b = px[2];
+  auto mix = [&](unsigned int r, unsigned int g, unsigned int b) -> unsigned int {
     if (lut) { r = lut_s[r]; g = lut_s[g]; b = lut_s[b]; }
-    dst[i] = (uint8_t)((9798u * r + 19235u * g + 3735u * b + (1u << 14)) >> 15);
+    return (9798u * r + 19235u * g + 3735u * b + (1u << 14)) >> 15;
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long done = 0;
+  if (sizeof(T) == 1 && (reinterpret_cast<uintptr_t>(src) & (channels == 4 ? 15 : 3)) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+    // four pixels per thread: 3 (RGB) or 4 (RGBA) aligned 32-bit loads, one 32-bit store
+    const long long quads = n_px / 4;
+    const unsigned int* w32 = reinterpret_cast<const unsigned int*>(src);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads; q += stride) {
+      unsigned int o;
+      if (channels == 3) {
+        const unsigned int a = __ldg(w32 + 3 * q), b = __ldg(w32 + 3 * q + 1), c = __ldg(w32 + 3 * q + 2);
+        o = mix(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u) | (mix(a >> 24, b & 255u, (b >> 8) & 255u) << 8) |
+            (mix((b >> 16) & 255u, b >> 24, c & 255u) << 16) | (mix((c >> 8) & 255u, (c >> 16) & 255u, c >> 24) << 24);
+      } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + q);
+        const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+        o = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o |= mix(w[k] & 255u, (w[k] >> 8) & 255u, (w[k] >> 16) & 255u) << (8 * k);
+      }
+      reinterpret_cast<unsigned int*>(dst)[q] = o;
+    }
+    done = quads * 4;
+  }
+  for (long long i = done + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_px; i += stride) {
+    const T* px = src + i * channels;
+    dst[i] = (uint8_t)mix(px[0], px[1], px[2]);
   }
 }
 }  // namespace cpn
 
 extern "C" int cpn_histogram(const void* data, int dtype, int64_t n, uint32_t* hist, void* stream) {
   using namespace cpn;
-  CPN_REQUIRE(data && hist && n >= 0 && (dtype == CPN_DT_U8 || dtype == CPN_DT_U16), "histogram: uint8 / uint16 data required");
+  CPN_REQUIRE(hist && (data || n == 0) && n >= 0 && (dtype == CPN_DT_U8 || dtype == CPN_DT_U16), "histogram: uint8 / uint16 data required");
   cudaStream_t st = (cudaStream_t)stream;
   const int bins = dtype == CPN_DT_U8 ? 256 : 65536;
   CPN_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)bins * sizeof(uint32_t), st));
   if (n == 0) return 0;
   if (dtype == CPN_DT_U8) histogram_u8_kernel<<<grid_for(n, 256 * 64), 256, 0, st>>>((const uint8_t*)data, n, hist);
-  else histogram_u16_kernel<<<grid_for(n, 256 * 8), 256, 0, st>>>((const uint16_t*)data, n, hist);
+  else {
+    static bool attr = false;
+    if (!attr) {
+      CPN_CHECK_CUDA(cudaFuncSetAttribute(histogram_u16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+      attr = true;
+    }
+    long long blocks = (n + 57343) / 57344;
+    if (blocks > sm_count()) blocks = sm_count();
+    histogram_u16_kernel<<<(unsigned)blocks, H16_THREADS, 131072, st>>>((const uint16_t*)data, n, hist);
+  }
   CPN_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int cpn_apply_lut(const void* src, int dtype, int64_t n, const uint8_t* lut, uint8_t* dst, void* stream) {
   using namespace cpn;
-  CPN_REQUIRE(src && lut && dst && n >= 0 && (dtype == CPN_DT_U8 || dtype == CPN_DT_U16), "apply_lut: uint8 / uint16 source required");
+  CPN_REQUIRE(n >= 0 && (dtype == CPN_DT_U8 || dtype == CPN_DT_U16), "apply_lut: uint8 / uint16 source required");
   if (n == 0) return 0;
+  CPN_REQUIRE(src && lut && dst, "apply_lut: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == CPN_DT_U8) {
     lut_kernel<uint8_t><<<grid_for(n, 256 * 16), 256, 256, st>>>((const uint8_t*)src, n, lut, 256, dst);
@@ -1026,7 +1091,7 @@ extern "C" int cpn_apply_lut(const void* src, int dtype, int64_t n, const uint8_
 extern "C" int cpn_rgb2gray(const void* src, int dtype, int64_t n_px, int channels, const uint8_t* lut, uint8_t* dst,
                             void* stream) {
   using namespace cpn;
-  CPN_REQUIRE(src && dst && n_px >= 0 && (channels == 3 || channels == 4), "rgb2gray: 3 or 4 interleaved channels required");
+  CPN_REQUIRE((n_px == 0 || (src && dst)) && n_px >= 0 && (channels == 3 || channels == 4), "rgb2gray: 3 or 4 interleaved channels required");
   CPN_REQUIRE(dtype == CPN_DT_U8 || (dtype == CPN_DT_U16 && lut), "rgb2gray: uint8 data, or uint16 data with a table to uint8");
   if (n_px == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;

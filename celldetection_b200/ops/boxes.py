@@ -19,7 +19,8 @@ def box_votes(boxes: Tensor, thresh: float) -> Tensor:
     votes = torch.empty((K,), dtype=torch.float32, device=boxes.device)
     if K:
         ws = torch.empty((int(lib.cpn_box_votes_workspace_bytes(K)),), dtype=torch.uint8, device=boxes.device)
-        L.check(lib.cpn_box_votes(L.ptr(boxes.contiguous().float()), K, float(thresh), L.ptr(ws), L.ptr(votes),
+        boxes = boxes.contiguous().float()                    # named: a converted copy must outlive the launch
+        L.check(lib.cpn_box_votes(L.ptr(boxes), K, float(thresh), L.ptr(ws), L.ptr(votes),
                                   L.stream_ptr()), 'box_votes')
     return votes
 

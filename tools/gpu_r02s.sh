@@ -1,0 +1,7 @@
+#!/bin/bash
+# Round 2, call s: slide kernels after the packed-counter uint16 histogram / vectorised gray kernel.
+cd "$(dirname "$0")/.." || exit 1
+mkdir -p gpurun_out; OUT=gpurun_out
+timeout -s KILL 900 python -m pytest tests/test_preprocess.py tests/test_outputs.py -m gpu -q --timeout 600 -p no:cacheprovider > $OUT/r02s_pytest_new.log 2>&1
+echo "pytest rc=$?" >> $OUT/r02s_pytest_new.log; tail -15 $OUT/r02s_pytest_new.log
+timeout -s KILL 600 python tools/bench_preprocess.py > $OUT/r02s_bench_preprocess.log 2>&1; tail -20 $OUT/r02s_bench_preprocess.log
