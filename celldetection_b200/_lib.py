@@ -55,6 +55,7 @@ SYMBOLS = {
     'cpn_plan_forward': (_I, [_P, _P, _I, ctypes.POINTER(_P), _I, _P]),
     'cpn_plan_forward_range': (_I, [_P, _I, _I, _P, _I, ctypes.POINTER(_P), _I, _P]),
     'cpn_plan_num_launches': (_I, [_P]),
+    'cpn_plan_set_active_rows': (_I, [_P, _I64]),
     'cpn_plan_run_op': (_I, [_P, _I, _P, _I, ctypes.POINTER(_P), _I, _P]),
     'cpn_plan_destroy': (None, [_P]),
     'cpn_conv2d': (_I, [ctypes.POINTER(Op), _P, _P, _P, _P, _P]),
@@ -132,6 +133,27 @@ def addr(t):
 def stream_ptr():
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class nvtx_range:
+    """NVTX range around a stage of the path when ``CPN_NVTX=1`` (nsys / ncu --nvtx timelines: ``cpn.plan``, ``cpn.post``,
+    ``cpn.tiles``, ``cpn.exchange``, ``cpn.stitch``, ``cpn.preprocess``); a no-op otherwise."""
+    enabled = os.environ.get('CPN_NVTX', '0') == '1'
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if nvtx_range.enabled:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if nvtx_range.enabled:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def launch_count():

@@ -61,6 +61,7 @@ int conv_tc_plan_create(const cpn_op_t& op, const void* src, void* dst, const vo
 int conv_tc_launch(const ConvTcPlan* p, cudaStream_t st);
 int conv_tc_fuse_proj(ConvTcPlan* p, int n, const cpn_op_t* projs, const char* weights);
 void conv_tc_bind_proj_out(ConvTcPlan* p, int head, void* out);
+int conv_tc_limit_rows(ConvTcPlan* p, long long rows);
 void conv_tc_plan_destroy(ConvTcPlan* p);
 
 int prep_launch(const cpn_op_t& op, const void* input, int input_format, void* dst, int32_t* flags, cudaStream_t st);

@@ -110,6 +110,8 @@ struct ConvTcPlan {
   int stages;
   int smem_bytes;
   int grid;
+  long long full_tiles;   // total_tiles / grid of the whole tensor (conv_tc_limit_rows trims the launch to leading rows)
+  int full_grid;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1909,7 +1911,25 @@ int conv_tc_plan_create(const cpn_op_t& op_in, const void* src, void* dst, const
       pl->grid = (int)(2 * pairs);
     }
   }
+  pl->full_tiles = p.total_tiles;
+  pl->full_grid = pl->grid;
   *out = owner.release();
+  return 0;
+}
+
+// Run only the M tiles that hold the first `rows` pixels (row-major over the whole batch) of the next launches: the sparse
+// heads' row matrix is sized for a power-of-two row count but only the leading P rows are proposals.  Tiles are ordered N
+// fastest, so trimming the tile count trims whole 128-pixel row blocks.  rows < 0 restores the full launch.
+int conv_tc_limit_rows(ConvTcPlan* pl, long long rows) {
+  ConvTcParams& p = pl->p;
+  if (rows < 0) { p.total_tiles = pl->full_tiles; pl->grid = pl->full_grid; return 0; }
+  CPN_REQUIRE(!pl->pair && !p.halo && p.tiles_x == 1, "conv_tc: row limit needs a plain 1x1 layer over a [1, rows/16, 16] tensor");
+  long long m_tiles = (rows + TC_BM - 1) / TC_BM;
+  if (m_tiles < 1) m_tiles = 1;
+  long long tiles = m_tiles * p.tiles_n;
+  if (tiles > pl->full_tiles) tiles = pl->full_tiles;
+  p.total_tiles = tiles;
+  pl->grid = (int)(tiles < pl->full_grid ? tiles : pl->full_grid);
   return 0;
 }
 

@@ -207,6 +207,13 @@ extern "C" int cpn_plan_run_op(cpn_plan_t* plan, int index, const void* input, i
 
 extern "C" int cpn_plan_num_launches(const cpn_plan_t* plan) { return plan ? plan->n_launches : 0; }
 
+extern "C" int cpn_plan_set_active_rows(cpn_plan_t* plan, int64_t rows) {
+  CPN_REQUIRE(plan, "plan_set_active_rows: NULL plan");
+  for (ConvTcPlan* t : plan->tc)
+    if (t && conv_tc_limit_rows(t, (long long)rows)) return 1;
+  return 0;
+}
+
 extern "C" void cpn_plan_destroy(cpn_plan_t* plan) {
   if (!plan) return;
   for (ConvTcPlan* t : plan->tc)

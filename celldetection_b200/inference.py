@@ -204,6 +204,7 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
 
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max_workers=1)
+    tiles_range = L.nvtx_range('cpn.tiles').__enter__()
     try:
         nxt = pool.submit(load, 0, 0) if (pool is not None and nb) else None
         for bi in range(nb):
@@ -250,6 +251,7 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
             rows = torch.arange(K, dtype=torch.float32)
             acc.append((flat, keep, torch.stack((tile_ids, rows), 1).to(dev, non_blocking=True)))
     finally:
+        tiles_range.__exit__()
         if pool is not None:
             pool.shutdown(wait=True)
     t_tiles = _now(dev, timings)
@@ -266,14 +268,16 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
         if getattr(model, 'uncertainty_head', False):
             res['box_uncertainties'] = z(0, 4)
         res['order_key'] = z(0, 2)
-    res = allgather_detections(res)
-    if world > 1:
-        res = canonical_order(res)      # 1-GPU and N-GPU runs feed the global NMS the same sequence
-    res.pop('order_key')
+    with L.nvtx_range('cpn.exchange'):
+        res = allgather_detections(res)
+        if world > 1:
+            res = canonical_order(res)      # 1-GPU and N-GPU runs feed the global NMS the same sequence
+        res.pop('order_key')
     t_gather = _now(dev, timings)
     if 'nms' in rules and res['boxes'].shape[0] > 0:
-        keep = O.nms(res['boxes'], res['scores'], nms_thresh)
-        res = OrderedDict((k, v[keep]) for k, v in res.items())
+        with L.nvtx_range('cpn.stitch'):
+            keep = O.nms(res['boxes'], res['scores'], nms_thresh)
+            res = OrderedDict((k, v[keep]) for k, v in res.items())
     if timings is not None:
         t_end = _now(dev, timings)
         timings.update(tiles_s=t_tiles - t_start, exchange_s=t_gather - t_tiles, stitch_s=t_end - t_gather,
@@ -353,8 +357,9 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
         from .preprocessing import preprocess
         if isinstance(img, np.ndarray) and img.dtype == np.uint16:
             img = img.view(np.int16)
-        img = preprocess(img, gamma=gamma, contrast=contrast, brightness=brightness, percentile=percentile,
-                         grayscale=grayscale, device=dev)
+        with L.nvtx_range('cpn.preprocess'):
+            img = preprocess(img, gamma=gamma, contrast=contrast, brightness=brightness, percentile=percentile,
+                             grayscale=grayscale, device=dev)
         resident = True
     if resident:                                             # slide already resident in HBM: [h, w, c] uint8 / float32
         if img.dim() != 3 or img.dtype not in (torch.uint8, torch.float32) or img.device != dev:

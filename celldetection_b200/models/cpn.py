@@ -273,6 +273,8 @@ class CPN(nn.Module):
             dst_view = sp.view_of(sp.g.input_tensor)
             L.check(lib.cpn_gather_patches(L.ptr(plan.arena), ctypes.byref(src_view), L.ptr(idx[start:]), n, g.head_k,
                                            L.ptr(sp.arena), ctypes.byref(dst_view), L.stream_ptr()), 'gather_patches')
+            if os.environ.get('CPN_SPARSE_TRIM', '1') != '0':
+                sp.set_active_rows(n)        # the row matrix is sized for `rows` (a power of two), only n are proposals
             sp.forward(None, L.IN_F32_NCHW, [rec[start:]])
         self.last_sparse_rows = sum(c[2] for c in chunks)
         return rec
@@ -499,9 +501,11 @@ class CPN(nn.Module):
     def forward_flat(self, inputs, fmt=None, nms=True, **kwargs):
         """Like ``forward`` but returns (flat dict of concatenated tensors, rows per image); accepts uint8 NHWC
         batches (``fmt=_lib.IN_U8_NHWC``) so tile crops need no host-side transpose."""
-        plan, outs, hw, rest = self._run_plan(inputs, fmt, staged=True)
-        return self.post_flat(outs[0], outs[1], outs[2], hw, nms=nms, after_count=rest,
-                              **self._post_kwargs(plan, outs, kwargs))
+        with L.nvtx_range('cpn.plan'):
+            plan, outs, hw, rest = self._run_plan(inputs, fmt, staged=True)
+        with L.nvtx_range('cpn.post'):
+            return self.post_flat(outs[0], outs[1], outs[2], hw, nms=nms, after_count=rest,
+                                  **self._post_kwargs(plan, outs, kwargs))
 
     # ---- model(x) ---------------------------------------------------------------------------------------------------
     def forward(self, inputs: Tensor, targets=None, nms=True, **kwargs):
@@ -509,8 +513,11 @@ class CPN(nn.Module):
             if self.training and targets is None:
                 raise ValueError('In training mode, targets should be passed')
             raise NotImplementedError('celldetection_b200 accelerates CPN inference only (use .eval()).')
-        plan, outs, hw, rest = self._run_plan(inputs, staged=True)
-        return self.post(outs[0], outs[1], outs[2], hw, nms=nms, after_count=rest, **self._post_kwargs(plan, outs, kwargs))
+        with L.nvtx_range('cpn.plan'):
+            plan, outs, hw, rest = self._run_plan(inputs, staged=True)
+        with L.nvtx_range('cpn.post'):
+            return self.post(outs[0], outs[1], outs[2], hw, nms=nms, after_count=rest,
+                             **self._post_kwargs(plan, outs, kwargs))
 
 
 def _make(arch):

@@ -356,6 +356,10 @@ class Plan:
                     'plan_forward_range')
         return outputs
 
+    def set_active_rows(self, rows):
+        """Sparse-heads plans: compute only the 128-row blocks holding the first ``rows`` rows (< 0: all)."""
+        L.check(L.load().cpn_plan_set_active_rows(self.handle, int(rows)), 'plan_set_active_rows')
+
     def forward_graph(self, x, input_format):
         """CUDA-graph replay of the whole plan (one graph launch instead of ``n_launches`` kernel launches): the input is
         copied into a static buffer, the graph is replayed on the current stream and the STATIC output tensors are

@@ -152,6 +152,9 @@ int cpn_plan_forward_range(cpn_plan_t* plan, int first_op, int end_op, const voi
                            void* const* outputs_host, int n_outputs, void* stream);
 /* Kernel launches one forward of this plan issues. */
 int cpn_plan_num_launches(const cpn_plan_t* plan);
+/* Sparse-heads plans (one 1x1 layer over a [1, rows/16, 16] row matrix): the following forwards compute only the 128-row
+ * blocks that hold the first `rows` rows (the proposals actually gathered); rows < 0 restores the whole matrix. */
+int cpn_plan_set_active_rows(cpn_plan_t* plan, int64_t rows);
 /* Debug/profiling: run only op `index` (same bindings as forward). */
 int cpn_plan_run_op(cpn_plan_t* plan, int index, const void* input, int input_format, void* const* outputs_host,
                     int n_outputs, void* stream);
