@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcpn_b200.so')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # ---- enums (mirror include/cpn_b200.h) -------------------------------------------------------------------------------
 DT_F32, DT_F16, DT_U8, DT_F16X2, DT_F16F8, DT_U16 = 0, 1, 2, 3, 4, 5

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CPN_B200_ABI_VERSION 4
+#define CPN_B200_ABI_VERSION 5
 
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* status / diagnostics                                                                                             */
