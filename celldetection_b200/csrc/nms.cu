@@ -7,17 +7,135 @@
 // the result lists kept indices in descending score order.  The 50 000-chunk rule of batched_box_nmsi is reproduced
 // with two passes (chunks of the ORIGINAL row order, then NMS over the concatenated survivors).
 //
-// Algorithm: one stable radix sort of (segment, ~score) keys (CUB, utility only), then one CTA per segment runs a
+// Algorithm: one stable radix sort of (segment, ~score) keys (radix_sort_pairs below), then one CTA per segment runs a
 // blocked greedy scan with O(P) memory: 256 candidates at a time are (a) tested against all previously kept boxes
 // (staged through shared memory), (b) cross-tested inside the tile into a 256x256 bit matrix, (c) resolved by one warp
 // that jumps from kept box to kept box (__ffs over the alive bitmap), so the sequential chain is K long, not P long.
 // Compiled with -fmad=false so the IoU arithmetic rounds exactly like the reference's.
 #include "common.cuh"
-#include <cub/device/device_radix_sort.cuh>
 
 namespace cpn {
 
 constexpr int NMS_T = 256;  // candidates per tile == threads per CTA
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (uint64 key, int32 value) pairs, 8 bits per pass over bits [0, end_bit): the ordering step of
+// every NMS variant here (score order, (segment, score) order, (grid cell, rank) order).  Three kernels per pass: per-block
+// digit histograms (shared-memory atomics), one exclusive scan over (digit-major, block-minor) counts, and a scatter in
+// which every block walks its 4096-pair chunk in order -- ranks among equal digits come from __match_any_sync inside a warp
+// and per-warp digit counts across warps, so equal keys keep their input order (the NMS tie-break depends on it).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256, RS_TILES = 16, RS_CHUNK = RS_THREADS * RS_TILES;
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, int n, int shift, uint32_t mask,
+                                                             uint32_t* __restrict__ counts, int nblocks) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * RS_CHUNK;
+#pragma unroll 4
+  for (int t = 0; t < RS_TILES; ++t) {
+    const int i = base + t * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t* __restrict__ counts, int total) {
+  __shared__ uint32_t part[1024];
+  const int per = (total + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(lo + per, total);
+  uint32_t sum = 0;
+  for (int i = lo; i < hi; ++i) sum += counts[i];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {               // Hillis-Steele inclusive scan of the 1024 partial sums
+    const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - sum;                  // exclusive prefix of this thread's segment
+  for (int i = lo; i < hi; ++i) { const uint32_t c = counts[i]; counts[i] = run; run += c; }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
+                                                                uint64_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int n,
+                                                                int shift, uint32_t mask, const uint32_t* __restrict__ offsets,
+                                                                int nblocks) {
+  __shared__ uint32_t base[256];
+  __shared__ uint32_t wcnt[RS_THREADS / 32][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  base[threadIdx.x] = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
+  for (int w = 0; w < RS_THREADS / 32; ++w) wcnt[w][threadIdx.x] = 0;
+  __syncthreads();
+  const int start = blockIdx.x * RS_CHUNK;
+  for (int t = 0; t < RS_TILES; ++t) {
+    const int i = start + t * RS_THREADS + threadIdx.x;
+    if (start + t * RS_THREADS >= n) break;                 // block-uniform
+    const bool ok = i < n;
+    uint64_t k = 0; int32_t v = 0;
+    if (ok) { k = keys_in[i]; v = vals_in[i]; }
+    const uint32_t d = ok ? ((uint32_t)(k >> shift) & mask) : (0x100u + lane);
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (ok && rank == 0) wcnt[warp][d] = __popc(peers);
+    __syncthreads();
+    if (ok) {
+      uint32_t pos = base[d] + rank;
+      for (int w = 0; w < warp; ++w) pos += wcnt[w][d];
+      keys_out[pos] = k;
+      vals_out[pos] = v;
+    }
+    __syncthreads();
+    uint32_t add = 0;
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; ++w) { add += wcnt[w][threadIdx.x]; wcnt[w][threadIdx.x] = 0; }
+    base[threadIdx.x] += add;
+    __syncthreads();
+  }
+}
+
+static inline size_t rs_align(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t radix_sort_tmp_bytes(int64_t n) {
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  const size_t nblocks = (nn + RS_CHUNK - 1) / RS_CHUNK;
+  return rs_align(256 * nblocks * 4) + rs_align(nn * 8) + rs_align(nn * 4) + 256;
+}
+
+// keys_in / vals_in are not modified; the sorted pairs land in keys_out / vals_out.
+int radix_sort_pairs(void* tmp, const uint64_t* keys_in, uint64_t* keys_out, const int32_t* vals_in, int32_t* vals_out, int n,
+                     int end_bit, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int nblocks = (n + RS_CHUNK - 1) / RS_CHUNK;
+  char* b = reinterpret_cast<char*>(tmp);
+  uint32_t* counts = reinterpret_cast<uint32_t*>(b);
+  uint64_t* keys_t = reinterpret_cast<uint64_t*>(b + rs_align(256 * (size_t)nblocks * 4));
+  int32_t* vals_t = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(keys_t) + rs_align((size_t)n * 8));
+  const int passes = end_bit <= 0 ? 1 : (end_bit + 7) / 8;
+  const uint64_t* ksrc = keys_in;
+  const int32_t* vsrc = vals_in;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    const int bits = end_bit - shift < 8 ? (end_bit - shift > 0 ? end_bit - shift : 8) : 8;
+    const uint32_t mask = (1u << bits) - 1u;
+    const bool to_out = ((passes - 1 - p) & 1) == 0;
+    uint64_t* kdst = to_out ? keys_out : keys_t;
+    int32_t* vdst = to_out ? vals_out : vals_t;
+    rs_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(ksrc, n, shift, mask, counts, nblocks);
+    CPN_CHECK_LAUNCH();
+    rs_scan_kernel<<<1, 1024, 0, st>>>(counts, 256 * nblocks);
+    CPN_CHECK_LAUNCH();
+    rs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, shift, mask, counts, nblocks);
+    CPN_CHECK_LAUNCH();
+    count_launch(3);
+    ksrc = kdst;
+    vsrc = vdst;
+  }
+  return 0;
+}
 
 __device__ __forceinline__ uint32_t float_desc_key(float f) {
   uint32_t u = __float_as_uint(f);
@@ -230,8 +348,8 @@ struct NmsWs {
   float4* kept_boxes;
   int32_t *keepA, *rows2, *group_start, *countsA;
   long long* n2;
-  void* cub_tmp;
-  size_t cub_bytes;
+  void* sort_tmp;
+  size_t sort_bytes;
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -253,14 +371,12 @@ static size_t carve(void* base, int64_t n, int n_segments, NmsWs* ws) {
   int32_t* gs = (int32_t*)take((size_t)(n_sub_max + 2) * 4);
   int32_t* ca = (int32_t*)take((size_t)(n_sub_max + 2) * 4);
   long long* n2 = (long long*)take(64);
-  size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)nn, 0, 64, (cudaStream_t)0);
-  void* tmp = take(cub_bytes + 256);
+  const size_t sort_bytes = radix_sort_tmp_bytes((int64_t)nn);
+  void* tmp = take(sort_bytes + 256);
   if (ws) {
     ws->keys_a = ka; ws->keys_b = kb2; ws->vals_a = va; ws->vals_b = vb; ws->kept_boxes = kept; ws->keepA = keepA;
-    ws->rows2 = rows2; ws->group_start = gs; ws->countsA = ca; ws->n2 = n2; ws->cub_tmp = tmp;
-    ws->cub_bytes = cub_bytes + 256;
+    ws->rows2 = rows2; ws->group_start = gs; ws->countsA = ca; ws->n2 = n2; ws->sort_tmp = tmp;
+    ws->sort_bytes = sort_bytes + 256;
   }
   return off;
 }
@@ -297,10 +413,7 @@ extern "C" int cpn_nms_segments(const float* boxes, const float* scores, const i
   const int n_groups_a = two_pass ? (int)(n_segments + n_boxes / chunk + 1) : n_segments;
   int end_bit = 32;
   while ((1ll << (end_bit - 32)) < n_groups_a + 1 && end_bit < 64) ++end_bit;
-  size_t cb = ws.cub_bytes;
-  CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, cb, ws.keys_a, ws.keys_b, ws.vals_a, ws.vals_b, n, 0,
-                                                 end_bit, st));
-  count_launch(4);
+  if (radix_sort_pairs(ws.sort_tmp, ws.keys_a, ws.keys_b, ws.vals_a, ws.vals_b, n, end_bit, st)) return 1;
   nms_bounds_kernel<<<(n_groups_a + 1 + 127) / 128, 128, 0, st>>>(ws.keys_b, n, n_groups_a, ws.group_start);
   CPN_CHECK_LAUNCH();
   if (!two_pass) {
@@ -317,10 +430,7 @@ extern "C" int cpn_nms_segments(const float* boxes, const float* scores, const i
   CPN_CHECK_LAUNCH();
   nms_keys_rows_kernel<<<gb, tb, 0, st>>>(scores, seg_offsets, n_segments, ws.rows2, ws.n2, ws.keys_a, ws.vals_a, n);
   CPN_CHECK_LAUNCH();
-  cb = ws.cub_bytes;
-  CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, cb, ws.keys_a, ws.keys_b, ws.vals_a, ws.vals_b, n, 0, 64,
-                                                 st));
-  count_launch(4);
+  if (radix_sort_pairs(ws.sort_tmp, ws.keys_a, ws.keys_b, ws.vals_a, ws.vals_b, n, 64, st)) return 1;
   nms_bounds_kernel<<<(n_segments + 1 + 127) / 128, 128, 0, st>>>(ws.keys_b, n, n_segments, ws.group_start);
   CPN_CHECK_LAUNCH();
   // results are packed at each segment's ORIGINAL offset (seg_offsets), as documented
@@ -473,11 +583,9 @@ __global__ void __launch_bounds__(1024) grid_compact_kernel(const int32_t* __res
 
 extern "C" size_t cpn_nms_grid_workspace_bytes(int64_t n_boxes) {
   const size_t nn = (size_t)(n_boxes > 0 ? n_boxes : 1);
-  size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)nn, 0, 64, (cudaStream_t)0);
+  const size_t sort_bytes = radix_sort_tmp_bytes((int64_t)nn);
   // keys a/b (8), vals a/b (4), perm (4), cell_keys (8), cell_rows (4), state a/b (1), flags (4) + small
-  return align_up(nn * 8, 256) * 3 + align_up(nn * 4, 256) * 5 + align_up(nn, 256) * 2 + align_up(cub_bytes + 256, 256) +
+  return align_up(nn * 8, 256) * 3 + align_up(nn * 4, 256) * 5 + align_up(nn, 256) * 2 + align_up(sort_bytes + 256, 256) +
          4096;
 }
 
@@ -508,10 +616,8 @@ extern "C" int cpn_nms_grid(const float* boxes, const float* scores, int64_t n_b
   uint8_t* state_b = (uint8_t*)take(nn);
   int* small = (int*)take(2048);   // [0..4] extents, [8] undecided, GridInfo at +64 bytes
   GridInfo* gi = reinterpret_cast<GridInfo*>(reinterpret_cast<char*>(small) + 64);
-  size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                  (const int32_t*)nullptr, (int32_t*)nullptr, n, 0, 64, st);
-  void* cub_tmp = take(cub_bytes + 256);
+  const size_t sort_bytes = radix_sort_tmp_bytes(n);
+  void* sort_tmp = take(sort_bytes + 256);
   const int tb = 256, gb = (n + tb - 1) / tb;
   // 1. stable descending score order -> perm[rank] = row
   const int32_t seg_host[2] = {0, n};
@@ -519,9 +625,7 @@ extern "C" int cpn_nms_grid(const float* boxes, const float* scores, int64_t n_b
   CPN_CHECK_CUDA(cudaMemcpyAsync(seg_dev, seg_host, sizeof(seg_host), cudaMemcpyHostToDevice, st));
   nms_keys_kernel<<<gb, tb, 0, st>>>(scores, seg_dev, 1, n, 0, keys_a, vals_a);
   CPN_CHECK_LAUNCH();
-  size_t cb = cub_bytes + 256;
-  CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_a, keys_b, vals_a, perm, n, 0, 33, st));
-  count_launch(4);
+  if (radix_sort_pairs(sort_tmp, keys_a, keys_b, vals_a, perm, n, 33, st)) return 1;
   // 2. grid: extents -> cell size -> (cell, rank) order
   const int ext_init[5] = {0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
   CPN_CHECK_CUDA(cudaMemcpyAsync(small, ext_init, sizeof(ext_init), cudaMemcpyHostToDevice, st));
@@ -531,9 +635,7 @@ extern "C" int cpn_nms_grid(const float* boxes, const float* scores, int64_t n_b
   CPN_CHECK_LAUNCH();
   grid_cellkeys_kernel<<<gb, tb, 0, st>>>(reinterpret_cast<const float4*>(boxes), perm, n, gi, keys_a, vals_a);
   CPN_CHECK_LAUNCH();
-  cb = cub_bytes + 256;
-  CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_a, cell_keys, vals_a, cell_rows, n, 0, 64, st));
-  count_launch(4);
+  if (radix_sort_pairs(sort_tmp, keys_a, cell_keys, vals_a, cell_rows, n, 64, st)) return 1;
   // 3. rounds until every box is decided (the undecided count is read back every 4 rounds)
   CPN_CHECK_CUDA(cudaMemsetAsync(state_a, 0, nn, st));
   uint8_t *s_in = state_a, *s_out = state_b;
@@ -617,10 +719,8 @@ namespace cpn {
 
 size_t grid_bin_workspace_bytes(int64_t n_boxes) {
   const size_t nn = (size_t)(n_boxes > 0 ? n_boxes : 1);
-  size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)nn, 0, 64, (cudaStream_t)0);
-  return align_up(nn * 8, 256) * 2 + align_up(nn * 4, 256) * 2 + 2048 + align_up(cub_bytes + 256, 256) + 1024;
+  const size_t sort_bytes = radix_sort_tmp_bytes((int64_t)nn);
+  return align_up(nn * 8, 256) * 2 + align_up(nn * 4, 256) * 2 + 2048 + align_up(sort_bytes + 256, 256) + 1024;
 }
 
 // Bins `n` boxes (by centre) into the uniform grid whose cell is the largest box extent: boxes that overlap lie in
@@ -637,10 +737,8 @@ int grid_bin_boxes(const float4* boxes, int n, void* workspace, GridBins* out, c
   int32_t* cell_rows = (int32_t*)take(nn * 4);
   int* small = (int*)take(2048);
   GridInfo* gi = reinterpret_cast<GridInfo*>(reinterpret_cast<char*>(small) + 64);
-  size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                  (const int32_t*)nullptr, (int32_t*)nullptr, n, 0, 64, st);
-  void* cub_tmp = take(cub_bytes + 256);
+  const size_t sort_bytes = radix_sort_tmp_bytes(n);
+  void* sort_tmp = take(sort_bytes + 256);
   const int tb = 256, gb = (n + tb - 1) / tb;
   const int ext_init[5] = {0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
   CPN_CHECK_CUDA(cudaMemcpyAsync(small, ext_init, sizeof(ext_init), cudaMemcpyHostToDevice, st));
@@ -650,9 +748,7 @@ int grid_bin_boxes(const float4* boxes, int n, void* workspace, GridBins* out, c
   CPN_CHECK_LAUNCH();
   votes_cellkeys_kernel<<<gb, tb, 0, st>>>(boxes, n, gi, keys_a, vals_a);
   CPN_CHECK_LAUNCH();
-  size_t cb = cub_bytes + 256;
-  CPN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_a, cell_keys, vals_a, cell_rows, n, 0, 64, st));
-  count_launch(4);
+  if (radix_sort_pairs(sort_tmp, keys_a, cell_keys, vals_a, cell_rows, n, 64, st)) return 1;
   out->cell_keys = cell_keys; out->cell_rows = cell_rows; out->gi = gi;
   return 0;
 }

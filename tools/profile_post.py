@@ -29,7 +29,7 @@ sd = bench.build_state_dict(core_fn, calib)
 model.load_state_dict(sd)
 model.to(dev)
 x = torch.rand(N, 3, 512, 512, generator=g).to(dev)
-plan, outs, hw = model._run_plan(x)
+plan, outs, hw = model._run_plan(x, dense=True)      # dense heads: the stand-alone decode entry point reads locfou per pixel
 sc, lf, rf = outs[:3]
 torch.cuda.synchronize()
 lib = L.load()
