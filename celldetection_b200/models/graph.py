@@ -39,14 +39,15 @@ RESNETS = {
 ARCHS = ('CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet') + tuple(
     f'Cpn{e}{d}' for d in ('UNet', 'FPN') for e in RESNETS
     if not (d == 'UNet' and e.startswith('Wide')) and f'Cpn{e}{d}' not in ('CpnResNet18FPN', 'CpnResNeXt101UNet')) + (
-    'CpnWideU22',)      # models/cpn.py:890-929, unet.py:497-524: U22 with doubled widths (128 ... 2048)
+    'CpnWideU22',       # models/cpn.py:890-929, unet.py:497-524: U22 with doubled widths (128 ... 2048)
+    'CpnResUNet')       # models/cpn.py:811-849, unet.py:434-464: U-Net whose encoder AND decoder blocks are ResBlocks
 # U-Net encoders of models/unet.py:405-524 by base width (CpnSlimU22's 32-channel layers are below the 64-wide MMA tile)
 U22_BASE = {'U22': 64, 'WideU22': 128}
 
 
 def split_arch(arch):
     """'CpnResNet50FPN' -> ('ResNet50', 'FPN'); 'CpnU22' -> ('U22', 'UNet')."""
-    if arch in ('CpnU22', 'CpnWideU22'):
+    if arch in ('CpnU22', 'CpnWideU22', 'CpnResUNet'):
         return arch[3:], 'UNet'
     for d in ('UNet', 'FPN'):
         if arch.endswith(d) and arch[3:-len(d)] in RESNETS:
@@ -107,6 +108,8 @@ class LOp:
     up2: bool = False                          # 3x3 conv on the 2x nearest-up-sampled src, computed from the low-res src
     gather: Optional[Tuple[int, int]] = None   # (k, cin): 1x1 conv over rows written by cpn_gather_patches, i.e. the
                                                # k x k convolution evaluated at selected pixels only
+    embed1x1: bool = False                     # a 1x1 convolution of the raw input that reads the SAME im2col matrix as the
+                                               # k x k stem convolution: its weights sit at the centre tap's K positions
 
 
 class Tracer:
@@ -173,6 +176,18 @@ class Tracer:
         x.c, x.h, x.w = kp, ho, wo                 # the prep output is now the im2col matrix
         op = LOp('conv', src=x, dst=self.tensor(cout, ho, wo), k=1, stride=1, pad=0, act=act, params=params,
                  name=name, im2col=(k, cin))
+        return self._emit(op)
+
+    def stem_conv_1x1(self, x, cout, act, params, name):
+        """A 1x1 convolution of the raw network input next to a k x k stem convolution (ResBlock's identity mapping,
+        commons.py:292-296).  After ``stem_conv`` turned the input into an im2col matrix, the pixel itself is the centre tap's
+        column block, so the 1x1 runs on the same matrix with its weights embedded there (zeros elsewhere)."""
+        prep = next(o for o in self.ops if o.kind == 'prep')
+        if not (self.stem_im2col and prep.im2col is not None and prep.dst is x):
+            return self.conv(x, cout, 1, act=act, params=params, name=name)
+        assert prep.stride == 1, 'embedded 1x1: the k x k stem convolution must have stride 1'
+        op = LOp('conv', src=x, dst=self.tensor(cout, x.h, x.w), k=1, stride=1, pad=0, act=act, params=params, name=name,
+                 im2col=prep.im2col, embed1x1=True)
         return self._emit(op)
 
     def conv(self, x, cout, k, stride=1, pad=None, act='none', res=None, params=None, name=''):
@@ -277,16 +292,47 @@ def _two_conv_norm_relu(g, x, p, cin, cout, bias=True):
     return _conv_bn_act(g, x, f'{p}.3', f'{p}.4', cout, cout, 3, bias=bias)
 
 
-def _unet_encoder(g, x, p, cin, depth=5, base=64):
-    """models/unet.py:29-58"""
+def _res_block_spec(g, p, cin, cout):
+    """Parameters of ``ResBlock`` (models/commons.py:259-359) in module order: downsample (ConvNorm 1x1, bias=False) when the
+    widths differ, then block = conv3x3 (no bias), BN, act, conv3x3 (no bias), BN."""
+    if cin != cout:
+        g.conv_spec(f'{p}.downsample.0', cin, cout, 1, False)
+        g.bn_spec(f'{p}.downsample.1', cout)
+    g.conv_spec(f'{p}.block.0', cin, cout, 3, False)
+    g.bn_spec(f'{p}.block.1', cout)
+    g.conv_spec(f'{p}.block.3', cout, cout, 3, False)
+    g.bn_spec(f'{p}.block.4', cout, True)
+
+
+def _res_block_ops(g, x, p, cin, cout):
+    """``act(block(x) + downsample(x))`` (commons.py:300-304): the second convolution adds the identity branch through its
+    residual input.  On the raw network input the 3x3 becomes the im2col stem and the 1x1 identity mapping reads the same
+    matrix (``Tracer.stem_conv_1x1``)."""
+    pa = ConvParams([f'{p}.block.0.weight'], [None], [f'{p}.block.1'])
+    pb = ConvParams([f'{p}.block.3.weight'], [None], [f'{p}.block.4'])
+    pd = ConvParams([f'{p}.downsample.0.weight'], [None], [f'{p}.downsample.1'])
+    if getattr(x, 'is_input', False):
+        y = g.stem_conv(x, cout, 3, 1, 'relu', pa, f'{p}.block.0')
+        idt = g.stem_conv_1x1(x, cout, 'none', pd, f'{p}.downsample.0')
+    else:
+        y = g.conv(x, cout, 3, act='relu', params=pa, name=f'{p}.block.0')
+        idt = g.conv(x, cout, 1, act='none', params=pd, name=f'{p}.downsample.0') if cin != cout else x
+    return g.conv(y, cout, 3, act='relu', res=idt, params=pb, name=f'{p}.block.3')
+
+
+def _unet_encoder(g, x, p, cin, depth=5, base=64, block='two_conv'):
+    """models/unet.py:29-58 (``block``: 'two_conv' = TwoConvNormRelu, 'res' = ResBlock)"""
     feats, chans = [], []
     for i in range(depth):
         cout = base * 2 ** i
-        if i == 0:
-            x = _two_conv_norm_relu(g, x, f'{p}.0', cin, cout)
-        else:
+        bp, bc = (f'{p}.0', cin) if i == 0 else (f'{p}.{i}.1', chans[-1])
+        if i > 0:
             x = g.maxpool(x, 2, 2, 0)
-            x = _two_conv_norm_relu(g, x, f'{p}.{i}.1', chans[-1], cout)
+        if block == 'res':
+            _res_block_spec(g, bp, bc, cout)
+            x = _res_block_ops(g, x, bp, bc, cout)
+        else:
+            x = _two_conv_norm_relu(g, x, bp, bc, cout)
         feats.append(x)
         chans.append(cout)
     return feats, chans
@@ -338,7 +384,7 @@ def _resnet_encoder(g, x, p, cin, kind):
     return feats, chans
 
 
-def _unet_decoder(g, feats, chans, p, bridges):
+def _unet_decoder(g, feats, chans, p, bridges, block='two_conv'):
     """models/unet.py:62-176 (bookkeeping) and :178-249 (forward), with the inner 1x1 conv commuted before the
     nearest up-sampling.  Returns the decoder outputs per level (index 0 = finest)."""
     in_list = [0] * bridges + list(chans)
@@ -361,6 +407,11 @@ def _unet_decoder(g, feats, chans, p, bridges):
         bias = lat > 0                           # bridge block = TwoConvNormRelu(bias=False) (unet.py:95-98)
         cin = inc + lat
         bp = f'{p}.layer_blocks.{i}'
+        if block == 'res':                       # ResUNet: block_cls = ResBlock for the decoder too (unet.py:459-463)
+            assert lat > 0, 'ResBlock decoders have no bridge levels'
+            _res_block_spec(g, bp, cin, ouc)
+            blocks[i] = (cin, ouc, bias)
+            continue
         g.conv_spec(f'{bp}.0', cin, ouc, 3, bias)
         g.bn_spec(f'{bp}.1', ouc)
         g.conv_spec(f'{bp}.3', ouc, ouc, 3, bias)
@@ -381,6 +432,14 @@ def _unet_decoder(g, feats, chans, p, bridges):
             last_c = ouc
         cin, ouc, bias = blocks[i]
         bp = f'{p}.layer_blocks.{i}'
+        if block == 'res':
+            up = g.upsample(top, lateral.h, lateral.w)
+            x = g.cat(lateral, up)               # cat_order 0: (lateral, top_down) (unet.py:219-224)
+            assert x.c == cin, (x.c, cin)
+            x = _res_block_ops(g, x, bp, cin, ouc)
+            last, last_c = x, ouc
+            results[i] = x
+            continue
         pa = ConvParams([f'{bp}.0.weight'], [f'{bp}.0.bias' if bias else None], [f'{bp}.1'])
         pb = ConvParams([f'{bp}.3.weight'], [f'{bp}.3.bias' if bias else None], [f'{bp}.4'])
         if (lateral is not None and g.fuse_up2 and (lateral.h, lateral.w) == (2 * top.h, 2 * top.w) and
@@ -471,9 +530,10 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
     bb = 'core.backbone'
     x = g.prep(in_channels)
     enc, dec = split_arch(arch)
-    if enc in U22_BASE:
-        feats, chans = _unet_encoder(g, x, f'{bb}.body', in_channels, base=U22_BASE[enc])
-        res, out_ch = _unet_decoder(g, feats, chans, f'{bb}.unet', bridges=0)
+    if enc in U22_BASE or enc == 'ResUNet':
+        block = 'res' if enc == 'ResUNet' else 'two_conv'
+        feats, chans = _unet_encoder(g, x, f'{bb}.body', in_channels, base=U22_BASE.get(enc, 64), block=block)
+        res, out_ch = _unet_decoder(g, feats, chans, f'{bb}.unet', bridges=0, block=block)
         head_feat, head_c, ref_feat, ref_c = res[1], out_ch[1], res[0], out_ch[0]
     elif dec == 'UNet':
         feats, chans = _resnet_encoder(g, x, f'{bb}.body', in_channels, enc)
@@ -584,6 +644,8 @@ def conv_flops(g: Tracer):
     for op in g.ops:
         if op.kind == 'conv':
             kk = op.im2col[0] ** 2 * op.im2col[1] if op.im2col else (op.src.c // op.params.groups) * op.k * op.k
+            if op.embed1x1:
+                kk = op.im2col[1]
             if op.up2 and op.params.cin_range is not None:
                 kk = kk * 4 // 9          # phase N tiles issue their 2 x 2 taps only (the reference formulation: 9 taps)
             if op.gather:

@@ -149,6 +149,11 @@ class WeightPack:
                 cout_ = w.shape[0]
                 w = w.reshape(cout_, cin_ // 64, 64, k_, k_).permute(0, 1, 3, 4, 2).reshape(cout_, -1, 1, 1).contiguous()
             if op.kind == 'conv' and op.im2col is not None:   # [cout, cin, k, k] -> [cout, (r*k+s)*cin + c] padded
+                if getattr(op, 'embed1x1', False):             # 1x1 on the raw input: the centre tap of the k x k matrix
+                    k_ = op.im2col[0]
+                    w1 = w
+                    w = torch.zeros(w1.shape[0], w1.shape[1], k_, k_, dtype=w1.dtype)
+                    w[:, :, k_ // 2, k_ // 2] = w1[:, :, 0, 0]
                 cout_ = w.shape[0]
                 wk = w.permute(0, 2, 3, 1).reshape(cout_, -1)
                 w = torch.zeros(cout_, op.src.c, 1, 1, dtype=w.dtype)

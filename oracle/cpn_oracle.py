@@ -53,7 +53,9 @@ RESNETS = {
 }
 ARCHS = {'CpnU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0'),
          # models/cpn.py:890-929 / unet.py:497-524: U22 with doubled channel widths (the widths are read off the state_dict)
-         'CpnWideU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0')}
+         'CpnWideU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0'),
+         # models/cpn.py:811-849 / unet.py:434-464: U-Net of ResBlocks (the block type is read off the state_dict keys)
+         'CpnResUNet': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0')}
 for _e in RESNETS:                       # models/cpn.py:930-1637 (the reference has no CpnWideResNet*UNet)
     ARCHS[f'Cpn{_e}FPN'] = dict(decoder='fpn', encoder=_e, head_key='1', ref_key='0')
     if not _e.startswith('Wide'):
@@ -86,15 +88,31 @@ def two_conv_norm_relu(x, sd, p):
     return x
 
 
+def res_block(x, sd, p):
+    """models/commons.py:259-359 ``ResBlock``: act(block(x) + downsample(x)); downsample = ConvNorm 1x1 (bias=False) when the
+    widths differ, block = conv3x3, BN, ReLU, conv3x3, BN (both convolutions without bias)."""
+    idt = x
+    if f'{p}.downsample.0.weight' in sd:
+        idt = _bn(_conv(x, sd, f'{p}.downsample.0'), sd, f'{p}.downsample.1')
+    out = F.relu(_bn(_conv(x, sd, f'{p}.block.0', padding=1), sd, f'{p}.block.1'))
+    out = _bn(_conv(out, sd, f'{p}.block.3', padding=1), sd, f'{p}.block.4')
+    return F.relu(out + idt)
+
+
+def unet_block(x, sd, p):
+    """The U-Net's ``block_cls`` at prefix ``p``: ResBlock (ResUNet, unet.py:455-463) or TwoConvNormRelu."""
+    return res_block(x, sd, p) if f'{p}.block.0.weight' in sd else two_conv_norm_relu(x, sd, p)
+
+
 def unet_encoder(x, sd, p, depth=5):
     """models/unet.py:29-58: level 0 is the bare block, levels > 0 are Sequential(MaxPool(2, 2), block)."""
     feats = OrderedDict()
     for i in range(depth):
         if i == 0:
-            x = two_conv_norm_relu(x, sd, f'{p}.0')
+            x = unet_block(x, sd, f'{p}.0')
         else:
             x = F.max_pool2d(x, 2, 2)
-            x = two_conv_norm_relu(x, sd, f'{p}.{i}.1')
+            x = unet_block(x, sd, f'{p}.{i}.1')
         feats[str(i)] = x
     return feats
 
@@ -155,7 +173,7 @@ def unet_decoder(feats, sd, p, bridges, size):
         if f'{p}.inner_blocks.{i}.weight' in sd:  # otherwise nn.Identity (unet.py:121-128)
             top = _conv(top, sd, f'{p}.inner_blocks.{i}')
         inp = torch.cat((lateral, top), 1) if lateral is not None else top  # cat_order 0 (unet.py:219-224)
-        last_inner = two_conv_norm_relu(inp, sd, f'{p}.layer_blocks.{i}')
+        last_inner = unet_block(inp, sd, f'{p}.layer_blocks.{i}')
         results.insert(0, last_inner)
     final = F.interpolate(last_inner, size=size, mode='bilinear', align_corners=False)  # unet.py:237
     results.insert(0, final)
