@@ -85,6 +85,8 @@ SYMBOLS = {
     'cpn_resolve_label_channels_workspace_bytes': (_SZ, [_I, _I]),
     'cpn_resolve_label_channels': (_I, [_P, _I, _I, _I, _I, _P, _P, ctypes.POINTER(_I), _P]),
     'cpn_gather_rows': (_I, [_P, _I64, _P, _I64, _P, _P]),
+    'cpn_unshuffle2': (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    'cpn_copy_window': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'cpn_label_props': (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     'cpn_histogram': (_I, [_P, _I, _I64, _P, _P]),
     'cpn_apply_lut': (_I, [_P, _I, _I64, _P, _P, _P]),

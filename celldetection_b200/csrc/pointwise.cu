@@ -1109,3 +1109,87 @@ extern "C" int cpn_rgb2gray(const void* src, int dtype, int64_t n_px, int channe
   CPN_CHECK_LAUNCH();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Helpers of the phase-decomposed refinement head (bilinear x2 followed by a k x k convolution evaluated as four phase
+// convolutions on the low-resolution map, models/cpn.py:274-279): the phase-packed records [N, h, w, 4 * c] are shuffled
+// into the full-resolution map [N, 2h, 2w, c], and the image-border strips -- where bilinear clamping and the
+// convolution's zero padding make the phase identity inexact -- are cropped, recomputed by the plain path on small tensors
+// and pasted back.  Byte movers, HBM-bound.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace cpn {
+__global__ void __launch_bounds__(256) copy_window_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N,
+                                                          int Hs, int Ws, int Hd, int Wd, int vec_per_px, int ys, int xs,
+                                                          int yd, int xd, int hh, int ww) {
+  const long long total = (long long)N * hh * ww * vec_per_px;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec_per_px);
+    long long t = i / vec_per_px;
+    const int x = (int)(t % ww); t /= ww;
+    const int y = (int)(t % hh);
+    const int n = (int)(t / hh);
+    dst[(((long long)n * Hd + yd + y) * Wd + xd + x) * vec_per_px + v] =
+        __ldg(src + (((long long)n * Hs + ys + y) * Ws + xs + x) * vec_per_px + v);
+  }
+}
+
+__global__ void __launch_bounds__(256) copy_window4_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int Hs,
+                                                           int Ws, int Hd, int Wd, int words_per_px, int ys, int xs, int yd,
+                                                           int xd, int hh, int ww) {
+  const long long total = (long long)N * hh * ww * words_per_px;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % words_per_px);
+    long long t = i / words_per_px;
+    const int x = (int)(t % ww); t /= ww;
+    const int y = (int)(t % hh);
+    const int n = (int)(t / hh);
+    dst[(((long long)n * Hd + yd + y) * Wd + xd + x) * words_per_px + v] =
+        __ldg(src + (((long long)n * Hs + ys + y) * Ws + xs + x) * words_per_px + v);
+  }
+}
+
+// rec [N, h, w, 4 * c] (phase (a, b) at channels (2a + b) * c ...) -> out [N, 2h, 2w, c]: out[n, 2y + a, 2x + b, :]
+__global__ void __launch_bounds__(256) unshuffle2_kernel(const float* __restrict__ rec, float* __restrict__ out, int N, int h,
+                                                         int w, int c) {
+  const long long total = (long long)N * h * w * 4 * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    long long t = i / c;
+    const int ph = (int)(t & 3); t >>= 2;
+    const int x = (int)(t % w); t /= w;
+    const int y = (int)(t % h);
+    const int n = (int)(t / h);
+    out[(((long long)n * 2 * h + 2 * y + (ph >> 1)) * 2 * w + 2 * x + (ph & 1)) * c + ch] = __ldg(rec + i);
+  }
+}
+}  // namespace cpn
+
+extern "C" int cpn_copy_window(const void* src, void* dst, int N, int Hs, int Ws, int Hd, int Wd, int bytes_per_px, int ys,
+                               int xs, int yd, int xd, int hh, int ww, void* stream) {
+  using namespace cpn;
+  CPN_REQUIRE(src && dst && N >= 0 && hh >= 0 && ww >= 0 && bytes_per_px > 0 && bytes_per_px % 4 == 0, "copy_window: bad arguments");
+  CPN_REQUIRE(ys >= 0 && xs >= 0 && yd >= 0 && xd >= 0 && ys + hh <= Hs && xs + ww <= Ws && yd + hh <= Hd && xd + ww <= Wd,
+              "copy_window: window outside the source or the destination");
+  const long long px = (long long)N * hh * ww;
+  if (px == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bytes_per_px % 16 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) {
+    copy_window_kernel<<<grid_for(px * (bytes_per_px / 16), 256), 256, 0, st>>>((const uint4*)src, (uint4*)dst, N, Hs, Ws, Hd, Wd,
+                                                                             bytes_per_px / 16, ys, xs, yd, xd, hh, ww);
+  } else {
+    copy_window4_kernel<<<grid_for(px * (bytes_per_px / 4), 256), 256, 0, st>>>((const float*)src, (float*)dst, N, Hs, Ws, Hd, Wd,
+                                                                             bytes_per_px / 4, ys, xs, yd, xd, hh, ww);
+  }
+  CPN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cpn_unshuffle2(const float* rec, int N, int h, int w, int c, float* out, void* stream) {
+  using namespace cpn;
+  CPN_REQUIRE(rec && out && N >= 0 && h >= 0 && w >= 0 && c >= 1, "unshuffle2: bad arguments");
+  const long long total = (long long)N * h * w * 4 * c;
+  if (total == 0) return 0;
+  unshuffle2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(rec, out, N, h, w, c);
+  CPN_CHECK_LAUNCH();
+  return 0;
+}

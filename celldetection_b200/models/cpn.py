@@ -22,7 +22,7 @@ from torch import Tensor
 
 from .. import _lib as L
 from ..ops import cpn as O
-from .graph import trace, trace_sparse_heads, ARCHS, HEAD_KERNEL_KEYS
+from .graph import trace, trace_sparse_heads, trace_ring_strip, ARCHS, HEAD_KERNEL_KEYS
 from .plan import Plan, WeightPack, SPLIT_NONE, SPLIT_X3, SPLIT_F8
 
 
@@ -144,6 +144,10 @@ class CPN(nn.Module):
         # models/cpn.py:253-263, and reads them at the selected pixels only, :620-623): same outputs, ~2/3 of the head
         # convolution's work gone.  ``core_forward`` (raw head tensors) always runs the dense plan.
         self.sparse_heads = True
+        # Refinement head on bilinearly x2 up-sampled features (the FPN models, models/cpn.py:274-279) as four phase
+        # convolutions on the low-res features (25 instead of 49 taps per output, no full-resolution feature tensor); the
+        # 4-pixel image border is recomputed by the plain path on two strips (see ``_assemble_refinement``).
+        self.phase_refinement = os.environ.get('CPN_REF_PHASE', '1') != '0'
         self.cuda_graph = False     # True: replay the backbone + heads as one CUDA graph (static buffers; see Plan.forward_graph)
         self.hparams = dict(in_channels=in_channels, order=order, nms_thresh=nms_thresh, score_thresh=score_thresh,
                             samples=samples, classes=classes, refinement=refinement,
@@ -279,6 +283,58 @@ class CPN(nn.Module):
         self.last_sparse_rows = sum(c[2] for c in chunks)
         return rec
 
+    def _strip_plan(self, n, hs, ws, ref) -> Plan:
+        """Plan of the refinement head on a cropped [n, hs, ws] strip of the low-res features (graph.trace_ring_strip)."""
+        key = ('ring', n, hs, ws, self.precision)
+        plan = self._sparse_plans.get(key)
+        if plan is None:
+            g = trace_ring_strip(n, hs, ws, ref['c'], ref['mid'], ref['c2'], ref['margin'], ref['k'])
+            pk = ('ring', self.precision)
+            pack = self._packs.get(pk)
+            if pack is None:            # both strip orientations have the same op list: one packed copy of the head
+                with torch.no_grad():
+                    pack = WeightPack(g, self.state_dict(), True, self.device, split=_SPLIT[self.precision])
+                self._packs[pk] = pack
+            plan = Plan(g, pack, True, self.device, split=_SPLIT[self.precision])
+            self._sparse_plans[key] = plan
+        return plan
+
+    def _assemble_refinement(self, plan: Plan, rec: Tensor, n, h, w) -> Tensor:
+        """Full-resolution refinement tensor [n, h, w, 2B] of a ``phase_refinement`` plan: the phase-packed records are
+        shuffled to full resolution; the image border (4 pixels), where bilinear clamping and the convolution's zero padding
+        break the phase identity, is recomputed by the plain path on two strips of the low-res features -- (top 4 rows |
+        bottom 4 rows) and (left 4 columns | right 4 columns); the seam inside a strip only touches outputs that are not
+        used -- and pasted over it."""
+        lib = L.load()
+        ref = plan.g.ref_phase
+        feat = ref['feat']
+        hl, wl, c2 = int(feat.h), int(feat.w), int(ref['c2'])
+        st = L.stream_ptr()
+        out = torch.empty((n, h, w, c2), dtype=torch.float32, device=rec.device)
+        L.check(lib.cpn_unshuffle2(L.ptr(rec), n, hl, wl, c2, L.ptr(out), st), 'unshuffle2')
+        sv = plan.view_of(feat)
+        px_bytes = int(sv.pitch) * int(plan.views['es'])
+        src = ctypes.c_void_p(plan.arena.data_ptr() + int(sv.offset))
+        m, sl = 4, 4                    # border width in output pixels (k//2 + 1), low-res rows / columns per side
+        for rows, hs, ws in ((True, 2 * sl, wl), (False, hl, 2 * sl)):   # (top | bottom) rows, (left | right) columns
+            sp = self._strip_plan(n, hs, ws, ref)
+            dv = sp.view_of(sp.g.input_tensor)
+            assert int(dv.pitch) * int(sp.views['es']) == px_bytes
+            dst = ctypes.c_void_p(sp.arena.data_ptr() + int(dv.offset))
+            for part in range(2):       # crop the two sides into the strip's input
+                ys, xs = ((0 if part == 0 else hl - sl), 0) if rows else (0, (0 if part == 0 else wl - sl))
+                yd, xd = (part * sl, 0) if rows else (0, part * sl)
+                L.check(lib.cpn_copy_window(src, dst, n, hl, wl, hs, ws, px_bytes, ys, xs, yd, xd,
+                                            sl if rows else hl, wl if rows else sl, st), 'copy_window')
+            strip = sp.forward(None, L.IN_F32_NCHW)[0]              # [n, 2 hs, 2 ws, c2]
+            for part in range(2):       # paste the m valid output rows / columns of each side
+                if rows:
+                    args = (2 * hs, 2 * ws, h, w, c2 * 4, (0 if part == 0 else 2 * hs - m), 0, (0 if part == 0 else h - m), 0, m, w)
+                else:
+                    args = (2 * hs, 2 * ws, h, w, c2 * 4, 0, (0 if part == 0 else 2 * ws - m), 0, (0 if part == 0 else w - m), h, m)
+                L.check(lib.cpn_copy_window(L.ptr(strip), L.ptr(out), n, *args, st), 'copy_window')
+        return out
+
     def _plan(self, n, h, w, dense=False) -> Plan:
         dev = self.device
         if dev.type != 'cuda':
@@ -287,14 +343,15 @@ class CPN(nn.Module):
         fast = self.precision in _SPLIT
         split = _SPLIT.get(self.precision, SPLIT_NONE)
         sparse = bool(self.sparse_heads) and fast and not dense
-        key = (n, h, w, self.precision, sparse)
+        phase = bool(self.phase_refinement) and fast
+        key = (n, h, w, self.precision, sparse, phase)
         plan = self._plans.get(key)
         if plan is None:
             g = trace(self.arch, n, h, w, in_channels=self.in_channels, order=self.core_order,
                       refinement_margin=self.refinement_margin, stem_im2col=fast,
                       fuse_up2=fast and os.environ.get('CPN_UP2', '1') != '0', sparse_heads=sparse,
-                      **self._variant())
-            pk = (self.precision, bool(g.sparse))
+                      phase_refinement=phase, **self._variant())
+            pk = (self.precision, bool(g.sparse), g.ref_phase is not None)
             pack = self._packs.get(pk)
             if pack is None:
                 with torch.no_grad():
@@ -469,6 +526,8 @@ class CPN(nn.Module):
         plan.flags.zero_()
 
         def full_res(rf):
+            if getattr(plan.g, 'ref_phase', None):
+                return self._assemble_refinement(plan, rf, n, h, w)
             if tuple(rf.shape[1:3]) == (h, w):
                 return rf
             # strided / low-res refinement head: _equal_size to the input (cpn.py:279)

@@ -108,6 +108,9 @@ class LOp:
     up2: bool = False                          # 3x3 conv on the 2x nearest-up-sampled src, computed from the low-res src
     gather: Optional[Tuple[int, int]] = None   # (k, cin): 1x1 conv over rows written by cpn_gather_patches, i.e. the
                                                # k x k convolution evaluated at selected pixels only
+    bilin2: Optional[int] = None               # k: this (k//2 + 2 | 1)-tap convolution on the low-res src with 4 x the output
+                                               # channels IS conv_kxk(interpolate(src, x2, bilinear)), phase-major columns
+                                               # (plan.bilinear2_weights); exact outside an output border of k//2 + 1 pixels
     embed1x1: bool = False                     # a 1x1 convolution of the raw input that reads the SAME im2col matrix as the
                                                # k x k stem convolution: its weights sit at the centre tap's K positions
 
@@ -503,7 +506,7 @@ HEAD_KERNEL_KEYS = ('score', 'location', 'fourier', 'uncertainty', 'refinement')
 def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_margin=3., refinement_buckets=1,
           uncertainty_head=False, stem_im2col=False, kernel_sizes=None, contour_head_channels=None,
           refinement_head_channels=None, contour_head_stride=1, refinement_head_stride=1, refinement_full_res=True,
-          fpn_channels=256, fuse_up2=False, sparse_heads=False):
+          fpn_channels=256, fuse_up2=False, sparse_heads=False, phase_refinement=False):
     """Trace architecture `arch` for an [n, in_channels, h, w] input.  Returns the Tracer; ``g.outputs`` maps
     'scores' / 'locfou' / 'refinement' (/ 'uncertainty') to fp32 output tensors (bindings 0 / 1 / 2 (/ 3)).
 
@@ -519,7 +522,14 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
     ``sparse_heads``: the location and fourier heads are NOT part of this plan -- they are only read at proposals
     (cpn.py:620-623) and are evaluated there by ``trace_sparse_heads`` after the selection; the head feature map stays
     alive until the end of the plan (``g.head_feat``) and ``g.outputs`` has no 'locfou'.  ``g.sparse`` tells whether the
-    option could be applied (stride-1 contour heads, equal location / fourier kernel sizes)."""
+    option could be applied (stride-1 contour heads, equal location / fourier kernel sizes).
+
+    ``phase_refinement``: when the refinement features are up-sampled x2 to the input size before a 7x7 head (:274-279; the
+    FPN models), the bilinear op and the 7x7 convolution at full resolution are replaced by ONE 5x5 convolution on the
+    low-res features with 4 x the mid channels (the four output phases; 25 instead of 49 taps per output, no full-res
+    feature tensor) and the fused projection per phase.  'refinement' is then the phase-packed record map [n, h/2, w/2,
+    4 * 2B] (``g.ref_phase``); the caller shuffles it to full resolution and recomputes the 4-pixel image border, where the
+    identity does not hold, with ``trace_ring_strip`` plans on cropped features (kept alive: ``g.ref_phase['feat']``)."""
     assert arch in ARCHS, arch
     assert score_channels >= 1 and refinement_buckets >= 1
     ks = dict.fromkeys(HEAD_KERNEL_KEYS, 7)
@@ -583,16 +593,31 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
         for j, ((hp, co, act, _), dst) in enumerate(grp):
             pp = ConvParams([f'{hp}.block.4.weight'], [f'{hp}.block.4.bias'], [None])
             g.proj(mid, dst, j * head_mid, head_mid, pp, act=act, name=f'{hp}.block.4')
-    if refinement_full_res and (ref_feat.h, ref_feat.w) != (h, w):       # refinement_full_res (cpn.py:277-278)
-        ref_feat = g.bilinear(ref_feat, h, w)
+    c2 = 2 * refinement_buckets
     pr = ConvParams(['core.refinement_head.block.0.weight'], ['core.refinement_head.block.0.bias'],
                     ['core.refinement_head.block.1'])
-    rmid = g.conv(ref_feat, ref_mid, int(ks['refinement']), stride=int(refinement_head_stride), act='relu', params=pr,
-                  name='core.refinement_head.block.0')
-    refinement = g.tensor(2 * refinement_buckets, rmid.h, rmid.w, f32=True, binding=2)
     pp = ConvParams(['core.refinement_head.block.4.weight'], ['core.refinement_head.block.4.bias'], [None])
-    g.proj(rmid, refinement, 0, ref_mid, pp, act='scaled_tanh', act_scale=float(refinement_margin),
-           name='core.refinement_head.block.4')
+    g.ref_phase = None
+    if (phase_refinement and refinement_full_res and (2 * ref_feat.h, 2 * ref_feat.w) == (h, w) and
+            int(ks['refinement']) == 7 and int(refinement_head_stride) == 1 and ref_mid % 256 == 0 and ref_c % 64 == 0 and
+            ref_feat.parent is None and ref_feat.h >= 8 and ref_feat.w >= 8):
+        rmid = g._emit(LOp('conv', src=ref_feat, dst=g.tensor(4 * ref_mid, ref_feat.h, ref_feat.w), k=5, stride=1, pad=2,
+                           act='relu', params=pr, name='core.refinement_head.block.0', bilin2=7))
+        refinement = g.tensor(4 * c2, rmid.h, rmid.w, f32=True, binding=2)
+        for ph in range(4):
+            dst = g.tensor(c2, rmid.h, rmid.w, f32=True, parent=refinement, c_off=ph * c2, binding=2)
+            g.proj(rmid, dst, ph * ref_mid, ref_mid, pp, act='scaled_tanh', act_scale=float(refinement_margin),
+                   name=f'core.refinement_head.block.4.phase{ph}')
+        ref_feat.last = 1 << 29            # cropped into the border-strip plans after the plan
+        g.ref_phase = dict(feat=ref_feat, c=ref_c, mid=ref_mid, k=7, c2=c2, margin=float(refinement_margin))
+    else:
+        if refinement_full_res and (ref_feat.h, ref_feat.w) != (h, w):       # refinement_full_res (cpn.py:277-278)
+            ref_feat = g.bilinear(ref_feat, h, w)
+        rmid = g.conv(ref_feat, ref_mid, int(ks['refinement']), stride=int(refinement_head_stride), act='relu', params=pr,
+                      name='core.refinement_head.block.0')
+        refinement = g.tensor(c2, rmid.h, rmid.w, f32=True, binding=2)
+        g.proj(rmid, refinement, 0, ref_mid, pp, act='scaled_tanh', act_scale=float(refinement_margin),
+               name='core.refinement_head.block.4')
     g.outputs = OrderedDict(scores=scores, locfou=locfou, refinement=refinement)
     if g.sparse:
         del g.outputs['locfou']
@@ -607,6 +632,26 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
         head_ops = [o.name for o in g.ops if o.name.startswith('heads.block.0') or
                     o.name in ('core.score_head.block.4', 'core.uncertainty_head.block.4')]
         g.split_index = g.move_ops(head_ops, head_feat)
+    g.finalize()
+    return g
+
+
+def trace_ring_strip(n, hs, ws, ref_c, ref_mid, c2, margin, k=7):
+    """The refinement ReadOut on a cropped strip of the low-res refinement features, by the plain path (bilinear x2, k x k
+    convolution, projection; models/cpn.py:274-279): recomputes the image border of a ``phase_refinement`` plan.  External
+    input [n, hs, ws, ref_c] -> 'refinement' [n, 2 hs, 2 ws, c2]."""
+    g = Tracer(n, hs, ws)
+    a = g.external(ref_c, hs, ws)
+    u = g.bilinear(a, 2 * hs, 2 * ws)
+    pr = ConvParams(['core.refinement_head.block.0.weight'], ['core.refinement_head.block.0.bias'],
+                    ['core.refinement_head.block.1'])
+    rmid = g.conv(u, ref_mid, k, act='relu', params=pr, name='core.refinement_head.block.0')
+    out = g.tensor(c2, 2 * hs, 2 * ws, f32=True, binding=0)
+    pp = ConvParams(['core.refinement_head.block.4.weight'], ['core.refinement_head.block.4.bias'], [None])
+    g.proj(rmid, out, 0, ref_mid, pp, act='scaled_tanh', act_scale=float(margin), name='core.refinement_head.block.4')
+    g.outputs = OrderedDict(refinement=out)
+    g.input_tensor = a
+    g.head_hw = g.ref_hw = (2 * hs, 2 * ws)
     g.finalize()
     return g
 
@@ -646,6 +691,8 @@ def conv_flops(g: Tracer):
             kk = op.im2col[0] ** 2 * op.im2col[1] if op.im2col else (op.src.c // op.params.groups) * op.k * op.k
             if op.embed1x1:
                 kk = op.im2col[1]
+            if op.bilin2:                 # counted in the reference formulation: k x k taps at the full resolution
+                kk = op.src.c * op.bilin2 ** 2
             if op.up2 and op.params.cin_range is not None:
                 kk = kk * 4 // 9          # phase N tiles issue their 2 x 2 taps only (the reference formulation: 9 taps)
             if op.gather:

@@ -92,6 +92,43 @@ def up2_weights(w, b):
     return out.reshape(4 * cout, cin, 3, 3), b.repeat(4)
 
 
+def bilinear2_phase_matrix(k, phase):
+    """1-D composition of ``F.interpolate(scale_factor=2, mode='bilinear', align_corners=False)`` with a k-tap correlation:
+    ``A[r, d]`` such that ``sum_r W[r] U[2i + phase + r - k//2] = sum_d (W @ A)[d] L[i + d - D]`` for every output whose taps
+    stay inside the image, with ``U[2m] = .25 L[m-1] + .75 L[m]``, ``U[2m+1] = .75 L[m] + .25 L[m+1]`` and ``D`` the low-res
+    reach (2 for k = 7).  Returns (A [k, 2D + 1] float64, D)."""
+    pad = k // 2
+    D = (pad + 2) // 2
+    A = torch.zeros(k, 2 * D + 1, dtype=torch.float64)
+    for r in range(k):
+        q = phase + r - pad
+        m, odd = q // 2, q % 2                     # floor division: U row 2 (i + m) + odd
+        if odd:
+            A[r, m + D] += .75
+            A[r, m + 1 + D] += .25
+        else:
+            A[r, m - 1 + D] += .25
+            A[r, m + D] += .75
+    return A, D
+
+
+def bilinear2_weights(w, b):
+    """``conv_kxk(pad k//2)(interpolate(x, x2, bilinear))`` as ONE (2D+1) x (2D+1) convolution on the low-res map with
+    4 * cout output channels, phase (a, b') major (models/cpn.py:274-279 + the ReadOut's first convolution): ``w`` [cout, cin,
+    k, k], ``b`` [cout] -> ([4 * cout, cin, 2D+1, 2D+1], [4 * cout]).  Exact wherever no tap of the k x k window touches the
+    first / last row or column of the up-sampled image or its zero padding, i.e. outside a border of k//2 + 1 output
+    pixels; the caller recomputes that border."""
+    cout, cin, k, _ = w.shape
+    w64 = w.double()
+    outs = []
+    for a in range(2):
+        Ay, D = bilinear2_phase_matrix(k, a)
+        for bb in range(2):
+            Ax, _ = bilinear2_phase_matrix(k, bb)
+            outs.append(torch.einsum('ocrs,rd,se->ocde', w64, Ay, Ax))
+    return torch.cat(outs, 0).to(w.dtype).contiguous(), b.repeat(4)
+
+
 def engine_for(op: LOp, fast, cin):
     if not fast:
         return L.ENGINE_SIMT
@@ -144,6 +181,8 @@ class WeightPack:
             w, b = fold_conv(sd, op.params)
             if op.kind == 'conv' and getattr(op, 'up2', False):
                 w, b = up2_weights(w, b)
+            if op.kind == 'conv' and getattr(op, 'bilin2', None):     # phase convolution of a bilinearly up-sampled input
+                w, b = bilinear2_weights(w, b)
             if op.kind == 'conv' and getattr(op, 'gather', None):     # k x k conv as a 1x1 over gathered patches:
                 k_, cin_ = op.gather                                   # K order [cin/64 blocks][k*k taps][64 channels]
                 cout_ = w.shape[0]

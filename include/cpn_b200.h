@@ -349,6 +349,16 @@ int cpn_apply_lut(const void* src, int dtype, int64_t n, const uint8_t* lut, uin
  * need `lut`), each element first mapped through `lut` when given (nullable), dst [n_px] uint8. */
 int cpn_rgb2gray(const void* src, int dtype, int64_t n_px, int channels, const uint8_t* lut, uint8_t* dst, void* stream);
 
+/* Phase-decomposed refinement head (models/cpn.py:274-279: F.interpolate(x2, bilinear) followed by the ReadOut's k x k
+ * convolution, run as four phase convolutions on the low-resolution map).  cpn_unshuffle2: phase-packed records
+ * rec [N, h, w, 4 * c] (phase (a, b) at channels (2a + b) * c ...) -> out [N, 2h, 2w, c] with out[n, 2y + a, 2x + b] = that
+ * phase's record.  cpn_copy_window: copies the hh x ww pixel window at (ys, xs) of every image of src [N, Hs, Ws] to
+ * (yd, xd) of dst [N, Hd, Wd]; pixels are bytes_per_px bytes (multiple of 4) in both -- crops the border strips of a
+ * feature map into the small tensors the plain path recomputes them on, and pastes their results back. */
+int cpn_unshuffle2(const float* rec, int N, int h, int w, int c, float* out, void* stream);
+int cpn_copy_window(const void* src, void* dst, int N, int Hs, int Ws, int Hd, int Wd, int bytes_per_px, int ys, int xs,
+                    int yd, int xd, int hh, int ww, void* stream);
+
 /* dst[i, :] = src[index[i], :] for rows of row_bytes (multiple of 4) bytes (resolve_keep_indices, cpn.py:53-60). */
 int cpn_gather_rows(const void* src, int64_t row_bytes, const int32_t* index, int64_t n_rows, void* dst, void* stream);
 

@@ -221,6 +221,45 @@ def test_apply_model_preprocesses_like_the_reference_chain():
     assert total > 0
 
 
+@pytest.mark.parametrize('hw', [(128, 128), (96, 160), (16, 16), (512, 512)])
+def test_phase_refinement_head_equals_plain_path(hw):
+    """bilinear x2 o 7x7 as four 5x5 phase convolutions on the low-res map (+ border strips by the plain path) against the
+    plain path of the same engine: the border ring is the same arithmetic (bit-identical), the interior differs only by the
+    rounding of the composed weights; both sit inside the gate against the oracle (test_ragged_input_sizes_against_oracle,
+    the FPN fixtures)."""
+    from helpers import key_spec
+    from celldetection_b200.utils.synth import synth_state_dict
+    arch = 'CpnResNet18FPN'
+    sd = synth_state_dict(key_spec(arch), seed=21)
+    torch.manual_seed(3)
+    h, w = hw
+    x = torch.rand(2, 3, h, w).cuda()
+    for prec, tol in (('fp16f8', 2e-4), ('fp16', 4e-3)):
+        m = getattr(cd.models, arch)(3, precision=prec)
+        m.load_state_dict(sd)
+        m = m.cuda()
+        assert m.phase_refinement
+        a = m.core_forward(x)['refinement']
+        assert m._plan(2, h, w, dense=True).g.ref_phase is not None
+        m.phase_refinement = False
+        b = m.core_forward(x)['refinement']
+        assert m._plan(2, h, w, dense=True).g.ref_phase is None
+        assert a.shape == b.shape == (2, 2, h, w)
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) / scale < tol, (prec, float((a - b).abs().max()) / scale)
+        ring = torch.ones((h, w), dtype=torch.bool, device='cuda')
+        ring[4:-4, 4:-4] = False
+        assert torch.equal(a[..., ring], b[..., ring]), prec        # recomputed border == plain path, bit for bit
+        for k in ('scores', 'locations', 'fourier'):
+            pass
+    # the decoded results agree as well (refinement only moves vertices by rounded offsets)
+    m.phase_refinement = True
+    out_a = m(x)
+    m.phase_refinement = False
+    out_b = m(x)
+    assert [len(v) for v in out_a['scores']] == [len(v) for v in out_b['scores']]
+
+
 def test_full_size_c3_properties():
     """BASELINE config C3 (CpnResNeXt101UNet, 3x512x512 tiles): size-independent properties at full tile size --
     batch invariance (tile i of a batch == the same tile alone, bit for bit) and fp16-vs-fp32 engine agreement."""
