@@ -430,7 +430,9 @@ def config_c2(dev, peaks):
     fl = conv_flops(m._plan(32, TILE, TILE).g)
     tf = fl / (ms / 1e3) / 1e12
     return dict(workload=f'{arch}, batch 32x3x{TILE}x{TILE}, {HEADLINE}', value=32 / (ms / 1e3), unit='tiles/s',
-                ms_per_step=ms, kept_last_step=kept, conv_tflops=tf, frac_of_sustained_peak=tf / peaks['tflops_sustained'])
+                ms_per_step=ms, kept_last_step=kept, conv_tflops=tf, frac_of_sustained_peak=tf / peaks['tflops_sustained'],
+                note='conv_tflops counts the reference formulation (7x7 refinement head on the bilinearly up-sampled 512^2 '
+                     'features); the plan runs that head as four 5x5 phase convolutions on the 256^2 features + border strips')
 
 
 def config_c5(dev, peaks):

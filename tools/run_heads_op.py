@@ -1,5 +1,5 @@
 """Runs single ops of the bench workload (CpnResNeXt101UNet, batch 16 x 3x512x512) inside a profiler range, for
-`ncu --profile-from-start off --set full`:  run_heads_op.py name[,name...] [precision]   (default: the dominant kernel,
+`ncu --profile-from-start off --set full`:  run_heads_op.py name[,name...] [precision] [arch] [batch]   (default: the dominant kernel,
 the merged 7x7 head convolution) or  run_heads_op.py post  (one whole post-head chain on calibrated heads)."""
 import os
 import sys
@@ -14,11 +14,13 @@ from celldetection_b200.utils.synth import synth_state_dict  # noqa: E402
 
 names = (sys.argv[1] if len(sys.argv) > 1 else 'heads.block.0').split(',')
 prec = sys.argv[2] if len(sys.argv) > 2 else 'fp16'
-m = cd.models.CpnResNeXt101UNet(3, precision=prec)
+arch = sys.argv[3] if len(sys.argv) > 3 else 'CpnResNeXt101UNet'
+batch = int(sys.argv[4]) if len(sys.argv) > 4 else 16
+m = getattr(cd.models, arch)(3, precision=prec)
 m.load_state_dict(synth_state_dict(m._spec, seed=0))
 m = m.cuda()
-x = torch.rand(16, 3, 512, 512, device='cuda')
-plan = m._plan(16, 512, 512)
+x = torch.rand(batch, 3, 512, 512, device='cuda')
+plan = m._plan(batch, 512, 512)
 outs = plan.new_outputs()
 plan.forward(x, L.IN_F32_NCHW, outs)
 if names == ['post']:
