@@ -598,7 +598,9 @@ def test_tiled_driver_flagship_2048_against_oracle(stride):
     _report(f'tiled_2048_s{stride}/counts', dict(oracle=k_ref, got=k))
     assert k_ref > 100 and abs(k - k_ref) <= 2, (k, k_ref)
     pairs = match_by_box(got['boxes'].cpu().numpy(), want['boxes'].numpy())
-    assert len(pairs) >= k_ref - 2
+    # boxes are matched on the REFINED contours: besides the instances that exist on one side only (the count difference
+    # above), a torch.round flip in the refinement loop may unmatch an instance (see __graft_entry__.smoke)
+    assert len(pairs) >= min(k, k_ref) - 2, (len(pairs), k, k_ref)
     gp, gc = got['contour_proposals'].cpu().numpy(), got['contours'].cpu().numpy()
     wp, wc = want['contour_proposals'].numpy(), want['contours'].numpy()
     perr = max(float(np.abs(gp[a] - wp[b]).max()) for a, b in pairs)
