@@ -382,3 +382,49 @@ def test_up2_phase_kernels_equal_upsample_then_conv():
     assert G.conv_flops(c) < G.conv_flops(a)
     ragged = G.trace('CpnResNeXt101UNet', 1, 90, 120, stem_im2col=True, fuse_up2=True)   # non-2x levels keep up-sample + cat
     assert any(o.kind == 'upsample' for o in ragged.ops)
+
+
+@pytest.mark.parametrize('k', [7, 5, 3])
+def test_bilinear2_phase_weights_equal_upsample_then_conv(k):
+    """``conv_kxk(interpolate(x, x2, bilinear))`` == the composed phase convolution on the low-res map (plan.bilinear2_weights)
+    outside an output border of k//2 + 1 pixels, and -- for the k = 7 head -- everywhere once the two merged border strips
+    ((top 4 | bottom 4) rows, (left 4 | right 4) columns of the low-res map) are recomputed by the plain path, which is what
+    models/cpn.py:_assemble_refinement does on the GPU (float64, exact to rounding)."""
+    torch.manual_seed(k)
+    L = torch.randn(2, 6, 13, 17, dtype=torch.float64)
+    w = torch.randn(5, 6, k, k, dtype=torch.float64)
+    b = torch.randn(5, dtype=torch.float64)
+    up = lambda t: F.interpolate(t, scale_factor=2, mode='bilinear', align_corners=False)      # noqa: E731
+    ref = F.conv2d(up(L), w, b, padding=k // 2)
+    wp, bp = PL.bilinear2_weights(w, b)
+    D = wp.shape[-1] // 2
+    assert wp.shape == (20, 6, 2 * D + 1, 2 * D + 1) and D == (k // 2 + 2) // 2
+    o = F.conv2d(L, wp, bp, padding=D).reshape(2, 2, 2, 5, 13, 17).permute(0, 3, 4, 1, 5, 2).reshape(2, 5, 26, 34)
+    m = k // 2 + 1
+    assert float((o - ref)[..., m:-m, m:-m].abs().max()) < 1e-12
+    assert float((o - ref).abs().max()) > 1e-3                      # the border really differs
+    if k == 7:
+        sl = 4
+        tb = F.conv2d(up(torch.cat((L[:, :, :sl], L[:, :, -sl:]), 2)), w, b, padding=3)
+        o[:, :, :m], o[:, :, -m:] = tb[:, :, :m], tb[:, :, -m:]
+        lr = F.conv2d(up(torch.cat((L[:, :, :, :sl], L[:, :, :, -sl:]), 3)), w, b, padding=3)
+        o[:, :, :, :m], o[:, :, :, -m:] = lr[:, :, :, :m], lr[:, :, :, -m:]
+        assert float((o - ref).abs().max()) < 1e-12
+
+
+def test_phase_refinement_trace_keeps_the_reference_flop_count_and_keys():
+    """The phase-decomposed refinement head changes ops, not parameters: same state_dict spec, same FLOPs in the reference
+    formulation, a 5x5 convolution with four fused projections in place of bilinear + 7x7 + projection."""
+    a = G.trace('CpnResNet18FPN', 2, 128, 128, stem_im2col=True, fuse_up2=True)
+    b = G.trace('CpnResNet18FPN', 2, 128, 128, stem_im2col=True, fuse_up2=True, phase_refinement=True)
+    assert list(a.spec.keys()) == list(b.spec.keys())
+    assert G.conv_flops(a) == G.conv_flops(b)
+    assert a.ref_phase is None and b.ref_phase is not None and b.ref_hw == (64, 64)
+    assert [o.kind for o in b.ops[-5:]] == ['conv', 'proj', 'proj', 'proj', 'proj'] and b.ops[-5].k == 5
+    assert not any(o.kind == 'bilinear' for o in b.ops) and any(o.kind == 'bilinear' for o in a.ops)
+    # not applicable: refinement features already at the input resolution (U-Net models), other kernel sizes
+    assert G.trace('CpnU22', 1, 64, 64, stem_im2col=True, phase_refinement=True).ref_phase is None
+    assert G.trace('CpnResNet18FPN', 1, 128, 128, stem_im2col=True, phase_refinement=True,
+                   kernel_sizes=dict(refinement=5)).ref_phase is None
+    s = G.trace_ring_strip(2, 8, 64, 256, 256, 2, 3.)
+    assert [o.kind for o in s.ops] == ['bilinear', 'conv', 'proj'] and s.ref_hw == (16, 128)
