@@ -40,14 +40,16 @@ ARCHS = ('CpnU22', 'CpnResNet18FPN', 'CpnResNeXt101UNet') + tuple(
     f'Cpn{e}{d}' for d in ('UNet', 'FPN') for e in RESNETS
     if not (d == 'UNet' and e.startswith('Wide')) and f'Cpn{e}{d}' not in ('CpnResNet18FPN', 'CpnResNeXt101UNet')) + (
     'CpnWideU22',       # models/cpn.py:890-929, unet.py:497-524: U22 with doubled widths (128 ... 2048)
-    'CpnResUNet')       # models/cpn.py:811-849, unet.py:434-464: U-Net whose encoder AND decoder blocks are ResBlocks
-# U-Net encoders of models/unet.py:405-524 by base width (CpnSlimU22's 32-channel layers are below the 64-wide MMA tile)
-U22_BASE = {'U22': 64, 'WideU22': 128}
+    'CpnResUNet',       # models/cpn.py:811-849, unet.py:434-464: U-Net whose encoder AND decoder blocks are ResBlocks
+    'CpnSlimU22')       # models/cpn.py:851-889, unet.py:467-494: U22 with halved widths (32 ... 512); its 32-channel layers run
+                        # zero-padded to the 64-wide tile (padded_conv)
+# U-Net encoders of models/unet.py:405-524 by base width
+U22_BASE = {'U22': 64, 'WideU22': 128, 'SlimU22': 32}
 
 
 def split_arch(arch):
     """'CpnResNet50FPN' -> ('ResNet50', 'FPN'); 'CpnU22' -> ('U22', 'UNet')."""
-    if arch in ('CpnU22', 'CpnWideU22', 'CpnResUNet'):
+    if arch in ('CpnU22', 'CpnWideU22', 'CpnResUNet', 'CpnSlimU22'):
         return arch[3:], 'UNet'
     for d in ('UNet', 'FPN'):
         if arch.endswith(d) and arch[3:-len(d)] in RESNETS:
@@ -68,6 +70,8 @@ class TT:
     binding: int = -1
     first: int = 1 << 30            # op index of first write
     last: int = -1                  # op index of last access
+    segs: Optional[list] = None     # [(real channels, padded channels), ...] when the tensor carries zero-padded channel
+                                    # blocks (widths that are not multiples of 64, CpnSlimU22); None = no padding
 
     def root(self):
         t, off = self, 0
@@ -86,6 +90,35 @@ class ConvParams:
     groups: int = 1
     cin_range: Optional[Tuple[int, int]] = None   # contract over this slice of the (folded) weight's input channels only
     no_bias: bool = False                         # the folded bias is applied by another op of the same convolution
+    pad_out: int = 0                              # > 0: zero rows / biases are appended up to this many output channels
+    cin_segs: Optional[list] = None               # [(real, padded), ...]: the input tensor's channel blocks; the weight's input
+                                                  # channels are spread accordingly (zero columns at the padded positions)
+
+
+def channel_segs(t):
+    """[(real, padded), ...] channel blocks of tensor ``t`` (one unpadded block unless ``t.segs`` says otherwise)."""
+    return list(t.segs) if t.segs else [(t.c, t.c)]
+
+
+def pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def padded_conv(g, x, cout, k, params, **kw):
+    """``g.conv`` for layers whose real widths are not multiples of 64 (CpnSlimU22's 32-channel layers): the output gets
+    zero-padded channels up to the next multiple of 64 (zero weights and biases: exactly 0 after any activation used here) and
+    the weight's input channels are spread over the padded blocks of ``x``.  Widths that are multiples of 64 pass through
+    unchanged (same params object: the packed weights of every other architecture are bit-identical)."""
+    from dataclasses import replace
+    cp = pad64(cout)
+    segs = channel_segs(x)
+    spread = any(r != p for r, p in segs)
+    if cp != cout or spread:
+        params = replace(params, pad_out=cp if cp != cout else 0, cin_segs=segs if spread else None)
+    out = g.conv(x, cp, k, params=params, **kw)
+    if cp != cout:
+        out.segs = [(cout, cp)]
+    return out
 
 
 @dataclass
@@ -219,18 +252,20 @@ class Tracer:
 
     def maxpool(self, x, k, stride, pad):
         ho, wo = (x.h + 2 * pad - k) // stride + 1, (x.w + 2 * pad - k) // stride + 1
-        return self._emit(LOp('maxpool', src=x, dst=self.tensor(x.c, ho, wo), k=k, stride=stride, pad=pad))
+        return self._emit(LOp('maxpool', src=x, dst=self.tensor(x.c, ho, wo, segs=x.segs), k=k, stride=stride, pad=pad))
 
     def upsample(self, x, h, w):
-        return self._emit(LOp('upsample', src=x, dst=self.tensor(x.c, h, w)))
+        return self._emit(LOp('upsample', src=x, dst=self.tensor(x.c, h, w, segs=x.segs)))
 
     def bilinear(self, x, h, w):
-        return self._emit(LOp('bilinear', src=x, dst=self.tensor(x.c, h, w)))
+        return self._emit(LOp('bilinear', src=x, dst=self.tensor(x.c, h, w, segs=x.segs)))
 
     def cat(self, a, b):
         """Concatenate along channels by making `a` and `b` slices of one buffer (both must be unplaced)."""
         assert a.parent is None and b.parent is None and (a.h, a.w) == (b.h, b.w)
         t = self.tensor(a.c + b.c, a.h, a.w)
+        if a.segs or b.segs:
+            t.segs = channel_segs(a) + channel_segs(b)
         a.parent, a.c_off = t, 0
         b.parent, b.c_off = t, a.c
         t.first = min(a.first, b.first)
@@ -285,7 +320,16 @@ def _conv_bn_act(g: Tracer, x, key, bn_key, cin, cout, k, stride=1, bias=True, g
         g.bn_spec(bn_key, cout, res_branch)
     p = ConvParams([key + '.weight'], [key + '.bias' if bias else None], [bn_key], groups)
     if getattr(x, 'is_input', False) and res is None and groups == 1:
-        return g.stem_conv(x, cout, k, stride, act, p, key)
+        cp = pad64(cout)
+        if cp != cout:
+            from dataclasses import replace
+            p = replace(p, pad_out=cp)
+        out = g.stem_conv(x, cp, k, stride, act, p, key)
+        if cp != cout:
+            out.segs = [(cout, cp)]
+        return out
+    if groups == 1 and (cout % 64 or x.segs):
+        return padded_conv(g, x, cout, k, p, stride=stride, act=act, res=res, name=key)
     return g.conv(x, cout, k, stride=stride, act=act, res=res, params=p, name=key)
 
 
@@ -431,7 +475,7 @@ def _unet_decoder(g, feats, chans, p, bridges, block='two_conv'):
             inc, ouc = inner[i]
             assert inc == last_c
             pr = ConvParams([f'{p}.inner_blocks.{i}.weight'], [f'{p}.inner_blocks.{i}.bias'], [None])
-            top = g.conv(top, ouc, 1, act='none', params=pr, name=f'{p}.inner_blocks.{i}')
+            top = padded_conv(g, top, ouc, 1, pr, act='none', name=f'{p}.inner_blocks.{i}')
             last_c = ouc
         cin, ouc, bias = blocks[i]
         bp = f'{p}.layer_blocks.{i}'
@@ -466,9 +510,9 @@ def _unet_decoder(g, feats, chans, p, bridges, block='two_conv'):
             continue
         else:
             x = g.upsample(top, top.h * 2, top.w * 2)
-        assert x.c == cin, (x.c, cin)
-        x = g.conv(x, ouc, 3, act='relu', params=pa, name=f'{bp}.0')
-        x = g.conv(x, ouc, 3, act='relu', params=pb, name=f'{bp}.3')
+        assert sum(r for r, _ in channel_segs(x)) == cin, (channel_segs(x), cin)
+        x = padded_conv(g, x, ouc, 3, pa, act='relu', name=f'{bp}.0')
+        x = padded_conv(g, x, ouc, 3, pb, act='relu', name=f'{bp}.3')
         last, last_c = x, ouc
         results[i] = x
     return results, out_list
@@ -613,10 +657,13 @@ def trace(arch, n, h, w, in_channels=3, order=5, score_channels=1, refinement_ma
     else:
         if refinement_full_res and (ref_feat.h, ref_feat.w) != (h, w):       # refinement_full_res (cpn.py:277-278)
             ref_feat = g.bilinear(ref_feat, h, w)
-        rmid = g.conv(ref_feat, ref_mid, int(ks['refinement']), stride=int(refinement_head_stride), act='relu', params=pr,
-                      name='core.refinement_head.block.0')
+        rmid = padded_conv(g, ref_feat, ref_mid, int(ks['refinement']), pr, stride=int(refinement_head_stride), act='relu',
+                           name='core.refinement_head.block.0')
         refinement = g.tensor(c2, rmid.h, rmid.w, f32=True, binding=2)
-        g.proj(rmid, refinement, 0, ref_mid, pp, act='scaled_tanh', act_scale=float(refinement_margin),
+        if rmid.segs:                      # zero-padded mid channels: the projection reads them with zero weights
+            from dataclasses import replace
+            pp = replace(pp, cin_segs=rmid.segs)
+        g.proj(rmid, refinement, 0, rmid.c, pp, act='scaled_tanh', act_scale=float(refinement_margin),
                name='core.refinement_head.block.4')
     g.outputs = OrderedDict(scores=scores, locfou=locfou, refinement=refinement)
     if g.sparse:

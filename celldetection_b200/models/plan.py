@@ -47,6 +47,19 @@ def fold_conv(sd, params):
         w = w[:, params.cin_range[0]:params.cin_range[1]].contiguous()
     if getattr(params, 'no_bias', False):
         b = torch.zeros_like(b)
+    segs = getattr(params, 'cin_segs', None)
+    if segs:                                   # input tensor with zero-padded channel blocks: spread the weight's columns
+        assert sum(r for r, _ in segs) == w.shape[1], (segs, tuple(w.shape))
+        w2 = torch.zeros(w.shape[0], sum(p for _, p in segs), w.shape[2], w.shape[3], dtype=w.dtype, device=w.device)
+        rs = ps = 0
+        for r, p in segs:
+            w2[:, ps:ps + r] = w[:, rs:rs + r]
+            rs, ps = rs + r, ps + p
+        w = w2
+    pad_out = int(getattr(params, 'pad_out', 0) or 0)
+    if pad_out > w.shape[0]:                   # zero-padded output channels (zero rows, zero biases)
+        w = torch.cat((w, torch.zeros(pad_out - w.shape[0], *w.shape[1:], dtype=w.dtype, device=w.device)), 0)
+        b = torch.cat((b, torch.zeros(pad_out - b.shape[0], dtype=b.dtype, device=b.device)), 0)
     return w, b
 
 

@@ -55,7 +55,9 @@ ARCHS = {'CpnU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0
          # models/cpn.py:890-929 / unet.py:497-524: U22 with doubled channel widths (the widths are read off the state_dict)
          'CpnWideU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0'),
          # models/cpn.py:811-849 / unet.py:434-464: U-Net of ResBlocks (the block type is read off the state_dict keys)
-         'CpnResUNet': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0')}
+         'CpnResUNet': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0'),
+         # models/cpn.py:851-889 / unet.py:467-494: U22 with halved channel widths
+         'CpnSlimU22': dict(decoder='unet', encoder='unet', head_key='1', ref_key='0')}
 for _e in RESNETS:                       # models/cpn.py:930-1637 (the reference has no CpnWideResNet*UNet)
     ARCHS[f'Cpn{_e}FPN'] = dict(decoder='fpn', encoder=_e, head_key='1', ref_key='0')
     if not _e.startswith('Wide'):

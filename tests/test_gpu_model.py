@@ -335,7 +335,8 @@ def test_gate_passing_tensor_core_engines_meet_parity_gate(name, precision):
                                      ('CpnResNet152FPN', (64, 64)), ('CpnResNeXt50FPN', (96, 128)),
                                      ('CpnResNeXt101FPN', (64, 96)), ('CpnResNeXt152FPN', (64, 64)),
                                      ('CpnWideResNet50FPN', (96, 128)), ('CpnWideResNet101FPN', (64, 64)),
-                                     ('CpnWideU22', (80, 112)), ('CpnResUNet', (80, 112)), ('CpnResUNet', (128, 64))])
+                                     ('CpnWideU22', (80, 112)), ('CpnResUNet', (80, 112)), ('CpnResUNet', (128, 64)),
+                                     ('CpnSlimU22', (80, 112)), ('CpnSlimU22', (64, 64))])
 def test_ragged_input_sizes_against_oracle(arch, hw):
     """Sizes that are not multiples of the encoder stride: partial conv tiles, non-integer nearest up-sampling factors
     (floor(dst * in / out)), odd max-pool extents, bilinear resize for the FPN refinement features.  Checked directly

@@ -428,3 +428,82 @@ def test_phase_refinement_trace_keeps_the_reference_flop_count_and_keys():
                    kernel_sizes=dict(refinement=5)).ref_phase is None
     s = G.trace_ring_strip(2, 8, 64, 256, 256, 2, 3.)
     assert [o.kind for o in s.ops] == ['bilinear', 'conv', 'proj'] and s.ref_hw == (16, 128)
+
+
+def _interpret_trace(g, sd, x):
+    """CPU interpreter of a (non-fused) trace with torch ops on the FOLDED weights the packer would upload (plan.fold_conv):
+    validates the graph lowering -- op order, concatenation buffers, channel padding, BN folding, projections -- without a
+    GPU.  Returns {output key: NCHW tensor}."""
+    bufs = {}
+
+    def root_buf(t):
+        r, off = t.root()
+        if r.id not in bufs:
+            bufs[r.id] = torch.zeros(x.shape[0], r.c, r.h, r.w, dtype=torch.float64)
+        return bufs[r.id], off
+
+    def read(t):
+        b, off = root_buf(t)
+        return b[:, off:off + t.c]
+
+    def write(t, v):
+        b, off = root_buf(t)
+        assert tuple(v.shape[1:]) == (t.c, t.h, t.w), (tuple(v.shape), (t.c, t.h, t.w))
+        b[:, off:off + t.c] = v
+
+    acts = dict(none=lambda v, s: v, relu=lambda v, s: F.relu(v), sigmoid=lambda v, s: torch.sigmoid(v),
+                scaled_tanh=lambda v, s: torch.tanh(v) * s)
+    for op in g.ops:
+        if op.kind == 'prep':
+            write(op.dst, x.double())
+        elif op.kind == 'conv':
+            assert not op.up2 and not op.bilin2 and op.im2col is None and op.gather is None
+            w, b = PL.fold_conv(sd, op.params)
+            v = F.conv2d(read(op.src), w.double(), b.double(), stride=op.stride, padding=op.pad, groups=op.params.groups)
+            if op.res is not None:
+                r = read(op.res)
+                if tuple(r.shape[2:]) != tuple(v.shape[2:]):      # FPN top-down path: nearest up-sampling inside the residual add
+                    r = F.interpolate(r, size=v.shape[2:], mode='nearest')
+                v = v + r
+            write(op.dst, acts[op.act](v, op.act_scale))
+        elif op.kind == 'proj':
+            w, b = PL.fold_conv(sd, op.params)
+            v = F.conv2d(read(op.src)[:, op.cin_off:op.cin_off + op.cin], w.double(), b.double())
+            write(op.dst, acts[op.act](v, op.act_scale))
+        elif op.kind == 'maxpool':
+            write(op.dst, F.max_pool2d(read(op.src), op.k, op.stride, op.pad))
+        elif op.kind == 'upsample':
+            write(op.dst, F.interpolate(read(op.src), size=(op.dst.h, op.dst.w), mode='nearest'))
+        elif op.kind == 'bilinear':
+            write(op.dst, F.interpolate(read(op.src), size=(op.dst.h, op.dst.w), mode='bilinear', align_corners=False))
+        else:
+            raise AssertionError(op.kind)
+    return {k: read(t) for k, t in g.outputs.items()}
+
+
+@pytest.mark.parametrize('arch,hw', [('CpnSlimU22', (64, 80)), ('CpnU22', (48, 64)), ('CpnResUNet', (64, 64)),
+                                     ('CpnResNet18FPN', (64, 96)), ('CpnResNeXt50UNet', (64, 64))])
+def test_trace_interpreted_on_the_cpu_equals_the_oracle(arch, hw):
+    """The lowered graph + folded (and, for CpnSlimU22, zero-padded) weights reproduce the oracle's head tensors."""
+    import cpn_oracle as orc
+    from celldetection_b200.utils.synth import synth_state_dict
+    sd = synth_state_dict(key_spec(arch), seed=5)
+    torch.manual_seed(2)
+    h, w = hw
+    x = torch.rand(1, 3, h, w)
+    g = G.trace(arch, 1, h, w)
+    got = _interpret_trace(g, sd, x)
+    with torch.no_grad():
+        s, l, r, f = orc.cpn_core(x, sd, arch)
+    want = dict(scores=s, locations=l, fourier=f, refinement=r)
+    lf = got['locfou']
+    outs = dict(scores=got['scores'], locations=lf[:, :2], fourier=lf[:, 2:], refinement=got['refinement'])
+    for k, v in want.items():
+        a = outs[k].float()
+        if tuple(a.shape[2:]) != tuple(v.shape[2:]):          # strided / low-res refinement is resized by the caller
+            a = F.interpolate(a, size=v.shape[2:], mode='bilinear', align_corners=False)
+        assert tuple(a.shape) == tuple(v.shape), (k, a.shape, v.shape)
+        err = float((a - v).abs().max()) / max(float(v.abs().max()), 1e-12)
+        assert err < 3e-4, (arch, k, err)     # float64 interpreter vs the fp32 oracle; a lowering error is O(1)
+    if arch == 'CpnSlimU22':                                 # padded channel blocks stay exactly zero
+        assert any(op.params.pad_out for op in g.ops if op.kind == 'conv')
