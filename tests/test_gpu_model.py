@@ -250,8 +250,6 @@ def test_phase_refinement_head_equals_plain_path(hw):
         ring = torch.ones((h, w), dtype=torch.bool, device='cuda')
         ring[4:-4, 4:-4] = False
         assert torch.equal(a[..., ring], b[..., ring]), prec        # recomputed border == plain path, bit for bit
-        for k in ('scores', 'locations', 'fourier'):
-            pass
     # the decoded results agree as well (refinement only moves vertices by rounded offsets)
     m.phase_refinement = True
     out_a = m(x)

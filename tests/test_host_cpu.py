@@ -457,9 +457,16 @@ def _interpret_trace(g, sd, x):
         if op.kind == 'prep':
             write(op.dst, x.double())
         elif op.kind == 'conv':
-            assert not op.up2 and not op.bilin2 and op.im2col is None and op.gather is None
+            assert op.im2col is None and op.gather is None
             w, b = PL.fold_conv(sd, op.params)
-            v = F.conv2d(read(op.src), w.double(), b.double(), stride=op.stride, padding=op.pad, groups=op.params.groups)
+            if op.up2 or op.bilin2:        # phase convolutions on the low-res map: transformed weights, then pixel shuffle
+                w, b = PL.up2_weights(w, b) if op.up2 else PL.bilinear2_weights(w, b)
+                v = F.conv2d(read(op.src), w.double(), b.double(), padding=w.shape[-1] // 2)
+                if op.up2:
+                    n_, c4, hh, ww = v.shape
+                    v = v.reshape(n_, 2, 2, c4 // 4, hh, ww).permute(0, 3, 4, 1, 5, 2).reshape(n_, c4 // 4, 2 * hh, 2 * ww)
+            else:
+                v = F.conv2d(read(op.src), w.double(), b.double(), stride=op.stride, padding=op.pad, groups=op.params.groups)
             if op.res is not None:
                 r = read(op.res)
                 if tuple(r.shape[2:]) != tuple(v.shape[2:]):      # FPN top-down path: nearest up-sampling inside the residual add
@@ -507,3 +514,32 @@ def test_trace_interpreted_on_the_cpu_equals_the_oracle(arch, hw):
         assert err < 3e-4, (arch, k, err)     # float64 interpreter vs the fp32 oracle; a lowering error is O(1)
     if arch == 'CpnSlimU22':                                 # padded channel blocks stay exactly zero
         assert any(op.params.pad_out for op in g.ops if op.kind == 'conv')
+
+
+@pytest.mark.parametrize('arch,hw', [('CpnResNeXt50UNet', (64, 64)), ('CpnU22', (64, 96)), ('CpnResNet18FPN', (64, 96))])
+def test_fused_trace_interpreted_on_the_cpu_equals_the_oracle(arch, hw):
+    """The tensor-core engines' graph rewrites with their transformed weights -- bridge block and decoder convolutions as
+    phase convolutions on the low-res map (up2_weights, the split over cat(lateral, up(top))), the phase-decomposed refinement
+    head (bilinear2_weights; compared outside the 4-pixel border the border strips recompute) -- against the oracle."""
+    import cpn_oracle as orc
+    from celldetection_b200.utils.synth import synth_state_dict
+    sd = synth_state_dict(key_spec(arch), seed=6)
+    torch.manual_seed(4)
+    h, w = hw
+    x = torch.rand(1, 3, h, w)
+    g = G.trace(arch, 1, h, w, fuse_up2=True, phase_refinement=True)
+    assert any(op.up2 for op in g.ops if op.kind == 'conv') or arch.endswith('FPN')
+    got = _interpret_trace(g, sd, x)
+    with torch.no_grad():
+        s, l, r, f = orc.cpn_core(x, sd, arch)
+    lf = got['locfou']
+    ref = got['refinement']
+    if g.ref_phase is not None:            # phase-packed records [1, 4 * c2, h/2, w/2] -> [1, c2, h, w]
+        c2 = g.ref_phase['c2']
+        ref = ref.reshape(1, 2, 2, c2, h // 2, w // 2).permute(0, 3, 4, 1, 5, 2).reshape(1, c2, h, w)
+        ref, r = ref[..., 4:-4, 4:-4], r[..., 4:-4, 4:-4]
+    for k, a, v in (('scores', got['scores'], s), ('locations', lf[:, :2], l), ('fourier', lf[:, 2:], f), ('refinement', ref, r)):
+        assert tuple(a.shape) == tuple(v.shape), (k, a.shape, v.shape)
+        err = float((a.float() - v).abs().max()) / max(float(v.abs().max()), 1e-12)
+        assert err < 3e-4, (arch, k, err)
+    assert (g.ref_phase is not None) == arch.endswith('FPN')
