@@ -440,7 +440,8 @@ def _load_image_file(path, dataset='image'):
 def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, border_removal=4, stitching_rule='nms',
                   batch_size=1, devices='auto', precision=None, return_results=True, model_parameters=None,
                   labels=False, flat_labels=False, properties=None, spacing=1., separator='-', overlay=False,
-                  inputs_dataset='image', skip_existing=False, verbose=False, **kwargs):
+                  inputs_dataset='image', masks=None, point_masks=None, masks_dataset='mask',
+                  point_masks_dataset='point_mask', skip_existing=False, verbose=False, **kwargs):
     """Entry point in the spirit of cpn_inference.py:432-869: run tiled inference for each input (numpy arrays or image /
     hdf5 file names).  ``models``: CPN instance(s) or a filename loadable by ``load_model``; ``masks`` / ``point_masks`` /
     ``min_vote`` / ``gamma`` / ``percentile`` / ``reps`` ... are forwarded to ``apply_model``.  ``labels`` / ``flat_labels`` add
@@ -449,10 +450,21 @@ def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, bord
     the reference's (:797-851): ``<name>.h5`` with all result tensors (+ the call's arguments as json attribute of
     ``contours``), ``<name>[_flat].csv`` region-property tables when ``properties`` are given, ``<name>_overlay.tif`` with
     ``overlay=True``; ``<name>`` is ``ndarray_<index>`` for array inputs.  In a distributed run rank 0 writes.
-    Returns ``{index: result dict}``."""
+    ``masks`` / ``point_masks``: one array or file name per input (:595-622, 757-768), handed to ``apply_model`` as that
+    input's ``mask`` / ``point_mask``.  Returns ``{index: result dict}``."""
     from .utils import load_model
     if not isinstance(inputs, (list, tuple)):
         inputs = [inputs]
+    per_input = {}
+    for key, lst, ds in (('mask', masks, masks_dataset), ('point_mask', point_masks, point_masks_dataset)):
+        if lst is None:
+            continue
+        if not isinstance(lst, (list, tuple)):
+            lst = [lst]
+        assert len(lst) == len(inputs), (f'Expecting same number of inputs and {key}s, but found {len(inputs)} inputs and '
+                                         f'{len(lst)} {key}s.')
+        assert key not in kwargs, f'pass either {key}s (one per input) or {key}'
+        per_input[key] = [(_load_image_file(m, ds) if isinstance(m, str) else m) for m in lst]
     args = dict(tile_size=tile_size, stride=stride, border_removal=border_removal, stitching_rule=stitching_rule,
                 batch_size=batch_size, precision=precision, model_parameters=model_parameters, labels=labels,
                 flat_labels=flat_labels, properties=properties, spacing=spacing, separator=separator, overlay=overlay,
@@ -491,8 +503,9 @@ def cpn_inference(inputs, models, outputs=None, tile_size=1024, stride=768, bord
             img = _load_image_file(img, inputs_dataset)
         else:
             dst = os.path.join(outputs, f'ndarray_{i}' + '{ext}') if outputs is not None else None
+        extra = {key: lst[i] for key, lst in per_input.items()}
         results[i] = y = apply_model(img, models, crop_size=tile_size, strides=stride, border_removal=border_removal,
-                                     stitching_rule=stitching_rule, batch_size=batch_size, verbose=verbose, **kwargs)
+                                     stitching_rule=stitching_rule, batch_size=batch_size, verbose=verbose, **extra, **kwargs)
         shape = tuple(img.shape[:2])
         if labels or flat_labels:                  # cpn_inference.py:805-818
             from .data import contours2labels, resolve_label_channels

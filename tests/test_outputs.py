@@ -89,6 +89,28 @@ def test_tiff_writer_is_read_back_by_libtiff(tmp_path, shape, dtype):
             assert b.dtype == a.dtype and np.array_equal(a, b), (big, comp)
 
 
+def test_file_inputs_are_read_as_rgb_arrays(tmp_path):
+    """cpn_inference.py:689-716: image files (OpenCV here) and hdf5 datasets as inputs / masks."""
+    cv2 = pytest.importorskip('cv2')
+    from celldetection_b200.inference import _load_image_file
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, (21, 33, 3)).astype(np.uint8)
+    png = str(tmp_path / 'a.png')
+    cv2.imwrite(png, np.ascontiguousarray(img[..., ::-1]))                     # OpenCV writes BGR
+    assert np.array_equal(_load_image_file(png), img)
+    gray16 = rng.randint(0, 65536, (17, 19)).astype(np.uint16)
+    tif = str(tmp_path / 'g.tif')
+    tiffmin.imwrite(tif, gray16)
+    got = _load_image_file(tif)
+    assert got.dtype == np.uint16 and np.array_equal(got, gray16)
+    h5 = str(tmp_path / 'in.h5')
+    OUT.to_h5(h5, image=img, mask=(img[..., 0] > 128))
+    assert np.array_equal(_load_image_file(h5, 'image'), img)
+    assert np.array_equal(_load_image_file(h5, 'mask'), (img[..., 0] > 128).astype(np.uint8))
+    with pytest.raises(FileNotFoundError):
+        _load_image_file(str(tmp_path / 'missing.png'))
+
+
 def _scipy_table(lab, properties, spacing=(1., 1.)):
     """The same table from scipy.ndimage (an independent implementation of the region statistics)."""
     from scipy import ndimage as ndi
