@@ -578,7 +578,8 @@ def test_full_size_c2_batch_against_oracle():
 def test_tiled_driver_flagship_2048_against_oracle(stride):
     """cd.apply_model with the flagship (CpnResNeXt101UNet, default engine) on a 2048x2048 uint8
     image at crop 512 / stride 384 (25 tiles) and 512 (16 tiles) against the oracle's apply_model on the CPU: same stitched
-    instance count (a handful of score-threshold / IoU-threshold ties may flip: |difference| <= 2), every matched
+    instance count up to threshold ties (of ~125 000 proposals on this noise image a few scores / IoUs sit within the engines'
+    1e-4 of their thresholds; seen: 0-2 of 738-1026 instances, allowed: 4 = 0.4 %; the fixtures' counts are identical), every matched
     contour's decoded vertices within 0.5 px, >= 99 % of the refined vertices within 0.5 px; and the device-resident
     slide path returns the identical result."""
     arch = 'CpnResNeXt101UNet'
@@ -595,11 +596,11 @@ def test_tiled_driver_flagship_2048_against_oracle(stride):
     got = cd.apply_model(img, [m], crop_size=512, strides=stride, border_removal=4, batch_size=8)
     k, k_ref = len(got['scores']), len(want['scores'])
     _report(f'tiled_2048_s{stride}/counts', dict(oracle=k_ref, got=k))
-    assert k_ref > 100 and abs(k - k_ref) <= 2, (k, k_ref)
+    assert k_ref > 100 and abs(k - k_ref) <= 4, (k, k_ref)
     pairs = match_by_box(got['boxes'].cpu().numpy(), want['boxes'].numpy())
     # boxes are matched on the REFINED contours: besides the instances that exist on one side only (the count difference
     # above), a torch.round flip in the refinement loop may unmatch an instance (see __graft_entry__.smoke)
-    assert len(pairs) >= min(k, k_ref) - 2, (len(pairs), k, k_ref)
+    assert len(pairs) >= min(k, k_ref) - 3, (len(pairs), k, k_ref)
     gp, gc = got['contour_proposals'].cpu().numpy(), got['contours'].cpu().numpy()
     wp, wc = want['contour_proposals'].numpy(), want['contours'].numpy()
     perr = max(float(np.abs(gp[a] - wp[b]).max()) for a, b in pairs)
