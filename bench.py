@@ -321,7 +321,8 @@ def heads_roofline(model, x, precision):
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture of the same
     # launch (a profiler cannot run inside the bench); null until a capture of this engine is committed
     traffic, src = None, None
-    for cand in (f'r02_ncu_heads_conv_{precision}.json', 'r01_ncu_heads_conv.json' if precision == 'fp16' else None):
+    for cand in ('r02_final_ncu_c3_heads.json' if precision == 'fp16f8' else None,      # final-state capture of this kernel
+                 f'r02_ncu_heads_conv_{precision}.json', 'r01_ncu_heads_conv.json' if precision == 'fp16' else None):
         path = cand and os.path.join(ROOT, 'profiles', cand)
         if path and os.path.exists(path):
             try:
