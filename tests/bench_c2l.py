@@ -1,6 +1,7 @@
 """contours2labels micro-benchmark: 1e5 contours x 128 samples on a 16384 x 16384 label image (the C4 slide),
 GPU (cpn_contours2labels, device-resident contours, CUDA events) next to the CPU port (oracle/c2l_oracle.py, the
-restated cv2 fill + greedy channel rule) on a bounded sample.  Prints one JSON line."""
+restated cv2 fill + greedy channel rule) on a bounded sample.  Prints one JSON line.  Lives under tests/ because it executes
+the oracle as its CPU baseline (test infrastructure; not collected by pytest).  Usage: python tests/bench_c2l.py"""
 import json
 import os
 import sys

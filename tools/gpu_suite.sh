@@ -11,7 +11,7 @@ timeout -s KILL 600 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail 
 timeout -s KILL 900 python bench.py > $OUT/bench_fp16.log 2>&1; tail -1 $OUT/bench_fp16.log | cut -c1-300
 timeout -s KILL 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.log 2>&1; tail -1 $OUT/bench_reference.log | cut -c1-300
 timeout -s KILL 300 python tools/bench_decode.py > $OUT/bench_decode.log 2>&1; cat $OUT/bench_decode.log
-timeout -s KILL 600 python tools/bench_c2l.py > $OUT/bench_c2l.log 2>&1; tail -1 $OUT/bench_c2l.log | cut -c1-300
+timeout -s KILL 600 python tests/bench_c2l.py > $OUT/bench_c2l.log 2>&1; tail -1 $OUT/bench_c2l.log | cut -c1-300
 timeout -s KILL 600 python tools/profile_plan.py CpnResNeXt101UNet 16 512 fp16 > $OUT/plan_profile.txt 2>&1; head -4 $OUT/plan_profile.txt
 timeout -s KILL 600 python tools/profile_plan.py CpnResNeXt101UNet 16 512 fp16x3 > $OUT/plan_profile_fp16x3.txt 2>&1; head -2 $OUT/plan_profile_fp16x3.txt
 timeout -s KILL 600 python tools/profile_plan.py CpnResNet18FPN 32 512 fp16 > $OUT/plan_profile_c2.txt 2>&1; head -2 $OUT/plan_profile_c2.txt
