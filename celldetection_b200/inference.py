@@ -349,8 +349,9 @@ def apply_model(img, models, trainer=None, mask=None, point_mask=None, crop_size
     resident = isinstance(img, torch.Tensor) and img.is_cuda
     if not isinstance(img, torch.Tensor):
         img = np.asarray(img)
-    wide = img.dtype in (np.uint16, np.int16, torch.uint16, torch.int16) if not resident else img.dtype in (
-        torch.uint16, torch.int16)
+    # 16-bit images: numpy uint16, or a tensor of torch.uint16 / torch.int16 holding the uint16 bit pattern (signed 16-bit
+    # numpy images are rejected below like every other unsupported type)
+    wide = img.dtype in ((torch.uint16, torch.int16) if isinstance(img, torch.Tensor) else (np.uint16,))
     if wide or percentile is not None or gamma != 1. or contrast != 1. or grayscale:
         # the reference conditions the whole image on the CPU before tiling (:328-329); here it goes to the GPU once and
         # continues as a device-resident uint8 slide

@@ -99,7 +99,8 @@ def _apply_lut(lib, t, dtype, lut):
 
 
 def preprocess(img, gamma=1., contrast=1., brightness=0., percentile=None, grayscale=False, device='cuda'):
-    """``Array[h, w(, c)]`` uint8 / uint16 (or a CUDA tensor of that type) -> CUDA uint8 ``Tensor[h, w, 3 | c]``
+    """``Array[h, w(, c)]`` uint8 / uint16 (or a tensor of that type; ``torch.int16`` is read as the uint16 bit pattern, for
+    torch builds whose ``from_numpy`` has no uint16) -> CUDA uint8 ``Tensor[h, w, 3 | c]``
     (cpn_inference.py:196-222; 2-D and single-channel images come back as three equal channels, :214-215)."""
     t = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img))
     if t.dtype == torch.uint8:
