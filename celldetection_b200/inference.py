@@ -24,7 +24,7 @@ from . import _lib as L
 from .ops import cpn as O
 from .ops.boxes import filter_by_box_voting
 
-__all__ = ['get_tiling_slices', 'apply_model', 'cpn_inference']
+__all__ = ['get_tiling_slices', 'apply_model', 'cpn_inference', 'shard_items']
 
 
 def get_tiling_slices(size: Sequence[int], crop_size: Union[int, Sequence[int]], strides: Union[int, Sequence[int]],
@@ -166,8 +166,7 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
             if bnd is not False:
                 bounds[t] = bnd
                 todo.append(t)
-    items = [t * reps + r for t in todo for r in range(reps)]      # TileLoader.__getitem__: slice_idx = item // reps
-    mine = items[rank::world]
+    mine = shard_items(todo, reps, rank, world)
     th, tw = (slices[0][0].stop - slices[0][0].start), (slices[0][1].stop - slices[0][1].start)
     is_u8 = img.dtype in (np.uint8, torch.uint8)
     C = int(img.shape[-1])
@@ -283,6 +282,14 @@ def _apply_single(img, model, mask, point_mask, point_mask_exclusive, crop_size,
         timings.update(tiles_s=t_tiles - t_start, exchange_s=t_gather - t_tiles, stitch_s=t_end - t_gather,
                        tiles_mine=len(mine), tiles_total=len(slices))
     return res
+
+
+def shard_items(tiles, reps, rank, world):
+    """Work items of one rank: item = tile * reps + rep_idx (TileLoader.__getitem__, cpn_inference.py:88-91: slice_idx =
+    item // reps, rep_idx = item % reps) over the tiles that are inferred at all, dealt round-robin.  The item index is also
+    the canonical order key of the exchange, so the union over ranks, sorted, is the single-process sequence."""
+    items = [t * reps + r for t in tiles for r in range(reps)]
+    return items[rank::world]
 
 
 def _checked_transform(transforms, crop, rep_idx):

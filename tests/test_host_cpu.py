@@ -543,3 +543,18 @@ def test_fused_trace_interpreted_on_the_cpu_equals_the_oracle(arch, hw):
         err = float((a.float() - v).abs().max()) / max(float(v.abs().max()), 1e-12)
         assert err < 3e-4, (arch, k, err)
     assert (g.ref_phase is not None) == arch.endswith('FPN')
+
+
+def test_work_items_are_sharded_without_loss_or_overlap():
+    """Tiles x test-time repetitions dealt round-robin to the ranks (inference.shard_items): every item exactly once, the
+    union in key order is the single-process sequence, tile / repetition recovered like TileLoader.__getitem__."""
+    from celldetection_b200.inference import shard_items
+    tiles = [0, 1, 2, 5, 6, 9]                      # tiles 3, 4, 7, 8 were skipped by an empty mask crop
+    for reps in (1, 3):
+        single = shard_items(tiles, reps, 0, 1)
+        assert single == sorted(single) and len(single) == len(tiles) * reps
+        assert [(i // reps, i % reps) for i in single] == [(t, r) for t in tiles for r in range(reps)]
+        for world in (2, 3, 8, 32):
+            parts = [shard_items(tiles, reps, r, world) for r in range(world)]
+            assert sorted(i for p in parts for i in p) == single
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
